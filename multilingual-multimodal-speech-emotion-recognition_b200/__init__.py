@@ -1,0 +1,8 @@
+"""B200-native fusion head (sm_100a CUDA behind a C-ABI) -- drop-in for the reference's src/models head.
+
+Import as ``mmser_b200`` (see mmser_b200.py at the repo root: the on-disk directory name carries
+hyphens, so the alias module gives it an importable name).
+"""
+from . import _lib  # noqa: F401
+
+__all__ = ["_lib"]

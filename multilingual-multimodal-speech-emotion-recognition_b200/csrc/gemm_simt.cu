@@ -1,0 +1,161 @@
+// fp32 tier GEMM: CUDA-core FFMA, 64x64x16 tiles, 4x4 register micro-tiles, optional split-K.
+// This is the "within 1e-4 of the fp32 reference" path (TF32 tensor cores are not accurate enough,
+// see SURVEY.md section 7 "Hard parts"); it shares the epilogue contract of the tcgen05 kernel.
+#include "common.cuh"
+#include <mutex>
+
+namespace ser {
+
+namespace {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+struct SimtEpilogue {
+  float* C; long long ldc;
+  const float* bias;
+  const float* R; long long ldr;
+  const float* G; long long ldg; int gate_mode;
+  int act;
+  int atomic;
+  float alpha;
+};
+
+// A(m,k) = A[m*sam + k*sak],  B(n,k) = B[n*sbn + k*sbk]
+template <bool A_KCONT, bool B_KCONT>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ B,
+                 long long sbn, long long sbk, SimtEpilogue ep, int M, int N, int K, int splits) {
+  __shared__ float As[TK][TM + 4];
+  __shared__ float Bs[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int sp = blockIdx.z;
+  const int ktiles = (K + TK - 1) / TK;
+  const int kt0 = static_cast<int>((static_cast<long long>(sp) * ktiles) / splits);
+  const int kt1 = static_cast<int>((static_cast<long long>(sp + 1) * ktiles) / splits);
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int kt = kt0; kt < kt1; ++kt) {
+    const int k0 = kt * TK;
+    // 64x16 tile = 1024 elements, 4 per thread; thread order follows the contiguous axis
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + r * 256;
+      int mm, kk;
+      if (A_KCONT) { kk = e & 15; mm = e >> 4; } else { mm = e & 63; kk = e >> 6; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < K) ? A[gm * sam + gk * sak] : 0.f;
+      int nn, kb;
+      if (B_KCONT) { kb = e & 15; nn = e >> 4; } else { nn = e & 63; kb = e >> 6; }
+      const int gn = n0 + nn, gkb = k0 + kb;
+      Bs[kb][nn] = (gn < N && gkb < K) ? B[gn * sbn + gkb * sbk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const bool lead = (sp == 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] * ep.alpha;
+      if (ep.bias != nullptr && lead) v += ep.bias[n];
+      v = apply_act(v, ep.act);
+      if (ep.gate_mode != GATE_NONE) v = apply_gate(v, ep.G[m * ep.ldg + n], ep.gate_mode);
+      if (ep.R != nullptr && lead) v += ep.R[m * ep.ldr + n];
+      float* c = ep.C + m * ep.ldc + n;
+      if (ep.atomic) atomicAdd(c, v); else *c = v;
+    }
+  }
+}
+
+}  // namespace
+
+int gemm_simt_f32(const GemmArgs& a, cudaStream_t stream) {
+  SER_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm_simt: empty problem");
+  SER_REQUIRE(a.c_f32 && (a.R == nullptr || a.r_f32) && (a.G == nullptr || a.g_f32),
+              "gemm_simt: fp32 tier expects fp32 C / residual / gate");
+  const int mt = ceil_div(a.M, TM), nt = ceil_div(a.N, TN), ktiles = ceil_div(a.K, TK);
+  const bool linear = (a.act == ACT_NONE && a.gate_mode == GATE_NONE);
+  int splits = a.splits;
+  if (splits <= 0) {
+    splits = 1;
+    const int tiles = mt * nt;
+    const int target = 2 * device_sm_count();
+    if (linear && tiles < target && ktiles >= 16) {
+      splits = target / tiles;
+      if (splits > ktiles / 8) splits = ktiles / 8;
+      if (splits < 1) splits = 1;
+    }
+  }
+  if (!linear) splits = 1;
+  if (splits > ktiles) splits = ktiles;
+
+  SimtEpilogue ep;
+  ep.C = reinterpret_cast<float*>(a.C); ep.ldc = a.ldc;
+  ep.bias = a.bias;
+  ep.R = reinterpret_cast<const float*>(a.R); ep.ldr = a.ldr;
+  ep.G = reinterpret_cast<const float*>(a.G); ep.ldg = a.ldg; ep.gate_mode = a.gate_mode;
+  ep.act = a.act; ep.alpha = a.alpha;
+  ep.atomic = (splits > 1 || a.accumulate) ? 1 : 0;
+  if (ep.atomic && !a.accumulate) {
+    SER_CUDA_CHECK(cudaMemset2DAsync(a.C, a.ldc * sizeof(float), 0, a.N * sizeof(float), a.M, stream));
+  }
+  const float* A = reinterpret_cast<const float*>(a.A);
+  const float* B = reinterpret_cast<const float*>(a.B);
+  const long long sam = a.a_trans ? 1 : a.lda, sak = a.a_trans ? a.lda : 1;
+  const long long sbn = a.b_trans ? 1 : a.ldb, sbk = a.b_trans ? a.ldb : 1;
+  dim3 grid(nt, mt, splits);
+  if (!a.a_trans && !a.b_trans)
+    gemm_simt_kernel<true, true><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, ep, a.M, a.N, a.K, splits);
+  else if (!a.a_trans && a.b_trans)
+    gemm_simt_kernel<true, false><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, ep, a.M, a.N, a.K, splits);
+  else if (a.a_trans && a.b_trans)
+    gemm_simt_kernel<false, false><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, ep, a.M, a.N, a.K, splits);
+  else
+    gemm_simt_kernel<false, true><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, ep, a.M, a.N, a.K, splits);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+int gemm(const GemmArgs& a, cudaStream_t stream) {
+  if (a.dtype == DT_F32) return gemm_simt_f32(a, stream);
+  if (a.dtype == DT_BF16) return gemm_tc_bf16(a, stream);
+  set_last_error(__FILE__, __LINE__, "gemm: unknown dtype");
+  return SER_ERR_ARG;
+}
+
+int device_sm_count() {
+  static int sms = 0;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { sms = 148; return; }
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  });
+  return sms;
+}
+
+}  // namespace ser

@@ -1,0 +1,486 @@
+// bf16 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM), operands staged by TMA.
+//
+// One persistent CTA per SM walks output tiles of 128 x BN (BN = 128 or 256).  Warp roles:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled shared-memory stages)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, M=128, N=BN, K=16)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> bias / activation / gate / residual -> global)
+// The accumulator is double buffered in TMEM (2 x BN fp32 columns) so the epilogue of tile i overlaps
+// the main loop of tile i+1.  Both operands may be K-major or MN-major (nn.Linear weights are
+// consumed in place for forward, dX and dW GEMMs: no transposed copies are ever materialised).
+//
+// Serves: adapters, q/k/v + MHA in/out projections, out_a/out_t, pooling scorer, fusion projections,
+// the 35-block classifier stack (reference: src/models/audio_encoder.py:19-21, cross_attention.py:38-51,
+// pooling.py:9-13, fusion.py:8-16, classifier.py:73-129) in the bf16 tier.
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace ser {
+
+namespace {
+
+constexpr int BM = 128;       // UMMA M (one TMEM lane per output row)
+constexpr int BK = 64;        // 64 bf16 = one 128-byte swizzle atom along the contraction axis
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 196608;
+
+template <int BN> struct TileCfg {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = kSmemBudget / kStageBytes;
+  static constexpr int kTmemCols = 2 * BN;      // double-buffered accumulator
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct TcEpilogue {
+  void* C; long long ldc; int c_f32;
+  const float* bias;
+  const void* R; long long ldr; int r_f32;
+  const void* G; long long ldg; int g_f32; int gate_mode;
+  int act;
+  int atomic;        // accumulate with fp32 atomics (split-K or C +=)
+  float alpha;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
+//   K-major : rows of 128 B; 8-row groups are SBO = 1024 B apart; LBO unused.
+//   MN-major: 64-element (128 B) atoms along MN, 8 contraction rows per 1024 B group (SBO);
+//             successive MN atoms are LBO = BK*128 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;   // descriptor version (Blackwell)
+  d |= 2ull << 61;   // SWIZZLE_128B
+  return d;
+}
+
+template <int BN, int AMAJ, int BMAJ>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4)                               // D format F32
+         | (1u << 7) | (1u << 10)                // A, B format BF16
+         | (static_cast<uint32_t>(AMAJ) << 15)   // A major: 0 K, 1 MN
+         | (static_cast<uint32_t>(BMAJ) << 16)   // B major
+         | (static_cast<uint32_t>(BN >> 3) << 17)
+         | (static_cast<uint32_t>(BM >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN, int AMAJ, int BMAJ>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcEpilogue ep, const int M, const int N, const int K, const int splits) {
+  using Cfg = TileCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                         // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;         // [kStages]
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;     // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (M + BM - 1) / BM;
+  const int n_tiles = N / BN;
+  const int kblocks = (K + BK - 1) / BK;
+  const int total_tiles = m_tiles * n_tiles * splits;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % n_tiles;
+        const int rest = tile / n_tiles;
+        const int mt = rest % m_tiles;
+        const int sp = rest / m_tiles;
+        const int kb0 = static_cast<int>((static_cast<long long>(sp) * kblocks) / splits);
+        const int kb1 = static_cast<int>((static_cast<long long>(sp + 1) * kblocks) / splits);
+        const int m0 = mt * BM, n0 = nt * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          uint8_t* sa = smem_a + stage * Cfg::kABytes;
+          uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+          const int k0 = kb * BK;
+          if (AMAJ == 0) {
+            tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(&tmA, &full_bar[stage], sa + j * (BK * 128), m0 + 64 * j, k0);
+          }
+          if (BMAJ == 0) {
+            tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tmB, &full_bar[stage], sb + j * (BK * 128), n0 + 64 * j, k0);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN, AMAJ, BMAJ>();
+      constexpr uint32_t a_lbo = (AMAJ == 0) ? 0u : BK * 128u;
+      constexpr uint32_t b_lbo = (BMAJ == 0) ? 0u : BK * 128u;
+      constexpr uint32_t a_kstep = (AMAJ == 0) ? UMMA_K * 2u : UMMA_K * 128u;   // bytes per K=16 step
+      constexpr uint32_t b_kstep = (BMAJ == 0) ? UMMA_K * 2u : UMMA_K * 128u;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int rest = tile / n_tiles;
+        const int sp = rest / m_tiles;
+        const int kb0 = static_cast<int>((static_cast<long long>(sp) * kblocks) / splits);
+        const int kb1 = static_cast<int>((static_cast<long long>(sp + 1) * kblocks) / splits);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * Cfg::kABytes);
+          const uint32_t sb = smem_u32(smem_b + stage * Cfg::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+            tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);      // frees the smem stage once these MMAs retire
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[acc]);          // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue (4 warps)
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % n_tiles;
+      const int rest = tile / n_tiles;
+      const int mt = rest % m_tiles;
+      const int sp = rest / m_tiles;
+      const int m = mt * BM + q * 32 + lane;
+      const int n0 = nt * BN;
+      const bool lead_split = (sp == 0);
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(taddr0 + c * 32, raw);
+        if (m < M) {
+          const int n = n0 + c * 32;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * ep.alpha;
+          if (ep.bias != nullptr && lead_split) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+          }
+          if (ep.act != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
+          }
+          if (ep.gate_mode != GATE_NONE) {
+            if (ep.g_f32) {
+              const float* g = reinterpret_cast<const float*>(ep.G) + static_cast<size_t>(m) * ep.ldg + n;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float t[8]; load8(g + j, t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[j + i] = apply_gate(v[j + i], t[i], ep.gate_mode);
+              }
+            } else {
+              const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(ep.G) + static_cast<size_t>(m) * ep.ldg + n;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float t[8]; load8(g + j, t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[j + i] = apply_gate(v[j + i], t[i], ep.gate_mode);
+              }
+            }
+          }
+          if (ep.R != nullptr && lead_split) {
+            if (ep.r_f32) {
+              const float* r = reinterpret_cast<const float*>(ep.R) + static_cast<size_t>(m) * ep.ldr + n;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float t[8]; load8(r + j, t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[j + i] += t[i];
+              }
+            } else {
+              const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(ep.R) + static_cast<size_t>(m) * ep.ldr + n;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float t[8]; load8(r + j, t);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[j + i] += t[i];
+              }
+            }
+          }
+          if (ep.c_f32) {
+            float* cptr = reinterpret_cast<float*>(ep.C) + static_cast<size_t>(m) * ep.ldc + n;
+            if (ep.atomic) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) atomicAdd(cptr + j, v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                float t[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t[i] = v[j + i];
+                store8(cptr + j, t);
+              }
+            }
+          } else {
+            __nv_bfloat16* cptr = reinterpret_cast<__nv_bfloat16*>(ep.C) + static_cast<size_t>(m) * ep.ldc + n;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float t[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) t[i] = v[j + i];
+              store8(cptr + j, t);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+
+// 2-D bf16 matrix stored row-major as [rows, cols] with leading dimension ld (elements);
+// the box is [box_rows, box_cols] with box_cols * 2 <= 128 bytes (one swizzle atom).
+int make_tmap(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows,
+              int box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) { set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable"); return SER_ERR_CUDA; }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d base=%p",
+             (int)r, rows, cols, ld, box_rows, box_cols, base);
+    set_last_error(__FILE__, __LINE__, msg);
+    return SER_ERR_CUDA;
+  }
+  return SER_OK;
+}
+
+template <int BN, int AMAJ, int BMAJ>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& ep, int M, int N, int K, int splits,
+           cudaStream_t stream) {
+  using Cfg = TileCfg<BN>;
+  static bool configured = false;
+  auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ>;
+  if (!configured) {
+    SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int m_tiles = ceil_div(M, BM), n_tiles = N / BN;
+  const long long total = static_cast<long long>(m_tiles) * n_tiles * splits;
+  const int grid = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
+  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, ep, M, N, K, splits);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+template <int BN>
+int dispatch_major(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& ep, int splits,
+                   cudaStream_t stream) {
+  if (!a.a_trans && !a.b_trans) return launch<BN, 0, 0>(tmA, tmB, ep, a.M, a.N, a.K, splits, stream);
+  if (!a.a_trans && a.b_trans) return launch<BN, 0, 1>(tmA, tmB, ep, a.M, a.N, a.K, splits, stream);
+  if (a.a_trans && a.b_trans) return launch<BN, 1, 1>(tmA, tmB, ep, a.M, a.N, a.K, splits, stream);
+  return launch<BN, 1, 0>(tmA, tmB, ep, a.M, a.N, a.K, splits, stream);
+}
+
+}  // namespace
+
+int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
+  SER_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm_tc: empty problem");
+  SER_REQUIRE(a.N % 128 == 0, "gemm_tc: N must be a multiple of 128");
+  SER_REQUIRE(a.lda % 8 == 0 && a.ldb % 8 == 0, "gemm_tc: leading dimensions must be multiples of 8 elements");
+  SER_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0,
+              "gemm_tc: operands must be 16-byte aligned");
+  SER_REQUIRE(a.ldc % 8 == 0, "gemm_tc: ldc must be a multiple of 8");
+  const int BN = (a.N % 256 == 0) ? 256 : 128;
+
+  const int m_tiles = ceil_div(a.M, BM), n_tiles = a.N / BN, kblocks = ceil_div(a.K, BK);
+  int splits = a.splits;
+  const bool linear = (a.act == ACT_NONE && a.gate_mode == GATE_NONE && a.c_f32);
+  if (splits <= 0) {
+    splits = 1;
+    const int tiles = m_tiles * n_tiles;
+    const int sms = device_sm_count();
+    if (linear && tiles * 2 <= sms && kblocks >= 8) {
+      splits = sms / tiles;
+      const int max_by_k = kblocks / 4;        // keep >= 4 k-blocks per split
+      if (splits > max_by_k) splits = max_by_k;
+      if (splits < 1) splits = 1;
+    }
+  }
+  if (!linear) splits = 1;
+  if (splits > kblocks) splits = kblocks;
+
+  CUtensorMap tmA, tmB;
+  if (!a.a_trans) SER_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM, BK));
+  else            SER_TRY(make_tmap(&tmA, a.A, a.K, a.M, a.lda, BK, 64));
+  if (!a.b_trans) SER_TRY(make_tmap(&tmB, a.B, a.N, a.K, a.ldb, BN, BK));
+  else            SER_TRY(make_tmap(&tmB, a.B, a.K, a.N, a.ldb, BK, 64));
+
+  TcEpilogue ep;
+  ep.C = a.C; ep.ldc = a.ldc; ep.c_f32 = a.c_f32;
+  ep.bias = a.bias;
+  ep.R = a.R; ep.ldr = a.ldr; ep.r_f32 = a.r_f32;
+  ep.G = a.G; ep.ldg = a.ldg; ep.g_f32 = a.g_f32; ep.gate_mode = a.gate_mode;
+  ep.act = a.act;
+  ep.alpha = a.alpha;
+  ep.atomic = (splits > 1 || a.accumulate) ? 1 : 0;
+  if (ep.atomic) {
+    SER_REQUIRE(a.c_f32, "gemm_tc: accumulate / split-K needs an fp32 output");
+    if (!a.accumulate) {
+      SER_CUDA_CHECK(cudaMemset2DAsync(a.C, a.ldc * sizeof(float), 0, a.N * sizeof(float), a.M, stream));
+    }
+  }
+  if (BN == 256) return dispatch_major<256>(a, tmA, tmB, ep, splits, stream);
+  return dispatch_major<128>(a, tmA, tmB, ep, splits, stream);
+}
+
+}  // namespace ser
