@@ -1,0 +1,176 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference modules (imported by file path from
+/root/reference, CPU fp32) on the deterministic synthetic weights/inputs of oracle/synth.py.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python oracle/make_golden.py
+The fixtures hold outputs and gradient summaries -- never weights (those are regenerated from
+synth.py) -- so they stay small.  tests/test_oracle_golden.py pins oracle/fusion_head_oracle.py to them.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import re
+import sys
+
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import synth  # noqa: E402
+
+REF = os.environ.get("SER_REFERENCE", "/root/reference")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def load_ref(name: str):
+    """Load src/models/<name>.py by path; the package __init__ needs librosa."""
+    path = os.path.join(REF, "src", "models", f"{name}.py")
+    spec = importlib.util.spec_from_file_location(f"ref_{name}", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def build_reference_head(C: int, num_layers: int, weights):
+    ca = load_ref("cross_attention"); po = load_ref("pooling"); fu = load_ref("fusion")
+    cl = load_ref("classifier"); pr = load_ref("prototypes"); lo = load_ref("losses")
+    m = {
+        # adapters exactly as src/models/audio_encoder.py:19-21 / text_encoder.py:17-19
+        "adapter_a": nn.Sequential(nn.Linear(768, 256), nn.ReLU(), nn.Linear(256, 768)),
+        "adapter_t": nn.Sequential(nn.Linear(768, 256), nn.ReLU(), nn.Linear(256, 768)),
+        "cross": ca.CrossModalAttention(768, 768, shared_dim=256, num_heads=8),
+        "pool_a": po.AttentiveStatsPooling(768),
+        "pool_t": po.AttentiveStatsPooling(768),
+        "fusion": fu.FusionLayer(1536, 1536, 512),
+        "classifier": cl.AdvancedOpenMaxClassifier(input_dim=512, num_labels=C, num_layers=num_layers, base_dim=512,
+                                                   dropout=0.15),
+        "prototypes": pr.PrototypeMemory(C, 512),
+    }
+    for k, mod in m.items():
+        missing = mod.load_state_dict(weights[k], strict=True)
+        assert not missing.missing_keys and not missing.unexpected_keys
+        mod.eval()      # dropout off; nothing else differs between train/eval on this path
+    losses = {"ce": lo.LabelSmoothingCrossEntropy(0.1),
+              "focal": lo.ClassBalancedFocalLoss(beta=0.9999, gamma=2.0, num_classes=C)}
+    return m, losses
+
+
+def summarize(t: torch.Tensor, name: str):
+    flat = t.detach().reshape(-1).double()
+    g = torch.Generator().manual_seed(abs(hash(name)) % (2 ** 31))
+    n = flat.numel()
+    # fixed pseudo-random probe positions (stored, so the hash seed does not matter to readers)
+    idx = torch.randint(0, n, (min(32, n),), generator=g)
+    out = {"shape": tuple(t.shape), "norm": flat.norm().item(), "sum": flat.sum().item(),
+           "idx": idx, "vals": flat[idx].float()}
+    m = re.search(r"(residual_layers|layer_norms)\.(\d+)\.", name)
+    keep_full = n <= 4096 and (m is None or int(m.group(2)) in (0, 17, 34))
+    if keep_full:
+        out["full"] = t.detach().clone().float()
+    return out
+
+
+def run_train_case(name, B, Ta, Tt, C, seed, with_masks=True, num_layers=35):
+    weights = synth.head_weights(C, num_layers, seed=0)
+    m, L = build_reference_head(C, num_layers, weights)
+    a_hid, t_hid, a_mask, t_mask, labels = synth.make_inputs(B, Ta, Tt, C, seed, with_masks)
+    # src/train.py:145-168 (adapters applied as in the encoders' forward)
+    a_seq = a_hid + m["adapter_a"](a_hid)
+    t_seq = t_hid + m["adapter_t"](t_hid)
+    a_enh, t_enh = m["cross"](a_seq, t_seq, a_mask, t_mask)
+    a_vec = m["pool_a"](a_enh, a_mask)
+    t_vec = m["pool_t"](t_enh, t_mask)
+    fused = m["fusion"](a_vec, t_vec)
+    logits, unc, anchor_loss = m["classifier"](fused, use_openmax=False, return_uncertainty=True)
+    ce = L["ce"](logits, labels)
+    focal = L["focal"](logits, labels)
+    loss = ce + 0.3 * focal
+    loss = loss + 0.1 * anchor_loss
+    unc_loss = torch.mean(unc * (labels == logits.argmax(dim=1)).float())
+    loss = loss + 0.05 * unc_loss
+    proto = m["prototypes"].prototype_loss(fused, labels)
+    loss = loss + 0.01 * proto
+    loss.backward()
+
+    grads = {}
+    for k, mod in m.items():
+        for pn, p in mod.named_parameters():
+            grads[f"{k}/{pn}"] = None if p.grad is None else summarize(p.grad, f"{k}/{pn}")
+    gold = {
+        "config": dict(B=B, Ta=Ta, Tt=Tt, C=C, seed=seed, with_masks=with_masks, num_layers=num_layers),
+        "logits": logits.detach(), "unc": unc.detach(), "fused": fused.detach(),
+        "a_vec": a_vec.detach(), "t_vec": t_vec.detach(),
+        "a_enh_head": a_enh[:, :4].detach().clone(), "t_enh_head": t_enh[:, :4].detach().clone(),
+        "a_enh_norm": a_enh.detach().double().norm().item(), "t_enh_norm": t_enh.detach().double().norm().item(),
+        "ce": ce.item(), "focal": focal.item(), "anchor": anchor_loss.item(), "unc_loss": unc_loss.item(),
+        "proto": proto.item(), "loss": loss.item(),
+        "grads": grads,
+        "torch": torch.__version__,
+    }
+    torch.save(gold, os.path.join(OUT, f"{name}.pt"))
+    print(f"{name}: loss={loss.item():.6f} ce={ce.item():.6f} focal={focal.item():.6f} proto={proto.item():.6f} "
+          f"unc={unc_loss.item():.6f} anchor={anchor_loss.item()}")
+
+
+def run_eval_case(name, B, C, seed, views=5):
+    """cfg5 semantics at small B: classifier eval path with fitted OpenMax + TTA mean + temperature + energy."""
+    weights = synth.head_weights(C, 35, seed=0)
+    m, _ = build_reference_head(C, 35, weights)
+    clf = m["classifier"]
+    g = torch.Generator().manual_seed(seed)
+    val_fused = torch.randn(64, 512, generator=g)
+    val_labels = torch.randint(0, C, (64,), generator=g)
+    with torch.no_grad():
+        # hand-unrolled feature extraction, src/train.py:221-236
+        f = val_fused
+        for layer in clf.deep_classifier.input_projection:
+            f = layer(f)
+        for blk, ln in zip(clf.deep_classifier.residual_layers, clf.deep_classifier.layer_norms):
+            f = blk(ln(f))
+        for i in range(4):
+            f = clf.deep_classifier.output_projection[i](f)
+        clf.fit_weibull(f, val_labels)
+        fused_views = torch.randn(views, B, 512, generator=g)
+        labels = torch.randint(0, C, (B,), generator=g)
+        logits_views = torch.stack([clf(fused_views[v]) for v in range(views)])       # OpenMax on (eval.py:198)
+        logits_plain = torch.stack([clf(fused_views[v], use_openmax=False) for v in range(views)])
+        mean_logits = logits_views.mean(0)                                              # eval.py:186-190
+        ev = load_eval_helpers()
+        T = ev["find_optimal_temperature"](logits_plain[0], labels, "cpu")
+        scaled = mean_logits / T
+        probs = torch.softmax(scaled, dim=-1)
+        preds = probs.argmax(dim=-1)
+        energy = -torch.logsumexp(scaled, dim=-1)                                       # utils.py:12-14
+    gold = {
+        "config": dict(B=B, C=C, seed=seed, views=views),
+        "weibull": {k: getattr(clf, k).clone() for k in synth.CLASSIFIER_BUFFERS},
+        "val_features": f, "logits_views": logits_views, "logits_plain": logits_plain,
+        "mean_logits": mean_logits, "temperature": float(T), "probs": probs, "preds": preds, "energy": energy,
+    }
+    torch.save(gold, os.path.join(OUT, f"{name}.pt"))
+    print(f"{name}: T={T:.4f} preds={preds[:8].tolist()}")
+
+
+def load_eval_helpers():
+    """temperature_scaling + find_optimal_temperature from src/eval.py:43-67, extracted without importing the
+    script's heavy dependencies."""
+    src = open(os.path.join(REF, "src", "eval.py")).read()
+    start = src.index("def temperature_scaling")
+    end = src.index("\ndef main", start + 10)
+    ns = {"torch": torch}
+    exec(compile(src[start:end], "ref_eval_calibrate", "exec"), ns)
+    return ns
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    # small-B versions of BASELINE.json configs 1-4 (same T / C structure, B cut so files stay small)
+    run_train_case("train_cfg1_small", B=4, Ta=50, Tt=16, C=4, seed=1235)
+    run_train_case("train_cfg2_shape", B=3, Ta=250, Tt=64, C=4, seed=1236)
+    run_train_case("train_cfg3_c6", B=6, Ta=40, Tt=24, C=6, seed=1237)
+    run_train_case("train_nomask", B=4, Ta=33, Tt=9, C=4, seed=1238, with_masks=False)
+    run_train_case("train_cfg4_long", B=2, Ta=300, Tt=96, C=4, seed=1239)
+    run_eval_case("eval_cfg5_small", B=32, C=6, seed=1240)

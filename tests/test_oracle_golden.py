@@ -1,0 +1,123 @@
+"""Pins oracle/fusion_head_oracle.py to the reference: the golden fixtures were produced by the reference's
+own modules (oracle/make_golden.py, run where /root/reference exists).  CPU only."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import fusion_head_oracle as O
+from oracle import synth
+
+TOL = 2e-5   # fp32 CPU vs fp32 CPU, different op order (explicit MHA vs fused kernels)
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-12)
+
+
+def _train_cases(golden_dir=None):
+    root = os.path.join(os.path.dirname(__file__), "golden")
+    return sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(root, "train_*.pt")))
+
+
+@pytest.mark.parametrize("case", _train_cases())
+def test_oracle_matches_reference_train(case, golden_dir):
+    gold = torch.load(os.path.join(golden_dir, f"{case}.pt"), weights_only=False)
+    cfg = gold["config"]
+    weights = synth.head_weights(cfg["C"], cfg["num_layers"], seed=0)
+    for grp in weights.values():
+        for k, v in grp.items():
+            if v.is_floating_point() and k not in synth.CLASSIFIER_BUFFERS:
+                v.requires_grad_(True)
+    a, t, am, tm, labels = synth.make_inputs(cfg["B"], cfg["Ta"], cfg["Tt"], cfg["C"], cfg["seed"], cfg["with_masks"])
+    out = O.head_forward(a, t, am, tm, labels, weights, cfg["C"], cfg["num_layers"])
+    out["loss"].backward()
+
+    for k in ("logits", "unc", "fused", "a_vec", "t_vec"):
+        assert rel(out[k], gold[k]) < TOL, k
+    assert rel(out["a_enh"][:, :4], gold["a_enh_head"]) < TOL
+    assert rel(out["t_enh"][:, :4], gold["t_enh_head"]) < TOL
+    assert abs(out["a_enh"].double().norm().item() - gold["a_enh_norm"]) / gold["a_enh_norm"] < TOL
+    for k, gk in (("ce", "ce"), ("focal", "focal"), ("unc_loss", "unc_loss"), ("proto", "proto"), ("loss", "loss")):
+        assert abs(out[k].item() - gold[gk]) <= TOL * max(1.0, abs(gold[gk])), k
+    assert out["anchor"].item() == 0.0 and gold["anchor"] == 0.0
+    # bit-exact argmax
+    assert torch.equal(out["logits"].argmax(1), gold["logits"].argmax(1))
+
+    checked = 0
+    for key, summ in gold["grads"].items():
+        grp, name = key.split("/", 1)
+        g = weights[grp][name].grad
+        if summ is None:                      # anchor temperature: reference leaves .grad = None
+            assert g is None or float(g.abs().max()) == 0.0, key
+            continue
+        assert g is not None, key
+        scale = summ["norm"] / max(1.0, g.numel() ** 0.5) + 1e-12
+        if summ["norm"] == 0.0:               # anchor parameters: exactly-zero gradients
+            assert float(g.abs().max()) == 0.0, key
+            continue
+        if summ["norm"] < 1e-6:               # mathematically zero (e.g. MHA key bias): rounding noise only
+            assert g.double().norm().item() < 1e-5, key
+            continue
+        assert abs(g.double().norm().item() - summ["norm"]) <= 5 * TOL * summ["norm"], key
+        probe = g.reshape(-1)[summ["idx"]]
+        assert (probe.double() - summ["vals"].double()).abs().max().item() <= 50 * TOL * max(scale, summ["vals"].abs().max().item()), key
+        if "full" in summ:
+            assert rel(g, summ["full"]) < 10 * TOL, key
+        checked += 1
+    assert checked > 300
+
+
+def test_oracle_matches_reference_eval(golden_dir):
+    gold = torch.load(os.path.join(golden_dir, "eval_cfg5_small.pt"), weights_only=False)
+    cfg = gold["config"]
+    C = cfg["C"]
+    w = synth.classifier_weights(C, 35, seed=0)
+    g = torch.Generator().manual_seed(cfg["seed"])
+    val_fused = torch.randn(64, 512, generator=g)
+    val_labels = torch.randint(0, C, (64,), generator=g)
+    with torch.no_grad():
+        f = O.classifier_features(val_fused, w)
+        assert rel(f, gold["val_features"]) < TOL
+        w.update(O.fit_weibull(f, val_labels, C, w))
+        for k in synth.CLASSIFIER_BUFFERS:
+            assert rel(w[k], gold["weibull"][k]) < 1e-4, k
+        fused_views = torch.randn(cfg["views"], cfg["B"], 512, generator=g)
+        labels = torch.randint(0, C, (cfg["B"],), generator=g)
+        lv = torch.stack([O.classifier(fused_views[v], w, use_openmax=True, training=False) for v in range(cfg["views"])])
+        lp = torch.stack([O.classifier(fused_views[v], w, use_openmax=False) for v in range(cfg["views"])])
+        assert rel(lv, gold["logits_views"]) < 1e-4
+        assert rel(lp, gold["logits_plain"]) < TOL
+        mean_logits = O.tta_mean(lv)
+        T = O.find_optimal_temperature(lp[0], labels)
+        assert abs(T - gold["temperature"]) < 1e-4 * gold["temperature"]
+        scaled = mean_logits / T
+        probs = torch.softmax(scaled, -1)
+        assert rel(probs, gold["probs"]) < 1e-4
+        assert torch.equal(probs.argmax(-1), gold["preds"])
+        assert rel(O.energy_score(scaled), gold["energy"]) < 1e-4
+
+
+def test_quirks():
+    """SURVEY.md 8(a) quirks the CUDA path must reproduce."""
+    torch.manual_seed(0)
+    C = 4
+    w = synth.classifier_weights(C, 2, seed=0)
+    f = torch.randn(8, 256)
+    _, al = O.anchor_clustering(f, w)
+    assert al.item() == 0.0
+    # uncertainty term = mean(unc) * mean(correct)  ([B,1]*[B] broadcast)
+    unc = torch.rand(8, 1)
+    corr = (torch.rand(8) > 0.5).float()
+    assert abs((unc * corr).mean().item() - unc.mean().item() * corr.mean().item()) < 1e-6
+    # fully padded key row -> NaN
+    cw = synth.cross_weights(0)
+    a = torch.randn(2, 5, 768); t = torch.randn(2, 3, 768)
+    tm = torch.tensor([[1., 1., 0.], [0., 0., 0.]])
+    ae, te = O.cross_attention(a, t, None, tm, cw)
+    assert torch.isfinite(ae[0]).all() and torch.isnan(ae[1]).all()
+    pw = synth.pool_weights("pool_a", 0)
+    pooled = O.attentive_stats_pooling(torch.randn(2, 3, 768), tm, pw)
+    assert torch.isfinite(pooled[0]).all() and torch.isnan(pooled[1]).all()
