@@ -41,6 +41,9 @@ extern "C" {
 int ser_version(void);
 const char* ser_last_error(void);
 int ser_sm_count(void);
+/* sizeof() of descriptor `id` as compiled (0 gemm, 1 adapter, 2 xattn, 3 asp, 4 fusion, 5 clf, 6 loss):
+ * lets a foreign-language binding verify its struct layout at load time                           */
+int ser_desc_size(int id);
 
 /* ---- generic fused GEMM (building block; also exported for tests and micro-benchmarks) -------
  * C[M,N] = epilogue(alpha * op(A) op(B)^T), see csrc/common.cuh GemmArgs.  Replaces every nn.Linear
@@ -60,6 +63,188 @@ typedef struct ser_gemm_desc {
   int splits;                                  /* split-K factor, 0 = auto                       */
 } ser_gemm_desc;
 int ser_gemm(const ser_gemm_desc* d, void* stream);
+
+
+/* ---- utilities ------------------------------------------------------------------------------ */
+/* fp32 -> bf16 parameter copy (the Python modules keep fp32 masters; bf16 tier consumes copies)    */
+int ser_cast(const void* src, int src_f32, void* dst, int dst_f32, long long n, void* stream);
+
+/* row/column primitives behind the individually callable children of the classifier
+ * (nn.LayerNorm / bias-gradient column sums; src/train.py:221-236 calls those children one by one)  */
+int ser_layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, const float* gamma, const float* beta,
+                      float* stats, int M, int N, int relu, void* stream);
+int ser_layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const float* stats, const float* gamma,
+                      const float* beta, void* dx, int dx_f32, float* dgamma, float* dbeta, int M, int N, int relu,
+                      void* stream);            /* dgamma / dbeta are overwritten */
+int ser_colsum(const void* X, int x_f32, long long ld, int M, int N, float* out, void* stream);
+
+/* ---- a1: bottleneck adapter  (src/models/audio_encoder.py:19-21,112; text_encoder.py:17-19,57) --
+ * y = x + W2 relu(W1 x + b1) + b2.   "act" = tensor of the tier's dtype; weights w* are act-dtype
+ * copies of the nn.Linear weights ([out,in] row-major); biases and all gradients are fp32.         */
+typedef struct ser_adapter_desc {
+  int dtype; int M; int D; int S;          /* tokens, 768, 256                                    */
+  int add_residual;                        /* 1: y = x + branch(x) (fused); 0: y = branch(x) only  */
+  const void* x;                           /* [M,D] act                                           */
+  const void* w1; const float* b1;         /* [S,D], [S]                                          */
+  const void* w2; const float* b2;         /* [D,S], [D]                                          */
+  void* h;                                 /* [M,S] act, saved for backward                       */
+  void* y;                                 /* [M,D] act, output                                   */
+  /* backward */
+  const void* dy;                          /* [M,D] act                                           */
+  void* dh;                                /* [M,S] act scratch                                   */
+  void* dx;                                /* [M,D] act or NULL (frozen-encoder input)            */
+  float* dw1; float* db1; float* dw2; float* db2;   /* overwritten                                */
+} ser_adapter_desc;
+int ser_adapter_fwd(const ser_adapter_desc* d, void* stream);
+int ser_adapter_bwd(const ser_adapter_desc* d, void* stream);
+
+/* ---- a2: CrossModalAttention.forward  (src/models/cross_attention.py:32-53) ---------------------
+ * Both directions.  Weight packing (done once per optimiser step by the Python module):
+ *   wqkv_a = rows [q_a ; k_a ; v_a] ([3S,D]),  wqkv_t = [q_t ; k_t ; v_t];
+ *   win_a / win_t = attn_a / attn_t .in_proj_weight ([3S,S], rows q|k|v); wo_* = out_proj; wout_* = out_a/out_t.
+ * Saved activations: qkv_* [M,3S]; p_a = [Qa' | Ka' | Va'] where Qa' feeds attn_a and Ka',Va' feed attn_t
+ * (p_t likewise); ctx_* [M,S]; lse_* [B,H,T] fp32; o_* [M,S]; z_* [M,D] pre-LayerNorm; stats_* [M,2].
+ * Masks are float, 0 = padded (cross_attention.py:34-35), or NULL.                                 */
+typedef struct ser_xattn_desc {
+  int dtype; int B, Ta, Tt; int D, S, H;
+  const void* a; const void* t;
+  const float* a_mask; const float* t_mask;
+  const void* wqkv_a; const float* bqkv_a; const void* wqkv_t; const float* bqkv_t;
+  const void* win_a; const float* bin_a; const void* win_t; const float* bin_t;
+  const void* wo_a; const float* bo_a; const void* wo_t; const float* bo_t;
+  const void* wout_a; const float* bout_a; const void* wout_t; const float* bout_t;
+  const float* ln_a_g; const float* ln_a_b; const float* ln_t_g; const float* ln_t_b;
+  void* qkv_a; void* qkv_t; void* p_a; void* p_t; void* ctx_a; void* ctx_t;
+  float* lse_a; float* lse_t; void* o_a; void* o_t; void* z_a; void* z_t; float* stats_a; float* stats_t;
+  void* enh_a; void* enh_t;                /* outputs [B*Ta,D], [B*Tt,D]                          */
+  /* backward */
+  const void* d_enh_a; const void* d_enh_t;
+  void* da; void* dt;                      /* [M,D] act gradients w.r.t. the inputs               */
+  float* dwqkv_a; float* dbqkv_a; float* dwqkv_t; float* dbqkv_t;
+  float* dwin_a; float* dbin_a; float* dwin_t; float* dbin_t;
+  float* dwo_a; float* dbo_a; float* dwo_t; float* dbo_t;
+  float* dwout_a; float* dbout_a; float* dwout_t; float* dbout_t;
+  float* dln_a_g; float* dln_a_b; float* dln_t_g; float* dln_t_b;
+  void* ws; size_t ws_bytes;               /* backward scratch, ser_xattn_bwd_ws_bytes()          */
+} ser_xattn_desc;
+size_t ser_xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H);
+int ser_xattn_fwd(const ser_xattn_desc* d, void* stream);
+int ser_xattn_bwd(const ser_xattn_desc* d, void* stream);
+
+/* ---- a3: AttentiveStatsPooling.forward  (src/models/pooling.py:15-28) -------------------------- */
+typedef struct ser_asp_desc {
+  int dtype; int B, T, D, Hd;              /* D = 768, Hd = 128                                   */
+  const void* x; const float* mask;        /* [B*T,D] act; [B,T] float (0 = pad) or NULL          */
+  const void* w1; const float* b1;         /* attention.0: [Hd,D], [Hd]                           */
+  const float* w2; const float* b2;        /* attention.2: [Hd], [1] fp32                         */
+  void* u;                                 /* [B*T,Hd] act: tanh(W1 x + b1), saved                */
+  float* e; float* alpha;                  /* [B,T] scratch scores; [B,T] softmax weights, saved  */
+  void* out; int out_f32;                  /* [B,2D] mean | std                                   */
+  /* backward */
+  const void* dout; int dout_f32;          /* [B,2D]                                              */
+  void* dx;                                /* [B*T,D] act                                         */
+  void* dpre; float* dalpha;               /* [B*T,Hd] act scratch; [B,T] fp32 scratch            */
+  float* dw1; float* db1; float* dw2; float* db2;   /* overwritten                                */
+} ser_asp_desc;
+int ser_asp_fwd(const ser_asp_desc* d, void* stream);
+int ser_asp_bwd(const ser_asp_desc* d, void* stream);
+
+/* ---- a4: FusionLayer.forward  (src/models/fusion.py:18-25) ------------------------------------- */
+typedef struct ser_fusion_desc {
+  int dtype; int B, Din, P, G;             /* Din = 1536, P = 512, G = 256                        */
+  const void* av; const void* tv;          /* [B,Din] act                                         */
+  const void* w1a; const float* b1a; const void* w2a; const float* b2a;   /* proj_a.0, proj_a.3   */
+  const void* w1t; const float* b1t; const void* w2t; const float* b2t;
+  const void* wg1a; const float* bg1a; const float* wg2a; const float* bg2a;  /* gate_a.0 (act), gate_a.2 (fp32 [G],[1]) */
+  const void* wg1t; const float* bg1t; const float* wg2t; const float* bg2t;
+  void* ha; void* ht; void* pa; void* pt; void* ga; void* gt;   /* saved: [B,P],[B,P],[B,G] act   */
+  float* gates;                            /* [B,2] sigmoid gate values, saved                    */
+  void* fused;                             /* [B,P] act, output                                   */
+  /* backward */
+  const void* dfused;                      /* [B,P] act                                           */
+  void* dav; void* dtv;                    /* [B,Din] act                                         */
+  float* dw1a; float* db1a; float* dw2a; float* db2a; float* dw1t; float* db1t; float* dw2t; float* db2t;
+  float* dwg1a; float* dbg1a; float* dwg2a; float* dbg2a; float* dwg1t; float* dbg1t; float* dwg2t; float* dbg2t;
+  void* ws; size_t ws_bytes;               /* ser_fusion_bwd_ws_bytes()                           */
+} ser_fusion_desc;
+size_t ser_fusion_bwd_ws_bytes(int dtype, int B, int Din, int P, int G);
+int ser_fusion_fwd(const ser_fusion_desc* d, void* stream);
+int ser_fusion_bwd(const ser_fusion_desc* d, void* stream);
+
+/* ---- a5/a6: AdvancedOpenMaxClassifier.forward, training path (src/models/classifier.py:200-238) --
+ * 35 x { y = LN_outer(h); h' = y + W2 relu(W1 LN_inner(y) + b1) + b2 }.  Per-block parameters are passed
+ * as HOST arrays (length L) of device pointers.  The residual stream is kept in fp32 in both tiers.
+ * The anchor-clustering branch is not evaluated: its similarity output is discarded by the caller and its
+ * loss is identically zero with exactly-zero gradients (classifier.py:64-68).     */
+typedef struct ser_clf_desc {
+  int dtype; int B, P, F, C, L, U;         /* 512, 256, classes, 35, 64                           */
+  const void* x;                           /* [B,P] act                                           */
+  const void* w_in; const float* b_in; const float* ln_in_g; const float* ln_in_b;
+  const void* const* w1; const float* const* b1; const void* const* w2; const float* const* b2;
+  const float* const* lno_g; const float* const* lno_b; const float* const* lni_g; const float* const* lni_b;
+  const void* w_out; const float* b_out; const float* ln_out_g; const float* ln_out_b;
+  const float* w_c; const float* b_c;      /* output_projection.4: [C,F] fp32                     */
+  const float* w_u1; const float* b_u1; const float* w_u2; const float* b_u2;   /* uncertainty head */
+  /* saved activations */
+  float* p0; float* stats0;                /* [B,P], [B,2]                                        */
+  float* h;                                /* [(L+1),B,P] fp32 stream                             */
+  float* y;                                /* [L,B,P] fp32 outer-LN outputs                       */
+  void* n; void* r;                        /* [L,B,P] act                                         */
+  float* stats_o; float* stats_i;          /* [L,B,2]                                             */
+  void* h_last;                            /* [B,P] act copy of h[L]                              */
+  float* q; float* stats_q;                /* [B,F], [B,2]                                        */
+  float* f;                                /* [B,F] penultimate features (fp32), output           */
+  float* u1;                               /* [B,U]                                               */
+  float* logits; float* unc;               /* [B,C], [B,1] outputs; unc may be NULL               */
+  /* backward */
+  const float* dlogits; const float* dunc; /* [B,C]; [B,1] or NULL                                */
+  void* dx;                                /* [B,P] act                                           */
+  float* dw_in; float* db_in; float* dln_in_g; float* dln_in_b;
+  float* const* dw1; float* const* db1; float* const* dw2; float* const* db2;
+  float* const* dlno_g; float* const* dlno_b; float* const* dlni_g; float* const* dlni_b;
+  float* dw_out; float* db_out; float* dln_out_g; float* dln_out_b;
+  float* dw_c; float* db_c; float* dw_u1; float* db_u1; float* dw_u2; float* db_u2;
+  void* ws; size_t ws_bytes;               /* ser_clf_bwd_ws_bytes()                              */
+} ser_clf_desc;
+size_t ser_clf_bwd_ws_bytes(int dtype, int B, int P, int F, int C, int U);
+int ser_clf_fwd(const ser_clf_desc* d, void* stream);
+int ser_clf_bwd(const ser_clf_desc* d, void* stream);
+
+/* ---- a8-a11: losses  (src/models/losses.py:12-30,41-64; prototypes.py:13-53; train.py:151-168) ----
+ * ser_loss_fwd writes raw batch sums (ce, focal, sum unc, sum correct, pos, neg); a data-parallel caller
+ * all-reduces them (and passes global class counts / B_global) before ser_loss_finalize / ser_loss_bwd,
+ * which evaluate the reference's non-finite guards on the global values.
+ * loss = w_ce*CE_smooth + w_focal*CBFocal + w_unc*mean(unc)*mean(correct) + w_proto*proto            */
+typedef struct ser_loss_desc {
+  int B, C, D; long long B_global;
+  const float* logits; const float* unc;   /* [B,C] ; [B] or NULL                                 */
+  const void* emb; int emb_f32;            /* [B,D] or NULL                                       */
+  const float* protos;                     /* [C,D]                                               */
+  const long long* labels;                 /* [B] int64                                           */
+  const float* counts;                     /* [C] global class counts (float) or NULL             */
+  float smoothing, beta, gamma, margin; int focal_use_weights;
+  float* class_w;                          /* [C] scratch                                         */
+  float* sums;                             /* [8]                                                 */
+  float w_ce, w_focal, w_unc, w_proto;
+  float* terms;                            /* [6]: ce, focal, unc_loss, proto, total, accuracy    */
+  /* backward */
+  const float* gscale;                     /* device scalar multiplied into every gradient, or NULL */
+  float* dlogits; float* dunc; void* demb; int demb_f32; float* dprotos;   /* dprotos accumulates  */
+} ser_loss_desc;
+int ser_loss_fwd(const ser_loss_desc* d, void* stream);
+int ser_loss_finalize(const ser_loss_desc* d, void* stream);
+int ser_loss_bwd(const ser_loss_desc* d, void* stream);
+
+/* ---- a7 / a12: inference post-processing --------------------------------------------------------
+ * ser_openmax_fwd : classifier.py:240-275 (Weibull CDF of distances to activation vectors, re-scale logits)
+ * ser_eval_post   : eval.py:186-190 (mean over V views), :201-206 (/T, softmax, argmax), utils.py:12-14 (energy)
+ * ser_temperature_sweep : eval.py:48-67, err[t] = mean |max prob - correct| for each temperature    */
+int ser_openmax_fwd(const float* feats, const float* logits, const float* act_vecs, const float* w_alpha,
+                    const float* w_beta, const float* w_tau, float* out, int B, int C, int F, void* stream);
+int ser_eval_post(const float* logits_views, int V, int B, int C, float temperature, float* mean_logits,
+                  float* probs, long long* preds, float* energy, void* stream);
+int ser_temperature_sweep(const float* logits, const long long* labels, int B, int C, const float* temps, int nT,
+                          float* err, void* stream);
 
 #ifdef __cplusplus
 }

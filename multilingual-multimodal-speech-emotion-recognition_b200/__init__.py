@@ -4,5 +4,8 @@ Import as ``mmser_b200`` (see mmser_b200.py at the repo root: the on-disk direct
 hyphens, so the alias module gives it an importable name).
 """
 from . import _lib  # noqa: F401
+from . import functional  # noqa: F401
+from . import models  # noqa: F401
+from .head import FusionHead  # noqa: F401
 
-__all__ = ["_lib"]
+__all__ = ["_lib", "functional", "models", "FusionHead"]

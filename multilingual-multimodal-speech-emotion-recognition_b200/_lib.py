@@ -2,16 +2,22 @@
 
 The library is the only compute path: there is no PyTorch / CPU fallback.  If the shared object is
 missing or fails to load, every op raises -- loudly -- instead of silently running something else.
+
+The ctypes structures are generated from include/ser_head.h at import time, so the Python layout can
+never drift from the C declaration.
 """
 from __future__ import annotations
 
 import ctypes as C
 import os
+import re
+from typing import Dict
 
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libser_head.so")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "ser_head.h")
 
 SER_F32, SER_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3
@@ -22,18 +28,55 @@ class SerError(RuntimeError):
     pass
 
 
-class GemmDesc(C.Structure):
-    _fields_ = [
-        ("dtype", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
-        ("A", C.c_void_p), ("lda", C.c_longlong), ("a_trans", C.c_int),
-        ("B", C.c_void_p), ("ldb", C.c_longlong), ("b_trans", C.c_int),
-        ("C", C.c_void_p), ("ldc", C.c_longlong), ("c_f32", C.c_int),
-        ("bias", C.c_void_p),
-        ("R", C.c_void_p), ("ldr", C.c_longlong), ("r_f32", C.c_int),
-        ("G", C.c_void_p), ("ldg", C.c_longlong), ("g_f32", C.c_int), ("gate_mode", C.c_int),
-        ("act", C.c_int), ("accumulate", C.c_int), ("alpha", C.c_float), ("splits", C.c_int),
-    ]
+# --------------------------------------------------------------------------------------------------
+# header -> ctypes
+# --------------------------------------------------------------------------------------------------
+_SCALARS = {"int": C.c_int, "float": C.c_float, "long long": C.c_longlong, "size_t": C.c_size_t}
 
+
+def _parse_structs(text: str) -> Dict[str, type]:
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"typedef\s+struct\s+(\w+)\s*\{(.*?)\}\s*(\w+)\s*;", text, flags=re.S):
+        name, body = m.group(3), m.group(2)
+        fields = []
+        for decl in body.split(";"):
+            decl = " ".join(decl.split())
+            if not decl:
+                continue
+            if "*" in decl:                       # every pointer flavour is a void*
+                for part in decl.split(","):
+                    fname = re.findall(r"(\w+)\s*$", part.strip())[0]
+                    fields.append((fname, C.c_void_p))
+                continue
+            for tname, ctype in _SCALARS.items():
+                if decl.startswith(tname + " "):
+                    for fname in decl[len(tname):].split(","):
+                        fields.append((fname.strip(), ctype))
+                    break
+            else:
+                raise SerError(f"cannot parse field declaration '{decl}' in {name}")
+        out[name] = type(name, (C.Structure,), {"_fields_": fields})
+    return out
+
+
+def _parse_exports(text: str):
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ser_\w+)\s*\(", text)))
+
+
+with open(HEADER_PATH, "r") as _f:
+    _HEADER = _f.read()
+STRUCTS = _parse_structs(_HEADER)
+EXPORTS = _parse_exports(_HEADER)
+
+GemmDesc = STRUCTS["ser_gemm_desc"]
+AdapterDesc = STRUCTS["ser_adapter_desc"]
+XattnDesc = STRUCTS["ser_xattn_desc"]
+AspDesc = STRUCTS["ser_asp_desc"]
+FusionDesc = STRUCTS["ser_fusion_desc"]
+ClfDesc = STRUCTS["ser_clf_desc"]
+LossDesc = STRUCTS["ser_loss_desc"]
 
 _lib = None
 
@@ -49,11 +92,36 @@ def load():
             "There is no fallback path."
         )
     lib = C.CDLL(LIB_PATH)
-    lib.ser_version.restype = C.c_int
+    missing = [n for n in EXPORTS if not hasattr(lib, n)]
+    if missing:
+        raise SerError(f"libser_head.so does not export {missing}; rebuild it")
+    for n in EXPORTS:
+        getattr(lib, n).restype = C.c_int
     lib.ser_last_error.restype = C.c_char_p
-    lib.ser_sm_count.restype = C.c_int
-    lib.ser_gemm.restype = C.c_int
-    lib.ser_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
+    for n in ("ser_xattn_bwd_ws_bytes", "ser_fusion_bwd_ws_bytes", "ser_clf_bwd_ws_bytes"):
+        getattr(lib, n).restype = C.c_size_t
+    P, I, LL, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+    lib.ser_gemm.argtypes = [C.POINTER(GemmDesc), P]
+    lib.ser_cast.argtypes = [P, I, P, I, LL, P]
+    lib.ser_layernorm_fwd.argtypes = [P, I, P, I, P, P, P, I, I, I, P]
+    lib.ser_layernorm_bwd.argtypes = [P, I, P, I, P, P, P, P, I, P, P, I, I, I, P]
+    lib.ser_colsum.argtypes = [P, I, LL, I, I, P, P]
+    for n, S in (("adapter", AdapterDesc), ("xattn", XattnDesc), ("asp", AspDesc), ("fusion", FusionDesc),
+                 ("clf", ClfDesc)):
+        getattr(lib, f"ser_{n}_fwd").argtypes = [C.POINTER(S), P]
+        getattr(lib, f"ser_{n}_bwd").argtypes = [C.POINTER(S), P]
+    for n in ("ser_loss_fwd", "ser_loss_finalize", "ser_loss_bwd"):
+        getattr(lib, n).argtypes = [C.POINTER(LossDesc), P]
+    lib.ser_xattn_bwd_ws_bytes.argtypes = [I] * 7
+    lib.ser_fusion_bwd_ws_bytes.argtypes = [I] * 5
+    lib.ser_clf_bwd_ws_bytes.argtypes = [I] * 6
+    lib.ser_openmax_fwd.argtypes = [P, P, P, P, P, P, P, I, I, I, P]
+    lib.ser_eval_post.argtypes = [P, I, I, I, F, P, P, P, P, P]
+    lib.ser_temperature_sweep.argtypes = [P, P, I, I, P, I, P, P]
+    lib.ser_desc_size.argtypes = [I]
+    for i, S in enumerate((GemmDesc, AdapterDesc, XattnDesc, AspDesc, FusionDesc, ClfDesc, LossDesc)):
+        if lib.ser_desc_size(i) != C.sizeof(S):
+            raise SerError(f"layout mismatch for {S.__name__}: C {lib.ser_desc_size(i)} vs ctypes {C.sizeof(S)}")
     _lib = lib
     return lib
 
@@ -87,6 +155,37 @@ def require_cuda(*tensors) -> None:
                 "the B200 fusion head has no CPU path: tensors must live on a CUDA device "
                 f"(got {t.device})"
             )
+
+
+def fill(desc, keep: list, **fields):
+    """Set descriptor fields.  Tensors become device pointers; lists of tensors become host arrays of
+    device pointers (kept alive through `keep`); None becomes NULL."""
+    valid = {n for n, _ in desc._fields_}
+    for k, v in fields.items():
+        if k not in valid:
+            raise SerError(f"{type(desc).__name__} has no field '{k}'")
+        if isinstance(v, torch.Tensor):
+            if not v.is_cuda:
+                raise SerError(f"field '{k}': tensor is on {v.device}; the fusion head has no CPU path")
+            if not v.is_contiguous():
+                raise SerError(f"field '{k}': tensor must be contiguous")
+            keep.append(v)
+            setattr(desc, k, v.data_ptr())
+        elif isinstance(v, (list, tuple)):
+            arr = (C.c_void_p * len(v))(*[t.data_ptr() for t in v])
+            keep.append(arr)
+            keep.extend(v)
+            setattr(desc, k, C.cast(arr, C.c_void_p))
+        elif v is None:
+            setattr(desc, k, None)
+        else:
+            setattr(desc, k, v)
+    return desc
+
+
+def call(name: str, desc, device) -> None:
+    lib = load()
+    check(getattr(lib, name)(C.byref(desc), stream_ptr(device)), name)
 
 
 def gemm(a, b, *, a_trans=False, b_trans=False, bias=None, act=ACT_NONE, residual=None, gate=None,

@@ -1,0 +1,90 @@
+"""Flat parameter storage for the drop-in modules.
+
+Each module keeps its nn.Parameters exactly as the reference names them (state_dict compatible), but
+re-points their storage into ONE contiguous fp32 buffer.  That gives
+  * one `ser_cast` launch per forward to produce the bf16 operand copies of every weight,
+  * packed weights (q|k|v rows) as plain views, no concatenation,
+  * a contiguous gradient buffer for bucketed NCCL all-reduce in data-parallel runs.
+Parameters stay ordinary fp32 leaf tensors: optimisers, load_state_dict, .grad all work unchanged.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+ALIGN = 64  # elements; keeps every tensor 128-byte (bf16) / 256-byte (fp32) aligned
+
+
+class FlatParams:
+    def __init__(self, named: Sequence[Tuple[str, nn.Parameter]]):
+        self.names: List[str] = [n for n, _ in named]
+        self.params: List[nn.Parameter] = [p for _, p in named]
+        self.offsets: List[int] = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            n = p.numel()
+            off += n if n % ALIGN == 0 else n + (ALIGN - n % ALIGN)
+        self.total = off
+        self.flat: torch.Tensor | None = None
+        self._lowp: Dict[torch.dtype, torch.Tensor] = {}
+        self.index = {n: i for i, n in enumerate(self.names)}
+
+    # ---------------------------------------------------------------------------------------------
+    def ensure(self) -> None:
+        """(Re)build the flat buffer if the parameters moved (e.g. after module.to(device))."""
+        p0 = self.params[0]
+        if not p0.is_cuda:
+            raise _lib.SerError("the B200 fusion head has no CPU path: move the module to a CUDA device")
+        if p0.dtype != torch.float32:
+            raise _lib.SerError("module parameters must stay float32 (masters); feed bfloat16 inputs to select "
+                                "the bf16 tensor-core tier")
+        if self.flat is not None and self.flat.device == p0.device:
+            base = self.flat.data_ptr()
+            if all(p.data_ptr() == base + 4 * o for p, o in zip(self.params, self.offsets)):
+                return
+        flat = torch.zeros(self.total, device=p0.device, dtype=torch.float32)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                v = flat[o:o + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+        self.flat = flat
+        self._lowp = {}
+
+    def view(self, flat: torch.Tensor, name: str, count: int = 1) -> torch.Tensor:
+        """View of `name` inside a flat buffer; count > 1 spans that many consecutive same-shape params
+        stacked along dim 0 (packed q|k|v)."""
+        i = self.index[name]
+        p = self.params[i]
+        n = p.numel() * count
+        shape = (p.shape[0] * count,) + tuple(p.shape[1:]) if p.dim() > 0 else ()
+        if count > 1:
+            for j in range(1, count):
+                assert self.offsets[i + j] == self.offsets[i] + j * p.numel(), "packed params must be adjacent"
+        return flat[self.offsets[i]:self.offsets[i] + n].view(shape)
+
+    def compute_copy(self, dtype: torch.dtype) -> torch.Tensor:
+        """Flat buffer in the compute dtype: the fp32 masters themselves, or a fresh bf16 cast (one launch)."""
+        self.ensure()
+        if dtype == torch.float32:
+            return self.flat
+        buf = self._lowp.get(dtype)
+        if buf is None or buf.device != self.flat.device:
+            buf = torch.empty(self.total, device=self.flat.device, dtype=dtype)
+            self._lowp[dtype] = buf
+        lib = _lib.load()
+        _lib.check(lib.ser_cast(self.flat.data_ptr(), 1, buf.data_ptr(), 0, self.total,
+                                _lib.stream_ptr(self.flat.device)), "ser_cast")
+        return buf
+
+    def new_grad_buffer(self) -> torch.Tensor:
+        return torch.zeros(self.total, device=self.flat.device, dtype=torch.float32)
+
+    def grads_from(self, gflat: torch.Tensor) -> List[torch.Tensor]:
+        return [gflat[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, self.offsets)]

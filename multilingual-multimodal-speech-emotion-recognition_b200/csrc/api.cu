@@ -1,6 +1,7 @@
 // extern "C" surface of libser_head.so (declared in include/ser_head.h).
 #include "common.cuh"
-#include "../../include/ser_head.h"
+#include "kernels.cuh"
+#include "modules.cuh"
 #include <string.h>
 
 namespace ser {
@@ -23,6 +24,19 @@ const char* ser_last_error(void) { return ser::last_error(); }
 
 int ser_sm_count(void) { return ser::device_sm_count(); }
 
+int ser_desc_size(int id) {
+  switch (id) {
+    case 0: return static_cast<int>(sizeof(ser_gemm_desc));
+    case 1: return static_cast<int>(sizeof(ser_adapter_desc));
+    case 2: return static_cast<int>(sizeof(ser_xattn_desc));
+    case 3: return static_cast<int>(sizeof(ser_asp_desc));
+    case 4: return static_cast<int>(sizeof(ser_fusion_desc));
+    case 5: return static_cast<int>(sizeof(ser_clf_desc));
+    case 6: return static_cast<int>(sizeof(ser_loss_desc));
+    default: return -1;
+  }
+}
+
 int ser_gemm(const ser_gemm_desc* d, void* stream) {
   if (d == nullptr) { ser::set_last_error(__FILE__, __LINE__, "null descriptor"); return SER_ERR_ARG; }
   ser::GemmArgs a;
@@ -35,6 +49,88 @@ int ser_gemm(const ser_gemm_desc* d, void* stream) {
   a.G = d->G; a.ldg = d->ldg; a.g_f32 = d->g_f32; a.gate_mode = d->gate_mode;
   a.act = d->act; a.accumulate = d->accumulate; a.alpha = d->alpha; a.splits = d->splits;
   return ser::gemm(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+
+#define SER_STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define SER_NOT_NULL(d)                                                                  \
+  if ((d) == nullptr) { ser::set_last_error(__FILE__, __LINE__, "null descriptor"); return SER_ERR_ARG; }
+
+int ser_cast(const void* src, int src_f32, void* dst, int dst_f32, long long n, void* stream) {
+  return ser::cast_any(src, src_f32, dst, dst_f32, n, SER_STREAM(stream));
+}
+
+int ser_layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, const float* gamma, const float* beta,
+                      float* stats, int M, int N, int relu, void* stream) {
+  return ser::layernorm_fwd(x, x_f32, y, y_f32, nullptr, 1, gamma, beta, stats, M, N, relu, SER_STREAM(stream));
+}
+int ser_layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const float* stats, const float* gamma,
+                      const float* beta, void* dx, int dx_f32, float* dgamma, float* dbeta, int M, int N, int relu,
+                      void* stream) {
+  cudaStream_t s = SER_STREAM(stream);
+  SER_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, sizeof(float) * N, s));
+  SER_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, sizeof(float) * N, s));
+  return ser::layernorm_bwd(dy, dy_f32, x, x_f32, stats, gamma, beta, nullptr, 1, dx, dx_f32, nullptr, 1, dgamma, dbeta,
+                            M, N, relu, s);
+}
+int ser_colsum(const void* X, int x_f32, long long ld, int M, int N, float* out, void* stream) {
+  return ser::colsum(X, x_f32, ld, M, N, out, SER_STREAM(stream));
+}
+
+int ser_adapter_fwd(const ser_adapter_desc* d, void* stream) { SER_NOT_NULL(d); return ser::adapter_fwd(*d, SER_STREAM(stream)); }
+int ser_adapter_bwd(const ser_adapter_desc* d, void* stream) { SER_NOT_NULL(d); return ser::adapter_bwd(*d, SER_STREAM(stream)); }
+
+size_t ser_xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H) {
+  return ser::xattn_bwd_ws_bytes(dtype, B, Ta, Tt, D, S, H);
+}
+int ser_xattn_fwd(const ser_xattn_desc* d, void* stream) { SER_NOT_NULL(d); return ser::xattn_fwd(*d, SER_STREAM(stream)); }
+int ser_xattn_bwd(const ser_xattn_desc* d, void* stream) { SER_NOT_NULL(d); return ser::xattn_bwd(*d, SER_STREAM(stream)); }
+
+int ser_asp_fwd(const ser_asp_desc* d, void* stream) { SER_NOT_NULL(d); return ser::asp_module_fwd(*d, SER_STREAM(stream)); }
+int ser_asp_bwd(const ser_asp_desc* d, void* stream) { SER_NOT_NULL(d); return ser::asp_module_bwd(*d, SER_STREAM(stream)); }
+
+size_t ser_fusion_bwd_ws_bytes(int dtype, int B, int Din, int P, int G) { return ser::fusion_bwd_ws_bytes(dtype, B, Din, P, G); }
+int ser_fusion_fwd(const ser_fusion_desc* d, void* stream) { SER_NOT_NULL(d); return ser::fusion_fwd(*d, SER_STREAM(stream)); }
+int ser_fusion_bwd(const ser_fusion_desc* d, void* stream) { SER_NOT_NULL(d); return ser::fusion_bwd(*d, SER_STREAM(stream)); }
+
+size_t ser_clf_bwd_ws_bytes(int dtype, int B, int P, int F, int C, int U) { return ser::clf_bwd_ws_bytes(dtype, B, P, F, C, U); }
+int ser_clf_fwd(const ser_clf_desc* d, void* stream) { SER_NOT_NULL(d); return ser::clf_fwd(*d, SER_STREAM(stream)); }
+int ser_clf_bwd(const ser_clf_desc* d, void* stream) { SER_NOT_NULL(d); return ser::clf_bwd(*d, SER_STREAM(stream)); }
+
+static ser::LossArgs to_loss_args(const ser_loss_desc& d) {
+  ser::LossArgs a{};
+  a.B = d.B; a.C = d.C; a.D = d.D; a.B_global = d.B_global > 0 ? d.B_global : d.B;
+  a.logits = d.logits; a.unc = d.unc; a.emb = d.emb; a.emb_f32 = d.emb_f32; a.protos = d.protos;
+  a.labels = d.labels; a.counts = d.counts;
+  a.smoothing = d.smoothing; a.beta = d.beta; a.gamma = d.gamma; a.margin = d.margin;
+  a.focal_use_weights = d.focal_use_weights; a.class_w = d.class_w; a.sums = d.sums;
+  a.w_ce = d.w_ce; a.w_focal = d.w_focal; a.w_unc = d.w_unc; a.w_proto = d.w_proto;
+  a.dlogits = d.dlogits; a.dunc = d.dunc; a.demb = d.demb; a.demb_f32 = d.demb_f32; a.dprotos = d.dprotos;
+  return a;
+}
+int ser_loss_fwd(const ser_loss_desc* d, void* stream) { SER_NOT_NULL(d); return ser::loss_fwd(to_loss_args(*d), SER_STREAM(stream)); }
+int ser_loss_finalize(const ser_loss_desc* d, void* stream) {
+  SER_NOT_NULL(d);
+  const long long bg = d->B_global > 0 ? d->B_global : d->B;
+  return ser::loss_finalize(d->sums, bg, d->margin, d->w_ce, d->w_focal, d->w_unc, d->w_proto, d->emb != nullptr,
+                            d->terms, SER_STREAM(stream));
+}
+int ser_loss_bwd(const ser_loss_desc* d, void* stream) {
+  SER_NOT_NULL(d);
+  return ser::loss_bwd_scaled(to_loss_args(*d), d->gscale, SER_STREAM(stream));
+}
+
+int ser_openmax_fwd(const float* feats, const float* logits, const float* act_vecs, const float* w_alpha,
+                    const float* w_beta, const float* w_tau, float* out, int B, int C, int F, void* stream) {
+  return ser::openmax_fwd(feats, logits, act_vecs, w_alpha, w_beta, w_tau, out, B, C, F, SER_STREAM(stream));
+}
+int ser_eval_post(const float* logits_views, int V, int B, int C, float temperature, float* mean_logits,
+                  float* probs, long long* preds, float* energy, void* stream) {
+  return ser::eval_post(logits_views, V, B, C, temperature, mean_logits, probs, preds, energy, SER_STREAM(stream));
+}
+int ser_temperature_sweep(const float* logits, const long long* labels, int B, int C, const float* temps, int nT,
+                          float* err, void* stream) {
+  return ser::temperature_sweep(logits, labels, B, C, temps, nT, err, SER_STREAM(stream));
 }
 
 }  // extern "C"

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include "../../include/ser_head.h"
 
 namespace ser {
 
@@ -14,21 +15,14 @@ enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_SIGMOID = 3 };
 // gate modes: multiply the GEMM result by a derivative read from a saved activation
 enum : int { GATE_NONE = 0, GATE_RELU = 1 /* g > 0 */, GATE_TANH = 2 /* 1 - g^2 */ };
 
-// error codes returned through the C-ABI
-enum : int {
-  SER_OK = 0,
-  SER_ERR_CUDA = 1,
-  SER_ERR_ARG = 2,
-  SER_ERR_UNSUPPORTED = 3,
-  SER_ERR_WORKSPACE = 4,
-};
+// error codes returned through the C-ABI are the SER_OK / SER_ERR_* macros of include/ser_head.h
 
 #define SER_CUDA_CHECK(expr)                                                         \
   do {                                                                               \
     cudaError_t _e = (expr);                                                         \
     if (_e != cudaSuccess) {                                                         \
       ser::set_last_error(__FILE__, __LINE__, cudaGetErrorString(_e));               \
-      return ser::SER_ERR_CUDA;                                                      \
+      return SER_ERR_CUDA;                                                      \
     }                                                                                \
   } while (0)
 
@@ -38,14 +32,14 @@ enum : int {
   do {                                                                               \
     if (!(cond)) {                                                                   \
       ser::set_last_error(__FILE__, __LINE__, msg);                                  \
-      return ser::SER_ERR_ARG;                                                       \
+      return SER_ERR_ARG;                                                       \
     }                                                                                \
   } while (0)
 
 #define SER_TRY(expr)                                                                \
   do {                                                                               \
     int _rc = (expr);                                                                \
-    if (_rc != ser::SER_OK) return _rc;                                              \
+    if (_rc != SER_OK) return _rc;                                              \
   } while (0)
 
 void set_last_error(const char* file, int line, const char* msg);

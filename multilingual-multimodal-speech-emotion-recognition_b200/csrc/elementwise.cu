@@ -1,0 +1,270 @@
+// Memory-bound row/column kernels: casts, column sums (bias gradients), LayerNorm forward/backward.
+// LayerNorm is used by cross_attention.py:43,51 (norm_a / norm_t, N = 768) and by every block of the
+// classifier (classifier.py:80,107,119,125; N = 512 / 256).  One warp owns one row; each lane moves
+// 8 consecutive elements per 128-bit (bf16) / 2x128-bit (fp32) access; statistics are fp32 and the
+// variance is the two-pass form on register-resident data.
+#include "kernels.cuh"
+
+namespace ser {
+
+namespace {
+
+constexpr float kLnEps = 1e-5f;
+constexpr int kMaxChunks = 4;     // N <= 1024
+
+__device__ __forceinline__ void load8_dyn(const void* p, size_t idx, int f32, float (&v)[8]) {
+  if (f32) load8(reinterpret_cast<const float*>(p) + idx, v);
+  else load8(reinterpret_cast<const __nv_bfloat16*>(p) + idx, v);
+}
+__device__ __forceinline__ void store8_dyn(void* p, size_t idx, int f32, const float (&v)[8]) {
+  if (f32) store8(reinterpret_cast<float*>(p) + idx, v);
+  else store8(reinterpret_cast<__nv_bfloat16*>(p) + idx, v);
+}
+
+__global__ void cast_kernel(const void* __restrict__ src, int src_f32, void* __restrict__ dst, int dst_f32,
+                            long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float v[8];
+      load8_dyn(src, i, src_f32, v);
+      store8_dyn(dst, i, dst_f32, v);
+    } else {
+      for (long long j = i; j < n; ++j) st_dyn(dst, j, dst_f32, ld_dyn(src, j, src_f32));
+    }
+  }
+}
+
+// blockDim = (32, 8): x walks columns, y walks rows; grid = (ceil(N/32), row_splits)
+__global__ void colsum_kernel(const void* __restrict__ X, int x_f32, long long ld, int M, int N,
+                              float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (n < N) {
+    for (int m = blockIdx.y * 8 + threadIdx.y; m < M; m += gridDim.y * 8)
+      acc += ld_dyn(X, static_cast<size_t>(m) * ld + n, x_f32);
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x];
+    if (gridDim.y == 1) out[n] = s; else atomicAdd(out + n, s);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ln_fwd_kernel(const void* __restrict__ x, int x_f32, void* __restrict__ y, int y_f32, void* __restrict__ y2,
+              int y2_f32, const float* __restrict__ gamma, const float* __restrict__ beta,
+              float* __restrict__ stats, int M, int N, int relu) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int nch = (N + 255) >> 8;
+  const float invN = 1.f / static_cast<float>(N);
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
+    float v[kMaxChunks][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (c < nch && col < N) {
+        load8_dyn(x, static_cast<size_t>(row) * N + col, x_f32, v[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[c][i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[c][i] = 0.f;
+      }
+    }
+    const float mean = warp_sum(s) * invN;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (c < nch && col < N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[c][i] - mean; q += d * d; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * invN + kLnEps);
+    if (lane == 0 && stats != nullptr) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (c < nch && col < N) {
+        float g[8], b[8], o[8];
+        load8(gamma + col, g);
+        load8(beta + col, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float t = (v[c][i] - mean) * rstd * g[i] + b[i];
+          o[i] = (relu && t < 0.f) ? 0.f : t;
+        }
+        store8_dyn(y, static_cast<size_t>(row) * N + col, y_f32, o);
+        if (y2 != nullptr) store8_dyn(y2, static_cast<size_t>(row) * N + col, y2_f32, o);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ln_bwd_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ x, int x_f32,
+              const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+              const void* __restrict__ add, int add_f32, void* __restrict__ dx, int dx_f32, void* __restrict__ dx2,
+              int dx2_f32, float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int N, int relu) {
+  __shared__ float sg[kMaxChunks * 256];
+  __shared__ float sb[kMaxChunks * 256];
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int nch = (N + 255) >> 8;
+  const float invN = 1.f / static_cast<float>(N);
+  for (int i = threadIdx.x; i < kMaxChunks * 256; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
+  __syncthreads();
+
+  float ag[kMaxChunks][8], ab[kMaxChunks][8];
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ag[c][i] = 0.f; ab[c][i] = 0.f; }
+
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
+    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+    float xh[kMaxChunks][8], a[kMaxChunks][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (c < nch && col < N) {
+        float xv[8], gv[8], gm[8];
+        load8_dyn(x, static_cast<size_t>(row) * N + col, x_f32, xv);
+        load8_dyn(dy, static_cast<size_t>(row) * N + col, dy_f32, gv);
+        load8(gamma + col, gm);
+        float bt[8];
+        if (relu) load8(beta + col, bt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float h = (xv[i] - mean) * rstd;
+          float g = gv[i];
+          if (relu && !(h * gm[i] + bt[i] > 0.f)) g = 0.f;
+          xh[c][i] = h;
+          a[c][i] = g * gm[i];
+          s1 += a[c][i];
+          s2 += a[c][i] * h;
+          ag[c][i] += g * h;
+          ab[c][i] += g;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { xh[c][i] = 0.f; a[c][i] = 0.f; }
+      }
+    }
+    s1 = warp_sum(s1) * invN;
+    s2 = warp_sum(s2) * invN;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (c < nch && col < N) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rstd * (a[c][i] - s1 - xh[c][i] * s2);
+        if (add != nullptr) {
+          float r[8];
+          load8_dyn(add, static_cast<size_t>(row) * N + col, add_f32, r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += r[i];
+        }
+        store8_dyn(dx, static_cast<size_t>(row) * N + col, dx_f32, o);
+        if (dx2 != nullptr) store8_dyn(dx2, static_cast<size_t>(row) * N + col, dx2_f32, o);
+      }
+    }
+  }
+  if (dgamma != nullptr) {
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (c < nch && col < N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { atomicAdd(&sg[col + i], ag[c][i]); atomicAdd(&sb[col + i], ab[c][i]); }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { atomicAdd(dgamma + i, sg[i]); atomicAdd(dbeta + i, sb[i]); }
+  }
+}
+
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ ds,
+                                   long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) ds[i] = dy[i] * y[i] * (1.f - y[i]);
+}
+
+}  // namespace
+
+int cast_any(const void* src, int src_f32, void* dst, int dst_f32, long long n, cudaStream_t s) {
+  if (n <= 0) return SER_OK;
+  SER_REQUIRE((reinterpret_cast<uintptr_t>(src) & 31) == 0 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0,
+              "cast: buffers must be 32-byte aligned");
+  long long blocks = (n / 8 + 255) / 256;
+  const long long cap = 8LL * device_sm_count();
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cast_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(src, src_f32, dst, dst_f32, n);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+int cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t s) {
+  return cast_any(src, 1, dst, 0, n, s);
+}
+
+int colsum(const void* X, int x_f32, long long ld, int M, int N, float* out, cudaStream_t s) {
+  SER_REQUIRE(M > 0 && N > 0, "colsum: empty");
+  const int gx = ceil_div(N, 32);
+  int gy = ceil_div(4 * device_sm_count(), gx);
+  const int max_gy = ceil_div(M, 64);
+  if (gy > max_gy) gy = max_gy;
+  if (gy < 1) gy = 1;
+  if (gy > 1) SER_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * N, s));
+  colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, s>>>(X, x_f32, ld, M, N, out);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+static int ln_grid(int M) {
+  int blocks = ceil_div(M, 8);
+  const int cap = 8 * device_sm_count();
+  if (blocks > cap) blocks = cap;
+  return blocks < 1 ? 1 : blocks;
+}
+
+int layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, void* y2, int y2_f32, const float* gamma,
+                  const float* beta, float* stats, int M, int N, int relu, cudaStream_t s) {
+  SER_REQUIRE(N % 8 == 0 && N <= kMaxChunks * 256, "layernorm: N must be a multiple of 8 and <= 1024");
+  ln_fwd_kernel<<<ln_grid(M), 256, 0, s>>>(x, x_f32, y, y_f32, y2, y2_f32, gamma, beta, stats, M, N, relu);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+int layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const float* stats, const float* gamma,
+                  const float* beta, const void* add, int add_f32, void* dx, int dx_f32, void* dx2, int dx2_f32,
+                  float* dgamma, float* dbeta, int M, int N, int relu, cudaStream_t s) {
+  SER_REQUIRE(N % 8 == 0 && N <= kMaxChunks * 256, "layernorm: N must be a multiple of 8 and <= 1024");
+  int blocks = ceil_div(M, 8);
+  const int cap = 2 * device_sm_count();     // fewer CTAs -> fewer global atomics for dgamma/dbeta
+  if (blocks > cap) blocks = cap;
+  ln_bwd_kernel<<<blocks, 256, 0, s>>>(dy, dy_f32, x, x_f32, stats, gamma, beta, add, add_f32, dx, dx_f32, dx2,
+                                       dx2_f32, dgamma, dbeta, M, N, relu);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+int sigmoid_bwd(const float* dy, const float* y, float* ds, long long n, cudaStream_t s) {
+  if (n <= 0) return SER_OK;
+  sigmoid_bwd_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(dy, y, ds, n);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+}  // namespace ser

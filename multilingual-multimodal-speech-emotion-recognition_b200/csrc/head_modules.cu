@@ -1,0 +1,498 @@
+// Module-level orchestration behind the C-ABI: each function enqueues the kernel sequence of one
+// reference module (forward or backward) on the caller's stream.  The same code drives both tiers:
+// `dtype` picks the CUDA-core fp32 GEMM or the tcgen05 bf16 GEMM and the storage type of activations.
+#include "kernels.cuh"
+#include "../../include/ser_head.h"
+
+namespace ser {
+
+namespace {
+
+inline size_t esize(int dtype) { return dtype == DT_F32 ? 4 : 2; }
+inline int is_f32(int dtype) { return dtype == DT_F32 ? 1 : 0; }
+inline const void* off(const void* p, long long elems, int dtype) {
+  return reinterpret_cast<const char*>(p) + elems * static_cast<long long>(esize(dtype));
+}
+inline void* off(void* p, long long elems, int dtype) {
+  return reinterpret_cast<char*>(p) + elems * static_cast<long long>(esize(dtype));
+}
+
+// bump allocator over the caller-provided workspace
+struct Arena {
+  char* base; size_t cap; size_t used = 0; bool ok = true;
+  Arena(void* p, size_t n) : base(reinterpret_cast<char*>(p)), cap(n) {}
+  void* take(size_t bytes) {
+    const size_t a = (used + 255) & ~size_t(255);
+    if (base == nullptr || a + bytes > cap) { ok = false; return nullptr; }
+    used = a + bytes;
+    return base + a;
+  }
+};
+inline size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
+
+// C[M,Nout] = act(A[M,Kin] W[Nout,Kin]^T + bias) (+ R)
+int linear_fwd(int dt, int M, int Nout, int Kin, const void* A, long long lda, const void* W, long long ldw,
+               const float* bias, void* C, long long ldc, int c_f32, int act, const void* R, long long ldr, int r_f32,
+               cudaStream_t s) {
+  GemmArgs g;
+  g.dtype = dt; g.M = M; g.N = Nout; g.K = Kin;
+  g.A = A; g.lda = lda; g.a_trans = 0;
+  g.B = W; g.ldb = ldw; g.b_trans = 0;
+  g.C = C; g.ldc = ldc; g.c_f32 = c_f32;
+  g.bias = bias; g.act = act;
+  g.R = R; g.ldr = ldr; g.r_f32 = r_f32;
+  return gemm(g, s);
+}
+
+// dX[M,Kin] = gate'(dY[M,Nout] W[Nout,Kin]) (+ R)
+int linear_dgrad(int dt, int M, int Nout, int Kin, const void* dY, long long lddy, const void* W, long long ldw,
+                 void* dX, long long lddx, int dx_f32, const void* G, long long ldg, int g_f32, int gate_mode,
+                 const void* R, long long ldr, int r_f32, cudaStream_t s) {
+  GemmArgs g;
+  g.dtype = dt; g.M = M; g.N = Kin; g.K = Nout;
+  g.A = dY; g.lda = lddy; g.a_trans = 0;
+  g.B = W; g.ldb = ldw; g.b_trans = 1;
+  g.C = dX; g.ldc = lddx; g.c_f32 = dx_f32;
+  g.G = G; g.ldg = ldg; g.g_f32 = g_f32; g.gate_mode = gate_mode;
+  g.R = R; g.ldr = ldr; g.r_f32 = r_f32;
+  return gemm(g, s);
+}
+
+// dW[Nout,Kin] (fp32) = dY[M,Nout]^T X[M,Kin]
+int linear_wgrad(int dt, int M, int Nout, int Kin, const void* dY, long long lddy, const void* X, long long ldx,
+                 float* dW, long long lddw, cudaStream_t s) {
+  GemmArgs g;
+  g.dtype = dt; g.M = Nout; g.N = Kin; g.K = M;
+  g.A = dY; g.lda = lddy; g.a_trans = 1;
+  g.B = X; g.ldb = ldx; g.b_trans = 1;
+  g.C = dW; g.ldc = lddw; g.c_f32 = 1;
+  return gemm(g, s);
+}
+
+}  // namespace
+
+// =================================================================================================
+// a1 adapter
+// =================================================================================================
+int adapter_fwd(const ser_adapter_desc& d, cudaStream_t s) {
+  const int dt = d.dtype, f = is_f32(dt);
+  SER_REQUIRE(d.M > 0 && d.x && d.h && d.y, "adapter_fwd: null tensor");
+  SER_TRY(linear_fwd(dt, d.M, d.S, d.D, d.x, d.D, d.w1, d.D, d.b1, d.h, d.S, f, ACT_RELU, nullptr, 0, f, s));
+  SER_TRY(linear_fwd(dt, d.M, d.D, d.S, d.h, d.S, d.w2, d.S, d.b2, d.y, d.D, f, ACT_NONE,
+                     d.add_residual ? d.x : nullptr, d.D, f, s));
+  return SER_OK;
+}
+
+int adapter_bwd(const ser_adapter_desc& d, cudaStream_t s) {
+  const int dt = d.dtype, f = is_f32(dt);
+  SER_REQUIRE(d.M > 0 && d.dy && d.dh && d.h && d.x, "adapter_bwd: null tensor");
+  SER_TRY(colsum(d.dy, f, d.D, d.M, d.D, d.db2, s));
+  SER_TRY(linear_wgrad(dt, d.M, d.D, d.S, d.dy, d.D, d.h, d.S, d.dw2, d.S, s));
+  SER_TRY(linear_dgrad(dt, d.M, d.D, d.S, d.dy, d.D, d.w2, d.S, d.dh, d.S, f, d.h, d.S, f, GATE_RELU, nullptr, 0, f, s));
+  SER_TRY(colsum(d.dh, f, d.S, d.M, d.S, d.db1, s));
+  SER_TRY(linear_wgrad(dt, d.M, d.S, d.D, d.dh, d.S, d.x, d.D, d.dw1, d.D, s));
+  if (d.dx != nullptr)
+    SER_TRY(linear_dgrad(dt, d.M, d.S, d.D, d.dh, d.S, d.w1, d.D, d.dx, d.D, f, nullptr, 0, f, GATE_NONE,
+                         d.add_residual ? d.dy : nullptr, d.D, f, s));
+  return SER_OK;
+}
+
+// =================================================================================================
+// a2 cross-modal attention
+// =================================================================================================
+int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s) {
+  const int dt = d.dtype, f = is_f32(dt);
+  const int S = d.S, D = d.D, S3 = 3 * d.S;
+  const int Ma = d.B * d.Ta, Mt = d.B * d.Tt;
+  SER_REQUIRE(S % d.H == 0, "xattn: shared_dim must be divisible by num_heads");   // cross_attention.py:12
+  SER_REQUIRE(Ma > 0 && Mt > 0, "xattn: empty input");
+  // outer projections, one packed GEMM per modality (cross_attention.py:38-40,46-48)
+  SER_TRY(linear_fwd(dt, Ma, S3, D, d.a, D, d.wqkv_a, D, d.bqkv_a, d.qkv_a, S3, f, ACT_NONE, nullptr, 0, f, s));
+  SER_TRY(linear_fwd(dt, Mt, S3, D, d.t, D, d.wqkv_t, D, d.bqkv_t, d.qkv_t, S3, f, ACT_NONE, nullptr, 0, f, s));
+  // MHA in-projections (torch/nn/functional.py:5798 chunking): attn_a takes (qa, kt, vt), attn_t takes (qt, ka, va)
+  struct InProj { const void* src; int M; int scol; const void* w; const float* b; int wrow; void* dst; int dcol; };
+  const InProj ip[6] = {
+      {d.qkv_a, Ma, 0,     d.win_a, d.bin_a, 0,     d.p_a, 0},
+      {d.qkv_t, Mt, S,     d.win_a, d.bin_a, S,     d.p_t, S},
+      {d.qkv_t, Mt, 2 * S, d.win_a, d.bin_a, 2 * S, d.p_t, 2 * S},
+      {d.qkv_t, Mt, 0,     d.win_t, d.bin_t, 0,     d.p_t, 0},
+      {d.qkv_a, Ma, S,     d.win_t, d.bin_t, S,     d.p_a, S},
+      {d.qkv_a, Ma, 2 * S, d.win_t, d.bin_t, 2 * S, d.p_a, 2 * S},
+  };
+  for (const InProj& p : ip) {
+    SER_TRY(linear_fwd(dt, p.M, S, S, off(p.src, p.scol, dt), S3, off(p.w, static_cast<long long>(p.wrow) * S, dt), S,
+                       p.b + p.wrow, off(p.dst, p.dcol, dt), S3, f, ACT_NONE, nullptr, 0, f, s));
+  }
+  AttnArgs at{};
+  at.dtype = dt; at.B = d.B; at.H = d.H; at.dh = S / d.H;
+  at.scale = 1.0f / sqrtf(static_cast<float>(at.dh));
+  // A <- T
+  at.Tq = d.Ta; at.Tk = d.Tt;
+  at.Q = d.p_a; at.ldq = S3;
+  at.K = off(d.p_t, S, dt); at.ldk = S3;
+  at.V = off(d.p_t, 2 * S, dt); at.ldv = S3;
+  at.kmask = d.t_mask; at.O = d.ctx_a; at.ldo = S; at.lse = d.lse_a;
+  SER_TRY(attention_fwd(at, s));
+  // T <- A
+  at.Tq = d.Tt; at.Tk = d.Ta;
+  at.Q = d.p_t;
+  at.K = off(d.p_a, S, dt);
+  at.V = off(d.p_a, 2 * S, dt);
+  at.kmask = d.a_mask; at.O = d.ctx_t; at.lse = d.lse_t;
+  SER_TRY(attention_fwd(at, s));
+  // out_proj, out_a / out_t + residual, LayerNorm (cross_attention.py:42-43,50-51)
+  SER_TRY(linear_fwd(dt, Ma, S, S, d.ctx_a, S, d.wo_a, S, d.bo_a, d.o_a, S, f, ACT_NONE, nullptr, 0, f, s));
+  SER_TRY(linear_fwd(dt, Ma, D, S, d.o_a, S, d.wout_a, S, d.bout_a, d.z_a, D, f, ACT_NONE, d.a, D, f, s));
+  SER_TRY(layernorm_fwd(d.z_a, f, d.enh_a, f, nullptr, f, d.ln_a_g, d.ln_a_b, d.stats_a, Ma, D, 0, s));
+  SER_TRY(linear_fwd(dt, Mt, S, S, d.ctx_t, S, d.wo_t, S, d.bo_t, d.o_t, S, f, ACT_NONE, nullptr, 0, f, s));
+  SER_TRY(linear_fwd(dt, Mt, D, S, d.o_t, S, d.wout_t, S, d.bout_t, d.z_t, D, f, ACT_NONE, d.t, D, f, s));
+  SER_TRY(layernorm_fwd(d.z_t, f, d.enh_t, f, nullptr, f, d.ln_t_g, d.ln_t_b, d.stats_t, Mt, D, 0, s));
+  return SER_OK;
+}
+
+size_t xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H) {
+  const size_t e = esize(dtype);
+  size_t tot = 0;
+  for (int T : {Ta, Tt}) {
+    const size_t M = static_cast<size_t>(B) * T;
+    tot += pad256(M * D * e);            // dz
+    tot += 2 * pad256(M * S * e);        // do, dctx
+    tot += 2 * pad256(M * 3 * S * e);    // dp, dqkv
+    tot += pad256(static_cast<size_t>(B) * H * T * sizeof(float));   // delta
+  }
+  return tot + 4096;
+}
+
+int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
+  const int dt = d.dtype, f = is_f32(dt);
+  const int S = d.S, D = d.D, S3 = 3 * d.S;
+  const int Ma = d.B * d.Ta, Mt = d.B * d.Tt;
+  const size_t e = esize(dt);
+  Arena ws(d.ws, d.ws_bytes);
+  void* dz_a = ws.take(static_cast<size_t>(Ma) * D * e);
+  void* dz_t = ws.take(static_cast<size_t>(Mt) * D * e);
+  void* do_a = ws.take(static_cast<size_t>(Ma) * S * e);
+  void* do_t = ws.take(static_cast<size_t>(Mt) * S * e);
+  void* dctx_a = ws.take(static_cast<size_t>(Ma) * S * e);
+  void* dctx_t = ws.take(static_cast<size_t>(Mt) * S * e);
+  void* dp_a = ws.take(static_cast<size_t>(Ma) * S3 * e);
+  void* dp_t = ws.take(static_cast<size_t>(Mt) * S3 * e);
+  void* dqkv_a = ws.take(static_cast<size_t>(Ma) * S3 * e);
+  void* dqkv_t = ws.take(static_cast<size_t>(Mt) * S3 * e);
+  float* delta_a = reinterpret_cast<float*>(ws.take(static_cast<size_t>(d.B) * d.H * d.Ta * sizeof(float)));
+  float* delta_t = reinterpret_cast<float*>(ws.take(static_cast<size_t>(d.B) * d.H * d.Tt * sizeof(float)));
+  if (!ws.ok) { set_last_error(__FILE__, __LINE__, "xattn_bwd: workspace too small"); return SER_ERR_WORKSPACE; }
+
+  // LayerNorm backward (parameter gradients accumulate with atomics -> zero first)
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_a_g, 0, sizeof(float) * D, s));
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_a_b, 0, sizeof(float) * D, s));
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_t_g, 0, sizeof(float) * D, s));
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_t_b, 0, sizeof(float) * D, s));
+  SER_TRY(layernorm_bwd(d.d_enh_a, f, d.z_a, f, d.stats_a, d.ln_a_g, d.ln_a_b, nullptr, f, dz_a, f, nullptr, f,
+                        d.dln_a_g, d.dln_a_b, Ma, D, 0, s));
+  SER_TRY(layernorm_bwd(d.d_enh_t, f, d.z_t, f, d.stats_t, d.ln_t_g, d.ln_t_b, nullptr, f, dz_t, f, nullptr, f,
+                        d.dln_t_g, d.dln_t_b, Mt, D, 0, s));
+  // out_a / out_t and out_proj
+  struct Side { int M; void* dz; const void* o; const void* ctx; void* dob; void* dctx; const void* wout; const void* wo;
+                float* dwout; float* dbout; float* dwo; float* dbo; };
+  const Side sides[2] = {
+      {Ma, dz_a, d.o_a, d.ctx_a, do_a, dctx_a, d.wout_a, d.wo_a, d.dwout_a, d.dbout_a, d.dwo_a, d.dbo_a},
+      {Mt, dz_t, d.o_t, d.ctx_t, do_t, dctx_t, d.wout_t, d.wo_t, d.dwout_t, d.dbout_t, d.dwo_t, d.dbo_t},
+  };
+  for (const Side& sd : sides) {
+    SER_TRY(colsum(sd.dz, f, D, sd.M, D, sd.dbout, s));
+    SER_TRY(linear_wgrad(dt, sd.M, D, S, sd.dz, D, sd.o, S, sd.dwout, S, s));
+    SER_TRY(linear_dgrad(dt, sd.M, D, S, sd.dz, D, sd.wout, S, sd.dob, S, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
+    SER_TRY(colsum(sd.dob, f, S, sd.M, S, sd.dbo, s));
+    SER_TRY(linear_wgrad(dt, sd.M, S, S, sd.dob, S, sd.ctx, S, sd.dwo, S, s));
+    SER_TRY(linear_dgrad(dt, sd.M, S, S, sd.dob, S, sd.wo, S, sd.dctx, S, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
+  }
+  // attention core backward
+  AttnArgs at{};
+  at.dtype = dt; at.B = d.B; at.H = d.H; at.dh = S / d.H;
+  at.scale = 1.0f / sqrtf(static_cast<float>(at.dh));
+  at.ldq = at.ldk = at.ldv = S3; at.ldo = S; at.lddo = S; at.lddq = at.lddk = at.lddv = S3;
+  // A <- T
+  at.Tq = d.Ta; at.Tk = d.Tt;
+  at.Q = d.p_a; at.K = off(d.p_t, S, dt); at.V = off(d.p_t, 2 * S, dt);
+  at.kmask = d.t_mask; at.O = d.ctx_a; at.lse = d.lse_a; at.dO = dctx_a; at.delta = delta_a;
+  at.dQ = dp_a; at.dK = off(dp_t, S, dt); at.dV = off(dp_t, 2 * S, dt);
+  SER_TRY(attention_bwd(at, s));
+  // T <- A
+  at.Tq = d.Tt; at.Tk = d.Ta;
+  at.Q = d.p_t; at.K = off(d.p_a, S, dt); at.V = off(d.p_a, 2 * S, dt);
+  at.kmask = d.a_mask; at.O = d.ctx_t; at.lse = d.lse_t; at.dO = dctx_t; at.delta = delta_t;
+  at.dQ = dp_t; at.dK = off(dp_a, S, dt); at.dV = off(dp_a, 2 * S, dt);
+  SER_TRY(attention_bwd(at, s));
+  // MHA in-projection backward
+  struct InProjB { const void* dp; const void* src; int M; int col; const void* w; float* dw; float* db; int wrow; void* dsrc; };
+  const InProjB ip[6] = {
+      {dp_a, d.qkv_a, Ma, 0,     d.win_a, d.dwin_a, d.dbin_a, 0,     dqkv_a},
+      {dp_t, d.qkv_t, Mt, S,     d.win_a, d.dwin_a, d.dbin_a, S,     dqkv_t},
+      {dp_t, d.qkv_t, Mt, 2 * S, d.win_a, d.dwin_a, d.dbin_a, 2 * S, dqkv_t},
+      {dp_t, d.qkv_t, Mt, 0,     d.win_t, d.dwin_t, d.dbin_t, 0,     dqkv_t},
+      {dp_a, d.qkv_a, Ma, S,     d.win_t, d.dwin_t, d.dbin_t, S,     dqkv_a},
+      {dp_a, d.qkv_a, Ma, 2 * S, d.win_t, d.dwin_t, d.dbin_t, 2 * S, dqkv_a},
+  };
+  for (const InProjB& p : ip) {
+    const void* g = off(p.dp, p.col, dt);
+    SER_TRY(colsum(g, f, S3, p.M, S, p.db + p.wrow, s));
+    SER_TRY(linear_wgrad(dt, p.M, S, S, g, S3, off(p.src, p.col, dt), S3, p.dw + static_cast<long long>(p.wrow) * S, S, s));
+    SER_TRY(linear_dgrad(dt, p.M, S, S, g, S3, off(p.w, static_cast<long long>(p.wrow) * S, dt), S,
+                         off(p.dsrc, p.col, dt), S3, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
+  }
+  // outer projections + residual path
+  SER_TRY(colsum(dqkv_a, f, S3, Ma, S3, d.dbqkv_a, s));
+  SER_TRY(linear_wgrad(dt, Ma, S3, D, dqkv_a, S3, d.a, D, d.dwqkv_a, D, s));
+  SER_TRY(linear_dgrad(dt, Ma, S3, D, dqkv_a, S3, d.wqkv_a, D, d.da, D, f, nullptr, 0, f, GATE_NONE, dz_a, D, f, s));
+  SER_TRY(colsum(dqkv_t, f, S3, Mt, S3, d.dbqkv_t, s));
+  SER_TRY(linear_wgrad(dt, Mt, S3, D, dqkv_t, S3, d.t, D, d.dwqkv_t, D, s));
+  SER_TRY(linear_dgrad(dt, Mt, S3, D, dqkv_t, S3, d.wqkv_t, D, d.dt, D, f, nullptr, 0, f, GATE_NONE, dz_t, D, f, s));
+  return SER_OK;
+}
+
+// =================================================================================================
+// a3 attentive statistics pooling
+// =================================================================================================
+static AspArgs to_asp(const ser_asp_desc& d) {
+  AspArgs a{};
+  a.dtype = d.dtype; a.B = d.B; a.T = d.T; a.D = d.D; a.Hd = d.Hd;
+  a.x = d.x; a.u = d.u; a.w2 = d.w2; a.b2 = d.b2; a.mask = d.mask; a.e = d.e; a.alpha = d.alpha;
+  a.out = d.out; a.out_f32 = d.out_f32; a.dout = d.dout; a.dout_f32 = d.dout_f32; a.dx = d.dx;
+  a.dalpha = d.dalpha; a.dpre = d.dpre; a.dw2 = d.dw2; a.db2 = d.db2;
+  return a;
+}
+
+int asp_module_fwd(const ser_asp_desc& d, cudaStream_t s) {
+  const int dt = d.dtype, f = is_f32(dt);
+  const int M = d.B * d.T;
+  SER_REQUIRE(M > 0 && d.x && d.u && d.e && d.alpha && d.out, "asp_fwd: null tensor");
+  SER_TRY(linear_fwd(dt, M, d.Hd, d.D, d.x, d.D, d.w1, d.D, d.b1, d.u, d.Hd, f, ACT_TANH, nullptr, 0, f, s));
+  return asp_fwd(to_asp(d), s);
+}
+
+int asp_module_bwd(const ser_asp_desc& d, cudaStream_t s) {
+  const int dt = d.dtype, f = is_f32(dt);
+  const int M = d.B * d.T;
+  SER_REQUIRE(d.dout && d.dx && d.dpre && d.dalpha, "asp_bwd: null tensor");
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dw2, 0, sizeof(float) * d.Hd, s));
+  SER_CUDA_CHECK(cudaMemsetAsync(d.db2, 0, sizeof(float), s));
+  SER_TRY(asp_bwd(to_asp(d), s));
+  SER_TRY(colsum(d.dpre, f, d.Hd, M, d.Hd, d.db1, s));
+  SER_TRY(linear_wgrad(dt, M, d.Hd, d.D, d.dpre, d.Hd, d.x, d.D, d.dw1, d.D, s));
+  SER_TRY(linear_dgrad(dt, M, d.Hd, d.D, d.dpre, d.Hd, d.w1, d.D, d.dx, d.D, f, nullptr, 0, f, GATE_NONE, d.dx, d.D, f, s));
+  return SER_OK;
+}
+
+// =================================================================================================
+// a4 gated fusion
+// =================================================================================================
+static MixArgs to_mix(const ser_fusion_desc& d) {
+  MixArgs m{};
+  m.dtype = d.dtype; m.B = d.B; m.P = d.P; m.G = d.G;
+  m.pa = d.pa; m.pt = d.pt; m.ga = d.ga; m.gt = d.gt;
+  m.wga = d.wg2a; m.bga = d.bg2a; m.wgt = d.wg2t; m.bgt = d.bg2t;
+  m.gates = d.gates; m.fused = d.fused; m.dfused = d.dfused;
+  m.dwga = d.dwg2a; m.dbga = d.dbg2a; m.dwgt = d.dwg2t; m.dbgt = d.dbg2t;
+  return m;
+}
+
+int fusion_fwd(const ser_fusion_desc& d, cudaStream_t s) {
+  const int dt = d.dtype, f = is_f32(dt);
+  const int B = d.B, P = d.P, G = d.G, Din = d.Din;
+  SER_REQUIRE(B > 0 && d.av && d.tv && d.fused, "fusion_fwd: null tensor");
+  SER_TRY(linear_fwd(dt, B, P, Din, d.av, Din, d.w1a, Din, d.b1a, d.ha, P, f, ACT_RELU, nullptr, 0, f, s));
+  SER_TRY(linear_fwd(dt, B, P, P, d.ha, P, d.w2a, P, d.b2a, d.pa, P, f, ACT_NONE, nullptr, 0, f, s));
+  SER_TRY(linear_fwd(dt, B, G, P, d.pa, P, d.wg1a, P, d.bg1a, d.ga, G, f, ACT_RELU, nullptr, 0, f, s));
+  SER_TRY(linear_fwd(dt, B, P, Din, d.tv, Din, d.w1t, Din, d.b1t, d.ht, P, f, ACT_RELU, nullptr, 0, f, s));
+  SER_TRY(linear_fwd(dt, B, P, P, d.ht, P, d.w2t, P, d.b2t, d.pt, P, f, ACT_NONE, nullptr, 0, f, s));
+  SER_TRY(linear_fwd(dt, B, G, P, d.pt, P, d.wg1t, P, d.bg1t, d.gt, G, f, ACT_RELU, nullptr, 0, f, s));
+  return fusion_mix_fwd(to_mix(d), s);
+}
+
+size_t fusion_bwd_ws_bytes(int dtype, int B, int Din, int P, int G) {
+  (void)Din;
+  const size_t e = esize(dtype);
+  return 4 * pad256(static_cast<size_t>(B) * P * e) + 2 * pad256(static_cast<size_t>(B) * G * e) + 4096;
+}
+
+int fusion_bwd(const ser_fusion_desc& d, cudaStream_t s) {
+  const int dt = d.dtype, f = is_f32(dt);
+  const int B = d.B, P = d.P, G = d.G, Din = d.Din;
+  const size_t e = esize(dt);
+  Arena ws(d.ws, d.ws_bytes);
+  void* dpa = ws.take(static_cast<size_t>(B) * P * e);
+  void* dpt = ws.take(static_cast<size_t>(B) * P * e);
+  void* dha = ws.take(static_cast<size_t>(B) * P * e);
+  void* dht = ws.take(static_cast<size_t>(B) * P * e);
+  void* dga = ws.take(static_cast<size_t>(B) * G * e);
+  void* dgt = ws.take(static_cast<size_t>(B) * G * e);
+  if (!ws.ok) { set_last_error(__FILE__, __LINE__, "fusion_bwd: workspace too small"); return SER_ERR_WORKSPACE; }
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dwg2a, 0, sizeof(float) * G, s));
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dwg2t, 0, sizeof(float) * G, s));
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dbg2a, 0, sizeof(float), s));
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dbg2t, 0, sizeof(float), s));
+  MixArgs m = to_mix(d);
+  m.dpa = dpa; m.dpt = dpt; m.dga = dga; m.dgt = dgt;
+  SER_TRY(fusion_mix_bwd(m, s));
+  struct Side { void* dp; void* dg; void* dh; const void* p; const void* h; const void* v; const void* wg1; const void* w2;
+                const void* w1; float* dwg1; float* dbg1; float* dw2; float* db2; float* dw1; float* db1; void* dv; };
+  const Side sides[2] = {
+      {dpa, dga, dha, d.pa, d.ha, d.av, d.wg1a, d.w2a, d.w1a, d.dwg1a, d.dbg1a, d.dw2a, d.db2a, d.dw1a, d.db1a, d.dav},
+      {dpt, dgt, dht, d.pt, d.ht, d.tv, d.wg1t, d.w2t, d.w1t, d.dwg1t, d.dbg1t, d.dw2t, d.db2t, d.dw1t, d.db1t, d.dtv},
+  };
+  for (const Side& sd : sides) {
+    SER_TRY(colsum(sd.dg, f, G, B, G, sd.dbg1, s));
+    SER_TRY(linear_wgrad(dt, B, G, P, sd.dg, G, sd.p, P, sd.dwg1, P, s));
+    SER_TRY(linear_dgrad(dt, B, G, P, sd.dg, G, sd.wg1, P, sd.dp, P, f, nullptr, 0, f, GATE_NONE, sd.dp, P, f, s));
+    SER_TRY(colsum(sd.dp, f, P, B, P, sd.db2, s));
+    SER_TRY(linear_wgrad(dt, B, P, P, sd.dp, P, sd.h, P, sd.dw2, P, s));
+    SER_TRY(linear_dgrad(dt, B, P, P, sd.dp, P, sd.w2, P, sd.dh, P, f, sd.h, P, f, GATE_RELU, nullptr, 0, f, s));
+    SER_TRY(colsum(sd.dh, f, P, B, P, sd.db1, s));
+    SER_TRY(linear_wgrad(dt, B, P, Din, sd.dh, P, sd.v, Din, sd.dw1, Din, s));
+    SER_TRY(linear_dgrad(dt, B, P, Din, sd.dh, P, sd.w1, Din, sd.dv, Din, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
+  }
+  return SER_OK;
+}
+
+// =================================================================================================
+// a5 classifier stack + heads
+// =================================================================================================
+int clf_fwd(const ser_clf_desc& d, cudaStream_t s) {
+  const int dt = d.dtype, f = is_f32(dt);
+  const int B = d.B, P = d.P, F = d.F, L = d.L;
+  const size_t BP = static_cast<size_t>(B) * P;
+  SER_REQUIRE(B > 0 && d.x && d.h && d.y && d.n && d.r && d.logits, "clf_fwd: null tensor");
+  // input_projection: Linear -> LayerNorm -> ReLU (classifier.py:105-110)
+  SER_TRY(linear_fwd(dt, B, P, P, d.x, P, d.w_in, P, d.b_in, d.p0, P, 1, ACT_NONE, nullptr, 0, 1, s));
+  SER_TRY(layernorm_fwd(d.p0, 1, d.h, 1, nullptr, 1, d.ln_in_g, d.ln_in_b, d.stats0, B, P, 1, s));
+  for (int i = 0; i < L; ++i) {
+    float* hi = d.h + i * BP;
+    float* hn = d.h + (i + 1) * BP;
+    float* yi = d.y + i * BP;
+    void* ni = off(d.n, static_cast<long long>(i) * BP, dt);
+    void* ri = off(d.r, static_cast<long long>(i) * BP, dt);
+    // outer LayerNorm, then the block's own LayerNorm (classifier.py:207-212, :79-80)
+    SER_TRY(layernorm_fwd(hi, 1, yi, 1, nullptr, 1, d.lno_g[i], d.lno_b[i], d.stats_o + static_cast<size_t>(i) * B * 2, B, P, 0, s));
+    SER_TRY(layernorm_fwd(yi, 1, ni, f, nullptr, 1, d.lni_g[i], d.lni_b[i], d.stats_i + static_cast<size_t>(i) * B * 2, B, P, 0, s));
+    SER_TRY(linear_fwd(dt, B, P, P, ni, P, d.w1[i], P, d.b1[i], ri, P, f, ACT_RELU, nullptr, 0, 1, s));
+    // residual from the OUTER-LN output y
+    SER_TRY(linear_fwd(dt, B, P, P, ri, P, d.w2[i], P, d.b2[i], hn, P, 1, ACT_NONE, yi, P, 1, s));
+  }
+  const float* hL = d.h + static_cast<size_t>(L) * BP;
+  SER_TRY(cast_any(hL, 1, d.h_last, f, static_cast<long long>(BP), s));
+  // output_projection[0..2]: Linear(512->256) -> LN -> ReLU (classifier.py:215-218)
+  if (F % 128 == 0 || dt == DT_F32) {
+    SER_TRY(linear_fwd(dt, B, F, P, d.h_last, P, d.w_out, P, d.b_out, d.q, F, 1, ACT_NONE, nullptr, 0, 1, s));
+  } else {
+    set_last_error(__FILE__, __LINE__, "clf: base_dim/2 must be a multiple of 128 in the bf16 tier");
+    return SER_ERR_UNSUPPORTED;
+  }
+  SER_TRY(layernorm_fwd(d.q, 1, d.f, 1, nullptr, 1, d.ln_out_g, d.ln_out_b, d.stats_q, B, F, 1, s));
+  // heads run in fp32 on the master weights (tiny: C x 256, 64 x 256)
+  SER_TRY(linear_fwd(DT_F32, B, d.C, F, d.f, F, d.w_c, F, d.b_c, d.logits, d.C, 1, ACT_NONE, nullptr, 0, 1, s));
+  if (d.unc != nullptr) {
+    SER_TRY(linear_fwd(DT_F32, B, d.U, F, d.f, F, d.w_u1, F, d.b_u1, d.u1, d.U, 1, ACT_RELU, nullptr, 0, 1, s));
+    SER_TRY(linear_fwd(DT_F32, B, 1, d.U, d.u1, d.U, d.w_u2, d.U, d.b_u2, d.unc, 1, 1, ACT_SIGMOID, nullptr, 0, 1, s));
+  }
+  return SER_OK;
+}
+
+size_t clf_bwd_ws_bytes(int dtype, int B, int P, int F, int C, int U) {
+  (void)C;
+  const size_t e = esize(dtype);
+  const size_t b = static_cast<size_t>(B);
+  return pad256(b * F * 4) + pad256(b * F * e) + 2 * pad256(b * P * 4) + 2 * pad256(b * P * e) + pad256(b * P * 4) +
+         pad256(b * P * e) + pad256(b * U * 4) + pad256(b * 4) + pad256(b * P * e) + 8192;
+}
+
+int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
+  const int dt = d.dtype, f = is_f32(dt);
+  const int B = d.B, P = d.P, F = d.F, L = d.L, C = d.C, U = d.U;
+  const size_t BP = static_cast<size_t>(B) * P;
+  const size_t e = esize(dt);
+  SER_REQUIRE(d.dlogits != nullptr || d.dunc != nullptr, "clf_bwd: no incoming gradient");
+  Arena ws(d.ws, d.ws_bytes);
+  float* df = reinterpret_cast<float*>(ws.take(static_cast<size_t>(B) * F * 4));
+  void* dq = ws.take(static_cast<size_t>(B) * F * e);
+  float* dh32 = reinterpret_cast<float*>(ws.take(BP * 4));      // gradient of the fp32 residual stream
+  float* dy32 = reinterpret_cast<float*>(ws.take(BP * 4));
+  void* dhT = ws.take(BP * e);                                  // act-dtype copy (GEMM operand)
+  void* drT = ws.take(BP * e);
+  float* dn32 = reinterpret_cast<float*>(ws.take(BP * 4));
+  void* dp0 = ws.take(BP * e);
+  float* du1 = reinterpret_cast<float*>(ws.take(static_cast<size_t>(B) * U * 4));
+  float* dsg = reinterpret_cast<float*>(ws.take(static_cast<size_t>(B) * 4));
+  if (!ws.ok) { set_last_error(__FILE__, __LINE__, "clf_bwd: workspace too small"); return SER_ERR_WORKSPACE; }
+
+  // ---- heads (fp32) ----
+  bool have_df = false;
+  if (d.dlogits != nullptr) {
+    SER_TRY(colsum(d.dlogits, 1, C, B, C, d.db_c, s));
+    SER_TRY(linear_wgrad(DT_F32, B, C, F, d.dlogits, C, d.f, F, d.dw_c, F, s));
+    SER_TRY(linear_dgrad(DT_F32, B, C, F, d.dlogits, C, d.w_c, F, df, F, 1, nullptr, 0, 1, GATE_NONE, nullptr, 0, 1, s));
+    have_df = true;
+  } else {
+    SER_CUDA_CHECK(cudaMemsetAsync(d.db_c, 0, sizeof(float) * C, s));
+    SER_CUDA_CHECK(cudaMemsetAsync(d.dw_c, 0, sizeof(float) * C * F, s));
+  }
+  if (d.dunc != nullptr && d.unc != nullptr) {
+    SER_TRY(sigmoid_bwd(d.dunc, d.unc, dsg, B, s));
+    SER_TRY(colsum(dsg, 1, 1, B, 1, d.db_u2, s));
+    SER_TRY(linear_wgrad(DT_F32, B, 1, U, dsg, 1, d.u1, U, d.dw_u2, U, s));
+    SER_TRY(linear_dgrad(DT_F32, B, 1, U, dsg, 1, d.w_u2, U, du1, U, 1, d.u1, U, 1, GATE_RELU, nullptr, 0, 1, s));
+    SER_TRY(colsum(du1, 1, U, B, U, d.db_u1, s));
+    SER_TRY(linear_wgrad(DT_F32, B, U, F, du1, U, d.f, F, d.dw_u1, F, s));
+    SER_TRY(linear_dgrad(DT_F32, B, U, F, du1, U, d.w_u1, F, df, F, 1, nullptr, 0, 1, GATE_NONE, have_df ? df : nullptr, F, 1, s));
+    have_df = true;
+  } else {
+    SER_CUDA_CHECK(cudaMemsetAsync(d.db_u2, 0, sizeof(float), s));
+    SER_CUDA_CHECK(cudaMemsetAsync(d.dw_u2, 0, sizeof(float) * U, s));
+    SER_CUDA_CHECK(cudaMemsetAsync(d.db_u1, 0, sizeof(float) * U, s));
+    SER_CUDA_CHECK(cudaMemsetAsync(d.dw_u1, 0, sizeof(float) * U * F, s));
+  }
+  // ---- output projection: relu(LN(q)) ----
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_out_g, 0, sizeof(float) * F, s));
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_out_b, 0, sizeof(float) * F, s));
+  SER_TRY(layernorm_bwd(df, 1, d.q, 1, d.stats_q, d.ln_out_g, d.ln_out_b, nullptr, 1, dq, f, nullptr, 1, d.dln_out_g,
+                        d.dln_out_b, B, F, 1, s));
+  SER_TRY(colsum(dq, f, F, B, F, d.db_out, s));
+  SER_TRY(linear_wgrad(dt, B, F, P, dq, F, d.h_last, P, d.dw_out, P, s));
+  SER_TRY(linear_dgrad(dt, B, F, P, dq, F, d.w_out, P, dh32, P, 1, nullptr, 0, 1, GATE_NONE, nullptr, 0, 1, s));
+  SER_TRY(cast_any(dh32, 1, dhT, f, static_cast<long long>(BP), s));
+  // ---- 35 residual blocks, last to first ----
+  for (int i = L - 1; i >= 0; --i) {
+    const float* hi = d.h + i * BP;
+    const float* yi = d.y + i * BP;
+    const void* ni = off(static_cast<const void*>(d.n), static_cast<long long>(i) * BP, dt);
+    const void* ri = off(static_cast<const void*>(d.r), static_cast<long long>(i) * BP, dt);
+    SER_TRY(colsum(dh32, 1, P, B, P, d.db2[i], s));
+    SER_TRY(linear_wgrad(dt, B, P, P, dhT, P, ri, P, d.dw2[i], P, s));
+    SER_TRY(linear_dgrad(dt, B, P, P, dhT, P, d.w2[i], P, drT, P, f, ri, P, f, GATE_RELU, nullptr, 0, 1, s));
+    SER_TRY(colsum(drT, f, P, B, P, d.db1[i], s));
+    SER_TRY(linear_wgrad(dt, B, P, P, drT, P, ni, P, d.dw1[i], P, s));
+    SER_TRY(linear_dgrad(dt, B, P, P, drT, P, d.w1[i], P, dn32, P, 1, nullptr, 0, 1, GATE_NONE, nullptr, 0, 1, s));
+    SER_CUDA_CHECK(cudaMemsetAsync(d.dlni_g[i], 0, sizeof(float) * P, s));
+    SER_CUDA_CHECK(cudaMemsetAsync(d.dlni_b[i], 0, sizeof(float) * P, s));
+    SER_CUDA_CHECK(cudaMemsetAsync(d.dlno_g[i], 0, sizeof(float) * P, s));
+    SER_CUDA_CHECK(cudaMemsetAsync(d.dlno_b[i], 0, sizeof(float) * P, s));
+    // dy = dh_next (skip) + LN_inner'(dn)
+    SER_TRY(layernorm_bwd(dn32, 1, yi, 1, d.stats_i + static_cast<size_t>(i) * B * 2, d.lni_g[i], d.lni_b[i], dh32, 1,
+                          dy32, 1, nullptr, 1, d.dlni_g[i], d.dlni_b[i], B, P, 0, s));
+    // dh_i = LN_outer'(dy)  (fp32 stream + act-dtype copy for the next GEMMs)
+    SER_TRY(layernorm_bwd(dy32, 1, hi, 1, d.stats_o + static_cast<size_t>(i) * B * 2, d.lno_g[i], d.lno_b[i], nullptr, 1,
+                          dh32, 1, dhT, f, d.dlno_g[i], d.dlno_b[i], B, P, 0, s));
+  }
+  // ---- input projection: h0 = relu(LN(p0)) ----
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_in_g, 0, sizeof(float) * P, s));
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_in_b, 0, sizeof(float) * P, s));
+  SER_TRY(layernorm_bwd(dh32, 1, d.p0, 1, d.stats0, d.ln_in_g, d.ln_in_b, nullptr, 1, dp0, f, nullptr, 1, d.dln_in_g,
+                        d.dln_in_b, B, P, 1, s));
+  SER_TRY(colsum(dp0, f, P, B, P, d.db_in, s));
+  SER_TRY(linear_wgrad(dt, B, P, P, dp0, P, d.x, P, d.dw_in, P, s));
+  if (d.dx != nullptr)
+    SER_TRY(linear_dgrad(dt, B, P, P, dp0, P, d.w_in, P, d.dx, P, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
+  return SER_OK;
+}
+
+}  // namespace ser

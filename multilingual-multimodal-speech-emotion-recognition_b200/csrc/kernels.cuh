@@ -1,0 +1,134 @@
+// Internal launch functions shared by the module-level orchestration (head_modules.cu) and api.cu.
+// Every function enqueues on `stream`, returns an SER_* code and never synchronises.
+#pragma once
+#include "common.cuh"
+
+namespace ser {
+
+// ---- elementwise.cu ------------------------------------------------------------------------------
+int cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t s);
+int cast_any(const void* src, int src_f32, void* dst, int dst_f32, long long n, cudaStream_t s);
+// out[n] (fp32) = sum_m X[m, n]           X: [M, N] with leading dim ld, fp32 or bf16
+int colsum(const void* X, int x_f32, long long ld, int M, int N, float* out, cudaStream_t s);
+// y = [relu](LayerNorm(x)); stats[m] = {mean, rstd}.  N % 8 == 0, N <= 1024.  eps = 1e-5.
+int layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, void* y2, int y2_f32, const float* gamma,
+                  const float* beta, float* stats, int M, int N, int relu, cudaStream_t s);
+// dx = LN'(dy) [+ add];  dgamma/dbeta accumulate (+=) into fp32 [N] buffers (caller zeroes them).
+// With relu != 0 the op was y = relu(LN(x)) and dy is masked by (LN(x) > 0) first.
+int layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const float* stats, const float* gamma,
+                  const float* beta, const void* add, int add_f32, void* dx, int dx_f32, void* dx2, int dx2_f32,
+                  float* dgamma, float* dbeta, int M, int N, int relu, cudaStream_t s);
+// ds = dy * y * (1 - y)    (sigmoid backward, fp32)
+int sigmoid_bwd(const float* dy, const float* y, float* ds, long long n, cudaStream_t s);
+
+// ---- attention.cu --------------------------------------------------------------------------------
+// Masked multi-head cross attention, heads packed along the feature axis (head h = columns [h*dh, (h+1)*dh)).
+//   Q: [B*Tq, *] ldq,  K/V: [B*Tk, *] ldk/ldv,  kmask: [B, Tk] float (0 = padded key) or NULL
+//   O: [B*Tq, H*dh] ldo,  lse: [B, H, Tq] fp32 (log-sum-exp of the scaled masked scores)
+struct AttnArgs {
+  int dtype;
+  int B, H, Tq, Tk, dh;
+  const void* Q; long long ldq;
+  const void* K; long long ldk;
+  const void* V; long long ldv;
+  const float* kmask;
+  void* O; long long ldo;
+  float* lse;
+  float scale;
+  // backward only
+  const void* dO; long long lddo;
+  void* dQ; long long lddq;
+  void* dK; long long lddk;
+  void* dV; long long lddv;
+  float* delta;             // [B, H, Tq] scratch: rowsum(dO * O)
+};
+int attention_fwd(const AttnArgs& a, cudaStream_t s);
+int attention_bwd(const AttnArgs& a, cudaStream_t s);
+
+// ---- pooling.cu ----------------------------------------------------------------------------------
+// Attentive statistics pooling, everything after the 768->128 tanh GEMM (src/models/pooling.py:21-28).
+struct AspArgs {
+  int dtype;
+  int B, T, D, Hd;           // D = 768, Hd = 128
+  const void* x;             // [B*T, D]
+  const void* u;             // [B*T, Hd] tanh(W1 x + b1)
+  const float* w2; const float* b2;   // [Hd], [1]
+  const float* mask;         // [B, T] or NULL
+  float* e;                  // [B, T] scratch scores
+  float* alpha;              // [B, T] softmax weights (saved)
+  void* out;                 // [B, 2*D] mean | std
+  int out_f32;
+  // backward
+  const void* dout; int dout_f32;   // [B, 2*D]
+  void* dx;                  // [B*T, D]  (statistics part; the scorer GEMM adds its part afterwards)
+  float* dalpha;             // [B, T] scratch (zeroed inside)
+  void* dpre;                // [B*T, Hd] gradient at the scorer pre-activation
+  float* dw2; float* db2;    // [Hd], [1] accumulate (+=)
+};
+int asp_fwd(const AspArgs& a, cudaStream_t s);
+int asp_bwd(const AspArgs& a, cudaStream_t s);
+
+// ---- fusion mix (fusion.py:21-25) ----------------------------------------------------------------
+struct MixArgs {
+  int dtype; int B, P, G;    // P = 512, G = 256
+  const void* pa; const void* pt;        // [B, P]
+  const void* ga; const void* gt;        // [B, G] relu(gate hidden)
+  const float* wga; const float* bga;    // [G], [1]
+  const float* wgt; const float* bgt;
+  float* gates;              // [B, 2] sigmoid outputs (wa, wt), saved
+  void* fused;               // [B, P]
+  // backward
+  const void* dfused;        // [B, P]
+  void* dpa; void* dpt;      // [B, P] direct part (gate path added by the GEMM afterwards)
+  void* dga; void* dgt;      // [B, G] gradient at the gate hidden pre-activation (already relu-masked)
+  float* dwga; float* dbga; float* dwgt; float* dbgt;   // accumulate (+=)
+};
+int fusion_mix_fwd(const MixArgs& a, cudaStream_t s);
+int fusion_mix_bwd(const MixArgs& a, cudaStream_t s);
+
+// ---- loss.cu -------------------------------------------------------------------------------------
+// Training loss terms of src/train.py:151-168 (a9, a10, a8, a11).  sums[] layout:
+enum : int {
+  LS_CE = 0, LS_FOCAL = 1, LS_UNC = 2 /* sum(unc) */, LS_CORRECT = 3 /* sum(correct) */, LS_POS = 4, LS_NEG = 5,
+  LS_COUNT = 8
+};
+struct LossArgs {
+  int B, C, D;                           // D = prototype dim (512)
+  long long B_global;                    // divisor of every mean (== B on one GPU)
+  const float* logits;                   // [B, C] fp32
+  const float* unc;                      // [B] fp32 or NULL
+  const void* emb; int emb_f32;          // [B, D] or NULL (prototype term off)
+  const float* protos;                   // [C, D]
+  const long long* labels;               // [B] int64
+  const float* counts;                   // [C] GLOBAL per-class counts as float, or NULL -> computed from labels
+  float smoothing, beta, gamma, margin;
+  int focal_use_weights;
+  float* class_w;                        // [C] scratch/out: normalised class weights
+  float* sums;                           // [LS_COUNT] raw local sums (fwd out; bwd in, possibly all-reduced)
+  // backward: loss = w_ce*ce + w_focal*focal + w_unc*mean(unc)*mean(correct) + w_proto*proto, scaled by gscale
+  float w_ce, w_focal, w_unc, w_proto;
+  float* dlogits;                        // [B, C]
+  float* dunc;                           // [B]
+  void* demb; int demb_f32;              // [B, D]
+  float* dprotos;                        // [C, D] accumulate (+=)
+};
+int loss_fwd(const LossArgs& a, cudaStream_t s);
+int loss_bwd(const LossArgs& a, cudaStream_t s);
+// same, with every gradient multiplied by the device scalar *gscale (autograd's grad_output); NULL = 1
+int loss_bwd_scaled(const LossArgs& a, const float* gscale, cudaStream_t s);
+// terms[6] = {ce, focal, unc_loss, proto, weighted total, accuracy}; non-finite terms -> 0
+int loss_finalize(const float* sums, long long B_global, float margin, float w_ce, float w_focal, float w_unc,
+                  float w_proto, int have_proto, float* terms, cudaStream_t s);
+
+// ---- eval.cu -------------------------------------------------------------------------------------
+// OpenMax re-scaling (classifier.py:240-275): logits_out = logits * (u > 0.3 ? 1 - 0.8u : 1)
+int openmax_fwd(const float* feats, const float* logits, const float* act_vecs, const float* w_alpha,
+                const float* w_beta, const float* w_tau, float* out, int B, int C, int F, cudaStream_t s);
+// TTA view mean + temperature + softmax / argmax / energy (eval.py:186-206, utils.py:12-14)
+int eval_post(const float* logits_views, int V, int B, int C, float temperature, float* mean_logits, float* probs,
+              long long* preds, float* energy, cudaStream_t s);
+// err[t] = mean_b | max softmax(logits/T_t) - [argmax == label] |   (eval.py:48-67)
+int temperature_sweep(const float* logits, const long long* labels, int B, int C, const float* temps, int nT,
+                      float* err, cudaStream_t s);
+
+}  // namespace ser

@@ -1,0 +1,347 @@
+// AttentiveStatsPooling (src/models/pooling.py:15-28) after the 768->128 tanh GEMM, and the gated
+// fusion mix (src/models/fusion.py:21-25).  These are the bandwidth-bound kernels of the head:
+// 128-bit loads, warp-shuffle / shared-memory reductions over time and feature axes, masks in-kernel.
+//
+// Pooling layout: x is [B, T, D] row-major.  The statistics kernels run one CTA per (sample, 64-column
+// slab): 8 lanes x 8 elements cover the slab width (128 B of bf16 per row), 32 row-groups walk T.
+// The weighted variance is the reference's two-pass form  sum_t a_t (x_t - mu)^2  (pooling.py:26).
+// A sample whose frames are all padded yields NaN (softmax over all -inf), as in the reference.
+#include "kernels.cuh"
+
+namespace ser {
+
+namespace {
+
+constexpr int SLAB = 64;      // columns per CTA
+constexpr int NTH = 256;      // threads: 8 column-lanes x 32 row-groups
+constexpr int RG = NTH / 8;   // row groups
+
+// e[b,t] = u[b,t,:] . w2 + b2 ; one warp per row (Hd = 128 -> 4 elements per lane)
+template <typename T>
+__global__ void __launch_bounds__(256)
+asp_score_kernel(const T* __restrict__ u, const float* __restrict__ w2, const float* __restrict__ b2,
+                 float* __restrict__ e, int M, int Hd) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float acc = 0.f;
+  for (int c = lane; c < Hd; c += 32) acc = fmaf(to_f32(u[static_cast<size_t>(row) * Hd + c]), w2[c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) e[row] = acc + b2[0];
+}
+
+// softmax over T of the masked scores of sample b into smem `sa` (all threads participate)
+__device__ __forceinline__ void softmax_row(const float* __restrict__ e, const float* __restrict__ mask, int T,
+                                            float* sa, float* red) {
+  float mx = -INFINITY;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float v = e[t];
+    if (mask != nullptr && mask[t] == 0.f) v = -INFINITY;
+    sa[t] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float p = expf(sa[t] - mx);      // all-masked: exp(-inf - -inf) = NaN, as torch.softmax
+    sa[t] = p;
+    sum += p;
+  }
+  sum = block_sum(sum, red);
+  const float inv = 1.f / sum;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) sa[t] *= inv;
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NTH)
+asp_stats_kernel(const T* __restrict__ x, const float* __restrict__ e, const float* __restrict__ mask,
+                 float* __restrict__ alpha, void* __restrict__ out, int out_f32, int Tlen, int D) {
+  extern __shared__ float smem[];
+  float* sa = smem;                      // [T]
+  float* red = sa + Tlen;                // [32]
+  float* part = red + 32;                // [RG][SLAB]
+  float* smean = part + RG * SLAB;       // [SLAB]
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * SLAB;
+  const int cl = (threadIdx.x & 7) * 8;  // column offset inside the slab
+  const int rg = threadIdx.x >> 3;
+  softmax_row(e + static_cast<size_t>(b) * Tlen, mask ? mask + static_cast<size_t>(b) * Tlen : nullptr, Tlen, sa, red);
+  if (blockIdx.x == 0 && alpha != nullptr)
+    for (int t = threadIdx.x; t < Tlen; t += blockDim.x) alpha[static_cast<size_t>(b) * Tlen + t] = sa[t];
+
+  const T* xb = x + static_cast<size_t>(b) * Tlen * D + c0 + cl;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int t = rg; t < Tlen; t += RG) {
+    float v[8];
+    load8(xb + static_cast<size_t>(t) * D, v);
+    const float a = sa[t];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, v[i], acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[rg * SLAB + cl + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < SLAB) {
+    float s = 0.f;
+    for (int r = 0; r < RG; ++r) s += part[r * SLAB + threadIdx.x];
+    smean[threadIdx.x] = s;
+  }
+  __syncthreads();
+  float mu[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mu[i] = smean[cl + i]; acc[i] = 0.f; }
+  for (int t = rg; t < Tlen; t += RG) {
+    float v[8];
+    load8(xb + static_cast<size_t>(t) * D, v);       // second pass: L2-resident slab
+    const float a = sa[t];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - mu[i]; acc[i] = fmaf(a * d, d, acc[i]); }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[rg * SLAB + cl + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < SLAB) {
+    float s = 0.f;
+    for (int r = 0; r < RG; ++r) s += part[r * SLAB + threadIdx.x];
+    const size_t o = static_cast<size_t>(b) * 2 * D + c0 + threadIdx.x;
+    st_dyn(out, o, out_f32, smean[threadIdx.x]);
+    st_dyn(out, o + D, out_f32, sqrtf(s + 1e-6f));
+  }
+}
+
+// backward, part A: per (sample, slab): dx_stats and partial dalpha
+template <typename T>
+__global__ void __launch_bounds__(NTH)
+asp_bwd_stats_kernel(const T* __restrict__ x, const float* __restrict__ alpha, const void* __restrict__ out,
+                     int out_f32, const void* __restrict__ dout, int dout_f32, T* __restrict__ dx,
+                     float* __restrict__ dalpha, int Tlen, int D) {
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * SLAB;
+  const int cl = (threadIdx.x & 7) * 8;
+  const int rg = threadIdx.x >> 3;
+  float mu[8], dmu[8], dvar[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const size_t o = static_cast<size_t>(b) * 2 * D + c0 + cl + i;
+    mu[i] = ld_dyn(out, o, out_f32);
+    const float sd = ld_dyn(out, o + D, out_f32);
+    dmu[i] = ld_dyn(dout, o, dout_f32);
+    dvar[i] = ld_dyn(dout, o + D, dout_f32) / (2.f * sd);
+  }
+  const size_t base = static_cast<size_t>(b) * Tlen * D + c0 + cl;
+  for (int t = rg; t < Tlen; t += RG) {
+    float v[8], g[8];
+    load8(x + base + static_cast<size_t>(t) * D, v);
+    const float a = alpha[static_cast<size_t>(b) * Tlen + t];
+    float da = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = v[i] - mu[i];
+      g[i] = a * (dmu[i] + 2.f * d * dvar[i]);
+      da = fmaf(v[i], dmu[i], da);
+      da = fmaf(d * d, dvar[i], da);
+    }
+    store8(dx + base + static_cast<size_t>(t) * D, g);
+    // reduce over the 8 column-lanes that share this row (lanes differ in the low 3 bits)
+    da += __shfl_xor_sync(0xffffffffu, da, 1);
+    da += __shfl_xor_sync(0xffffffffu, da, 2);
+    da += __shfl_xor_sync(0xffffffffu, da, 4);
+    if ((threadIdx.x & 7) == 0) atomicAdd(dalpha + static_cast<size_t>(b) * Tlen + t, da);
+  }
+}
+
+// backward, part B: softmax backward + scorer pre-activation gradient; one CTA per sample
+template <typename T>
+__global__ void __launch_bounds__(256)
+asp_bwd_score_kernel(const T* __restrict__ u, const float* __restrict__ w2, const float* __restrict__ alpha,
+                     const float* __restrict__ dalpha, T* __restrict__ dpre, float* __restrict__ dw2,
+                     float* __restrict__ db2, int Tlen, int Hd) {
+  extern __shared__ float smem[];
+  float* sde = smem;             // [T]
+  float* red = sde + Tlen;       // [32]
+  float* sw = red + 32;          // [Hd] local dw2
+  const int b = blockIdx.x;
+  const float* al = alpha + static_cast<size_t>(b) * Tlen;
+  const float* da = dalpha + static_cast<size_t>(b) * Tlen;
+  float dot = 0.f;
+  for (int t = threadIdx.x; t < Tlen; t += blockDim.x) {
+    const float a = al[t];
+    if (a != 0.f) dot = fmaf(a, da[t], dot);       // padded frames have alpha = 0 exactly
+  }
+  dot = block_sum(dot, red);
+  float dbl = 0.f;
+  for (int t = threadIdx.x; t < Tlen; t += blockDim.x) {
+    const float a = al[t];
+    const float de = (a != 0.f) ? a * (da[t] - dot) : 0.f;
+    sde[t] = de;
+    dbl += de;
+  }
+  for (int c = threadIdx.x; c < Hd; c += blockDim.x) sw[c] = 0.f;
+  dbl = block_sum(dbl, red);
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(db2, dbl);
+  // each thread owns one scorer column c and walks a strided set of rows
+  const int c = threadIdx.x % Hd;
+  const int rstep = blockDim.x / Hd;
+  float accw = 0.f;
+  const float wc = w2[c];
+  for (int t = threadIdx.x / Hd; t < Tlen; t += rstep) {
+    const size_t o = (static_cast<size_t>(b) * Tlen + t) * Hd + c;
+    const float uv = to_f32(u[o]);
+    const float de = sde[t];
+    dpre[o] = from_f32<T>(de * wc * (1.f - uv * uv));
+    accw = fmaf(de, uv, accw);
+  }
+  atomicAdd(&sw[c], accw);
+  __syncthreads();
+  for (int i = threadIdx.x; i < Hd; i += blockDim.x) atomicAdd(dw2 + i, sw[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// gated fusion mix: one warp per sample
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+mix_fwd_kernel(const T* __restrict__ pa, const T* __restrict__ pt, const T* __restrict__ ga, const T* __restrict__ gt,
+               const float* __restrict__ wga, const float* __restrict__ bga, const float* __restrict__ wgt,
+               const float* __restrict__ bgt, float* __restrict__ gates, T* __restrict__ fused, int B, int P, int G) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  float sa = 0.f, st = 0.f;
+  for (int c = lane; c < G; c += 32) {
+    sa = fmaf(to_f32(ga[static_cast<size_t>(row) * G + c]), wga[c], sa);
+    st = fmaf(to_f32(gt[static_cast<size_t>(row) * G + c]), wgt[c], st);
+  }
+  sa = warp_sum(sa) + bga[0];
+  st = warp_sum(st) + bgt[0];
+  const float wa = 1.f / (1.f + expf(-sa)), wt = 1.f / (1.f + expf(-st));
+  const float ws = wa + wt + 1e-8f;
+  const float na = wa / ws, nt = wt / ws;
+  if (lane == 0) { gates[2 * row] = wa; gates[2 * row + 1] = wt; }
+  for (int c = lane; c < P; c += 32) {
+    const size_t o = static_cast<size_t>(row) * P + c;
+    fused[o] = from_f32<T>(na * to_f32(pa[o]) + nt * to_f32(pt[o]));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+mix_bwd_kernel(const T* __restrict__ pa, const T* __restrict__ pt, const T* __restrict__ ga, const T* __restrict__ gt,
+               const float* __restrict__ wga, const float* __restrict__ wgt, const float* __restrict__ gates,
+               const T* __restrict__ dfused, T* __restrict__ dpa, T* __restrict__ dpt, T* __restrict__ dga,
+               T* __restrict__ dgt, float* __restrict__ dwga, float* __restrict__ dbga, float* __restrict__ dwgt,
+               float* __restrict__ dbgt, int B, int P, int G) {
+  extern __shared__ float smem[];       // [2*G + 2] block-local accumulation of gate-weight grads
+  for (int i = threadIdx.x; i < 2 * G + 2; i += blockDim.x) smem[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row < B) {
+    const float wa = gates[2 * row], wt = gates[2 * row + 1];
+    const float ws = wa + wt + 1e-8f;
+    const float na = wa / ws, nt = wt / ws;
+    float dna = 0.f, dnt = 0.f;
+    for (int c = lane; c < P; c += 32) {
+      const size_t o = static_cast<size_t>(row) * P + c;
+      const float g = to_f32(dfused[o]);
+      dna = fmaf(g, to_f32(pa[o]), dna);
+      dnt = fmaf(g, to_f32(pt[o]), dnt);
+      dpa[o] = from_f32<T>(na * g);
+      dpt[o] = from_f32<T>(nt * g);
+    }
+    dna = warp_sum(dna);
+    dnt = warp_sum(dnt);
+    const float inv2 = 1.f / (ws * ws);
+    const float dwa = dna * (ws - wa) * inv2 - dnt * wt * inv2;
+    const float dwt = dnt * (ws - wt) * inv2 - dna * wa * inv2;
+    const float dsa = dwa * wa * (1.f - wa), dst = dwt * wt * (1.f - wt);
+    for (int c = lane; c < G; c += 32) {
+      const size_t o = static_cast<size_t>(row) * G + c;
+      const float hav = to_f32(ga[o]), htv = to_f32(gt[o]);
+      dga[o] = from_f32<T>(hav > 0.f ? dsa * wga[c] : 0.f);
+      dgt[o] = from_f32<T>(htv > 0.f ? dst * wgt[c] : 0.f);
+      atomicAdd(&smem[c], dsa * hav);
+      atomicAdd(&smem[G + c], dst * htv);
+    }
+    if (lane == 0) { atomicAdd(&smem[2 * G], dsa); atomicAdd(&smem[2 * G + 1], dst); }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G; i += blockDim.x) { atomicAdd(dwga + i, smem[i]); atomicAdd(dwgt + i, smem[G + i]); }
+  if (threadIdx.x == 0) { atomicAdd(dbga, smem[2 * G]); atomicAdd(dbgt, smem[2 * G + 1]); }
+}
+
+template <typename T>
+int asp_fwd_impl(const AspArgs& a, cudaStream_t s) {
+  const int M = a.B * a.T;
+  asp_score_kernel<T><<<ceil_div(M, 8), 256, 0, s>>>(reinterpret_cast<const T*>(a.u), a.w2, a.b2, a.e, M, a.Hd);
+  SER_LAUNCH_CHECK();
+  const size_t smem = sizeof(float) * (a.T + 32 + RG * SLAB + SLAB);
+  auto kern = asp_stats_kernel<T>;
+  if (smem > 48 * 1024) SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3(a.D / SLAB, a.B), NTH, smem, s>>>(reinterpret_cast<const T*>(a.x), a.e, a.mask, a.alpha, a.out,
+                                                a.out_f32, a.T, a.D);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+template <typename T>
+int asp_bwd_impl(const AspArgs& a, cudaStream_t s) {
+  SER_CUDA_CHECK(cudaMemsetAsync(a.dalpha, 0, sizeof(float) * a.B * a.T, s));
+  asp_bwd_stats_kernel<T><<<dim3(a.D / SLAB, a.B), NTH, 0, s>>>(reinterpret_cast<const T*>(a.x), a.alpha, a.out,
+                                                                a.out_f32, a.dout, a.dout_f32,
+                                                                reinterpret_cast<T*>(a.dx), a.dalpha, a.T, a.D);
+  SER_LAUNCH_CHECK();
+  const size_t smem = sizeof(float) * (a.T + 32 + a.Hd);
+  auto kern = asp_bwd_score_kernel<T>;
+  if (smem > 48 * 1024) SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<a.B, 256, smem, s>>>(reinterpret_cast<const T*>(a.u), a.w2, a.alpha, a.dalpha, reinterpret_cast<T*>(a.dpre),
+                              a.dw2, a.db2, a.T, a.Hd);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+}  // namespace
+
+int asp_fwd(const AspArgs& a, cudaStream_t s) {
+  SER_REQUIRE(a.D % SLAB == 0, "asp: feature dim must be a multiple of 64");
+  SER_REQUIRE(a.Hd <= 256 && 256 % a.Hd == 0, "asp: scorer hidden dim must divide 256");
+  SER_REQUIRE(a.T > 0 && a.B > 0, "asp: empty input");
+  return a.dtype == DT_F32 ? asp_fwd_impl<float>(a, s) : asp_fwd_impl<__nv_bfloat16>(a, s);
+}
+int asp_bwd(const AspArgs& a, cudaStream_t s) {
+  SER_REQUIRE(a.D % SLAB == 0, "asp: feature dim must be a multiple of 64");
+  SER_REQUIRE(a.Hd <= 256 && 256 % a.Hd == 0, "asp: scorer hidden dim must divide 256");
+  return a.dtype == DT_F32 ? asp_bwd_impl<float>(a, s) : asp_bwd_impl<__nv_bfloat16>(a, s);
+}
+
+int fusion_mix_fwd(const MixArgs& a, cudaStream_t s) {
+#define SER_MIX_FWD(T)                                                                                             \
+  mix_fwd_kernel<T><<<ceil_div(a.B, 8), 256, 0, s>>>(                                                              \
+      reinterpret_cast<const T*>(a.pa), reinterpret_cast<const T*>(a.pt), reinterpret_cast<const T*>(a.ga),       \
+      reinterpret_cast<const T*>(a.gt), a.wga, a.bga, a.wgt, a.bgt, a.gates, reinterpret_cast<T*>(a.fused), a.B,  \
+      a.P, a.G)
+  if (a.dtype == DT_F32) SER_MIX_FWD(float); else SER_MIX_FWD(__nv_bfloat16);
+#undef SER_MIX_FWD
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+int fusion_mix_bwd(const MixArgs& a, cudaStream_t s) {
+  const size_t smem = sizeof(float) * (2 * a.G + 2);
+#define SER_MIX_BWD(T)                                                                                             \
+  mix_bwd_kernel<T><<<ceil_div(a.B, 8), 256, smem, s>>>(                                                           \
+      reinterpret_cast<const T*>(a.pa), reinterpret_cast<const T*>(a.pt), reinterpret_cast<const T*>(a.ga),       \
+      reinterpret_cast<const T*>(a.gt), a.wga, a.wgt, a.gates, reinterpret_cast<const T*>(a.dfused),              \
+      reinterpret_cast<T*>(a.dpa), reinterpret_cast<T*>(a.dpt), reinterpret_cast<T*>(a.dga),                      \
+      reinterpret_cast<T*>(a.dgt), a.dwga, a.dbga, a.dwgt, a.dbgt, a.B, a.P, a.G)
+  if (a.dtype == DT_F32) SER_MIX_BWD(float); else SER_MIX_BWD(__nv_bfloat16);
+#undef SER_MIX_BWD
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+}  // namespace ser

@@ -1,0 +1,578 @@
+"""torch.autograd.Function wrappers over the C-ABI (one per fused stage of the fusion head).
+
+Tier selection: float32 inputs run the CUDA-core fp32 tier (1e-4 parity with the reference), bfloat16
+inputs run the tcgen05 tensor-core tier (bf16 operands, fp32 accumulation / statistics / losses).
+Parameters are always the fp32 masters held by the drop-in nn.Modules; their gradients are fp32.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from ._params import FlatParams
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    return t.to(torch.float32).contiguous()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), device=device, dtype=torch.uint8)
+
+
+# --------------------------------------------------------------------------------------------------
+# a1 adapter
+# --------------------------------------------------------------------------------------------------
+class AdapterFn(torch.autograd.Function):
+    """y = [x +] W2 relu(W1 x + b1) + b2   (src/models/audio_encoder.py:19-21,112)."""
+
+    @staticmethod
+    def forward(ctx, x, fp: FlatParams, add_residual: bool, *params):
+        L.require_cuda(x)
+        dt = L.dtype_code(x.dtype)
+        wc = fp.compute_copy(x.dtype)
+        D = x.shape[-1]
+        x2 = x.reshape(-1, D).contiguous()
+        M = x2.shape[0]
+        w1 = fp.view(wc, "0.weight"); w2 = fp.view(wc, "2.weight")
+        S = w1.shape[0]
+        h = torch.empty(M, S, device=x.device, dtype=x.dtype)
+        y = torch.empty(M, D, device=x.device, dtype=x.dtype)
+        keep = []
+        d = L.fill(L.AdapterDesc(), keep, dtype=dt, M=M, D=D, S=S, add_residual=int(add_residual), x=x2, w1=w1,
+                   b1=fp.view(fp.flat, "0.bias"), w2=w2, b2=fp.view(fp.flat, "2.bias"), h=h, y=y)
+        L.call("ser_adapter_fwd", d, x.device)
+        ctx.save_for_backward(x2, h, w1, w2)
+        ctx.fp, ctx.add_residual, ctx.shape = fp, add_residual, x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, h, w1, w2 = ctx.saved_tensors
+        fp = ctx.fp
+        M, D = x2.shape
+        S = h.shape[1]
+        dy2 = dy.reshape(M, D).to(x2.dtype).contiguous()
+        g = fp.new_grad_buffer()
+        dh = torch.empty_like(h)
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        keep = []
+        d = L.fill(L.AdapterDesc(), keep, dtype=L.dtype_code(x2.dtype), M=M, D=D, S=S,
+                   add_residual=int(ctx.add_residual), x=x2, w1=w1, w2=w2, h=h, dy=dy2, dh=dh, dx=dx,
+                   dw1=fp.view(g, "0.weight"), db1=fp.view(g, "0.bias"), dw2=fp.view(g, "2.weight"),
+                   db2=fp.view(g, "2.bias"))
+        L.call("ser_adapter_bwd", d, x2.device)
+        return (dx.view(ctx.shape) if dx is not None else None, None, None, *fp.grads_from(g))
+
+
+# --------------------------------------------------------------------------------------------------
+# a2 cross-modal attention
+# --------------------------------------------------------------------------------------------------
+class CrossAttentionFn(torch.autograd.Function):
+    """CrossModalAttention.forward (src/models/cross_attention.py:32-53), dropout off."""
+
+    @staticmethod
+    def forward(ctx, a, t, a_mask, t_mask, fp: FlatParams, num_heads: int, *params):
+        L.require_cuda(a, t, a_mask, t_mask)
+        if a.dtype != t.dtype:
+            raise L.SerError("audio and text sequences must share a dtype")
+        dt = L.dtype_code(a.dtype)
+        wc = fp.compute_copy(a.dtype)
+        B, Ta, D = a.shape
+        Tt = t.shape[1]
+        S = fp.params[fp.index["q_a.weight"]].shape[0]
+        dev, ty = a.device, a.dtype
+        a2 = a.reshape(B * Ta, D).contiguous()
+        t2 = t.reshape(B * Tt, D).contiguous()
+        am, tm = _f32c(a_mask), _f32c(t_mask)
+        Ma, Mt = B * Ta, B * Tt
+        E = lambda *s: torch.empty(*s, device=dev, dtype=ty)           # noqa: E731
+        F = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        sv = dict(qkv_a=E(Ma, 3 * S), qkv_t=E(Mt, 3 * S), p_a=E(Ma, 3 * S), p_t=E(Mt, 3 * S), ctx_a=E(Ma, S),
+                  ctx_t=E(Mt, S), lse_a=F(B, num_heads, Ta), lse_t=F(B, num_heads, Tt), o_a=E(Ma, S), o_t=E(Mt, S),
+                  z_a=E(Ma, D), z_t=E(Mt, D), stats_a=F(Ma, 2), stats_t=F(Mt, 2))
+        enh_a, enh_t = E(Ma, D), E(Mt, D)
+        w = CrossAttentionFn._weights(fp, wc)
+        keep = []
+        d = L.fill(L.XattnDesc(), keep, dtype=dt, B=B, Ta=Ta, Tt=Tt, D=D, S=S, H=num_heads, a=a2, t=t2, a_mask=am,
+                   t_mask=tm, enh_a=enh_a, enh_t=enh_t, **w, **sv)
+        L.call("ser_xattn_fwd", d, dev)
+        ctx.save_for_backward(a2, t2, am, tm, wc, *sv.values())
+        ctx.sv_keys = list(sv.keys())
+        ctx.fp, ctx.dims = fp, (B, Ta, Tt, D, S, num_heads)
+        return enh_a.view(B, Ta, D), enh_t.view(B, Tt, D)
+
+    @staticmethod
+    def _weights(fp: FlatParams, wc: torch.Tensor):
+        f = fp.flat
+        return dict(
+            wqkv_a=fp.view(wc, "q_a.weight", 3), bqkv_a=fp.view(f, "q_a.bias", 3),
+            wqkv_t=fp.view(wc, "q_t.weight", 3), bqkv_t=fp.view(f, "q_t.bias", 3),
+            win_a=fp.view(wc, "attn_a.in_proj_weight"), bin_a=fp.view(f, "attn_a.in_proj_bias"),
+            win_t=fp.view(wc, "attn_t.in_proj_weight"), bin_t=fp.view(f, "attn_t.in_proj_bias"),
+            wo_a=fp.view(wc, "attn_a.out_proj.weight"), bo_a=fp.view(f, "attn_a.out_proj.bias"),
+            wo_t=fp.view(wc, "attn_t.out_proj.weight"), bo_t=fp.view(f, "attn_t.out_proj.bias"),
+            wout_a=fp.view(wc, "out_a.weight"), bout_a=fp.view(f, "out_a.bias"),
+            wout_t=fp.view(wc, "out_t.weight"), bout_t=fp.view(f, "out_t.bias"),
+            ln_a_g=fp.view(f, "norm_a.weight"), ln_a_b=fp.view(f, "norm_a.bias"),
+            ln_t_g=fp.view(f, "norm_t.weight"), ln_t_b=fp.view(f, "norm_t.bias"),
+        )
+
+    @staticmethod
+    def backward(ctx, d_enh_a, d_enh_t):
+        a2, t2, am, tm, wc, *svt = ctx.saved_tensors
+        sv = dict(zip(ctx.sv_keys, svt))
+        fp = ctx.fp
+        B, Ta, Tt, D, S, H = ctx.dims
+        dev, ty = a2.device, a2.dtype
+        dt = L.dtype_code(ty)
+        Ma, Mt = B * Ta, B * Tt
+        zero = lambda M: torch.zeros(M, D, device=dev, dtype=ty)   # noqa: E731
+        ga = d_enh_a.reshape(Ma, D).to(ty).contiguous() if d_enh_a is not None else zero(Ma)
+        gt = d_enh_t.reshape(Mt, D).to(ty).contiguous() if d_enh_t is not None else zero(Mt)
+        g = fp.new_grad_buffer()
+        da = torch.empty_like(a2)
+        dtt = torch.empty_like(t2)
+        lib = L.load()
+        ws = _ws(lib.ser_xattn_bwd_ws_bytes(dt, B, Ta, Tt, D, S, H), dev)
+        grads = dict(
+            dwqkv_a=fp.view(g, "q_a.weight", 3), dbqkv_a=fp.view(g, "q_a.bias", 3),
+            dwqkv_t=fp.view(g, "q_t.weight", 3), dbqkv_t=fp.view(g, "q_t.bias", 3),
+            dwin_a=fp.view(g, "attn_a.in_proj_weight"), dbin_a=fp.view(g, "attn_a.in_proj_bias"),
+            dwin_t=fp.view(g, "attn_t.in_proj_weight"), dbin_t=fp.view(g, "attn_t.in_proj_bias"),
+            dwo_a=fp.view(g, "attn_a.out_proj.weight"), dbo_a=fp.view(g, "attn_a.out_proj.bias"),
+            dwo_t=fp.view(g, "attn_t.out_proj.weight"), dbo_t=fp.view(g, "attn_t.out_proj.bias"),
+            dwout_a=fp.view(g, "out_a.weight"), dbout_a=fp.view(g, "out_a.bias"),
+            dwout_t=fp.view(g, "out_t.weight"), dbout_t=fp.view(g, "out_t.bias"),
+            dln_a_g=fp.view(g, "norm_a.weight"), dln_a_b=fp.view(g, "norm_a.bias"),
+            dln_t_g=fp.view(g, "norm_t.weight"), dln_t_b=fp.view(g, "norm_t.bias"),
+        )
+        keep = []
+        d = L.fill(L.XattnDesc(), keep, dtype=dt, B=B, Ta=Ta, Tt=Tt, D=D, S=S, H=H, a=a2, t=t2, a_mask=am, t_mask=tm,
+                   d_enh_a=ga, d_enh_t=gt, da=da, dt=dtt, ws=ws, ws_bytes=ws.numel(),
+                   **CrossAttentionFn._weights(fp, wc), **sv, **grads)
+        L.call("ser_xattn_bwd", d, dev)
+        return (da.view(B, Ta, D) if ctx.needs_input_grad[0] else None,
+                dtt.view(B, Tt, D) if ctx.needs_input_grad[1] else None,
+                None, None, None, None, *fp.grads_from(g))
+
+
+# --------------------------------------------------------------------------------------------------
+# a3 attentive statistics pooling
+# --------------------------------------------------------------------------------------------------
+class AttentiveStatsPoolingFn(torch.autograd.Function):
+    """AttentiveStatsPooling.forward (src/models/pooling.py:15-28)."""
+
+    @staticmethod
+    def forward(ctx, x, mask, fp: FlatParams, *params):
+        L.require_cuda(x, mask)
+        dt = L.dtype_code(x.dtype)
+        wc = fp.compute_copy(x.dtype)
+        B, T, D = x.shape
+        dev, ty = x.device, x.dtype
+        x2 = x.reshape(B * T, D).contiguous()
+        m = _f32c(mask)
+        w1 = fp.view(wc, "attention.0.weight")
+        Hd = w1.shape[0]
+        u = torch.empty(B * T, Hd, device=dev, dtype=ty)
+        e = torch.empty(B, T, device=dev, dtype=torch.float32)
+        alpha = torch.empty(B, T, device=dev, dtype=torch.float32)
+        out = torch.empty(B, 2 * D, device=dev, dtype=ty)
+        keep = []
+        d = L.fill(L.AspDesc(), keep, dtype=dt, B=B, T=T, D=D, Hd=Hd, x=x2, mask=m, w1=w1,
+                   b1=fp.view(fp.flat, "attention.0.bias"), w2=fp.view(fp.flat, "attention.2.weight"),
+                   b2=fp.view(fp.flat, "attention.2.bias"), u=u, e=e, alpha=alpha, out=out,
+                   out_f32=int(ty == torch.float32))
+        L.call("ser_asp_fwd", d, dev)
+        ctx.save_for_backward(x2, m, w1, u, alpha, out)
+        ctx.fp, ctx.dims = fp, (B, T, D, Hd)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, m, w1, u, alpha, out = ctx.saved_tensors
+        fp = ctx.fp
+        B, T, D, Hd = ctx.dims
+        dev, ty = x2.device, x2.dtype
+        dout = dout.to(ty).contiguous()
+        g = fp.new_grad_buffer()
+        dx = torch.empty_like(x2)
+        dpre = torch.empty_like(u)
+        dalpha = torch.empty(B, T, device=dev, dtype=torch.float32)
+        f32 = int(ty == torch.float32)
+        keep = []
+        d = L.fill(L.AspDesc(), keep, dtype=L.dtype_code(ty), B=B, T=T, D=D, Hd=Hd, x=x2, mask=m, w1=w1,
+                   w2=fp.view(fp.flat, "attention.2.weight"), b2=fp.view(fp.flat, "attention.2.bias"), u=u,
+                   alpha=alpha, out=out, out_f32=f32, dout=dout, dout_f32=f32, dx=dx, dpre=dpre, dalpha=dalpha,
+                   dw1=fp.view(g, "attention.0.weight"), db1=fp.view(g, "attention.0.bias"),
+                   dw2=fp.view(g, "attention.2.weight"), db2=fp.view(g, "attention.2.bias"))
+        L.call("ser_asp_bwd", d, dev)
+        return (dx.view(B, T, D) if ctx.needs_input_grad[0] else None, None, None, *fp.grads_from(g))
+
+
+# --------------------------------------------------------------------------------------------------
+# a4 gated fusion
+# --------------------------------------------------------------------------------------------------
+class FusionFn(torch.autograd.Function):
+    """FusionLayer.forward (src/models/fusion.py:18-25), dropout off."""
+
+    @staticmethod
+    def _weights(fp, wc):
+        f = fp.flat
+        out = {}
+        for m in ("a", "t"):
+            out[f"w1{m}"] = fp.view(wc, f"proj_{m}.0.weight"); out[f"b1{m}"] = fp.view(f, f"proj_{m}.0.bias")
+            out[f"w2{m}"] = fp.view(wc, f"proj_{m}.3.weight"); out[f"b2{m}"] = fp.view(f, f"proj_{m}.3.bias")
+            out[f"wg1{m}"] = fp.view(wc, f"gate_{m}.0.weight"); out[f"bg1{m}"] = fp.view(f, f"gate_{m}.0.bias")
+            out[f"wg2{m}"] = fp.view(f, f"gate_{m}.2.weight"); out[f"bg2{m}"] = fp.view(f, f"gate_{m}.2.bias")
+        return out
+
+    @staticmethod
+    def forward(ctx, av, tv, fp: FlatParams, *params):
+        L.require_cuda(av, tv)
+        dt = L.dtype_code(av.dtype)
+        wc = fp.compute_copy(av.dtype)
+        av2, tv2 = av.contiguous(), tv.to(av.dtype).contiguous()
+        B, Din = av2.shape
+        P = fp.params[fp.index["proj_a.0.weight"]].shape[0]
+        G = fp.params[fp.index["gate_a.0.weight"]].shape[0]
+        dev, ty = av.device, av.dtype
+        E = lambda *s: torch.empty(*s, device=dev, dtype=ty)   # noqa: E731
+        sv = dict(ha=E(B, P), ht=E(B, P), pa=E(B, P), pt=E(B, P), ga=E(B, G), gt=E(B, G),
+                  gates=torch.empty(B, 2, device=dev, dtype=torch.float32))
+        fused = E(B, P)
+        keep = []
+        d = L.fill(L.FusionDesc(), keep, dtype=dt, B=B, Din=Din, P=P, G=G, av=av2, tv=tv2, fused=fused,
+                   **FusionFn._weights(fp, wc), **sv)
+        L.call("ser_fusion_fwd", d, dev)
+        ctx.save_for_backward(av2, tv2, wc, *sv.values())
+        ctx.sv_keys = list(sv.keys())
+        ctx.fp, ctx.dims = fp, (B, Din, P, G)
+        return fused
+
+    @staticmethod
+    def backward(ctx, dfused):
+        av2, tv2, wc, *svt = ctx.saved_tensors
+        sv = dict(zip(ctx.sv_keys, svt))
+        fp = ctx.fp
+        B, Din, P, G = ctx.dims
+        dev, ty = av2.device, av2.dtype
+        dt = L.dtype_code(ty)
+        g = fp.new_grad_buffer()
+        dav, dtv = torch.empty_like(av2), torch.empty_like(tv2)
+        lib = L.load()
+        ws = _ws(lib.ser_fusion_bwd_ws_bytes(dt, B, Din, P, G), dev)
+        grads = {}
+        for m in ("a", "t"):
+            grads[f"dw1{m}"] = fp.view(g, f"proj_{m}.0.weight"); grads[f"db1{m}"] = fp.view(g, f"proj_{m}.0.bias")
+            grads[f"dw2{m}"] = fp.view(g, f"proj_{m}.3.weight"); grads[f"db2{m}"] = fp.view(g, f"proj_{m}.3.bias")
+            grads[f"dwg1{m}"] = fp.view(g, f"gate_{m}.0.weight"); grads[f"dbg1{m}"] = fp.view(g, f"gate_{m}.0.bias")
+            grads[f"dwg2{m}"] = fp.view(g, f"gate_{m}.2.weight"); grads[f"dbg2{m}"] = fp.view(g, f"gate_{m}.2.bias")
+        keep = []
+        d = L.fill(L.FusionDesc(), keep, dtype=dt, B=B, Din=Din, P=P, G=G, av=av2, tv=tv2,
+                   dfused=dfused.to(ty).contiguous(), dav=dav, dtv=dtv, ws=ws, ws_bytes=ws.numel(),
+                   **FusionFn._weights(fp, wc), **sv, **grads)
+        L.call("ser_fusion_bwd", d, dev)
+        return (dav if ctx.needs_input_grad[0] else None, dtv if ctx.needs_input_grad[1] else None, None,
+                *fp.grads_from(g))
+
+
+# --------------------------------------------------------------------------------------------------
+# a5 classifier stack + heads
+# --------------------------------------------------------------------------------------------------
+class ClassifierFn(torch.autograd.Function):
+    """AdvancedOpenMaxClassifier.forward up to (logits, uncertainty, features) -- classifier.py:200-229, dropout off.
+    Returns (logits [B,C] fp32, unc [B,1] fp32, features [B,256] fp32 (non-differentiable))."""
+
+    @staticmethod
+    def _weights(fp, wc, L_):
+        f = fp.flat
+        p = "deep_classifier."
+        blk = lambda i, k: f"{p}residual_layers.{i}.block.{k}"   # noqa: E731
+        return dict(
+            w_in=fp.view(wc, p + "input_projection.0.weight"), b_in=fp.view(f, p + "input_projection.0.bias"),
+            ln_in_g=fp.view(f, p + "input_projection.1.weight"), ln_in_b=fp.view(f, p + "input_projection.1.bias"),
+            w1=[fp.view(wc, blk(i, "1.weight")) for i in range(L_)], b1=[fp.view(f, blk(i, "1.bias")) for i in range(L_)],
+            w2=[fp.view(wc, blk(i, "4.weight")) for i in range(L_)], b2=[fp.view(f, blk(i, "4.bias")) for i in range(L_)],
+            lni_g=[fp.view(f, blk(i, "0.weight")) for i in range(L_)], lni_b=[fp.view(f, blk(i, "0.bias")) for i in range(L_)],
+            lno_g=[fp.view(f, f"{p}layer_norms.{i}.weight") for i in range(L_)],
+            lno_b=[fp.view(f, f"{p}layer_norms.{i}.bias") for i in range(L_)],
+            w_out=fp.view(wc, p + "output_projection.0.weight"), b_out=fp.view(f, p + "output_projection.0.bias"),
+            ln_out_g=fp.view(f, p + "output_projection.1.weight"), ln_out_b=fp.view(f, p + "output_projection.1.bias"),
+            w_c=fp.view(f, p + "output_projection.4.weight"), b_c=fp.view(f, p + "output_projection.4.bias"),
+            w_u1=fp.view(f, "uncertainty_head.0.weight"), b_u1=fp.view(f, "uncertainty_head.0.bias"),
+            w_u2=fp.view(f, "uncertainty_head.3.weight"), b_u2=fp.view(f, "uncertainty_head.3.bias"),
+        )
+
+    @staticmethod
+    def _grads(fp, g, L_):
+        p = "deep_classifier."
+        blk = lambda i, k: f"{p}residual_layers.{i}.block.{k}"   # noqa: E731
+        return dict(
+            dw_in=fp.view(g, p + "input_projection.0.weight"), db_in=fp.view(g, p + "input_projection.0.bias"),
+            dln_in_g=fp.view(g, p + "input_projection.1.weight"), dln_in_b=fp.view(g, p + "input_projection.1.bias"),
+            dw1=[fp.view(g, blk(i, "1.weight")) for i in range(L_)], db1=[fp.view(g, blk(i, "1.bias")) for i in range(L_)],
+            dw2=[fp.view(g, blk(i, "4.weight")) for i in range(L_)], db2=[fp.view(g, blk(i, "4.bias")) for i in range(L_)],
+            dlni_g=[fp.view(g, blk(i, "0.weight")) for i in range(L_)], dlni_b=[fp.view(g, blk(i, "0.bias")) for i in range(L_)],
+            dlno_g=[fp.view(g, f"{p}layer_norms.{i}.weight") for i in range(L_)],
+            dlno_b=[fp.view(g, f"{p}layer_norms.{i}.bias") for i in range(L_)],
+            dw_out=fp.view(g, p + "output_projection.0.weight"), db_out=fp.view(g, p + "output_projection.0.bias"),
+            dln_out_g=fp.view(g, p + "output_projection.1.weight"), dln_out_b=fp.view(g, p + "output_projection.1.bias"),
+            dw_c=fp.view(g, p + "output_projection.4.weight"), db_c=fp.view(g, p + "output_projection.4.bias"),
+            dw_u1=fp.view(g, "uncertainty_head.0.weight"), db_u1=fp.view(g, "uncertainty_head.0.bias"),
+            dw_u2=fp.view(g, "uncertainty_head.3.weight"), db_u2=fp.view(g, "uncertainty_head.3.bias"),
+        )
+
+    @staticmethod
+    def forward(ctx, x, fp: FlatParams, num_layers: int, want_unc: bool, *params):
+        L.require_cuda(x)
+        dt = L.dtype_code(x.dtype)
+        wc = fp.compute_copy(x.dtype)
+        x2 = x.contiguous()
+        B, P = x2.shape
+        p = "deep_classifier."
+        F_ = fp.params[fp.index[p + "output_projection.0.weight"]].shape[0]
+        C_ = fp.params[fp.index[p + "output_projection.4.weight"]].shape[0]
+        U = fp.params[fp.index["uncertainty_head.0.weight"]].shape[0]
+        Ln = num_layers
+        dev, ty = x.device, x.dtype
+        E = lambda *s: torch.empty(*s, device=dev, dtype=ty)             # noqa: E731
+        F = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
+        sv = dict(p0=F(B, P), stats0=F(B, 2), h=F(Ln + 1, B, P), y=F(Ln, B, P), n=E(Ln, B, P), r=E(Ln, B, P),
+                  stats_o=F(Ln, B, 2), stats_i=F(Ln, B, 2), h_last=E(B, P), q=F(B, F_), stats_q=F(B, 2), f=F(B, F_),
+                  u1=F(B, U), unc=F(B, 1))
+        logits = F(B, C_)
+        keep = []
+        d = L.fill(L.ClfDesc(), keep, dtype=dt, B=B, P=P, F=F_, C=C_, L=Ln, U=U, x=x2, logits=logits,
+                   **ClassifierFn._weights(fp, wc, Ln), **sv)
+        L.call("ser_clf_fwd", d, dev)
+        ctx.save_for_backward(x2, wc, *sv.values())
+        ctx.sv_keys = list(sv.keys())
+        ctx.fp, ctx.dims = fp, (B, P, F_, C_, Ln, U)
+        ctx.mark_non_differentiable(sv["f"])
+        return logits, sv["unc"], sv["f"]
+
+    @staticmethod
+    def backward(ctx, dlogits, dunc, _dfeat):
+        x2, wc, *svt = ctx.saved_tensors
+        sv = dict(zip(ctx.sv_keys, svt))
+        fp = ctx.fp
+        B, P, F_, C_, Ln, U = ctx.dims
+        dev, ty = x2.device, x2.dtype
+        dt = L.dtype_code(ty)
+        g = fp.new_grad_buffer()
+        dx = torch.empty_like(x2)
+        lib = L.load()
+        ws = _ws(lib.ser_clf_bwd_ws_bytes(dt, B, P, F_, C_, U), dev)
+        if dlogits is None and dunc is None:
+            dlogits = torch.zeros(B, C_, device=dev, dtype=torch.float32)
+        keep = []
+        d = L.fill(L.ClfDesc(), keep, dtype=dt, B=B, P=P, F=F_, C=C_, L=Ln, U=U, x=x2,
+                   dlogits=_f32c(dlogits), dunc=_f32c(dunc), dx=dx, ws=ws, ws_bytes=ws.numel(),
+                   **ClassifierFn._weights(fp, wc, Ln), **sv, **ClassifierFn._grads(fp, g, Ln))
+        L.call("ser_clf_bwd", d, dev)
+        grads = fp.grads_from(g)
+        # the anchor temperature never receives a gradient in the reference (.grad stays None)
+        ti = fp.index.get("anchor_clustering.temperature")
+        if ti is not None:
+            grads[ti] = None
+        return (dx if ctx.needs_input_grad[0] else None, None, None, None, *grads)
+
+
+# --------------------------------------------------------------------------------------------------
+# a8-a11 losses
+# --------------------------------------------------------------------------------------------------
+class HeadLossFn(torch.autograd.Function):
+    """w_ce*LabelSmoothingCE + w_focal*ClassBalancedFocal + w_unc*mean(unc)*mean(correct) + w_proto*prototype_loss.
+    Returns the 6-vector (ce, focal, unc_loss, proto, total, accuracy); only `total` (index 4) carries gradient.
+    (src/models/losses.py:12-30,41-64; src/models/prototypes.py:13-53; src/train.py:154-168)"""
+
+    @staticmethod
+    def forward(ctx, logits, unc, emb, protos, labels, cfg: dict):
+        L.require_cuda(logits, unc, emb, protos, labels)
+        dev = logits.device
+        lg = _f32c(logits)
+        B, C_ = lg.shape
+        un = _f32c(unc.reshape(-1)) if unc is not None else None
+        em = emb.contiguous() if emb is not None else None
+        pr = _f32c(protos) if protos is not None else None
+        lab = labels.to(torch.int64).contiguous()
+        counts = cfg.get("counts")
+        sums = torch.zeros(8, device=dev, dtype=torch.float32)
+        class_w = torch.empty(C_, device=dev, dtype=torch.float32)
+        terms = torch.zeros(6, device=dev, dtype=torch.float32)
+        keep = []
+        d = L.fill(L.LossDesc(), keep, B=B, C=C_, D=(em.shape[1] if em is not None else 0),
+                   B_global=int(cfg.get("B_global", B)), logits=lg, unc=un, emb=em,
+                   emb_f32=int(em is not None and em.dtype == torch.float32), protos=pr, labels=lab,
+                   counts=_f32c(counts) if counts is not None else None,
+                   smoothing=float(cfg.get("smoothing", 0.1)), beta=float(cfg.get("beta", 0.9999)),
+                   gamma=float(cfg.get("gamma", 2.0)), margin=float(cfg.get("margin", 0.5)),
+                   focal_use_weights=int(cfg.get("focal_use_weights", 1)), class_w=class_w, sums=sums,
+                   w_ce=float(cfg.get("w_ce", 0.0)), w_focal=float(cfg.get("w_focal", 0.0)),
+                   w_unc=float(cfg.get("w_unc", 0.0)), w_proto=float(cfg.get("w_proto", 0.0)), terms=terms)
+        L.call("ser_loss_fwd", d, dev)
+        reduce_fn = cfg.get("all_reduce")
+        if reduce_fn is not None:          # data-parallel: make the batch sums global before the guards
+            reduce_fn(sums)
+        L.call("ser_loss_finalize", d, dev)
+        ctx.save_for_backward(lg, un, em, pr, lab, class_w, sums)
+        ctx.cfg = dict(cfg)
+        ctx.shapes = (logits.shape, None if unc is None else unc.shape)
+        ctx.dtypes = (logits.dtype, None if unc is None else unc.dtype)
+        return terms
+
+    @staticmethod
+    def backward(ctx, dterms):
+        lg, un, em, pr, lab, class_w, sums = ctx.saved_tensors
+        cfg = ctx.cfg
+        dev = lg.device
+        B, C_ = lg.shape
+        gscale = dterms[4:5].to(torch.float32).contiguous()
+        dlogits = torch.empty_like(lg) if ctx.needs_input_grad[0] else None
+        dunc = torch.empty(B, device=dev, dtype=torch.float32) if (un is not None and ctx.needs_input_grad[1]) else None
+        demb = torch.empty_like(em) if (em is not None and ctx.needs_input_grad[2]) else None
+        dprotos = torch.zeros_like(pr) if (pr is not None and ctx.needs_input_grad[3]) else None
+        if demb is None and dprotos is not None:
+            demb = torch.empty_like(em)      # the kernel produces both in one pass
+        counts = cfg.get("counts")
+        keep = []
+        d = L.fill(L.LossDesc(), keep, B=B, C=C_, D=(em.shape[1] if em is not None else 0),
+                   B_global=int(cfg.get("B_global", B)), logits=lg, unc=un, emb=em,
+                   emb_f32=int(em is not None and em.dtype == torch.float32), protos=pr, labels=lab,
+                   counts=_f32c(counts) if counts is not None else None,
+                   smoothing=float(cfg.get("smoothing", 0.1)), beta=float(cfg.get("beta", 0.9999)),
+                   gamma=float(cfg.get("gamma", 2.0)), margin=float(cfg.get("margin", 0.5)),
+                   focal_use_weights=int(cfg.get("focal_use_weights", 1)), class_w=class_w, sums=sums,
+                   w_ce=float(cfg.get("w_ce", 0.0)), w_focal=float(cfg.get("w_focal", 0.0)),
+                   w_unc=float(cfg.get("w_unc", 0.0)), w_proto=float(cfg.get("w_proto", 0.0)),
+                   gscale=gscale, dlogits=dlogits, dunc=dunc, demb=demb,
+                   demb_f32=int(em is not None and em.dtype == torch.float32), dprotos=dprotos)
+        L.call("ser_loss_bwd", d, dev)
+        lshape, ushape = ctx.shapes
+        return (dlogits.view(lshape).to(ctx.dtypes[0]) if dlogits is not None else None,
+                dunc.view(ushape).to(ctx.dtypes[1]) if dunc is not None else None,
+                demb if ctx.needs_input_grad[2] else None, dprotos, None, None)
+
+
+# --------------------------------------------------------------------------------------------------
+# individually callable children (nn.Linear / nn.LayerNorm replacements used by src/train.py:221-236)
+# --------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        L.require_cuda(x, weight, bias)
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        if x2.dtype == torch.float32:
+            wc = weight.contiguous()
+        else:
+            wc = torch.empty(weight.shape, device=x.device, dtype=x.dtype)
+            lib = L.load()
+            L.check(lib.ser_cast(weight.contiguous().data_ptr(), 1, wc.data_ptr(), 0, weight.numel(),
+                                 L.stream_ptr(x.device)), "ser_cast")
+        y = L.gemm(x2, wc, bias=_f32c(bias))
+        ctx.save_for_backward(x2, wc)
+        ctx.has_bias = bias is not None
+        ctx.shape = x.shape
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wc = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).to(x2.dtype).contiguous()
+        dx = L.gemm(dy2, wc, b_trans=True) if ctx.needs_input_grad[0] else None
+        dw = L.gemm(dy2, x2, a_trans=True, b_trans=True, out_dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        db = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(dy2.shape[1], device=dy2.device, dtype=torch.float32)
+            lib = L.load()
+            L.check(lib.ser_colsum(dy2.data_ptr(), int(dy2.dtype == torch.float32), dy2.stride(0), dy2.shape[0],
+                                   dy2.shape[1], db.data_ptr(), L.stream_ptr(dy2.device)), "ser_colsum")
+        return (dx.view(ctx.shape) if dx is not None else None, dw, db)
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        L.require_cuda(x, weight, bias)
+        N = x.shape[-1]
+        x2 = x.reshape(-1, N).contiguous()
+        M = x2.shape[0]
+        y = torch.empty_like(x2)
+        stats = torch.empty(M, 2, device=x.device, dtype=torch.float32)
+        f32 = int(x2.dtype == torch.float32)
+        lib = L.load()
+        L.check(lib.ser_layernorm_fwd(x2.data_ptr(), f32, y.data_ptr(), f32, weight.data_ptr(), bias.data_ptr(),
+                                      stats.data_ptr(), M, N, 0, L.stream_ptr(x.device)), "ser_layernorm_fwd")
+        ctx.save_for_backward(x2, stats, weight, bias)
+        ctx.shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, stats, weight, bias = ctx.saved_tensors
+        M, N = x2.shape
+        dy2 = dy.reshape(M, N).to(x2.dtype).contiguous()
+        dx = torch.empty_like(x2)
+        dg = torch.empty(N, device=x2.device, dtype=torch.float32)
+        db = torch.empty(N, device=x2.device, dtype=torch.float32)
+        f32 = int(x2.dtype == torch.float32)
+        lib = L.load()
+        L.check(lib.ser_layernorm_bwd(dy2.data_ptr(), f32, x2.data_ptr(), f32, stats.data_ptr(), weight.data_ptr(),
+                                      bias.data_ptr(), dx.data_ptr(), f32, dg.data_ptr(), db.data_ptr(), M, N, 0,
+                                      L.stream_ptr(x2.device)), "ser_layernorm_bwd")
+        return dx.view(ctx.shape), dg, db
+
+
+# --------------------------------------------------------------------------------------------------
+# a7 / a12 inference post-processing (no autograd)
+# --------------------------------------------------------------------------------------------------
+def openmax(features, logits, activation_vectors, weibull_alpha, weibull_beta, weibull_tau):
+    L.require_cuda(features, logits)
+    f, lg = _f32c(features), _f32c(logits)
+    out = torch.empty_like(lg)
+    lib = L.load()
+    L.check(lib.ser_openmax_fwd(f.data_ptr(), lg.data_ptr(), _f32c(activation_vectors).data_ptr(),
+                                _f32c(weibull_alpha).data_ptr(), _f32c(weibull_beta).data_ptr(),
+                                _f32c(weibull_tau).data_ptr(), out.data_ptr(), lg.shape[0], lg.shape[1], f.shape[1],
+                                L.stream_ptr(lg.device)), "ser_openmax_fwd")
+    return out
+
+
+def eval_post(logits_views, temperature: float = 1.0):
+    """[V,B,C] (or [B,C]) logits -> dict(mean_logits, probs, preds, energy): TTA mean, /T, softmax, argmax, energy."""
+    L.require_cuda(logits_views)
+    lv = _f32c(logits_views if logits_views.dim() == 3 else logits_views.unsqueeze(0))
+    V, B, C_ = lv.shape
+    dev = lv.device
+    mean = torch.empty(B, C_, device=dev, dtype=torch.float32)
+    probs = torch.empty(B, C_, device=dev, dtype=torch.float32)
+    preds = torch.empty(B, device=dev, dtype=torch.int64)
+    energy = torch.empty(B, device=dev, dtype=torch.float32)
+    lib = L.load()
+    L.check(lib.ser_eval_post(lv.data_ptr(), V, B, C_, float(temperature), mean.data_ptr(), probs.data_ptr(),
+                              preds.data_ptr(), energy.data_ptr(), L.stream_ptr(dev)), "ser_eval_post")
+    return {"mean_logits": mean, "probs": probs, "preds": preds, "energy": energy}
+
+
+def find_optimal_temperature(val_logits, val_labels, temperatures=None) -> float:
+    """src/eval.py:48-67: the first temperature of logspace(-1, 2, 100) minimising mean|max prob - correct|."""
+    L.require_cuda(val_logits, val_labels)
+    lg = _f32c(val_logits)
+    lab = val_labels.to(torch.int64).contiguous()
+    dev = lg.device
+    temps = (torch.logspace(-1, 2, 100) if temperatures is None else temperatures).to(dev, torch.float32).contiguous()
+    err = torch.empty(temps.numel(), device=dev, dtype=torch.float32)
+    lib = L.load()
+    L.check(lib.ser_temperature_sweep(lg.data_ptr(), lab.data_ptr(), lg.shape[0], lg.shape[1], temps.data_ptr(),
+                                      temps.numel(), err.data_ptr(), L.stream_ptr(dev)), "ser_temperature_sweep")
+    err_h, temps_h = err.cpu(), temps.cpu()
+    best, best_t = float("inf"), 1.0
+    for e, t in zip(err_h.tolist(), temps_h.tolist()):     # strict '<' keeps the first minimum, as the reference
+        if e < best:
+            best, best_t = e, t
+    return best_t

@@ -1,0 +1,61 @@
+"""FusionHead: the reference's hand-wired call sequence (src/train.py:54-69 construction, :145-168 step) as
+one nn.Module over the drop-in modules.  This is the public entry point used by bench.py and the tests;
+the individual modules remain usable on their own exactly like the reference's."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from .functional import HeadLossFn
+from .models import (AdvancedOpenMaxClassifier, AttentiveStatsPooling, BottleneckAdapter, CrossModalAttention,
+                     FusionLayer, PrototypeMemory)
+
+
+class FusionHead(nn.Module):
+    def __init__(self, num_labels: int = 4, hidden: int = 768, shared_dim: int = 256, num_heads: int = 8,
+                 proj_dim: int = 512, num_layers: int = 35, dropout: float = 0.0):
+        super().__init__()
+        self.num_labels = num_labels
+        self.adapter_a = BottleneckAdapter(hidden, 256)
+        self.adapter_t = BottleneckAdapter(hidden, 256)
+        self.cross = CrossModalAttention(hidden, hidden, shared_dim=shared_dim, num_heads=num_heads, dropout=dropout)
+        self.pool_a = AttentiveStatsPooling(hidden)
+        self.pool_t = AttentiveStatsPooling(hidden)
+        self.fusion = FusionLayer(hidden * 2, hidden * 2, proj_dim)
+        self.classifier = AdvancedOpenMaxClassifier(input_dim=proj_dim, num_labels=num_labels, num_layers=num_layers,
+                                                    base_dim=proj_dim, dropout=dropout)
+        self.prototypes = PrototypeMemory(num_labels, proj_dim)
+        self.loss_weights = dict(w_ce=1.0, w_focal=0.3, w_unc=0.05, w_proto=0.01)   # train.py:156-168
+
+    GROUPS = ("adapter_a", "adapter_t", "cross", "pool_a", "pool_t", "fusion", "classifier", "prototypes")
+
+    def load_group_state(self, weights: Dict[str, Dict[str, torch.Tensor]]) -> None:
+        for k in self.GROUPS:
+            getattr(self, k).load_state_dict(weights[k], strict=True)
+
+    def features(self, a_hid, t_hid, a_mask=None, t_mask=None):
+        a_seq = self.adapter_a.residual_forward(a_hid)
+        t_seq = self.adapter_t.residual_forward(t_hid)
+        a_enh, t_enh = self.cross(a_seq, t_seq, a_mask, t_mask)
+        a_vec = self.pool_a(a_enh, a_mask)
+        t_vec = self.pool_t(t_enh, t_mask)
+        fused = self.fusion(a_vec, t_vec)
+        return dict(a_enh=a_enh, t_enh=t_enh, a_vec=a_vec, t_vec=t_vec, fused=fused)
+
+    def forward(self, a_hid: torch.Tensor, t_hid: torch.Tensor, a_mask: Optional[torch.Tensor] = None,
+                t_mask: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
+                loss_cfg: Optional[dict] = None) -> Dict[str, torch.Tensor]:
+        out = self.features(a_hid, t_hid, a_mask, t_mask)
+        if labels is None:
+            out["logits"] = self.classifier(out["fused"])
+            return out
+        logits, unc, anchor_loss = self.classifier(out["fused"], use_openmax=False, return_uncertainty=True)
+        cfg = dict(self.loss_weights)
+        if loss_cfg:
+            cfg.update(loss_cfg)
+        terms = HeadLossFn.apply(logits, unc, out["fused"], self.prototypes.prototypes, labels, cfg)
+        out.update(logits=logits, unc=unc, anchor=anchor_loss, ce=terms[0], focal=terms[1], unc_loss=terms[2],
+                   proto=terms[3], loss=terms[4] + 0.1 * anchor_loss, accuracy=terms[5])
+        return out

@@ -1,0 +1,36 @@
+"""Drop-in FusionLayer (reference: src/models/fusion.py:5-25): per-modality MLP projection to proj_dim and a
+normalised two-way sigmoid gate, executed by the fused fusion kernels."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .._params import FlatParams
+from ..functional import FusionFn
+from ._common import Linear, check_dropout
+
+
+def _mlp(din: int, dout: int) -> nn.Sequential:
+    # indices 0 and 3 hold the Linear layers, as in the reference state_dict (proj_*.0.*, proj_*.3.*)
+    return nn.Sequential(Linear(din, dout), nn.ReLU(), nn.Dropout(0.1), Linear(dout, dout))
+
+
+def _gate(d: int, hidden: int) -> nn.Sequential:
+    return nn.Sequential(Linear(d, hidden), nn.ReLU(), Linear(hidden, 1))
+
+
+class FusionLayer(nn.Module):
+    def __init__(self, audio_dim: int, text_dim: int, proj_dim: int):
+        super().__init__()
+        if audio_dim != text_dim:
+            raise ValueError("the fused kernel expects audio_dim == text_dim (both 2*768 in every reference script)")
+        self.proj_a = _mlp(audio_dim, proj_dim)
+        self.proj_t = _mlp(text_dim, proj_dim)
+        hidden = max(32, proj_dim // 2)
+        self.gate_a = _gate(proj_dim, hidden)
+        self.gate_t = _gate(proj_dim, hidden)
+        self._flat = FlatParams([(n, p) for n, p in self.named_parameters()])
+
+    def forward(self, audio_vec: torch.Tensor, text_vec: torch.Tensor) -> torch.Tensor:
+        check_dropout(self, 0.1, "FusionLayer")
+        return FusionFn.apply(audio_vec, text_vec, self._flat, *self._flat.params)

@@ -1,0 +1,35 @@
+"""Drop-in LabelSmoothingCrossEntropy and ClassBalancedFocalLoss (reference: src/models/losses.py:7-64)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from ..functional import HeadLossFn
+
+
+class LabelSmoothingCrossEntropy(nn.Module):
+    def __init__(self, smoothing: float = 0.1):
+        super().__init__()
+        self.smoothing = smoothing
+
+    def forward(self, logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        terms = HeadLossFn.apply(logits, None, None, None, target,
+                                 dict(w_ce=1.0, smoothing=self.smoothing, focal_use_weights=0))
+        return terms[4]
+
+
+class ClassBalancedFocalLoss(nn.Module):
+    def __init__(self, beta: float = 0.9999, gamma: float = 2.0, num_classes: Optional[int] = None):
+        super().__init__()
+        self.beta, self.gamma, self.num_classes = beta, gamma, num_classes
+        self.register_buffer("effective_num", torch.tensor(1.0))
+
+    def forward(self, logits: torch.Tensor, targets: torch.Tensor, class_counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`class_counts` (optional, [C]) overrides the per-batch bincount -- data-parallel callers pass the global one."""
+        cfg = dict(w_focal=1.0, beta=self.beta, gamma=self.gamma, focal_use_weights=int(self.num_classes is not None))
+        if class_counts is not None:
+            cfg["counts"] = class_counts
+        terms = HeadLossFn.apply(logits, None, None, None, targets, cfg)
+        return terms[4]
