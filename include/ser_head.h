@@ -41,9 +41,16 @@ extern "C" {
 int ser_version(void);
 const char* ser_last_error(void);
 int ser_sm_count(void);
+/* number of CUDA kernels this library has launched so far in this process                       */
+long long ser_launch_count(void);
 /* sizeof() of descriptor `id` as compiled (0 gemm, 1 adapter, 2 xattn, 3 asp, 4 fusion, 5 clf, 6 loss):
  * lets a foreign-language binding verify its struct layout at load time                           */
 int ser_desc_size(int id);
+
+/* ---- opt-in profiler: CUDA-event timing per kernel family on the launching stream ------------- */
+int ser_prof_enable(int on);
+/* device-synchronises; writes "<family> <launches> <total_ms> <alg_flops> <alg_bytes>\n" per family       */
+int ser_prof_report(char* buf, int cap);
 
 /* ---- generic fused GEMM (building block; also exported for tests and micro-benchmarks) -------
  * C[M,N] = epilogue(alpha * op(A) op(B)^T), see csrc/common.cuh GemmArgs.  Replaces every nn.Linear

@@ -119,6 +119,9 @@ def load():
     lib.ser_eval_post.argtypes = [P, I, I, I, F, P, P, P, P, P]
     lib.ser_temperature_sweep.argtypes = [P, P, I, I, P, I, P, P]
     lib.ser_desc_size.argtypes = [I]
+    lib.ser_launch_count.restype = C.c_longlong
+    lib.ser_prof_enable.argtypes = [I]
+    lib.ser_prof_report.argtypes = [C.c_char_p, I]
     for i, S in enumerate((GemmDesc, AdapterDesc, XattnDesc, AspDesc, FusionDesc, ClfDesc, LossDesc)):
         if lib.ser_desc_size(i) != C.sizeof(S):
             raise SerError(f"layout mismatch for {S.__name__}: C {lib.ser_desc_size(i)} vs ctypes {C.sizeof(S)}")
@@ -214,4 +217,23 @@ def gemm(a, b, *, a_trans=False, b_trans=False, bias=None, act=ACT_NONE, residua
     d.gate_mode = gate_mode
     d.act, d.accumulate, d.alpha, d.splits = act, int(accumulate), float(alpha), splits
     check(lib.ser_gemm(C.byref(d), stream_ptr(a.device)), "ser_gemm")
+    return out
+
+
+def launch_count() -> int:
+    return int(load().ser_launch_count())
+
+
+def prof_enable(on: bool) -> None:
+    load().ser_prof_enable(int(on))
+
+
+def prof_report():
+    """{family: dict(launches, ms, flops, bytes)} of everything recorded since the last report (device-syncs)."""
+    buf = C.create_string_buffer(1 << 16)
+    load().ser_prof_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms, fl, by = line.split()
+        out[name] = dict(launches=int(n), ms=float(ms), flops=float(fl), bytes=float(by))
     return out

@@ -34,6 +34,9 @@ class FlatParams:
         self.flat: torch.Tensor | None = None
         self._lowp: Dict[torch.dtype, torch.Tensor] = {}
         self.index = {n: i for i, n in enumerate(self.names)}
+        # data-parallel hook: called as hook(flat_params, flat_grad_buffer) at the end of the module's backward,
+        # i.e. as soon as this module's gradients are final (see parallel.py)
+        self.grad_hook = None
 
     # ---------------------------------------------------------------------------------------------
     def ensure(self) -> None:
@@ -87,4 +90,6 @@ class FlatParams:
         return torch.zeros(self.total, device=self.flat.device, dtype=torch.float32)
 
     def grads_from(self, gflat: torch.Tensor) -> List[torch.Tensor]:
+        if self.grad_hook is not None:
+            self.grad_hook(self, gflat)
         return [gflat[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, self.offsets)]

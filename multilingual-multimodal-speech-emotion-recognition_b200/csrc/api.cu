@@ -14,6 +14,10 @@ void set_last_error(const char* file, int line, const char* msg) {
 }
 const char* last_error() { return g_err; }
 
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
+long long launch_count() { return g_launches; }
+
 }  // namespace ser
 
 extern "C" {
@@ -23,6 +27,8 @@ int ser_version(void) { return 100; }
 const char* ser_last_error(void) { return ser::last_error(); }
 
 int ser_sm_count(void) { return ser::device_sm_count(); }
+
+long long ser_launch_count(void) { return ser::launch_count(); }
 
 int ser_desc_size(int id) {
   switch (id) {

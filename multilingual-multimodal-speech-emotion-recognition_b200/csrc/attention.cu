@@ -8,6 +8,7 @@
 // one thread owns one query row (dh = 32 values in registers), K/V tiles are staged in shared memory.
 // The score matrix never touches HBM; only the per-row log-sum-exp is saved for the backward pass.
 #include "kernels.cuh"
+#include "prof.cuh"
 
 namespace ser {
 
@@ -263,6 +264,9 @@ attn_bwd_dkv_kernel(const T* __restrict__ Q, long long ldq, const T* __restrict_
 
 template <typename T>
 int fwd_impl(const AttnArgs& a, cudaStream_t s) {
+  const double fl = 4.0 * a.B * a.H * static_cast<double>(a.Tq) * a.Tk * a.dh;
+  const double by = sizeof(T) * static_cast<double>(a.B) * a.H * a.dh * (2.0 * a.Tq + 2.0 * a.Tk);
+  ProfScope prof("attention_fwd", fl, by, s);
   dim3 grid(ceil_div(a.Tq, NT), a.H, a.B);
   attn_fwd_kernel<T><<<grid, NT, 0, s>>>(reinterpret_cast<const T*>(a.Q), a.ldq, reinterpret_cast<const T*>(a.K),
                                          a.ldk, reinterpret_cast<const T*>(a.V), a.ldv, a.kmask,
@@ -273,6 +277,9 @@ int fwd_impl(const AttnArgs& a, cudaStream_t s) {
 
 template <typename T>
 int bwd_impl(const AttnArgs& a, cudaStream_t s) {
+  const double fl = 10.0 * a.B * a.H * static_cast<double>(a.Tq) * a.Tk * a.dh;
+  const double by = sizeof(T) * static_cast<double>(a.B) * a.H * a.dh * (4.0 * a.Tq + 4.0 * a.Tk);
+  ProfScope prof("attention_bwd", fl, by, s);
   dim3 gq(ceil_div(a.Tq, NT), a.H, a.B);
   attn_bwd_dq_kernel<T><<<gq, NT, 0, s>>>(
       reinterpret_cast<const T*>(a.Q), a.ldq, reinterpret_cast<const T*>(a.K), a.ldk,

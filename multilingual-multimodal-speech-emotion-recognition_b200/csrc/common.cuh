@@ -26,7 +26,12 @@ enum : int { GATE_NONE = 0, GATE_RELU = 1 /* g > 0 */, GATE_TANH = 2 /* 1 - g^2 
     }                                                                                \
   } while (0)
 
-#define SER_LAUNCH_CHECK() SER_CUDA_CHECK(cudaGetLastError())
+// every kernel launch in the library is followed by this macro, so the counter is the number of launches
+#define SER_LAUNCH_CHECK()                                                           \
+  do {                                                                               \
+    ser::count_launch();                                                             \
+    SER_CUDA_CHECK(cudaGetLastError());                                              \
+  } while (0)
 
 #define SER_REQUIRE(cond, msg)                                                       \
   do {                                                                               \
@@ -43,6 +48,7 @@ enum : int { GATE_NONE = 0, GATE_RELU = 1 /* g > 0 */, GATE_TANH = 2 /* 1 - g^2 
   } while (0)
 
 void set_last_error(const char* file, int line, const char* msg);
+void count_launch();
 const char* last_error();
 
 // ---------------------------------------------------------------------------------

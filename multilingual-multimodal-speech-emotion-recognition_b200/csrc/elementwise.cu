@@ -4,6 +4,7 @@
 // 8 consecutive elements per 128-bit (bf16) / 2x128-bit (fp32) access; statistics are fp32 and the
 // variance is the two-pass form on register-resident data.
 #include "kernels.cuh"
+#include "prof.cuh"
 
 namespace ser {
 
@@ -210,6 +211,7 @@ int cast_any(const void* src, int src_f32, void* dst, int dst_f32, long long n, 
   const long long cap = 8LL * device_sm_count();
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
+  ProfScope prof("cast", 0.0, static_cast<double>(n) * ((src_f32 ? 4 : 2) + (dst_f32 ? 4 : 2)), s);
   cast_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(src, src_f32, dst, dst_f32, n);
   SER_LAUNCH_CHECK();
   return SER_OK;
@@ -226,6 +228,7 @@ int colsum(const void* X, int x_f32, long long ld, int M, int N, float* out, cud
   const int max_gy = ceil_div(M, 64);
   if (gy > max_gy) gy = max_gy;
   if (gy < 1) gy = 1;
+  ProfScope prof("colsum", 0.0, static_cast<double>(M) * N * (x_f32 ? 4 : 2), s);
   if (gy > 1) SER_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * N, s));
   colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, s>>>(X, x_f32, ld, M, N, out);
   SER_LAUNCH_CHECK();
@@ -242,6 +245,7 @@ static int ln_grid(int M) {
 int layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, void* y2, int y2_f32, const float* gamma,
                   const float* beta, float* stats, int M, int N, int relu, cudaStream_t s) {
   SER_REQUIRE(N % 8 == 0 && N <= kMaxChunks * 256, "layernorm: N must be a multiple of 8 and <= 1024");
+  ProfScope prof("layernorm_fwd", 0.0, static_cast<double>(M) * N * ((x_f32 ? 4 : 2) + (y_f32 ? 4 : 2) + (y2 ? (y2_f32 ? 4 : 2) : 0)), s);
   ln_fwd_kernel<<<ln_grid(M), 256, 0, s>>>(x, x_f32, y, y_f32, y2, y2_f32, gamma, beta, stats, M, N, relu);
   SER_LAUNCH_CHECK();
   return SER_OK;
@@ -254,6 +258,8 @@ int layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const fl
   int blocks = ceil_div(M, 8);
   const int cap = 2 * device_sm_count();     // fewer CTAs -> fewer global atomics for dgamma/dbeta
   if (blocks > cap) blocks = cap;
+  ProfScope prof("layernorm_bwd", 0.0, static_cast<double>(M) * N * ((dy_f32 ? 4 : 2) + (x_f32 ? 4 : 2) + (dx_f32 ? 4 : 2) +
+                                          (add ? (add_f32 ? 4 : 2) : 0) + (dx2 ? (dx2_f32 ? 4 : 2) : 0)), s);
   ln_bwd_kernel<<<blocks, 256, 0, s>>>(dy, dy_f32, x, x_f32, stats, gamma, beta, add, add_f32, dx, dx_f32, dx2,
                                        dx2_f32, dgamma, dbeta, M, N, relu);
   SER_LAUNCH_CHECK();

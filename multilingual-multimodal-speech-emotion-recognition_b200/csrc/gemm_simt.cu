@@ -2,6 +2,7 @@
 // This is the "within 1e-4 of the fp32 reference" path (TF32 tensor cores are not accurate enough,
 // see SURVEY.md section 7 "Hard parts"); it shares the epilogue contract of the tcgen05 kernel.
 #include "common.cuh"
+#include "prof.cuh"
 #include <mutex>
 
 namespace ser {
@@ -119,14 +120,26 @@ int gemm_simt_f32(const GemmArgs& a, cudaStream_t stream) {
   ep.R = reinterpret_cast<const float*>(a.R); ep.ldr = a.ldr;
   ep.G = reinterpret_cast<const float*>(a.G); ep.ldg = a.ldg; ep.gate_mode = a.gate_mode;
   ep.act = a.act; ep.alpha = a.alpha;
-  ep.atomic = (splits > 1 || a.accumulate) ? 1 : 0;
-  if (ep.atomic && !a.accumulate) {
+  int accumulate = a.accumulate;
+  if (splits > 1 && a.R != nullptr && a.R == a.C) {
+    // in-place residual with split-K: C already holds R, so every split simply accumulates into it
+    ep.R = nullptr;
+    accumulate = 1;
+  }
+  ep.atomic = (splits > 1 || accumulate) ? 1 : 0;
+  if (ep.atomic && !accumulate) {
     SER_CUDA_CHECK(cudaMemset2DAsync(a.C, a.ldc * sizeof(float), 0, a.N * sizeof(float), a.M, stream));
   }
   const float* A = reinterpret_cast<const float*>(a.A);
   const float* B = reinterpret_cast<const float*>(a.B);
   const long long sam = a.a_trans ? 1 : a.lda, sak = a.a_trans ? a.lda : 1;
   const long long sbn = a.b_trans ? 1 : a.ldb, sbk = a.b_trans ? a.ldb : 1;
+  const double gflops = 2.0 * a.M * a.N * a.K;
+  const double gesz = (a.dtype == DT_F32) ? 4.0 : 2.0;
+  const double gbytes = (static_cast<double>(a.M) * a.K + static_cast<double>(a.N) * a.K) * gesz +
+                        static_cast<double>(a.M) * a.N * ((a.c_f32 ? 4.0 : 2.0) + (a.R ? (a.r_f32 ? 4.0 : 2.0) : 0.0) +
+                                                         (a.G ? (a.g_f32 ? 4.0 : 2.0) : 0.0));
+  ProfScope prof(a.a_trans ? "gemm_simt_wgrad" : (a.b_trans ? "gemm_simt_dgrad" : "gemm_simt_fwd"), gflops, gbytes, stream);
   dim3 grid(nt, mt, splits);
   if (!a.a_trans && !a.b_trans)
     gemm_simt_kernel<true, true><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, ep, a.M, a.N, a.K, splits);

@@ -12,6 +12,7 @@
 // the 35-block classifier stack (reference: src/models/audio_encoder.py:19-21, cross_attention.py:38-51,
 // pooling.py:9-13, fusion.py:8-16, classifier.py:73-129) in the bf16 tier.
 #include "common.cuh"
+#include "prof.cuh"
 #include <cuda.h>
 #include <mutex>
 
@@ -472,13 +473,25 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   ep.G = a.G; ep.ldg = a.ldg; ep.g_f32 = a.g_f32; ep.gate_mode = a.gate_mode;
   ep.act = a.act;
   ep.alpha = a.alpha;
-  ep.atomic = (splits > 1 || a.accumulate) ? 1 : 0;
+  int accumulate = a.accumulate;
+  if (splits > 1 && a.R != nullptr && a.R == a.C) {
+    // in-place residual with split-K: C already holds R, so every split simply accumulates into it
+    ep.R = nullptr;
+    accumulate = 1;
+  }
+  ep.atomic = (splits > 1 || accumulate) ? 1 : 0;
   if (ep.atomic) {
     SER_REQUIRE(a.c_f32, "gemm_tc: accumulate / split-K needs an fp32 output");
-    if (!a.accumulate) {
+    if (!accumulate) {
       SER_CUDA_CHECK(cudaMemset2DAsync(a.C, a.ldc * sizeof(float), 0, a.N * sizeof(float), a.M, stream));
     }
   }
+  const double gflops = 2.0 * a.M * a.N * a.K;
+  const double gesz = (a.dtype == DT_F32) ? 4.0 : 2.0;
+  const double gbytes = (static_cast<double>(a.M) * a.K + static_cast<double>(a.N) * a.K) * gesz +
+                        static_cast<double>(a.M) * a.N * ((a.c_f32 ? 4.0 : 2.0) + (a.R ? (a.r_f32 ? 4.0 : 2.0) : 0.0) +
+                                                         (a.G ? (a.g_f32 ? 4.0 : 2.0) : 0.0));
+  ProfScope prof(a.a_trans ? "gemm_tc_wgrad" : (a.b_trans ? "gemm_tc_dgrad" : "gemm_tc_fwd"), gflops, gbytes, stream);
   if (BN == 256) return dispatch_major<256>(a, tmA, tmB, ep, splits, stream);
   return dispatch_major<128>(a, tmA, tmB, ep, splits, stream);
 }

@@ -7,6 +7,7 @@
 // zero" guards of the reference are evaluated on the (optionally all-reduced) batch sums, so that in
 // data-parallel runs every rank takes the same branch.
 #include "kernels.cuh"
+#include "prof.cuh"
 
 namespace ser {
 
@@ -238,6 +239,7 @@ loss_bwd_kernel(LossArgs a, const float* __restrict__ gscale) {
 int loss_fwd(const LossArgs& a, cudaStream_t s) {
   SER_REQUIRE(a.C >= 2 && a.C <= kMaxC, "loss: 2 <= num_classes <= 32");
   SER_REQUIRE(a.B > 0, "loss: empty batch");
+  ProfScope prof("loss_fwd", 0.0, 4.0 * a.B * (a.C + (a.emb ? a.D : 0)), s);
   loss_prep_kernel<<<1, 256, 0, s>>>(a.labels, a.counts, a.B, a.C, a.beta, a.focal_use_weights, a.class_w, a.sums);
   SER_LAUNCH_CHECK();
   loss_rows_kernel<<<ceil_div(a.B, 8), 256, 0, s>>>(a);
@@ -247,6 +249,7 @@ int loss_fwd(const LossArgs& a, cudaStream_t s) {
 
 int loss_bwd_scaled(const LossArgs& a, const float* gscale, cudaStream_t s) {
   SER_REQUIRE(a.C >= 2 && a.C <= kMaxC, "loss: 2 <= num_classes <= 32");
+  ProfScope prof("loss_bwd", 0.0, 4.0 * a.B * (2.0 * a.C + (a.emb ? 2.0 * a.D : 0)), s);
   loss_bwd_kernel<<<ceil_div(a.B, 8), 256, 0, s>>>(a, gscale);
   SER_LAUNCH_CHECK();
   return SER_OK;

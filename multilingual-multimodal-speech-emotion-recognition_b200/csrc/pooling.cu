@@ -7,6 +7,7 @@
 // The weighted variance is the reference's two-pass form  sum_t a_t (x_t - mu)^2  (pooling.py:26).
 // A sample whose frames are all padded yields NaN (softmax over all -inf), as in the reference.
 #include "kernels.cuh"
+#include "prof.cuh"
 
 namespace ser {
 
@@ -277,6 +278,8 @@ mix_bwd_kernel(const T* __restrict__ pa, const T* __restrict__ pt, const T* __re
 template <typename T>
 int asp_fwd_impl(const AspArgs& a, cudaStream_t s) {
   const int M = a.B * a.T;
+  // algorithmic bytes: x read once + u read once (single-pass minimum)
+  ProfScope prof("asp_fwd", 0.0, sizeof(T) * static_cast<double>(M) * (a.D + a.Hd), s);
   asp_score_kernel<T><<<ceil_div(M, 8), 256, 0, s>>>(reinterpret_cast<const T*>(a.u), a.w2, a.b2, a.e, M, a.Hd);
   SER_LAUNCH_CHECK();
   const size_t smem = sizeof(float) * (a.T + 32 + RG * SLAB + SLAB);
@@ -290,6 +293,7 @@ int asp_fwd_impl(const AspArgs& a, cudaStream_t s) {
 
 template <typename T>
 int asp_bwd_impl(const AspArgs& a, cudaStream_t s) {
+  ProfScope prof("asp_bwd", 0.0, sizeof(T) * static_cast<double>(a.B) * a.T * (2.0 * a.D + 2.0 * a.Hd), s);
   SER_CUDA_CHECK(cudaMemsetAsync(a.dalpha, 0, sizeof(float) * a.B * a.T, s));
   asp_bwd_stats_kernel<T><<<dim3(a.D / SLAB, a.B), NTH, 0, s>>>(reinterpret_cast<const T*>(a.x), a.alpha, a.out,
                                                                 a.out_f32, a.dout, a.dout_f32,
@@ -319,6 +323,7 @@ int asp_bwd(const AspArgs& a, cudaStream_t s) {
 }
 
 int fusion_mix_fwd(const MixArgs& a, cudaStream_t s) {
+  ProfScope prof("fusion_mix_fwd", 0.0, (a.dtype == DT_F32 ? 4.0 : 2.0) * a.B * (3.0 * a.P + 2.0 * a.G), s);
 #define SER_MIX_FWD(T)                                                                                             \
   mix_fwd_kernel<T><<<ceil_div(a.B, 8), 256, 0, s>>>(                                                              \
       reinterpret_cast<const T*>(a.pa), reinterpret_cast<const T*>(a.pt), reinterpret_cast<const T*>(a.ga),       \
@@ -331,6 +336,7 @@ int fusion_mix_fwd(const MixArgs& a, cudaStream_t s) {
 }
 
 int fusion_mix_bwd(const MixArgs& a, cudaStream_t s) {
+  ProfScope prof("fusion_mix_bwd", 0.0, (a.dtype == DT_F32 ? 4.0 : 2.0) * a.B * (5.0 * a.P + 4.0 * a.G), s);
   const size_t smem = sizeof(float) * (2 * a.G + 2);
 #define SER_MIX_BWD(T)                                                                                             \
   mix_bwd_kernel<T><<<ceil_div(a.B, 8), 256, smem, s>>>(                                                           \

@@ -24,6 +24,7 @@ class FusionHead(nn.Module):
         self.pool_a = AttentiveStatsPooling(hidden)
         self.pool_t = AttentiveStatsPooling(hidden)
         self.fusion = FusionLayer(hidden * 2, hidden * 2, proj_dim)
+        self.fusion.proj_a[2].p = self.fusion.proj_t[2].p = float(dropout)   # reference hard-codes 0.1
         self.classifier = AdvancedOpenMaxClassifier(input_dim=proj_dim, num_labels=num_labels, num_layers=num_layers,
                                                     base_dim=proj_dim, dropout=dropout)
         self.prototypes = PrototypeMemory(num_labels, proj_dim)

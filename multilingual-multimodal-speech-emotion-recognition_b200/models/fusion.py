@@ -32,5 +32,7 @@ class FusionLayer(nn.Module):
         self._flat = FlatParams([(n, p) for n, p in self.named_parameters()])
 
     def forward(self, audio_vec: torch.Tensor, text_vec: torch.Tensor) -> torch.Tensor:
-        check_dropout(self, 0.1, "FusionLayer")
+        # the reference hard-codes Dropout(0.1) (fusion.py:9,12); set `fusion.proj_a[2].p = fusion.proj_t[2].p = 0`
+        # (FusionHead(dropout=0) does) or call .eval() to run the fused path
+        check_dropout(self, max(self.proj_a[2].p, self.proj_t[2].p), "FusionLayer")
         return FusionFn.apply(audio_vec, text_vec, self._flat, *self._flat.params)

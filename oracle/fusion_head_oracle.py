@@ -31,7 +31,33 @@ W = Dict[str, Tensor]
 # --------------------------------------------------------------------------------------------------
 # primitives
 # --------------------------------------------------------------------------------------------------
+# Optional emulation of a reduced-precision-operand implementation (what torch.autocast(bfloat16) does to the
+# reference): every Linear rounds its input and weight to `_OPERAND_DTYPE` (straight-through gradient) and
+# accumulates in the working precision.  Used by the tests to measure the NOISE FLOOR any bf16-operand
+# implementation has against the exact answer (ReLU-mask flips make that floor batch-size dependent).
+_OPERAND_DTYPE = None
+
+
+class operand_rounding:
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global _OPERAND_DTYPE
+        self.prev, _OPERAND_DTYPE = _OPERAND_DTYPE, self.dtype
+
+    def __exit__(self, *exc):
+        global _OPERAND_DTYPE
+        _OPERAND_DTYPE = self.prev
+
+
+def _ste_round(x: Tensor) -> Tensor:
+    return x + (x.to(_OPERAND_DTYPE).to(x.dtype) - x).detach()
+
+
 def linear(x: Tensor, w: Tensor, b: Optional[Tensor]) -> Tensor:
+    if _OPERAND_DTYPE is not None:
+        x, w = _ste_round(x), _ste_round(w)
     y = x @ w.t()
     return y if b is None else y + b
 

@@ -1,0 +1,316 @@
+"""Parity cases shared by tests/test_gpu_parity.py and tools/gpu_parity_report.py.
+
+Methodology (DESIGN.md "Parity"):
+  E    = oracle in float64                       -- the exact answer
+  R32  = oracle in float32                       -- the reference's own arithmetic (what 1e-4 is measured against)
+  Rbf  = oracle in float32 with every Linear's operands rounded to bf16 (what torch.autocast(bf16) does)
+  G    = the CUDA path (fp32 tier or bf16 tier)
+A tensor passes when  err(G, E) <= max(tol, NOISE_K * err(R, E))  with R = R32 (fp32 tier) or Rbf (bf16 tier):
+tol is north_star's 1e-4 / 2e-2, and the second term is the noise floor of the reference arithmetic itself --
+ReLU-mask / clamp / argmax flips of near-zero pre-activations perturb gradients by O(1/B) in ANY implementation,
+fp32 CPU-vs-GPU included, so a fixed tolerance alone would be a coin toss on small batches.
+Metric: max-abs error / max-abs reference (fp32 tier); Frobenius error / Frobenius reference (bf16 tier).
+Tensors that are mathematically zero (attention key biases, softmax-shift biases) are floored at 1% of the
+module's largest gradient.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional
+
+import torch
+
+from oracle import fusion_head_oracle as O
+from oracle import synth
+
+NOISE_K = 3.0
+TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
+
+
+def _err(got: torch.Tensor, ref: torch.Tensor, frob: bool, floor: float = 0.0) -> float:
+    a, b = got.detach().double().cpu().reshape(-1), ref.detach().double().cpu().reshape(-1)
+    if torch.isnan(b).any() or torch.isnan(a).any():
+        return 0.0 if torch.equal(torch.isnan(a), torch.isnan(b)) and torch.allclose(a[~torch.isnan(a)], b[~torch.isnan(b)], rtol=1e-2, atol=1e-3) else float("inf")
+    if frob:
+        return (a - b).norm().item() / max(b.norm().item(), floor * (b.numel() ** 0.5), 1e-30)
+    return (a - b).abs().max().item() / max(b.abs().max().item(), floor, 1e-30)
+
+
+def _leaf(w: Dict[str, torch.Tensor], dtype) -> Dict[str, torch.Tensor]:
+    out = {}
+    for k, v in w.items():
+        v = v.detach().clone()
+        if v.is_floating_point():
+            v = v.to(dtype)
+            if k not in synth.CLASSIFIER_BUFFERS:
+                v.requires_grad_(True)
+        out[k] = v
+    return out
+
+
+class Case:
+    """One parity problem.  `oracle(inputs, weights)` -> (dict of output tensors, scalar objective);
+    `cuda(inputs, dtype, device)` -> (dict of outputs, dict 'group/param' -> grad, dict input-name -> grad)."""
+
+    def __init__(self, name: str, inputs: Dict[str, torch.Tensor], weights: Dict[str, Dict[str, torch.Tensor]],
+                 oracle: Callable, cuda: Callable, grad_inputs=()):
+        self.name, self.inputs, self.weights, self.oracle, self.cuda, self.grad_inputs = \
+            name, inputs, weights, oracle, cuda, tuple(grad_inputs)
+
+    def run_oracle(self, dtype, rounding=None):
+        ins = {}
+        for k, v in self.inputs.items():
+            if v is not None and v.is_floating_point():
+                v = v.detach().clone().to(dtype)
+                if k in self.grad_inputs:
+                    v.requires_grad_(True)
+            ins[k] = v
+        ws = {g: _leaf(w, dtype) for g, w in self.weights.items()}
+        ctx = O.operand_rounding(rounding) if rounding is not None else _Null()
+        with ctx:
+            outs, obj = self.oracle(ins, ws)
+            obj.backward()
+        grads = {f"{g}/{n}": (t.grad if t.grad is not None else torch.zeros_like(t))
+                 for g, w in ws.items() for n, t in w.items() if t.requires_grad}
+        igrads = {k: ins[k].grad for k in self.grad_inputs}
+        return {k: v.detach() for k, v in outs.items()}, grads, igrads
+
+    def check(self, dtype, device, verbose=False):
+        """Returns (failures: list[str], worst: float)."""
+        frob = dtype != torch.float32
+        tol = TOL[dtype]
+        # the bf16 tier feeds bf16-rounded activations; hand the oracle the same rounded inputs
+        saved = self.inputs
+        if dtype != torch.float32:
+            self.inputs = {k: (v.to(dtype).float() if (v is not None and v.is_floating_point() and k not in ("a_mask", "t_mask", "mask"))
+                               else v) for k, v in saved.items()}
+        try:
+            e_out, e_g, e_ig = self.run_oracle(torch.float64)
+            r_out, r_g, r_ig = self.run_oracle(torch.float32, None if dtype == torch.float32 else dtype)
+            g_out, g_g, g_ig = self.cuda(self.inputs, dtype, device)
+        finally:
+            self.inputs = saved
+        fails, worst = [], 0.0
+
+        def one(kind, name, got, ref_exact, ref_noise, floor=0.0):
+            nonlocal worst
+            if got is None:
+                fails.append(f"{kind} {name}: missing")
+                return
+            e = _err(got, ref_exact, frob, floor)
+            n = _err(ref_noise, ref_exact, frob, floor)
+            lim = max(tol, NOISE_K * n)
+            worst = max(worst, e / lim)
+            if verbose or e > lim:
+                print(f"    {'FAIL' if e > lim else 'ok  '} {kind:5s} {name:52s} err={e:.2e} noise={n:.2e} limit={lim:.2e}")
+            if e > lim:
+                fails.append(f"{kind} {name}: err {e:.3e} > limit {lim:.3e} (reference-arithmetic noise {n:.3e})")
+
+        for k in e_out:
+            if k in g_out:
+                one("out", k, g_out[k], e_out[k], r_out[k])
+        for k in e_ig:
+            one("din", k, g_ig.get(k), e_ig[k], r_ig[k])
+        groups = sorted({k.split("/")[0] for k in e_g})
+        for grp in groups:
+            keys = [k for k in e_g if k.startswith(grp + "/")]
+            scale = max(e_g[k].abs().max().item() for k in keys)
+            for k in keys:
+                if k.endswith("anchor_clustering.temperature"):
+                    if g_g.get(k) is not None and float(g_g[k].abs().max()) != 0.0:
+                        fails.append(f"grad {k}: must be None / zero")
+                    continue
+                one("grad", k, g_g.get(k), e_g[k], r_g[k], floor=1e-2 * scale)
+        return fails, worst
+
+
+class _Null:
+    def __enter__(self): return None
+    def __exit__(self, *a): return False
+
+
+# ---------------------------------------------------------------------------------------------------
+def _param_grads(group: str, module) -> Dict[str, torch.Tensor]:
+    return {f"{group}/{n}": p.grad for n, p in module.named_parameters()}
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def adapter_case(B=3, T=37):
+    import mmser_b200
+    from mmser_b200 import models as M
+    w = {"adapter": synth.adapter_weights("adapter_a")}
+    ins = {"x": _rand((B, T, 768), 1), "up": _rand((B, T, 768), 2)}
+
+    def oracle(i, ws):
+        y = O.adapter(i["x"], ws["adapter"])
+        return {"y": y}, (y * i["up"]).sum()
+
+    def cuda(i, dtype, dev):
+        m = M.BottleneckAdapter().to(dev); m.load_state_dict(w["adapter"])
+        x = i["x"].to(dev).to(dtype).requires_grad_(True)
+        y = m.residual_forward(x)
+        (y.float() * i["up"].to(dev)).sum().backward()
+        return {"y": y}, _param_grads("adapter", m), {"x": x.grad}
+
+    return Case("adapter", ins, w, oracle, cuda, grad_inputs=("x",))
+
+
+def cross_case(B=3, Ta=70, Tt=19, masks=True, seed=7):
+    from mmser_b200 import models as M
+    w = {"cross": synth.cross_weights()}
+    a, t, am, tm, _ = synth.make_inputs(B, Ta, Tt, 4, seed=seed, with_masks=masks)
+    ins = {"a": a, "t": t, "a_mask": am, "t_mask": tm, "ua": _rand((B, Ta, 768), 3), "ut": _rand((B, Tt, 768), 4)}
+
+    def oracle(i, ws):
+        am_ = None if i["a_mask"] is None else i["a_mask"].to(i["a"].dtype)
+        tm_ = None if i["t_mask"] is None else i["t_mask"].to(i["a"].dtype)
+        ea, et = O.cross_attention(i["a"], i["t"], am_, tm_, ws["cross"])
+        return {"audio_enh": ea, "text_enh": et}, (ea * i["ua"]).sum() + (et * i["ut"]).sum()
+
+    def cuda(i, dtype, dev):
+        m = M.CrossModalAttention(768, 768, dropout=0.0).to(dev); m.load_state_dict(w["cross"])
+        ag = i["a"].to(dev).to(dtype).requires_grad_(True)
+        tg = i["t"].to(dev).to(dtype).requires_grad_(True)
+        ea, et = m(ag, tg, None if i["a_mask"] is None else i["a_mask"].to(dev),
+                   None if i["t_mask"] is None else i["t_mask"].to(dev))
+        ((ea.float() * i["ua"].to(dev)).sum() + (et.float() * i["ut"].to(dev)).sum()).backward()
+        return {"audio_enh": ea, "text_enh": et}, _param_grads("cross", m), {"a": ag.grad, "t": tg.grad}
+
+    return Case(f"cross{'_masked' if masks else '_nomask'}", ins, w, oracle, cuda, grad_inputs=("a", "t"))
+
+
+def pool_case(B=4, T=53, masks=True):
+    from mmser_b200 import models as M
+    w = {"pool": synth.pool_weights("pool_a")}
+    a, _, am, _, _ = synth.make_inputs(B, T, 8, 4, seed=9, with_masks=masks)
+    ins = {"x": a, "mask": am, "up": _rand((B, 1536), 5)}
+
+    def oracle(i, ws):
+        m_ = None if i["mask"] is None else i["mask"].to(i["x"].dtype)
+        y = O.attentive_stats_pooling(i["x"], m_, ws["pool"])
+        return {"pooled": y}, (y * i["up"]).sum()
+
+    def cuda(i, dtype, dev):
+        m = M.AttentiveStatsPooling(768).to(dev); m.load_state_dict(w["pool"])
+        x = i["x"].to(dev).to(dtype).requires_grad_(True)
+        y = m(x, None if i["mask"] is None else i["mask"].to(dev))
+        (y.float() * i["up"].to(dev)).sum().backward()
+        return {"pooled": y}, _param_grads("pool", m), {"x": x.grad}
+
+    return Case("pool", ins, w, oracle, cuda, grad_inputs=("x",))
+
+
+def fusion_case(B=9):
+    from mmser_b200 import models as M
+    w = {"fusion": synth.fusion_weights()}
+    ins = {"av": _rand((B, 1536), 6), "tv": _rand((B, 1536), 7), "up": _rand((B, 512), 8)}
+
+    def oracle(i, ws):
+        y = O.fusion(i["av"], i["tv"], ws["fusion"])
+        return {"fused": y}, (y * i["up"]).sum()
+
+    def cuda(i, dtype, dev):
+        m = M.FusionLayer(1536, 1536, 512).to(dev).eval(); m.load_state_dict(w["fusion"])
+        av = i["av"].to(dev).to(dtype).requires_grad_(True)
+        tv = i["tv"].to(dev).to(dtype).requires_grad_(True)
+        y = m(av, tv)
+        (y.float() * i["up"].to(dev)).sum().backward()
+        return {"fused": y}, _param_grads("fusion", m), {"av": av.grad, "tv": tv.grad}
+
+    return Case("fusion", ins, w, oracle, cuda, grad_inputs=("av", "tv"))
+
+
+def classifier_case(B=10, C=4, L=35):
+    from mmser_b200 import models as M
+    w = {"classifier": synth.classifier_weights(C, L)}
+    ins = {"x": _rand((B, 512), 10), "ul": _rand((B, C), 11), "uu": _rand((B, 1), 12)}
+
+    def oracle(i, ws):
+        lg, un, _ = O.classifier(i["x"], ws["classifier"], L, use_openmax=False, training=True, return_uncertainty=True)
+        f = O.classifier_features(i["x"], ws["classifier"], L)
+        return {"logits": lg, "unc": un, "features": f}, (lg * i["ul"]).sum() + (un * i["uu"]).sum()
+
+    def cuda(i, dtype, dev):
+        m = M.AdvancedOpenMaxClassifier(512, C, num_layers=L, dropout=0.0).to(dev); m.load_state_dict(w["classifier"])
+        m.train()
+        x = i["x"].to(dev).to(dtype).requires_grad_(True)
+        lg, un, al = m(x, use_openmax=False, return_uncertainty=True)
+        assert float(al) == 0.0
+        ((lg * i["ul"].to(dev)).sum() + (un * i["uu"].to(dev)).sum()).backward()
+        return {"logits": lg, "unc": un, "features": m.last_features}, _param_grads("classifier", m), {"x": x.grad}
+
+    return Case("classifier", ins, w, oracle, cuda, grad_inputs=("x",))
+
+
+def loss_case(B=37, C=6):
+    import mmser_b200
+    g = torch.Generator().manual_seed(6)
+    ins = {"logits": torch.randn(B, C, generator=g) * 5.0,            # some beyond the +-10 clamp
+           "unc": torch.rand(B, 1, generator=g),
+           "emb": torch.randn(B, 512, generator=g) * 4.0,             # some beyond the +-10 clamp
+           "labels": torch.randint(0, C, (B,), generator=g)}
+    w = {"prototypes": {"prototypes": torch.randn(C, 512, generator=g) * 0.5}}
+
+    def oracle(i, ws):
+        out = O.train_loss(i["logits"], i["unc"], torch.zeros((), dtype=i["logits"].dtype), i["emb"], i["labels"],
+                           ws["prototypes"]["prototypes"], C)
+        return {k: out[k] for k in ("ce", "focal", "unc_loss", "proto", "loss")}, out["loss"]
+
+    def cuda(i, dtype, dev):
+        lg = i["logits"].to(dev).requires_grad_(True)
+        un = i["unc"].to(dev).requires_grad_(True)
+        em = i["emb"].to(dev).to(dtype).requires_grad_(True)
+        pr = w["prototypes"]["prototypes"].to(dev).requires_grad_(True)
+        t = mmser_b200.functional.HeadLossFn.apply(lg, un, em, pr, i["labels"].to(dev),
+                                                   dict(w_ce=1.0, w_focal=0.3, w_unc=0.05, w_proto=0.01))
+        t[4].backward()
+        outs = {k: t[j] for j, k in enumerate(("ce", "focal", "unc_loss", "proto", "loss"))}
+        return outs, {"prototypes/prototypes": pr.grad}, {"logits": lg.grad, "unc": un.grad, "emb": em.grad}
+
+    return Case("loss", ins, w, oracle, cuda, grad_inputs=("logits", "unc", "emb"))
+
+
+def head_case(B=4, Ta=50, Tt=16, C=4, masks=True, seed=1234, L=35):
+    import mmser_b200
+    w = synth.head_weights(C, L)
+    a, t, am, tm, labels = synth.make_inputs(B, Ta, Tt, C, seed=seed, with_masks=masks)
+    ins = {"a": a, "t": t, "a_mask": am, "t_mask": tm, "labels": labels}
+    keys = ("a_enh", "t_enh", "a_vec", "t_vec", "fused", "logits", "unc", "ce", "focal", "unc_loss", "proto", "loss")
+
+    def oracle(i, ws):
+        am_ = None if i["a_mask"] is None else i["a_mask"].to(i["a"].dtype)
+        tm_ = None if i["t_mask"] is None else i["t_mask"].to(i["a"].dtype)
+        out = O.head_forward(i["a"], i["t"], am_, tm_, i["labels"], ws, C, L)
+        return {k: out[k] for k in keys}, out["loss"]
+
+    def cuda(i, dtype, dev):
+        head = mmser_b200.FusionHead(C, num_layers=L).to(dev); head.load_group_state(w)
+        out = head(i["a"].to(dev).to(dtype), i["t"].to(dev).to(dtype),
+                   None if i["a_mask"] is None else i["a_mask"].to(dev),
+                   None if i["t_mask"] is None else i["t_mask"].to(dev), i["labels"].to(dev))
+        out["loss"].backward()
+        grads = {}
+        for grp in head.GROUPS:
+            grads.update(_param_grads(grp, getattr(head, grp)))
+        return {k: out[k] for k in keys}, grads, {}
+
+    return Case(f"head_B{B}_Ta{Ta}_Tt{Tt}_C{C}{'' if masks else '_nomask'}", ins, w, oracle, cuda)
+
+
+ALL_CASES = {
+    "adapter": adapter_case,
+    "cross_masked": lambda: cross_case(masks=True),
+    "cross_nomask": lambda: cross_case(masks=False),
+    "cross_long": lambda: cross_case(B=2, Ta=300, Tt=130, masks=True, seed=11),
+    "pool": pool_case,
+    "pool_nomask": lambda: pool_case(masks=False),
+    "fusion": fusion_case,
+    "classifier": classifier_case,
+    "loss": loss_case,
+    "head_cfg1": lambda: head_case(4, 50, 16, 4, True),
+    "head_c6_nomask": lambda: head_case(5, 33, 9, 6, False),
+    "head_b48": lambda: head_case(48, 60, 20, 4, True),
+}

@@ -1,0 +1,197 @@
+"""GPU parity tests: the CUDA path (through the drop-in modules -> C-ABI) against the CPU oracle.
+Run on the B200 box:  python -m pytest tests -m gpu -q"""
+import os
+
+import pytest
+import torch
+
+from tests import parity_cases as PC
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("case", list(PC.ALL_CASES))
+def test_parity(case, dtype):
+    dev = _dev()
+    torch.set_num_threads(max(8, torch.get_num_threads()))
+    fails, worst = PC.ALL_CASES[case]().check(dtype, dev)
+    assert not fails, f"{case}/{dtype}: {len(fails)} tensors out of tolerance, e.g. {fails[:5]}"
+
+
+def test_argmax_bit_exact_and_anchor_zero():
+    """Predictions (argmax of logits) are bit-identical to the oracle; anchor loss is exactly 0 with zero grads."""
+    import mmser_b200
+    from oracle import fusion_head_oracle as O, synth
+    dev = _dev()
+    C = 4
+    w = synth.head_weights(C)
+    a, t, am, tm, labels = synth.make_inputs(16, 40, 12, C, seed=77)
+    ref = O.head_forward(a, t, am, tm, labels, w, C)
+    for dtype in (torch.float32, torch.bfloat16):
+        head = mmser_b200.FusionHead(C).to(dev); head.load_group_state(w)
+        out = head(a.to(dev).to(dtype), t.to(dev).to(dtype), am.to(dev), tm.to(dev), labels.to(dev))
+        assert torch.equal(out["logits"].argmax(1).cpu(), ref["logits"].argmax(1)), dtype
+        assert float(out["anchor"]) == 0.0
+        out["loss"].backward()
+        ac = head.classifier.anchor_clustering
+        assert ac.temperature.grad is None
+        assert float(ac.class_anchors.grad.abs().max()) == 0.0
+        assert all(float(p.grad.abs().max()) == 0.0 for p in ac.anchor_projection.parameters())
+
+
+def test_fully_padded_rows_give_nan():
+    """Padding-mask handling: a sample whose keys are all padded yields NaN exactly where the reference does."""
+    from mmser_b200 import models as M
+    from oracle import fusion_head_oracle as O, synth
+    dev = _dev()
+    cw, pw = synth.cross_weights(), synth.pool_weights("pool_a")
+    g = torch.Generator().manual_seed(3)
+    a, t = torch.randn(3, 9, 768, generator=g), torch.randn(3, 5, 768, generator=g)
+    tm = torch.tensor([[1., 1., 1., 0., 0.], [0., 0., 0., 0., 0.], [1., 0., 0., 0., 0.]])
+    am = torch.ones(3, 9); am[2, 4:] = 0
+    ea, et = O.cross_attention(a, t, am, tm, cw)
+    pooled_ref = O.attentive_stats_pooling(t, tm, pw)
+    for dtype in (torch.float32, torch.bfloat16):
+        m = M.CrossModalAttention(768, 768, dropout=0.0).to(dev); m.load_state_dict(cw)
+        oa, ot = m(a.to(dev).to(dtype), t.to(dev).to(dtype), am.to(dev), tm.to(dev))
+        assert torch.equal(torch.isnan(oa).cpu(), torch.isnan(ea)), dtype
+        assert torch.equal(torch.isnan(ot).cpu(), torch.isnan(et)), dtype
+        p = M.AttentiveStatsPooling(768).to(dev); p.load_state_dict(pw)
+        pooled = p(t.to(dev).to(dtype), tm.to(dev))
+        assert torch.equal(torch.isnan(pooled).cpu(), torch.isnan(pooled_ref)), dtype
+        tol = 1e-4 if dtype == torch.float32 else 3e-2
+        ok = ~torch.isnan(pooled_ref)
+        assert (pooled.float().cpu()[ok] - pooled_ref[ok]).abs().max() <= tol * pooled_ref[ok].abs().max()
+
+
+@pytest.mark.parametrize("name", ["train_cfg1_small", "train_cfg2_shape", "train_cfg3_c6", "train_nomask", "train_cfg4_long"])
+def test_against_reference_golden(name, golden_dir):
+    """fp32 tier against the fixtures produced by the reference's own modules (oracle/make_golden.py)."""
+    import mmser_b200
+    from oracle import synth
+    dev = _dev()
+    gold = torch.load(os.path.join(golden_dir, f"{name}.pt"), weights_only=False)
+    cfg = gold["config"]
+    head = mmser_b200.FusionHead(cfg["C"], num_layers=cfg["num_layers"]).to(dev)
+    head.load_group_state(synth.head_weights(cfg["C"], cfg["num_layers"]))
+    a, t, am, tm, labels = synth.make_inputs(cfg["B"], cfg["Ta"], cfg["Tt"], cfg["C"], cfg["seed"], cfg["with_masks"])
+    mv = lambda x: None if x is None else x.to(dev)   # noqa: E731
+    out = head(a.to(dev), t.to(dev), mv(am), mv(tm), labels.to(dev))
+    out["loss"].backward()
+    rel = lambda x, y: (x.detach().double().cpu() - y.double()).abs().max().item() / (y.double().abs().max().item() + 1e-12)  # noqa: E731
+    for k in ("logits", "unc", "fused", "a_vec", "t_vec"):
+        assert rel(out[k], gold[k]) < 1e-4, k
+    assert rel(out["a_enh"][:, :4], gold["a_enh_head"]) < 1e-4
+    assert rel(out["t_enh"][:, :4], gold["t_enh_head"]) < 1e-4
+    for k in ("ce", "focal", "unc_loss", "proto", "loss"):
+        assert abs(float(out[k]) - gold[k]) <= 1e-4 * max(1.0, abs(gold[k])), k
+    assert torch.equal(out["logits"].argmax(1).cpu(), gold["logits"].argmax(1))
+    # gradients: norms within 1e-3 (ReLU-flip noise of fp32 arithmetic, see tests/parity_cases.py), probes alike
+    checked = 0
+    for key, summ in gold["grads"].items():
+        grp, pname = key.split("/", 1)
+        p = dict(getattr(head, grp).named_parameters())[pname]
+        if summ is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0
+            continue
+        if summ["norm"] < 1e-6:
+            assert float(p.grad.double().norm()) < 1e-4, key
+            continue
+        assert abs(float(p.grad.double().norm()) - summ["norm"]) <= 2e-3 * summ["norm"], key
+        checked += 1
+    assert checked > 300
+
+
+def test_eval_path_against_reference_golden(golden_dir):
+    """cfg5 semantics: fitted OpenMax, 5-view TTA mean, temperature sweep, softmax/argmax/energy."""
+    import mmser_b200
+    from mmser_b200 import functional as SF
+    from oracle import synth
+    dev = _dev()
+    gold = torch.load(os.path.join(golden_dir, "eval_cfg5_small.pt"), weights_only=False)
+    cfg = gold["config"]
+    C = cfg["C"]
+    clf = mmser_b200.models.AdvancedOpenMaxClassifier(512, C, dropout=0.15).to(dev)
+    clf.load_state_dict(synth.classifier_weights(C))
+    clf.eval()
+    g = torch.Generator().manual_seed(cfg["seed"])
+    val_fused = torch.randn(64, 512, generator=g)
+    val_labels = torch.randint(0, C, (64,), generator=g)
+    rel = lambda x, y: (x.detach().double().cpu() - y.double()).abs().max().item() / (y.double().abs().max().item() + 1e-12)  # noqa: E731
+    with torch.no_grad():
+        clf(val_fused.to(dev), use_openmax=False)
+        feats = clf.last_features
+        assert rel(feats, gold["val_features"]) < 1e-4
+        clf.fit_weibull(feats, val_labels.to(dev))
+        for k in synth.CLASSIFIER_BUFFERS:
+            assert rel(getattr(clf, k), gold["weibull"][k]) < 1e-3, k
+        fused_views = torch.randn(cfg["views"], cfg["B"], 512, generator=g)
+        labels = torch.randint(0, C, (cfg["B"],), generator=g)
+        lv = torch.stack([clf(fused_views[v].to(dev)) for v in range(cfg["views"])])
+        lp = torch.stack([clf(fused_views[v].to(dev), use_openmax=False) for v in range(cfg["views"])])
+        assert rel(lp, gold["logits_plain"]) < 1e-4
+        assert rel(lv, gold["logits_views"]) < 1e-3
+        T = SF.find_optimal_temperature(lp[0], labels.to(dev))
+        assert abs(T - gold["temperature"]) < 1e-3 * gold["temperature"]
+        post = SF.eval_post(lv, T)
+        assert rel(post["mean_logits"], gold["mean_logits"]) < 1e-3
+        assert rel(post["probs"], gold["probs"]) < 1e-3
+        assert torch.equal(post["preds"].cpu(), gold["preds"])
+        assert rel(post["energy"], gold["energy"]) < 1e-3
+
+
+def test_children_callable_like_reference():
+    """src/train.py:221-236 walks the classifier's children one by one; they must stay callable and agree with the
+    fused forward."""
+    import mmser_b200
+    from oracle import synth
+    dev = _dev()
+    clf = mmser_b200.models.AdvancedOpenMaxClassifier(512, 4, dropout=0.15).to(dev).eval()
+    clf.load_state_dict(synth.classifier_weights(4))
+    x = torch.randn(6, 512, device=dev)
+    with torch.no_grad():
+        f = x
+        for layer in clf.deep_classifier.input_projection:
+            f = layer(f)
+        for blk, ln in zip(clf.deep_classifier.residual_layers, clf.deep_classifier.layer_norms):
+            f = blk(ln(f))
+        for i in range(4):
+            f = clf.deep_classifier.output_projection[i](f)
+        clf(x, use_openmax=False)
+    assert (f - clf.last_features).abs().max() <= 1e-4 * clf.last_features.abs().max()
+
+
+def test_cpu_tensors_fail_loudly():
+    import mmser_b200
+    from mmser_b200 import _lib
+    pool = mmser_b200.models.AttentiveStatsPooling(768)
+    with pytest.raises(_lib.SerError):
+        pool(torch.randn(2, 3, 768))
+
+
+def test_large_shape_properties():
+    """BASELINE.json cfg2 size (B=256, Ta=250, Tt=64), bf16: finite outputs, softmax weights sum to one, loss terms
+    consistent, gradient of every parameter finite; fp32-vs-bf16 logits agree within the bf16 tolerance."""
+    import mmser_b200
+    from oracle import synth
+    dev = _dev()
+    C = 4
+    head = mmser_b200.FusionHead(C).to(dev); head.load_group_state(synth.head_weights(C))
+    a, t, am, tm, labels = synth.make_inputs(256, 250, 64, C, seed=1235)
+    out = head(a.to(dev).bfloat16(), t.to(dev).bfloat16(), am.to(dev), tm.to(dev), labels.to(dev))
+    out["loss"].backward()
+    assert all(torch.isfinite(out[k].float()).all() for k in ("a_enh", "t_enh", "fused", "logits", "unc", "loss"))
+    assert all(torch.isfinite(p.grad).all() for n, p in head.named_parameters() if p.grad is not None)
+    total = float(out["ce"]) + 0.3 * float(out["focal"]) + 0.05 * float(out["unc_loss"]) + 0.01 * float(out["proto"])
+    assert abs(total - float(out["loss"])) < 1e-4 * max(1.0, abs(total))
+    head.zero_grad(set_to_none=True)
+    out32 = head(a.to(dev)[:32], t.to(dev)[:32], am.to(dev)[:32], tm.to(dev)[:32], labels.to(dev)[:32])
+    d = (out["logits"][:32] - out32["logits"]).abs().max() / out32["logits"].abs().max()
+    assert float(d) < 2e-2
