@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- fusion-head training throughput (forward + backward incl. loss) on N B200s of one node.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5                 # our arm (bf16 tensor-core tier)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # data parallel, one rank per GPU
+  python bench.py --impl reference ...                            # the reference's CPU path (oracle port)
+
+One JSON line on stdout (rank 0).  metric = BASELINE.json's "fusion-head train samples/sec"; a step is one
+forward+backward of the whole head (adapters -> cross attention -> pooling -> fusion -> 35-block classifier ->
+loss) over one synthetic batch of the named shapes.  `value` times the step with inputs resident in HBM;
+`e2e` times the public API (FusionHead / DataParallelHead) with HOST (pinned) inputs, host->device copies and a
+device->host read of the loss inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1] / configs[2] (per-GPU batch 256) / configs[3]
+    "cfg2": dict(B=256, Ta=250, Tt=64, C=4, desc="fusion head fwd+bwd bf16: B=256/GPU, T_audio=250, T_text=64, 4 classes"),
+    "cfg3": dict(B=256, Ta=250, Tt=64, C=6, desc="CREMA-D shape DP step: 256/GPU, 6 classes"),
+    "cfg4": dict(B=128, Ta=1500, Tt=256, C=4, desc="long utterance: B=128/GPU, T_audio=1500, T_text=256"),
+    "cfg1": dict(B=8, Ta=250, Tt=64, C=4, desc="RAVDESS shape B=8"),
+}
+
+
+def fwd_flops_per_sample(Ta, Tt, C):
+    """algorithmic forward FLOPs (2*MAC) per sample."""
+    tok = (2 * (768 * 256 + 256 * 768) + 3 * 2 * 768 * 256 + 3 * 2 * 256 * 256 + 2 * 256 * 256 + 2 * 256 * 768 +
+           2 * (768 * 128 + 128) + 6 * 768)
+    return ((Ta + Tt) * tok + 4 * 2 * Ta * Tt * 256 + 2 * 2 * (1536 * 512 + 512 * 512) + 2 * 2 * (512 * 256 + 256) +
+            2 * 512 * 512 * 71 + 2 * 512 * 256 + 2 * 256 * C + 2 * 256 * 128 + 2 * 128 * C + 2 * 256 * 64 + 2 * 64)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            sm.sort()
+            out = dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_run(wl, steps, warmup, sample_B):
+    from oracle import fusion_head_oracle as O
+    from oracle import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    C = wl["C"]
+    w = synth.head_weights(C)
+    for grp in w.values():
+        for k, v in grp.items():
+            if v.is_floating_point() and k not in synth.CLASSIFIER_BUFFERS:
+                v.requires_grad_(True)
+    a, t, am, tm, labels = synth.make_inputs(sample_B, wl["Ta"], wl["Tt"], C, seed=1234)
+
+    def step():
+        for grp in w.values():
+            for v in grp.values():
+                v.grad = None
+        out = O.head_forward(a, t, am, tm, labels, w, C)
+        out["loss"].backward()
+        return float(out["loss"])
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=sample_B / dt, ms_per_step=dt * 1e3, cores=torch.get_num_threads(),
+                sample=f"{steps} fwd+bwd steps of B={sample_B} at (Ta={wl['Ta']}, Tt={wl['Tt']}, C={C}), fp32, "
+                       f"torch {torch.__version__} CPU")
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_B = min(wl["B"], 32)
+    steps = max(1, min(args.steps, 8))
+    r = cpu_reference_run(wl, steps, max(1, min(args.warmup, 2)), sample_B)
+    line = {
+        "impl": "reference", "metric": "fusion_head_train_samples_per_sec", "value": r["value"], "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "shape": wl["desc"], "sample_batch": sample_B},
+        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch.distributed as dist
+    import mmser_b200
+    from mmser_b200 import _lib as L
+    from mmser_b200.parallel import DataParallelHead
+    from oracle import synth          # synthetic weights/inputs only (shared generator); the oracle itself is not used here
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the fusion head has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+    peaks = load_peaks()
+    B, Ta, Tt, C = wl["B"], wl["Ta"], wl["Tt"], wl["C"]
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+
+    head = mmser_b200.FusionHead(C, dropout=0.0).to(dev)
+    head.load_group_state(synth.head_weights(C))
+    head.train()
+    dp = DataParallelHead(head)
+
+    # per-rank shard of the synthetic global batch (different seed per rank = different samples)
+    a, t, am, tm, labels = synth.make_inputs(B, Ta, Tt, C, seed=1234 + rank)
+    host = dict(a=a.to(dtype).pin_memory(), t=t.to(dtype).pin_memory(), am=am.pin_memory(), tm=tm.pin_memory(),
+                labels=labels.pin_memory())
+    devin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    torch.cuda.synchronize()
+
+    def step(inp):
+        return dp.train_step(inp["a"], inp["t"], inp["am"], inp["tm"], inp["labels"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    # ---------------- device-resident timing (value) ----------------
+    for _ in range(max(args.warmup, 3)):
+        out = step(devin)
+    barrier()
+    l0 = L.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = timed(lambda: step(devin), args.steps)
+    clocks = sampler.stop() if sampler else None
+    launches = (L.launch_count() - l0)
+    loss_val = float(out["loss"])
+
+    # ---------------- end-to-end through the public API with host buffers ----------------
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [dict(), dict()]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            for k, v in host.items():
+                bufs[i][k] = v.to(dev, non_blocking=True)
+            ready[i].record(copy_stream)
+
+    state = {"i": 0, "loss": 0.0}
+    prefetch(0)
+
+    def e2e_step():
+        i = state["i"]
+        torch.cuda.current_stream().wait_event(ready[i])
+        prefetch(1 - i)                                  # next step's host->device copy overlaps this step's compute
+        o = step(bufs[i])
+        state["loss"] = o["loss"].item()                 # device->host read of the step's result
+        state["i"] = 1 - i
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, max(3, args.steps // 2))
+
+    # ---------------- per-kernel-family profile (CUDA events around every launch; separate pass) ----------------
+    prof = {}
+    if rank == 0:
+        torch.cuda.synchronize()
+        L.prof_enable(True)
+        nprof = 3
+        for _ in range(nprof):
+            step(devin)
+        prof = L.prof_report()
+        L.prof_enable(False)
+        for v in prof.values():
+            v["ms_per_step"] = v["ms"] / nprof
+            v["launches_per_step"] = v["launches"] / nprof
+
+    # ---------------- cpu baseline (rank 0, N = 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(WORKLOADS["cfg1"] | {"C": C}, steps=6, warmup=1, sample_B=8)
+        cpu = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_B = B * world
+    value = total_B / (ms * 1e-3)
+    step_flops = 3.0 * fwd_flops_per_sample(Ta, Tt, C) * B             # per GPU, 3x-forward convention
+    # dominant kernel family = the tcgen05 GEMM (forward / dgrad / wgrad launches of gemm_tc_kernel)
+    fam = {k: v for k, v in prof.items() if k.startswith("gemm_tc")}
+    roof = None
+    if fam:
+        gflops = sum(v["flops"] for v in fam.values())
+        gms = sum(v["ms"] for v in fam.values())
+        ach = gflops / (gms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all fwd/dgrad/wgrad launches)",
+                "achieved": ach, "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sus"],
+                "traffic": None, "peak_source": peaks["src"] + " sustained bf16",
+                "launches_per_step": sum(v["launches_per_step"] for v in fam.values()),
+                "ms_per_step": sum(v["ms_per_step"] for v in fam.values())}
+    tot_prof_ms = sum(v["ms_per_step"] for v in prof.values()) or 1.0
+    families = {k: {"ms_per_step": round(v["ms_per_step"], 4), "launches_per_step": v["launches_per_step"],
+                    "share": round(v["ms_per_step"] / tot_prof_ms, 4),
+                    "tflops": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
+                    "gbs": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in sorted(prof.items())}
+    line = {
+        "metric": "fusion_head_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": args.workload, "shape": wl["desc"], "global_batch": total_B, "per_gpu_batch": B,
+                   "parallelism": f"dp{world}", "dropout": 0.0,
+                   "l2": "no explicit flush: one step touches > 2 GB of activations per GPU, far above the 126 MB L2"},
+        "step_model_flops_per_gpu": step_flops,
+        "model_tflops_per_gpu": step_flops / (ms * 1e-3) / 1e12,
+        "model_frac_of_sustained_bf16_peak": step_flops / (ms * 1e-3) / 1e12 / peaks["tf_sus"],
+        "roofline": roof, "kernel_families": families,
+        "cpu_baseline": cpu,
+        "e2e": {"value": total_B / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "api": "mmser_b200.parallel.DataParallelHead.train_step(FusionHead) with pinned host inputs"},
+        "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
+        "clocks": clocks, "loss": loss_val,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch > 0:
+        wl["B"] = args.batch
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -223,7 +223,7 @@ def fusion_case(B=9):
     return Case("fusion", ins, w, oracle, cuda, grad_inputs=("av", "tv"))
 
 
-def classifier_case(B=10, C=4, L=35):
+def classifier_case(B=64, C=4, L=35):
     from mmser_b200 import models as M
     w = {"classifier": synth.classifier_weights(C, L)}
     ins = {"x": _rand((B, 512), 10), "ul": _rand((B, C), 11), "uu": _rand((B, 1), 12)}
