@@ -220,7 +220,7 @@ def run_ours(args, wl):
     ms = timed(lambda: step(devin), args.steps)
     clocks = sampler.stop() if sampler else None
     launches = (L.launch_count() - l0)
-    loss_val = float(out["loss"])
+    loss_val = float(out["loss"].detach())
 
     # ---------------- end-to-end through the public API with host buffers ----------------
     copy_stream = torch.cuda.Stream(device=dev)
@@ -257,8 +257,18 @@ def run_ours(args, wl):
         nprof = 3
         for _ in range(nprof):
             step(devin)
-        prof = L.prof_report()
+        detail = L.prof_report()
         L.prof_enable(False)
+        if args.profile_detail:
+            with open(args.profile_detail, "w") as f:
+                for k, v in sorted(detail.items(), key=lambda kv: -kv[1]["ms"]):
+                    f.write(f"{k:44s} n/step={v['launches']/nprof:6.1f} ms/step={v['ms']/nprof:8.4f} us/launch={1e3*v['ms']/v['launches']:8.1f} "
+                            f"TFLOP/s={v['flops']/max(v['ms'],1e-9)/1e9:8.1f} GB/s={v['bytes']/max(v['ms'],1e-9)/1e6:8.1f}\n")
+        prof = {}
+        for k, v in detail.items():            # aggregate shape-tagged records per kernel family
+            fam = prof.setdefault(k.split(":")[0], dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            for kk in fam:
+                fam[kk] += v[kk]
         for v in prof.values():
             v["ms_per_step"] = v["ms"] / nprof
             v["launches_per_step"] = v["launches"] / nprof
@@ -327,6 +337,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-detail", default="", help="write the per-shape kernel table of the profiling pass here")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch > 0:

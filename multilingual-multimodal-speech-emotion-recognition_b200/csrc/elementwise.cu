@@ -56,6 +56,49 @@ __global__ void colsum_kernel(const void* __restrict__ X, int x_f32, long long l
   }
 }
 
+// vectorised variant: each lane owns 8 consecutive columns (one 128-bit load of bf16 / two of fp32), a warp spans
+// 256 columns, the 8 warps of a CTA walk rows 4 at a time (4 independent loads in flight per lane).
+// grid = (ceil(N/256), row_splits)
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const void* __restrict__ X, int x_f32, long long ld, int M, int N, float* __restrict__ out) {
+  __shared__ float red[8][256 + 8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (col < N) {
+    const int stride = gridDim.y * 8;
+    int m = blockIdx.y * 8 + w;
+    for (; m + 3 * stride < M; m += 4 * stride) {
+      float v0[8], v1[8], v2[8], v3[8];
+      load8_dyn(X, static_cast<size_t>(m) * ld + col, x_f32, v0);
+      load8_dyn(X, static_cast<size_t>(m + stride) * ld + col, x_f32, v1);
+      load8_dyn(X, static_cast<size_t>(m + 2 * stride) * ld + col, x_f32, v2);
+      load8_dyn(X, static_cast<size_t>(m + 3 * stride) * ld + col, x_f32, v3);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += (v0[i] + v1[i]) + (v2[i] + v3[i]);
+    }
+    for (; m < M; m += stride) {
+      float v0[8];
+      load8_dyn(X, static_cast<size_t>(m) * ld + col, x_f32, v0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v0[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[w][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;
+  const int n = blockIdx.x * 256 + c;
+  if (n < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += red[j][c];
+    if (gridDim.y == 1) out[n] = s; else atomicAdd(out + n, s);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const void* __restrict__ x, int x_f32, void* __restrict__ y, int y_f32, void* __restrict__ y2,
               int y2_f32, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -228,7 +271,9 @@ int colsum(const void* X, int x_f32, long long ld, int M, int N, float* out, cud
   const int max_gy = ceil_div(M, 64);
   if (gy > max_gy) gy = max_gy;
   if (gy < 1) gy = 1;
-  ProfScope prof("colsum", 0.0, static_cast<double>(M) * N * (x_f32 ? 4 : 2), s);
+  char pname[64];
+  if (prof_enabled()) snprintf(pname, sizeof(pname), "colsum:%dx%d", M, N);
+  ProfScope prof(pname, 0.0, static_cast<double>(M) * N * (x_f32 ? 4 : 2), s);
   if (gy > 1) SER_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * N, s));
   colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, s>>>(X, x_f32, ld, M, N, out);
   SER_LAUNCH_CHECK();
@@ -245,7 +290,9 @@ static int ln_grid(int M) {
 int layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, void* y2, int y2_f32, const float* gamma,
                   const float* beta, float* stats, int M, int N, int relu, cudaStream_t s) {
   SER_REQUIRE(N % 8 == 0 && N <= kMaxChunks * 256, "layernorm: N must be a multiple of 8 and <= 1024");
-  ProfScope prof("layernorm_fwd", 0.0, static_cast<double>(M) * N * ((x_f32 ? 4 : 2) + (y_f32 ? 4 : 2) + (y2 ? (y2_f32 ? 4 : 2) : 0)), s);
+  char pname[64];
+  if (prof_enabled()) snprintf(pname, sizeof(pname), "layernorm_fwd:%dx%d", M, N);
+  ProfScope prof(pname, 0.0, static_cast<double>(M) * N * ((x_f32 ? 4 : 2) + (y_f32 ? 4 : 2) + (y2 ? (y2_f32 ? 4 : 2) : 0)), s);
   ln_fwd_kernel<<<ln_grid(M), 256, 0, s>>>(x, x_f32, y, y_f32, y2, y2_f32, gamma, beta, stats, M, N, relu);
   SER_LAUNCH_CHECK();
   return SER_OK;
@@ -258,7 +305,9 @@ int layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const fl
   int blocks = ceil_div(M, 8);
   const int cap = 2 * device_sm_count();     // fewer CTAs -> fewer global atomics for dgamma/dbeta
   if (blocks > cap) blocks = cap;
-  ProfScope prof("layernorm_bwd", 0.0, static_cast<double>(M) * N * ((dy_f32 ? 4 : 2) + (x_f32 ? 4 : 2) + (dx_f32 ? 4 : 2) +
+  char pname[64];
+  if (prof_enabled()) snprintf(pname, sizeof(pname), "layernorm_bwd:%dx%d", M, N);
+  ProfScope prof(pname, 0.0, static_cast<double>(M) * N * ((dy_f32 ? 4 : 2) + (x_f32 ? 4 : 2) + (dx_f32 ? 4 : 2) +
                                           (add ? (add_f32 ? 4 : 2) : 0) + (dx2 ? (dx2_f32 ? 4 : 2) : 0)), s);
   ln_bwd_kernel<<<blocks, 256, 0, s>>>(dy, dy_f32, x, x_f32, stats, gamma, beta, add, add_f32, dx, dx_f32, dx2,
                                        dx2_f32, dgamma, dbeta, M, N, relu);

@@ -491,7 +491,11 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   const double gbytes = (static_cast<double>(a.M) * a.K + static_cast<double>(a.N) * a.K) * gesz +
                         static_cast<double>(a.M) * a.N * ((a.c_f32 ? 4.0 : 2.0) + (a.R ? (a.r_f32 ? 4.0 : 2.0) : 0.0) +
                                                          (a.G ? (a.g_f32 ? 4.0 : 2.0) : 0.0));
-  ProfScope prof(a.a_trans ? "gemm_tc_wgrad" : (a.b_trans ? "gemm_tc_dgrad" : "gemm_tc_fwd"), gflops, gbytes, stream);
+  char pname[96];
+  if (prof_enabled())
+    snprintf(pname, sizeof(pname), "%s:%dx%dx%d:s%d", a.a_trans ? "gemm_tc_wgrad" : (a.b_trans ? "gemm_tc_dgrad" : "gemm_tc_fwd"),
+             a.M, a.N, a.K, splits);
+  ProfScope prof(pname, gflops, gbytes, stream);
   if (BN == 256) return dispatch_major<256>(a, tmA, tmB, ep, splits, stream);
   return dispatch_major<128>(a, tmA, tmB, ep, splits, stream);
 }

@@ -26,13 +26,23 @@ NOISE_K = 3.0
 TOL = {torch.float32: 1e-4, torch.bfloat16: 2e-2}
 
 
-def _err(got: torch.Tensor, ref: torch.Tensor, frob: bool, floor: float = 0.0) -> float:
+OUTLIER_FRAC = 0.002      # gradients only: a ReLU-mask flip perturbs a handful of entries (one row of dW, one of db)
+
+
+def _err(got: torch.Tensor, ref: torch.Tensor, frob: bool, floor: float = 0.0, outliers: bool = False) -> float:
+    """fp32 tier: max-abs error / max-abs reference; with `outliers` the largest max(2, 0.2%) entries are set aside
+    (they must still be sane: the Frobenius error of the whole tensor is bounded separately by the caller).
+    bf16 tier: Frobenius error / Frobenius reference."""
     a, b = got.detach().double().cpu().reshape(-1), ref.detach().double().cpu().reshape(-1)
     if torch.isnan(b).any() or torch.isnan(a).any():
         return 0.0 if torch.equal(torch.isnan(a), torch.isnan(b)) and torch.allclose(a[~torch.isnan(a)], b[~torch.isnan(b)], rtol=1e-2, atol=1e-3) else float("inf")
     if frob:
         return (a - b).norm().item() / max(b.norm().item(), floor * (b.numel() ** 0.5), 1e-30)
-    return (a - b).abs().max().item() / max(b.abs().max().item(), floor, 1e-30)
+    d = (a - b).abs()
+    if outliers and d.numel() > 8:
+        k = max(2, int(OUTLIER_FRAC * d.numel()))
+        d = torch.topk(d, k + 1, largest=True).values[-1:]      # (k+1)-th largest
+    return d.max().item() / max(b.abs().max().item(), floor, 1e-30)
 
 
 def _leaf(w: Dict[str, torch.Tensor], dtype) -> Dict[str, torch.Tensor]:
@@ -96,9 +106,15 @@ class Case:
             if got is None:
                 fails.append(f"{kind} {name}: missing")
                 return
-            e = _err(got, ref_exact, frob, floor)
-            n = _err(ref_noise, ref_exact, frob, floor)
+            is_grad = kind != "out"
+            e = _err(got, ref_exact, frob, floor, outliers=is_grad)
+            n = _err(ref_noise, ref_exact, frob, floor, outliers=is_grad)
             lim = max(tol, NOISE_K * n)
+            if is_grad and not frob:
+                # the set-aside outliers must be flip-sized, not garbage: bound the whole tensor in Frobenius norm
+                ef = _err(got, ref_exact, True, floor)
+                if ef > 50 * lim:
+                    e = max(e, ef / 50)
             worst = max(worst, e / lim)
             if verbose or e > lim:
                 print(f"    {'FAIL' if e > lim else 'ok  '} {kind:5s} {name:52s} err={e:.2e} noise={n:.2e} limit={lim:.2e}")
