@@ -208,7 +208,7 @@ typedef struct ser_clf_desc {
   void* dx;                                /* [B,P] act                                           */
   float* dw_in; float* db_in; float* dln_in_g; float* dln_in_b;
   float* const* dw1; float* const* db1; float* const* dw2; float* const* db2;
-  float* const* dlno_g; float* const* dlno_b; float* const* dlni_g; float* const* dlni_b;
+  float* const* dlno_g; float* const* dlno_b; float* const* dlni_g; float* const* dlni_b;  /* ACCUMULATED: pass zeroed */
   float* dw_out; float* db_out; float* dln_out_g; float* dln_out_b;
   float* dw_c; float* db_c; float* dw_u1; float* db_u1; float* dw_u2; float* db_u2;
   void* ws; size_t ws_bytes;               /* ser_clf_bwd_ws_bytes()                              */

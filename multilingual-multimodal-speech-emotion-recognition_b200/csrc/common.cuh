@@ -181,6 +181,9 @@ struct GemmArgs {
   int accumulate = 0;            // C += (fp32 C only)
   float alpha = 1.f;
   int splits = 0;                // 0 = choose automatically
+  // batched GEMM: `batch` independent problems, operand / output b at base + b * stride (elements)
+  int batch = 1;
+  long long strideA = 0, strideB = 0, strideC = 0, strideR = 0, strideG = 0;
 };
 
 int gemm(const GemmArgs& a, cudaStream_t stream);

@@ -60,8 +60,12 @@ __global__ void colsum_kernel(const void* __restrict__ X, int x_f32, long long l
 // 256 columns, the 8 warps of a CTA walk rows 4 at a time (4 independent loads in flight per lane).
 // grid = (ceil(N/256), row_splits)
 __global__ void __launch_bounds__(256)
-colsum_vec_kernel(const void* __restrict__ X, int x_f32, long long ld, int M, int N, float* __restrict__ out) {
+colsum_vec_kernel(const void* __restrict__ X0, int x_f32, long long ld, int M, int N, float* __restrict__ out0,
+                  long long strideX, long long strideOut) {
   __shared__ float red[8][256 + 8];
+  const void* X = x_f32 ? static_cast<const void*>(reinterpret_cast<const float*>(X0) + blockIdx.z * strideX)
+                        : static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(X0) + blockIdx.z * strideX);
+  float* out = out0 + blockIdx.z * strideOut;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
   float acc[8];
@@ -238,6 +242,181 @@ ln_bwd_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Classifier block prologue: y = LN_outer(h); n = LN_inner(y)   (classifier.py:207-212 + :80), one pass over h.
+// fp32 residual stream in / out, n in the tier's dtype (GEMM operand).  One warp per row.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ln2_fwd_kernel(const float* __restrict__ h, float* __restrict__ y, void* __restrict__ n, int n_f32,
+               const float* __restrict__ go, const float* __restrict__ bo, const float* __restrict__ gi,
+               const float* __restrict__ bi, float* __restrict__ stats_o, float* __restrict__ stats_i, int M, int N) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nch = (N + 255) >> 8;
+  const float invN = 1.f / static_cast<float>(N);
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+    float v[kMaxChunks][8];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (c < nch && col < N) {
+        load8(h + static_cast<size_t>(row) * N + col, v[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[c][i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[c][i] = 0.f;
+      }
+    }
+    float mean = warp_sum(s) * invN;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (c < nch && col < N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[c][i] - mean; q += d * d; }
+      }
+    }
+    float rstd = rsqrtf(warp_sum(q) * invN + kLnEps);
+    if (lane == 0) { stats_o[2 * row] = mean; stats_o[2 * row + 1] = rstd; }
+    s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (c < nch && col < N) {
+        float g[8], b[8];
+        load8(go + col, g); load8(bo + col, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[c][i] = (v[c][i] - mean) * rstd * g[i] + b[i]; s += v[c][i]; }
+        store8(y + static_cast<size_t>(row) * N + col, v[c]);
+      }
+    }
+    mean = warp_sum(s) * invN;
+    q = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (c < nch && col < N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = v[c][i] - mean; q += d * d; }
+      }
+    }
+    rstd = rsqrtf(warp_sum(q) * invN + kLnEps);
+    if (lane == 0) { stats_i[2 * row] = mean; stats_i[2 * row + 1] = rstd; }
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (c < nch && col < N) {
+        float g[8], b[8], o[8];
+        load8(gi + col, g); load8(bi + col, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = (v[c][i] - mean) * rstd * g[i] + b[i];
+        store8_dyn(n, static_cast<size_t>(row) * N + col, n_f32, o);
+      }
+    }
+  }
+}
+
+// Backward of the pair: dy = dskip + LN_inner'(dn) ; dh = LN_outer'(dy).  y is recomputed from h.
+// dgi/dbi/dgo/dbo accumulate (+=) into fp32 [N] buffers.
+__global__ void __launch_bounds__(256)
+ln2_bwd_kernel(const float* __restrict__ dn, const float* __restrict__ dskip, const float* __restrict__ h,
+               const float* __restrict__ stats_o, const float* __restrict__ stats_i, const float* __restrict__ go,
+               const float* __restrict__ bo, const float* __restrict__ gi, float* __restrict__ dh,
+               void* __restrict__ dh2, int dh2_f32, float* __restrict__ dgi, float* __restrict__ dbi,
+               float* __restrict__ dgo, float* __restrict__ dbo, int M, int N) {
+  __shared__ float sacc[4][kMaxChunks * 256];
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nch = (N + 255) >> 8;
+  const float invN = 1.f / static_cast<float>(N);
+  for (int i = threadIdx.x; i < 4 * kMaxChunks * 256; i += blockDim.x) (&sacc[0][0])[i] = 0.f;
+  __syncthreads();
+  float agi[kMaxChunks][8], abi[kMaxChunks][8], ago[kMaxChunks][8], abo[kMaxChunks][8];
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { agi[c][i] = 0.f; abi[c][i] = 0.f; ago[c][i] = 0.f; abo[c][i] = 0.f; }
+
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+    const float mo = stats_o[2 * row], ro = stats_o[2 * row + 1];
+    const float mi = stats_i[2 * row], ri = stats_i[2 * row + 1];
+    float xo[kMaxChunks][8], xi[kMaxChunks][8], a[kMaxChunks][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (c < nch && col < N) {
+        float hv[8], gv[8], g_o[8], b_o[8], g_i[8];
+        load8(h + static_cast<size_t>(row) * N + col, hv);
+        load8(dn + static_cast<size_t>(row) * N + col, gv);
+        load8(go + col, g_o); load8(bo + col, b_o); load8(gi + col, g_i);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (hv[i] - mo) * ro;
+          const float yv = xh * g_o[i] + b_o[i];
+          const float xih = (yv - mi) * ri;
+          xo[c][i] = xh; xi[c][i] = xih;
+          a[c][i] = gv[i] * g_i[i];
+          s1 += a[c][i]; s2 += a[c][i] * xih;
+          agi[c][i] += gv[i] * xih; abi[c][i] += gv[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { xo[c][i] = 0.f; xi[c][i] = 0.f; a[c][i] = 0.f; }
+      }
+    }
+    s1 = warp_sum(s1) * invN; s2 = warp_sum(s2) * invN;
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (c < nch && col < N) {
+        float sk[8], g_o[8];
+        load8(dskip + static_cast<size_t>(row) * N + col, sk);
+        load8(go + col, g_o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float dy = ri * (a[c][i] - s1 - xi[c][i] * s2) + sk[i];
+          ago[c][i] += dy * xo[c][i]; abo[c][i] += dy;
+          a[c][i] = dy * g_o[i];
+          t1 += a[c][i]; t2 += a[c][i] * xo[c][i];
+        }
+      }
+    }
+    t1 = warp_sum(t1) * invN; t2 = warp_sum(t2) * invN;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (c < nch && col < N) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = ro * (a[c][i] - t1 - xo[c][i] * t2);
+        store8(dh + static_cast<size_t>(row) * N + col, o);
+        if (dh2 != nullptr) store8_dyn(dh2, static_cast<size_t>(row) * N + col, dh2_f32, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (c < nch && col < N) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(&sacc[0][col + i], agi[c][i]); atomicAdd(&sacc[1][col + i], abi[c][i]);
+        atomicAdd(&sacc[2][col + i], ago[c][i]); atomicAdd(&sacc[3][col + i], abo[c][i]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    atomicAdd(dgi + i, sacc[0][i]); atomicAdd(dbi + i, sacc[1][i]);
+    atomicAdd(dgo + i, sacc[2][i]); atomicAdd(dbo + i, sacc[3][i]);
+  }
+}
+
 __global__ void sigmoid_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ ds,
                                    long long n) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -245,6 +424,8 @@ __global__ void sigmoid_bwd_kernel(const float* __restrict__ dy, const float* __
 }
 
 }  // namespace
+
+static int ln_grid(int M);
 
 int cast_any(const void* src, int src_f32, void* dst, int dst_f32, long long n, cudaStream_t s) {
   if (n <= 0) return SER_OK;
@@ -280,6 +461,23 @@ int colsum(const void* X, int x_f32, long long ld, int M, int N, float* out, cud
   return SER_OK;
 }
 
+// `batch` column sums in one launch: X_b = X + b*strideX ([M,N], ld), out_b = out + b*strideOut
+int colsum_batched(const void* X, int x_f32, long long ld, int M, int N, float* out, int batch, long long strideX,
+                   long long strideOut, cudaStream_t s) {
+  SER_REQUIRE(M > 0 && N > 0 && batch > 0, "colsum_batched: empty");
+  SER_REQUIRE((N % 8 == 0) && (ld % 8 == 0) && (strideX % 8 == 0) && ((reinterpret_cast<uintptr_t>(X) & 31) == 0),
+              "colsum_batched: needs 8-element aligned rows");
+  const int gx = ceil_div(N, 256);
+  int gy = ceil_div(M, 64);
+  if (gy > 8) gy = 8;
+  if (gy > 1)
+    for (int b = 0; b < batch; ++b) SER_CUDA_CHECK(cudaMemsetAsync(out + b * strideOut, 0, sizeof(float) * N, s));
+  ProfScope prof("colsum_batched", 0.0, static_cast<double>(batch) * M * N * (x_f32 ? 4 : 2), s);
+  colsum_vec_kernel<<<dim3(gx, gy, batch), 256, 0, s>>>(X, x_f32, ld, M, N, out, strideX, strideOut);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
 static int ln_grid(int M) {
   int blocks = ceil_div(M, 8);
   const int cap = 8 * device_sm_count();
@@ -311,6 +509,28 @@ int layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const fl
                                           (add ? (add_f32 ? 4 : 2) : 0) + (dx2 ? (dx2_f32 ? 4 : 2) : 0)), s);
   ln_bwd_kernel<<<blocks, 256, 0, s>>>(dy, dy_f32, x, x_f32, stats, gamma, beta, add, add_f32, dx, dx_f32, dx2,
                                        dx2_f32, dgamma, dbeta, M, N, relu);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+int layernorm2_fwd(const float* h, float* y, void* n, int n_f32, const float* go, const float* bo, const float* gi,
+                   const float* bi, float* stats_o, float* stats_i, int M, int N, cudaStream_t s) {
+  SER_REQUIRE(N % 8 == 0 && N <= kMaxChunks * 256 && M > 0, "layernorm2: N must be a multiple of 8 and <= 1024");
+  ProfScope prof("layernorm2_fwd", 0.0, static_cast<double>(M) * N * (8 + (n_f32 ? 4 : 2)), s);
+  ln2_fwd_kernel<<<ln_grid(M), 256, 0, s>>>(h, y, n, n_f32, go, bo, gi, bi, stats_o, stats_i, M, N);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+int layernorm2_bwd(const float* dn, const float* dskip, const float* h, const float* stats_o, const float* stats_i,
+                   const float* go, const float* bo, const float* gi, float* dh, void* dh2, int dh2_f32, float* dgi,
+                   float* dbi, float* dgo, float* dbo, int M, int N, cudaStream_t s) {
+  SER_REQUIRE(N % 8 == 0 && N <= kMaxChunks * 256 && M > 0, "layernorm2: N must be a multiple of 8 and <= 1024");
+  int blocks = ceil_div(M, 8);
+  const int cap = 2 * device_sm_count();
+  if (blocks > cap) blocks = cap;
+  ProfScope prof("layernorm2_bwd", 0.0, static_cast<double>(M) * N * (16 + (dh2 ? (dh2_f32 ? 4 : 2) : 0)), s);
+  ln2_bwd_kernel<<<blocks, 256, 0, s>>>(dn, dskip, h, stats_o, stats_i, go, bo, gi, dh, dh2, dh2_f32, dgi, dbi, dgo, dbo, M, N);
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

@@ -94,7 +94,21 @@ gemm_simt_kernel(const float* __restrict__ A, long long sam, long long sak, cons
 
 }  // namespace
 
-int gemm_simt_f32(const GemmArgs& a, cudaStream_t stream) {
+int gemm_simt_f32(const GemmArgs& a0, cudaStream_t stream) {
+  if (a0.batch > 1) {          // fp32 tier: batched problems are simply issued one by one
+    for (int b = 0; b < a0.batch; ++b) {
+      GemmArgs a = a0;
+      a.batch = 1;
+      a.A = reinterpret_cast<const float*>(a0.A) + b * a0.strideA;
+      a.B = reinterpret_cast<const float*>(a0.B) + b * a0.strideB;
+      a.C = reinterpret_cast<float*>(a0.C) + b * a0.strideC;
+      if (a0.R) a.R = reinterpret_cast<const float*>(a0.R) + b * a0.strideR;
+      if (a0.G) a.G = reinterpret_cast<const float*>(a0.G) + b * a0.strideG;
+      SER_TRY(gemm_simt_f32(a, stream));
+    }
+    return SER_OK;
+  }
+  const GemmArgs& a = a0;
   SER_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm_simt: empty problem");
   SER_REQUIRE(a.c_f32 && (a.R == nullptr || a.r_f32) && (a.G == nullptr || a.g_f32),
               "gemm_simt: fp32 tier expects fp32 C / residual / gate");
@@ -105,7 +119,7 @@ int gemm_simt_f32(const GemmArgs& a, cudaStream_t stream) {
     splits = 1;
     const int tiles = mt * nt;
     const int target = 2 * device_sm_count();
-    if (linear && tiles < target && ktiles >= 16) {
+    if (linear && tiles < target && ktiles >= 128) {
       splits = target / tiles;
       if (splits > ktiles / 8) splits = ktiles / 8;
       if (splits < 1) splits = 1;

@@ -43,6 +43,7 @@ struct TcEpilogue {
   int act;
   int atomic;        // accumulate with fp32 atomics (split-K or C +=)
   float alpha;
+  long long strideC, strideR, strideG;   // batch strides in elements
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -74,10 +75,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+// all operands are described by rank-3 tensor maps (columns, rows, batch); batch = 1 for plain GEMMs
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -138,7 +140,7 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 template <int BN, int AMAJ, int BMAJ>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const TcEpilogue ep, const int M, const int N, const int K, const int splits) {
+               const TcEpilogue ep, const int M, const int N, const int K, const int splits, const int batch) {
   using Cfg = TileCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -157,7 +159,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m_tiles = (M + BM - 1) / BM;
   const int n_tiles = N / BN;
   const int kblocks = (K + BK - 1) / BK;
-  const int total_tiles = m_tiles * n_tiles * splits;
+  const int total_tiles = m_tiles * n_tiles * splits * batch;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -184,7 +186,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nt = tile % n_tiles;
         const int rest = tile / n_tiles;
         const int mt = rest % m_tiles;
-        const int sp = rest / m_tiles;
+        const int rest2 = rest / m_tiles;
+        const int sp = rest2 % splits;
+        const int bz = rest2 / splits;
         const int kb0 = static_cast<int>((static_cast<long long>(sp) * kblocks) / splits);
         const int kb1 = static_cast<int>((static_cast<long long>(sp + 1) * kblocks) / splits);
         const int m0 = mt * BM, n0 = nt * BN;
@@ -195,16 +199,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sb = smem_b + stage * Cfg::kBBytes;
           const int k0 = kb * BK;
           if (AMAJ == 0) {
-            tma_load_2d(&tmA, &full_bar[stage], sa, k0, m0);
+            tma_load_3d(&tmA, &full_bar[stage], sa, k0, m0, bz);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(&tmA, &full_bar[stage], sa + j * (BK * 128), m0 + 64 * j, k0);
+            for (int j = 0; j < BM / 64; ++j) tma_load_3d(&tmA, &full_bar[stage], sa + j * (BK * 128), m0 + 64 * j, k0, bz);
           }
           if (BMAJ == 0) {
-            tma_load_2d(&tmB, &full_bar[stage], sb, k0, n0);
+            tma_load_3d(&tmB, &full_bar[stage], sb, k0, n0, bz);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tmB, &full_bar[stage], sb + j * (BK * 128), n0 + 64 * j, k0);
+            for (int j = 0; j < BN / 64; ++j) tma_load_3d(&tmB, &full_bar[stage], sb + j * (BK * 128), n0 + 64 * j, k0, bz);
           }
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -222,7 +226,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int rest = tile / n_tiles;
-        const int sp = rest / m_tiles;
+        const int sp = (rest / m_tiles) % splits;
         const int kb0 = static_cast<int>((static_cast<long long>(sp) * kblocks) / splits);
         const int kb1 = static_cast<int>((static_cast<long long>(sp + 1) * kblocks) / splits);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -254,7 +258,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int nt = tile % n_tiles;
       const int rest = tile / n_tiles;
       const int mt = rest % m_tiles;
-      const int sp = rest / m_tiles;
+      const int rest2 = rest / m_tiles;
+      const int sp = rest2 % splits;
+      const long long bz = rest2 / splits;
       const int m = mt * BM + q * 32 + lane;
       const int n0 = nt * BN;
       const bool lead_split = (sp == 0);
@@ -283,7 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (ep.gate_mode != GATE_NONE) {
             if (ep.g_f32) {
-              const float* g = reinterpret_cast<const float*>(ep.G) + static_cast<size_t>(m) * ep.ldg + n;
+              const float* g = reinterpret_cast<const float*>(ep.G) + bz * ep.strideG + static_cast<size_t>(m) * ep.ldg + n;
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 float t[8]; load8(g + j, t);
@@ -291,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int i = 0; i < 8; ++i) v[j + i] = apply_gate(v[j + i], t[i], ep.gate_mode);
               }
             } else {
-              const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(ep.G) + static_cast<size_t>(m) * ep.ldg + n;
+              const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(ep.G) + bz * ep.strideG + static_cast<size_t>(m) * ep.ldg + n;
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 float t[8]; load8(g + j, t);
@@ -302,7 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (ep.R != nullptr && lead_split) {
             if (ep.r_f32) {
-              const float* r = reinterpret_cast<const float*>(ep.R) + static_cast<size_t>(m) * ep.ldr + n;
+              const float* r = reinterpret_cast<const float*>(ep.R) + bz * ep.strideR + static_cast<size_t>(m) * ep.ldr + n;
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 float t[8]; load8(r + j, t);
@@ -310,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int i = 0; i < 8; ++i) v[j + i] += t[i];
               }
             } else {
-              const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(ep.R) + static_cast<size_t>(m) * ep.ldr + n;
+              const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(ep.R) + bz * ep.strideR + static_cast<size_t>(m) * ep.ldr + n;
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
                 float t[8]; load8(r + j, t);
@@ -320,7 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           if (ep.c_f32) {
-            float* cptr = reinterpret_cast<float*>(ep.C) + static_cast<size_t>(m) * ep.ldc + n;
+            float* cptr = reinterpret_cast<float*>(ep.C) + bz * ep.strideC + static_cast<size_t>(m) * ep.ldc + n;
             if (ep.atomic) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) atomicAdd(cptr + j, v[j]);
@@ -334,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           } else {
-            __nv_bfloat16* cptr = reinterpret_cast<__nv_bfloat16*>(ep.C) + static_cast<size_t>(m) * ep.ldc + n;
+            __nv_bfloat16* cptr = reinterpret_cast<__nv_bfloat16*>(ep.C) + bz * ep.strideC + static_cast<size_t>(m) * ep.ldc + n;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               float t[8];
@@ -385,14 +391,15 @@ EncodeTiledFn get_encode_fn() {
 // 2-D bf16 matrix stored row-major as [rows, cols] with leading dimension ld (elements);
 // the box is [box_rows, box_cols] with box_cols * 2 <= 128 bytes (one swizzle atom).
 int make_tmap(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows,
-              int box_cols) {
+              int box_cols, int batch, long long batch_stride) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) { set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable"); return SER_ERR_CUDA; }
-  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  if (batch <= 1) { batch = 1; batch_stride = rows * ld; }
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(batch_stride) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -407,7 +414,7 @@ int make_tmap(CUtensorMap* tm, const void* base, long long rows, long long cols,
 
 template <int BN, int AMAJ, int BMAJ>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& ep, int M, int N, int K, int splits,
-           cudaStream_t stream) {
+           int batch, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
   static bool configured = false;
   auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ>;
@@ -416,9 +423,9 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& ep,
     configured = true;
   }
   const int m_tiles = ceil_div(M, BM), n_tiles = N / BN;
-  const long long total = static_cast<long long>(m_tiles) * n_tiles * splits;
+  const long long total = static_cast<long long>(m_tiles) * n_tiles * splits * batch;
   const int grid = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
-  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, ep, M, N, K, splits);
+  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, ep, M, N, K, splits, batch);
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -426,10 +433,11 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& ep,
 template <int BN>
 int dispatch_major(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& ep, int splits,
                    cudaStream_t stream) {
-  if (!a.a_trans && !a.b_trans) return launch<BN, 0, 0>(tmA, tmB, ep, a.M, a.N, a.K, splits, stream);
-  if (!a.a_trans && a.b_trans) return launch<BN, 0, 1>(tmA, tmB, ep, a.M, a.N, a.K, splits, stream);
-  if (a.a_trans && a.b_trans) return launch<BN, 1, 1>(tmA, tmB, ep, a.M, a.N, a.K, splits, stream);
-  return launch<BN, 1, 0>(tmA, tmB, ep, a.M, a.N, a.K, splits, stream);
+  const int nb = a.batch > 1 ? a.batch : 1;
+  if (!a.a_trans && !a.b_trans) return launch<BN, 0, 0>(tmA, tmB, ep, a.M, a.N, a.K, splits, nb, stream);
+  if (!a.a_trans && a.b_trans) return launch<BN, 0, 1>(tmA, tmB, ep, a.M, a.N, a.K, splits, nb, stream);
+  if (a.a_trans && a.b_trans) return launch<BN, 1, 1>(tmA, tmB, ep, a.M, a.N, a.K, splits, nb, stream);
+  return launch<BN, 1, 0>(tmA, tmB, ep, a.M, a.N, a.K, splits, nb, stream);
 }
 
 }  // namespace
@@ -450,9 +458,12 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
     splits = 1;
     const int tiles = m_tiles * n_tiles;
     const int sms = device_sm_count();
-    if (linear && tiles * 2 <= sms && kblocks >= 8) {
-      splits = sms / tiles;
-      const int max_by_k = kblocks / 4;        // keep >= 4 k-blocks per split
+    const int tiles_all = tiles * (a.batch > 1 ? a.batch : 1);
+    // split-K pays only when the contraction is long (token-dimension wgrads); tiny problems stay unsplit:
+    // the fp32-atomic epilogue costs more than the serial K loop it saves
+    if (linear && tiles_all * 2 <= sms && kblocks >= 64) {
+      splits = sms / tiles_all;
+      const int max_by_k = kblocks / 8;        // keep >= 8 k-blocks per split
       if (splits > max_by_k) splits = max_by_k;
       if (splits < 1) splits = 1;
     }
@@ -461,10 +472,10 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   if (splits > kblocks) splits = kblocks;
 
   CUtensorMap tmA, tmB;
-  if (!a.a_trans) SER_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM, BK));
-  else            SER_TRY(make_tmap(&tmA, a.A, a.K, a.M, a.lda, BK, 64));
-  if (!a.b_trans) SER_TRY(make_tmap(&tmB, a.B, a.N, a.K, a.ldb, BN, BK));
-  else            SER_TRY(make_tmap(&tmB, a.B, a.K, a.N, a.ldb, BK, 64));
+  if (!a.a_trans) SER_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM, BK, a.batch, a.strideA));
+  else            SER_TRY(make_tmap(&tmA, a.A, a.K, a.M, a.lda, BK, 64, a.batch, a.strideA));
+  if (!a.b_trans) SER_TRY(make_tmap(&tmB, a.B, a.N, a.K, a.ldb, BN, BK, a.batch, a.strideB));
+  else            SER_TRY(make_tmap(&tmB, a.B, a.K, a.N, a.ldb, BK, 64, a.batch, a.strideB));
 
   TcEpilogue ep;
   ep.C = a.C; ep.ldc = a.ldc; ep.c_f32 = a.c_f32;
@@ -473,6 +484,8 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   ep.G = a.G; ep.ldg = a.ldg; ep.g_f32 = a.g_f32; ep.gate_mode = a.gate_mode;
   ep.act = a.act;
   ep.alpha = a.alpha;
+  ep.strideC = a.strideC; ep.strideR = a.strideR; ep.strideG = a.strideG;
+  SER_REQUIRE(a.batch <= 1 || (a.strideA % 8 == 0 && a.strideB % 8 == 0), "gemm_tc: batch strides must be multiples of 8");
   int accumulate = a.accumulate;
   if (splits > 1 && a.R != nullptr && a.R == a.C) {
     // in-place residual with split-K: C already holds R, so every split simply accumulates into it
@@ -483,10 +496,12 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   if (ep.atomic) {
     SER_REQUIRE(a.c_f32, "gemm_tc: accumulate / split-K needs an fp32 output");
     if (!accumulate) {
-      SER_CUDA_CHECK(cudaMemset2DAsync(a.C, a.ldc * sizeof(float), 0, a.N * sizeof(float), a.M, stream));
+      for (int b = 0; b < (a.batch > 1 ? a.batch : 1); ++b)
+        SER_CUDA_CHECK(cudaMemset2DAsync(reinterpret_cast<float*>(a.C) + b * a.strideC, a.ldc * sizeof(float), 0,
+                                         a.N * sizeof(float), a.M, stream));
     }
   }
-  const double gflops = 2.0 * a.M * a.N * a.K;
+  const double gflops = 2.0 * a.M * a.N * a.K * (a.batch > 1 ? a.batch : 1);
   const double gesz = (a.dtype == DT_F32) ? 4.0 : 2.0;
   const double gbytes = (static_cast<double>(a.M) * a.K + static_cast<double>(a.N) * a.K) * gesz +
                         static_cast<double>(a.M) * a.N * ((a.c_f32 ? 4.0 : 2.0) + (a.R ? (a.r_f32 ? 4.0 : 2.0) : 0.0) +

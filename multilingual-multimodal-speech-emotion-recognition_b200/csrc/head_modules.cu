@@ -372,9 +372,9 @@ int clf_fwd(const ser_clf_desc& d, cudaStream_t s) {
     float* yi = d.y + i * BP;
     void* ni = off(d.n, static_cast<long long>(i) * BP, dt);
     void* ri = off(d.r, static_cast<long long>(i) * BP, dt);
-    // outer LayerNorm, then the block's own LayerNorm (classifier.py:207-212, :79-80)
-    SER_TRY(layernorm_fwd(hi, 1, yi, 1, nullptr, 1, d.lno_g[i], d.lno_b[i], d.stats_o + static_cast<size_t>(i) * B * 2, B, P, 0, s));
-    SER_TRY(layernorm_fwd(yi, 1, ni, f, nullptr, 1, d.lni_g[i], d.lni_b[i], d.stats_i + static_cast<size_t>(i) * B * 2, B, P, 0, s));
+    // outer LayerNorm, then the block's own LayerNorm (classifier.py:207-212, :79-80), one fused pass
+    SER_TRY(layernorm2_fwd(hi, yi, ni, f, d.lno_g[i], d.lno_b[i], d.lni_g[i], d.lni_b[i],
+                           d.stats_o + static_cast<size_t>(i) * B * 2, d.stats_i + static_cast<size_t>(i) * B * 2, B, P, s));
     SER_TRY(linear_fwd(dt, B, P, P, ni, P, d.w1[i], P, d.b1[i], ri, P, f, ACT_RELU, nullptr, 0, 1, s));
     // residual from the OUTER-LN output y
     SER_TRY(linear_fwd(dt, B, P, P, ri, P, d.w2[i], P, d.b2[i], hn, P, 1, ACT_NONE, yi, P, 1, s));
@@ -402,8 +402,9 @@ size_t clf_bwd_ws_bytes(int dtype, int B, int P, int F, int C, int U) {
   (void)C;
   const size_t e = esize(dtype);
   const size_t b = static_cast<size_t>(B);
-  return pad256(b * F * 4) + pad256(b * F * e) + 2 * pad256(b * P * 4) + 2 * pad256(b * P * e) + pad256(b * P * 4) +
-         pad256(b * P * e) + pad256(b * U * 4) + pad256(b * 4) + pad256(b * P * e) + 8192;
+  const size_t Lmax = 64;          // upper bound on the number of residual blocks covered by this query
+  return pad256(b * F * 4) + pad256(b * F * e) + 3 * pad256(b * P * 4) + pad256(b * P * e) + pad256(b * U * 4) +
+         pad256(b * 4) + 2 * pad256(Lmax * b * P * e) + 8192;
 }
 
 int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
@@ -413,16 +414,18 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
   const size_t e = esize(dt);
   SER_REQUIRE(d.dlogits != nullptr || d.dunc != nullptr, "clf_bwd: no incoming gradient");
   Arena ws(d.ws, d.ws_bytes);
+  SER_REQUIRE(L <= 64, "clf_bwd: at most 64 residual blocks");
   float* df = reinterpret_cast<float*>(ws.take(static_cast<size_t>(B) * F * 4));
   void* dq = ws.take(static_cast<size_t>(B) * F * e);
   float* dh32 = reinterpret_cast<float*>(ws.take(BP * 4));      // gradient of the fp32 residual stream
-  float* dy32 = reinterpret_cast<float*>(ws.take(BP * 4));
-  void* dhT = ws.take(BP * e);                                  // act-dtype copy (GEMM operand)
-  void* drT = ws.take(BP * e);
+  float* dh32b = reinterpret_cast<float*>(ws.take(BP * 4));     // ping-pong partner
   float* dn32 = reinterpret_cast<float*>(ws.take(BP * 4));
   void* dp0 = ws.take(BP * e);
   float* du1 = reinterpret_cast<float*>(ws.take(static_cast<size_t>(B) * U * 4));
   float* dsg = reinterpret_cast<float*>(ws.take(static_cast<size_t>(B) * 4));
+  // per-block GEMM operands kept for ONE batched weight-gradient launch per weight family after the loop:
+  void* dhn_all = ws.take(static_cast<size_t>(L) * BP * e);     // [L,B,P] act: gradient at each block's output
+  void* dr_all = ws.take(static_cast<size_t>(L) * BP * e);      // [L,B,P] act: gradient at relu(W1 n + b1)
   if (!ws.ok) { set_last_error(__FILE__, __LINE__, "clf_bwd: workspace too small"); return SER_ERR_WORKSPACE; }
 
   // ---- heads (fp32) ----
@@ -459,34 +462,60 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
   SER_TRY(colsum(dq, f, F, B, F, d.db_out, s));
   SER_TRY(linear_wgrad(dt, B, F, P, dq, F, d.h_last, P, d.dw_out, P, s));
   SER_TRY(linear_dgrad(dt, B, F, P, dq, F, d.w_out, P, dh32, P, 1, nullptr, 0, 1, GATE_NONE, nullptr, 0, 1, s));
-  SER_TRY(cast_any(dh32, 1, dhT, f, static_cast<long long>(BP), s));
-  // ---- 35 residual blocks, last to first ----
+  SER_TRY(cast_any(dh32, 1, off(dhn_all, static_cast<long long>(L - 1) * BP, dt), f, static_cast<long long>(BP), s));
+  // ---- 35 residual blocks, last to first: only the serial dX chain lives in the loop ----
+  // LayerNorm parameter gradients accumulate with atomics: the per-block dlni / dlno buffers must arrive zeroed
+  // (they are slices of the caller's zero-initialised gradient buffer).
+  float* cur = dh32;
+  float* nxt = dh32b;
   for (int i = L - 1; i >= 0; --i) {
     const float* hi = d.h + i * BP;
-    const float* yi = d.y + i * BP;
-    const void* ni = off(static_cast<const void*>(d.n), static_cast<long long>(i) * BP, dt);
     const void* ri = off(static_cast<const void*>(d.r), static_cast<long long>(i) * BP, dt);
-    SER_TRY(colsum(dh32, 1, P, B, P, d.db2[i], s));
-    SER_TRY(linear_wgrad(dt, B, P, P, dhT, P, ri, P, d.dw2[i], P, s));
-    SER_TRY(linear_dgrad(dt, B, P, P, dhT, P, d.w2[i], P, drT, P, f, ri, P, f, GATE_RELU, nullptr, 0, 1, s));
-    SER_TRY(colsum(drT, f, P, B, P, d.db1[i], s));
-    SER_TRY(linear_wgrad(dt, B, P, P, drT, P, ni, P, d.dw1[i], P, s));
-    SER_TRY(linear_dgrad(dt, B, P, P, drT, P, d.w1[i], P, dn32, P, 1, nullptr, 0, 1, GATE_NONE, nullptr, 0, 1, s));
-    SER_CUDA_CHECK(cudaMemsetAsync(d.dlni_g[i], 0, sizeof(float) * P, s));
-    SER_CUDA_CHECK(cudaMemsetAsync(d.dlni_b[i], 0, sizeof(float) * P, s));
-    SER_CUDA_CHECK(cudaMemsetAsync(d.dlno_g[i], 0, sizeof(float) * P, s));
-    SER_CUDA_CHECK(cudaMemsetAsync(d.dlno_b[i], 0, sizeof(float) * P, s));
-    // dy = dh_next (skip) + LN_inner'(dn)
-    SER_TRY(layernorm_bwd(dn32, 1, yi, 1, d.stats_i + static_cast<size_t>(i) * B * 2, d.lni_g[i], d.lni_b[i], dh32, 1,
-                          dy32, 1, nullptr, 1, d.dlni_g[i], d.dlni_b[i], B, P, 0, s));
-    // dh_i = LN_outer'(dy)  (fp32 stream + act-dtype copy for the next GEMMs)
-    SER_TRY(layernorm_bwd(dy32, 1, hi, 1, d.stats_o + static_cast<size_t>(i) * B * 2, d.lno_g[i], d.lno_b[i], nullptr, 1,
-                          dh32, 1, dhT, f, d.dlno_g[i], d.dlno_b[i], B, P, 0, s));
+    void* dhn_i = off(dhn_all, static_cast<long long>(i) * BP, dt);
+    void* dr_i = off(dr_all, static_cast<long long>(i) * BP, dt);
+    SER_TRY(linear_dgrad(dt, B, P, P, dhn_i, P, d.w2[i], P, dr_i, P, f, ri, P, f, GATE_RELU, nullptr, 0, 1, s));
+    SER_TRY(linear_dgrad(dt, B, P, P, dr_i, P, d.w1[i], P, dn32, P, 1, nullptr, 0, 1, GATE_NONE, nullptr, 0, 1, s));
+    // dy = dh_next (skip) + LN_inner'(dn);  dh_i = LN_outer'(dy): fp32 stream + act-dtype copy for block i-1
+    void* dh_prev = (i > 0) ? off(dhn_all, static_cast<long long>(i - 1) * BP, dt) : nullptr;
+    SER_TRY(layernorm2_bwd(dn32, cur, hi, d.stats_o + static_cast<size_t>(i) * B * 2,
+                           d.stats_i + static_cast<size_t>(i) * B * 2, d.lno_g[i], d.lno_b[i], d.lni_g[i], nxt, dh_prev, f,
+                           d.dlni_g[i], d.dlni_b[i], d.dlno_g[i], d.dlno_b[i], B, P, s));
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  // ---- weight / bias gradients of all blocks: batched when the per-block buffers are uniformly strided ----
+  bool uniform = L > 1;
+  long long sw1 = 0, sw2 = 0, sb1 = 0, sb2 = 0;
+  if (uniform) {
+    sw1 = d.dw1[1] - d.dw1[0]; sw2 = d.dw2[1] - d.dw2[0]; sb1 = d.db1[1] - d.db1[0]; sb2 = d.db2[1] - d.db2[0];
+    for (int i = 1; i < L && uniform; ++i)
+      uniform = (d.dw1[i] - d.dw1[i - 1] == sw1) && (d.dw2[i] - d.dw2[i - 1] == sw2) &&
+                (d.db1[i] - d.db1[i - 1] == sb1) && (d.db2[i] - d.db2[i - 1] == sb2);
+    uniform = uniform && sw1 > 0 && sw2 > 0 && sb1 > 0 && sb2 > 0 && (P % 8 == 0);
+  }
+  if (uniform) {
+    GemmArgs g;
+    g.dtype = dt; g.M = P; g.N = P; g.K = B; g.a_trans = 1; g.b_trans = 1; g.lda = P; g.ldb = P; g.ldc = P; g.c_f32 = 1;
+    g.batch = L; g.strideA = static_cast<long long>(BP); g.strideB = static_cast<long long>(BP);
+    g.A = dhn_all; g.B = d.r; g.C = d.dw2[0]; g.strideC = sw2;
+    SER_TRY(gemm(g, s));
+    g.A = dr_all; g.B = d.n; g.C = d.dw1[0]; g.strideC = sw1;
+    SER_TRY(gemm(g, s));
+    SER_TRY(colsum_batched(dhn_all, f, P, B, P, d.db2[0], L, static_cast<long long>(BP), sb2, s));
+    SER_TRY(colsum_batched(dr_all, f, P, B, P, d.db1[0], L, static_cast<long long>(BP), sb1, s));
+  } else {
+    for (int i = 0; i < L; ++i) {
+      const void* dhn_i = off(static_cast<const void*>(dhn_all), static_cast<long long>(i) * BP, dt);
+      const void* dr_i = off(static_cast<const void*>(dr_all), static_cast<long long>(i) * BP, dt);
+      SER_TRY(colsum(dhn_i, f, P, B, P, d.db2[i], s));
+      SER_TRY(linear_wgrad(dt, B, P, P, dhn_i, P, off(static_cast<const void*>(d.r), static_cast<long long>(i) * BP, dt), P, d.dw2[i], P, s));
+      SER_TRY(colsum(dr_i, f, P, B, P, d.db1[i], s));
+      SER_TRY(linear_wgrad(dt, B, P, P, dr_i, P, off(static_cast<const void*>(d.n), static_cast<long long>(i) * BP, dt), P, d.dw1[i], P, s));
+    }
   }
   // ---- input projection: h0 = relu(LN(p0)) ----
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_in_g, 0, sizeof(float) * P, s));
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_in_b, 0, sizeof(float) * P, s));
-  SER_TRY(layernorm_bwd(dh32, 1, d.p0, 1, d.stats0, d.ln_in_g, d.ln_in_b, nullptr, 1, dp0, f, nullptr, 1, d.dln_in_g,
+  SER_TRY(layernorm_bwd(cur, 1, d.p0, 1, d.stats0, d.ln_in_g, d.ln_in_b, nullptr, 1, dp0, f, nullptr, 1, d.dln_in_g,
                         d.dln_in_b, B, P, 1, s));
   SER_TRY(colsum(dp0, f, P, B, P, d.db_in, s));
   SER_TRY(linear_wgrad(dt, B, P, P, dp0, P, d.x, P, d.dw_in, P, s));

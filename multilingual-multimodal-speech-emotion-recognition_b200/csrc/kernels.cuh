@@ -18,6 +18,14 @@ int layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, void* y2, int y2
 int layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const float* stats, const float* gamma,
                   const float* beta, const void* add, int add_f32, void* dx, int dx_f32, void* dx2, int dx2_f32,
                   float* dgamma, float* dbeta, int M, int N, int relu, cudaStream_t s);
+int colsum_batched(const void* X, int x_f32, long long ld, int M, int N, float* out, int batch, long long strideX,
+                   long long strideOut, cudaStream_t s);
+// classifier block prologue / its backward: y = LN_outer(h), n = LN_inner(y) in one pass (fp32 stream)
+int layernorm2_fwd(const float* h, float* y, void* n, int n_f32, const float* go, const float* bo, const float* gi,
+                   const float* bi, float* stats_o, float* stats_i, int M, int N, cudaStream_t s);
+int layernorm2_bwd(const float* dn, const float* dskip, const float* h, const float* stats_o, const float* stats_i,
+                   const float* go, const float* bo, const float* gi, float* dh, void* dh2, int dh2_f32, float* dgi,
+                   float* dbi, float* dgo, float* dbo, int M, int N, cudaStream_t s);
 // ds = dy * y * (1 - y)    (sigmoid backward, fp32)
 int sigmoid_bwd(const float* dy, const float* y, float* ds, long long n, cudaStream_t s);
 

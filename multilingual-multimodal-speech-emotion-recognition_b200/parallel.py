@@ -45,9 +45,12 @@ class GradBucketReducer:
 def global_loss_cfg(labels: torch.Tensor, num_classes: int, group=None) -> Dict:
     """loss_cfg entries that turn the per-shard loss kernels into the exact global-batch loss."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    counts = torch.bincount(labels, minlength=num_classes).to(torch.float32)
-    if world > 1:
-        dist.all_reduce(counts, group=group)
+    if world == 1:
+        return dict(B_global=int(labels.shape[0]))        # the loss kernel counts the labels itself
+    # scatter_add instead of torch.bincount: no device->host sync, CUDA-graph capturable
+    counts = torch.zeros(num_classes, device=labels.device, dtype=torch.float32)
+    counts.scatter_add_(0, labels.clamp(0, num_classes - 1), torch.ones_like(labels, dtype=torch.float32))
+    dist.all_reduce(counts, group=group)
 
     def reduce_sums(sums: torch.Tensor) -> None:
         if world > 1:
@@ -106,3 +109,42 @@ class DataParallelHead:
                 if p.grad is not None and p.grad.data_ptr() != base + 4 * o:
                     p.grad.copy_(g[o:o + p.numel()].view(p.shape))
         return out
+
+
+class GraphedTrainStep:
+    """CUDA-graph replay of DataParallelHead.train_step for fixed shapes (single GPU, or per rank when the
+    process group supports capture).  The ~600 small launches of a step are recorded once and replayed with
+    one cudaGraphLaunch, which removes the CPU launch bound of the 35-block classifier.
+
+        g = GraphedTrainStep(dp, a, t, a_mask, t_mask, labels)      # warm-up + capture
+        out = g(a, t, a_mask, t_mask, labels)                        # copy into static inputs, replay
+    Outputs (loss terms, logits, ...) are static tensors overwritten by every replay; parameter .grad tensors
+    are static as well, so an optimizer step between replays works as usual.
+    """
+
+    def __init__(self, dp: DataParallelHead, a, t, a_mask, t_mask, labels, warmup: int = 3):
+        self.dp = dp
+        self.static = [None if x is None else x.clone() for x in (a, t, a_mask, t_mask, labels)]
+        side = torch.cuda.Stream(device=a.device)
+        side.wait_stream(torch.cuda.current_stream(a.device))
+        with torch.cuda.stream(side):                       # warm-up on a side stream, as torch.cuda.graphs requires
+            for _ in range(warmup):
+                dp.train_step(*self.static)
+        torch.cuda.current_stream(a.device).wait_stream(side)
+        torch.cuda.synchronize(a.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = dp.train_step(*self.static)
+
+    def load_inputs(self, a, t, a_mask, t_mask, labels, non_blocking: bool = True) -> None:
+        for dst, src in zip(self.static, (a, t, a_mask, t_mask, labels)):
+            if dst is not None and src is not None and dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=non_blocking)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+    def __call__(self, a, t, a_mask, t_mask, labels):
+        self.load_inputs(a, t, a_mask, t_mask, labels)
+        return self.replay()
