@@ -308,13 +308,14 @@ int check(const AttnArgs& a) {
 
 int attention_fwd(const AttnArgs& a, cudaStream_t s) {
   SER_TRY(check(a));
-  return a.dtype == DT_F32 ? fwd_impl<float>(a, s) : fwd_impl<__nv_bfloat16>(a, s);
+  // bf16 tier: tensor-core kernels (attention_tc.cu); fp32 tier: the CUDA-core kernels of this file
+  return a.dtype == DT_F32 ? fwd_impl<float>(a, s) : attention_fwd_tc(a, s);
 }
 
 int attention_bwd(const AttnArgs& a, cudaStream_t s) {
   SER_TRY(check(a));
   SER_REQUIRE(a.delta != nullptr && a.lse != nullptr, "attention_bwd: lse / delta buffers required");
-  return a.dtype == DT_F32 ? bwd_impl<float>(a, s) : bwd_impl<__nv_bfloat16>(a, s);
+  return a.dtype == DT_F32 ? bwd_impl<float>(a, s) : attention_bwd_tc(a, s);
 }
 
 }  // namespace ser

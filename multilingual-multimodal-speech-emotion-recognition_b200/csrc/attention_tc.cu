@@ -1,0 +1,421 @@
+// Masked multi-head cross attention core on tensor cores (bf16 tier): QK^T -> masked streaming softmax -> PV,
+// forward and backward.  Semantics are those of attention.cu (nn.MultiheadAttention's math path as used by
+// cross_attention.py:41,49; torch/nn/functional.py:6609-6645): additive -inf key padding, softmax over keys,
+// attention weights never materialised, a sample whose keys are ALL padded yields NaN for every query.
+//
+// Shapes are tiny per (sample, head): dh = 32, Tk in {64, 250, 256, 1500}.  One CTA of 4 warps owns 64 rows
+// (queries in fwd / dQ, keys in dK/dV); every warp owns 16 of them as mma.m16n8k16 bf16 fragments with fp32
+// accumulation.  The other operand is streamed through shared memory in 64-row tiles (rows padded to 80 bytes so
+// ldmatrix is bank-conflict free).  Scores / probabilities live only in registers: the S accumulator layout
+// is re-packed in place as the A operand of the second GEMM.  Heads are addressed as 32-column slices of the packed
+// q|k|v projection buffers (row stride 768), so there is no head transpose anywhere.
+#include "kernels.cuh"
+#include "prof.cuh"
+
+namespace ser {
+
+namespace {
+
+constexpr int DH = 32;
+constexpr int TILE = 64;               // rows of the streamed operand per shared-memory tile
+constexpr int ROWS = 64;               // rows owned by a CTA (16 per warp)
+constexpr int NT = 128;
+constexpr int LDS = 40;                // smem row stride in bf16 elements (80 B)
+constexpr float kLog2e = 1.4426950408889634f;
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+// D(16x8, fp32) += A(16x16, bf16 row) * B(16x8, bf16 col)
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// cooperative copy of `rows` x 32 bf16 (row stride ld) into smem [TILE][LDS]; rows beyond `rows` are zero filled
+__device__ __forceinline__ void stage_rows(const bf16* __restrict__ g, long long ld, int rows, bf16* sm) {
+  for (int e = threadIdx.x; e < TILE * 4; e += NT) {
+    const int r = e >> 2, c = (e & 3) * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows) v = *reinterpret_cast<const uint4*>(g + static_cast<size_t>(r) * ld + c);
+    *reinterpret_cast<uint4*>(sm + r * LDS + c) = v;
+  }
+}
+
+// A fragments (2 k-steps over dh = 32) of the warp's 16 rows from a staged [.,LDS] tile
+__device__ __forceinline__ void load_a_frags(const bf16* sm, int row0, int lane, uint32_t (&a)[2][4]) {
+  const int r = row0 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int c = s * 16 + (lane >> 4) * 8;
+    ldsm_x4(smem_addr(sm + r * LDS + c), a[s][0], a[s][1], a[s][2], a[s][3]);
+  }
+}
+
+// acc[j] (16 x 8 slice j of a 16 x 64 product) = A(16 x 32) * T^T, T = staged tile [64][dh] used as "n = tile row, k = d"
+__device__ __forceinline__ void mma_nt(const uint32_t (&a)[2][4], const bf16* tile, int lane, float (&acc)[8][4]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t b0, b1, b2, b3;
+    ldsm_x4(smem_addr(tile + (8 * j + (lane & 7)) * LDS + (lane >> 3) * 8), b0, b1, b2, b3);
+    mma16816(acc[j], a[0], b0, b1);
+    mma16816(acc[j], a[1], b2, b3);
+  }
+}
+
+// out[j] (16 x 8 slice j of a 16 x 32 product) += P(16 x 64, given as 4 A fragments) * T, T = staged tile [64][dh]
+// used as "k = tile row, n = d"
+__device__ __forceinline__ void mma_nn(const uint32_t (&p)[4][4], const bf16* tile, int lane, float (&out)[4][4]) {
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int r = 16 * s + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(smem_addr(tile + r * LDS + 16 * jj + (lane >> 4) * 8), b0, b1, b2, b3);
+      mma16816(out[2 * jj], p[s], b0, b1);
+      mma16816(out[2 * jj + 1], p[s], b2, b3);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+attn_tc_fwd_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk,
+                   const bf16* __restrict__ V, long long ldv, const float* __restrict__ kmask, bf16* __restrict__ O,
+                   long long ldo, float* __restrict__ lse, int H, int Tq, int Tk, float scale) {
+  __shared__ __align__(16) bf16 sQ[ROWS * LDS];
+  __shared__ __align__(16) bf16 sK[TILE * LDS];
+  __shared__ __align__(16) bf16 sV[TILE * LDS];
+  __shared__ float sBias[TILE];            // 0 for a valid key, -inf for a padded / out-of-range one
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ROWS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qrows = min(ROWS, Tq - q0);
+  const float c = scale * kLog2e;
+
+  stage_rows(Q + (static_cast<size_t>(b) * Tq + q0) * ldq + h * DH, ldq, qrows, sQ);
+  __syncthreads();
+  uint32_t qa[2][4];
+  load_a_frags(sQ, warp * 16, lane, qa);
+
+  float o[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[j][i] = 0.f;
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};      // rows lane/4 and lane/4 + 8 (raw score units)
+
+  for (int k0 = 0; k0 < Tk; k0 += TILE) {
+    const int rows = min(TILE, Tk - k0);
+    __syncthreads();
+    stage_rows(K + (static_cast<size_t>(b) * Tk + k0) * ldk + h * DH, ldk, rows, sK);
+    stage_rows(V + (static_cast<size_t>(b) * Tk + k0) * ldv + h * DH, ldv, rows, sV);
+    if (threadIdx.x < TILE) {
+      const int j = threadIdx.x;
+      const bool ok = j < rows && (kmask == nullptr || kmask[static_cast<size_t>(b) * Tk + k0 + j] != 0.f);
+      sBias[j] = ok ? 0.f : -INFINITY;
+    }
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[j][i] = 0.f;
+    mma_nt(qa, sK, lane, s);
+    float tmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 bias = *reinterpret_cast<const float2*>(&sBias[8 * j + 2 * (lane & 3)]);
+      s[j][0] += bias.x; s[j][1] += bias.y; s[j][2] += bias.x; s[j][3] += bias.y;
+      tmax[0] = fmaxf(tmax[0], fmaxf(s[j][0], s[j][1]));
+      tmax[1] = fmaxf(tmax[1], fmaxf(s[j][2], s[j][3]));
+    }
+    float corr[2], mu[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 1));
+      tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 2));
+      const float mn = fmaxf(m[r], tmax[r]);
+      mu[r] = (mn == -INFINITY) ? 0.f : mn;            // nothing but padded keys so far: keep exp() finite
+      corr[r] = exp2f((m[r] - mu[r]) * c);             // m = -inf -> 0
+      m[r] = mn;
+      l[r] *= corr[r];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o[j][0] *= corr[0]; o[j][1] *= corr[0]; o[j][2] *= corr[1]; o[j][3] *= corr[1]; }
+    uint32_t p[4][4];
+    float ls[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = exp2f((s[j][0] - mu[0]) * c), p1 = exp2f((s[j][1] - mu[0]) * c);
+      const float p2 = exp2f((s[j][2] - mu[1]) * c), p3 = exp2f((s[j][3] - mu[1]) * c);
+      ls[0] += p0 + p1; ls[1] += p2 + p3;
+      p[j >> 1][(j & 1) * 2] = pack_bf16(p0, p1);
+      p[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+    }
+    l[0] += ls[0]; l[1] += ls[1];
+    mma_nn(p, sV, lane, o);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+  }
+  const float nan = __int_as_float(0x7fc00000);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int qi = q0 + warp * 16 + (lane >> 2) + 8 * r;
+    if (qi < Tq) {
+      const float inv = (l[r] > 0.f) ? 1.f / l[r] : nan;      // all keys padded -> NaN (reference behaviour)
+      bf16* dst = O + (static_cast<size_t>(b) * Tq + qi) * ldo + h * DH + 2 * (lane & 3);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint32_t*>(dst + 8 * j) = pack_bf16(o[j][2 * r] * inv, o[j][2 * r + 1] * inv);
+      if (lse != nullptr && (lane & 3) == 0)
+        lse[(static_cast<size_t>(b) * H + h) * Tq + qi] = (l[r] > 0.f) ? m[r] * scale + logf(l[r]) : nan;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward, dQ (one CTA per 64 queries, streaming key tiles).  Also emits delta = rowsum(dO * O).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+attn_tc_bwd_dq_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk,
+                      const bf16* __restrict__ V, long long ldv, const float* __restrict__ kmask,
+                      const bf16* __restrict__ O, long long ldo, const bf16* __restrict__ dO, long long lddo,
+                      const float* __restrict__ lse, float* __restrict__ delta, bf16* __restrict__ dQ, long long lddq,
+                      int H, int Tq, int Tk, float scale) {
+  __shared__ __align__(16) bf16 sQ[ROWS * LDS];
+  __shared__ __align__(16) bf16 sG[ROWS * LDS];
+  __shared__ __align__(16) bf16 sK[TILE * LDS];
+  __shared__ __align__(16) bf16 sV[TILE * LDS];
+  __shared__ float sBias[TILE];
+  __shared__ float sDelta[ROWS];
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ROWS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qrows = min(ROWS, Tq - q0);
+  const float c = scale * kLog2e;
+
+  stage_rows(Q + (static_cast<size_t>(b) * Tq + q0) * ldq + h * DH, ldq, qrows, sQ);
+  stage_rows(dO + (static_cast<size_t>(b) * Tq + q0) * lddo + h * DH, lddo, qrows, sG);
+  {
+    // delta[q] = sum_d dO[q,d] * O[q,d]: two threads per query, 16 columns each
+    const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
+    float acc = 0.f;
+    if (r < qrows) {
+      const size_t row = static_cast<size_t>(b) * Tq + q0 + r;
+      float g[8], ov[8];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        load8(dO + row * lddo + h * DH + half * 16 + i * 8, g);
+        load8(O + row * ldo + h * DH + half * 16 + i * 8, ov);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(g[k], ov[k], acc);
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (half == 0) {
+      sDelta[r] = acc;
+      if (r < qrows) delta[(static_cast<size_t>(b) * H + h) * Tq + q0 + r] = acc;
+    }
+  }
+  __syncthreads();
+  uint32_t qa[2][4], ga[2][4];
+  load_a_frags(sQ, warp * 16, lane, qa);
+  load_a_frags(sG, warp * 16, lane, ga);
+  float rl[2], rd[2];                       // per-row lse (in log2 units) and delta
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int lr = warp * 16 + (lane >> 2) + 8 * r;
+    const int qi = q0 + lr;
+    rl[r] = (qi < Tq) ? lse[(static_cast<size_t>(b) * H + h) * Tq + qi] * kLog2e : INFINITY;   // +inf -> P = 0
+    rd[r] = sDelta[lr];
+  }
+  float dq[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dq[j][i] = 0.f;
+
+  for (int k0 = 0; k0 < Tk; k0 += TILE) {
+    const int rows = min(TILE, Tk - k0);
+    __syncthreads();
+    stage_rows(K + (static_cast<size_t>(b) * Tk + k0) * ldk + h * DH, ldk, rows, sK);
+    stage_rows(V + (static_cast<size_t>(b) * Tk + k0) * ldv + h * DH, ldv, rows, sV);
+    if (threadIdx.x < TILE) {
+      const int j = threadIdx.x;
+      const bool ok = j < rows && (kmask == nullptr || kmask[static_cast<size_t>(b) * Tk + k0 + j] != 0.f);
+      sBias[j] = ok ? 0.f : -INFINITY;
+    }
+    __syncthreads();
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s[j][i] = 0.f; dp[j][i] = 0.f; }
+    mma_nt(qa, sK, lane, s);
+    mma_nt(ga, sV, lane, dp);
+    uint32_t ds[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 bias = *reinterpret_cast<const float2*>(&sBias[8 * j + 2 * (lane & 3)]);
+      const float p0 = exp2f(s[j][0] * c + bias.x - rl[0]), p1 = exp2f(s[j][1] * c + bias.y - rl[0]);
+      const float p2 = exp2f(s[j][2] * c + bias.x - rl[1]), p3 = exp2f(s[j][3] * c + bias.y - rl[1]);
+      ds[j >> 1][(j & 1) * 2] = pack_bf16(p0 * (dp[j][0] - rd[0]), p1 * (dp[j][1] - rd[0]));
+      ds[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2 * (dp[j][2] - rd[1]), p3 * (dp[j][3] - rd[1]));
+    }
+    mma_nn(ds, sK, lane, dq);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int qi = q0 + warp * 16 + (lane >> 2) + 8 * r;
+    if (qi < Tq) {
+      bf16* dst = dQ + (static_cast<size_t>(b) * Tq + qi) * lddq + h * DH + 2 * (lane & 3);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint32_t*>(dst + 8 * j) = pack_bf16(dq[j][2 * r] * scale, dq[j][2 * r + 1] * scale);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward, dK / dV (one CTA per 64 keys, streaming query tiles): S^T = K Q^T, dP^T = V dO^T
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT)
+attn_tc_bwd_dkv_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk,
+                       const bf16* __restrict__ V, long long ldv, const float* __restrict__ kmask,
+                       const bf16* __restrict__ dO, long long lddo, const float* __restrict__ lse,
+                       const float* __restrict__ delta, bf16* __restrict__ dK, long long lddk, bf16* __restrict__ dV,
+                       long long lddv, int H, int Tq, int Tk, float scale) {
+  __shared__ __align__(16) bf16 sK[ROWS * LDS];
+  __shared__ __align__(16) bf16 sV[ROWS * LDS];
+  __shared__ __align__(16) bf16 sQ[TILE * LDS];
+  __shared__ __align__(16) bf16 sG[TILE * LDS];
+  __shared__ float sLse[TILE];             // log2 units; +inf for out-of-range queries -> P = 0
+  __shared__ float sDel[TILE];
+  const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * ROWS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int krows = min(ROWS, Tk - k0);
+  const float c = scale * kLog2e;
+
+  stage_rows(K + (static_cast<size_t>(b) * Tk + k0) * ldk + h * DH, ldk, krows, sK);
+  stage_rows(V + (static_cast<size_t>(b) * Tk + k0) * ldv + h * DH, ldv, krows, sV);
+  __syncthreads();
+  uint32_t ka[2][4], va[2][4];
+  load_a_frags(sK, warp * 16, lane, ka);
+  load_a_frags(sV, warp * 16, lane, va);
+  float kb[2];                              // 0 / -inf per owned key row
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int kj = k0 + warp * 16 + (lane >> 2) + 8 * r;
+    const bool ok = kj < Tk && (kmask == nullptr || kmask[static_cast<size_t>(b) * Tk + kj] != 0.f);
+    kb[r] = ok ? 0.f : -INFINITY;
+  }
+  float dk[4][4], dv[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { dk[j][i] = 0.f; dv[j][i] = 0.f; }
+
+  for (int q0 = 0; q0 < Tq; q0 += TILE) {
+    const int rows = min(TILE, Tq - q0);
+    __syncthreads();
+    stage_rows(Q + (static_cast<size_t>(b) * Tq + q0) * ldq + h * DH, ldq, rows, sQ);
+    stage_rows(dO + (static_cast<size_t>(b) * Tq + q0) * lddo + h * DH, lddo, rows, sG);
+    if (threadIdx.x < TILE) {
+      const int j = threadIdx.x;
+      const size_t idx = (static_cast<size_t>(b) * H + h) * Tq + q0 + j;
+      sLse[j] = (j < rows) ? lse[idx] * kLog2e : INFINITY;
+      sDel[j] = (j < rows) ? delta[idx] : 0.f;
+    }
+    __syncthreads();
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { s[j][i] = 0.f; dp[j][i] = 0.f; }
+    mma_nt(ka, sQ, lane, s);               // [keys x queries]
+    mma_nt(va, sG, lane, dp);
+    uint32_t pt[4][4], dst[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 ql = *reinterpret_cast<const float2*>(&sLse[8 * j + 2 * (lane & 3)]);
+      const float2 qd = *reinterpret_cast<const float2*>(&sDel[8 * j + 2 * (lane & 3)]);
+      const float p0 = exp2f(s[j][0] * c + kb[0] - ql.x), p1 = exp2f(s[j][1] * c + kb[0] - ql.y);
+      const float p2 = exp2f(s[j][2] * c + kb[1] - ql.x), p3 = exp2f(s[j][3] * c + kb[1] - ql.y);
+      pt[j >> 1][(j & 1) * 2] = pack_bf16(p0, p1);
+      pt[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+      dst[j >> 1][(j & 1) * 2] = pack_bf16(p0 * (dp[j][0] - qd.x), p1 * (dp[j][1] - qd.y));
+      dst[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2 * (dp[j][2] - qd.x), p3 * (dp[j][3] - qd.y));
+    }
+    mma_nn(pt, sG, lane, dv);              // dV += P^T dO
+    mma_nn(dst, sQ, lane, dk);             // dK += dS^T Q
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int kj = k0 + warp * 16 + (lane >> 2) + 8 * r;
+    if (kj < Tk) {
+      const size_t row = static_cast<size_t>(b) * Tk + kj;
+      bf16* pk = dK + row * lddk + h * DH + 2 * (lane & 3);
+      bf16* pv = dV + row * lddv + h * DH + 2 * (lane & 3);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        *reinterpret_cast<uint32_t*>(pk + 8 * j) = pack_bf16(dk[j][2 * r] * scale, dk[j][2 * r + 1] * scale);
+        *reinterpret_cast<uint32_t*>(pv + 8 * j) = pack_bf16(dv[j][2 * r], dv[j][2 * r + 1]);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int attention_fwd_tc(const AttnArgs& a, cudaStream_t s) {
+  const double fl = 4.0 * a.B * a.H * static_cast<double>(a.Tq) * a.Tk * a.dh;
+  const double by = 2.0 * static_cast<double>(a.B) * a.H * a.dh * (2.0 * a.Tq + 2.0 * a.Tk);
+  ProfScope prof("attention_fwd", fl, by, s);
+  dim3 grid(ceil_div(a.Tq, ROWS), a.H, a.B);
+  attn_tc_fwd_kernel<<<grid, NT, 0, s>>>(reinterpret_cast<const bf16*>(a.Q), a.ldq, reinterpret_cast<const bf16*>(a.K),
+                                         a.ldk, reinterpret_cast<const bf16*>(a.V), a.ldv, a.kmask,
+                                         reinterpret_cast<bf16*>(a.O), a.ldo, a.lse, a.H, a.Tq, a.Tk, a.scale);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+int attention_bwd_tc(const AttnArgs& a, cudaStream_t s) {
+  const double fl = 10.0 * a.B * a.H * static_cast<double>(a.Tq) * a.Tk * a.dh;
+  const double by = 2.0 * static_cast<double>(a.B) * a.H * a.dh * (4.0 * a.Tq + 4.0 * a.Tk);
+  ProfScope prof("attention_bwd", fl, by, s);
+  dim3 gq(ceil_div(a.Tq, ROWS), a.H, a.B);
+  attn_tc_bwd_dq_kernel<<<gq, NT, 0, s>>>(
+      reinterpret_cast<const bf16*>(a.Q), a.ldq, reinterpret_cast<const bf16*>(a.K), a.ldk,
+      reinterpret_cast<const bf16*>(a.V), a.ldv, a.kmask, reinterpret_cast<const bf16*>(a.O), a.ldo,
+      reinterpret_cast<const bf16*>(a.dO), a.lddo, a.lse, a.delta, reinterpret_cast<bf16*>(a.dQ), a.lddq, a.H, a.Tq,
+      a.Tk, a.scale);
+  SER_LAUNCH_CHECK();
+  dim3 gk(ceil_div(a.Tk, ROWS), a.H, a.B);
+  attn_tc_bwd_dkv_kernel<<<gk, NT, 0, s>>>(
+      reinterpret_cast<const bf16*>(a.Q), a.ldq, reinterpret_cast<const bf16*>(a.K), a.ldk,
+      reinterpret_cast<const bf16*>(a.V), a.ldv, a.kmask, reinterpret_cast<const bf16*>(a.dO), a.lddo, a.lse, a.delta,
+      reinterpret_cast<bf16*>(a.dK), a.lddk, reinterpret_cast<bf16*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+}  // namespace ser

@@ -25,6 +25,8 @@ constexpr int BK = 64;        // 64 bf16 = one 128-byte swizzle atom along the c
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
 constexpr int kSmemBudget = 196608;
+constexpr int kStgStride = 36;                        // floats per staged epilogue row (32 + 4 pad: conflict-free)
+constexpr int kStgBytes = 4 * 32 * kStgStride * 4;    // one 32x32 fp32 transpose tile per epilogue warp
 
 template <int BN> struct TileCfg {
   static constexpr int kABytes = BM * BK * 2;
@@ -32,7 +34,7 @@ template <int BN> struct TileCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = kSmemBudget / kStageBytes;
   static constexpr int kTmemCols = 2 * BN;      // double-buffered accumulator
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStgBytes;
 };
 
 struct TcEpilogue {
@@ -97,7 +99,7 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -107,7 +109,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, float& a, float& b, float& c, float& d) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
 }
 
 // Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
@@ -143,7 +159,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const TcEpilogue ep, const int M, const int N, const int K, const int splits, const int batch) {
   using Cfg = TileCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (offset arithmetic on the __shared__ array keeps the shared address space visible to the compiler)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -252,7 +269,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ---------------------------------------------------------------- epilogue (4 warps)
+    // TMEM hands every lane one output ROW (32 consecutive columns per tcgen05.ld).  Writing rows straight to global
+    // memory would touch 32 different lines per store instruction, so each warp transposes its 32x32 chunk through a
+    // private padded shared-memory tile and runs bias / activation / gate / residual / store in the COALESCED
+    // domain: 4 lanes x 8 columns cover one row segment, 8 rows per instruction.
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const uint32_t stg = smem_u32(smem + Cfg::kStages * Cfg::kStageBytes + 256) + q * (32 * kStgStride * 4);
+    const int rsub = lane >> 2;              // row within an 8-row group (coalesced domain)
+    const int csub = (lane & 3) * 8;         // first of this lane's 8 columns within the chunk
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % n_tiles;
@@ -261,95 +285,118 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int rest2 = rest / m_tiles;
       const int sp = rest2 % splits;
       const long long bz = rest2 / splits;
-      const int m = mt * BM + q * 32 + lane;
+      const int mw = mt * BM + q * 32;       // first row of this warp
       const int n0 = nt * BN;
       const bool lead_split = (sp == 0);
+      // Residual / gate operands are fetched in the coalesced domain one chunk AHEAD of their use (the first
+      // chunk before the accumulator is even complete), so their global-load latency never sits on the
+      // per-chunk critical path.  bf16 operands only; fp32 ones (small classifier GEMMs) are loaded in-chunk.
+      const bool use_r = (ep.R != nullptr) && lead_split;
+      const bool use_g = (ep.gate_mode != GATE_NONE);
+      const bool pre_r = use_r && !ep.r_f32;
+      const bool pre_g = use_g;
+      const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(ep.R) + bz * ep.strideR + n0 + csub;
+      const __nv_bfloat16* gbase = reinterpret_cast<const __nv_bfloat16*>(ep.G) + bz * ep.strideG + n0 + csub;
+      uint4 rN[4], gN[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) { rN[it] = make_uint4(0u, 0u, 0u, 0u); gN[it] = make_uint4(0u, 0u, 0u, 0u); }
+      auto prefetch = [&](int c) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int m = min(mw + it * 8 + rsub, M - 1);      // rows past M are clamped: loaded, never stored
+          if (pre_r) rN[it] = *reinterpret_cast<const uint4*>(rbase + static_cast<size_t>(m) * ep.ldr + c * 32);
+          if (pre_g) gN[it] = *reinterpret_cast<const uint4*>(gbase + static_cast<size_t>(m) * ep.ldg + c * 32);
+        }
+      };
+      if (pre_r || pre_g) prefetch(0);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t raw[32];
-        tmem_ld32(taddr0 + c * 32, raw);
-        if (m < M) {
-          const int n = n0 + c * 32;
-          float v[32];
+        tmem_ld32_issue(taddr0 + c * 32, raw);
+        uint4 rC[4], gC[4];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * ep.alpha;
-          if (ep.bias != nullptr && lead_split) {
+        for (int it = 0; it < 4; ++it) { rC[it] = rN[it]; gC[it] = gN[it]; }
+        if ((pre_r || pre_g) && c + 1 < BN / 32) prefetch(c + 1);
+        tmem_ld_wait();
+        {
+          const uint32_t row = stg + lane * (kStgStride * 4);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
-              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-            }
+          for (int j = 0; j < 8; ++j)
+            sts128(row + j * 16, __uint_as_float(raw[4 * j]) * ep.alpha, __uint_as_float(raw[4 * j + 1]) * ep.alpha,
+                   __uint_as_float(raw[4 * j + 2]) * ep.alpha, __uint_as_float(raw[4 * j + 3]) * ep.alpha);
+        }
+        __syncwarp();
+        const int n = n0 + c * 32 + csub;
+        float bv[8];
+        if (ep.bias != nullptr && lead_split) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
+          bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = 0.f;
+        }
+        // fp32 residual / gate operands: all four row groups are loaded before the first store of the chunk
+        // (C may alias R, so the compiler cannot hoist these loads across the stores by itself)
+        float rf[4][8];
+        if (use_r && ep.r_f32) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int m = min(mw + it * 8 + rsub, M - 1);
+            load8(reinterpret_cast<const float*>(ep.R) + bz * ep.strideR + static_cast<size_t>(m) * ep.ldr + n, rf[it]);
           }
-          if (ep.act != ACT_NONE) {
+        }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ep.act);
-          }
-          if (ep.gate_mode != GATE_NONE) {
-            if (ep.g_f32) {
-              const float* g = reinterpret_cast<const float*>(ep.G) + bz * ep.strideG + static_cast<size_t>(m) * ep.ldg + n;
+        for (int it = 0; it < 4; ++it) {
+          const int r = it * 8 + rsub;
+          const int m = mw + r;
+          {
+            float v[8];
+            lds128(stg + (r * kStgStride + csub) * 4, v[0], v[1], v[2], v[3]);
+            lds128(stg + (r * kStgStride + csub) * 4 + 16, v[4], v[5], v[6], v[7]);
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                float t[8]; load8(g + j, t);
+            for (int i = 0; i < 8; ++i) v[i] += bv[i];
+            if (ep.act != ACT_NONE) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[j + i] = apply_gate(v[j + i], t[i], ep.gate_mode);
-              }
-            } else {
-              const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(ep.G) + bz * ep.strideG + static_cast<size_t>(m) * ep.ldg + n;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                float t[8]; load8(g + j, t);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[j + i] = apply_gate(v[j + i], t[i], ep.gate_mode);
-              }
+              for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], ep.act);
             }
-          }
-          if (ep.R != nullptr && lead_split) {
-            if (ep.r_f32) {
-              const float* r = reinterpret_cast<const float*>(ep.R) + bz * ep.strideR + static_cast<size_t>(m) * ep.ldr + n;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                float t[8]; load8(r + j, t);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[j + i] += t[i];
-              }
-            } else {
-              const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(ep.R) + bz * ep.strideR + static_cast<size_t>(m) * ep.ldr + n;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                float t[8]; load8(r + j, t);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[j + i] += t[i];
-              }
-            }
-          }
-          if (ep.c_f32) {
-            float* cptr = reinterpret_cast<float*>(ep.C) + bz * ep.strideC + static_cast<size_t>(m) * ep.ldc + n;
-            if (ep.atomic) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) atomicAdd(cptr + j, v[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                float t[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) t[i] = v[j + i];
-                store8(cptr + j, t);
-              }
-            }
-          } else {
-            __nv_bfloat16* cptr = reinterpret_cast<__nv_bfloat16*>(ep.C) + bz * ep.strideC + static_cast<size_t>(m) * ep.ldc + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
+            if (use_g) {
               float t[8];
+              unpack8(gC[it], t);           // the gate operand is always bf16 in this tier (checked on the host)
 #pragma unroll
-              for (int i = 0; i < 8; ++i) t[i] = v[j + i];
-              store8(cptr + j, t);
+              for (int i = 0; i < 8; ++i) v[i] = apply_gate(v[i], t[i], ep.gate_mode);
+            }
+            if (use_r) {
+              float t[8];
+              if (ep.r_f32) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t[i] = rf[it][i];
+              } else {
+                unpack8(rC[it], t);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += t[i];
+            }
+            const size_t ci = bz * ep.strideC + static_cast<size_t>(m) * ep.ldc + n;
+            if (m >= M) {
+              // tail row: nothing to store
+            } else if (ep.c_f32) {
+              float* cptr = reinterpret_cast<float*>(ep.C) + ci;
+              if (ep.atomic) {
+                atomicAdd(reinterpret_cast<float4*>(cptr), make_float4(v[0], v[1], v[2], v[3]));
+                atomicAdd(reinterpret_cast<float4*>(cptr + 4), make_float4(v[4], v[5], v[6], v[7]));
+              } else {
+                store8(cptr, v);
+              }
+            } else {
+              store8(reinterpret_cast<__nv_bfloat16*>(ep.C) + ci, v);
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -449,7 +496,12 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   SER_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0,
               "gemm_tc: operands must be 16-byte aligned");
   SER_REQUIRE(a.ldc % 8 == 0, "gemm_tc: ldc must be a multiple of 8");
-  const int BN = (a.N % 256 == 0) ? 256 : 128;
+  SER_REQUIRE(a.gate_mode == GATE_NONE || (a.G != nullptr && !a.g_f32 && a.ldg % 8 == 0),
+              "gemm_tc: the gate operand must be bf16 with an 8-element aligned leading dimension");
+  SER_REQUIRE(a.R == nullptr || a.ldr % 8 == 0, "gemm_tc: ldr must be a multiple of 8");
+  int BN = (a.N % 256 == 0) ? 256 : 128;
+  // small problems: narrower tiles put twice as many SMs to work and halve each CTA's serial epilogue
+  if (BN == 256 && 2LL * ceil_div(a.M, BM) * (a.N / 256) * (a.batch > 1 ? a.batch : 1) <= device_sm_count()) BN = 128;
 
   const int m_tiles = ceil_div(a.M, BM), n_tiles = a.N / BN, kblocks = ceil_div(a.K, BK);
   int splits = a.splits;

@@ -52,6 +52,9 @@ struct AttnArgs {
 };
 int attention_fwd(const AttnArgs& a, cudaStream_t s);
 int attention_bwd(const AttnArgs& a, cudaStream_t s);
+// bf16 tensor-core variants (attention_tc.cu); attention_fwd / attention_bwd dispatch to them for dtype == bf16
+int attention_fwd_tc(const AttnArgs& a, cudaStream_t s);
+int attention_bwd_tc(const AttnArgs& a, cudaStream_t s);
 
 // ---- pooling.cu ----------------------------------------------------------------------------------
 // Attentive statistics pooling, everything after the 768->128 tanh GEMM (src/models/pooling.py:21-28).
