@@ -3,13 +3,18 @@
 // One persistent CTA per SM walks output tiles of 128 x BN (BN = 128 or 256).  Warp roles:
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled shared-memory stages)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, M=128, N=BN, K=16)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> bias / activation / gate / residual -> global)
+//   warps 2..5  : epilogue.  Every lane owns one output row (tcgen05.ld 32x32b).  The row is finished in
+//                 registers -- alpha, bias, activation, gate derivative, residual -- packed, written into a
+//                 128B-swizzled staging tile (32 rows x 128 B per warp) and leaves the SM as ONE TMA store
+//                 (or TMA reduce-add for split-K / accumulate).  Residual / gate operands arrive the same way:
+//                 a TMA load of the matching 32 x 128 B box, issued one chunk ahead.  No per-thread global
+//                 address arithmetic, no row predicates (TMA clips the M tail), fully coalesced traffic.
 // The accumulator is double buffered in TMEM (2 x BN fp32 columns) so the epilogue of tile i overlaps
 // the main loop of tile i+1.  Both operands may be K-major or MN-major (nn.Linear weights are
 // consumed in place for forward, dX and dW GEMMs: no transposed copies are ever materialised).
 //
 // Serves: adapters, q/k/v + MHA in/out projections, out_a/out_t, pooling scorer, fusion projections,
-// the 35-block classifier stack (reference: src/models/audio_encoder.py:19-21, cross_attention.py:38-51,
+// the classifier heads (reference: src/models/audio_encoder.py:19-21, cross_attention.py:38-51,
 // pooling.py:9-13, fusion.py:8-16, classifier.py:73-129) in the bf16 tier.
 #include "common.cuh"
 #include "prof.cuh"
@@ -24,28 +29,31 @@ constexpr int BM = 128;       // UMMA M (one TMEM lane per output row)
 constexpr int BK = 64;        // 64 bf16 = one 128-byte swizzle atom along the contraction axis
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
-constexpr int kSmemBudget = 196608;
-constexpr int kStgStride = 36;                        // floats per staged epilogue row (32 + 4 pad: conflict-free)
-constexpr int kStgBytes = 4 * 32 * kStgStride * 4;    // one 32x32 fp32 transpose tile per epilogue warp
+constexpr int kSmemTotal = 232448;                    // 227 KB opt-in maximum per CTA
+constexpr int kStgTile = 32 * 128;                    // one staged chunk: 32 rows x 128 B (SWIZZLE_128B)
+constexpr int kStgBytes = 4 * 4 * kStgTile;           // per epilogue warp: 2 output tiles + 2 source tiles
+constexpr int kBarBytes = 256;
+constexpr int kSmemBudget = kSmemTotal - 1024 /*align*/ - kStgBytes - kBarBytes;
 
 template <int BN> struct TileCfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kSmemBudget / kStageBytes;      // 3 (BN = 256) / 5 (BN = 128)
   static constexpr int kTmemCols = 2 * BN;      // double-buffered accumulator
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStgBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kStgBytes + kBarBytes;
 };
 
+enum : int { SRC_NONE = 0, SRC_RESIDUAL = 1, SRC_GATE = 2 };
+
 struct TcEpilogue {
-  void* C; long long ldc; int c_f32;
   const float* bias;
-  const void* R; long long ldr; int r_f32;
-  const void* G; long long ldg; int g_f32; int gate_mode;
+  int c_f32;         // output (and source) element type: fp32 or bf16
+  int src;           // SRC_*: a second [M,N] operand streamed through TMA (same dtype as the output)
+  int gate_mode;
   int act;
-  int atomic;        // accumulate with fp32 atomics (split-K or C +=)
+  int atomic;        // accumulate with TMA reduce-add (split-K or C +=); fp32 output only
   float alpha;
-  long long strideC, strideR, strideG;   // batch strides in elements
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -84,6 +92,12 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint64_t* bar
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_raw(const CUtensorMap* tm, uint64_t* bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -110,21 +124,32 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
-__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void lds128(uint32_t addr, float& a, float& b, float& c, float& d) {
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr) : "memory");
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void unpack8(const uint4& raw, float (&v)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 f = __bfloat1622float2(h[i]);
-    v[2 * i] = f.x; v[2 * i + 1] = f.y;
-  }
-}
 
 // Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
 //   K-major : rows of 128 B; 8-row groups are SBO = 1024 B apart; LBO unused.
@@ -151,11 +176,137 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 }
 
 // ------------------------------------------------------------------------------------------------
+// epilogue of one 128 x BN tile for one warp (32 rows).  OUT_F32: 32 fp32 columns per 128-byte chunk,
+// otherwise 64 bf16 columns.  SRC: residual / gate operand of the same dtype, streamed by TMA.
+// ------------------------------------------------------------------------------------------------
+struct EpiWarp {
+  uint32_t base;              // shared address of this warp's 4 staging tiles: output 0, 1, source 0, 1
+  __device__ __forceinline__ uint32_t cst(uint32_t i) const { return base + i * kStgTile; }
+  __device__ __forceinline__ uint32_t sst(uint32_t i) const { return base + (2u + i) * kStgTile; }
+  uint64_t* src_full;         // [2] mbarriers of the source tiles
+  uint32_t cbuf;              // next output tile to fill
+  uint32_t sbuf, sphase;      // next source tile to consume and the parity of its barrier
+};
+
+template <int BN, bool OUT_F32, int SRC>
+__device__ __forceinline__ void epilogue_tile(const TcEpilogue& ep, const CUtensorMap* tmC, const CUtensorMap* tmS,
+                                              EpiWarp& w, uint32_t taddr0, int lane, int n0, int mw, int bz,
+                                              bool lead_split, uint64_t* tfull, uint32_t tfull_parity) {
+  constexpr int CW = OUT_F32 ? 32 : 64;          // output columns per 128-byte chunk
+  constexpr int NCH = BN / CW;
+  const bool with_src = (SRC != SRC_NONE) && (SRC == SRC_GATE || lead_split);
+  const uint32_t swz = static_cast<uint32_t>(lane & 7);
+  const uint32_t rowoff = static_cast<uint32_t>(lane) * 128u;
+  // source chunk 0 is requested before the accumulator is even complete
+  if (with_src && lane == 0) {
+    mbar_expect_tx(&w.src_full[w.sbuf], kStgTile);
+    tma_load_3d_raw(tmS, &w.src_full[w.sbuf], w.sst(w.sbuf), n0, mw, bz);
+  }
+  mbar_wait(tfull, tfull_parity);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t raw[CW];
+    tmem_ld32_issue(taddr0 + c * CW, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+    if (!OUT_F32) tmem_ld32_issue(taddr0 + c * CW + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[CW - 32]));
+    if (with_src && c + 1 < NCH && lane == 0) {          // prefetch the next source chunk into the other tile
+      const uint32_t nb = w.sbuf ^ 1u;
+      mbar_expect_tx(&w.src_full[nb], kStgTile);
+      tma_load_3d_raw(tmS, &w.src_full[nb], w.sst(nb), n0 + (c + 1) * CW, mw, bz);
+    }
+    // the output tile written two chunks ago must have been read by its TMA store before it is overwritten
+    if (lane == 0) tma_wait_group_read<1>();
+    __syncwarp();
+    tmem_ld_wait();
+    float v[CW];
+    const float alpha = ep.alpha;
+    if (ep.bias != nullptr && lead_split) {
+      const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0 + c * CW);
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j) {
+        const float4 b = __ldg(bp + j);
+        v[4 * j] = fmaf(__uint_as_float(raw[4 * j]), alpha, b.x);
+        v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), alpha, b.y);
+        v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), alpha, b.z);
+        v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), alpha, b.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(raw[j]) * alpha;
+    }
+    if (ep.act == ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (ep.act == ACT_TANH) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) v[j] = tanhf(v[j]);
+    } else if (ep.act == ACT_SIGMOID) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+    }
+    if (SRC != SRC_NONE && with_src) {
+      mbar_wait(&w.src_full[w.sbuf], w.sphase);
+      const uint32_t sbase = w.sst(w.sbuf) + rowoff;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {                       // 8 x 16 bytes of this lane's source row
+        uint32_t x0, x1, x2, x3;
+        lds128(sbase + ((static_cast<uint32_t>(j) ^ swz) << 4), x0, x1, x2, x3);
+        if (OUT_F32) {
+          const float s0 = __uint_as_float(x0), s1 = __uint_as_float(x1), s2 = __uint_as_float(x2), s3 = __uint_as_float(x3);
+          if (SRC == SRC_RESIDUAL) {
+            v[4 * j] += s0; v[4 * j + 1] += s1; v[4 * j + 2] += s2; v[4 * j + 3] += s3;
+          } else {
+            v[4 * j] = apply_gate(v[4 * j], s0, ep.gate_mode); v[4 * j + 1] = apply_gate(v[4 * j + 1], s1, ep.gate_mode);
+            v[4 * j + 2] = apply_gate(v[4 * j + 2], s2, ep.gate_mode); v[4 * j + 3] = apply_gate(v[4 * j + 3], s3, ep.gate_mode);
+          }
+        } else {
+          const uint32_t xs[4] = {x0, x1, x2, x3};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float lo = bf_lo(xs[t]), hi = bf_hi(xs[t]);
+            if (SRC == SRC_RESIDUAL) {
+              v[8 * j + 2 * t] += lo; v[8 * j + 2 * t + 1] += hi;
+            } else {
+              v[8 * j + 2 * t] = apply_gate(v[8 * j + 2 * t], lo, ep.gate_mode);
+              v[8 * j + 2 * t + 1] = apply_gate(v[8 * j + 2 * t + 1], hi, ep.gate_mode);
+            }
+          }
+        }
+      }
+      w.sbuf ^= 1u;
+      if (w.sbuf == 0u) w.sphase ^= 1u;
+    }
+    // finished row -> swizzled staging tile -> one TMA store per warp and chunk
+    const uint32_t cbase = w.cst(w.cbuf) + rowoff;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t dst = cbase + ((static_cast<uint32_t>(j) ^ swz) << 4);
+      if (OUT_F32) {
+        sts128(dst, __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+               __float_as_uint(v[4 * j + 3]));
+      } else {
+        sts128(dst, pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]), pack2(v[8 * j + 4], v[8 * j + 5]),
+               pack2(v[8 * j + 6], v[8 * j + 7]));
+      }
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (ep.atomic) tma_reduce_add_3d(tmC, w.cst(w.cbuf), n0 + c * CW, mw, bz);
+      else tma_store_3d(tmC, w.cst(w.cbuf), n0 + c * CW, mw, bz);
+      tma_commit_group();
+    }
+    w.cbuf ^= 1u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
 template <int BN, int AMAJ, int BMAJ>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS,
                const TcEpilogue ep, const int M, const int N, const int K, const int splits, const int batch) {
   using Cfg = TileCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -163,12 +314,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_stg = smem + Cfg::kStages * Cfg::kStageBytes;        // 1024-byte aligned: 16 staging tiles of 4 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + kStgBytes);
   uint64_t* full_bar = bars;                         // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;         // [kStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;     // [2]
   uint64_t* tempty_bar = tfull_bar + 2;              // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* src_bar = tempty_bar + 2;                // [4 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(src_bar + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -183,6 +336,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 8; ++s) mbar_init(&src_bar[s], 1);
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
+    if (ep.src != SRC_NONE) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmS)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -269,14 +425,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ---------------------------------------------------------------- epilogue (4 warps)
-    // TMEM hands every lane one output ROW (32 consecutive columns per tcgen05.ld).  Writing rows straight to global
-    // memory would touch 32 different lines per store instruction, so each warp transposes its 32x32 chunk through a
-    // private padded shared-memory tile and runs bias / activation / gate / residual / store in the COALESCED
-    // domain: 4 lanes x 8 columns cover one row segment, 8 rows per instruction.
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const uint32_t stg = smem_u32(smem + Cfg::kStages * Cfg::kStageBytes + 256) + q * (32 * kStgStride * 4);
-    const int rsub = lane >> 2;              // row within an 8-row group (coalesced domain)
-    const int csub = (lane & 3) * 8;         // first of this lane's 8 columns within the chunk
+    EpiWarp w;
+    {
+      const uint32_t base = smem_u32(smem_stg) + static_cast<uint32_t>(q) * (4u * kStgTile);
+      w.base = base;
+      w.src_full = src_bar + 2 * q;
+      w.cbuf = 0; w.sbuf = 0; w.sphase = 0;
+    }
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % n_tiles;
@@ -284,125 +440,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int mt = rest % m_tiles;
       const int rest2 = rest / m_tiles;
       const int sp = rest2 % splits;
-      const long long bz = rest2 / splits;
+      const int bz = rest2 / splits;
       const int mw = mt * BM + q * 32;       // first row of this warp
       const int n0 = nt * BN;
-      const bool lead_split = (sp == 0);
-      // Residual / gate operands are fetched in the coalesced domain one chunk AHEAD of their use (the first
-      // chunk before the accumulator is even complete), so their global-load latency never sits on the
-      // per-chunk critical path.  bf16 operands only; fp32 ones (small classifier GEMMs) are loaded in-chunk.
-      const bool use_r = (ep.R != nullptr) && lead_split;
-      const bool use_g = (ep.gate_mode != GATE_NONE);
-      const bool pre_r = use_r && !ep.r_f32;
-      const bool pre_g = use_g;
-      const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(ep.R) + bz * ep.strideR + n0 + csub;
-      const __nv_bfloat16* gbase = reinterpret_cast<const __nv_bfloat16*>(ep.G) + bz * ep.strideG + n0 + csub;
-      uint4 rN[4], gN[4];
-#pragma unroll
-      for (int it = 0; it < 4; ++it) { rN[it] = make_uint4(0u, 0u, 0u, 0u); gN[it] = make_uint4(0u, 0u, 0u, 0u); }
-      auto prefetch = [&](int c) {
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int m = min(mw + it * 8 + rsub, M - 1);      // rows past M are clamped: loaded, never stored
-          if (pre_r) rN[it] = *reinterpret_cast<const uint4*>(rbase + static_cast<size_t>(m) * ep.ldr + c * 32);
-          if (pre_g) gN[it] = *reinterpret_cast<const uint4*>(gbase + static_cast<size_t>(m) * ep.ldg + c * 32);
-        }
-      };
-      if (pre_r || pre_g) prefetch(0);
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
+      const bool lead = (sp == 0);
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t raw[32];
-        tmem_ld32_issue(taddr0 + c * 32, raw);
-        uint4 rC[4], gC[4];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) { rC[it] = rN[it]; gC[it] = gN[it]; }
-        if ((pre_r || pre_g) && c + 1 < BN / 32) prefetch(c + 1);
-        tmem_ld_wait();
-        {
-          const uint32_t row = stg + lane * (kStgStride * 4);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts128(row + j * 16, __uint_as_float(raw[4 * j]) * ep.alpha, __uint_as_float(raw[4 * j + 1]) * ep.alpha,
-                   __uint_as_float(raw[4 * j + 2]) * ep.alpha, __uint_as_float(raw[4 * j + 3]) * ep.alpha);
-        }
-        __syncwarp();
-        const int n = n0 + c * 32 + csub;
-        float bv[8];
-        if (ep.bias != nullptr && lead_split) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + 4));
-          bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) bv[i] = 0.f;
-        }
-        // fp32 residual / gate operands: all four row groups are loaded before the first store of the chunk
-        // (C may alias R, so the compiler cannot hoist these loads across the stores by itself)
-        float rf[4][8];
-        if (use_r && ep.r_f32) {
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int m = min(mw + it * 8 + rsub, M - 1);
-            load8(reinterpret_cast<const float*>(ep.R) + bz * ep.strideR + static_cast<size_t>(m) * ep.ldr + n, rf[it]);
-          }
-        }
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int r = it * 8 + rsub;
-          const int m = mw + r;
-          {
-            float v[8];
-            lds128(stg + (r * kStgStride + csub) * 4, v[0], v[1], v[2], v[3]);
-            lds128(stg + (r * kStgStride + csub) * 4 + 16, v[4], v[5], v[6], v[7]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] += bv[i];
-            if (ep.act != ACT_NONE) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], ep.act);
-            }
-            if (use_g) {
-              float t[8];
-              unpack8(gC[it], t);           // the gate operand is always bf16 in this tier (checked on the host)
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = apply_gate(v[i], t[i], ep.gate_mode);
-            }
-            if (use_r) {
-              float t[8];
-              if (ep.r_f32) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) t[i] = rf[it][i];
-              } else {
-                unpack8(rC[it], t);
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] += t[i];
-            }
-            const size_t ci = bz * ep.strideC + static_cast<size_t>(m) * ep.ldc + n;
-            if (m >= M) {
-              // tail row: nothing to store
-            } else if (ep.c_f32) {
-              float* cptr = reinterpret_cast<float*>(ep.C) + ci;
-              if (ep.atomic) {
-                atomicAdd(reinterpret_cast<float4*>(cptr), make_float4(v[0], v[1], v[2], v[3]));
-                atomicAdd(reinterpret_cast<float4*>(cptr + 4), make_float4(v[4], v[5], v[6], v[7]));
-              } else {
-                store8(cptr, v);
-              }
-            } else {
-              store8(reinterpret_cast<__nv_bfloat16*>(ep.C) + ci, v);
-            }
-          }
-        }
-        __syncwarp();
+      uint64_t* tf = &tfull_bar[acc];
+      if (ep.c_f32) {
+        if (ep.src == SRC_NONE) epilogue_tile<BN, true, SRC_NONE>(ep, &tmC, &tmS, w, taddr0, lane, n0, mw, bz, lead, tf, acc_phase);
+        else if (ep.src == SRC_RESIDUAL) epilogue_tile<BN, true, SRC_RESIDUAL>(ep, &tmC, &tmS, w, taddr0, lane, n0, mw, bz, lead, tf, acc_phase);
+        else epilogue_tile<BN, true, SRC_GATE>(ep, &tmC, &tmS, w, taddr0, lane, n0, mw, bz, lead, tf, acc_phase);
+      } else {
+        if (ep.src == SRC_NONE) epilogue_tile<BN, false, SRC_NONE>(ep, &tmC, &tmS, w, taddr0, lane, n0, mw, bz, lead, tf, acc_phase);
+        else if (ep.src == SRC_RESIDUAL) epilogue_tile<BN, false, SRC_RESIDUAL>(ep, &tmC, &tmS, w, taddr0, lane, n0, mw, bz, lead, tf, acc_phase);
+        else epilogue_tile<BN, false, SRC_GATE>(ep, &tmC, &tmS, w, taddr0, lane, n0, mw, bz, lead, tf, acc_phase);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    // staged tiles must outlive the TMA stores that read them
+    if (lane == 0) tma_wait_group_read<0>();
+    __syncwarp();
   }
 
   tc_fence_before();
@@ -435,24 +495,25 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 matrix stored row-major as [rows, cols] with leading dimension ld (elements);
-// the box is [box_rows, box_cols] with box_cols * 2 <= 128 bytes (one swizzle atom).
-int make_tmap(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows,
+// 2-D matrix stored row-major as [rows, cols] with leading dimension ld (elements), optionally batched;
+// the box is [box_rows, box_cols] with box_cols * esize <= 128 bytes (one swizzle atom).
+int make_tmap(CUtensorMap* tm, const void* base, int f32, long long rows, long long cols, long long ld, int box_rows,
               int box_cols, int batch, long long batch_stride) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) { set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable"); return SER_ERR_CUDA; }
   if (batch <= 1) { batch = 1; batch_stride = rows * ld; }
+  const cuuint64_t es = f32 ? 4 : 2;
   cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
-  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(batch_stride) * 2};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * es, static_cast<cuuint64_t>(batch_stride) * es};
   cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                  const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    char msg[160];
-    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d base=%p",
-             (int)r, rows, cols, ld, box_rows, box_cols, base);
+    char msg[200];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d base=%p f32=%d "
+             "batch=%d stride=%lld", (int)r, rows, cols, ld, box_rows, box_cols, base, f32, batch, batch_stride);
     set_last_error(__FILE__, __LINE__, msg);
     return SER_ERR_CUDA;
   }
@@ -460,8 +521,8 @@ int make_tmap(CUtensorMap* tm, const void* base, long long rows, long long cols,
 }
 
 template <int BN, int AMAJ, int BMAJ>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& ep, int M, int N, int K, int splits,
-           int batch, cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmS,
+           const TcEpilogue& ep, int M, int N, int K, int splits, int batch, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
   static bool configured = false;
   auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ>;
@@ -472,19 +533,19 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& ep,
   const int m_tiles = ceil_div(M, BM), n_tiles = N / BN;
   const long long total = static_cast<long long>(m_tiles) * n_tiles * splits * batch;
   const int grid = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
-  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, ep, M, N, K, splits, batch);
+  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmS, ep, M, N, K, splits, batch);
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
 
 template <int BN>
-int dispatch_major(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcEpilogue& ep, int splits,
-                   cudaStream_t stream) {
+int dispatch_major(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                   const CUtensorMap& tmS, const TcEpilogue& ep, int splits, cudaStream_t stream) {
   const int nb = a.batch > 1 ? a.batch : 1;
-  if (!a.a_trans && !a.b_trans) return launch<BN, 0, 0>(tmA, tmB, ep, a.M, a.N, a.K, splits, nb, stream);
-  if (!a.a_trans && a.b_trans) return launch<BN, 0, 1>(tmA, tmB, ep, a.M, a.N, a.K, splits, nb, stream);
-  if (a.a_trans && a.b_trans) return launch<BN, 1, 1>(tmA, tmB, ep, a.M, a.N, a.K, splits, nb, stream);
-  return launch<BN, 1, 0>(tmA, tmB, ep, a.M, a.N, a.K, splits, nb, stream);
+  if (!a.a_trans && !a.b_trans) return launch<BN, 0, 0>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
+  if (!a.a_trans && a.b_trans) return launch<BN, 0, 1>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
+  if (a.a_trans && a.b_trans) return launch<BN, 1, 1>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
+  return launch<BN, 1, 0>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
 }
 
 }  // namespace
@@ -523,26 +584,50 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   if (!linear) splits = 1;
   if (splits > kblocks) splits = kblocks;
 
-  CUtensorMap tmA, tmB;
-  if (!a.a_trans) SER_TRY(make_tmap(&tmA, a.A, a.M, a.K, a.lda, BM, BK, a.batch, a.strideA));
-  else            SER_TRY(make_tmap(&tmA, a.A, a.K, a.M, a.lda, BK, 64, a.batch, a.strideA));
-  if (!a.b_trans) SER_TRY(make_tmap(&tmB, a.B, a.N, a.K, a.ldb, BN, BK, a.batch, a.strideB));
-  else            SER_TRY(make_tmap(&tmB, a.B, a.K, a.N, a.ldb, BK, 64, a.batch, a.strideB));
+  SER_REQUIRE(a.batch <= 1 || (a.strideA % 8 == 0 && a.strideB % 8 == 0 && a.strideC % 8 == 0),
+              "gemm_tc: batch strides must be multiples of 8");
+  SER_REQUIRE((reinterpret_cast<uintptr_t>(a.C) & 15) == 0, "gemm_tc: output must be 16-byte aligned");
+  CUtensorMap tmA, tmB, tmC, tmS;
+  if (!a.a_trans) SER_TRY(make_tmap(&tmA, a.A, 0, a.M, a.K, a.lda, BM, BK, a.batch, a.strideA));
+  else            SER_TRY(make_tmap(&tmA, a.A, 0, a.K, a.M, a.lda, BK, 64, a.batch, a.strideA));
+  if (!a.b_trans) SER_TRY(make_tmap(&tmB, a.B, 0, a.N, a.K, a.ldb, BN, BK, a.batch, a.strideB));
+  else            SER_TRY(make_tmap(&tmB, a.B, 0, a.K, a.N, a.ldb, BK, 64, a.batch, a.strideB));
 
+  // epilogue operands travel as 32-row x 128-byte TMA boxes: 64 bf16 or 32 fp32 columns
+  const int cw = a.c_f32 ? 32 : 64;
+  SER_TRY(make_tmap(&tmC, a.C, a.c_f32, a.M, a.N, a.ldc, 32, cw, a.batch, a.strideC));
   TcEpilogue ep;
-  ep.C = a.C; ep.ldc = a.ldc; ep.c_f32 = a.c_f32;
+  ep.c_f32 = a.c_f32;
   ep.bias = a.bias;
-  ep.R = a.R; ep.ldr = a.ldr; ep.r_f32 = a.r_f32;
-  ep.G = a.G; ep.ldg = a.ldg; ep.g_f32 = a.g_f32; ep.gate_mode = a.gate_mode;
+  ep.gate_mode = a.gate_mode;
   ep.act = a.act;
   ep.alpha = a.alpha;
-  ep.strideC = a.strideC; ep.strideR = a.strideR; ep.strideG = a.strideG;
-  SER_REQUIRE(a.batch <= 1 || (a.strideA % 8 == 0 && a.strideB % 8 == 0), "gemm_tc: batch strides must be multiples of 8");
+  ep.src = SRC_NONE;
+  const void* R = a.R;
   int accumulate = a.accumulate;
-  if (splits > 1 && a.R != nullptr && a.R == a.C) {
+  if (splits > 1 && R != nullptr && R == a.C) {
     // in-place residual with split-K: C already holds R, so every split simply accumulates into it
-    ep.R = nullptr;
+    R = nullptr;
     accumulate = 1;
+  }
+  if (R != nullptr && a.gate_mode != GATE_NONE) {
+    set_last_error(__FILE__, __LINE__, "gemm_tc: residual and gate operands cannot be combined");
+    return SER_ERR_UNSUPPORTED;
+  }
+  if (R != nullptr) {
+    SER_REQUIRE(a.r_f32 == a.c_f32, "gemm_tc: the residual must have the output's element type");
+    SER_REQUIRE((reinterpret_cast<uintptr_t>(R) & 15) == 0 && (a.batch <= 1 || a.strideR % 8 == 0),
+                "gemm_tc: residual must be 16-byte aligned");
+    SER_TRY(make_tmap(&tmS, R, a.r_f32, a.M, a.N, a.ldr, 32, cw, a.batch, a.strideR));
+    ep.src = SRC_RESIDUAL;
+  } else if (a.gate_mode != GATE_NONE) {
+    SER_REQUIRE(!a.c_f32, "gemm_tc: a gated GEMM writes bf16 (the gate operand's element type)");
+    SER_REQUIRE((reinterpret_cast<uintptr_t>(a.G) & 15) == 0 && (a.batch <= 1 || a.strideG % 8 == 0),
+                "gemm_tc: gate operand must be 16-byte aligned");
+    SER_TRY(make_tmap(&tmS, a.G, 0, a.M, a.N, a.ldg, 32, cw, a.batch, a.strideG));
+    ep.src = SRC_GATE;
+  } else {
+    tmS = tmC;
   }
   ep.atomic = (splits > 1 || accumulate) ? 1 : 0;
   if (ep.atomic) {
@@ -563,8 +648,8 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
     snprintf(pname, sizeof(pname), "%s:%dx%dx%d:s%d", a.a_trans ? "gemm_tc_wgrad" : (a.b_trans ? "gemm_tc_dgrad" : "gemm_tc_fwd"),
              a.M, a.N, a.K, splits);
   ProfScope prof(pname, gflops, gbytes, stream);
-  if (BN == 256) return dispatch_major<256>(a, tmA, tmB, ep, splits, stream);
-  return dispatch_major<128>(a, tmA, tmB, ep, splits, stream);
+  if (BN == 256) return dispatch_major<256>(a, tmA, tmB, tmC, tmS, ep, splits, stream);
+  return dispatch_major<128>(a, tmA, tmB, tmC, tmS, ep, splits, stream);
 }
 
 }  // namespace ser
