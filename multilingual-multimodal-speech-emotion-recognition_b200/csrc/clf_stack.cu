@@ -1,0 +1,732 @@
+// The 35-block residual stack of AdvancedOpenMaxClassifier as ONE kernel per direction (bf16 tier).
+//
+// Reference: src/models/classifier.py:207-212 (outer LayerNorm -> block -> residual from the outer-LN output)
+// and :79-89 (block = LayerNorm -> Linear -> ReLU -> Linear).  Per block i:
+//     y = LN_o(h_i);  n = LN_i(y);  u = relu(W1 n + b1);  h_{i+1} = y + W2 u + b2
+// 70 strictly sequential [B,512]x[512,512] GEMMs separated by row-wise LayerNorms: launched layer by layer this
+// is pure launch / fill latency (0.13 GFLOP per launch).  Here a thread-block CLUSTER of 8 CTAs owns 128 batch
+// rows for the whole stack:
+//   * CTA j of the cluster owns output columns [64j, 64j+64) of every GEMM: its 64x512 weight slice streams through
+//     an 8-stage TMA ring (always one GEMM ahead), the accumulator is a 128x64 fp32 tile in TMEM,
+//     tcgen05.mma M=128 N=64 K=16 issued by one thread.
+//   * every epilogue thread owns one row x 64 columns IN REGISTERS across the block (the residual y never leaves
+//     the register file); LayerNorm statistics are combined across the 8 column slices through distributed
+//     shared memory (st.shared::cluster + barrier.cluster), Chan-style (mean, M2) so the variance is two-pass exact.
+//   * the full-width GEMM operand (n, u, and in backward dh, da) is exchanged through the SAME global buffers the
+//     backward pass needs anyway (saved activations / weight-gradient operands): each CTA stores its bf16 slice,
+//     a cluster barrier orders it, and every CTA pulls the 128x512 operand back as eight 128B-swizzled TMA boxes.
+// Backward mirrors it with the weights read MN-major in place (dX = dY W), recomputing x-hat from the saved h and
+// statistics, and reduces the four LayerNorm parameter gradients over rows with a register transpose-reduce.
+// The batched weight-gradient GEMMs stay outside (head_modules.cu).
+#include "kernels.cuh"
+#include "prof.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace ser {
+
+namespace {
+
+constexpr int CS = 8;                 // CTAs per cluster = column slices
+constexpr int PD = 512;               // base_dim of the stack
+constexpr int NS = PD / CS;           // 64 output columns per CTA
+constexpr int RM = 128;               // rows per cluster (UMMA M)
+constexpr int KBLK = PD / 64;         // 8 k-blocks of 64
+constexpr int A_BYTES = RM * 128;     // one k-block of the A operand: 128 rows x 128 B
+constexpr int W_BYTES = NS * 128;     // one weight stage: 64 x 64 bf16
+constexpr int kThreads = 192;
+constexpr float kEps = 1e-5f;
+
+constexpr int OFF_A = 0;
+constexpr int OFF_W = OFF_A + KBLK * A_BYTES;                 // 131072
+constexpr int OFF_STATS = OFF_W + KBLK * W_BYTES;             // 196608: float2 [2][CS][RM]
+constexpr int OFF_COLACC = OFF_STATS + 2 * CS * RM * 8;       // 212992: float [4][NS]
+constexpr int OFF_BARS = OFF_COLACC + 4 * NS * 4;             // 214016
+constexpr int kSmemBytes = OFF_BARS + 256 + 1024;
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float2 ld_shared_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// shared-memory matrix descriptor (sm_100), SWIZZLE_128B; see gemm_tc.cu
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+template <int BMAJ> __device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BMAJ) << 16) |
+         (static_cast<uint32_t>(NS >> 3) << 17) | (static_cast<uint32_t>(RM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// shared pieces of the two kernels
+// ---------------------------------------------------------------------------------------------------------
+struct Ctx {
+  uint32_t sA, sW, sStats, sColacc;      // shared-window addresses
+  uint32_t a_full, w_full, w_empty, acc_full;   // first barrier of each family (8 bytes apart)
+  uint32_t tmem;
+  uint32_t rank;                         // column slice of this CTA
+  int row0;                              // first row of the cluster
+};
+
+__device__ __forceinline__ uint32_t bar_at(uint32_t base, int i) { return base + 8u * static_cast<uint32_t>(i); }
+
+// MMA issuer: one GEMM = 8 k-blocks x 4 tcgen05.mma (M=128, N=64, K=16) into the 64-column accumulator
+template <int BMAJ>
+__device__ __forceinline__ void issue_gemm(const Ctx& c, uint32_t parity) {
+  constexpr uint32_t idesc = make_idesc<BMAJ>();
+  constexpr uint32_t b_kstep = (BMAJ == 0) ? 32u : 16u * 128u;     // bytes per K = 16 step inside a weight stage
+  constexpr uint32_t b_lbo = (BMAJ == 0) ? 0u : 64u * 128u;
+  for (int kb = 0; kb < KBLK; ++kb) {
+    mbar_wait(bar_at(c.a_full, kb), parity);
+    mbar_wait(bar_at(c.w_full, kb), parity);
+    tc_fence_after();
+    const uint32_t sa = c.sA + kb * A_BYTES;
+    const uint32_t sb = c.sW + kb * W_BYTES;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t adesc = make_smem_desc(sa + k * 32u, 0u, 1024u);
+      const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024u);
+      tc_mma_bf16(c.tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+    }
+    tc_commit(bar_at(c.w_empty, kb));      // weight stage (and this k-block of A) consumed
+  }
+  tc_commit(c.acc_full);
+}
+
+// producer: full-width A operand (128 rows x 512) of one GEMM from the exchange buffer `tm` (layer `layer`)
+__device__ __forceinline__ void load_a(const Ctx& c, const CUtensorMap* tm, int layer) {
+  fence_proxy_async_all();
+  for (int kb = 0; kb < KBLK; ++kb) {
+    mbar_expect_tx(bar_at(c.a_full, kb), A_BYTES);
+    tma_load_3d(tm, bar_at(c.a_full, kb), c.sA + kb * A_BYTES, kb * 64, c.row0, layer);
+  }
+}
+// producer: weight slice of one GEMM.  FWD: rows = output features of this CTA, columns = k; BWD (MN-major):
+// rows = k (output features of the forward Linear), columns = this CTA's input features.
+template <int BMAJ>
+__device__ __forceinline__ void load_w(const Ctx& c, const CUtensorMap* tm, int layer, bool wait_empty, uint32_t empty_parity) {
+  for (int kb = 0; kb < KBLK; ++kb) {
+    if (wait_empty) mbar_wait(bar_at(c.w_empty, kb), empty_parity);
+    mbar_expect_tx(bar_at(c.w_full, kb), W_BYTES);
+    if (BMAJ == 0) tma_load_3d(tm, bar_at(c.w_full, kb), c.sW + kb * W_BYTES, kb * 64, static_cast<int>(c.rank) * NS, layer);
+    else           tma_load_3d(tm, bar_at(c.w_full, kb), c.sW + kb * W_BYTES, static_cast<int>(c.rank) * NS, kb * 64, layer);
+  }
+}
+
+// all-reduce of two per-row partial values over the 8 column slices of the cluster (one cluster barrier)
+__device__ __forceinline__ void exchange2(const Ctx& c, int buf, int rl, float a, float b, float (&oa)[CS], float (&ob)[CS]) {
+  const uint32_t slot = c.sStats + static_cast<uint32_t>(((buf * CS + static_cast<int>(c.rank)) * RM + rl) * 8);
+#pragma unroll
+  for (int t = 0; t < CS; ++t) st_cluster_f2(map_to_cta(slot, t), a, b);
+  cluster_sync_all();
+#pragma unroll
+  for (int s = 0; s < CS; ++s) {
+    const float2 v = ld_shared_f2(c.sStats + static_cast<uint32_t>(((buf * CS + s) * RM + rl) * 8));
+    oa[s] = v.x; ob[s] = v.y;
+  }
+}
+
+// LayerNorm statistics of a 512-wide row held as 8 slices of 64: local two-pass (mean, M2), Chan combination
+__device__ __forceinline__ void row_stats(const Ctx& c, int buf, int rl, const float (&v)[NS], float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) s += v[k];
+  const float m = s * (1.f / NS);
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) { const float d = v[k] - m; q = fmaf(d, d, q); }
+  float ms[CS], qs[CS];
+  exchange2(c, buf, rl, m, q, ms, qs);
+  float mu = 0.f;
+#pragma unroll
+  for (int t = 0; t < CS; ++t) mu += ms[t];
+  mu *= (1.f / CS);
+  float m2 = 0.f;
+#pragma unroll
+  for (int t = 0; t < CS; ++t) { const float d = ms[t] - mu; m2 += qs[t] + static_cast<float>(NS) * d * d; }
+  mean = mu;
+  rstd = rsqrtf(m2 * (1.f / PD) + kEps);
+}
+
+__device__ __forceinline__ void load_vec64(const float* __restrict__ p, float (&v)[NS]) {
+#pragma unroll
+  for (int k = 0; k < NS / 4; ++k) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + k);
+    v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void load_vec32(const float* __restrict__ p, float (&v)[32]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + k);
+    v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void store_bf16_64(__nv_bfloat16* p, const float (&v)[NS]) {
+#pragma unroll
+  for (int k = 0; k < NS / 8; ++k) {
+    uint4 w;
+    w.x = pack2(v[8 * k], v[8 * k + 1]); w.y = pack2(v[8 * k + 2], v[8 * k + 3]);
+    w.z = pack2(v[8 * k + 4], v[8 * k + 5]); w.w = pack2(v[8 * k + 6], v[8 * k + 7]);
+    reinterpret_cast<uint4*>(p)[k] = w;
+  }
+}
+__device__ __forceinline__ void store_f32_64(float* p, const float (&v)[NS]) {
+#pragma unroll
+  for (int k = 0; k < NS / 4; ++k) reinterpret_cast<float4*>(p)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+// a slice written for the other CTAs of the cluster: order it before the cluster barrier and before the TMA reads
+__device__ __forceinline__ void publish() {
+  __threadfence();
+  fence_proxy_async_all();
+}
+
+struct StackParams {
+  int B, L;
+  // per-layer parameter vectors: pointer of layer 0 + element stride between layers
+  const float* b1; const float* b2; const float* lni_g; const float* lni_b; long long s_blk;   // block params share one stride
+  const float* lno_g; const float* lno_b; long long s_lno;
+  float* h;                 // [(L+1), B, 512] fp32 residual stream (h[0] is the input)
+  __nv_bfloat16* n; __nv_bfloat16* r;      // [L, B, 512] exchange + saved operands
+  float* stats_o; float* stats_i;          // [L, B, 2]
+  // backward
+  const float* dh_in; float* dh_out;       // [B, 512] fp32: dL/dh_L in, dL/dh_0 out
+  __nv_bfloat16* dhn; __nv_bfloat16* dr;   // [L, B, 512] exchange + weight-gradient operands
+  float* dlni_g; float* dlni_b; float* dlno_g; float* dlno_b;    // layer 0 pointers (strides as the parameters)
+};
+
+__device__ __forceinline__ void setup(Ctx& c, uint8_t* smem, int warp, int lane) {
+  c.sA = smem_u32(smem + OFF_A);
+  c.sW = smem_u32(smem + OFF_W);
+  c.sStats = smem_u32(smem + OFF_STATS);
+  c.sColacc = smem_u32(smem + OFF_COLACC);
+  const uint32_t bars = smem_u32(smem + OFF_BARS);
+  c.a_full = bars; c.w_full = bars + 64; c.w_empty = bars + 128; c.acc_full = bars + 192;
+  const uint32_t tmem_slot = bars + 200;
+  c.rank = cluster_rank();
+  c.row0 = static_cast<int>(blockIdx.x / CS) * RM;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < KBLK; ++i) { mbar_init(bar_at(c.a_full, i), 1); mbar_init(bar_at(c.w_full, i), 1); mbar_init(bar_at(c.w_empty, i), 1); }
+    mbar_init(c.acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(64) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c.tmem) : "r"(tmem_slot) : "memory");
+  cluster_sync_all();            // every CTA's barriers / stats buffers exist before any remote traffic
+}
+
+__device__ __forceinline__ void teardown(const Ctx& c, int warp) {
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "r"(64) : "memory");
+  }
+  cluster_sync_all();            // no CTA leaves while a peer may still address its shared memory
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kThreads, 1)
+clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                     const __grid_constant__ CUtensorMap tmN, const __grid_constant__ CUtensorMap tmR,
+                     const StackParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Ctx c;
+  setup(c, smem, warp, lane);
+  const int L = p.L;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) load_w<0>(c, &tmW1, 0, false, 0);
+    for (int g = 0; g < 2 * L; ++g) {
+      const int layer = g >> 1;
+      __syncwarp();
+      if ((g & 1) == 0) { cluster_sync_all(); cluster_sync_all(); }     // the two LayerNorm statistics rounds
+      cluster_sync_all();                                               // operand slices of GEMM g published
+      if (lane == 0) {
+        load_a(c, (g & 1) ? &tmR : &tmN, layer);
+        if (g + 1 < 2 * L) load_w<0>(c, ((g + 1) & 1) ? &tmW2 : &tmW1, (g + 1) >> 1, true, static_cast<uint32_t>(g & 1));
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    for (int g = 0; g < 2 * L; ++g) {
+      __syncwarp();
+      if ((g & 1) == 0) { cluster_sync_all(); cluster_sync_all(); }
+      cluster_sync_all();
+      if (lane == 0) { tc_fence_after(); issue_gemm<0>(c, static_cast<uint32_t>(g & 1)); }
+    }
+  } else {
+    // ------------------------------------------------------------------ row owners (4 warps x 32 rows)
+    const int q = warp & 3;
+    const int rl = q * 32 + lane;
+    const int row = c.row0 + rl;
+    const bool valid = row < p.B;
+    const int col0 = static_cast<int>(c.rank) * NS;
+    const uint32_t taddr = c.tmem + (static_cast<uint32_t>(q * 32) << 16);
+    const size_t BP = static_cast<size_t>(p.B) * PD;
+    float hv[NS];
+    if (valid) load_vec64(p.h + static_cast<size_t>(row) * PD + col0, hv);
+    else {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) hv[k] = 0.f;
+    }
+    for (int i = 0; i < L; ++i) {
+      float par[NS];
+      // ---- y = LN_outer(h)
+      float mu, rs;
+      row_stats(c, 0, rl, hv, mu, rs);
+      if (valid && c.rank == 0) *reinterpret_cast<float2*>(p.stats_o + (static_cast<size_t>(i) * p.B + row) * 2) = make_float2(mu, rs);
+      load_vec64(p.lno_g + i * p.s_lno + col0, par);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) hv[k] = (hv[k] - mu) * rs * par[k];
+      load_vec64(p.lno_b + i * p.s_lno + col0, par);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) hv[k] += par[k];                    // hv now holds y (kept for the residual)
+      // ---- n = LN_inner(y)
+      row_stats(c, 1, rl, hv, mu, rs);
+      if (valid && c.rank == 0) *reinterpret_cast<float2*>(p.stats_i + (static_cast<size_t>(i) * p.B + row) * 2) = make_float2(mu, rs);
+      float nv[NS];
+      load_vec64(p.lni_g + i * p.s_blk + col0, par);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) nv[k] = (hv[k] - mu) * rs * par[k];
+      load_vec64(p.lni_b + i * p.s_blk + col0, par);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) nv[k] += par[k];
+      if (valid) store_bf16_64(p.n + i * BP + static_cast<size_t>(row) * PD + col0, nv);
+      publish();
+      tc_fence_before();
+      cluster_sync_all();
+      // ---- u = relu(W1 n + b1)
+      mbar_wait(c.acc_full, 0u);
+      tc_fence_after();
+      tmem_ld32(taddr, nv);
+      tmem_ld32(taddr + 32, nv + 32);
+      load_vec64(p.b1 + i * p.s_blk + col0, par);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) nv[k] = fmaxf(nv[k] + par[k], 0.f);
+      if (valid) store_bf16_64(p.r + i * BP + static_cast<size_t>(row) * PD + col0, nv);
+      publish();
+      tc_fence_before();
+      cluster_sync_all();
+      // ---- h_next = y + W2 u + b2
+      mbar_wait(c.acc_full, 1u);
+      tc_fence_after();
+      tmem_ld32(taddr, nv);
+      tmem_ld32(taddr + 32, nv + 32);
+      load_vec64(p.b2 + i * p.s_blk + col0, par);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) hv[k] += nv[k] + par[k];
+      if (valid) store_f32_64(p.h + (i + 1) * BP + static_cast<size_t>(row) * PD + col0, hv);
+      tc_fence_before();
+    }
+  }
+  teardown(c, warp);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward (dX chain + LayerNorm parameter gradients)
+// ---------------------------------------------------------------------------------------------------------
+// sum over the 32 lanes of v[0..31] (one value per column): lane l ends up with the total of column l
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = up ? v[k] : v[k + off];
+      const float keep = up ? v[k + off] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+__device__ __forceinline__ void colacc_add(const Ctx& c, int which, int col, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(c.sColacc + static_cast<uint32_t>((which * NS + col) * 4)), "f"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kThreads, 1)
+clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                     const __grid_constant__ CUtensorMap tmDhn, const __grid_constant__ CUtensorMap tmDr,
+                     const StackParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Ctx c;
+  setup(c, smem, warp, lane);
+  const int L = p.L;
+
+  // GEMM g (g = 0 .. 2L-1): even = du = dh W2 of block L-1-g/2, odd = dn = da W1 of the same block
+  if (warp == 0) {
+    if (lane == 0) load_w<1>(c, &tmW2, L - 1, false, 0);
+    for (int g = 0; g < 2 * L; ++g) {
+      const int layer = L - 1 - (g >> 1);
+      __syncwarp();
+      cluster_sync_all();                                               // operand slices of GEMM g published
+      if (lane == 0) {
+        load_a(c, (g & 1) ? &tmDr : &tmDhn, layer);
+        if (g + 1 < 2 * L) {
+          const int nl = L - 1 - ((g + 1) >> 1);
+          load_w<1>(c, ((g + 1) & 1) ? &tmW1 : &tmW2, nl, true, static_cast<uint32_t>(g & 1));
+        }
+      }
+      __syncwarp();
+      if (g & 1) { cluster_sync_all(); cluster_sync_all(); }            // the two LayerNorm-backward reduction rounds
+    }
+  } else if (warp == 1) {
+    for (int g = 0; g < 2 * L; ++g) {
+      __syncwarp();
+      cluster_sync_all();
+      if (lane == 0) { tc_fence_after(); issue_gemm<1>(c, static_cast<uint32_t>(g & 1)); }
+      __syncwarp();
+      if (g & 1) { cluster_sync_all(); cluster_sync_all(); }
+    }
+  } else {
+    const int q = warp & 3;
+    const int rl = q * 32 + lane;
+    const int row = c.row0 + rl;
+    const bool valid = row < p.B;
+    const int col0 = static_cast<int>(c.rank) * NS;
+    const uint32_t taddr = c.tmem + (static_cast<uint32_t>(q * 32) << 16);
+    const size_t BP = static_cast<size_t>(p.B) * PD;
+    const int et = threadIdx.x - 64;                 // 0..127 among the row owners
+    // zero the column accumulators (each thread owns two of the 256 entries)
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.sColacc + et * 4), "f"(0.f) : "memory");
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.sColacc + (et + 128) * 4), "f"(0.f) : "memory");
+    named_bar_sync(1, 128);
+    float gv[NS];
+    if (valid) load_vec64(p.dh_in + static_cast<size_t>(row) * PD + col0, gv);
+    else {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) gv[k] = 0.f;
+    }
+    for (int i = L - 1; i >= 0; --i) {
+      // ---- publish dh_{i+1} (bf16): A operand of du = dh W2 and of the batched dW2 GEMM
+      if (valid) store_bf16_64(p.dhn + i * BP + static_cast<size_t>(row) * PD + col0, gv);
+      publish();
+      tc_fence_before();
+      cluster_sync_all();
+      // operands of the epilogues below, requested while the GEMM runs
+      float xo[NS];
+      float2 so = make_float2(0.f, 0.f), si = make_float2(0.f, 0.f);
+      uint4 um[NS / 8];
+      if (valid) {
+        load_vec64(p.h + i * BP + static_cast<size_t>(row) * PD + col0, xo);
+        so = *reinterpret_cast<const float2*>(p.stats_o + (static_cast<size_t>(i) * p.B + row) * 2);
+        si = *reinterpret_cast<const float2*>(p.stats_i + (static_cast<size_t>(i) * p.B + row) * 2);
+        const uint4* up = reinterpret_cast<const uint4*>(p.r + i * BP + static_cast<size_t>(row) * PD + col0);
+#pragma unroll
+        for (int k = 0; k < NS / 8; ++k) um[k] = up[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) xo[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < NS / 8; ++k) um[k] = make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int k = 0; k < NS; ++k) xo[k] = (xo[k] - so.x) * so.y;        // x-hat of the outer LayerNorm
+      // ---- da = du * (u > 0)
+      mbar_wait(c.acc_full, 0u);
+      tc_fence_after();
+      {
+        float du[NS];
+        tmem_ld32(taddr, du);
+        tmem_ld32(taddr + 32, du + 32);
+#pragma unroll
+        for (int k = 0; k < NS / 8; ++k) {
+          const uint32_t wds[4] = {um[k].x, um[k].y, um[k].z, um[k].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            // relu output is >= 0: "u > 0" <=> any magnitude bit set in the bf16 half
+            if ((wds[t] & 0x00007fffu) == 0u) du[8 * k + 2 * t] = 0.f;
+            if ((wds[t] & 0x7fff0000u) == 0u) du[8 * k + 2 * t + 1] = 0.f;
+          }
+        }
+        if (valid) store_bf16_64(p.dr + i * BP + static_cast<size_t>(row) * PD + col0, du);
+      }
+      publish();
+      tc_fence_before();
+      cluster_sync_all();
+      // ---- dn = da W1, then the two LayerNorm backward steps on the register-resident row slice
+      mbar_wait(c.acc_full, 1u);
+      tc_fence_after();
+      const float* go_p = p.lno_g + i * p.s_lno + col0;
+      const float* bo_p = p.lno_b + i * p.s_lno + col0;
+      const float* gi_p = p.lni_g + i * p.s_blk + col0;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float dn[32], t0[32], t1[32], go[32], bo[32], gi[32];
+        tmem_ld32(taddr + hh * 32, dn);
+        load_vec32(go_p + hh * 32, go); load_vec32(bo_p + hh * 32, bo); load_vec32(gi_p + hh * 32, gi);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const int kk = hh * 32 + k;
+          const float xi = (fmaf(xo[kk], go[k], bo[k]) - si.x) * si.y;
+          const float a = dn[k] * gi[k];
+          s1 += a; s2 = fmaf(a, xi, s2);
+          t0[k] = dn[k] * xi; t1[k] = dn[k];
+        }
+        const float cg = transpose_reduce32(t0, lane);
+        const float cb = transpose_reduce32(t1, lane);
+        colacc_add(c, 0, hh * 32 + lane, cg);
+        colacc_add(c, 1, hh * 32 + lane, cb);
+      }
+      {
+        float as[CS], bs[CS];
+        exchange2(c, 0, rl, s1, s2, as, bs);
+        s1 = 0.f; s2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < CS; ++t) { s1 += as[t]; s2 += bs[t]; }
+        s1 *= (1.f / PD); s2 *= (1.f / PD);
+      }
+      float u1 = 0.f, u2 = 0.f;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float dn[32], t0[32], t1[32], go[32], bo[32], gi[32];
+        tmem_ld32(taddr + hh * 32, dn);
+        load_vec32(go_p + hh * 32, go); load_vec32(bo_p + hh * 32, bo); load_vec32(gi_p + hh * 32, gi);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const int kk = hh * 32 + k;
+          const float xi = (fmaf(xo[kk], go[k], bo[k]) - si.x) * si.y;
+          const float a = dn[k] * gi[k];
+          const float dy = fmaf(si.y, a - s1 - xi * s2, gv[kk]);       // + skip gradient (residual from y)
+          gv[kk] = dy;
+          const float a2 = dy * go[k];
+          u1 += a2; u2 = fmaf(a2, xo[kk], u2);
+          t0[k] = dy * xo[kk]; t1[k] = dy;
+        }
+        const float cg = transpose_reduce32(t0, lane);
+        const float cb = transpose_reduce32(t1, lane);
+        colacc_add(c, 2, hh * 32 + lane, cg);
+        colacc_add(c, 3, hh * 32 + lane, cb);
+      }
+      tc_fence_before();
+      {
+        float as[CS], bs[CS];
+        exchange2(c, 1, rl, u1, u2, as, bs);
+        u1 = 0.f; u2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < CS; ++t) { u1 += as[t]; u2 += bs[t]; }
+        u1 *= (1.f / PD); u2 *= (1.f / PD);
+      }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float go[32];
+        load_vec32(go_p + hh * 32, go);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const int kk = hh * 32 + k;
+          gv[kk] = so.y * (gv[kk] * go[k] - u1 - xo[kk] * u2);
+        }
+      }
+      // ---- flush this block's LayerNorm parameter gradients (summed over the cluster's 128 rows)
+      named_bar_sync(1, 128);
+      {
+        float v0, v1;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(c.sColacc + et * 4) : "memory");
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(c.sColacc + (et + 128) * 4) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.sColacc + et * 4), "f"(0.f) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.sColacc + (et + 128) * 4), "f"(0.f) : "memory");
+        // entries: [0] dgamma_inner, [1] dbeta_inner, [2] dgamma_outer, [3] dbeta_outer, 64 columns each
+        const int w0 = et >> 6, cc = et & 63;            // et: 0..127 -> which 0/1 ; et+128 -> which 2/3
+        float* d0 = (w0 == 0 ? p.dlni_g : p.dlni_b) + i * p.s_blk + col0 + cc;
+        float* d1 = (w0 == 0 ? p.dlno_g : p.dlno_b) + i * p.s_lno + col0 + cc;
+        atomicAdd(d0, v0);
+        atomicAdd(d1, v1);
+      }
+      named_bar_sync(1, 128);
+    }
+    if (valid) store_f32_64(p.dh_out + static_cast<size_t>(row) * PD + col0, gv);
+  }
+  teardown(c, warp);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+// bf16 [layers][rows][512] (row pitch 512, layer pitch `layer_stride` elements), box = box_rows x 64 columns
+int make_map(CUtensorMap* tm, const void* base, long long rows, long long layer_stride, int layers, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) { set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable"); return SER_ERR_CUDA; }
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(PD), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(layers)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(PD) * 2, static_cast<cuuint64_t>(layer_stride) * 2};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error(__FILE__, __LINE__, "clf_stack: cuTensorMapEncodeTiled failed"); return SER_ERR_CUDA; }
+  return SER_OK;
+}
+
+template <typename K>
+int configure(K kern) {
+  SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  return SER_OK;
+}
+
+}  // namespace
+
+bool clf_stack_supported(int dtype, int P, int L, const ClfStackArgs& a) {
+  return dtype == DT_BF16 && P == PD && L >= 1 && a.s_blk > 0 && a.s_lno > 0 && a.s_w1 > 0 && a.s_w2 > 0 &&
+         (a.s_w1 % 8 == 0) && (a.s_w2 % 8 == 0);
+}
+
+static StackParams to_params(const ClfStackArgs& a) {
+  StackParams p{};
+  p.B = a.B; p.L = a.L;
+  p.b1 = a.b1; p.b2 = a.b2; p.lni_g = a.lni_g; p.lni_b = a.lni_b; p.s_blk = a.s_blk;
+  p.lno_g = a.lno_g; p.lno_b = a.lno_b; p.s_lno = a.s_lno;
+  p.h = a.h; p.n = reinterpret_cast<__nv_bfloat16*>(a.n); p.r = reinterpret_cast<__nv_bfloat16*>(a.r);
+  p.stats_o = a.stats_o; p.stats_i = a.stats_i;
+  p.dh_in = a.dh_in; p.dh_out = a.dh_out;
+  p.dhn = reinterpret_cast<__nv_bfloat16*>(a.dhn); p.dr = reinterpret_cast<__nv_bfloat16*>(a.dr);
+  p.dlni_g = a.dlni_g; p.dlni_b = a.dlni_b; p.dlno_g = a.dlno_g; p.dlno_b = a.dlno_b;
+  return p;
+}
+
+int clf_stack_fwd(const ClfStackArgs& a, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) { SER_TRY(configure(clf_stack_fwd_kernel)); configured = true; }
+  CUtensorMap tmW1, tmW2, tmN, tmR;
+  SER_TRY(make_map(&tmW1, a.w1, PD, a.s_w1, a.L, NS));
+  SER_TRY(make_map(&tmW2, a.w2, PD, a.s_w2, a.L, NS));
+  SER_TRY(make_map(&tmN, a.n, a.B, static_cast<long long>(a.B) * PD, a.L, RM));
+  SER_TRY(make_map(&tmR, a.r, a.B, static_cast<long long>(a.B) * PD, a.L, RM));
+  const int clusters = ceil_div(a.B, RM);
+  // algorithmic work: 2 GEMMs per block; bytes: weights once per cluster + the fp32 stream and bf16 operands
+  ProfScope prof("clf_stack_fwd", 4.0 * a.B * PD * PD * a.L,
+                 static_cast<double>(a.L) * (2.0 * PD * PD * 2 * clusters + a.B * PD * (4.0 + 2.0 + 2.0)), s);
+  clf_stack_fwd_kernel<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmN, tmR, to_params(a));
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+int clf_stack_bwd(const ClfStackArgs& a, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) { SER_TRY(configure(clf_stack_bwd_kernel)); configured = true; }
+  CUtensorMap tmW1, tmW2, tmDhn, tmDr;
+  SER_TRY(make_map(&tmW1, a.w1, PD, a.s_w1, a.L, 64));
+  SER_TRY(make_map(&tmW2, a.w2, PD, a.s_w2, a.L, 64));
+  SER_TRY(make_map(&tmDhn, a.dhn, a.B, static_cast<long long>(a.B) * PD, a.L, RM));
+  SER_TRY(make_map(&tmDr, a.dr, a.B, static_cast<long long>(a.B) * PD, a.L, RM));
+  const int clusters = ceil_div(a.B, RM);
+  ProfScope prof("clf_stack_bwd", 4.0 * a.B * PD * PD * a.L,
+                 static_cast<double>(a.L) * (2.0 * PD * PD * 2 * clusters + a.B * PD * (4.0 + 2.0 + 2.0 + 2.0)), s);
+  clf_stack_bwd_kernel<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmDhn, tmDr, to_params(a));
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+}  // namespace ser

@@ -2,6 +2,7 @@
 // reference module (forward or backward) on the caller's stream.  The same code drives both tiers:
 // `dtype` picks the CUDA-core fp32 GEMM or the tcgen05 bf16 GEMM and the storage type of activations.
 #include "kernels.cuh"
+#include <stdlib.h>
 #include "../../include/ser_head.h"
 
 namespace ser {
@@ -358,6 +359,44 @@ int fusion_bwd(const ser_fusion_desc& d, cudaStream_t s) {
 // =================================================================================================
 // a5 classifier stack + heads
 // =================================================================================================
+
+// Arguments of the fused stack kernels (clf_stack.cu) when the per-layer pointers are uniformly strided
+// (they are: every module keeps its parameters in one flat buffer, _params.FlatParams).
+static bool stack_args(const ser_clf_desc& d, ClfStackArgs& a) {
+  const int L = d.L;
+  a = ClfStackArgs{};
+  a.B = d.B; a.L = L;
+  if (d.dtype != DT_BF16 || L < 2) return false;
+  static const bool disabled = (getenv("SER_NO_FUSED_CLF") != nullptr);     // A/B switch: per-layer launches instead
+  if (disabled) return false;
+  auto estride = [](const void* p1, const void* p0, size_t es) {
+    return static_cast<long long>((reinterpret_cast<const char*>(p1) - reinterpret_cast<const char*>(p0)) / static_cast<long long>(es));
+  };
+  a.w1 = d.w1[0]; a.s_w1 = estride(d.w1[1], d.w1[0], 2);
+  a.w2 = d.w2[0]; a.s_w2 = estride(d.w2[1], d.w2[0], 2);
+  a.b1 = d.b1[0]; a.b2 = d.b2[0]; a.lni_g = d.lni_g[0]; a.lni_b = d.lni_b[0];
+  a.s_blk = estride(d.b1[1], d.b1[0], 4);
+  a.lno_g = d.lno_g[0]; a.lno_b = d.lno_b[0]; a.s_lno = estride(d.lno_g[1], d.lno_g[0], 4);
+  for (int i = 1; i < L; ++i) {
+    if (estride(d.w1[i], d.w1[i - 1], 2) != a.s_w1 || estride(d.w2[i], d.w2[i - 1], 2) != a.s_w2) return false;
+    if (estride(d.b1[i], d.b1[i - 1], 4) != a.s_blk || estride(d.b2[i], d.b2[i - 1], 4) != a.s_blk ||
+        estride(d.lni_g[i], d.lni_g[i - 1], 4) != a.s_blk || estride(d.lni_b[i], d.lni_b[i - 1], 4) != a.s_blk) return false;
+    if (estride(d.lno_g[i], d.lno_g[i - 1], 4) != a.s_lno || estride(d.lno_b[i], d.lno_b[i - 1], 4) != a.s_lno) return false;
+  }
+  a.h = d.h; a.n = d.n; a.r = d.r; a.stats_o = d.stats_o; a.stats_i = d.stats_i;
+  return clf_stack_supported(d.dtype, d.P, L, a);
+}
+static bool stack_grad_args(const ser_clf_desc& d, ClfStackArgs& a) {
+  const int L = d.L;
+  auto estride = [](const float* p1, const float* p0) { return static_cast<long long>(p1 - p0); };
+  a.dlni_g = d.dlni_g[0]; a.dlni_b = d.dlni_b[0]; a.dlno_g = d.dlno_g[0]; a.dlno_b = d.dlno_b[0];
+  for (int i = 1; i < L; ++i) {
+    if (estride(d.dlni_g[i], d.dlni_g[i - 1]) != a.s_blk || estride(d.dlni_b[i], d.dlni_b[i - 1]) != a.s_blk) return false;
+    if (estride(d.dlno_g[i], d.dlno_g[i - 1]) != a.s_lno || estride(d.dlno_b[i], d.dlno_b[i - 1]) != a.s_lno) return false;
+  }
+  return true;
+}
+
 int clf_fwd(const ser_clf_desc& d, cudaStream_t s) {
   const int dt = d.dtype, f = is_f32(dt);
   const int B = d.B, P = d.P, F = d.F, L = d.L;
@@ -366,7 +405,10 @@ int clf_fwd(const ser_clf_desc& d, cudaStream_t s) {
   // input_projection: Linear -> LayerNorm -> ReLU (classifier.py:105-110)
   SER_TRY(linear_fwd(dt, B, P, P, d.x, P, d.w_in, P, d.b_in, d.p0, P, 1, ACT_NONE, nullptr, 0, 1, s));
   SER_TRY(layernorm_fwd(d.p0, 1, d.h, 1, nullptr, 1, d.ln_in_g, d.ln_in_b, d.stats0, B, P, 1, s));
-  for (int i = 0; i < L; ++i) {
+  ClfStackArgs sa;
+  const bool fused = stack_args(d, sa);
+  if (fused) SER_TRY(clf_stack_fwd(sa, s));          // all L blocks in one cluster kernel (clf_stack.cu)
+  for (int i = 0; i < L && !fused; ++i) {
     float* hi = d.h + i * BP;
     float* hn = d.h + (i + 1) * BP;
     float* yi = d.y + i * BP;
@@ -462,13 +504,22 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
   SER_TRY(colsum(dq, f, F, B, F, d.db_out, s));
   SER_TRY(linear_wgrad(dt, B, F, P, dq, F, d.h_last, P, d.dw_out, P, s));
   SER_TRY(linear_dgrad(dt, B, F, P, dq, F, d.w_out, P, dh32, P, 1, nullptr, 0, 1, GATE_NONE, nullptr, 0, 1, s));
-  SER_TRY(cast_any(dh32, 1, off(dhn_all, static_cast<long long>(L - 1) * BP, dt), f, static_cast<long long>(BP), s));
+  ClfStackArgs sa;
+  bool fused = stack_args(d, sa) && stack_grad_args(d, sa);
+  if (fused) {
+    // the whole dX chain + LayerNorm parameter gradients in one cluster kernel; it leaves dL/dh_0 in dh32b and the
+    // per-block GEMM operands (dh_{i+1}, da_i as bf16) in dhn_all / dr_all for the batched weight gradients below
+    sa.dh_in = dh32; sa.dh_out = dh32b; sa.dhn = dhn_all; sa.dr = dr_all;
+    SER_TRY(clf_stack_bwd(sa, s));
+  } else {
+    SER_TRY(cast_any(dh32, 1, off(dhn_all, static_cast<long long>(L - 1) * BP, dt), f, static_cast<long long>(BP), s));
+  }
   // ---- 35 residual blocks, last to first: only the serial dX chain lives in the loop ----
   // LayerNorm parameter gradients accumulate with atomics: the per-block dlni / dlno buffers must arrive zeroed
   // (they are slices of the caller's zero-initialised gradient buffer).
-  float* cur = dh32;
-  float* nxt = dh32b;
-  for (int i = L - 1; i >= 0; --i) {
+  float* cur = fused ? dh32b : dh32;
+  float* nxt = fused ? dh32 : dh32b;
+  for (int i = L - 1; i >= 0 && !fused; --i) {
     const float* hi = d.h + i * BP;
     const void* ri = off(static_cast<const void*>(d.r), static_cast<long long>(i) * BP, dt);
     void* dhn_i = off(dhn_all, static_cast<long long>(i) * BP, dt);

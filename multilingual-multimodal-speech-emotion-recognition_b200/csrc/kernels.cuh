@@ -56,6 +56,22 @@ int attention_bwd(const AttnArgs& a, cudaStream_t s);
 int attention_fwd_tc(const AttnArgs& a, cudaStream_t s);
 int attention_bwd_tc(const AttnArgs& a, cudaStream_t s);
 
+// ---- clf_stack.cu --------------------------------------------------------------------------------
+// The whole residual stack (classifier.py:207-212) as one cluster kernel per direction, bf16 tier, base_dim 512.
+// Per-layer parameters are addressed as (layer-0 pointer, element stride between layers).
+struct ClfStackArgs {
+  int B, L;
+  const void* w1; long long s_w1; const void* w2; long long s_w2;      // bf16 [512,512] per layer
+  const float* b1; const float* b2; const float* lni_g; const float* lni_b; long long s_blk;
+  const float* lno_g; const float* lno_b; long long s_lno;
+  float* h; void* n; void* r; float* stats_o; float* stats_i;           // saved activations (see ser_clf_desc)
+  const float* dh_in; float* dh_out; void* dhn; void* dr;               // backward
+  float* dlni_g; float* dlni_b; float* dlno_g; float* dlno_b;
+};
+bool clf_stack_supported(int dtype, int P, int L, const ClfStackArgs& a);
+int clf_stack_fwd(const ClfStackArgs& a, cudaStream_t s);
+int clf_stack_bwd(const ClfStackArgs& a, cudaStream_t s);
+
 // ---- pooling.cu ----------------------------------------------------------------------------------
 // Attentive statistics pooling, everything after the 768->128 tanh GEMM (src/models/pooling.py:21-28).
 struct AspArgs {

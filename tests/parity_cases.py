@@ -11,7 +11,8 @@ ReLU-mask / clamp / argmax flips of near-zero pre-activations perturb gradients 
 fp32 CPU-vs-GPU included, so a fixed tolerance alone would be a coin toss on small batches.
 Metric: max-abs error / max-abs reference (fp32 tier); Frobenius error / Frobenius reference (bf16 tier).
 Tensors that are mathematically zero (attention key biases, softmax-shift biases) are floored at 1% of the
-module's largest gradient.
+module's largest gradient.  Bias gradients with fewer than 16 elements (the [1] gate biases) take their noise floor
+from the weight of the same layer: one element is one draw of the noise, not an estimate of its scale.
 """
 from __future__ import annotations
 
@@ -101,7 +102,7 @@ class Case:
             self.inputs = saved
         fails, worst = [], 0.0
 
-        def one(kind, name, got, ref_exact, ref_noise, floor=0.0):
+        def one(kind, name, got, ref_exact, ref_noise, floor=0.0, companion=None):
             nonlocal worst
             if got is None:
                 fails.append(f"{kind} {name}: missing")
@@ -109,6 +110,10 @@ class Case:
             is_grad = kind != "out"
             e = _err(got, ref_exact, frob, floor, outliers=is_grad)
             n = _err(ref_noise, ref_exact, frob, floor, outliers=is_grad)
+            if companion is not None:
+                # a tensor with a handful of elements (a [1] gate bias) yields ONE draw of the reference-arithmetic
+                # noise, not its scale; take the scale from the weight of the same layer (thousands of draws)
+                n = max(n, _err(companion[1], companion[0], frob, floor, outliers=is_grad))
             lim = max(tol, NOISE_K * n)
             if is_grad and not frob:
                 # the set-aside outliers must be flip-sized, not garbage: bound the whole tensor in Frobenius norm
@@ -135,7 +140,12 @@ class Case:
                     if g_g.get(k) is not None and float(g_g[k].abs().max()) != 0.0:
                         fails.append(f"grad {k}: must be None / zero")
                     continue
-                one("grad", k, g_g.get(k), e_g[k], r_g[k], floor=1e-2 * scale)
+                comp = None
+                if e_g[k].numel() < 16 and k.endswith(".bias"):
+                    kw = k[:-len(".bias")] + ".weight"
+                    if kw in e_g:
+                        comp = (e_g[kw], r_g[kw])
+                one("grad", k, g_g.get(k), e_g[k], r_g[k], floor=1e-2 * scale, companion=comp)
         return fails, worst
 
 
