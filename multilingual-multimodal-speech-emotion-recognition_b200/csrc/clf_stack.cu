@@ -22,6 +22,7 @@
 #include "prof.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <stdlib.h>
 
 namespace ser {
 
@@ -41,7 +42,8 @@ constexpr int OFF_A = 0;
 constexpr int OFF_W = OFF_A + KBLK * A_BYTES;                 // 131072
 constexpr int OFF_STATS = OFF_W + KBLK * W_BYTES;             // 196608: float2 [2][CS][RM]
 constexpr int OFF_COLACC = OFF_STATS + 2 * CS * RM * 8;       // 212992: float [4][NS]
-constexpr int OFF_BARS = OFF_COLACC + 4 * NS * 4;             // 214016
+constexpr int OFF_PAR = OFF_COLACC + 4 * NS * 4;              // 214016: float [2][6][NS] per-layer parameter slices
+constexpr int OFF_BARS = OFF_PAR + 2 * 6 * NS * 4;            // 217088
 constexpr int kSmemBytes = OFF_BARS + 256 + 1024;
 
 // ---------------------------------------------------------------------------------------------------------
@@ -68,6 +70,14 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar,
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// the same box delivered to every CTA of the cluster (same shared offset, same barrier offset in each)
+__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -145,7 +155,7 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 // shared pieces of the two kernels
 // ---------------------------------------------------------------------------------------------------------
 struct Ctx {
-  uint32_t sA, sW, sStats, sColacc;      // shared-window addresses
+  uint32_t sA, sW, sStats, sColacc, sPar;   // shared-window addresses
   uint32_t a_full, w_full, w_empty, acc_full;   // first barrier of each family (8 bytes apart)
   uint32_t tmem;
   uint32_t rank;                         // column slice of this CTA
@@ -156,12 +166,13 @@ __device__ __forceinline__ uint32_t bar_at(uint32_t base, int i) { return base +
 
 // MMA issuer: one GEMM = 8 k-blocks x 4 tcgen05.mma (M=128, N=64, K=16) into the 64-column accumulator
 template <int BMAJ>
-__device__ __forceinline__ void issue_gemm(const Ctx& c, uint32_t parity) {
+__device__ __forceinline__ void issue_gemm(const Ctx& c, uint32_t parity, long long* tl = nullptr) {
   constexpr uint32_t idesc = make_idesc<BMAJ>();
   constexpr uint32_t b_kstep = (BMAJ == 0) ? 32u : 16u * 128u;     // bytes per K = 16 step inside a weight stage
   constexpr uint32_t b_lbo = (BMAJ == 0) ? 0u : 64u * 128u;
   for (int kb = 0; kb < KBLK; ++kb) {
     mbar_wait(bar_at(c.a_full, kb), parity);
+    if (tl != nullptr && (kb == 0 || kb == KBLK - 1)) tl[kb == 0 ? 1 : 2] = clock64();
     mbar_wait(bar_at(c.w_full, kb), parity);
     tc_fence_after();
     const uint32_t sa = c.sA + kb * A_BYTES;
@@ -175,20 +186,28 @@ __device__ __forceinline__ void issue_gemm(const Ctx& c, uint32_t parity) {
     tc_commit(bar_at(c.w_empty, kb));      // weight stage (and this k-block of A) consumed
   }
   tc_commit(c.acc_full);
+  if (tl != nullptr) tl[3] = clock64();
 }
 
 // producer: full-width A operand (128 rows x 512) of one GEMM from the exchange buffer `tm` (layer `layer`)
+// Every CTA arms all eight k-block barriers, then fetches ONE k-block -- the slice it published itself -- and
+// multicasts it to the whole cluster: the 128 KB operand costs each CTA a single 16 KB L2 read.
 __device__ __forceinline__ void load_a(const Ctx& c, const CUtensorMap* tm, int layer) {
   fence_proxy_async_all();
-  for (int kb = 0; kb < KBLK; ++kb) {
-    mbar_expect_tx(bar_at(c.a_full, kb), A_BYTES);
-    tma_load_3d(tm, bar_at(c.a_full, kb), c.sA + kb * A_BYTES, kb * 64, c.row0, layer);
-  }
+  for (int kb = 0; kb < KBLK; ++kb) mbar_expect_tx(bar_at(c.a_full, kb), A_BYTES);
+  const int kb = static_cast<int>(c.rank);
+  tma_load_3d_mc(tm, bar_at(c.a_full, kb), c.sA + kb * A_BYTES, kb * 64, c.row0, layer, static_cast<uint16_t>((1u << CS) - 1u));
 }
 // producer: weight slice of one GEMM.  FWD: rows = output features of this CTA, columns = k; BWD (MN-major):
 // rows = k (output features of the forward Linear), columns = this CTA's input features.
+// `a_parity` >= 0: hold the weight traffic back until the whole A operand of the running GEMM has landed -- shared-
+// memory fill bandwidth per SM (~30-50 B/clk measured) is what bounds a GEMM phase, and A is on the critical path
+// while next GEMM's weights have a whole epilogue phase of idle fill time ahead of them.
 template <int BMAJ>
-__device__ __forceinline__ void load_w(const Ctx& c, const CUtensorMap* tm, int layer, bool wait_empty, uint32_t empty_parity) {
+__device__ __forceinline__ void load_w(const Ctx& c, const CUtensorMap* tm, int layer, bool wait_empty, uint32_t empty_parity,
+                                       int a_parity = -1) {
+  if (a_parity >= 0)
+    for (int kb = 0; kb < KBLK; ++kb) mbar_wait(bar_at(c.a_full, kb), static_cast<uint32_t>(a_parity));
   for (int kb = 0; kb < KBLK; ++kb) {
     if (wait_empty) mbar_wait(bar_at(c.w_empty, kb), empty_parity);
     mbar_expect_tx(bar_at(c.w_full, kb), W_BYTES);
@@ -260,13 +279,25 @@ __device__ __forceinline__ void store_f32_64(float* p, const float (&v)[NS]) {
   for (int k = 0; k < NS / 4; ++k) reinterpret_cast<float4*>(p)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
 }
 // a slice written for the other CTAs of the cluster: order it before the cluster barrier and before the TMA reads
+// (the cluster barrier that follows is a release/acquire pair at cluster scope; the proxy fence hands the
+// generic-proxy stores to the async proxy that TMA reads through)
 __device__ __forceinline__ void publish() {
-  __threadfence();
   fence_proxy_async_all();
 }
 
+// Per-layer parameter slices (64 floats each) are copied to shared memory one block AHEAD with cp.async, so the
+// row owners never wait on an L2 round trip between two cluster barriers; readers get them as broadcast LDS.
+__device__ __forceinline__ void lds_vec(uint32_t addr, float* v, int n) {
+  for (int k = 0; k < n / 4; ++k)
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[4 * k]), "=f"(v[4 * k + 1]), "=f"(v[4 * k + 2]), "=f"(v[4 * k + 3]) : "r"(addr + 16u * k) : "memory");
+}
+__device__ __forceinline__ uint32_t par_addr(const Ctx& c, int buf, int vec) { return c.sPar + static_cast<uint32_t>(((buf * 6 + vec) * NS) * 4); }
+
 struct StackParams {
   int B, L;
+  const float* pv[6]; long long ps[6]; int npv;   // per-layer parameter vectors staged in shared memory (layer-0 pointer, stride)
+  long long* dbg;                                  // optional clock64 timeline of one block (SER_CLF_TIMELINE)
   // per-layer parameter vectors: pointer of layer 0 + element stride between layers
   const float* b1; const float* b2; const float* lni_g; const float* lni_b; long long s_blk;   // block params share one stride
   const float* lno_g; const float* lno_b; long long s_lno;
@@ -279,11 +310,29 @@ struct StackParams {
   float* dlni_g; float* dlni_b; float* dlno_g; float* dlno_b;    // layer 0 pointers (strides as the parameters)
 };
 
+__device__ __forceinline__ void par_prefetch(const Ctx& c, const StackParams& p, int layer, int buf, int et, int col0, bool on) {
+  if (on && et < p.npv * 16) {
+    const int v = et >> 4, ch = et & 15;
+    const float* src = p.pv[v] + layer * p.ps[v] + col0 + ch * 4;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(par_addr(c, buf, v) + 16u * ch), "l"(src) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+// start of a block: recycle the older buffer for the layer after this one, then make this layer's slices visible
+__device__ __forceinline__ void par_advance(const Ctx& c, const StackParams& p, int next_layer, bool have_next, int next_buf, int et, int col0) {
+  named_bar_sync(2, 128);
+  par_prefetch(c, p, next_layer, next_buf, et, col0, have_next);
+  asm volatile("cp.async.wait_group 1;" ::: "memory");
+  named_bar_sync(2, 128);
+}
+#define SER_TL(k) do { if (tl) p.dbg[k] = clock64(); } while (0)
+
 __device__ __forceinline__ void setup(Ctx& c, uint8_t* smem, int warp, int lane) {
   c.sA = smem_u32(smem + OFF_A);
   c.sW = smem_u32(smem + OFF_W);
   c.sStats = smem_u32(smem + OFF_STATS);
   c.sColacc = smem_u32(smem + OFF_COLACC);
+  c.sPar = smem_u32(smem + OFF_PAR);
   const uint32_t bars = smem_u32(smem + OFF_BARS);
   c.a_full = bars; c.w_full = bars + 64; c.w_empty = bars + 128; c.acc_full = bars + 192;
   const uint32_t tmem_slot = bars + 200;
@@ -339,7 +388,7 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       cluster_sync_all();                                               // operand slices of GEMM g published
       if (lane == 0) {
         load_a(c, (g & 1) ? &tmR : &tmN, layer);
-        if (g + 1 < 2 * L) load_w<0>(c, ((g + 1) & 1) ? &tmW2 : &tmW1, (g + 1) >> 1, true, static_cast<uint32_t>(g & 1));
+        if (g + 1 < 2 * L) load_w<0>(c, ((g + 1) & 1) ? &tmW2 : &tmW1, (g + 1) >> 1, true, static_cast<uint32_t>(g & 1), g & 1);
       }
     }
   } else if (warp == 1) {
@@ -348,7 +397,12 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       __syncwarp();
       if ((g & 1) == 0) { cluster_sync_all(); cluster_sync_all(); }
       cluster_sync_all();
-      if (lane == 0) { tc_fence_after(); issue_gemm<0>(c, static_cast<uint32_t>(g & 1)); }
+      if (lane == 0) {
+        long long* tl = (p.dbg != nullptr && blockIdx.x == 0 && g == 2 * (L / 2)) ? p.dbg + 10 : nullptr;
+        if (tl != nullptr) tl[0] = clock64();
+        tc_fence_after();
+        issue_gemm<0>(c, static_cast<uint32_t>(g & 1), tl);
+      }
     }
   } else {
     // ------------------------------------------------------------------ row owners (4 warps x 32 rows)
@@ -365,55 +419,72 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
 #pragma unroll
       for (int k = 0; k < NS; ++k) hv[k] = 0.f;
     }
+    // parameter vectors in shared memory: 0 gamma_o, 1 beta_o, 2 gamma_i, 3 beta_i, 4 b1, 5 b2
+    const int et = threadIdx.x - 64;
+    par_prefetch(c, p, 0, 0, et, col0, true);
     for (int i = 0; i < L; ++i) {
+      const bool tl = (p.dbg != nullptr) && (blockIdx.x == 0) && (et == 0) && (i == L / 2);
+      const int pb = i & 1;
+      par_advance(c, p, i + 1, i + 1 < L, pb ^ 1, et, col0);
       float par[NS];
+      SER_TL(0);
       // ---- y = LN_outer(h)
       float mu, rs;
       row_stats(c, 0, rl, hv, mu, rs);
+      SER_TL(1);
       if (valid && c.rank == 0) *reinterpret_cast<float2*>(p.stats_o + (static_cast<size_t>(i) * p.B + row) * 2) = make_float2(mu, rs);
-      load_vec64(p.lno_g + i * p.s_lno + col0, par);
+      lds_vec(par_addr(c, pb, 0), par, NS);
 #pragma unroll
       for (int k = 0; k < NS; ++k) hv[k] = (hv[k] - mu) * rs * par[k];
-      load_vec64(p.lno_b + i * p.s_lno + col0, par);
+      lds_vec(par_addr(c, pb, 1), par, NS);
 #pragma unroll
       for (int k = 0; k < NS; ++k) hv[k] += par[k];                    // hv now holds y (kept for the residual)
       // ---- n = LN_inner(y)
       row_stats(c, 1, rl, hv, mu, rs);
+      SER_TL(2);
       if (valid && c.rank == 0) *reinterpret_cast<float2*>(p.stats_i + (static_cast<size_t>(i) * p.B + row) * 2) = make_float2(mu, rs);
       float nv[NS];
-      load_vec64(p.lni_g + i * p.s_blk + col0, par);
+      lds_vec(par_addr(c, pb, 2), par, NS);
 #pragma unroll
       for (int k = 0; k < NS; ++k) nv[k] = (hv[k] - mu) * rs * par[k];
-      load_vec64(p.lni_b + i * p.s_blk + col0, par);
+      lds_vec(par_addr(c, pb, 3), par, NS);
 #pragma unroll
       for (int k = 0; k < NS; ++k) nv[k] += par[k];
       if (valid) store_bf16_64(p.n + i * BP + static_cast<size_t>(row) * PD + col0, nv);
       publish();
       tc_fence_before();
+      SER_TL(3);
       cluster_sync_all();
+      SER_TL(4);
       // ---- u = relu(W1 n + b1)
       mbar_wait(c.acc_full, 0u);
+      SER_TL(5);
       tc_fence_after();
       tmem_ld32(taddr, nv);
       tmem_ld32(taddr + 32, nv + 32);
-      load_vec64(p.b1 + i * p.s_blk + col0, par);
+      lds_vec(par_addr(c, pb, 4), par, NS);
 #pragma unroll
       for (int k = 0; k < NS; ++k) nv[k] = fmaxf(nv[k] + par[k], 0.f);
       if (valid) store_bf16_64(p.r + i * BP + static_cast<size_t>(row) * PD + col0, nv);
       publish();
       tc_fence_before();
+      SER_TL(6);
       cluster_sync_all();
+      SER_TL(7);
       // ---- h_next = y + W2 u + b2
       mbar_wait(c.acc_full, 1u);
+      SER_TL(8);
       tc_fence_after();
       tmem_ld32(taddr, nv);
       tmem_ld32(taddr + 32, nv + 32);
-      load_vec64(p.b2 + i * p.s_blk + col0, par);
+      lds_vec(par_addr(c, pb, 5), par, NS);
 #pragma unroll
       for (int k = 0; k < NS; ++k) hv[k] += nv[k] + par[k];
       if (valid) store_f32_64(p.h + (i + 1) * BP + static_cast<size_t>(row) * PD + col0, hv);
       tc_fence_before();
+      SER_TL(9);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   teardown(c, warp);
 }
@@ -461,7 +532,7 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
         load_a(c, (g & 1) ? &tmDr : &tmDhn, layer);
         if (g + 1 < 2 * L) {
           const int nl = L - 1 - ((g + 1) >> 1);
-          load_w<1>(c, ((g + 1) & 1) ? &tmW1 : &tmW2, nl, true, static_cast<uint32_t>(g & 1));
+          load_w<1>(c, ((g + 1) & 1) ? &tmW1 : &tmW2, nl, true, static_cast<uint32_t>(g & 1), g & 1);
         }
       }
       __syncwarp();
@@ -494,12 +565,20 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
 #pragma unroll
       for (int k = 0; k < NS; ++k) gv[k] = 0.f;
     }
+    // parameter vectors in shared memory: 0 gamma_o, 1 beta_o, 2 gamma_i
+    par_prefetch(c, p, L - 1, (L - 1) & 1, et, col0, true);
     for (int i = L - 1; i >= 0; --i) {
+      const bool tl = (p.dbg != nullptr) && (blockIdx.x == 0) && (et == 0) && (i == L / 2);
+      const int pb = i & 1;
+      par_advance(c, p, i - 1, i > 0, pb ^ 1, et, col0);
+      SER_TL(16);
       // ---- publish dh_{i+1} (bf16): A operand of du = dh W2 and of the batched dW2 GEMM
       if (valid) store_bf16_64(p.dhn + i * BP + static_cast<size_t>(row) * PD + col0, gv);
       publish();
       tc_fence_before();
+      SER_TL(17);
       cluster_sync_all();
+      SER_TL(18);
       // operands of the epilogues below, requested while the GEMM runs
       float xo[NS];
       float2 so = make_float2(0.f, 0.f), si = make_float2(0.f, 0.f);
@@ -521,6 +600,7 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       for (int k = 0; k < NS; ++k) xo[k] = (xo[k] - so.x) * so.y;        // x-hat of the outer LayerNorm
       // ---- da = du * (u > 0)
       mbar_wait(c.acc_full, 0u);
+      SER_TL(19);
       tc_fence_after();
       {
         float du[NS];
@@ -540,19 +620,20 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       }
       publish();
       tc_fence_before();
+      SER_TL(20);
       cluster_sync_all();
+      SER_TL(21);
       // ---- dn = da W1, then the two LayerNorm backward steps on the register-resident row slice
       mbar_wait(c.acc_full, 1u);
+      SER_TL(22);
       tc_fence_after();
-      const float* go_p = p.lno_g + i * p.s_lno + col0;
-      const float* bo_p = p.lno_b + i * p.s_lno + col0;
-      const float* gi_p = p.lni_g + i * p.s_blk + col0;
+      const uint32_t go_p = par_addr(c, pb, 0), bo_p = par_addr(c, pb, 1), gi_p = par_addr(c, pb, 2);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float dn[32], t0[32], t1[32], go[32], bo[32], gi[32];
         tmem_ld32(taddr + hh * 32, dn);
-        load_vec32(go_p + hh * 32, go); load_vec32(bo_p + hh * 32, bo); load_vec32(gi_p + hh * 32, gi);
+        lds_vec(go_p + hh * 128, go, 32); lds_vec(bo_p + hh * 128, bo, 32); lds_vec(gi_p + hh * 128, gi, 32);
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           const int kk = hh * 32 + k;
@@ -574,12 +655,13 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
         for (int t = 0; t < CS; ++t) { s1 += as[t]; s2 += bs[t]; }
         s1 *= (1.f / PD); s2 *= (1.f / PD);
       }
+      SER_TL(23);
       float u1 = 0.f, u2 = 0.f;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float dn[32], t0[32], t1[32], go[32], bo[32], gi[32];
         tmem_ld32(taddr + hh * 32, dn);
-        load_vec32(go_p + hh * 32, go); load_vec32(bo_p + hh * 32, bo); load_vec32(gi_p + hh * 32, gi);
+        lds_vec(go_p + hh * 128, go, 32); lds_vec(bo_p + hh * 128, bo, 32); lds_vec(gi_p + hh * 128, gi, 32);
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           const int kk = hh * 32 + k;
@@ -608,13 +690,14 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         float go[32];
-        load_vec32(go_p + hh * 32, go);
+        lds_vec(go_p + hh * 128, go, 32);
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           const int kk = hh * 32 + k;
           gv[kk] = so.y * (gv[kk] * go[k] - u1 - xo[kk] * u2);
         }
       }
+      SER_TL(24);
       // ---- flush this block's LayerNorm parameter gradients (summed over the cluster's 128 rows)
       named_bar_sync(1, 128);
       {
@@ -631,7 +714,9 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
         atomicAdd(d1, v1);
       }
       named_bar_sync(1, 128);
+      SER_TL(25);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (valid) store_f32_64(p.dh_out + static_cast<size_t>(row) * PD + col0, gv);
   }
   teardown(c, warp);
@@ -683,7 +768,20 @@ bool clf_stack_supported(int dtype, int P, int L, const ClfStackArgs& a) {
          (a.s_w1 % 8 == 0) && (a.s_w2 % 8 == 0);
 }
 
-static StackParams to_params(const ClfStackArgs& a) {
+static long long* timeline_buffer() {
+  static long long* buf = nullptr;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    if (getenv("SER_CLF_TIMELINE") != nullptr && cudaMalloc(&buf, 32 * sizeof(long long)) == cudaSuccess)
+      cudaMemset(buf, 0, 32 * sizeof(long long));
+    else
+      buf = nullptr;
+  }
+  return buf;
+}
+
+static StackParams to_params(const ClfStackArgs& a, bool backward) {
   StackParams p{};
   p.B = a.B; p.L = a.L;
   p.b1 = a.b1; p.b2 = a.b2; p.lni_g = a.lni_g; p.lni_b = a.lni_b; p.s_blk = a.s_blk;
@@ -693,7 +791,30 @@ static StackParams to_params(const ClfStackArgs& a) {
   p.dh_in = a.dh_in; p.dh_out = a.dh_out;
   p.dhn = reinterpret_cast<__nv_bfloat16*>(a.dhn); p.dr = reinterpret_cast<__nv_bfloat16*>(a.dr);
   p.dlni_g = a.dlni_g; p.dlni_b = a.dlni_b; p.dlno_g = a.dlno_g; p.dlno_b = a.dlno_b;
+  const float* pv[6] = {a.lno_g, a.lno_b, a.lni_g, a.lni_b, a.b1, a.b2};
+  const long long ps[6] = {a.s_lno, a.s_lno, a.s_blk, a.s_blk, a.s_blk, a.s_blk};
+  for (int i = 0; i < 6; ++i) { p.pv[i] = pv[i]; p.ps[i] = ps[i]; }
+  p.npv = backward ? 3 : 6;
+  p.dbg = timeline_buffer();
   return p;
+}
+
+// SER_CLF_TIMELINE=1: one row-owner thread stamps clock64() at the phase boundaries of the middle block; the
+// host prints the deltas after the launch (debug aid: synchronises the stream)
+static void timeline_report(const char* what, cudaStream_t s) {
+  long long* d = timeline_buffer();
+  if (d == nullptr) return;
+  long long h[32];
+  cudaStreamSynchronize(s);
+  cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  fprintf(stderr, "[clf timeline %s]", what);
+  const int lo = (what[0] == 'f') ? 0 : 16, hi = (what[0] == 'f') ? 9 : 25;
+  for (int k = lo + 1; k <= hi; ++k) fprintf(stderr, " t%d-t%d=%lld", k, k - 1, h[k] - h[k - 1]);
+  fprintf(stderr, " | block=%lld cycles", h[hi] - h[lo]);
+  if (what[0] == 'f')
+    fprintf(stderr, " | mma(GEMM1): barrier->a_full[0]=%lld a_full[0]->a_full[7]=%lld ->issued=%lld ; epilogue saw barrier at %+lld, acc_full at %+lld (vs mma barrier exit)",
+            h[11] - h[10], h[12] - h[11], h[13] - h[12], h[4] - h[10], h[5] - h[10]);
+  fprintf(stderr, "\n");
 }
 
 int clf_stack_fwd(const ClfStackArgs& a, cudaStream_t s) {
@@ -708,8 +829,9 @@ int clf_stack_fwd(const ClfStackArgs& a, cudaStream_t s) {
   // algorithmic work: 2 GEMMs per block; bytes: weights once per cluster + the fp32 stream and bf16 operands
   ProfScope prof("clf_stack_fwd", 4.0 * a.B * PD * PD * a.L,
                  static_cast<double>(a.L) * (2.0 * PD * PD * 2 * clusters + a.B * PD * (4.0 + 2.0 + 2.0)), s);
-  clf_stack_fwd_kernel<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmN, tmR, to_params(a));
+  clf_stack_fwd_kernel<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmN, tmR, to_params(a, false));
   SER_LAUNCH_CHECK();
+  timeline_report("fwd", s);
   return SER_OK;
 }
 
@@ -724,8 +846,9 @@ int clf_stack_bwd(const ClfStackArgs& a, cudaStream_t s) {
   const int clusters = ceil_div(a.B, RM);
   ProfScope prof("clf_stack_bwd", 4.0 * a.B * PD * PD * a.L,
                  static_cast<double>(a.L) * (2.0 * PD * PD * 2 * clusters + a.B * PD * (4.0 + 2.0 + 2.0 + 2.0)), s);
-  clf_stack_bwd_kernel<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmDhn, tmDr, to_params(a));
+  clf_stack_bwd_kernel<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmDhn, tmDr, to_params(a, true));
   SER_LAUNCH_CHECK();
+  timeline_report("bwd", s);
   return SER_OK;
 }
 
