@@ -23,6 +23,7 @@ import time
 
 import torch
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -174,6 +175,11 @@ def run_ours(args, wl):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L.load()
+
+    def stage(msg):
+        if rank == 0 and os.environ.get("BENCH_VERBOSE"):
+            print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
     peaks = load_peaks()
     B, Ta, Tt, C = wl["B"], wl["Ta"], wl["Tt"], wl["C"]
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
@@ -231,6 +237,7 @@ def run_ours(args, wl):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps
 
+    stage(f"setup done (graph={'yes' if graphed is not None else 'no'})")
     # ---------------- device-resident timing (value) ----------------
     for _ in range(max(args.warmup, 3)):
         out = step(devin)
@@ -245,6 +252,7 @@ def run_ours(args, wl):
     launches = launches_per_step * args.steps
     loss_val = float(out["loss"].detach())
 
+    stage(f"device-resident timing done: {ms:.3f} ms/step")
     # ---------------- end-to-end through the public API with host buffers ----------------
     copy_stream = torch.cuda.Stream(device=dev)
     bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]   # double buffer
@@ -277,14 +285,17 @@ def run_ours(args, wl):
         e2e_step()
     ms_e2e = timed(e2e_step, max(3, args.steps // 2))
 
+    stage(f"e2e timing done: {ms_e2e:.3f} ms/step")
     # ---------------- per-kernel-family profile (CUDA events around every launch; separate pass) ----------------
     prof = {}
+    nprof = 3
+    barrier()
     if rank == 0:
-        torch.cuda.synchronize()
         L.prof_enable(True)
-        nprof = 3
-        for _ in range(nprof):
-            eager_step(devin)          # events cannot be timed inside a graph replay: profile the eager launches
+    for _ in range(nprof):             # every rank runs the pass (the steps contain collectives); rank 0 records
+        eager_step(devin)              # events cannot be timed inside a graph replay: profile the eager launches
+    barrier()
+    if rank == 0:
         detail = L.prof_report()
         L.prof_enable(False)
         if args.profile_detail:
@@ -307,9 +318,18 @@ def run_ours(args, wl):
         r = cpu_reference_run(WORKLOADS["cfg1"] | {"C": C}, steps=6, warmup=1, sample_B=8)
         cpu = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
-    if rank != 0:
+    def finish():
+        # Tear-down of a process group whose collectives live inside CUDA graphs can block; everything is
+        # measured and printed by now, so synchronise, meet once more and leave without the NCCL destructor.
+        sys.stdout.flush(); sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     total_B = B * world
@@ -351,8 +371,7 @@ def run_ours(args, wl):
         "clocks": clocks, "loss": loss_val,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():

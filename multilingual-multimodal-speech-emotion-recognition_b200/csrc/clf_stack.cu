@@ -79,6 +79,25 @@ __device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* tm, uint32_t b
       " [%0], [%1, {%3, %4, %5}], [%2], %6;"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
 }
+// 1-D bulk copies: shared -> global, and global -> the same shared offset of every CTA in `mask`
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load_mc(uint32_t sdst, const void* gsrc, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -190,13 +209,18 @@ __device__ __forceinline__ void issue_gemm(const Ctx& c, uint32_t parity, long l
 }
 
 // producer: full-width A operand (128 rows x 512) of one GEMM from the exchange buffer `tm` (layer `layer`)
-// Every CTA arms all eight k-block barriers, then fetches ONE k-block -- the slice it published itself -- and
-// multicasts it to the whole cluster: the 128 KB operand costs each CTA a single 16 KB L2 read.
-__device__ __forceinline__ void load_a(const Ctx& c, const CUtensorMap* tm, int layer) {
+// Exchange buffer (global, L2 resident): [cluster][slot = GEMM parity][k-block = producing CTA][128 rows x 128 B], each
+// 16 KB block already in the 128B-swizzled K-major image the tensor core reads.  Every CTA arms all eight k-block
+// barriers, then fetches ONE block -- the slice it published itself -- as a single contiguous bulk copy multicast
+// to the whole cluster (a contiguous 16 KB request moves several times faster than 128 strided 128-byte rows).
+__device__ __forceinline__ char* xchg_block(const Ctx& c, char* xchg, int g) {
+  return xchg + ((static_cast<size_t>(blockIdx.x / CS) * 2 + (g & 1)) * CS + c.rank) * A_BYTES;
+}
+__device__ __forceinline__ void load_a(const Ctx& c, char* xchg, int g) {
   fence_proxy_async_all();
   for (int kb = 0; kb < KBLK; ++kb) mbar_expect_tx(bar_at(c.a_full, kb), A_BYTES);
-  const int kb = static_cast<int>(c.rank);
-  tma_load_3d_mc(tm, bar_at(c.a_full, kb), c.sA + kb * A_BYTES, kb * 64, c.row0, layer, static_cast<uint16_t>((1u << CS) - 1u));
+  const uint32_t kb = c.rank;
+  bulk_load_mc(c.sA + kb * A_BYTES, xchg_block(c, xchg, g), A_BYTES, bar_at(c.a_full, kb), static_cast<uint16_t>((1u << CS) - 1u));
 }
 // producer: weight slice of one GEMM.  FWD: rows = output features of this CTA, columns = k; BWD (MN-major):
 // rows = k (output features of the forward Linear), columns = this CTA's input features.
@@ -278,11 +302,48 @@ __device__ __forceinline__ void store_f32_64(float* p, const float (&v)[NS]) {
 #pragma unroll
   for (int k = 0; k < NS / 4; ++k) reinterpret_cast<float4*>(p)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
 }
-// a slice written for the other CTAs of the cluster: order it before the cluster barrier and before the TMA reads
-// (the cluster barrier that follows is a release/acquire pair at cluster scope; the proxy fence hands the
-// generic-proxy stores to the async proxy that TMA reads through)
-__device__ __forceinline__ void publish() {
-  fence_proxy_async_all();
+// One row-slice (64 bf16 = 128 B per thread) of the next GEMM operand: written ONCE into this CTA's own k-block of
+// the A buffer (swizzled), from where one thread sends it (a) as a contiguous 16 KB bulk store to the exchange buffer
+// and (b) as a TMA tensor store to the saved-activation buffer [L,B,512] the backward pass reads (rows >= B are
+// clipped by the tensor map).  Both stores are complete before the caller enters the cluster barrier.
+__device__ __forceinline__ void publish_slice(const Ctx& c, const float (&v)[NS], int rl, int et, char* xblock,
+                                              const CUtensorMap* tm_save, int col0, int layer) {
+  const uint32_t tile = c.sA + c.rank * A_BYTES;
+  const uint32_t base = tile + static_cast<uint32_t>(rl) * 128u;
+  const uint32_t swz = static_cast<uint32_t>(rl & 7);
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    sts128(base + ((static_cast<uint32_t>(j) ^ swz) << 4), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+           pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+  fence_async_smem();
+  named_bar_sync(3, 128);
+  if (et == 0) {
+    bulk_store(xblock, tile, A_BYTES);
+    tma_store_3d(tm_save, tile, col0, c.row0, layer);
+    bulk_commit();
+    bulk_wait_all();
+  }
+}
+// fp32 row-slice (64 floats = 2 x 128 B per thread) -> two swizzled tiles in the idle k-blocks next to our own ->
+// two TMA tensor stores (fire and forget; drained by the next publish_slice before any peer can overwrite the tiles)
+__device__ __forceinline__ void store_slice_f32(const Ctx& c, const float (&v)[NS], int rl, int et, const CUtensorMap* tm,
+                                                int col0, int layer) {
+  const uint32_t swz = static_cast<uint32_t>(rl & 7);
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const uint32_t base = c.sA + ((c.rank + 1u + t) & 7u) * A_BYTES + static_cast<uint32_t>(rl) * 128u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts128(base + ((static_cast<uint32_t>(j) ^ swz) << 4), __float_as_uint(v[32 * t + 4 * j]), __float_as_uint(v[32 * t + 4 * j + 1]),
+             __float_as_uint(v[32 * t + 4 * j + 2]), __float_as_uint(v[32 * t + 4 * j + 3]));
+  }
+  fence_async_smem();
+  named_bar_sync(3, 128);
+  if (et == 0) {
+    tma_store_3d(tm, c.sA + ((c.rank + 1u) & 7u) * A_BYTES, col0, c.row0, layer);
+    tma_store_3d(tm, c.sA + ((c.rank + 2u) & 7u) * A_BYTES, col0 + 32, c.row0, layer);
+    bulk_commit();
+  }
 }
 
 // Per-layer parameter slices (64 floats each) are copied to shared memory one block AHEAD with cp.async, so the
@@ -298,6 +359,7 @@ struct StackParams {
   int B, L;
   const float* pv[6]; long long ps[6]; int npv;   // per-layer parameter vectors staged in shared memory (layer-0 pointer, stride)
   long long* dbg;                                  // optional clock64 timeline of one block (SER_CLF_TIMELINE)
+  char* xchg;                                      // exchange buffer, ceil(B/128) * 2 * 128 KB
   // per-layer parameter vectors: pointer of layer 0 + element stride between layers
   const float* b1; const float* b2; const float* lni_g; const float* lni_b; long long s_blk;   // block params share one stride
   const float* lno_g; const float* lno_b; long long s_lno;
@@ -370,7 +432,7 @@ __device__ __forceinline__ void teardown(const Ctx& c, int warp) {
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kThreads, 1)
 clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                      const __grid_constant__ CUtensorMap tmN, const __grid_constant__ CUtensorMap tmR,
-                     const StackParams p) {
+                     const __grid_constant__ CUtensorMap tmH, const StackParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -387,7 +449,7 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       if ((g & 1) == 0) { cluster_sync_all(); cluster_sync_all(); }     // the two LayerNorm statistics rounds
       cluster_sync_all();                                               // operand slices of GEMM g published
       if (lane == 0) {
-        load_a(c, (g & 1) ? &tmR : &tmN, layer);
+        load_a(c, p.xchg, g);
         if (g + 1 < 2 * L) load_w<0>(c, ((g + 1) & 1) ? &tmW2 : &tmW1, (g + 1) >> 1, true, static_cast<uint32_t>(g & 1), g & 1);
       }
     }
@@ -450,8 +512,7 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       lds_vec(par_addr(c, pb, 3), par, NS);
 #pragma unroll
       for (int k = 0; k < NS; ++k) nv[k] += par[k];
-      if (valid) store_bf16_64(p.n + i * BP + static_cast<size_t>(row) * PD + col0, nv);
-      publish();
+      publish_slice(c, nv, rl, et, xchg_block(c, p.xchg, 2 * i), &tmN, col0, i);
       tc_fence_before();
       SER_TL(3);
       cluster_sync_all();
@@ -465,8 +526,7 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       lds_vec(par_addr(c, pb, 4), par, NS);
 #pragma unroll
       for (int k = 0; k < NS; ++k) nv[k] = fmaxf(nv[k] + par[k], 0.f);
-      if (valid) store_bf16_64(p.r + i * BP + static_cast<size_t>(row) * PD + col0, nv);
-      publish();
+      publish_slice(c, nv, rl, et, xchg_block(c, p.xchg, 2 * i + 1), &tmR, col0, i);
       tc_fence_before();
       SER_TL(6);
       cluster_sync_all();
@@ -480,11 +540,12 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       lds_vec(par_addr(c, pb, 5), par, NS);
 #pragma unroll
       for (int k = 0; k < NS; ++k) hv[k] += nv[k] + par[k];
-      if (valid) store_f32_64(p.h + (i + 1) * BP + static_cast<size_t>(row) * PD + col0, hv);
+      store_slice_f32(c, hv, rl, et, &tmH, col0, i + 1);
       tc_fence_before();
       SER_TL(9);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (et == 0) bulk_wait_all();
   }
   teardown(c, warp);
 }
@@ -529,7 +590,7 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       __syncwarp();
       cluster_sync_all();                                               // operand slices of GEMM g published
       if (lane == 0) {
-        load_a(c, (g & 1) ? &tmDr : &tmDhn, layer);
+        load_a(c, p.xchg, g);
         if (g + 1 < 2 * L) {
           const int nl = L - 1 - ((g + 1) >> 1);
           load_w<1>(c, ((g + 1) & 1) ? &tmW1 : &tmW2, nl, true, static_cast<uint32_t>(g & 1), g & 1);
@@ -573,8 +634,7 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       par_advance(c, p, i - 1, i > 0, pb ^ 1, et, col0);
       SER_TL(16);
       // ---- publish dh_{i+1} (bf16): A operand of du = dh W2 and of the batched dW2 GEMM
-      if (valid) store_bf16_64(p.dhn + i * BP + static_cast<size_t>(row) * PD + col0, gv);
-      publish();
+      publish_slice(c, gv, rl, et, xchg_block(c, p.xchg, 2 * (L - 1 - i)), &tmDhn, col0, i);
       tc_fence_before();
       SER_TL(17);
       cluster_sync_all();
@@ -596,9 +656,7 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
 #pragma unroll
         for (int k = 0; k < NS / 8; ++k) um[k] = make_uint4(0u, 0u, 0u, 0u);
       }
-#pragma unroll
-      for (int k = 0; k < NS; ++k) xo[k] = (xo[k] - so.x) * so.y;        // x-hat of the outer LayerNorm
-      // ---- da = du * (u > 0)
+      // ---- da = du * (u > 0)   (the loads above stay in flight across the wait: nothing consumes them yet)
       mbar_wait(c.acc_full, 0u);
       SER_TL(19);
       tc_fence_after();
@@ -616,9 +674,8 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
             if ((wds[t] & 0x7fff0000u) == 0u) du[8 * k + 2 * t + 1] = 0.f;
           }
         }
-        if (valid) store_bf16_64(p.dr + i * BP + static_cast<size_t>(row) * PD + col0, du);
+        publish_slice(c, du, rl, et, xchg_block(c, p.xchg, 2 * (L - 1 - i) + 1), &tmDr, col0, i);
       }
-      publish();
       tc_fence_before();
       SER_TL(20);
       cluster_sync_all();
@@ -627,6 +684,8 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       mbar_wait(c.acc_full, 1u);
       SER_TL(22);
       tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < NS; ++k) xo[k] = (xo[k] - so.x) * so.y;        // x-hat of the outer LayerNorm
       const uint32_t go_p = par_addr(c, pb, 0), bo_p = par_addr(c, pb, 1), gi_p = par_addr(c, pb, 2);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -717,6 +776,7 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       SER_TL(25);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (et == 0) bulk_wait_all();
     if (valid) store_f32_64(p.dh_out + static_cast<size_t>(row) * PD + col0, gv);
   }
   teardown(c, warp);
@@ -740,17 +800,19 @@ EncodeTiledFn encode_fn() {
   });
   return fn;
 }
-// bf16 [layers][rows][512] (row pitch 512, layer pitch `layer_stride` elements), box = box_rows x 64 columns
-int make_map(CUtensorMap* tm, const void* base, long long rows, long long layer_stride, int layers, int box_rows) {
+// [layers][rows][512] bf16 or fp32 (row pitch 512, layer pitch `layer_stride` elements), box = box_rows x 128 bytes
+int make_map(CUtensorMap* tm, const void* base, long long rows, long long layer_stride, int layers, int box_rows,
+             int f32 = 0) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) { set_last_error(__FILE__, __LINE__, "cuTensorMapEncodeTiled unavailable"); return SER_ERR_CUDA; }
+  const cuuint64_t es = f32 ? 4 : 2;
   cuuint64_t gdim[3] = {static_cast<cuuint64_t>(PD), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(layers)};
-  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(PD) * 2, static_cast<cuuint64_t>(layer_stride) * 2};
-  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(PD) * es, static_cast<cuuint64_t>(layer_stride) * es};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / es), static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base),
+                  gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_last_error(__FILE__, __LINE__, "clf_stack: cuTensorMapEncodeTiled failed"); return SER_ERR_CUDA; }
   return SER_OK;
 }
@@ -764,8 +826,12 @@ int configure(K kern) {
 }  // namespace
 
 bool clf_stack_supported(int dtype, int P, int L, const ClfStackArgs& a) {
+  // the exchange buffer lives in the (otherwise unused) saved-y buffer of the descriptor: [L, B, 512] fp32
+  const size_t need = static_cast<size_t>(ceil_div(a.B, RM)) * 2 * CS * A_BYTES;
+  const size_t have = static_cast<size_t>(L) * a.B * PD * sizeof(float);
   return dtype == DT_BF16 && P == PD && L >= 1 && a.s_blk > 0 && a.s_lno > 0 && a.s_w1 > 0 && a.s_w2 > 0 &&
-         (a.s_w1 % 8 == 0) && (a.s_w2 % 8 == 0);
+         (a.s_w1 % 8 == 0) && (a.s_w2 % 8 == 0) && a.xchg != nullptr && have >= need &&
+         (reinterpret_cast<uintptr_t>(a.xchg) & 127) == 0;
 }
 
 static long long* timeline_buffer() {
@@ -796,6 +862,7 @@ static StackParams to_params(const ClfStackArgs& a, bool backward) {
   for (int i = 0; i < 6; ++i) { p.pv[i] = pv[i]; p.ps[i] = ps[i]; }
   p.npv = backward ? 3 : 6;
   p.dbg = timeline_buffer();
+  p.xchg = reinterpret_cast<char*>(a.xchg);
   return p;
 }
 
@@ -820,16 +887,17 @@ static void timeline_report(const char* what, cudaStream_t s) {
 int clf_stack_fwd(const ClfStackArgs& a, cudaStream_t s) {
   static bool configured = false;
   if (!configured) { SER_TRY(configure(clf_stack_fwd_kernel)); configured = true; }
-  CUtensorMap tmW1, tmW2, tmN, tmR;
+  CUtensorMap tmW1, tmW2, tmN, tmR, tmH;
   SER_TRY(make_map(&tmW1, a.w1, PD, a.s_w1, a.L, NS));
   SER_TRY(make_map(&tmW2, a.w2, PD, a.s_w2, a.L, NS));
   SER_TRY(make_map(&tmN, a.n, a.B, static_cast<long long>(a.B) * PD, a.L, RM));
   SER_TRY(make_map(&tmR, a.r, a.B, static_cast<long long>(a.B) * PD, a.L, RM));
+  SER_TRY(make_map(&tmH, a.h, a.B, static_cast<long long>(a.B) * PD, a.L + 1, RM, 1));
   const int clusters = ceil_div(a.B, RM);
   // algorithmic work: 2 GEMMs per block; bytes: weights once per cluster + the fp32 stream and bf16 operands
   ProfScope prof("clf_stack_fwd", 4.0 * a.B * PD * PD * a.L,
                  static_cast<double>(a.L) * (2.0 * PD * PD * 2 * clusters + a.B * PD * (4.0 + 2.0 + 2.0)), s);
-  clf_stack_fwd_kernel<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmN, tmR, to_params(a, false));
+  clf_stack_fwd_kernel<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmN, tmR, tmH, to_params(a, false));
   SER_LAUNCH_CHECK();
   timeline_report("fwd", s);
   return SER_OK;

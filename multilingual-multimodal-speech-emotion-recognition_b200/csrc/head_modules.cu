@@ -384,6 +384,7 @@ static bool stack_args(const ser_clf_desc& d, ClfStackArgs& a) {
     if (estride(d.lno_g[i], d.lno_g[i - 1], 4) != a.s_lno || estride(d.lno_b[i], d.lno_b[i - 1], 4) != a.s_lno) return false;
   }
   a.h = d.h; a.n = d.n; a.r = d.r; a.stats_o = d.stats_o; a.stats_i = d.stats_i;
+  a.xchg = d.y;       // the fused kernels keep y in registers; its [L,B,512] fp32 buffer serves as the exchange scratch
   return clf_stack_supported(d.dtype, d.P, L, a);
 }
 static bool stack_grad_args(const ser_clf_desc& d, ClfStackArgs& a) {

@@ -65,6 +65,7 @@ struct ClfStackArgs {
   const float* b1; const float* b2; const float* lni_g; const float* lni_b; long long s_blk;
   const float* lno_g; const float* lno_b; long long s_lno;
   float* h; void* n; void* r; float* stats_o; float* stats_i;           // saved activations (see ser_clf_desc)
+  void* xchg;                                                           // scratch >= ceil(B/128) * 256 KB (the saved-y buffer)
   const float* dh_in; float* dh_out; void* dhn; void* dr;               // backward
   float* dlni_g; float* dlni_b; float* dlno_g; float* dlno_b;
 };
