@@ -57,8 +57,9 @@ __global__ void colsum_kernel(const void* __restrict__ X, int x_f32, long long l
 }
 
 // vectorised variant: each lane owns 8 consecutive columns (one 128-bit load of bf16 / two of fp32), a warp spans
-// 256 columns, the 8 warps of a CTA walk rows 4 at a time (4 independent loads in flight per lane).
-// grid = (ceil(N/256), row_splits)
+// 256 columns.  Every CTA streams ONE CONTIGUOUS block of rows (DRAM-page friendly, like a copy kernel): its 8 warps
+// interleave over the block with 8 independent row loads in flight per lane.
+// grid = (ceil(N/256), row_blocks, batch)
 __global__ void __launch_bounds__(256)
 colsum_vec_kernel(const void* __restrict__ X0, int x_f32, long long ld, int M, int N, float* __restrict__ out0,
                   long long strideX, long long strideOut) {
@@ -72,18 +73,20 @@ colsum_vec_kernel(const void* __restrict__ X0, int x_f32, long long ld, int M, i
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   if (col < N) {
-    const int stride = gridDim.y * 8;
-    int m = blockIdx.y * 8 + w;
-    for (; m + 3 * stride < M; m += 4 * stride) {
-      float v0[8], v1[8], v2[8], v3[8];
-      load8_dyn(X, static_cast<size_t>(m) * ld + col, x_f32, v0);
-      load8_dyn(X, static_cast<size_t>(m + stride) * ld + col, x_f32, v1);
-      load8_dyn(X, static_cast<size_t>(m + 2 * stride) * ld + col, x_f32, v2);
-      load8_dyn(X, static_cast<size_t>(m + 3 * stride) * ld + col, x_f32, v3);
+    const int rows_per_cta = (M + gridDim.y - 1) / gridDim.y;
+    const int r_begin = blockIdx.y * rows_per_cta;
+    const int r_end = min(M, r_begin + rows_per_cta);
+    int m = r_begin + w;
+    constexpr int U = 8;
+    for (; m + (U - 1) * 8 < r_end; m += U * 8) {
+      float v[U][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += (v0[i] + v1[i]) + (v2[i] + v3[i]);
+      for (int u = 0; u < U; ++u) load8_dyn(X, static_cast<size_t>(m + u * 8) * ld + col, x_f32, v[u]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        acc[i] += ((v[0][i] + v[1][i]) + (v[2][i] + v[3][i])) + ((v[4][i] + v[5][i]) + (v[6][i] + v[7][i]));
     }
-    for (; m < M; m += stride) {
+    for (; m < r_end; m += 8) {
       float v0[8];
       load8_dyn(X, static_cast<size_t>(m) * ld + col, x_f32, v0);
 #pragma unroll
@@ -157,66 +160,76 @@ ln_fwd_kernel(const void* __restrict__ x, int x_f32, void* __restrict__ y, int y
   }
 }
 
-__global__ void __launch_bounds__(256)
-ln_bwd_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ x, int x_f32,
-              const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
-              const void* __restrict__ add, int add_f32, void* __restrict__ dx, int dx_f32, void* __restrict__ dx2,
-              int dx2_f32, float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int N, int relu) {
-  __shared__ float sg[kMaxChunks * 256];
-  __shared__ float sb[kMaxChunks * 256];
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int nch = (N + 255) >> 8;
-  const float invN = 1.f / static_cast<float>(N);
-  for (int i = threadIdx.x; i < kMaxChunks * 256; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
+// LayerNorm backward is split in two streaming kernels so that neither carries the other's register state:
+//   ln_bwd_dx_kernel    : one warp per row, dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)) [+ add];
+//                         the next row's operands are requested before the current row's reductions (2 rows in flight)
+//   ln_bwd_param_kernel : column owners (8 columns per lane), contiguous row blocks per CTA, dgamma += g*xhat,
+//                         dbeta += g; re-reads dy and x once (they sit in L2 / HBM) instead of holding 2 x N/32
+//                         accumulators per lane in the row kernel.
+template <int NCH>
+__global__ void __launch_bounds__(256, 3)
+ln_bwd_dx_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ x, int x_f32,
+                 const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 const void* __restrict__ add, int add_f32, void* __restrict__ dx, int dx_f32, void* __restrict__ dx2,
+                 int dx2_f32, int M, int N, int relu) {
+  // gamma / beta live in shared memory (broadcast-free 128-bit reads) so a row costs only its own x and dy in
+  // registers: <= 85 registers per thread keeps 24 warps per SM resident, which is what hides the HBM latency here
+  __shared__ __align__(16) float sg[NCH * 256];
+  __shared__ __align__(16) float sb[NCH * 256];
+  for (int i = threadIdx.x; i < NCH * 256; i += blockDim.x) {
+    sg[i] = (i < N) ? gamma[i] : 0.f;
+    sb[i] = (i < N && relu) ? beta[i] : 0.f;
+  }
   __syncthreads();
-
-  float ag[kMaxChunks][8], ab[kMaxChunks][8];
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const float invN = 1.f / static_cast<float>(N);
+  // contiguous block of rows per CTA, warps interleaved inside it
+  const int rows_per_cta = (M + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(M, r_begin + rows_per_cta);
+  for (int row = r_begin + (threadIdx.x >> 5); row < r_end; row += wpb) {
+    float xv[NCH][8], gv[NCH][8];
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { ag[c][i] = 0.f; ab[c][i] = 0.f; }
-
-  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
-    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
-    float xh[kMaxChunks][8], a[kMaxChunks][8];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int col = c * 256 + lane * 8;
-      if (c < nch && col < N) {
-        float xv[8], gv[8], gm[8];
-        load8_dyn(x, static_cast<size_t>(row) * N + col, x_f32, xv);
-        load8_dyn(dy, static_cast<size_t>(row) * N + col, dy_f32, gv);
-        load8(gamma + col, gm);
-        float bt[8];
-        if (relu) load8(beta + col, bt);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float h = (xv[i] - mean) * rstd;
-          float g = gv[i];
-          if (relu && !(h * gm[i] + bt[i] > 0.f)) g = 0.f;
-          xh[c][i] = h;
-          a[c][i] = g * gm[i];
-          s1 += a[c][i];
-          s2 += a[c][i] * h;
-          ag[c][i] += g * h;
-          ab[c][i] += g;
-        }
+      if (col < N) {
+        load8_dyn(x, static_cast<size_t>(row) * N + col, x_f32, xv[c]);
+        load8_dyn(dy, static_cast<size_t>(row) * N + col, dy_f32, gv[c]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { xh[c][i] = 0.f; a[c][i] = 0.f; }
+        for (int i = 0; i < 8; ++i) { xv[c][i] = 0.f; gv[c][i] = 0.f; }
+      }
+    }
+    const float mu = stats[2 * row], rs = stats[2 * row + 1];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = c * 256 + lane * 8;
+      float gm[8];
+      load8(sg + col, gm);
+      float bt[8];
+      if (relu) load8(sb + col, bt);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float h = (xv[c][i] - mu) * rs;
+        if (relu && !(h * gm[i] + bt[i] > 0.f)) gv[c][i] = 0.f;
+        const float a = gv[c][i] * gm[i];
+        xv[c][i] = h;                      // x-hat replaces x
+        gv[c][i] = a;                      // g * gamma replaces g
+        s1 += a;
+        s2 = fmaf(a, h, s2);
       }
     }
     s1 = warp_sum(s1) * invN;
     s2 = warp_sum(s2) * invN;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int col = c * 256 + lane * 8;
-      if (c < nch && col < N) {
+      if (col < N) {
         float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = rstd * (a[c][i] - s1 - xh[c][i] * s2);
+        for (int i = 0; i < 8; ++i) o[i] = rs * (gv[c][i] - s1 - xv[c][i] * s2);
         if (add != nullptr) {
           float r[8];
           load8_dyn(add, static_cast<size_t>(row) * N + col, add_f32, r);
@@ -228,17 +241,74 @@ ln_bwd_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ 
       }
     }
   }
-  if (dgamma != nullptr) {
+}
+
+// grid = (ceil(N/256), row_blocks); dgamma / dbeta accumulate with one atomic per column and CTA
+__global__ void __launch_bounds__(256)
+ln_bwd_param_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ x, int x_f32,
+                    const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int N, int relu) {
+  __shared__ float red[2][8][256 + 8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + lane * 8;
+  float ag[8], ab[8];
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
-      const int col = c * 256 + lane * 8;
-      if (c < nch && col < N) {
+  for (int i = 0; i < 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+  if (col < N) {
+    float gm[8], bt[8];
+    load8(gamma + col, gm);
+    load8(beta + col, bt);
+    const int rows_per_cta = (M + gridDim.y - 1) / gridDim.y;
+    const int r_begin = blockIdx.y * rows_per_cta;
+    const int r_end = min(M, r_begin + rows_per_cta);
+    constexpr int U = 4;
+    int m = r_begin + w;
+    for (; m + (U - 1) * 8 < r_end; m += U * 8) {
+      float xv[U][8], gv[U][8];
+      float2 st[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { atomicAdd(&sg[col + i], ag[c][i]); atomicAdd(&sb[col + i], ab[c][i]); }
+      for (int u = 0; u < U; ++u) {
+        load8_dyn(x, static_cast<size_t>(m + u * 8) * N + col, x_f32, xv[u]);
+        load8_dyn(dy, static_cast<size_t>(m + u * 8) * N + col, dy_f32, gv[u]);
+        st[u] = *reinterpret_cast<const float2*>(stats + 2 * (m + u * 8));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float h = (xv[u][i] - st[u].x) * st[u].y;
+          float g = gv[u][i];
+          if (relu && !(h * gm[i] + bt[i] > 0.f)) g = 0.f;
+          ag[i] = fmaf(g, h, ag[i]);
+          ab[i] += g;
+        }
+    }
+    for (; m < r_end; m += 8) {
+      float xv[8], gv[8];
+      load8_dyn(x, static_cast<size_t>(m) * N + col, x_f32, xv);
+      load8_dyn(dy, static_cast<size_t>(m) * N + col, dy_f32, gv);
+      const float2 st = *reinterpret_cast<const float2*>(stats + 2 * m);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float h = (xv[i] - st.x) * st.y;
+        float g = gv[i];
+        if (relu && !(h * gm[i] + bt[i] > 0.f)) g = 0.f;
+        ag[i] = fmaf(g, h, ag[i]);
+        ab[i] += g;
       }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < N; i += blockDim.x) { atomicAdd(dgamma + i, sg[i]); atomicAdd(dbeta + i, sb[i]); }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[0][w][lane * 8 + i] = ag[i]; red[1][w][lane * 8 + i] = ab[i]; }
+  __syncthreads();
+  const int c = threadIdx.x;
+  const int n = blockIdx.x * 256 + c;
+  if (n < N) {
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sg += red[0][j][c]; sb += red[1][j][c]; }
+    atomicAdd(dgamma + n, sg);
+    atomicAdd(dbeta + n, sb);
   }
 }
 
@@ -513,16 +583,32 @@ int layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const fl
                   const float* beta, const void* add, int add_f32, void* dx, int dx_f32, void* dx2, int dx2_f32,
                   float* dgamma, float* dbeta, int M, int N, int relu, cudaStream_t s) {
   SER_REQUIRE(N % 8 == 0 && N <= kMaxChunks * 256, "layernorm: N must be a multiple of 8 and <= 1024");
-  int blocks = ceil_div(M, 8);
-  const int cap = 2 * device_sm_count();     // fewer CTAs -> fewer global atomics for dgamma/dbeta
-  if (blocks > cap) blocks = cap;
+  SER_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma and dbeta go together");
   char pname[64];
   if (prof_enabled()) snprintf(pname, sizeof(pname), "layernorm_bwd:%dx%d", M, N);
+  // algorithmic bytes: dy, x read once, dx (and its copy / the added tensor) moved once
   ProfScope prof(pname, 0.0, static_cast<double>(M) * N * ((dy_f32 ? 4 : 2) + (x_f32 ? 4 : 2) + (dx_f32 ? 4 : 2) +
                                           (add ? (add_f32 ? 4 : 2) : 0) + (dx2 ? (dx2_f32 ? 4 : 2) : 0)), s);
-  ln_bwd_kernel<<<blocks, 256, 0, s>>>(dy, dy_f32, x, x_f32, stats, gamma, beta, add, add_f32, dx, dx_f32, dx2,
-                                       dx2_f32, dgamma, dbeta, M, N, relu);
+  int blocks = ceil_div(M, 16);
+  const int cap = 12 * device_sm_count();       // 3 resident CTAs per SM, 4 waves
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  const int nch = ceil_div(N, 256);
+#define SER_LN_DX(NCH)                                                                                              \
+  ln_bwd_dx_kernel<NCH><<<blocks, 256, 0, s>>>(dy, dy_f32, x, x_f32, stats, gamma, beta, add, add_f32, dx, dx_f32,  \
+                                               dx2, dx2_f32, M, N, relu)
+  if (nch == 1) SER_LN_DX(1); else if (nch == 2) SER_LN_DX(2); else if (nch == 3) SER_LN_DX(3); else SER_LN_DX(4);
+#undef SER_LN_DX
   SER_LAUNCH_CHECK();
+  if (dgamma != nullptr) {
+    const int gx = ceil_div(N, 256);
+    int gy = ceil_div(4 * device_sm_count(), gx);
+    const int max_gy = ceil_div(M, 64);
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    ln_bwd_param_kernel<<<dim3(gx, gy), 256, 0, s>>>(dy, dy_f32, x, x_f32, stats, gamma, beta, dgamma, dbeta, M, N, relu);
+    SER_LAUNCH_CHECK();
+  }
   return SER_OK;
 }
 

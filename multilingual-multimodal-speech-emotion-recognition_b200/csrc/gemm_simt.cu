@@ -1,4 +1,5 @@
-// fp32 tier GEMM: CUDA-core FFMA, 64x64x16 tiles, 4x4 register micro-tiles, optional split-K.
+// fp32 tier GEMM: CUDA-core FFMA, 64x64x32 tiles, 4x4 register micro-tiles, register-prefetched operand tiles
+// (the next K tile is in flight while the current one is multiplied), optional split-K.
 // This is the "within 1e-4 of the fp32 reference" path (TF32 tensor cores are not accurate enough,
 // see SURVEY.md section 7 "Hard parts"); it shares the epilogue contract of the tcgen05 kernel.
 #include "common.cuh"
@@ -9,7 +10,8 @@ namespace ser {
 
 namespace {
 
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int TM = 64, TN = 64, TK = 32;
+constexpr int EPT = TM * TK / 256;     // operand elements per thread and tile
 
 struct SimtEpilogue {
   float* C; long long ldc;
@@ -42,22 +44,37 @@ gemm_simt_kernel(const float* __restrict__ A, long long sam, long long sak, cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int kt = kt0; kt < kt1; ++kt) {
+  // element e of a tile -> (row, k): thread order follows the contiguous axis of the operand
+  auto fetch = [&](int kt, float (&ra)[EPT], float (&rb)[EPT]) {
     const int k0 = kt * TK;
-    // 64x16 tile = 1024 elements, 4 per thread; thread order follows the contiguous axis
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < EPT; ++r) {
       const int e = tid + r * 256;
       int mm, kk;
-      if (A_KCONT) { kk = e & 15; mm = e >> 4; } else { mm = e & 63; kk = e >> 6; }
+      if (A_KCONT) { kk = e % TK; mm = e / TK; } else { mm = e % TM; kk = e / TM; }
       const int gm = m0 + mm, gk = k0 + kk;
-      As[kk][mm] = (gm < M && gk < K) ? A[gm * sam + gk * sak] : 0.f;
+      ra[r] = (gm < M && gk < K) ? A[gm * sam + gk * sak] : 0.f;
       int nn, kb;
-      if (B_KCONT) { kb = e & 15; nn = e >> 4; } else { nn = e & 63; kb = e >> 6; }
+      if (B_KCONT) { kb = e % TK; nn = e / TK; } else { nn = e % TN; kb = e / TN; }
       const int gn = n0 + nn, gkb = k0 + kb;
-      Bs[kb][nn] = (gn < N && gkb < K) ? B[gn * sbn + gkb * sbk] : 0.f;
+      rb[r] = (gn < N && gkb < K) ? B[gn * sbn + gkb * sbk] : 0.f;
+    }
+  };
+  float ra[EPT], rb[EPT];
+  if (kt0 < kt1) fetch(kt0, ra, rb);
+  for (int kt = kt0; kt < kt1; ++kt) {
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+      const int e = tid + r * 256;
+      int mm, kk;
+      if (A_KCONT) { kk = e % TK; mm = e / TK; } else { mm = e % TM; kk = e / TM; }
+      As[kk][mm] = ra[r];
+      int nn, kb;
+      if (B_KCONT) { kb = e % TK; nn = e / TK; } else { nn = e % TN; kb = e / TN; }
+      Bs[kb][nn] = rb[r];
     }
     __syncthreads();
+    if (kt + 1 < kt1) fetch(kt + 1, ra, rb);          // global loads overlap the FFMA block below
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -119,9 +136,9 @@ int gemm_simt_f32(const GemmArgs& a0, cudaStream_t stream) {
     splits = 1;
     const int tiles = mt * nt;
     const int target = 2 * device_sm_count();
-    if (linear && tiles < target && ktiles >= 128) {
+    if (linear && tiles < target && ktiles >= 64) {
       splits = target / tiles;
-      if (splits > ktiles / 8) splits = ktiles / 8;
+      if (splits > ktiles / 4) splits = ktiles / 4;
       if (splits < 1) splits = 1;
     }
   }
