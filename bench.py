@@ -53,6 +53,14 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
 
 
+def latest_traffic_file():
+    d = os.path.join(ROOT, "profiles")
+    if not os.path.isdir(d):
+        return None
+    c = sorted(f for f in os.listdir(d) if f.endswith("_traffic.json"))
+    return os.path.join(d, c[-1]) if c else None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -341,10 +349,22 @@ def run_ours(args, wl):
     if fam:
         gflops = sum(v["flops"] for v in fam.values())
         gms = sum(v["ms"] for v in fam.values())
+        nl = sum(v["launches"] for v in fam.values())
         ach = gflops / (gms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all fwd/dgrad/wgrad launches)",
+        traffic, tsrc = None, None
+        tfile = latest_traffic_file()
+        if tfile:                      # DRAM bytes per launch of the same kernel from the committed ncu launch list
+            try:
+                tk = json.load(open(tfile))["kernels"].get("gemm_tc_kernel")
+                if tk:
+                    traffic, tsrc = tk["dram_bytes_per_launch"], os.path.relpath(tfile, ROOT)
+            except Exception:  # noqa: BLE001
+                pass
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all fwd/dgrad/wgrad launches of a step)",
                 "achieved": ach, "peak": peaks["tf_sus"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sus"],
-                "traffic": None, "peak_source": peaks["src"] + " sustained bf16",
+                "traffic": traffic, "traffic_source": tsrc,
+                "algorithmic_flops_per_launch": gflops / nl, "algorithmic_bytes_per_launch": sum(v["bytes"] for v in fam.values()) / nl,
+                "avg_launch_us": gms * 1e3 / nl, "peak_source": peaks["src"] + " sustained bf16 (kernel timed inside a long step)",
                 "launches_per_step": sum(v["launches_per_step"] for v in fam.values()),
                 "ms_per_step": sum(v["ms_per_step"] for v in fam.values())}
     tot_prof_ms = sum(v["ms_per_step"] for v in prof.values()) or 1.0

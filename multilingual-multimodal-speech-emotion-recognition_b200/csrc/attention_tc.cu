@@ -6,7 +6,8 @@
 // Shapes are tiny per (sample, head): dh = 32, Tk in {64, 250, 256, 1500}.  One CTA of 4 warps owns 64 rows
 // (queries in fwd / dQ, keys in dK/dV); every warp owns 16 of them as mma.m16n8k16 bf16 fragments with fp32
 // accumulation.  The other operand is streamed through shared memory in 64-row tiles (rows padded to 80 bytes so
-// ldmatrix is bank-conflict free).  Scores / probabilities live only in registers: the S accumulator layout
+// ldmatrix is bank-conflict free), double buffered with cp.async: the owned rows and the first streamed tile are
+// requested together (one exposed memory latency per CTA), every further tile lands while the previous one is used.  Scores / probabilities live only in registers: the S accumulator layout
 // is re-packed in place as the A operand of the second GEMM.  Heads are addressed as 32-column slices of the packed
 // q|k|v projection buffers (row stride 768), so there is no head transpose anywhere.
 #include "kernels.cuh"
@@ -46,15 +47,19 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// cooperative copy of `rows` x 32 bf16 (row stride ld) into smem [TILE][LDS]; rows beyond `rows` are zero filled
-__device__ __forceinline__ void stage_rows(const bf16* __restrict__ g, long long ld, int rows, bf16* sm) {
+// cooperative copy of `rows` x 32 bf16 (row stride ld) into smem [TILE][LDS], rows beyond `rows` zero filled:
+// asynchronous (cp.async, 16 B per request, src-size 0 = zero fill): the copy of the NEXT tile runs while the
+// tensor cores work on the current one
+__device__ __forceinline__ void stage_rows_async(const bf16* __restrict__ g, long long ld, int rows, bf16* sm) {
   for (int e = threadIdx.x; e < TILE * 4; e += NT) {
     const int r = e >> 2, c = (e & 3) * 8;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < rows) v = *reinterpret_cast<const uint4*>(g + static_cast<size_t>(r) * ld + c);
-    *reinterpret_cast<uint4*>(sm + r * LDS + c) = v;
+    const bf16* src = g + static_cast<size_t>(r < rows ? r : 0) * ld + c;
+    const int nbytes = (r < rows) ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr(sm + r * LDS + c)), "l"(src), "r"(nbytes) : "memory");
   }
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // A fragments (2 k-steps over dh = 32) of the warp's 16 rows from a staged [.,LDS] tile
 __device__ __forceinline__ void load_a_frags(const bf16* sm, int row0, int lane, uint32_t (&a)[2][4]) {
@@ -96,24 +101,37 @@ __device__ __forceinline__ void mma_nn(const uint32_t (&p)[4][4], const bf16* ti
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 5)
 attn_tc_fwd_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk,
                    const bf16* __restrict__ V, long long ldv, const float* __restrict__ kmask, bf16* __restrict__ O,
                    long long ldo, float* __restrict__ lse, int H, int Tq, int Tk, float scale) {
   __shared__ __align__(16) bf16 sQ[ROWS * LDS];
-  __shared__ __align__(16) bf16 sK[TILE * LDS];
-  __shared__ __align__(16) bf16 sV[TILE * LDS];
-  __shared__ float sBias[TILE];            // 0 for a valid key, -inf for a padded / out-of-range one
+  __shared__ __align__(16) bf16 sK[2][TILE * LDS];
+  __shared__ __align__(16) bf16 sV[2][TILE * LDS];
+  __shared__ float sBias[2][TILE];         // 0 for a valid key, -inf for a padded / out-of-range one
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qrows = min(ROWS, Tq - q0);
   const float c = scale * kLog2e;
+  const int ntiles = (Tk + TILE - 1) / TILE;
+  const bf16* Kb = K + static_cast<size_t>(b) * Tk * ldk + h * DH;
+  const bf16* Vb = V + static_cast<size_t>(b) * Tk * ldv + h * DH;
+  auto stage_kv = [&](int t, int buf) {
+    const int k0 = t * TILE, rows = min(TILE, Tk - k0);
+    stage_rows_async(Kb + static_cast<size_t>(k0) * ldk, ldk, rows, sK[buf]);
+    stage_rows_async(Vb + static_cast<size_t>(k0) * ldv, ldv, rows, sV[buf]);
+    if (threadIdx.x < TILE) {
+      const int j = threadIdx.x;
+      const bool ok = j < rows && (kmask == nullptr || kmask[static_cast<size_t>(b) * Tk + k0 + j] != 0.f);
+      sBias[buf][j] = ok ? 0.f : -INFINITY;
+    }
+    cp_async_commit();
+  };
+  // Q and the first K/V tile travel together: one exposed memory latency per CTA instead of two
+  stage_rows_async(Q + (static_cast<size_t>(b) * Tq + q0) * ldq + h * DH, ldq, qrows, sQ);
+  stage_kv(0, 0);
 
-  stage_rows(Q + (static_cast<size_t>(b) * Tq + q0) * ldq + h * DH, ldq, qrows, sQ);
-  __syncthreads();
   uint32_t qa[2][4];
-  load_a_frags(sQ, warp * 16, lane, qa);
-
   float o[4][4];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
@@ -121,27 +139,24 @@ attn_tc_fwd_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __rest
     for (int i = 0; i < 4; ++i) o[j][i] = 0.f;
   float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};      // rows lane/4 and lane/4 + 8 (raw score units)
 
-  for (int k0 = 0; k0 < Tk; k0 += TILE) {
-    const int rows = min(TILE, Tk - k0);
-    __syncthreads();
-    stage_rows(K + (static_cast<size_t>(b) * Tk + k0) * ldk + h * DH, ldk, rows, sK);
-    stage_rows(V + (static_cast<size_t>(b) * Tk + k0) * ldv + h * DH, ldv, rows, sV);
-    if (threadIdx.x < TILE) {
-      const int j = threadIdx.x;
-      const bool ok = j < rows && (kmask == nullptr || kmask[static_cast<size_t>(b) * Tk + k0 + j] != 0.f);
-      sBias[j] = ok ? 0.f : -INFINITY;
-    }
-    __syncthreads();
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    cp_async_wait_all();
+    __syncthreads();                       // tile t visible to all; everyone is done with tile t-1's buffer
+    if (t + 1 < ntiles) stage_kv(t + 1, buf ^ 1);
+    if (t == 0) load_a_frags(sQ, warp * 16, lane, qa);
+    const bf16* tK = sK[buf];
+    const bf16* tV = sV[buf];
     float s[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) s[j][i] = 0.f;
-    mma_nt(qa, sK, lane, s);
+    mma_nt(qa, tK, lane, s);
     float tmax[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float2 bias = *reinterpret_cast<const float2*>(&sBias[8 * j + 2 * (lane & 3)]);
+      const float2 bias = *reinterpret_cast<const float2*>(&sBias[buf][8 * j + 2 * (lane & 3)]);
       s[j][0] += bias.x; s[j][1] += bias.y; s[j][2] += bias.x; s[j][3] += bias.y;
       tmax[0] = fmaxf(tmax[0], fmaxf(s[j][0], s[j][1]));
       tmax[1] = fmaxf(tmax[1], fmaxf(s[j][2], s[j][3]));
@@ -170,7 +185,7 @@ attn_tc_fwd_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __rest
       p[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
     }
     l[0] += ls[0]; l[1] += ls[1];
-    mma_nn(p, sV, lane, o);
+    mma_nn(p, tV, lane, o);
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -196,7 +211,7 @@ attn_tc_fwd_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __rest
 // ------------------------------------------------------------------------------------------------------------
 // backward, dQ (one CTA per 64 queries, streaming key tiles).  Also emits delta = rowsum(dO * O).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 4)
 attn_tc_bwd_dq_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk,
                       const bf16* __restrict__ V, long long ldv, const float* __restrict__ kmask,
                       const bf16* __restrict__ O, long long ldo, const bf16* __restrict__ dO, long long lddo,
@@ -204,19 +219,33 @@ attn_tc_bwd_dq_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __r
                       int H, int Tq, int Tk, float scale) {
   __shared__ __align__(16) bf16 sQ[ROWS * LDS];
   __shared__ __align__(16) bf16 sG[ROWS * LDS];
-  __shared__ __align__(16) bf16 sK[TILE * LDS];
-  __shared__ __align__(16) bf16 sV[TILE * LDS];
-  __shared__ float sBias[TILE];
+  __shared__ __align__(16) bf16 sK[2][TILE * LDS];
+  __shared__ __align__(16) bf16 sV[2][TILE * LDS];
+  __shared__ float sBias[2][TILE];
   __shared__ float sDelta[ROWS];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qrows = min(ROWS, Tq - q0);
   const float c = scale * kLog2e;
-
-  stage_rows(Q + (static_cast<size_t>(b) * Tq + q0) * ldq + h * DH, ldq, qrows, sQ);
-  stage_rows(dO + (static_cast<size_t>(b) * Tq + q0) * lddo + h * DH, lddo, qrows, sG);
+  const int ntiles = (Tk + TILE - 1) / TILE;
+  const bf16* Kb = K + static_cast<size_t>(b) * Tk * ldk + h * DH;
+  const bf16* Vb = V + static_cast<size_t>(b) * Tk * ldv + h * DH;
+  auto stage_kv = [&](int t, int buf) {
+    const int k0 = t * TILE, rows = min(TILE, Tk - k0);
+    stage_rows_async(Kb + static_cast<size_t>(k0) * ldk, ldk, rows, sK[buf]);
+    stage_rows_async(Vb + static_cast<size_t>(k0) * ldv, ldv, rows, sV[buf]);
+    if (threadIdx.x < TILE) {
+      const int j = threadIdx.x;
+      const bool ok = j < rows && (kmask == nullptr || kmask[static_cast<size_t>(b) * Tk + k0 + j] != 0.f);
+      sBias[buf][j] = ok ? 0.f : -INFINITY;
+    }
+    cp_async_commit();
+  };
+  stage_rows_async(Q + (static_cast<size_t>(b) * Tq + q0) * ldq + h * DH, ldq, qrows, sQ);
+  stage_rows_async(dO + (static_cast<size_t>(b) * Tq + q0) * lddo + h * DH, lddo, qrows, sG);
+  stage_kv(0, 0);
   {
-    // delta[q] = sum_d dO[q,d] * O[q,d]: two threads per query, 16 columns each
+    // delta[q] = sum_d dO[q,d] * O[q,d]: two threads per query, 16 columns each (overlaps the copies above)
     const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
     float acc = 0.f;
     if (r < qrows) {
@@ -236,17 +265,12 @@ attn_tc_bwd_dq_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __r
       if (r < qrows) delta[(static_cast<size_t>(b) * H + h) * Tq + q0 + r] = acc;
     }
   }
-  __syncthreads();
   uint32_t qa[2][4], ga[2][4];
-  load_a_frags(sQ, warp * 16, lane, qa);
-  load_a_frags(sG, warp * 16, lane, ga);
   float rl[2], rd[2];                       // per-row lse (in log2 units) and delta
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
-    const int lr = warp * 16 + (lane >> 2) + 8 * r;
-    const int qi = q0 + lr;
+    const int qi = q0 + warp * 16 + (lane >> 2) + 8 * r;
     rl[r] = (qi < Tq) ? lse[(static_cast<size_t>(b) * H + h) * Tq + qi] * kLog2e : INFINITY;   // +inf -> P = 0
-    rd[r] = sDelta[lr];
   }
   float dq[4][4];
 #pragma unroll
@@ -254,34 +278,34 @@ attn_tc_bwd_dq_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __r
 #pragma unroll
     for (int i = 0; i < 4; ++i) dq[j][i] = 0.f;
 
-  for (int k0 = 0; k0 < Tk; k0 += TILE) {
-    const int rows = min(TILE, Tk - k0);
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    cp_async_wait_all();
     __syncthreads();
-    stage_rows(K + (static_cast<size_t>(b) * Tk + k0) * ldk + h * DH, ldk, rows, sK);
-    stage_rows(V + (static_cast<size_t>(b) * Tk + k0) * ldv + h * DH, ldv, rows, sV);
-    if (threadIdx.x < TILE) {
-      const int j = threadIdx.x;
-      const bool ok = j < rows && (kmask == nullptr || kmask[static_cast<size_t>(b) * Tk + k0 + j] != 0.f);
-      sBias[j] = ok ? 0.f : -INFINITY;
+    if (t + 1 < ntiles) stage_kv(t + 1, buf ^ 1);
+    if (t == 0) {
+      load_a_frags(sQ, warp * 16, lane, qa);
+      load_a_frags(sG, warp * 16, lane, ga);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) rd[r] = sDelta[warp * 16 + (lane >> 2) + 8 * r];
     }
-    __syncthreads();
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) { s[j][i] = 0.f; dp[j][i] = 0.f; }
-    mma_nt(qa, sK, lane, s);
-    mma_nt(ga, sV, lane, dp);
+    mma_nt(qa, sK[buf], lane, s);
+    mma_nt(ga, sV[buf], lane, dp);
     uint32_t ds[4][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float2 bias = *reinterpret_cast<const float2*>(&sBias[8 * j + 2 * (lane & 3)]);
+      const float2 bias = *reinterpret_cast<const float2*>(&sBias[buf][8 * j + 2 * (lane & 3)]);
       const float p0 = exp2f(s[j][0] * c + bias.x - rl[0]), p1 = exp2f(s[j][1] * c + bias.y - rl[0]);
       const float p2 = exp2f(s[j][2] * c + bias.x - rl[1]), p3 = exp2f(s[j][3] * c + bias.y - rl[1]);
       ds[j >> 1][(j & 1) * 2] = pack_bf16(p0 * (dp[j][0] - rd[0]), p1 * (dp[j][1] - rd[0]));
       ds[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2 * (dp[j][2] - rd[1]), p3 * (dp[j][3] - rd[1]));
     }
-    mma_nn(ds, sK, lane, dq);
+    mma_nn(ds, sK[buf], lane, dq);
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -298,7 +322,7 @@ attn_tc_bwd_dq_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __r
 // ------------------------------------------------------------------------------------------------------------
 // backward, dK / dV (one CTA per 64 keys, streaming query tiles): S^T = K Q^T, dP^T = V dO^T
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 4)
 attn_tc_bwd_dkv_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk,
                        const bf16* __restrict__ V, long long ldv, const float* __restrict__ kmask,
                        const bf16* __restrict__ dO, long long lddo, const float* __restrict__ lse,
@@ -306,21 +330,33 @@ attn_tc_bwd_dkv_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __
                        long long lddv, int H, int Tq, int Tk, float scale) {
   __shared__ __align__(16) bf16 sK[ROWS * LDS];
   __shared__ __align__(16) bf16 sV[ROWS * LDS];
-  __shared__ __align__(16) bf16 sQ[TILE * LDS];
-  __shared__ __align__(16) bf16 sG[TILE * LDS];
-  __shared__ float sLse[TILE];             // log2 units; +inf for out-of-range queries -> P = 0
-  __shared__ float sDel[TILE];
+  __shared__ __align__(16) bf16 sQ[2][TILE * LDS];
+  __shared__ __align__(16) bf16 sG[2][TILE * LDS];
+  __shared__ float sLse[2][TILE];          // log2 units; +inf for out-of-range queries -> P = 0
+  __shared__ float sDel[2][TILE];
   const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int krows = min(ROWS, Tk - k0);
   const float c = scale * kLog2e;
-
-  stage_rows(K + (static_cast<size_t>(b) * Tk + k0) * ldk + h * DH, ldk, krows, sK);
-  stage_rows(V + (static_cast<size_t>(b) * Tk + k0) * ldv + h * DH, ldv, krows, sV);
-  __syncthreads();
+  const int ntiles = (Tq + TILE - 1) / TILE;
+  const bf16* Qb = Q + static_cast<size_t>(b) * Tq * ldq + h * DH;
+  const bf16* Gb = dO + static_cast<size_t>(b) * Tq * lddo + h * DH;
+  auto stage_q = [&](int t, int buf) {
+    const int q0 = t * TILE, rows = min(TILE, Tq - q0);
+    stage_rows_async(Qb + static_cast<size_t>(q0) * ldq, ldq, rows, sQ[buf]);
+    stage_rows_async(Gb + static_cast<size_t>(q0) * lddo, lddo, rows, sG[buf]);
+    if (threadIdx.x < TILE) {
+      const int j = threadIdx.x;
+      const size_t idx = (static_cast<size_t>(b) * H + h) * Tq + q0 + j;
+      sLse[buf][j] = (j < rows) ? lse[idx] * kLog2e : INFINITY;
+      sDel[buf][j] = (j < rows) ? delta[idx] : 0.f;
+    }
+    cp_async_commit();
+  };
+  stage_rows_async(K + (static_cast<size_t>(b) * Tk + k0) * ldk + h * DH, ldk, krows, sK);
+  stage_rows_async(V + (static_cast<size_t>(b) * Tk + k0) * ldv + h * DH, ldv, krows, sV);
+  stage_q(0, 0);
   uint32_t ka[2][4], va[2][4];
-  load_a_frags(sK, warp * 16, lane, ka);
-  load_a_frags(sV, warp * 16, lane, va);
   float kb[2];                              // 0 / -inf per owned key row
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -334,30 +370,27 @@ attn_tc_bwd_dkv_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __
 #pragma unroll
     for (int i = 0; i < 4; ++i) { dk[j][i] = 0.f; dv[j][i] = 0.f; }
 
-  for (int q0 = 0; q0 < Tq; q0 += TILE) {
-    const int rows = min(TILE, Tq - q0);
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    cp_async_wait_all();
     __syncthreads();
-    stage_rows(Q + (static_cast<size_t>(b) * Tq + q0) * ldq + h * DH, ldq, rows, sQ);
-    stage_rows(dO + (static_cast<size_t>(b) * Tq + q0) * lddo + h * DH, lddo, rows, sG);
-    if (threadIdx.x < TILE) {
-      const int j = threadIdx.x;
-      const size_t idx = (static_cast<size_t>(b) * H + h) * Tq + q0 + j;
-      sLse[j] = (j < rows) ? lse[idx] * kLog2e : INFINITY;
-      sDel[j] = (j < rows) ? delta[idx] : 0.f;
+    if (t + 1 < ntiles) stage_q(t + 1, buf ^ 1);
+    if (t == 0) {
+      load_a_frags(sK, warp * 16, lane, ka);
+      load_a_frags(sV, warp * 16, lane, va);
     }
-    __syncthreads();
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int i = 0; i < 4; ++i) { s[j][i] = 0.f; dp[j][i] = 0.f; }
-    mma_nt(ka, sQ, lane, s);               // [keys x queries]
-    mma_nt(va, sG, lane, dp);
+    mma_nt(ka, sQ[buf], lane, s);               // [keys x queries]
+    mma_nt(va, sG[buf], lane, dp);
     uint32_t pt[4][4], dst[4][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float2 ql = *reinterpret_cast<const float2*>(&sLse[8 * j + 2 * (lane & 3)]);
-      const float2 qd = *reinterpret_cast<const float2*>(&sDel[8 * j + 2 * (lane & 3)]);
+      const float2 ql = *reinterpret_cast<const float2*>(&sLse[buf][8 * j + 2 * (lane & 3)]);
+      const float2 qd = *reinterpret_cast<const float2*>(&sDel[buf][8 * j + 2 * (lane & 3)]);
       const float p0 = exp2f(s[j][0] * c + kb[0] - ql.x), p1 = exp2f(s[j][1] * c + kb[0] - ql.y);
       const float p2 = exp2f(s[j][2] * c + kb[1] - ql.x), p3 = exp2f(s[j][3] * c + kb[1] - ql.y);
       pt[j >> 1][(j & 1) * 2] = pack_bf16(p0, p1);
@@ -365,8 +398,8 @@ attn_tc_bwd_dkv_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __
       dst[j >> 1][(j & 1) * 2] = pack_bf16(p0 * (dp[j][0] - qd.x), p1 * (dp[j][1] - qd.y));
       dst[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2 * (dp[j][2] - qd.x), p3 * (dp[j][3] - qd.y));
     }
-    mma_nn(pt, sG, lane, dv);              // dV += P^T dO
-    mma_nn(dst, sQ, lane, dk);             // dK += dS^T Q
+    mma_nn(pt, sG[buf], lane, dv);              // dV += P^T dO
+    mma_nn(dst, sQ[buf], lane, dk);             // dK += dS^T Q
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
