@@ -71,14 +71,6 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar,
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-// the same box delivered to every CTA of the cluster (same shared offset, same barrier offset in each)
-__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
-}
 // 1-D bulk copies: shared -> global, and global -> the same shared offset of every CTA in `mask`
 __device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
@@ -282,22 +274,6 @@ __device__ __forceinline__ void load_vec64(const float* __restrict__ p, float (&
     v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
   }
 }
-__device__ __forceinline__ void load_vec32(const float* __restrict__ p, float (&v)[32]) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + k);
-    v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
-  }
-}
-__device__ __forceinline__ void store_bf16_64(__nv_bfloat16* p, const float (&v)[NS]) {
-#pragma unroll
-  for (int k = 0; k < NS / 8; ++k) {
-    uint4 w;
-    w.x = pack2(v[8 * k], v[8 * k + 1]); w.y = pack2(v[8 * k + 2], v[8 * k + 3]);
-    w.z = pack2(v[8 * k + 4], v[8 * k + 5]); w.w = pack2(v[8 * k + 6], v[8 * k + 7]);
-    reinterpret_cast<uint4*>(p)[k] = w;
-  }
-}
 __device__ __forceinline__ void store_f32_64(float* p, const float (&v)[NS]) {
 #pragma unroll
   for (int k = 0; k < NS / 4; ++k) reinterpret_cast<float4*>(p)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
@@ -444,7 +420,6 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) load_w<0>(c, &tmW1, 0, false, 0);
     for (int g = 0; g < 2 * L; ++g) {
-      const int layer = g >> 1;
       __syncwarp();
       if ((g & 1) == 0) { cluster_sync_all(); cluster_sync_all(); }     // the two LayerNorm statistics rounds
       cluster_sync_all();                                               // operand slices of GEMM g published
@@ -474,7 +449,6 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
     const bool valid = row < p.B;
     const int col0 = static_cast<int>(c.rank) * NS;
     const uint32_t taddr = c.tmem + (static_cast<uint32_t>(q * 32) << 16);
-    const size_t BP = static_cast<size_t>(p.B) * PD;
     float hv[NS];
     if (valid) load_vec64(p.h + static_cast<size_t>(row) * PD + col0, hv);
     else {
@@ -586,7 +560,6 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
   if (warp == 0) {
     if (lane == 0) load_w<1>(c, &tmW2, L - 1, false, 0);
     for (int g = 0; g < 2 * L; ++g) {
-      const int layer = L - 1 - (g >> 1);
       __syncwarp();
       cluster_sync_all();                                               // operand slices of GEMM g published
       if (lane == 0) {

@@ -432,12 +432,8 @@ int clf_fwd(const ser_clf_desc& d, cudaStream_t s) {
     return SER_ERR_UNSUPPORTED;
   }
   SER_TRY(layernorm_fwd(d.q, 1, d.f, 1, nullptr, 1, d.ln_out_g, d.ln_out_b, d.stats_q, B, F, 1, s));
-  // heads run in fp32 on the master weights (tiny: C x 256, 64 x 256)
-  SER_TRY(linear_fwd(DT_F32, B, d.C, F, d.f, F, d.w_c, F, d.b_c, d.logits, d.C, 1, ACT_NONE, nullptr, 0, 1, s));
-  if (d.unc != nullptr) {
-    SER_TRY(linear_fwd(DT_F32, B, d.U, F, d.f, F, d.w_u1, F, d.b_u1, d.u1, d.U, 1, ACT_RELU, nullptr, 0, 1, s));
-    SER_TRY(linear_fwd(DT_F32, B, 1, d.U, d.u1, d.U, d.w_u2, d.U, d.b_u2, d.unc, 1, 1, ACT_SIGMOID, nullptr, 0, 1, s));
-  }
+  // heads run in fp32 on the master weights (tiny: C x 256, 64 x 256), one fused launch (heads.cu)
+  SER_TRY(heads_fwd(d.f, d.w_c, d.b_c, d.w_u1, d.b_u1, d.w_u2, d.b_u2, d.logits, d.u1, d.unc, B, F, d.C, d.U, s));
   return SER_OK;
 }
 
@@ -471,32 +467,9 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
   void* dr_all = ws.take(static_cast<size_t>(L) * BP * e);      // [L,B,P] act: gradient at relu(W1 n + b1)
   if (!ws.ok) { set_last_error(__FILE__, __LINE__, "clf_bwd: workspace too small"); return SER_ERR_WORKSPACE; }
 
-  // ---- heads (fp32) ----
-  bool have_df = false;
-  if (d.dlogits != nullptr) {
-    SER_TRY(colsum(d.dlogits, 1, C, B, C, d.db_c, s));
-    SER_TRY(linear_wgrad(DT_F32, B, C, F, d.dlogits, C, d.f, F, d.dw_c, F, s));
-    SER_TRY(linear_dgrad(DT_F32, B, C, F, d.dlogits, C, d.w_c, F, df, F, 1, nullptr, 0, 1, GATE_NONE, nullptr, 0, 1, s));
-    have_df = true;
-  } else {
-    SER_CUDA_CHECK(cudaMemsetAsync(d.db_c, 0, sizeof(float) * C, s));
-    SER_CUDA_CHECK(cudaMemsetAsync(d.dw_c, 0, sizeof(float) * C * F, s));
-  }
-  if (d.dunc != nullptr && d.unc != nullptr) {
-    SER_TRY(sigmoid_bwd(d.dunc, d.unc, dsg, B, s));
-    SER_TRY(colsum(dsg, 1, 1, B, 1, d.db_u2, s));
-    SER_TRY(linear_wgrad(DT_F32, B, 1, U, dsg, 1, d.u1, U, d.dw_u2, U, s));
-    SER_TRY(linear_dgrad(DT_F32, B, 1, U, dsg, 1, d.w_u2, U, du1, U, 1, d.u1, U, 1, GATE_RELU, nullptr, 0, 1, s));
-    SER_TRY(colsum(du1, 1, U, B, U, d.db_u1, s));
-    SER_TRY(linear_wgrad(DT_F32, B, U, F, du1, U, d.f, F, d.dw_u1, F, s));
-    SER_TRY(linear_dgrad(DT_F32, B, U, F, du1, U, d.w_u1, F, df, F, 1, nullptr, 0, 1, GATE_NONE, have_df ? df : nullptr, F, 1, s));
-    have_df = true;
-  } else {
-    SER_CUDA_CHECK(cudaMemsetAsync(d.db_u2, 0, sizeof(float), s));
-    SER_CUDA_CHECK(cudaMemsetAsync(d.dw_u2, 0, sizeof(float) * U, s));
-    SER_CUDA_CHECK(cudaMemsetAsync(d.db_u1, 0, sizeof(float) * U, s));
-    SER_CUDA_CHECK(cudaMemsetAsync(d.dw_u1, 0, sizeof(float) * U * F, s));
-  }
+  // ---- heads (fp32): row-wise gradients + every head parameter gradient in two launches (heads.cu) ----
+  SER_TRY(heads_bwd(d.dlogits, d.dunc, d.unc, d.u1, d.f, d.w_c, d.w_u1, d.w_u2, df, du1, dsg, d.dw_c, d.db_c, d.dw_u1,
+                    d.db_u1, d.dw_u2, d.db_u2, B, F, C, U, s));
   // ---- output projection: relu(LN(q)) ----
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_out_g, 0, sizeof(float) * F, s));
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_out_b, 0, sizeof(float) * F, s));

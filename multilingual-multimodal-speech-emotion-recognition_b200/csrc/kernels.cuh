@@ -73,6 +73,17 @@ bool clf_stack_supported(int dtype, int P, int L, const ClfStackArgs& a);
 int clf_stack_fwd(const ClfStackArgs& a, cudaStream_t s);
 int clf_stack_bwd(const ClfStackArgs& a, cudaStream_t s);
 
+// ---- heads.cu ------------------------------------------------------------------------------------
+// logits + uncertainty head on the fp32 penultimate features (classifier.py:192-198,224,229); u1 / unc may be NULL
+int heads_fwd(const float* f, const float* w_c, const float* b_c, const float* w_u1, const float* b_u1,
+              const float* w_u2, const float* b_u2, float* logits, float* u1, float* unc, int B, int F, int C, int U,
+              cudaStream_t s);
+// dlogits / dunc may be NULL (treated as zero); every parameter gradient is written (not accumulated)
+int heads_bwd(const float* dlogits, const float* dunc, const float* unc, const float* u1, const float* f,
+              const float* w_c, const float* w_u1, const float* w_u2, float* df, float* du1, float* dsg, float* dw_c,
+              float* db_c, float* dw_u1, float* db_u1, float* dw_u2, float* db_u2, int B, int F, int C, int U,
+              cudaStream_t s);
+
 // ---- pooling.cu ----------------------------------------------------------------------------------
 // Attentive statistics pooling, everything after the 768->128 tanh GEMM (src/models/pooling.py:21-28).
 struct AspArgs {

@@ -40,12 +40,29 @@ def test_struct_layouts_match_the_compiled_library(lib):
 
 
 def test_blackwell_instructions_present(lib):
-    """The GEMM path must be tcgen05 + TMA + TMEM loads (SASS: UTCHMMA / UTMALDG / LDTM), not mma.sync."""
+    """The GEMM path and the fused classifier stack must be tcgen05 + TMA + TMEM (SASS: UTCHMMA / UTMALDG / UTMASTG /
+    LDTM).  The legacy mma.sync path (SASS HMMA) is allowed in exactly one place: the dh = 32 attention core
+    (attention_tc.cu), and nowhere else."""
     sass = subprocess.run(["cuobjdump", "-sass", lib.LIB_PATH], capture_output=True, text=True).stdout
     if not sass:
         pytest.skip("cuobjdump unavailable")
-    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
-    assert "HMMA." not in sass.replace("UTCHMMA", "")
+    funcs, cur = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            funcs[cur] = []
+        elif cur is not None:
+            funcs[cur].append(line)
+    body = {k: "\n".join(v) for k, v in funcs.items()}
+    gemm = [k for k in body if "gemm_tc_kernel" in k]
+    stack = [k for k in body if "clf_stack_fwd_kernel" in k or "clf_stack_bwd_kernel" in k]
+    assert gemm and len(stack) == 2
+    for k in gemm:
+        assert "UTCHMMA" in body[k] and "UTMALDG" in body[k] and "LDTM" in body[k] and "UTMASTG" in body[k], k
+    for k in stack:
+        assert "UTCHMMA" in body[k] and "LDTM" in body[k] and "UTMASTG" in body[k] and "UBLKCP" in body[k], k
+    legacy = [k for k, b in body.items() if "HMMA." in b.replace("UTCHMMA", "")]
+    assert legacy and all("attn_tc_" in k for k in legacy), legacy
 
 
 def test_state_dict_keys_match_reference_goldens(lib, golden_dir):
