@@ -86,6 +86,8 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_but_one() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -287,6 +289,10 @@ __device__ __forceinline__ void publish_slice(const Ctx& c, const float (&v)[NS]
   const uint32_t tile = c.sA + c.rank * A_BYTES;
   const uint32_t base = tile + static_cast<uint32_t>(rl) * 128u;
   const uint32_t swz = static_cast<uint32_t>(rl & 7);
+  // earlier bulk stores may still be READING the staging tiles (the saved-activation store of the previous slice,
+  // the fp32 stream stores): drain their reads before the tile is rewritten
+  if (et == 0) bulk_wait_read_all();
+  named_bar_sync(3, 128);
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     sts128(base + ((static_cast<uint32_t>(j) ^ swz) << 4), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
@@ -294,10 +300,13 @@ __device__ __forceinline__ void publish_slice(const Ctx& c, const float (&v)[NS]
   fence_async_smem();
   named_bar_sync(3, 128);
   if (et == 0) {
+    // only the exchange block is on the critical path: its own bulk group, waited for completion; the
+    // saved-activation store rides in a second group that is merely drained before the next rewrite
     bulk_store(xblock, tile, A_BYTES);
+    bulk_commit();
     tma_store_3d(tm_save, tile, col0, c.row0, layer);
     bulk_commit();
-    bulk_wait_all();
+    bulk_wait_but_one();
   }
 }
 // fp32 row-slice (64 floats = 2 x 128 B per thread) -> two swizzled tiles in the idle k-blocks next to our own ->
@@ -612,7 +621,8 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       SER_TL(17);
       cluster_sync_all();
       SER_TL(18);
-      // operands of the epilogues below, requested while the GEMM runs
+      // operands of the epilogues below, requested while the GEMM runs (row-per-thread loads: 32 L1 wavefronts per
+      // instruction -- they must not sit in front of the publish in the load/store pipe, measured +4500 cycles)
       float xo[NS];
       float2 so = make_float2(0.f, 0.f), si = make_float2(0.f, 0.f);
       uint4 um[NS / 8];
