@@ -31,9 +31,9 @@ namespace {
 constexpr int CS = 8;                 // CTAs per cluster = column slices
 constexpr int PD = 512;               // base_dim of the stack
 constexpr int NS = PD / CS;           // 64 output columns per CTA
-constexpr int RM = 128;               // rows per cluster (UMMA M)
+constexpr int RM = 128;               // maximum rows per cluster (UMMA M = 128); small batches run M = 64 clusters
 constexpr int KBLK = PD / 64;         // 8 k-blocks of 64
-constexpr int A_BYTES = RM * 128;     // one k-block of the A operand: 128 rows x 128 B
+constexpr int A_BYTES = RM * 128;     // one k-block of the A operand at M = 128: 128 rows x 128 B (shared-memory carve-up)
 constexpr int W_BYTES = NS * 128;     // one weight stage: 64 x 64 bf16
 constexpr int kThreads = 192;
 constexpr float kEps = 1e-5f;
@@ -154,9 +154,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= 2ull << 61;
   return d;
 }
-template <int BMAJ> __device__ __forceinline__ constexpr uint32_t make_idesc() {
+template <int BMAJ> __device__ __forceinline__ uint32_t make_idesc(int rm) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(BMAJ) << 16) |
-         (static_cast<uint32_t>(NS >> 3) << 17) | (static_cast<uint32_t>(RM >> 4) << 24);
+         (static_cast<uint32_t>(NS >> 3) << 17) | (static_cast<uint32_t>(rm >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
@@ -173,72 +173,91 @@ struct Ctx {
   uint32_t tmem;
   uint32_t rank;                         // column slice of this CTA
   int row0;                              // first row of the cluster
+  int rm;                                // rows per cluster: 128 (UMMA M = 128) or 64 (UMMA M = 64)
+  uint32_t a_bytes;                      // rm * 128: one k-block of the A operand / one exchange block
 };
 
 __device__ __forceinline__ uint32_t bar_at(uint32_t base, int i) { return base + 8u * static_cast<uint32_t>(i); }
 
-// MMA issuer: one GEMM = 8 k-blocks x 4 tcgen05.mma (M=128, N=64, K=16) into the 64-column accumulator
+// MMA issuer: one GEMM = 8 k-blocks x 4 tcgen05.mma (M = 128 or 64, N = 64, K = 16) into the 64-column accumulator.
+// The issuing thread is the critical path of a GEMM phase (an N = 64 MMA is accepted every ~46 cycles, measured), so
+// the loop carries nothing but the MMAs: one operand barrier, two weight barriers (k-blocks 0-3 / 4-7), ONE commit.
 template <int BMAJ>
 __device__ __forceinline__ void issue_gemm(const Ctx& c, uint32_t parity, long long* tl = nullptr) {
-  constexpr uint32_t idesc = make_idesc<BMAJ>();
+  const uint32_t idesc = make_idesc<BMAJ>(c.rm);
   constexpr uint32_t b_kstep = (BMAJ == 0) ? 32u : 16u * 128u;     // bytes per K = 16 step inside a weight stage
   constexpr uint32_t b_lbo = (BMAJ == 0) ? 0u : 64u * 128u;
-  for (int kb = 0; kb < KBLK; ++kb) {
-    mbar_wait(bar_at(c.a_full, kb), parity);
-    if (tl != nullptr && (kb == 0 || kb == KBLK - 1)) tl[kb == 0 ? 1 : 2] = clock64();
-    mbar_wait(bar_at(c.w_full, kb), parity);
-    tc_fence_after();
-    const uint32_t sa = c.sA + kb * A_BYTES;
-    const uint32_t sb = c.sW + kb * W_BYTES;
+  // descriptors differ only in their start-address field (bits 0-13, 16-byte units): build the two bases once and
+  // step them with one add per MMA -- the issue loop is a single thread's dependent instruction stream
+  const uint64_t a_base = make_smem_desc(c.sA, 0u, 1024u);
+  const uint64_t b_base = make_smem_desc(c.sW, b_lbo, 1024u);
+  const uint64_t a_kb = static_cast<uint64_t>(c.a_bytes >> 4);     // descriptor units per k-block of A
+  mbar_wait(bar_at(c.a_full, 0), parity);                          // the whole operand arrives as one transfer
+  if (tl != nullptr) tl[1] = clock64();
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint64_t adesc = make_smem_desc(sa + k * 32u, 0u, 1024u);
-      const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024u);
-      tc_mma_bf16(c.tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+  for (int half = 0; half < 2; ++half) {
+    mbar_wait(bar_at(c.w_full, half), parity);
+    tc_fence_after();
+    if (tl != nullptr && half == 1) tl[2] = clock64();
+#pragma unroll
+    for (int kq = 0; kq < KBLK / 2; ++kq) {
+      const int kb = half * (KBLK / 2) + kq;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t adesc = a_base + static_cast<uint64_t>(kb) * a_kb + static_cast<uint64_t>((k * 32u) >> 4);
+        const uint64_t bdesc = b_base + static_cast<uint64_t>((kb * W_BYTES + k * b_kstep) >> 4);
+        tc_mma_bf16(c.tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+      }
     }
-    tc_commit(bar_at(c.w_empty, kb));      // weight stage (and this k-block of A) consumed
   }
-  tc_commit(c.acc_full);
+  tc_commit(c.acc_full);                   // accumulator complete; also tells the producer the weight ring is free
   if (tl != nullptr) tl[3] = clock64();
 }
 
-// producer: full-width A operand (128 rows x 512) of one GEMM from the exchange buffer `tm` (layer `layer`)
 // Exchange buffer (global, L2 resident): [cluster][slot = GEMM parity][k-block = producing CTA][128 rows x 128 B], each
 // 16 KB block already in the 128B-swizzled K-major image the tensor core reads.  Every CTA arms all eight k-block
 // barriers, then fetches ONE block -- the slice it published itself -- as a single contiguous bulk copy multicast
 // to the whole cluster (a contiguous 16 KB request moves several times faster than 128 strided 128-byte rows).
 __device__ __forceinline__ char* xchg_block(const Ctx& c, char* xchg, int g) {
-  return xchg + ((static_cast<size_t>(blockIdx.x / CS) * 2 + (g & 1)) * CS + c.rank) * A_BYTES;
+  return xchg + ((static_cast<size_t>(blockIdx.x / CS) * 2 + (g & 1)) * CS + c.rank) * c.a_bytes;
 }
+// Measured on B200: incoming bulk transfers are delivered to a CTA one after the other, ~600 cycles each whether they
+// carry 8 or 16 KB, so eight per-slice multicasts take ~4800 cycles.  The eight blocks of a slot are contiguous in the
+// exchange buffer, so CTA 0 fetches the WHOLE operand as one bulk copy and multicasts it to the cluster.
 __device__ __forceinline__ void load_a(const Ctx& c, char* xchg, int g) {
   fence_proxy_async_all();
-  for (int kb = 0; kb < KBLK; ++kb) mbar_expect_tx(bar_at(c.a_full, kb), A_BYTES);
-  const uint32_t kb = c.rank;
-  bulk_load_mc(c.sA + kb * A_BYTES, xchg_block(c, xchg, g), A_BYTES, bar_at(c.a_full, kb), static_cast<uint16_t>((1u << CS) - 1u));
+  mbar_expect_tx(bar_at(c.a_full, 0), KBLK * c.a_bytes);
+  if (c.rank == 0) {
+    char* slot = xchg + (static_cast<size_t>(blockIdx.x / CS) * 2 + (g & 1)) * CS * c.a_bytes;
+    bulk_load_mc(c.sA, slot, KBLK * c.a_bytes, bar_at(c.a_full, 0), static_cast<uint16_t>((1u << CS) - 1u));
+  }
 }
 // producer: weight slice of one GEMM.  FWD: rows = output features of this CTA, columns = k; BWD (MN-major):
 // rows = k (output features of the forward Linear), columns = this CTA's input features.
-// `a_parity` >= 0: hold the weight traffic back until the whole A operand of the running GEMM has landed -- shared-
-// memory fill bandwidth per SM (~30-50 B/clk measured) is what bounds a GEMM phase, and A is on the critical path
-// while next GEMM's weights have a whole epilogue phase of idle fill time ahead of them.
+// The 64 KB ring holds exactly one GEMM's slice, so the next GEMM's weights are requested the moment the running
+// GEMM's accumulator is complete (`acc_parity` >= 0: wait for that commit) and land during the epilogue / exchange
+// phase that follows, when nothing else is filling shared memory.
 template <int BMAJ>
-__device__ __forceinline__ void load_w(const Ctx& c, const CUtensorMap* tm, int layer, bool wait_empty, uint32_t empty_parity,
-                                       int a_parity = -1) {
-  if (a_parity >= 0)
-    for (int kb = 0; kb < KBLK; ++kb) mbar_wait(bar_at(c.a_full, kb), static_cast<uint32_t>(a_parity));
-  for (int kb = 0; kb < KBLK; ++kb) {
-    if (wait_empty) mbar_wait(bar_at(c.w_empty, kb), empty_parity);
-    mbar_expect_tx(bar_at(c.w_full, kb), W_BYTES);
-    if (BMAJ == 0) tma_load_3d(tm, bar_at(c.w_full, kb), c.sW + kb * W_BYTES, kb * 64, static_cast<int>(c.rank) * NS, layer);
-    else           tma_load_3d(tm, bar_at(c.w_full, kb), c.sW + kb * W_BYTES, static_cast<int>(c.rank) * NS, kb * 64, layer);
+__device__ __forceinline__ void load_w(const Ctx& c, const CUtensorMap* tm, int layer, int acc_parity) {
+  if (acc_parity >= 0) mbar_wait(c.acc_full, static_cast<uint32_t>(acc_parity));
+  for (int half = 0; half < 2; ++half) {
+    mbar_expect_tx(bar_at(c.w_full, half), (KBLK / 2) * W_BYTES);
+    for (int kq = 0; kq < KBLK / 2; ++kq) {
+      const int kb = half * (KBLK / 2) + kq;
+      if (BMAJ == 0) tma_load_3d(tm, bar_at(c.w_full, half), c.sW + kb * W_BYTES, kb * 64, static_cast<int>(c.rank) * NS, layer);
+      else           tma_load_3d(tm, bar_at(c.w_full, half), c.sW + kb * W_BYTES, static_cast<int>(c.rank) * NS, kb * 64, layer);
+    }
   }
 }
 
 // all-reduce of two per-row partial values over the 8 column slices of the cluster (one cluster barrier)
-__device__ __forceinline__ void exchange2(const Ctx& c, int buf, int rl, float a, float b, float (&oa)[CS], float (&ob)[CS]) {
+__device__ __forceinline__ void exchange2(const Ctx& c, int buf, int rl, bool active, float a, float b, float (&oa)[CS],
+                                          float (&ob)[CS]) {
   const uint32_t slot = c.sStats + static_cast<uint32_t>(((buf * CS + static_cast<int>(c.rank)) * RM + rl) * 8);
+  if (active) {
 #pragma unroll
-  for (int t = 0; t < CS; ++t) st_cluster_f2(map_to_cta(slot, t), a, b);
+    for (int t = 0; t < CS; ++t) st_cluster_f2(map_to_cta(slot, t), a, b);
+  }
   cluster_sync_all();
 #pragma unroll
   for (int s = 0; s < CS; ++s) {
@@ -248,7 +267,8 @@ __device__ __forceinline__ void exchange2(const Ctx& c, int buf, int rl, float a
 }
 
 // LayerNorm statistics of a 512-wide row held as 8 slices of 64: local two-pass (mean, M2), Chan combination
-__device__ __forceinline__ void row_stats(const Ctx& c, int buf, int rl, const float (&v)[NS], float& mean, float& rstd) {
+__device__ __forceinline__ void row_stats(const Ctx& c, int buf, int rl, bool active, const float (&v)[NS], float& mean,
+                                          float& rstd) {
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < NS; ++k) s += v[k];
@@ -257,7 +277,7 @@ __device__ __forceinline__ void row_stats(const Ctx& c, int buf, int rl, const f
 #pragma unroll
   for (int k = 0; k < NS; ++k) { const float d = v[k] - m; q = fmaf(d, d, q); }
   float ms[CS], qs[CS];
-  exchange2(c, buf, rl, m, q, ms, qs);
+  exchange2(c, buf, rl, active, m, q, ms, qs);
   float mu = 0.f;
 #pragma unroll
   for (int t = 0; t < CS; ++t) mu += ms[t];
@@ -284,25 +304,27 @@ __device__ __forceinline__ void store_f32_64(float* p, const float (&v)[NS]) {
 // the A buffer (swizzled), from where one thread sends it (a) as a contiguous 16 KB bulk store to the exchange buffer
 // and (b) as a TMA tensor store to the saved-activation buffer [L,B,512] the backward pass reads (rows >= B are
 // clipped by the tensor map).  Both stores are complete before the caller enters the cluster barrier.
-__device__ __forceinline__ void publish_slice(const Ctx& c, const float (&v)[NS], int rl, int et, char* xblock,
+__device__ __forceinline__ void publish_slice(const Ctx& c, const float (&v)[NS], int rl, bool active, int et, char* xblock,
                                               const CUtensorMap* tm_save, int col0, int layer) {
-  const uint32_t tile = c.sA + c.rank * A_BYTES;
+  const uint32_t tile = c.sA + c.rank * c.a_bytes;
   const uint32_t base = tile + static_cast<uint32_t>(rl) * 128u;
   const uint32_t swz = static_cast<uint32_t>(rl & 7);
   // earlier bulk stores may still be READING the staging tiles (the saved-activation store of the previous slice,
   // the fp32 stream stores): drain their reads before the tile is rewritten
   if (et == 0) bulk_wait_read_all();
   named_bar_sync(3, 128);
+  if (active) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    sts128(base + ((static_cast<uint32_t>(j) ^ swz) << 4), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
-           pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+    for (int j = 0; j < 8; ++j)
+      sts128(base + ((static_cast<uint32_t>(j) ^ swz) << 4), pack2(v[8 * j], v[8 * j + 1]), pack2(v[8 * j + 2], v[8 * j + 3]),
+             pack2(v[8 * j + 4], v[8 * j + 5]), pack2(v[8 * j + 6], v[8 * j + 7]));
+  }
   fence_async_smem();
   named_bar_sync(3, 128);
   if (et == 0) {
     // only the exchange block is on the critical path: its own bulk group, waited for completion; the
     // saved-activation store rides in a second group that is merely drained before the next rewrite
-    bulk_store(xblock, tile, A_BYTES);
+    bulk_store(xblock, tile, c.a_bytes);
     bulk_commit();
     tma_store_3d(tm_save, tile, col0, c.row0, layer);
     bulk_commit();
@@ -311,22 +333,24 @@ __device__ __forceinline__ void publish_slice(const Ctx& c, const float (&v)[NS]
 }
 // fp32 row-slice (64 floats = 2 x 128 B per thread) -> two swizzled tiles in the idle k-blocks next to our own ->
 // two TMA tensor stores (fire and forget; drained by the next publish_slice before any peer can overwrite the tiles)
-__device__ __forceinline__ void store_slice_f32(const Ctx& c, const float (&v)[NS], int rl, int et, const CUtensorMap* tm,
-                                                int col0, int layer) {
+__device__ __forceinline__ void store_slice_f32(const Ctx& c, const float (&v)[NS], int rl, bool active, int et,
+                                                const CUtensorMap* tm, int col0, int layer) {
   const uint32_t swz = static_cast<uint32_t>(rl & 7);
+  if (active) {
 #pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const uint32_t base = c.sA + ((c.rank + 1u + t) & 7u) * A_BYTES + static_cast<uint32_t>(rl) * 128u;
+    for (int t = 0; t < 2; ++t) {
+      const uint32_t base = c.sA + ((c.rank + 1u + t) & 7u) * c.a_bytes + static_cast<uint32_t>(rl) * 128u;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      sts128(base + ((static_cast<uint32_t>(j) ^ swz) << 4), __float_as_uint(v[32 * t + 4 * j]), __float_as_uint(v[32 * t + 4 * j + 1]),
-             __float_as_uint(v[32 * t + 4 * j + 2]), __float_as_uint(v[32 * t + 4 * j + 3]));
+      for (int j = 0; j < 8; ++j)
+        sts128(base + ((static_cast<uint32_t>(j) ^ swz) << 4), __float_as_uint(v[32 * t + 4 * j]),
+               __float_as_uint(v[32 * t + 4 * j + 1]), __float_as_uint(v[32 * t + 4 * j + 2]), __float_as_uint(v[32 * t + 4 * j + 3]));
+    }
   }
   fence_async_smem();
   named_bar_sync(3, 128);
   if (et == 0) {
-    tma_store_3d(tm, c.sA + ((c.rank + 1u) & 7u) * A_BYTES, col0, c.row0, layer);
-    tma_store_3d(tm, c.sA + ((c.rank + 2u) & 7u) * A_BYTES, col0 + 32, c.row0, layer);
+    tma_store_3d(tm, c.sA + ((c.rank + 1u) & 7u) * c.a_bytes, col0, c.row0, layer);
+    tma_store_3d(tm, c.sA + ((c.rank + 2u) & 7u) * c.a_bytes, col0 + 32, c.row0, layer);
     bulk_commit();
   }
 }
@@ -342,6 +366,7 @@ __device__ __forceinline__ uint32_t par_addr(const Ctx& c, int buf, int vec) { r
 
 struct StackParams {
   int B, L;
+  int rm;                                          // rows per cluster (128 or 64)
   const float* pv[6]; long long ps[6]; int npv;   // per-layer parameter vectors staged in shared memory (layer-0 pointer, stride)
   long long* dbg;                                  // optional clock64 timeline of one block (SER_CLF_TIMELINE)
   char* xchg;                                      // exchange buffer, ceil(B/128) * 2 * 128 KB
@@ -374,7 +399,9 @@ __device__ __forceinline__ void par_advance(const Ctx& c, const StackParams& p, 
 }
 #define SER_TL(k) do { if (tl) p.dbg[k] = clock64(); } while (0)
 
-__device__ __forceinline__ void setup(Ctx& c, uint8_t* smem, int warp, int lane) {
+__device__ __forceinline__ void setup(Ctx& c, uint8_t* smem, int warp, int lane, int rm) {
+  c.rm = rm;
+  c.a_bytes = static_cast<uint32_t>(rm) * 128u;
   c.sA = smem_u32(smem + OFF_A);
   c.sW = smem_u32(smem + OFF_W);
   c.sStats = smem_u32(smem + OFF_STATS);
@@ -384,7 +411,7 @@ __device__ __forceinline__ void setup(Ctx& c, uint8_t* smem, int warp, int lane)
   c.a_full = bars; c.w_full = bars + 64; c.w_empty = bars + 128; c.acc_full = bars + 192;
   const uint32_t tmem_slot = bars + 200;
   c.rank = cluster_rank();
-  c.row0 = static_cast<int>(blockIdx.x / CS) * RM;
+  c.row0 = static_cast<int>(blockIdx.x / CS) * rm;
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < KBLK; ++i) { mbar_init(bar_at(c.a_full, i), 1); mbar_init(bar_at(c.w_full, i), 1); mbar_init(bar_at(c.w_empty, i), 1); }
     mbar_init(c.acc_full, 1);
@@ -422,19 +449,19 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Ctx c;
-  setup(c, smem, warp, lane);
+  setup(c, smem, warp, lane, p.rm);
   const int L = p.L;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) load_w<0>(c, &tmW1, 0, false, 0);
+    if (lane == 0) load_w<0>(c, &tmW1, 0, -1);
     for (int g = 0; g < 2 * L; ++g) {
       __syncwarp();
       if ((g & 1) == 0) { cluster_sync_all(); cluster_sync_all(); }     // the two LayerNorm statistics rounds
       cluster_sync_all();                                               // operand slices of GEMM g published
       if (lane == 0) {
         load_a(c, p.xchg, g);
-        if (g + 1 < 2 * L) load_w<0>(c, ((g + 1) & 1) ? &tmW2 : &tmW1, (g + 1) >> 1, true, static_cast<uint32_t>(g & 1), g & 1);
+        if (g + 1 < 2 * L) load_w<0>(c, ((g + 1) & 1) ? &tmW2 : &tmW1, (g + 1) >> 1, g & 1);
       }
     }
   } else if (warp == 1) {
@@ -452,10 +479,13 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ row owners (4 warps x 32 rows)
+    // UMMA M = 128: accumulator row r sits in TMEM lane r.  M = 64: row r sits in lane 32*(r/16) + r%16 (probed on
+    // B200, tools/probe_tmem_layout.py), i.e. the first 16 lanes of every warp own rows and the other 16 idle.
     const int q = warp & 3;
-    const int rl = q * 32 + lane;
+    const bool active = (c.rm == RM) || (lane < 16);
+    const int rl = (c.rm == RM) ? q * 32 + lane : q * 16 + (lane & 15);
     const int row = c.row0 + rl;
-    const bool valid = row < p.B;
+    const bool valid = active && row < p.B;
     const int col0 = static_cast<int>(c.rank) * NS;
     const uint32_t taddr = c.tmem + (static_cast<uint32_t>(q * 32) << 16);
     float hv[NS];
@@ -475,7 +505,7 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       SER_TL(0);
       // ---- y = LN_outer(h)
       float mu, rs;
-      row_stats(c, 0, rl, hv, mu, rs);
+      row_stats(c, 0, rl, active, hv, mu, rs);
       SER_TL(1);
       if (valid && c.rank == 0) *reinterpret_cast<float2*>(p.stats_o + (static_cast<size_t>(i) * p.B + row) * 2) = make_float2(mu, rs);
       lds_vec(par_addr(c, pb, 0), par, NS);
@@ -485,7 +515,7 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
 #pragma unroll
       for (int k = 0; k < NS; ++k) hv[k] += par[k];                    // hv now holds y (kept for the residual)
       // ---- n = LN_inner(y)
-      row_stats(c, 1, rl, hv, mu, rs);
+      row_stats(c, 1, rl, active, hv, mu, rs);
       SER_TL(2);
       if (valid && c.rank == 0) *reinterpret_cast<float2*>(p.stats_i + (static_cast<size_t>(i) * p.B + row) * 2) = make_float2(mu, rs);
       float nv[NS];
@@ -495,7 +525,7 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       lds_vec(par_addr(c, pb, 3), par, NS);
 #pragma unroll
       for (int k = 0; k < NS; ++k) nv[k] += par[k];
-      publish_slice(c, nv, rl, et, xchg_block(c, p.xchg, 2 * i), &tmN, col0, i);
+      publish_slice(c, nv, rl, active, et, xchg_block(c, p.xchg, 2 * i), &tmN, col0, i);
       tc_fence_before();
       SER_TL(3);
       cluster_sync_all();
@@ -509,7 +539,7 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       lds_vec(par_addr(c, pb, 4), par, NS);
 #pragma unroll
       for (int k = 0; k < NS; ++k) nv[k] = fmaxf(nv[k] + par[k], 0.f);
-      publish_slice(c, nv, rl, et, xchg_block(c, p.xchg, 2 * i + 1), &tmR, col0, i);
+      publish_slice(c, nv, rl, active, et, xchg_block(c, p.xchg, 2 * i + 1), &tmR, col0, i);
       tc_fence_before();
       SER_TL(6);
       cluster_sync_all();
@@ -523,7 +553,7 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       lds_vec(par_addr(c, pb, 5), par, NS);
 #pragma unroll
       for (int k = 0; k < NS; ++k) hv[k] += nv[k] + par[k];
-      store_slice_f32(c, hv, rl, et, &tmH, col0, i + 1);
+      store_slice_f32(c, hv, rl, active, et, &tmH, col0, i + 1);
       tc_fence_before();
       SER_TL(9);
     }
@@ -562,12 +592,12 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Ctx c;
-  setup(c, smem, warp, lane);
+  setup(c, smem, warp, lane, p.rm);
   const int L = p.L;
 
   // GEMM g (g = 0 .. 2L-1): even = du = dh W2 of block L-1-g/2, odd = dn = da W1 of the same block
   if (warp == 0) {
-    if (lane == 0) load_w<1>(c, &tmW2, L - 1, false, 0);
+    if (lane == 0) load_w<1>(c, &tmW2, L - 1, -1);
     for (int g = 0; g < 2 * L; ++g) {
       __syncwarp();
       cluster_sync_all();                                               // operand slices of GEMM g published
@@ -575,7 +605,7 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
         load_a(c, p.xchg, g);
         if (g + 1 < 2 * L) {
           const int nl = L - 1 - ((g + 1) >> 1);
-          load_w<1>(c, ((g + 1) & 1) ? &tmW1 : &tmW2, nl, true, static_cast<uint32_t>(g & 1), g & 1);
+          load_w<1>(c, ((g + 1) & 1) ? &tmW1 : &tmW2, nl, g & 1);
         }
       }
       __syncwarp();
@@ -590,10 +620,13 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       if (g & 1) { cluster_sync_all(); cluster_sync_all(); }
     }
   } else {
+    // UMMA M = 128: accumulator row r sits in TMEM lane r.  M = 64: row r sits in lane 32*(r/16) + r%16 (probed on
+    // B200, tools/probe_tmem_layout.py), i.e. the first 16 lanes of every warp own rows and the other 16 idle.
     const int q = warp & 3;
-    const int rl = q * 32 + lane;
+    const bool active = (c.rm == RM) || (lane < 16);
+    const int rl = (c.rm == RM) ? q * 32 + lane : q * 16 + (lane & 15);
     const int row = c.row0 + rl;
-    const bool valid = row < p.B;
+    const bool valid = active && row < p.B;
     const int col0 = static_cast<int>(c.rank) * NS;
     const uint32_t taddr = c.tmem + (static_cast<uint32_t>(q * 32) << 16);
     const size_t BP = static_cast<size_t>(p.B) * PD;
@@ -616,7 +649,7 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       par_advance(c, p, i - 1, i > 0, pb ^ 1, et, col0);
       SER_TL(16);
       // ---- publish dh_{i+1} (bf16): A operand of du = dh W2 and of the batched dW2 GEMM
-      publish_slice(c, gv, rl, et, xchg_block(c, p.xchg, 2 * (L - 1 - i)), &tmDhn, col0, i);
+      publish_slice(c, gv, rl, active, et, xchg_block(c, p.xchg, 2 * (L - 1 - i)), &tmDhn, col0, i);
       tc_fence_before();
       SER_TL(17);
       cluster_sync_all();
@@ -657,7 +690,7 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
             if ((wds[t] & 0x7fff0000u) == 0u) du[8 * k + 2 * t + 1] = 0.f;
           }
         }
-        publish_slice(c, du, rl, et, xchg_block(c, p.xchg, 2 * (L - 1 - i) + 1), &tmDr, col0, i);
+        publish_slice(c, du, rl, active, et, xchg_block(c, p.xchg, 2 * (L - 1 - i) + 1), &tmDr, col0, i);
       }
       tc_fence_before();
       SER_TL(20);
@@ -675,6 +708,10 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       for (int hh = 0; hh < 2; ++hh) {
         float dn[32], t0[32], t1[32], go[32], bo[32], gi[32];
         tmem_ld32(taddr + hh * 32, dn);
+        if (!active) {                       // idle lanes of an M = 64 tile read untouched tensor memory
+#pragma unroll
+          for (int k = 0; k < 32; ++k) dn[k] = 0.f;
+        }
         lds_vec(go_p + hh * 128, go, 32); lds_vec(bo_p + hh * 128, bo, 32); lds_vec(gi_p + hh * 128, gi, 32);
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
@@ -691,7 +728,7 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       }
       {
         float as[CS], bs[CS];
-        exchange2(c, 0, rl, s1, s2, as, bs);
+        exchange2(c, 0, rl, active, s1, s2, as, bs);
         s1 = 0.f; s2 = 0.f;
 #pragma unroll
         for (int t = 0; t < CS; ++t) { s1 += as[t]; s2 += bs[t]; }
@@ -703,6 +740,10 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       for (int hh = 0; hh < 2; ++hh) {
         float dn[32], t0[32], t1[32], go[32], bo[32], gi[32];
         tmem_ld32(taddr + hh * 32, dn);
+        if (!active) {                       // idle lanes of an M = 64 tile read untouched tensor memory
+#pragma unroll
+          for (int k = 0; k < 32; ++k) dn[k] = 0.f;
+        }
         lds_vec(go_p + hh * 128, go, 32); lds_vec(bo_p + hh * 128, bo, 32); lds_vec(gi_p + hh * 128, gi, 32);
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
@@ -723,7 +764,7 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       tc_fence_before();
       {
         float as[CS], bs[CS];
-        exchange2(c, 1, rl, u1, u2, as, bs);
+        exchange2(c, 1, rl, active, u1, u2, as, bs);
         u1 = 0.f; u2 = 0.f;
 #pragma unroll
         for (int t = 0; t < CS; ++t) { u1 += as[t]; u2 += bs[t]; }
@@ -808,9 +849,18 @@ int configure(K kern) {
 
 }  // namespace
 
+// rows per cluster: the GEMM phases are bound by shared-memory fill (the 128 x 512 operand all-gather), so small
+// batches run UMMA M = 64 clusters -- twice as many SMs pull half as much each; large batches keep M = 128
+static int rows_per_cluster(int B) {
+  static const char* force = getenv("SER_CLF_RM");
+  if (force != nullptr) return atoi(force) == 64 ? 64 : RM;
+  return (ceil_div(B, 64) * CS <= device_sm_count()) ? 64 : RM;
+}
+
 bool clf_stack_supported(int dtype, int P, int L, const ClfStackArgs& a) {
   // the exchange buffer lives in the (otherwise unused) saved-y buffer of the descriptor: [L, B, 512] fp32
-  const size_t need = static_cast<size_t>(ceil_div(a.B, RM)) * 2 * CS * A_BYTES;
+  const int rm = rows_per_cluster(a.B);
+  const size_t need = static_cast<size_t>(ceil_div(a.B, rm)) * 2 * CS * rm * 128;
   const size_t have = static_cast<size_t>(L) * a.B * PD * sizeof(float);
   return dtype == DT_BF16 && P == PD && L >= 1 && a.s_blk > 0 && a.s_lno > 0 && a.s_w1 > 0 && a.s_w2 > 0 &&
          (a.s_w1 % 8 == 0) && (a.s_w2 % 8 == 0) && a.xchg != nullptr && have >= need &&
@@ -833,6 +883,7 @@ static long long* timeline_buffer() {
 static StackParams to_params(const ClfStackArgs& a, bool backward) {
   StackParams p{};
   p.B = a.B; p.L = a.L;
+  p.rm = rows_per_cluster(a.B);
   p.b1 = a.b1; p.b2 = a.b2; p.lni_g = a.lni_g; p.lni_b = a.lni_b; p.s_blk = a.s_blk;
   p.lno_g = a.lno_g; p.lno_b = a.lno_b; p.s_lno = a.s_lno;
   p.h = a.h; p.n = reinterpret_cast<__nv_bfloat16*>(a.n); p.r = reinterpret_cast<__nv_bfloat16*>(a.r);
@@ -873,10 +924,11 @@ int clf_stack_fwd(const ClfStackArgs& a, cudaStream_t s) {
   CUtensorMap tmW1, tmW2, tmN, tmR, tmH;
   SER_TRY(make_map(&tmW1, a.w1, PD, a.s_w1, a.L, NS));
   SER_TRY(make_map(&tmW2, a.w2, PD, a.s_w2, a.L, NS));
-  SER_TRY(make_map(&tmN, a.n, a.B, static_cast<long long>(a.B) * PD, a.L, RM));
-  SER_TRY(make_map(&tmR, a.r, a.B, static_cast<long long>(a.B) * PD, a.L, RM));
-  SER_TRY(make_map(&tmH, a.h, a.B, static_cast<long long>(a.B) * PD, a.L + 1, RM, 1));
-  const int clusters = ceil_div(a.B, RM);
+  const int rm = rows_per_cluster(a.B);
+  SER_TRY(make_map(&tmN, a.n, a.B, static_cast<long long>(a.B) * PD, a.L, rm));
+  SER_TRY(make_map(&tmR, a.r, a.B, static_cast<long long>(a.B) * PD, a.L, rm));
+  SER_TRY(make_map(&tmH, a.h, a.B, static_cast<long long>(a.B) * PD, a.L + 1, rm, 1));
+  const int clusters = ceil_div(a.B, rm);
   // algorithmic work: 2 GEMMs per block; bytes: weights once per cluster + the fp32 stream and bf16 operands
   ProfScope prof("clf_stack_fwd", 4.0 * a.B * PD * PD * a.L,
                  static_cast<double>(a.L) * (2.0 * PD * PD * 2 * clusters + a.B * PD * (4.0 + 2.0 + 2.0)), s);
@@ -892,9 +944,10 @@ int clf_stack_bwd(const ClfStackArgs& a, cudaStream_t s) {
   CUtensorMap tmW1, tmW2, tmDhn, tmDr;
   SER_TRY(make_map(&tmW1, a.w1, PD, a.s_w1, a.L, 64));
   SER_TRY(make_map(&tmW2, a.w2, PD, a.s_w2, a.L, 64));
-  SER_TRY(make_map(&tmDhn, a.dhn, a.B, static_cast<long long>(a.B) * PD, a.L, RM));
-  SER_TRY(make_map(&tmDr, a.dr, a.B, static_cast<long long>(a.B) * PD, a.L, RM));
-  const int clusters = ceil_div(a.B, RM);
+  const int rm = rows_per_cluster(a.B);
+  SER_TRY(make_map(&tmDhn, a.dhn, a.B, static_cast<long long>(a.B) * PD, a.L, rm));
+  SER_TRY(make_map(&tmDr, a.dr, a.B, static_cast<long long>(a.B) * PD, a.L, rm));
+  const int clusters = ceil_div(a.B, rm);
   ProfScope prof("clf_stack_bwd", 4.0 * a.B * PD * PD * a.L,
                  static_cast<double>(a.L) * (2.0 * PD * PD * 2 * clusters + a.B * PD * (4.0 + 2.0 + 2.0 + 2.0)), s);
   clf_stack_bwd_kernel<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmDhn, tmDr, to_params(a, true));

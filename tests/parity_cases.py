@@ -268,7 +268,7 @@ def classifier_case(B=64, C=4, L=35):
         ((lg * i["ul"].to(dev)).sum() + (un * i["uu"].to(dev)).sum()).backward()
         return {"logits": lg, "unc": un, "features": m.last_features}, _param_grads("classifier", m), {"x": x.grad}
 
-    return Case("classifier", ins, w, oracle, cuda, grad_inputs=("x",))
+    return Case("classifier" if B == 64 else f"classifier_B{B}", ins, w, oracle, cuda, grad_inputs=("x",))
 
 
 def loss_case(B=37, C=6):
@@ -335,6 +335,8 @@ ALL_CASES = {
     "pool_nomask": lambda: pool_case(masks=False),
     "fusion": fusion_case,
     "classifier": classifier_case,
+    # two 128-row clusters of the fused stack kernel, the second one partially filled (rows >= B must stay inert)
+    "classifier_b200": lambda: classifier_case(B=200, C=6),
     "loss": loss_case,
     "head_cfg1": lambda: head_case(4, 50, 16, 4, True),
     "head_c6_nomask": lambda: head_case(5, 33, 9, 6, False),
