@@ -2,8 +2,8 @@
 // fusion mix (src/models/fusion.py:21-25).  These are the bandwidth-bound kernels of the head:
 // 128-bit loads, warp-shuffle / shared-memory reductions over time and feature axes, masks in-kernel.
 //
-// Pooling layout: x is [B, T, D] row-major.  The statistics kernels run one CTA per (sample, 64-column
-// slab): 8 lanes x 8 elements cover the slab width (128 B of bf16 per row), 32 row-groups walk T.
+// Pooling layout: x is [B, T, D] row-major.  The statistics kernels run one CTA per (sample, 256-column
+// slab): a warp covers the slab width (512 contiguous bytes of bf16 per row), the 8 warps walk T with 4 rows in flight.
 // The weighted variance is the reference's two-pass form  sum_t a_t (x_t - mu)^2  (pooling.py:26).
 // A sample whose frames are all padded yields NaN (softmax over all -inf), as in the reference.
 #include "kernels.cuh"
@@ -13,22 +13,35 @@ namespace ser {
 
 namespace {
 
-constexpr int SLAB = 64;      // columns per CTA
-constexpr int NTH = 256;      // threads: 8 column-lanes x 32 row-groups
-constexpr int RG = NTH / 8;   // row groups
+constexpr int NTH = 256;      // threads per CTA
+// A CTA owns one (sample, SLAB-column slab).  SLAB = 256 (the fast path, D % 256 == 0): a warp reads 512 contiguous
+// bytes of a row (32 lanes x 8 elements), the 8 warps walk the time axis with 4 rows in flight each.  SLAB = 64 keeps
+// any D % 64 == 0 working (8 lanes per row, 32 row groups).
+template <int SLAB> struct SlabCfg {
+  static constexpr int kLanes = SLAB / 8;        // lanes that share a row
+  static constexpr int kRG = NTH / kLanes;       // row groups walking T
+};
 
-// e[b,t] = u[b,t,:] . w2 + b2 ; one warp per row (Hd = 128 -> 4 elements per lane)
+// e[b,t] = u[b,t,:] . w2 + b2 ; Hd / 8 lanes per row (16 for Hd = 128 -> two rows per warp), 128-bit loads
 template <typename T>
 __global__ void __launch_bounds__(256)
 asp_score_kernel(const T* __restrict__ u, const float* __restrict__ w2, const float* __restrict__ b2,
                  float* __restrict__ e, int M, int Hd) {
+  const int lpr = Hd >> 3;                         // lanes per row (power of two <= 32)
+  const int rpw = 32 / lpr;                        // rows per warp
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
+  const int sub = lane / lpr, cl = (lane % lpr) * 8;
+  const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * rpw + sub;
   float acc = 0.f;
-  for (int c = lane; c < Hd; c += 32) acc = fmaf(to_f32(u[static_cast<size_t>(row) * Hd + c]), w2[c], acc);
-  acc = warp_sum(acc);
-  if (lane == 0) e[row] = acc + b2[0];
+  if (row < M) {
+    float v[8], w[8];
+    load8(u + static_cast<size_t>(row) * Hd + cl, v);
+    load8(w2 + cl, w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc = fmaf(v[i], w[i], acc);
+  }
+  for (int o = lpr >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (row < M && (lane % lpr) == 0) e[row] = acc + b2[0];
 }
 
 // softmax over T of the masked scores of sample b into smem `sa` (all threads participate)
@@ -54,10 +67,11 @@ __device__ __forceinline__ void softmax_row(const float* __restrict__ e, const f
   __syncthreads();
 }
 
-template <typename T>
+template <typename T, int SLAB>
 __global__ void __launch_bounds__(NTH)
 asp_stats_kernel(const T* __restrict__ x, const float* __restrict__ e, const float* __restrict__ mask,
                  float* __restrict__ alpha, void* __restrict__ out, int out_f32, int Tlen, int D) {
+  constexpr int RG = SlabCfg<SLAB>::kRG, KL = SlabCfg<SLAB>::kLanes;
   extern __shared__ float smem[];
   float* sa = smem;                      // [T]
   float* red = sa + Tlen;                // [32]
@@ -65,8 +79,8 @@ asp_stats_kernel(const T* __restrict__ x, const float* __restrict__ e, const flo
   float* smean = part + RG * SLAB;       // [SLAB]
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * SLAB;
-  const int cl = (threadIdx.x & 7) * 8;  // column offset inside the slab
-  const int rg = threadIdx.x >> 3;
+  const int cl = (threadIdx.x % KL) * 8; // column offset inside the slab
+  const int rg = threadIdx.x / KL;
   softmax_row(e + static_cast<size_t>(b) * Tlen, mask ? mask + static_cast<size_t>(b) * Tlen : nullptr, Tlen, sa, red);
   if (blockIdx.x == 0 && alpha != nullptr)
     for (int t = threadIdx.x; t < Tlen; t += blockDim.x) alpha[static_cast<size_t>(b) * Tlen + t] = sa[t];
@@ -75,7 +89,20 @@ asp_stats_kernel(const T* __restrict__ x, const float* __restrict__ e, const flo
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int t = rg; t < Tlen; t += RG) {
+  constexpr int U = 4;                    // independent row loads in flight per thread
+  int t = rg;
+  for (; t + (U - 1) * RG < Tlen; t += U * RG) {
+    float v[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) load8(xb + static_cast<size_t>(t + u * RG) * D, v[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float a = sa[t + u * RG];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, v[u][i], acc[i]);
+    }
+  }
+  for (; t < Tlen; t += RG) {
     float v[8];
     load8(xb + static_cast<size_t>(t) * D, v);
     const float a = sa[t];
@@ -85,18 +112,30 @@ asp_stats_kernel(const T* __restrict__ x, const float* __restrict__ e, const flo
 #pragma unroll
   for (int i = 0; i < 8; ++i) part[rg * SLAB + cl + i] = acc[i];
   __syncthreads();
-  if (threadIdx.x < SLAB) {
+  for (int c = threadIdx.x; c < SLAB; c += NTH) {
     float s = 0.f;
-    for (int r = 0; r < RG; ++r) s += part[r * SLAB + threadIdx.x];
-    smean[threadIdx.x] = s;
+    for (int r = 0; r < RG; ++r) s += part[r * SLAB + c];
+    smean[c] = s;
   }
   __syncthreads();
   float mu[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { mu[i] = smean[cl + i]; acc[i] = 0.f; }
-  for (int t = rg; t < Tlen; t += RG) {
+  t = rg;
+  for (; t + (U - 1) * RG < Tlen; t += U * RG) {      // second pass: the slab is L2 resident
+    float v[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) load8(xb + static_cast<size_t>(t + u * RG) * D, v[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float a = sa[t + u * RG];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[u][i] - mu[i]; acc[i] = fmaf(a * d, d, acc[i]); }
+    }
+  }
+  for (; t < Tlen; t += RG) {
     float v[8];
-    load8(xb + static_cast<size_t>(t) * D, v);       // second pass: L2-resident slab
+    load8(xb + static_cast<size_t>(t) * D, v);
     const float a = sa[t];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { const float d = v[i] - mu[i]; acc[i] = fmaf(a * d, d, acc[i]); }
@@ -104,25 +143,26 @@ asp_stats_kernel(const T* __restrict__ x, const float* __restrict__ e, const flo
 #pragma unroll
   for (int i = 0; i < 8; ++i) part[rg * SLAB + cl + i] = acc[i];
   __syncthreads();
-  if (threadIdx.x < SLAB) {
+  for (int c = threadIdx.x; c < SLAB; c += NTH) {
     float s = 0.f;
-    for (int r = 0; r < RG; ++r) s += part[r * SLAB + threadIdx.x];
-    const size_t o = static_cast<size_t>(b) * 2 * D + c0 + threadIdx.x;
-    st_dyn(out, o, out_f32, smean[threadIdx.x]);
+    for (int r = 0; r < RG; ++r) s += part[r * SLAB + c];
+    const size_t o = static_cast<size_t>(b) * 2 * D + c0 + c;
+    st_dyn(out, o, out_f32, smean[c]);
     st_dyn(out, o + D, out_f32, sqrtf(s + 1e-6f));
   }
 }
 
 // backward, part A: per (sample, slab): dx_stats and partial dalpha
-template <typename T>
+template <typename T, int SLAB>
 __global__ void __launch_bounds__(NTH)
 asp_bwd_stats_kernel(const T* __restrict__ x, const float* __restrict__ alpha, const void* __restrict__ out,
                      int out_f32, const void* __restrict__ dout, int dout_f32, T* __restrict__ dx,
                      float* __restrict__ dalpha, int Tlen, int D) {
+  constexpr int RG = SlabCfg<SLAB>::kRG, KL = SlabCfg<SLAB>::kLanes;
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * SLAB;
-  const int cl = (threadIdx.x & 7) * 8;
-  const int rg = threadIdx.x >> 3;
+  const int cl = (threadIdx.x % KL) * 8;
+  const int rg = threadIdx.x / KL;
   float mu[8], dmu[8], dvar[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -133,9 +173,8 @@ asp_bwd_stats_kernel(const T* __restrict__ x, const float* __restrict__ alpha, c
     dvar[i] = ld_dyn(dout, o + D, dout_f32) / (2.f * sd);
   }
   const size_t base = static_cast<size_t>(b) * Tlen * D + c0 + cl;
-  for (int t = rg; t < Tlen; t += RG) {
-    float v[8], g[8];
-    load8(x + base + static_cast<size_t>(t) * D, v);
+  auto one_row = [&](int t, const float (&v)[8]) {
+    float g[8];
     const float a = alpha[static_cast<size_t>(b) * Tlen + t];
     float da = 0.f;
 #pragma unroll
@@ -146,11 +185,24 @@ asp_bwd_stats_kernel(const T* __restrict__ x, const float* __restrict__ alpha, c
       da = fmaf(d * d, dvar[i], da);
     }
     store8(dx + base + static_cast<size_t>(t) * D, g);
-    // reduce over the 8 column-lanes that share this row (lanes differ in the low 3 bits)
-    da += __shfl_xor_sync(0xffffffffu, da, 1);
-    da += __shfl_xor_sync(0xffffffffu, da, 2);
-    da += __shfl_xor_sync(0xffffffffu, da, 4);
-    if ((threadIdx.x & 7) == 0) atomicAdd(dalpha + static_cast<size_t>(b) * Tlen + t, da);
+    // reduce over the KL column-lanes that share this row (consecutive lanes of one warp)
+#pragma unroll
+    for (int o = KL >> 1; o > 0; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);
+    if ((threadIdx.x % KL) == 0) atomicAdd(dalpha + static_cast<size_t>(b) * Tlen + t, da);
+  };
+  constexpr int U = 4;
+  int t = rg;
+  for (; t + (U - 1) * RG < Tlen; t += U * RG) {
+    float v[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) load8(x + base + static_cast<size_t>(t + u * RG) * D, v[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) one_row(t + u * RG, v[u]);
+  }
+  for (; t < Tlen; t += RG) {
+    float v[8];
+    load8(x + base + static_cast<size_t>(t) * D, v);
+    one_row(t, v);
   }
 }
 
@@ -184,19 +236,28 @@ asp_bwd_score_kernel(const T* __restrict__ u, const float* __restrict__ w2, cons
   dbl = block_sum(dbl, red);
   __syncthreads();
   if (threadIdx.x == 0) atomicAdd(db2, dbl);
-  // each thread owns one scorer column c and walks a strided set of rows
-  const int c = threadIdx.x % Hd;
-  const int rstep = blockDim.x / Hd;
-  float accw = 0.f;
-  const float wc = w2[c];
-  for (int t = threadIdx.x / Hd; t < Tlen; t += rstep) {
-    const size_t o = (static_cast<size_t>(b) * Tlen + t) * Hd + c;
-    const float uv = to_f32(u[o]);
+  // Hd / 8 lanes per row, 128-bit loads / stores; every lane owns 8 scorer columns and accumulates their dw2
+  const int lpr = Hd >> 3;
+  const int rows_per_pass = blockDim.x / lpr;
+  const int cl = (threadIdx.x % lpr) * 8;
+  float wv[8], accw[8];
+  load8(w2 + cl, wv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) accw[i] = 0.f;
+  for (int t = threadIdx.x / lpr; t < Tlen; t += rows_per_pass) {
+    const size_t o = (static_cast<size_t>(b) * Tlen + t) * Hd + cl;
+    float uv[8], g[8];
+    load8(u + o, uv);
     const float de = sde[t];
-    dpre[o] = from_f32<T>(de * wc * (1.f - uv * uv));
-    accw = fmaf(de, uv, accw);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      g[i] = de * wv[i] * (1.f - uv[i] * uv[i]);
+      accw[i] = fmaf(de, uv[i], accw[i]);
+    }
+    store8(dpre + o, g);
   }
-  atomicAdd(&sw[c], accw);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(&sw[cl + i], accw[i]);
   __syncthreads();
   for (int i = threadIdx.x; i < Hd; i += blockDim.x) atomicAdd(dw2 + i, sw[i]);
 }
@@ -275,15 +336,11 @@ mix_bwd_kernel(const T* __restrict__ pa, const T* __restrict__ pt, const T* __re
   if (threadIdx.x == 0) { atomicAdd(dbga, smem[2 * G]); atomicAdd(dbgt, smem[2 * G + 1]); }
 }
 
-template <typename T>
-int asp_fwd_impl(const AspArgs& a, cudaStream_t s) {
-  const int M = a.B * a.T;
-  // algorithmic bytes: x read once + u read once (SURVEY.md 8(d): single-pass minimum)
-  ProfScope prof("asp_fwd", 0.0, sizeof(T) * static_cast<double>(M) * (a.D + a.Hd), s);
-  asp_score_kernel<T><<<ceil_div(M, 8), 256, 0, s>>>(reinterpret_cast<const T*>(a.u), a.w2, a.b2, a.e, M, a.Hd);
-  SER_LAUNCH_CHECK();
+template <typename T, int SLAB>
+int asp_stats_launch(const AspArgs& a, cudaStream_t s) {
+  constexpr int RG = SlabCfg<SLAB>::kRG;
   const size_t smem = sizeof(float) * (a.T + 32 + RG * SLAB + SLAB);
-  auto kern = asp_stats_kernel<T>;
+  auto kern = asp_stats_kernel<T, SLAB>;
   if (smem > 48 * 1024) SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<dim3(a.D / SLAB, a.B), NTH, smem, s>>>(reinterpret_cast<const T*>(a.x), a.e, a.mask, a.alpha, a.out,
                                                 a.out_f32, a.T, a.D);
@@ -292,12 +349,28 @@ int asp_fwd_impl(const AspArgs& a, cudaStream_t s) {
 }
 
 template <typename T>
+int asp_fwd_impl(const AspArgs& a, cudaStream_t s) {
+  const int M = a.B * a.T;
+  // algorithmic bytes: x read once + u read once (SURVEY.md 8(d): single-pass minimum)
+  ProfScope prof("asp_fwd", 0.0, sizeof(T) * static_cast<double>(M) * (a.D + a.Hd), s);
+  const int rows_per_cta = 8 * (32 / (a.Hd >> 3));
+  asp_score_kernel<T><<<ceil_div(M, rows_per_cta), 256, 0, s>>>(reinterpret_cast<const T*>(a.u), a.w2, a.b2, a.e, M, a.Hd);
+  SER_LAUNCH_CHECK();
+  return (a.D % 256 == 0) ? asp_stats_launch<T, 256>(a, s) : asp_stats_launch<T, 64>(a, s);
+}
+
+template <typename T>
 int asp_bwd_impl(const AspArgs& a, cudaStream_t s) {
   ProfScope prof("asp_bwd", 0.0, sizeof(T) * static_cast<double>(a.B) * a.T * (2.0 * a.D + 2.0 * a.Hd), s);
   SER_CUDA_CHECK(cudaMemsetAsync(a.dalpha, 0, sizeof(float) * a.B * a.T, s));
-  asp_bwd_stats_kernel<T><<<dim3(a.D / SLAB, a.B), NTH, 0, s>>>(reinterpret_cast<const T*>(a.x), a.alpha, a.out,
-                                                                a.out_f32, a.dout, a.dout_f32,
-                                                                reinterpret_cast<T*>(a.dx), a.dalpha, a.T, a.D);
+  if (a.D % 256 == 0)
+    asp_bwd_stats_kernel<T, 256><<<dim3(a.D / 256, a.B), NTH, 0, s>>>(reinterpret_cast<const T*>(a.x), a.alpha, a.out,
+                                                                      a.out_f32, a.dout, a.dout_f32,
+                                                                      reinterpret_cast<T*>(a.dx), a.dalpha, a.T, a.D);
+  else
+    asp_bwd_stats_kernel<T, 64><<<dim3(a.D / 64, a.B), NTH, 0, s>>>(reinterpret_cast<const T*>(a.x), a.alpha, a.out,
+                                                                    a.out_f32, a.dout, a.dout_f32,
+                                                                    reinterpret_cast<T*>(a.dx), a.dalpha, a.T, a.D);
   SER_LAUNCH_CHECK();
   const size_t smem = sizeof(float) * (a.T + 32 + a.Hd);
   auto kern = asp_bwd_score_kernel<T>;
@@ -311,14 +384,14 @@ int asp_bwd_impl(const AspArgs& a, cudaStream_t s) {
 }  // namespace
 
 int asp_fwd(const AspArgs& a, cudaStream_t s) {
-  SER_REQUIRE(a.D % SLAB == 0, "asp: feature dim must be a multiple of 64");
-  SER_REQUIRE(a.Hd <= 256 && 256 % a.Hd == 0, "asp: scorer hidden dim must divide 256");
+  SER_REQUIRE(a.D % 64 == 0, "asp: feature dim must be a multiple of 64");
+  SER_REQUIRE(a.Hd >= 8 && a.Hd <= 256 && 256 % a.Hd == 0, "asp: scorer hidden dim must be a power of two in [8, 256]");
   SER_REQUIRE(a.T > 0 && a.B > 0, "asp: empty input");
   return a.dtype == DT_F32 ? asp_fwd_impl<float>(a, s) : asp_fwd_impl<__nv_bfloat16>(a, s);
 }
 int asp_bwd(const AspArgs& a, cudaStream_t s) {
-  SER_REQUIRE(a.D % SLAB == 0, "asp: feature dim must be a multiple of 64");
-  SER_REQUIRE(a.Hd <= 256 && 256 % a.Hd == 0, "asp: scorer hidden dim must divide 256");
+  SER_REQUIRE(a.D % 64 == 0, "asp: feature dim must be a multiple of 64");
+  SER_REQUIRE(a.Hd >= 8 && a.Hd <= 256 && 256 % a.Hd == 0, "asp: scorer hidden dim must be a power of two in [8, 256]");
   return a.dtype == DT_F32 ? asp_bwd_impl<float>(a, s) : asp_bwd_impl<__nv_bfloat16>(a, s);
 }
 
