@@ -124,6 +124,11 @@ typedef struct ser_xattn_desc {
   void* qkv_a; void* qkv_t; void* p_a; void* p_t; void* ctx_a; void* ctx_t;
   float* lse_a; float* lse_t; void* o_a; void* o_t; void* z_a; void* z_t; float* stats_a; float* stats_t;
   void* enh_a; void* enh_t;                /* outputs [B*Ta,D], [B*Tt,D]                          */
+  /* bf16 tier, optional (NULL = unfolded path): storage for the folded Linear chains (outer q/k/v o MHA
+   * in-projection, MHA out_proj o out_a/out_t), written by fwd and read by bwd:
+   * fold_w [2*9*S*S + 2*3*S*D + 2*D*S] act elements, fold_b [2*3*S + 2*D] fp32.  With folding on, qkv_* and
+   * o_* are not touched.                                                                             */
+  void* fold_w; float* fold_b;
   /* backward */
   const void* d_enh_a; const void* d_enh_t;
   void* da; void* dt;                      /* [M,D] act gradients w.r.t. the inputs               */

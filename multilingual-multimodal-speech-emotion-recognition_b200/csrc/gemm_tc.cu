@@ -3,7 +3,7 @@
 // One persistent CTA per SM walks output tiles of 128 x BN (BN = 128 or 256).  Warp roles:
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled shared-memory stages)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (cta_group::1, M=128, N=BN, K=16)
-//   warps 2..5  : epilogue.  Every lane owns one output row (tcgen05.ld 32x32b).  The row is finished in
+//   warps 2..9  : epilogue (two warps per TMEM lane quarter, alternating chunks).  Every lane owns one output row (tcgen05.ld 32x32b).  The row is finished in
 //                 registers -- alpha, bias, activation, gate derivative, residual -- packed, written into a
 //                 128B-swizzled staging tile (32 rows x 128 B per warp) and leaves the SM as ONE TMA store
 //                 (or TMA reduce-add for split-K / accumulate).  Residual / gate operands arrive the same way:
@@ -28,10 +28,11 @@ namespace {
 constexpr int BM = 128;       // UMMA M (one TMEM lane per output row)
 constexpr int BK = 64;        // 64 bf16 = one 128-byte swizzle atom along the contraction axis
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;          // two per TMEM lane quarter: they interleave the 128-byte chunks of a tile
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemTotal = 232448;                    // 227 KB opt-in maximum per CTA
 constexpr int kStgTile = 32 * 128;                    // one staged chunk: 32 rows x 128 B (SWIZZLE_128B)
-constexpr int kStgBytes = 4 * 4 * kStgTile;           // per epilogue warp: 2 output tiles + 2 source tiles
+constexpr int kStgBytes = kEpiWarps * 2 * kStgTile;   // per epilogue warp: one output tile + one source tile
 constexpr int kBarBytes = 256;
 constexpr int kSmemBudget = kSmemTotal - 1024 /*align*/ - kStgBytes - kBarBytes;
 
@@ -180,12 +181,12 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 // otherwise 64 bf16 columns.  SRC: residual / gate operand of the same dtype, streamed by TMA.
 // ------------------------------------------------------------------------------------------------
 struct EpiWarp {
-  uint32_t base;              // shared address of this warp's 4 staging tiles: output 0, 1, source 0, 1
-  __device__ __forceinline__ uint32_t cst(uint32_t i) const { return base + i * kStgTile; }
-  __device__ __forceinline__ uint32_t sst(uint32_t i) const { return base + (2u + i) * kStgTile; }
-  uint64_t* src_full;         // [2] mbarriers of the source tiles
-  uint32_t cbuf;              // next output tile to fill
-  uint32_t sbuf, sphase;      // next source tile to consume and the parity of its barrier
+  uint32_t base;              // shared address of this warp's two staging tiles: output, source
+  __device__ __forceinline__ uint32_t cst() const { return base; }
+  __device__ __forceinline__ uint32_t sst() const { return base + kStgTile; }
+  uint64_t* src_full;         // mbarrier of the source tile
+  uint32_t sphase;            // parity of its next completion
+  int half;                   // 0 / 1: which of the two warps of this lane quarter (takes chunks half, half+2, ...)
 };
 
 template <int BN, bool OUT_F32, int SRC>
@@ -197,25 +198,23 @@ __device__ __forceinline__ void epilogue_tile(const TcEpilogue& ep, const CUtens
   const bool with_src = (SRC != SRC_NONE) && (SRC == SRC_GATE || lead_split);
   const uint32_t swz = static_cast<uint32_t>(lane & 7);
   const uint32_t rowoff = static_cast<uint32_t>(lane) * 128u;
-  // source chunk 0 is requested before the accumulator is even complete
-  if (with_src && lane == 0) {
-    mbar_expect_tx(&w.src_full[w.sbuf], kStgTile);
-    tma_load_3d_raw(tmS, &w.src_full[w.sbuf], w.sst(w.sbuf), n0, mw, bz);
+  // Eight epilogue warps: the two warps of a lane quarter take alternating chunks, so while one waits on tensor
+  // memory, its source tile or the store engine, the other issues -- the epilogue of the K = 256 shapes was bound by
+  // the latency of a single warp per scheduler (ncu: 0.25 eligible warps, 23 % issue-slot use).
+  // The first source chunk of this warp is requested before the accumulator is even complete.
+  if (with_src && lane == 0 && w.half < NCH) {
+    mbar_expect_tx(w.src_full, kStgTile);
+    tma_load_3d_raw(tmS, w.src_full, w.sst(), n0 + w.half * CW, mw, bz);
   }
   mbar_wait(tfull, tfull_parity);
   tc_fence_after();
 #pragma unroll 1
-  for (int c = 0; c < NCH; ++c) {
+  for (int c = w.half; c < NCH; c += 2) {
     uint32_t raw[CW];
     tmem_ld32_issue(taddr0 + c * CW, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
     if (!OUT_F32) tmem_ld32_issue(taddr0 + c * CW + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[CW - 32]));
-    if (with_src && c + 1 < NCH && lane == 0) {          // prefetch the next source chunk into the other tile
-      const uint32_t nb = w.sbuf ^ 1u;
-      mbar_expect_tx(&w.src_full[nb], kStgTile);
-      tma_load_3d_raw(tmS, &w.src_full[nb], w.sst(nb), n0 + (c + 1) * CW, mw, bz);
-    }
-    // the output tile written two chunks ago must have been read by its TMA store before it is overwritten
-    if (lane == 0) tma_wait_group_read<1>();
+    // the output tile of this warp's previous chunk must have been read by its TMA store before it is overwritten
+    if (lane == 0) tma_wait_group_read<0>();
     __syncwarp();
     tmem_ld_wait();
     float v[CW];
@@ -230,9 +229,12 @@ __device__ __forceinline__ void epilogue_tile(const TcEpilogue& ep, const CUtens
         v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), alpha, b.z);
         v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), alpha, b.w);
       }
-    } else {
+    } else if (alpha != 1.f) {
 #pragma unroll
       for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(raw[j]) * alpha;
+    } else {                               // the common dgrad / wgrad case: no bias, no scale -> no arithmetic at all
+#pragma unroll
+      for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(raw[j]);
     }
     if (ep.act == ACT_RELU) {
 #pragma unroll
@@ -245,8 +247,9 @@ __device__ __forceinline__ void epilogue_tile(const TcEpilogue& ep, const CUtens
       for (int j = 0; j < CW; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
     }
     if (SRC != SRC_NONE && with_src) {
-      mbar_wait(&w.src_full[w.sbuf], w.sphase);
-      const uint32_t sbase = w.sst(w.sbuf) + rowoff;
+      mbar_wait(w.src_full, w.sphase);
+      w.sphase ^= 1u;
+      const uint32_t sbase = w.sst() + rowoff;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {                       // 8 x 16 bytes of this lane's source row
         uint32_t x0, x1, x2, x3;
@@ -263,21 +266,30 @@ __device__ __forceinline__ void epilogue_tile(const TcEpilogue& ep, const CUtens
           const uint32_t xs[4] = {x0, x1, x2, x3};
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const float lo = bf_lo(xs[t]), hi = bf_hi(xs[t]);
             if (SRC == SRC_RESIDUAL) {
-              v[8 * j + 2 * t] += lo; v[8 * j + 2 * t + 1] += hi;
+              v[8 * j + 2 * t] += bf_lo(xs[t]); v[8 * j + 2 * t + 1] += bf_hi(xs[t]);
+            } else if (ep.gate_mode == GATE_RELU) {
+              // d relu: keep where the saved activation is > 0, decided on the packed bf16 bits (sign clear and
+              // magnitude non-zero) without unpacking
+              const uint32_t w = xs[t];
+              if ((w & 0x00008000u) != 0u || (w & 0x00007fffu) == 0u) v[8 * j + 2 * t] = 0.f;
+              if ((w & 0x80000000u) != 0u || (w & 0x7fff0000u) == 0u) v[8 * j + 2 * t + 1] = 0.f;
             } else {
-              v[8 * j + 2 * t] = apply_gate(v[8 * j + 2 * t], lo, ep.gate_mode);
-              v[8 * j + 2 * t + 1] = apply_gate(v[8 * j + 2 * t + 1], hi, ep.gate_mode);
+              v[8 * j + 2 * t] = apply_gate(v[8 * j + 2 * t], bf_lo(xs[t]), ep.gate_mode);
+              v[8 * j + 2 * t + 1] = apply_gate(v[8 * j + 2 * t + 1], bf_hi(xs[t]), ep.gate_mode);
             }
           }
         }
       }
-      w.sbuf ^= 1u;
-      if (w.sbuf == 0u) w.sphase ^= 1u;
+      // source tile consumed by every lane: request this warp's next chunk into it
+      __syncwarp();
+      if (c + 2 < NCH && lane == 0) {
+        mbar_expect_tx(w.src_full, kStgTile);
+        tma_load_3d_raw(tmS, w.src_full, w.sst(), n0 + (c + 2) * CW, mw, bz);
+      }
     }
     // finished row -> swizzled staging tile -> one TMA store per warp and chunk
-    const uint32_t cbase = w.cst(w.cbuf) + rowoff;
+    const uint32_t cbase = w.cst() + rowoff;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const uint32_t dst = cbase + ((static_cast<uint32_t>(j) ^ swz) << 4);
@@ -292,11 +304,10 @@ __device__ __forceinline__ void epilogue_tile(const TcEpilogue& ep, const CUtens
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
-      if (ep.atomic) tma_reduce_add_3d(tmC, w.cst(w.cbuf), n0 + c * CW, mw, bz);
-      else tma_store_3d(tmC, w.cst(w.cbuf), n0 + c * CW, mw, bz);
+      if (ep.atomic) tma_reduce_add_3d(tmC, w.cst(), n0 + c * CW, mw, bz);
+      else tma_store_3d(tmC, w.cst(), n0 + c * CW, mw, bz);
       tma_commit_group();
     }
-    w.cbuf ^= 1u;
   }
 }
 
@@ -320,8 +331,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = bars + Cfg::kStages;         // [kStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;     // [2]
   uint64_t* tempty_bar = tfull_bar + 2;              // [2]
-  uint64_t* src_bar = tempty_bar + 2;                // [4 warps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(src_bar + 8);
+  uint64_t* src_bar = tempty_bar + 2;                // [kEpiWarps]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(src_bar + kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -335,8 +346,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
-    for (int s = 0; s < 8; ++s) mbar_init(&src_bar[s], 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps); }
+    for (int s = 0; s < kEpiWarps; ++s) mbar_init(&src_bar[s], 1);
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
     if (ep.src != SRC_NONE) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmS)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -424,15 +435,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue (4 warps)
-    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    // ---------------------------------------------------------------- epilogue (8 warps)
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access (warp id mod 4)
+    const int ew = warp - 2;                 // 0..7
     EpiWarp w;
-    {
-      const uint32_t base = smem_u32(smem_stg) + static_cast<uint32_t>(q) * (4u * kStgTile);
-      w.base = base;
-      w.src_full = src_bar + 2 * q;
-      w.cbuf = 0; w.sbuf = 0; w.sphase = 0;
-    }
+    w.base = smem_u32(smem_stg) + static_cast<uint32_t>(ew) * (2u * kStgTile);
+    w.src_full = src_bar + ew;
+    w.sphase = 0;
+    w.half = ew >> 2;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % n_tiles;

@@ -101,7 +101,187 @@ int adapter_bwd(const ser_adapter_desc& d, cudaStream_t s) {
 // =================================================================================================
 // a2 cross-modal attention
 // =================================================================================================
+
+// ------------------------------------------------------------------------------------------------
+// bf16 tier with folded Linear chains (fold.cu): per modality ONE token-level GEMM produces [Q' | K' | V'] and ONE
+// produces z = a + out(out_proj(ctx)); the 8 token-level 256->256 GEMMs of the unfolded path (and their dgrad / wgrad /
+// bias-gradient launches) become weight-sized GEMMs.  fold_w / fold_b layouts:
+//   fold_w (act dtype): Wbd_a [3S,3S] | Wbd_t | Wc_a [3S,D] | Wc_t | Wz_a [D,S] | Wz_t
+//   fold_b (fp32)     : bc_a [3S] | bc_t | bz_a [D] | bz_t
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct FoldBufs {
+  void* wbd_a; void* wbd_t; void* wc_a; void* wc_t; void* wz_a; void* wz_t;
+  float* bc_a; float* bc_t; float* bz_a; float* bz_t;
+};
+FoldBufs fold_bufs(const ser_xattn_desc& d) {
+  const long long S = d.S, D = d.D, S3 = 3 * S;
+  FoldBufs f;
+  char* w = reinterpret_cast<char*>(d.fold_w);
+  const size_t e = 2;
+  f.wbd_a = w; f.wbd_t = w + S3 * S3 * e;
+  f.wc_a = w + 2 * S3 * S3 * e; f.wc_t = w + (2 * S3 * S3 + S3 * D) * e;
+  f.wz_a = w + (2 * S3 * S3 + 2 * S3 * D) * e; f.wz_t = w + (2 * S3 * S3 + 2 * S3 * D + D * S) * e;
+  f.bc_a = d.fold_b; f.bc_t = d.fold_b + S3; f.bz_a = d.fold_b + 2 * S3; f.bz_t = d.fold_b + 2 * S3 + D;
+  return f;
+}
+// C[M,N] (c_f32 ? fp32 : bf16) = op(A) op(B)^T, plain bf16 tensor-core GEMM on weight-sized operands
+int small_gemm(int M, int N, int K, const void* A, long long lda, int a_trans, const void* B, long long ldb, int b_trans,
+               void* C, long long ldc, int c_f32, cudaStream_t s) {
+  GemmArgs g;
+  g.dtype = DT_BF16; g.M = M; g.N = N; g.K = K;
+  g.A = A; g.lda = lda; g.a_trans = a_trans;
+  g.B = B; g.ldb = ldb; g.b_trans = b_trans;
+  g.C = C; g.ldc = ldc; g.c_f32 = c_f32;
+  g.splits = 1;
+  return gemm(g, s);
+}
+bool xattn_folded(const ser_xattn_desc& d) {
+  static const bool disabled = (getenv("SER_NO_FOLD") != nullptr);     // A/B switch
+  return !disabled && d.dtype == DT_BF16 && d.fold_w != nullptr && d.fold_b != nullptr && d.D == 3 * d.S;
+}
+}  // namespace
+
+static int xattn_fwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
+  const int dt = d.dtype, f = 0;
+  const int S = d.S, D = d.D, S3 = 3 * d.S;
+  const int Ma = d.B * d.Ta, Mt = d.B * d.Tt;
+  const FoldBufs fb = fold_bufs(d);
+  // weight-only part: block-diagonal in-projections, folded weights and biases
+  SER_TRY(fold_assemble(d.win_a, d.win_t, fb.wbd_a, fb.wbd_t, S, s));
+  SER_TRY(small_gemm(S3, D, S3, fb.wbd_a, S3, 0, d.wqkv_a, D, 1, fb.wc_a, D, 0, s));     // Wc = Wbd Wqkv
+  SER_TRY(small_gemm(S3, D, S3, fb.wbd_t, S3, 0, d.wqkv_t, D, 1, fb.wc_t, D, 0, s));
+  SER_TRY(small_gemm(D, S, S, d.wout_a, S, 0, d.wo_a, S, 1, fb.wz_a, S, 0, s));           // Wz = Wout Wo
+  SER_TRY(small_gemm(D, S, S, d.wout_t, S, 0, d.wo_t, S, 1, fb.wz_t, S, 0, s));
+  FoldBiasArgs ba{};
+  ba.S = S; ba.D = D; ba.win_a = d.win_a; ba.win_t = d.win_t; ba.bin_a = d.bin_a; ba.bin_t = d.bin_t;
+  ba.bqkv_a = d.bqkv_a; ba.bqkv_t = d.bqkv_t; ba.wout_a = d.wout_a; ba.wout_t = d.wout_t; ba.bo_a = d.bo_a; ba.bo_t = d.bo_t;
+  ba.bout_a = d.bout_a; ba.bout_t = d.bout_t; ba.bc_a = fb.bc_a; ba.bc_t = fb.bc_t; ba.bz_a = fb.bz_a; ba.bz_t = fb.bz_t;
+  SER_TRY(fold_bias_fwd(ba, s));
+  // token-level part
+  SER_TRY(linear_fwd(dt, Ma, S3, D, d.a, D, fb.wc_a, D, fb.bc_a, d.p_a, S3, f, ACT_NONE, nullptr, 0, f, s));
+  SER_TRY(linear_fwd(dt, Mt, S3, D, d.t, D, fb.wc_t, D, fb.bc_t, d.p_t, S3, f, ACT_NONE, nullptr, 0, f, s));
+  AttnArgs at{};
+  at.dtype = dt; at.B = d.B; at.H = d.H; at.dh = S / d.H;
+  at.scale = 1.0f / sqrtf(static_cast<float>(at.dh));
+  at.Tq = d.Ta; at.Tk = d.Tt;
+  at.Q = d.p_a; at.ldq = S3;
+  at.K = off(d.p_t, S, dt); at.ldk = S3;
+  at.V = off(d.p_t, 2 * S, dt); at.ldv = S3;
+  at.kmask = d.t_mask; at.O = d.ctx_a; at.ldo = S; at.lse = d.lse_a;
+  SER_TRY(attention_fwd(at, s));
+  at.Tq = d.Tt; at.Tk = d.Ta;
+  at.Q = d.p_t;
+  at.K = off(d.p_a, S, dt);
+  at.V = off(d.p_a, 2 * S, dt);
+  at.kmask = d.a_mask; at.O = d.ctx_t; at.lse = d.lse_t;
+  SER_TRY(attention_fwd(at, s));
+  SER_TRY(linear_fwd(dt, Ma, D, S, d.ctx_a, S, fb.wz_a, S, fb.bz_a, d.z_a, D, f, ACT_NONE, d.a, D, f, s));
+  SER_TRY(layernorm_fwd(d.z_a, f, d.enh_a, f, nullptr, f, d.ln_a_g, d.ln_a_b, d.stats_a, Ma, D, 0, s));
+  SER_TRY(linear_fwd(dt, Mt, D, S, d.ctx_t, S, fb.wz_t, S, fb.bz_t, d.z_t, D, f, ACT_NONE, d.t, D, f, s));
+  SER_TRY(layernorm_fwd(d.z_t, f, d.enh_t, f, nullptr, f, d.ln_t_g, d.ln_t_b, d.stats_t, Mt, D, 0, s));
+  return SER_OK;
+}
+
+static size_t xattn_fold_ws_bytes(int D, int S) {
+  const size_t S3 = 3 * static_cast<size_t>(S), d = D, s = S;
+  // dbz, dbc (fp32) ; dWz32, dWz16 ; dWc32 (reused as dWbd32), dWc16   -- all x 2 modalities
+  return 2 * (pad256(d * 4) + pad256(S3 * 4) + pad256(d * s * 4) + pad256(d * s * 2) + pad256(S3 * d * 4) + pad256(S3 * d * 2)) + 4096;
+}
+
+static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
+  const int dt = d.dtype, f = 0;
+  const int S = d.S, D = d.D, S3 = 3 * d.S;
+  const int Ma = d.B * d.Ta, Mt = d.B * d.Tt;
+  const size_t e = 2;
+  const FoldBufs fb = fold_bufs(d);
+  Arena ws(d.ws, d.ws_bytes);
+  void* dz_a = ws.take(static_cast<size_t>(Ma) * D * e);
+  void* dz_t = ws.take(static_cast<size_t>(Mt) * D * e);
+  void* dctx_a = ws.take(static_cast<size_t>(Ma) * S * e);
+  void* dctx_t = ws.take(static_cast<size_t>(Mt) * S * e);
+  void* dp_a = ws.take(static_cast<size_t>(Ma) * S3 * e);
+  void* dp_t = ws.take(static_cast<size_t>(Mt) * S3 * e);
+  float* delta_a = reinterpret_cast<float*>(ws.take(static_cast<size_t>(d.B) * d.H * d.Ta * sizeof(float)));
+  float* delta_t = reinterpret_cast<float*>(ws.take(static_cast<size_t>(d.B) * d.H * d.Tt * sizeof(float)));
+  float* dbz[2]; float* dbc[2]; float* dwz32[2]; void* dwz16[2]; float* dwc32[2]; void* dwc16[2];
+  for (int m = 0; m < 2; ++m) {
+    dbz[m] = reinterpret_cast<float*>(ws.take(static_cast<size_t>(D) * 4));
+    dbc[m] = reinterpret_cast<float*>(ws.take(static_cast<size_t>(S3) * 4));
+    dwz32[m] = reinterpret_cast<float*>(ws.take(static_cast<size_t>(D) * S * 4));
+    dwz16[m] = ws.take(static_cast<size_t>(D) * S * 2);
+    dwc32[m] = reinterpret_cast<float*>(ws.take(static_cast<size_t>(S3) * D * 4));
+    dwc16[m] = ws.take(static_cast<size_t>(S3) * D * 2);
+  }
+  if (!ws.ok) { set_last_error(__FILE__, __LINE__, "xattn_bwd: workspace too small"); return SER_ERR_WORKSPACE; }
+
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_a_g, 0, sizeof(float) * D, s));
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_a_b, 0, sizeof(float) * D, s));
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_t_g, 0, sizeof(float) * D, s));
+  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_t_b, 0, sizeof(float) * D, s));
+  SER_TRY(layernorm_bwd(d.d_enh_a, f, d.z_a, f, d.stats_a, d.ln_a_g, d.ln_a_b, nullptr, f, dz_a, f, nullptr, f,
+                        d.dln_a_g, d.dln_a_b, Ma, D, 0, s));
+  SER_TRY(layernorm_bwd(d.d_enh_t, f, d.z_t, f, d.stats_t, d.ln_t_g, d.ln_t_b, nullptr, f, dz_t, f, nullptr, f,
+                        d.dln_t_g, d.dln_t_b, Mt, D, 0, s));
+  // z = ctx Wz^T + bz + residual
+  struct SideZ { int M; void* dz; const void* ctx; void* dctx; const void* wz; const void* wout; const void* wo;
+                 float* dwout; float* dwo; int m; };
+  const SideZ sz[2] = {
+      {Ma, dz_a, d.ctx_a, dctx_a, fb.wz_a, d.wout_a, d.wo_a, d.dwout_a, d.dwo_a, 0},
+      {Mt, dz_t, d.ctx_t, dctx_t, fb.wz_t, d.wout_t, d.wo_t, d.dwout_t, d.dwo_t, 1},
+  };
+  for (const SideZ& z : sz) {
+    SER_TRY(colsum(z.dz, f, D, z.M, D, dbz[z.m], s));
+    SER_TRY(linear_wgrad(dt, z.M, D, S, z.dz, D, z.ctx, S, dwz32[z.m], S, s));
+    SER_TRY(linear_dgrad(dt, z.M, D, S, z.dz, D, z.wz, S, z.dctx, S, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
+    SER_TRY(cast_any(dwz32[z.m], 1, dwz16[z.m], 0, static_cast<long long>(D) * S, s));
+    // Wz = Wout Wo :  dWout = dWz Wo^T ,  dWo = Wout^T dWz
+    SER_TRY(small_gemm(D, S, S, dwz16[z.m], S, 0, z.wo, S, 0, z.dwout, S, 1, s));
+    SER_TRY(small_gemm(S, S, D, z.wout, S, 1, dwz16[z.m], S, 1, z.dwo, S, 1, s));
+  }
+  // attention core backward
+  AttnArgs at{};
+  at.dtype = dt; at.B = d.B; at.H = d.H; at.dh = S / d.H;
+  at.scale = 1.0f / sqrtf(static_cast<float>(at.dh));
+  at.ldq = at.ldk = at.ldv = S3; at.ldo = S; at.lddo = S; at.lddq = at.lddk = at.lddv = S3;
+  at.Tq = d.Ta; at.Tk = d.Tt;
+  at.Q = d.p_a; at.K = off(d.p_t, S, dt); at.V = off(d.p_t, 2 * S, dt);
+  at.kmask = d.t_mask; at.O = d.ctx_a; at.lse = d.lse_a; at.dO = dctx_a; at.delta = delta_a;
+  at.dQ = dp_a; at.dK = off(dp_t, S, dt); at.dV = off(dp_t, 2 * S, dt);
+  SER_TRY(attention_bwd(at, s));
+  at.Tq = d.Tt; at.Tk = d.Ta;
+  at.Q = d.p_t; at.K = off(d.p_a, S, dt); at.V = off(d.p_a, 2 * S, dt);
+  at.kmask = d.a_mask; at.O = d.ctx_t; at.lse = d.lse_t; at.dO = dctx_t; at.delta = delta_t;
+  at.dQ = dp_t; at.dK = off(dp_a, S, dt); at.dV = off(dp_a, 2 * S, dt);
+  SER_TRY(attention_bwd(at, s));
+  // p = x Wc^T + bc
+  struct SideP { int M; void* dp; const void* x; void* dx; const void* dz; const void* wc; const void* wbd; const void* wqkv;
+                 float* dwqkv; int m; };
+  const SideP sp[2] = {
+      {Ma, dp_a, d.a, d.da, dz_a, fb.wc_a, fb.wbd_a, d.wqkv_a, d.dwqkv_a, 0},
+      {Mt, dp_t, d.t, d.dt, dz_t, fb.wc_t, fb.wbd_t, d.wqkv_t, d.dwqkv_t, 1},
+  };
+  for (const SideP& p : sp) {
+    SER_TRY(colsum(p.dp, f, S3, p.M, S3, dbc[p.m], s));
+    SER_TRY(linear_wgrad(dt, p.M, S3, D, p.dp, S3, p.x, D, dwc32[p.m], D, s));
+    SER_TRY(linear_dgrad(dt, p.M, S3, D, p.dp, S3, p.wc, D, p.dx, D, f, nullptr, 0, f, GATE_NONE, p.dz, D, f, s));
+    SER_TRY(cast_any(dwc32[p.m], 1, dwc16[p.m], 0, static_cast<long long>(S3) * D, s));
+    // Wc = Wbd Wqkv :  dWqkv = Wbd^T dWc (exact: off-diagonal blocks of Wbd are zero) ,  dWbd = dWc Wqkv^T
+    SER_TRY(small_gemm(S3, D, S3, p.wbd, S3, 1, dwc16[p.m], D, 1, p.dwqkv, D, 1, s));
+    SER_TRY(small_gemm(S3, S3, D, dwc16[p.m], D, 0, p.wqkv, D, 0, dwc32[p.m], S3, 1, s));      // dWbd32 reuses dWc32
+  }
+  FoldBwdArgs g{};
+  g.S = S; g.D = D; g.win_a = d.win_a; g.win_t = d.win_t; g.wout_a = d.wout_a; g.wout_t = d.wout_t;
+  g.bqkv_a = d.bqkv_a; g.bqkv_t = d.bqkv_t; g.bo_a = d.bo_a; g.bo_t = d.bo_t;
+  g.dwbd_a = dwc32[0]; g.dwbd_t = dwc32[1]; g.dbc_a = dbc[0]; g.dbc_t = dbc[1]; g.dbz_a = dbz[0]; g.dbz_t = dbz[1];
+  g.dwin_a = d.dwin_a; g.dwin_t = d.dwin_t; g.dbin_a = d.dbin_a; g.dbin_t = d.dbin_t; g.dbqkv_a = d.dbqkv_a; g.dbqkv_t = d.dbqkv_t;
+  g.dbo_a = d.dbo_a; g.dbo_t = d.dbo_t; g.dwout_a = d.dwout_a; g.dwout_t = d.dwout_t; g.dbout_a = d.dbout_a; g.dbout_t = d.dbout_t;
+  SER_TRY(fold_bwd_glue(g, s));
+  return SER_OK;
+}
+
 int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s) {
+  if (xattn_folded(d)) return xattn_fwd_folded(d, s);
   const int dt = d.dtype, f = is_f32(dt);
   const int S = d.S, D = d.D, S3 = 3 * d.S;
   const int Ma = d.B * d.Ta, Mt = d.B * d.Tt;
@@ -161,10 +341,11 @@ size_t xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H)
     tot += 2 * pad256(M * 3 * S * e);    // dp, dqkv
     tot += pad256(static_cast<size_t>(B) * H * T * sizeof(float));   // delta
   }
-  return tot + 4096;
+  return tot + 4096 + xattn_fold_ws_bytes(D, S);
 }
 
 int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
+  if (xattn_folded(d)) return xattn_bwd_folded(d, s);
   const int dt = d.dtype, f = is_f32(dt);
   const int S = d.S, D = d.D, S3 = 3 * d.S;
   const int Ma = d.B * d.Ta, Mt = d.B * d.Tt;

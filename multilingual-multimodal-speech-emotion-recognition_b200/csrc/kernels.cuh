@@ -73,6 +73,26 @@ bool clf_stack_supported(int dtype, int P, int L, const ClfStackArgs& a);
 int clf_stack_fwd(const ClfStackArgs& a, cudaStream_t s);
 int clf_stack_bwd(const ClfStackArgs& a, cudaStream_t s);
 
+// ---- fold.cu -------------------------------------------------------------------------------------
+// element-wise glue of the folded Linear chains of CrossModalAttention (bf16 tier; see fold.cu)
+int fold_assemble(const void* win_a, const void* win_t, void* wbd_a, void* wbd_t, int S, cudaStream_t s);
+struct FoldBiasArgs {
+  int S, D;
+  const void* win_a; const void* win_t; const float* bin_a; const float* bin_t; const float* bqkv_a; const float* bqkv_t;
+  const void* wout_a; const void* wout_t; const float* bo_a; const float* bo_t; const float* bout_a; const float* bout_t;
+  float* bc_a; float* bc_t; float* bz_a; float* bz_t;
+};
+int fold_bias_fwd(const FoldBiasArgs& a, cudaStream_t s);
+struct FoldBwdArgs {
+  int S, D;
+  const void* win_a; const void* win_t; const void* wout_a; const void* wout_t;
+  const float* bqkv_a; const float* bqkv_t; const float* bo_a; const float* bo_t;
+  const float* dwbd_a; const float* dwbd_t; const float* dbc_a; const float* dbc_t; const float* dbz_a; const float* dbz_t;
+  float* dwin_a; float* dwin_t; float* dbin_a; float* dbin_t; float* dbqkv_a; float* dbqkv_t;
+  float* dbo_a; float* dbo_t; float* dwout_a; float* dwout_t; float* dbout_a; float* dbout_t;
+};
+int fold_bwd_glue(const FoldBwdArgs& a, cudaStream_t s);
+
 // ---- heads.cu ------------------------------------------------------------------------------------
 // logits + uncertainty head on the fp32 penultimate features (classifier.py:192-198,224,229); u1 / unc may be NULL
 int heads_fwd(const float* f, const float* w_c, const float* b_c, const float* w_u1, const float* b_u1,

@@ -92,9 +92,16 @@ class CrossAttentionFn(torch.autograd.Function):
         Ma, Mt = B * Ta, B * Tt
         E = lambda *s: torch.empty(*s, device=dev, dtype=ty)           # noqa: E731
         F = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
-        sv = dict(qkv_a=E(Ma, 3 * S), qkv_t=E(Mt, 3 * S), p_a=E(Ma, 3 * S), p_t=E(Mt, 3 * S), ctx_a=E(Ma, S),
-                  ctx_t=E(Mt, S), lse_a=F(B, num_heads, Ta), lse_t=F(B, num_heads, Tt), o_a=E(Ma, S), o_t=E(Mt, S),
+        # bf16 tier: consecutive Linear layers are folded (csrc/fold.cu) -- the library then never touches the
+        # outer-projection outputs qkv_* nor the out_proj outputs o_*, and keeps the folded weights in fold_w / fold_b
+        folded = (ty == torch.bfloat16) and (D == 3 * S)
+        tok = (lambda M, n: E(1, 8)) if folded else (lambda M, n: E(M, n))
+        sv = dict(qkv_a=tok(Ma, 3 * S), qkv_t=tok(Mt, 3 * S), p_a=E(Ma, 3 * S), p_t=E(Mt, 3 * S), ctx_a=E(Ma, S),
+                  ctx_t=E(Mt, S), lse_a=F(B, num_heads, Ta), lse_t=F(B, num_heads, Tt), o_a=tok(Ma, S), o_t=tok(Mt, S),
                   z_a=E(Ma, D), z_t=E(Mt, D), stats_a=F(Ma, 2), stats_t=F(Mt, 2))
+        if folded:
+            sv["fold_w"] = E(2 * 9 * S * S + 2 * 3 * S * D + 2 * D * S)
+            sv["fold_b"] = F(2 * 3 * S + 2 * D)
         enh_a, enh_t = E(Ma, D), E(Mt, D)
         w = CrossAttentionFn._weights(fp, wc)
         keep = []

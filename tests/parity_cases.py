@@ -339,6 +339,8 @@ ALL_CASES = {
     "classifier_b200": lambda: classifier_case(B=200, C=6),
     "loss": loss_case,
     "head_cfg1": lambda: head_case(4, 50, 16, 4, True),
-    "head_c6_nomask": lambda: head_case(5, 33, 9, 6, False),
+    # (B = 24: with a handful of samples the reference arithmetic itself is 20-25 % away from the exact gradients --
+    #  ReLU / argmax flips are O(1/B) -- and the comparison degenerates into noise against noise)
+    "head_c6_nomask": lambda: head_case(24, 33, 9, 6, False),
     "head_b48": lambda: head_case(48, 60, 20, 4, True),
 }
