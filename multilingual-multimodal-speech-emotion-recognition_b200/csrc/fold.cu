@@ -83,33 +83,44 @@ __global__ void fold_in_bwd_rows_kernel(const float* __restrict__ dwbd_a, const 
   if (threadIdx.x == 0) (use_a ? dbin_a : dbin_t)[r] = g;
 }
 
-// column-wise mat-vecs of the folds' bias paths.  grid = (ceil((3S + S) / 256), 2); thread per output column:
+// column-wise mat-vecs of the folds' bias paths.  block = (32 columns, 8 row groups), grid = (ceil(4S / 32), 2):
 //   dbqkv_mod[bS + s] = sum_{r in block b} Win_sel[r, s] * dbc[mod][r]          (3S outputs)
 //   dbo_mod[s]        = sum_r wout_mod[r, s] * dbz[mod][r]                       (S outputs)
-__global__ void fold_bias_bwd_cols_kernel(const bf16* __restrict__ win_a, const bf16* __restrict__ win_t,
-                                          const bf16* __restrict__ wout_a, const bf16* __restrict__ wout_t,
-                                          const float* __restrict__ dbc_a, const float* __restrict__ dbc_t,
-                                          const float* __restrict__ dbz_a, const float* __restrict__ dbz_t,
-                                          float* __restrict__ dbqkv_a, float* __restrict__ dbqkv_t,
-                                          float* __restrict__ dbo_a, float* __restrict__ dbo_t, int S, int D) {
+__global__ void __launch_bounds__(256)
+fold_bias_bwd_cols_kernel(const bf16* __restrict__ win_a, const bf16* __restrict__ win_t,
+                          const bf16* __restrict__ wout_a, const bf16* __restrict__ wout_t,
+                          const float* __restrict__ dbc_a, const float* __restrict__ dbc_t,
+                          const float* __restrict__ dbz_a, const float* __restrict__ dbz_t,
+                          float* __restrict__ dbqkv_a, float* __restrict__ dbqkv_t,
+                          float* __restrict__ dbo_a, float* __restrict__ dbo_t, int S, int D) {
+  __shared__ float red[8][33];
   const int S3 = 3 * S;
   const int mod = blockIdx.y;
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  float* dst = nullptr;
   if (o < S3) {
     const int b = o / S, s = o % S;
     const bool use_a = ((b == 0) == (mod == 0));
     const bf16* w = (use_a ? win_a : win_t) + static_cast<size_t>(b) * S * S + s;      // rows bS .. bS+S-1, column s
     const float* g = (mod == 0 ? dbc_a : dbc_t) + b * S;
-    float acc = 0.f;
-    for (int r = 0; r < S; ++r) acc = fmaf(__bfloat162float(w[static_cast<size_t>(r) * S]), g[r], acc);
-    (mod == 0 ? dbqkv_a : dbqkv_t)[o] = acc;
+    for (int r = ty; r < S; r += 8) acc = fmaf(__bfloat162float(w[static_cast<size_t>(r) * S]), g[r], acc);
+    dst = (mod == 0 ? dbqkv_a : dbqkv_t) + o;
   } else if (o < S3 + S) {
     const int s = o - S3;
     const bf16* w = (mod == 0 ? wout_a : wout_t) + s;
     const float* g = (mod == 0 ? dbz_a : dbz_t);
-    float acc = 0.f;
-    for (int r = 0; r < D; ++r) acc = fmaf(__bfloat162float(w[static_cast<size_t>(r) * S]), g[r], acc);
-    (mod == 0 ? dbo_a : dbo_t)[s] = acc;
+    for (int r = ty; r < D; r += 8) acc = fmaf(__bfloat162float(w[static_cast<size_t>(r) * S]), g[r], acc);
+    dst = (mod == 0 ? dbo_a : dbo_t) + s;
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && dst != nullptr) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][tx];
+    *dst = t;
   }
 }
 
@@ -152,7 +163,7 @@ int fold_bwd_glue(const FoldBwdArgs& a, cudaStream_t s) {
   fold_in_bwd_rows_kernel<<<dim3(3 * a.S, 2), 256, 0, s>>>(a.dwbd_a, a.dwbd_t, a.dbc_a, a.dbc_t, a.bqkv_a, a.bqkv_t, a.dwin_a,
                                                            a.dwin_t, a.dbin_a, a.dbin_t, a.S);
   SER_LAUNCH_CHECK();
-  fold_bias_bwd_cols_kernel<<<dim3(ceil_div(4 * a.S, 256), 2), 256, 0, s>>>(
+  fold_bias_bwd_cols_kernel<<<dim3(ceil_div(4 * a.S, 32), 2), 256, 0, s>>>(
       reinterpret_cast<const bf16*>(a.win_a), reinterpret_cast<const bf16*>(a.win_t), reinterpret_cast<const bf16*>(a.wout_a),
       reinterpret_cast<const bf16*>(a.wout_t), a.dbc_a, a.dbc_t, a.dbz_a, a.dbz_t, a.dbqkv_a, a.dbqkv_t, a.dbo_a, a.dbo_t,
       a.S, a.D);

@@ -136,6 +136,26 @@ int small_gemm(int M, int N, int K, const void* A, long long lda, int a_trans, c
   g.splits = 1;
   return gemm(g, s);
 }
+// the same weight-sized GEMM for both modalities: one batched launch when every operand's audio -> text distance is a
+// positive multiple of 8 elements (it is: parameters, gradients and scratch are laid out symmetrically), else two
+int small_gemm2(int M, int N, int K, const void* A0, const void* A1, long long lda, int a_trans, const void* B0,
+                const void* B1, long long ldb, int b_trans, void* C0, void* C1, long long ldc, int c_f32, cudaStream_t s) {
+  auto dist = [](const void* p1, const void* p0, long long es) {
+    const long long bytes = reinterpret_cast<const char*>(p1) - reinterpret_cast<const char*>(p0);
+    return (bytes > 0 && bytes % (8 * es) == 0) ? bytes / es : -1;
+  };
+  const long long sa = dist(A1, A0, 2), sb = dist(B1, B0, 2), sc = dist(C1, C0, c_f32 ? 4 : 2);
+  if (sa > 0 && sb > 0 && sc > 0) {
+    GemmArgs g;
+    g.dtype = DT_BF16; g.M = M; g.N = N; g.K = K;
+    g.A = A0; g.lda = lda; g.a_trans = a_trans; g.B = B0; g.ldb = ldb; g.b_trans = b_trans;
+    g.C = C0; g.ldc = ldc; g.c_f32 = c_f32; g.splits = 1;
+    g.batch = 2; g.strideA = sa; g.strideB = sb; g.strideC = sc;
+    return gemm(g, s);
+  }
+  SER_TRY(small_gemm(M, N, K, A0, lda, a_trans, B0, ldb, b_trans, C0, ldc, c_f32, s));
+  return small_gemm(M, N, K, A1, lda, a_trans, B1, ldb, b_trans, C1, ldc, c_f32, s);
+}
 bool xattn_folded(const ser_xattn_desc& d) {
   static const bool disabled = (getenv("SER_NO_FOLD") != nullptr);     // A/B switch
   return !disabled && d.dtype == DT_BF16 && d.fold_w != nullptr && d.fold_b != nullptr && d.D == 3 * d.S;
@@ -149,10 +169,8 @@ static int xattn_fwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
   const FoldBufs fb = fold_bufs(d);
   // weight-only part: block-diagonal in-projections, folded weights and biases
   SER_TRY(fold_assemble(d.win_a, d.win_t, fb.wbd_a, fb.wbd_t, S, s));
-  SER_TRY(small_gemm(S3, D, S3, fb.wbd_a, S3, 0, d.wqkv_a, D, 1, fb.wc_a, D, 0, s));     // Wc = Wbd Wqkv
-  SER_TRY(small_gemm(S3, D, S3, fb.wbd_t, S3, 0, d.wqkv_t, D, 1, fb.wc_t, D, 0, s));
-  SER_TRY(small_gemm(D, S, S, d.wout_a, S, 0, d.wo_a, S, 1, fb.wz_a, S, 0, s));           // Wz = Wout Wo
-  SER_TRY(small_gemm(D, S, S, d.wout_t, S, 0, d.wo_t, S, 1, fb.wz_t, S, 0, s));
+  SER_TRY(small_gemm2(S3, D, S3, fb.wbd_a, fb.wbd_t, S3, 0, d.wqkv_a, d.wqkv_t, D, 1, fb.wc_a, fb.wc_t, D, 0, s));   // Wc = Wbd Wqkv
+  SER_TRY(small_gemm2(D, S, S, d.wout_a, d.wout_t, S, 0, d.wo_a, d.wo_t, S, 1, fb.wz_a, fb.wz_t, S, 0, s));           // Wz = Wout Wo
   FoldBiasArgs ba{};
   ba.S = S; ba.D = D; ba.win_a = d.win_a; ba.win_t = d.win_t; ba.bin_a = d.bin_a; ba.bin_t = d.bin_t;
   ba.bqkv_a = d.bqkv_a; ba.bqkv_t = d.bqkv_t; ba.wout_a = d.wout_a; ba.wout_t = d.wout_t; ba.bo_a = d.bo_a; ba.bo_t = d.bo_t;
@@ -186,7 +204,8 @@ static int xattn_fwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
 static size_t xattn_fold_ws_bytes(int D, int S) {
   const size_t S3 = 3 * static_cast<size_t>(S), d = D, s = S;
   // dbz, dbc (fp32) ; dWz32, dWz16 ; dWc32 (reused as dWbd32), dWc16   -- all x 2 modalities
-  return 2 * (pad256(d * 4) + pad256(S3 * 4) + pad256(d * s * 4) + pad256(d * s * 2) + pad256(S3 * d * 4) + pad256(S3 * d * 2)) + 4096;
+  return pad256(2 * d * 4) + pad256(2 * S3 * 4) + pad256(2 * d * s * 4) + pad256(2 * d * s * 2) + pad256(2 * S3 * d * 4) +
+         pad256(2 * S3 * d * 2) + 4096;
 }
 
 static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
@@ -204,14 +223,21 @@ static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
   void* dp_t = ws.take(static_cast<size_t>(Mt) * S3 * e);
   float* delta_a = reinterpret_cast<float*>(ws.take(static_cast<size_t>(d.B) * d.H * d.Ta * sizeof(float)));
   float* delta_t = reinterpret_cast<float*>(ws.take(static_cast<size_t>(d.B) * d.H * d.Tt * sizeof(float)));
+  // weight-sized scratch, [audio | text] contiguous per kind so one cast / one batched GEMM serves both modalities
   float* dbz[2]; float* dbc[2]; float* dwz32[2]; void* dwz16[2]; float* dwc32[2]; void* dwc16[2];
-  for (int m = 0; m < 2; ++m) {
-    dbz[m] = reinterpret_cast<float*>(ws.take(static_cast<size_t>(D) * 4));
-    dbc[m] = reinterpret_cast<float*>(ws.take(static_cast<size_t>(S3) * 4));
-    dwz32[m] = reinterpret_cast<float*>(ws.take(static_cast<size_t>(D) * S * 4));
-    dwz16[m] = ws.take(static_cast<size_t>(D) * S * 2);
-    dwc32[m] = reinterpret_cast<float*>(ws.take(static_cast<size_t>(S3) * D * 4));
-    dwc16[m] = ws.take(static_cast<size_t>(S3) * D * 2);
+  {
+    const size_t nz = static_cast<size_t>(D) * S, nc = static_cast<size_t>(S3) * D;
+    float* pbz = reinterpret_cast<float*>(ws.take(2 * static_cast<size_t>(D) * 4));
+    float* pbc = reinterpret_cast<float*>(ws.take(2 * static_cast<size_t>(S3) * 4));
+    float* pz32 = reinterpret_cast<float*>(ws.take(2 * nz * 4));
+    char* pz16 = reinterpret_cast<char*>(ws.take(2 * nz * 2));
+    float* pc32 = reinterpret_cast<float*>(ws.take(2 * nc * 4));
+    char* pc16 = reinterpret_cast<char*>(ws.take(2 * nc * 2));
+    for (int m = 0; m < 2 && ws.ok; ++m) {
+      dbz[m] = pbz + m * D; dbc[m] = pbc + m * S3;
+      dwz32[m] = pz32 + m * nz; dwz16[m] = pz16 + m * nz * 2;
+      dwc32[m] = pc32 + m * nc; dwc16[m] = pc16 + m * nc * 2;
+    }
   }
   if (!ws.ok) { set_last_error(__FILE__, __LINE__, "xattn_bwd: workspace too small"); return SER_ERR_WORKSPACE; }
 
@@ -234,11 +260,11 @@ static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
     SER_TRY(colsum(z.dz, f, D, z.M, D, dbz[z.m], s));
     SER_TRY(linear_wgrad(dt, z.M, D, S, z.dz, D, z.ctx, S, dwz32[z.m], S, s));
     SER_TRY(linear_dgrad(dt, z.M, D, S, z.dz, D, z.wz, S, z.dctx, S, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
-    SER_TRY(cast_any(dwz32[z.m], 1, dwz16[z.m], 0, static_cast<long long>(D) * S, s));
-    // Wz = Wout Wo :  dWout = dWz Wo^T ,  dWo = Wout^T dWz
-    SER_TRY(small_gemm(D, S, S, dwz16[z.m], S, 0, z.wo, S, 0, z.dwout, S, 1, s));
-    SER_TRY(small_gemm(S, S, D, z.wout, S, 1, dwz16[z.m], S, 1, z.dwo, S, 1, s));
   }
+  SER_TRY(cast_any(dwz32[0], 1, dwz16[0], 0, 2LL * D * S, s));
+  // Wz = Wout Wo :  dWout = dWz Wo^T ,  dWo = Wout^T dWz
+  SER_TRY(small_gemm2(D, S, S, dwz16[0], dwz16[1], S, 0, d.wo_a, d.wo_t, S, 0, d.dwout_a, d.dwout_t, S, 1, s));
+  SER_TRY(small_gemm2(S, S, D, d.wout_a, d.wout_t, S, 1, dwz16[0], dwz16[1], S, 1, d.dwo_a, d.dwo_t, S, 1, s));
   // attention core backward
   AttnArgs at{};
   at.dtype = dt; at.B = d.B; at.H = d.H; at.dh = S / d.H;
@@ -265,11 +291,11 @@ static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
     SER_TRY(colsum(p.dp, f, S3, p.M, S3, dbc[p.m], s));
     SER_TRY(linear_wgrad(dt, p.M, S3, D, p.dp, S3, p.x, D, dwc32[p.m], D, s));
     SER_TRY(linear_dgrad(dt, p.M, S3, D, p.dp, S3, p.wc, D, p.dx, D, f, nullptr, 0, f, GATE_NONE, p.dz, D, f, s));
-    SER_TRY(cast_any(dwc32[p.m], 1, dwc16[p.m], 0, static_cast<long long>(S3) * D, s));
-    // Wc = Wbd Wqkv :  dWqkv = Wbd^T dWc (exact: off-diagonal blocks of Wbd are zero) ,  dWbd = dWc Wqkv^T
-    SER_TRY(small_gemm(S3, D, S3, p.wbd, S3, 1, dwc16[p.m], D, 1, p.dwqkv, D, 1, s));
-    SER_TRY(small_gemm(S3, S3, D, dwc16[p.m], D, 0, p.wqkv, D, 0, dwc32[p.m], S3, 1, s));      // dWbd32 reuses dWc32
   }
+  SER_TRY(cast_any(dwc32[0], 1, dwc16[0], 0, 2LL * S3 * D, s));
+  // Wc = Wbd Wqkv :  dWqkv = Wbd^T dWc (exact: off-diagonal blocks of Wbd are zero) ,  dWbd = dWc Wqkv^T
+  SER_TRY(small_gemm2(S3, D, S3, fb.wbd_a, fb.wbd_t, S3, 1, dwc16[0], dwc16[1], D, 1, d.dwqkv_a, d.dwqkv_t, D, 1, s));
+  SER_TRY(small_gemm2(S3, S3, D, dwc16[0], dwc16[1], D, 0, d.wqkv_a, d.wqkv_t, D, 0, dwc32[0], dwc32[1], S3, 1, s));   // dWbd32 reuses dWc32
   FoldBwdArgs g{};
   g.S = S; g.D = D; g.win_a = d.win_a; g.win_t = d.win_t; g.wout_a = d.wout_a; g.wout_t = d.wout_t;
   g.bqkv_a = d.bqkv_a; g.bqkv_t = d.bqkv_t; g.bo_a = d.bo_a; g.bo_t = d.bo_t;
