@@ -572,7 +572,9 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   SER_REQUIRE(a.R == nullptr || a.ldr % 8 == 0, "gemm_tc: ldr must be a multiple of 8");
   int BN = (a.N % 256 == 0) ? 256 : 128;
   // small problems: narrower tiles put twice as many SMs to work and halve each CTA's serial epilogue
-  if (BN == 256 && 2LL * ceil_div(a.M, BM) * (a.N / 256) * (a.batch > 1 ? a.batch : 1) <= device_sm_count()) BN = 128;
+  // (long contractions are split along K instead and keep the wider, shared-memory-friendlier tile)
+  if (BN == 256 && ceil_div(a.K, BK) < 64 &&
+      2LL * ceil_div(a.M, BM) * (a.N / 256) * (a.batch > 1 ? a.batch : 1) <= device_sm_count()) BN = 128;
 
   const int m_tiles = ceil_div(a.M, BM), n_tiles = a.N / BN, kblocks = ceil_div(a.K, BK);
   int splits = a.splits;

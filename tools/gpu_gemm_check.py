@@ -82,7 +82,7 @@ for ta in (False, True):
     for tb in (False, True):
         run_case("simt plain", f32, 300, 192, 100, ta, tb)
 run_case("simt bias+relu+res", f32, 257, 130, 77, bias=True, act=L.ACT_RELU, residual=f32)
-run_case("simt tanh", f32, 129, 128, 768, bias=True, act=L.ACT_TANH)
+run_case("simt tanh", f32, 129, 128, 768, bias=True, act=L.ACT_TANH, tol=1e-4)   # tanhf vs torch.tanh: a few ulp
 run_case("simt gate relu", f32, 200, 256, 96, gate_mode=L.GATE_RELU)
 run_case("simt gate tanh", f32, 200, 128, 96, gate_mode=L.GATE_TANH)
 run_case("simt dW splitK", f32, 256, 768, 20000, True, True, tol=1e-4)
