@@ -85,6 +85,27 @@ int ser_layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, cons
                       void* stream);            /* dgamma / dbeta are overwritten */
 int ser_colsum(const void* X, int x_f32, long long ld, int M, int N, float* out, void* stream);
 
+/* ---- dropout ------------------------------------------------------------------------------------
+ * Every nn.Dropout of the path (cross_attention.py:18,25,43,51; fusion.py:9,12; classifier.py:83,85,109,127,195) is
+ * applied inside the kernels from a counter-based mask: a pure function of (*drop_seed, site, row, col), see
+ * csrc/dropout.cuh.  A module descriptor switches it on with p_drop > 0 and a non-NULL drop_seed (DEVICE pointer to
+ * one uint64; forward and backward of the same step must see the same value).  The random stream is not torch's
+ * Philox stream; keep probability and the 1/(1-p) scaling are torch.nn.functional.dropout's.
+ * ser_dropout_mask writes the multipliers (0 or 1/(1-p)) the kernels apply at `site` for a [rows, cols] tensor:
+ * the parity tests hand them to the CPU oracle.  Sites: attention weights [B*H*Tq, Tk]; everything else [rows, dim]. */
+#define SER_DS_XA_PROB_A 1   /* attn_a weights, rows = (b*H + h)*Ta + i, cols = Tt */
+#define SER_DS_XA_PROB_T 2
+#define SER_DS_XA_RES_A 3    /* self.dropout(a_out) [B*Ta, D] */
+#define SER_DS_XA_RES_T 4
+#define SER_DS_FUS_A 5       /* proj_a[2] [B, P] */
+#define SER_DS_FUS_T 6
+#define SER_DS_CLF_IN 7      /* input_projection[3] [B, P] */
+#define SER_DS_CLF_OUT 8     /* output_projection[3] [B, F] */
+#define SER_DS_CLF_UNC 9     /* uncertainty_head[2] [B, U] */
+#define SER_DS_CLF_BLOCK0 16 /* residual block l: 16 + 2l = block[3] (after ReLU), 16 + 2l + 1 = block[5] */
+int ser_dropout_mask(const unsigned long long* seed, int site, float p, long long rows, int cols, float* out,
+                     void* stream);
+
 /* ---- a1: bottleneck adapter  (src/models/audio_encoder.py:19-21,112; text_encoder.py:17-19,57) --
  * y = x + W2 relu(W1 x + b1) + b2.   "act" = tensor of the tier's dtype; weights w* are act-dtype
  * copies of the nn.Linear weights ([out,in] row-major); biases and all gradients are fp32.         */
@@ -129,6 +150,7 @@ typedef struct ser_xattn_desc {
    * fold_w [2*9*S*S + 2*3*S*D + 2*D*S] act elements, fold_b [2*3*S + 2*D] fp32.  With folding on, qkv_* and
    * o_* are not touched.                                                                             */
   void* fold_w; float* fold_b;
+  float p_drop; const unsigned long long* drop_seed;   /* attention-weight + residual dropout; 0 / NULL = off */
   /* backward */
   const void* d_enh_a; const void* d_enh_t;
   void* da; void* dt;                      /* [M,D] act gradients w.r.t. the inputs               */
@@ -172,6 +194,7 @@ typedef struct ser_fusion_desc {
   void* ha; void* ht; void* pa; void* pt; void* ga; void* gt;   /* saved: [B,P],[B,P],[B,G] act   */
   float* gates;                            /* [B,2] sigmoid gate values, saved                    */
   void* fused;                             /* [B,P] act, output                                   */
+  float p_drop; const unsigned long long* drop_seed;   /* proj_a[2] / proj_t[2]; 0 / NULL = off; ha / ht are saved post-dropout */
   /* backward */
   const void* dfused;                      /* [B,P] act                                           */
   void* dav; void* dtv;                    /* [B,Din] act                                         */
@@ -208,6 +231,7 @@ typedef struct ser_clf_desc {
   float* f;                                /* [B,F] penultimate features (fp32), output           */
   float* u1;                               /* [B,U]                                               */
   float* logits; float* unc;               /* [B,C], [B,1] outputs; unc may be NULL               */
+  float p_drop; const unsigned long long* drop_seed;   /* all classifier dropouts; 0 / NULL = off; h[0], r, f, u1 are saved post-dropout */
   /* backward */
   const float* dlogits; const float* dunc; /* [B,C]; [B,1] or NULL                                */
   void* dx;                                /* [B,P] act                                           */

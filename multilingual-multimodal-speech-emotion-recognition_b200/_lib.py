@@ -119,6 +119,7 @@ def load():
     lib.ser_eval_post.argtypes = [P, I, I, I, F, P, P, P, P, P]
     lib.ser_temperature_sweep.argtypes = [P, P, I, I, P, I, P, P]
     lib.ser_desc_size.argtypes = [I]
+    lib.ser_dropout_mask.argtypes = [P, I, F, LL, I, P, P]
     lib.ser_launch_count.restype = C.c_longlong
     lib.ser_prof_enable.argtypes = [I]
     lib.ser_prof_report.argtypes = [C.c_char_p, I]

@@ -83,6 +83,11 @@ int ser_colsum(const void* X, int x_f32, long long ld, int M, int N, float* out,
   return ser::colsum(X, x_f32, ld, M, N, out, SER_STREAM(stream));
 }
 
+int ser_dropout_mask(const unsigned long long* seed, int site, float p, long long rows, int cols, float* out,
+                     void* stream) {
+  return ser::dropout_mask(ser::make_drop(seed, p, static_cast<unsigned>(site)), rows, cols, out, SER_STREAM(stream));
+}
+
 int ser_adapter_fwd(const ser_adapter_desc* d, void* stream) { SER_NOT_NULL(d); return ser::adapter_fwd(*d, SER_STREAM(stream)); }
 int ser_adapter_bwd(const ser_adapter_desc* d, void* stream) { SER_NOT_NULL(d); return ser::adapter_bwd(*d, SER_STREAM(stream)); }
 

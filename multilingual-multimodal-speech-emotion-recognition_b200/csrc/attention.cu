@@ -59,13 +59,16 @@ template <typename T>
 __global__ void __launch_bounds__(NT)
 attn_fwd_kernel(const T* __restrict__ Q, long long ldq, const T* __restrict__ K, long long ldk,
                 const T* __restrict__ V, long long ldv, const float* __restrict__ kmask, T* __restrict__ O,
-                long long ldo, float* __restrict__ lse, int H, int Tq, int Tk, float scale) {
+                long long ldo, float* __restrict__ lse, int H, int Tq, int Tk, float scale, DropSpec drop) {
   __shared__ float sK[KT][DH];
   __shared__ float sV[KT][DH];
   __shared__ float sMask[KT];
   const int b = blockIdx.z, h = blockIdx.y;
   const int qi = blockIdx.x * NT + threadIdx.x;
   const bool active = qi < Tq;
+  DropKey dkey{0u, 1u};
+  if (drop.on()) dkey = drop_key(drop);
+  const unsigned drow = ((static_cast<unsigned>(b) * H + h) * Tq + qi) * static_cast<unsigned>((Tk + 1) / 2);
 
   float q[DH], acc[DH];
 #pragma unroll
@@ -109,9 +112,10 @@ attn_fwd_kernel(const T* __restrict__ Q, long long ldq, const T* __restrict__ K,
       for (int d = 0; d < DH; ++d) acc[d] *= corr;
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
-        const float p = __expf(s[jj] - m_new);       // masked -> exp(-inf) = 0
-        l += p;
+        float p = __expf(s[jj] - m_new);             // masked -> exp(-inf) = 0
+        l += p;                                      // the softmax normaliser sees every key; dropout acts on the weights
         const int j = j0 + jj;
+        if (drop.on()) p *= drop_one(dkey, drow + ((k0 + j) >> 1), (k0 + j) & 1, drop.thr, drop.scale);
 #pragma unroll
         for (int d = 0; d < DH; d += 4) {
           const float4 vv = *reinterpret_cast<const float4*>(&sV[j][d]);
@@ -138,13 +142,16 @@ attn_bwd_dq_kernel(const T* __restrict__ Q, long long ldq, const T* __restrict__
                    const T* __restrict__ V, long long ldv, const float* __restrict__ kmask,
                    const T* __restrict__ O, long long ldo, const T* __restrict__ dO, long long lddo,
                    const float* __restrict__ lse, float* __restrict__ delta, T* __restrict__ dQ, long long lddq,
-                   int H, int Tq, int Tk, float scale) {
+                   int H, int Tq, int Tk, float scale, DropSpec drop) {
   __shared__ float sK[KT][DH];
   __shared__ float sV[KT][DH];
   __shared__ float sMask[KT];
   const int b = blockIdx.z, h = blockIdx.y;
   const int qi = blockIdx.x * NT + threadIdx.x;
   const bool active = qi < Tq;
+  DropKey dkey{0u, 1u};
+  if (drop.on()) dkey = drop_key(drop);
+  const unsigned drow = ((static_cast<unsigned>(b) * H + h) * Tq + qi) * static_cast<unsigned>((Tk + 1) / 2);
   float q[DH], go[DH], dq[DH];
 #pragma unroll
   for (int d = 0; d < DH; ++d) { q[d] = 0.f; go[d] = 0.f; dq[d] = 0.f; }
@@ -180,6 +187,7 @@ attn_bwd_dq_kernel(const T* __restrict__ Q, long long ldq, const T* __restrict__
         dp = fmaf(go[d + 2], vv.z, dp); dp = fmaf(go[d + 3], vv.w, dp);
       }
       const float p = __expf(dot - row_lse);
+      if (drop.on()) dp *= drop_one(dkey, drow + ((k0 + j) >> 1), (k0 + j) & 1, drop.thr, drop.scale);
       const float ds = p * (dp - dl);
 #pragma unroll
       for (int d = 0; d < DH; d += 4) {
@@ -203,7 +211,7 @@ attn_bwd_dkv_kernel(const T* __restrict__ Q, long long ldq, const T* __restrict_
                     const T* __restrict__ V, long long ldv, const float* __restrict__ kmask,
                     const T* __restrict__ dO, long long lddo, const float* __restrict__ lse,
                     const float* __restrict__ delta, T* __restrict__ dK, long long lddk, T* __restrict__ dV,
-                    long long lddv, int H, int Tq, int Tk, float scale) {
+                    long long lddv, int H, int Tq, int Tk, float scale, DropSpec drop) {
   __shared__ float sQ[KT][DH];
   __shared__ float sG[KT][DH];
   __shared__ float sLse[KT];
@@ -211,6 +219,9 @@ attn_bwd_dkv_kernel(const T* __restrict__ Q, long long ldq, const T* __restrict_
   const int b = blockIdx.z, h = blockIdx.y;
   const int kj = blockIdx.x * NT + threadIdx.x;
   const bool active = kj < Tk;
+  DropKey dkey{0u, 1u};
+  if (drop.on()) dkey = drop_key(drop);
+  const unsigned half_tk = static_cast<unsigned>((Tk + 1) / 2);
   float k[DH], v[DH], dk[DH], dv[DH];
 #pragma unroll
   for (int d = 0; d < DH; ++d) { k[d] = 0.f; v[d] = 0.f; dk[d] = 0.f; dv[d] = 0.f; }
@@ -243,6 +254,12 @@ attn_bwd_dkv_kernel(const T* __restrict__ Q, long long ldq, const T* __restrict_
           dp = fmaf(gv.z, v[d + 2], dp); dp = fmaf(gv.w, v[d + 3], dp);
         }
         const float p = __expf(dot * scale - sLse[i]);
+        float pm = p;                                  // dropped weight: feeds dV; dP is masked the same way
+        if (drop.on()) {
+          const unsigned row = (static_cast<unsigned>(b) * H + h) * Tq + q0 + i;
+          const float mk = drop_one(dkey, row * half_tk + (kj >> 1), kj & 1, drop.thr, drop.scale);
+          pm *= mk; dp *= mk;
+        }
         const float ds = p * (dp - sDel[i]) * scale;
 #pragma unroll
         for (int d = 0; d < DH; d += 4) {
@@ -250,8 +267,8 @@ attn_bwd_dkv_kernel(const T* __restrict__ Q, long long ldq, const T* __restrict_
           const float4 gv = *reinterpret_cast<const float4*>(&sG[i][d]);
           dk[d] = fmaf(ds, qv.x, dk[d]); dk[d + 1] = fmaf(ds, qv.y, dk[d + 1]);
           dk[d + 2] = fmaf(ds, qv.z, dk[d + 2]); dk[d + 3] = fmaf(ds, qv.w, dk[d + 3]);
-          dv[d] = fmaf(p, gv.x, dv[d]); dv[d + 1] = fmaf(p, gv.y, dv[d + 1]);
-          dv[d + 2] = fmaf(p, gv.z, dv[d + 2]); dv[d + 3] = fmaf(p, gv.w, dv[d + 3]);
+          dv[d] = fmaf(pm, gv.x, dv[d]); dv[d + 1] = fmaf(pm, gv.y, dv[d + 1]);
+          dv[d + 2] = fmaf(pm, gv.z, dv[d + 2]); dv[d + 3] = fmaf(pm, gv.w, dv[d + 3]);
         }
       }
     }
@@ -270,7 +287,7 @@ int fwd_impl(const AttnArgs& a, cudaStream_t s) {
   dim3 grid(ceil_div(a.Tq, NT), a.H, a.B);
   attn_fwd_kernel<T><<<grid, NT, 0, s>>>(reinterpret_cast<const T*>(a.Q), a.ldq, reinterpret_cast<const T*>(a.K),
                                          a.ldk, reinterpret_cast<const T*>(a.V), a.ldv, a.kmask,
-                                         reinterpret_cast<T*>(a.O), a.ldo, a.lse, a.H, a.Tq, a.Tk, a.scale);
+                                         reinterpret_cast<T*>(a.O), a.ldo, a.lse, a.H, a.Tq, a.Tk, a.scale, a.drop);
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -285,13 +302,13 @@ int bwd_impl(const AttnArgs& a, cudaStream_t s) {
       reinterpret_cast<const T*>(a.Q), a.ldq, reinterpret_cast<const T*>(a.K), a.ldk,
       reinterpret_cast<const T*>(a.V), a.ldv, a.kmask, reinterpret_cast<const T*>(a.O), a.ldo,
       reinterpret_cast<const T*>(a.dO), a.lddo, a.lse, a.delta, reinterpret_cast<T*>(a.dQ), a.lddq, a.H, a.Tq, a.Tk,
-      a.scale);
+      a.scale, a.drop);
   SER_LAUNCH_CHECK();
   dim3 gk(ceil_div(a.Tk, NT), a.H, a.B);
   attn_bwd_dkv_kernel<T><<<gk, NT, 0, s>>>(
       reinterpret_cast<const T*>(a.Q), a.ldq, reinterpret_cast<const T*>(a.K), a.ldk,
       reinterpret_cast<const T*>(a.V), a.ldv, a.kmask, reinterpret_cast<const T*>(a.dO), a.lddo, a.lse, a.delta,
-      reinterpret_cast<T*>(a.dK), a.lddk, reinterpret_cast<T*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale);
+      reinterpret_cast<T*>(a.dK), a.lddk, reinterpret_cast<T*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale, a.drop);
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -301,6 +318,8 @@ int check(const AttnArgs& a) {
   SER_REQUIRE(a.B > 0 && a.H > 0 && a.Tq > 0 && a.Tk > 0, "attention: empty problem");
   SER_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0,
               "attention: leading dimensions must be multiples of 8");
+  SER_REQUIRE(!a.drop.on() || static_cast<long long>(a.B) * a.H * a.Tq * ((a.Tk + 1) / 2) < (1LL << 32),
+              "attention: dropout site too large for the 32-bit pair index");
   return SER_OK;
 }
 

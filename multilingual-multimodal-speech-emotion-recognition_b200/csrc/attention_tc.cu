@@ -101,16 +101,27 @@ __device__ __forceinline__ void mma_nn(const uint32_t (&p)[4][4], const bf16* ti
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 5)
+template <bool DROP>
+__global__ void __launch_bounds__(NT, DROP ? 4 : 5)
 attn_tc_fwd_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk,
                    const bf16* __restrict__ V, long long ldv, const float* __restrict__ kmask, bf16* __restrict__ O,
-                   long long ldo, float* __restrict__ lse, int H, int Tq, int Tk, float scale) {
+                   long long ldo, float* __restrict__ lse, int H, int Tq, int Tk, float scale, DropSpec drop) {
   __shared__ __align__(16) bf16 sQ[ROWS * LDS];
   __shared__ __align__(16) bf16 sK[2][TILE * LDS];
   __shared__ __align__(16) bf16 sV[2][TILE * LDS];
   __shared__ float sBias[2][TILE];         // 0 for a valid key, -inf for a padded / out-of-range one
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // dropout on the attention weights: pair index of (query row r, key pair) = drow[r] + key / 2   (dropout.cuh)
+  DropKey dkey{0u, 1u};
+  unsigned drow[2] = {0u, 0u};
+  if (DROP) {
+    dkey = drop_key(drop);
+    const unsigned half_tk = static_cast<unsigned>((Tk + 1) / 2);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      drow[r] = ((static_cast<unsigned>(b) * H + h) * Tq + q0 + warp * 16 + (lane >> 2) + 8 * r) * half_tk + (lane & 3);
+  }
   const int qrows = min(ROWS, Tq - q0);
   const float c = scale * kLog2e;
   const int ntiles = (Tk + TILE - 1) / TILE;
@@ -178,9 +189,15 @@ attn_tc_fwd_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __rest
     float ls[2] = {0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float p0 = exp2f((s[j][0] - mu[0]) * c), p1 = exp2f((s[j][1] - mu[0]) * c);
-      const float p2 = exp2f((s[j][2] - mu[1]) * c), p3 = exp2f((s[j][3] - mu[1]) * c);
-      ls[0] += p0 + p1; ls[1] += p2 + p3;
+      float p0 = exp2f((s[j][0] - mu[0]) * c), p1 = exp2f((s[j][1] - mu[0]) * c);
+      float p2 = exp2f((s[j][2] - mu[1]) * c), p3 = exp2f((s[j][3] - mu[1]) * c);
+      ls[0] += p0 + p1; ls[1] += p2 + p3;        // the normaliser sees every key; dropout acts on the weights
+      if (DROP) {
+        const unsigned kp = static_cast<unsigned>(t * (TILE / 2) + 4 * j);
+        const float2 m0 = drop_pair(dkey, drow[0] + kp, drop.thr, drop.scale);
+        const float2 m1 = drop_pair(dkey, drow[1] + kp, drop.thr, drop.scale);
+        p0 *= m0.x; p1 *= m0.y; p2 *= m1.x; p3 *= m1.y;
+      }
       p[j >> 1][(j & 1) * 2] = pack_bf16(p0, p1);
       p[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
     }
@@ -211,12 +228,13 @@ attn_tc_fwd_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __rest
 // ------------------------------------------------------------------------------------------------------------
 // backward, dQ (one CTA per 64 queries, streaming key tiles).  Also emits delta = rowsum(dO * O).
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 4)
+template <bool DROP>
+__global__ void __launch_bounds__(NT, DROP ? 3 : 4)
 attn_tc_bwd_dq_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk,
                       const bf16* __restrict__ V, long long ldv, const float* __restrict__ kmask,
                       const bf16* __restrict__ O, long long ldo, const bf16* __restrict__ dO, long long lddo,
                       const float* __restrict__ lse, float* __restrict__ delta, bf16* __restrict__ dQ, long long lddq,
-                      int H, int Tq, int Tk, float scale) {
+                      int H, int Tq, int Tk, float scale, DropSpec drop) {
   __shared__ __align__(16) bf16 sQ[ROWS * LDS];
   __shared__ __align__(16) bf16 sG[ROWS * LDS];
   __shared__ __align__(16) bf16 sK[2][TILE * LDS];
@@ -225,6 +243,15 @@ attn_tc_bwd_dq_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __r
   __shared__ float sDelta[ROWS];
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  DropKey dkey{0u, 1u};
+  unsigned drow[2] = {0u, 0u};
+  if (DROP) {
+    dkey = drop_key(drop);
+    const unsigned half_tk = static_cast<unsigned>((Tk + 1) / 2);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      drow[r] = ((static_cast<unsigned>(b) * H + h) * Tq + q0 + warp * 16 + (lane >> 2) + 8 * r) * half_tk + (lane & 3);
+  }
   const int qrows = min(ROWS, Tq - q0);
   const float c = scale * kLog2e;
   const int ntiles = (Tk + TILE - 1) / TILE;
@@ -302,6 +329,12 @@ attn_tc_bwd_dq_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __r
       const float2 bias = *reinterpret_cast<const float2*>(&sBias[buf][8 * j + 2 * (lane & 3)]);
       const float p0 = exp2f(s[j][0] * c + bias.x - rl[0]), p1 = exp2f(s[j][1] * c + bias.y - rl[0]);
       const float p2 = exp2f(s[j][2] * c + bias.x - rl[1]), p3 = exp2f(s[j][3] * c + bias.y - rl[1]);
+      if (DROP) {                                  // dP = mask * (dO V^T)
+        const unsigned kp = static_cast<unsigned>(t * (TILE / 2) + 4 * j);
+        const float2 m0 = drop_pair(dkey, drow[0] + kp, drop.thr, drop.scale);
+        const float2 m1 = drop_pair(dkey, drow[1] + kp, drop.thr, drop.scale);
+        dp[j][0] *= m0.x; dp[j][1] *= m0.y; dp[j][2] *= m1.x; dp[j][3] *= m1.y;
+      }
       ds[j >> 1][(j & 1) * 2] = pack_bf16(p0 * (dp[j][0] - rd[0]), p1 * (dp[j][1] - rd[0]));
       ds[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2 * (dp[j][2] - rd[1]), p3 * (dp[j][3] - rd[1]));
     }
@@ -322,12 +355,13 @@ attn_tc_bwd_dq_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __r
 // ------------------------------------------------------------------------------------------------------------
 // backward, dK / dV (one CTA per 64 keys, streaming query tiles): S^T = K Q^T, dP^T = V dO^T
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT, 4)
+template <bool DROP>
+__global__ void __launch_bounds__(NT, DROP ? 3 : 4)
 attn_tc_bwd_dkv_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk,
                        const bf16* __restrict__ V, long long ldv, const float* __restrict__ kmask,
                        const bf16* __restrict__ dO, long long lddo, const float* __restrict__ lse,
                        const float* __restrict__ delta, bf16* __restrict__ dK, long long lddk, bf16* __restrict__ dV,
-                       long long lddv, int H, int Tq, int Tk, float scale) {
+                       long long lddv, int H, int Tq, int Tk, float scale, DropSpec drop) {
   __shared__ __align__(16) bf16 sK[ROWS * LDS];
   __shared__ __align__(16) bf16 sV[ROWS * LDS];
   __shared__ __align__(16) bf16 sQ[2][TILE * LDS];
@@ -358,6 +392,17 @@ attn_tc_bwd_dkv_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __
   stage_q(0, 0);
   uint32_t ka[2][4], va[2][4];
   float kb[2];                              // 0 / -inf per owned key row
+  // dropout: element (query q, key kj) -> pair (row(q) * ceil(Tk/2) + kj / 2), half kj & 1; the two owned keys
+  // (kj, kj + 8) have the same parity
+  DropKey dkey{0u, 1u};
+  unsigned dcol[2] = {0u, 0u}, dhalf = 0u, half_tk = 0u, dq0 = 0u;
+  if (DROP) {
+    dkey = drop_key(drop);
+    half_tk = static_cast<unsigned>((Tk + 1) / 2);
+    const unsigned kj0 = static_cast<unsigned>(k0 + warp * 16 + (lane >> 2));
+    dcol[0] = kj0 >> 1; dcol[1] = (kj0 + 8) >> 1; dhalf = kj0 & 1u;
+    dq0 = (static_cast<unsigned>(b) * H + h) * Tq + 2 * (lane & 3);
+  }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int kj = k0 + warp * 16 + (lane >> 2) + 8 * r;
@@ -393,8 +438,18 @@ attn_tc_bwd_dkv_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __
       const float2 qd = *reinterpret_cast<const float2*>(&sDel[buf][8 * j + 2 * (lane & 3)]);
       const float p0 = exp2f(s[j][0] * c + kb[0] - ql.x), p1 = exp2f(s[j][1] * c + kb[0] - ql.y);
       const float p2 = exp2f(s[j][2] * c + kb[1] - ql.x), p3 = exp2f(s[j][3] * c + kb[1] - ql.y);
-      pt[j >> 1][(j & 1) * 2] = pack_bf16(p0, p1);
-      pt[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+      float w0 = p0, w1 = p1, w2 = p2, w3 = p3;      // dropped weights feed dV; dP is masked the same way
+      if (DROP) {
+        const unsigned qa = (dq0 + t * TILE + 8 * j) * half_tk, qb = qa + half_tk;   // queries q, q + 1
+        const float m0 = drop_one(dkey, qa + dcol[0], dhalf, drop.thr, drop.scale);
+        const float m1 = drop_one(dkey, qb + dcol[0], dhalf, drop.thr, drop.scale);
+        const float m2 = drop_one(dkey, qa + dcol[1], dhalf, drop.thr, drop.scale);
+        const float m3 = drop_one(dkey, qb + dcol[1], dhalf, drop.thr, drop.scale);
+        w0 *= m0; w1 *= m1; w2 *= m2; w3 *= m3;
+        dp[j][0] *= m0; dp[j][1] *= m1; dp[j][2] *= m2; dp[j][3] *= m3;
+      }
+      pt[j >> 1][(j & 1) * 2] = pack_bf16(w0, w1);
+      pt[j >> 1][(j & 1) * 2 + 1] = pack_bf16(w2, w3);
       dst[j >> 1][(j & 1) * 2] = pack_bf16(p0 * (dp[j][0] - qd.x), p1 * (dp[j][1] - qd.y));
       dst[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2 * (dp[j][2] - qd.x), p3 * (dp[j][3] - qd.y));
     }
@@ -424,9 +479,10 @@ int attention_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   const double by = 2.0 * static_cast<double>(a.B) * a.H * a.dh * (2.0 * a.Tq + 2.0 * a.Tk);
   ProfScope prof("attention_fwd", fl, by, s);
   dim3 grid(ceil_div(a.Tq, ROWS), a.H, a.B);
-  attn_tc_fwd_kernel<<<grid, NT, 0, s>>>(reinterpret_cast<const bf16*>(a.Q), a.ldq, reinterpret_cast<const bf16*>(a.K),
-                                         a.ldk, reinterpret_cast<const bf16*>(a.V), a.ldv, a.kmask,
-                                         reinterpret_cast<bf16*>(a.O), a.ldo, a.lse, a.H, a.Tq, a.Tk, a.scale);
+  auto* kern = a.drop.on() ? attn_tc_fwd_kernel<true> : attn_tc_fwd_kernel<false>;
+  kern<<<grid, NT, 0, s>>>(reinterpret_cast<const bf16*>(a.Q), a.ldq, reinterpret_cast<const bf16*>(a.K), a.ldk,
+                           reinterpret_cast<const bf16*>(a.V), a.ldv, a.kmask, reinterpret_cast<bf16*>(a.O), a.ldo, a.lse,
+                           a.H, a.Tq, a.Tk, a.scale, a.drop);
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -436,17 +492,19 @@ int attention_bwd_tc(const AttnArgs& a, cudaStream_t s) {
   const double by = 2.0 * static_cast<double>(a.B) * a.H * a.dh * (4.0 * a.Tq + 4.0 * a.Tk);
   ProfScope prof("attention_bwd", fl, by, s);
   dim3 gq(ceil_div(a.Tq, ROWS), a.H, a.B);
-  attn_tc_bwd_dq_kernel<<<gq, NT, 0, s>>>(
+  auto* kdq = a.drop.on() ? attn_tc_bwd_dq_kernel<true> : attn_tc_bwd_dq_kernel<false>;
+  kdq<<<gq, NT, 0, s>>>(
       reinterpret_cast<const bf16*>(a.Q), a.ldq, reinterpret_cast<const bf16*>(a.K), a.ldk,
       reinterpret_cast<const bf16*>(a.V), a.ldv, a.kmask, reinterpret_cast<const bf16*>(a.O), a.ldo,
       reinterpret_cast<const bf16*>(a.dO), a.lddo, a.lse, a.delta, reinterpret_cast<bf16*>(a.dQ), a.lddq, a.H, a.Tq,
-      a.Tk, a.scale);
+      a.Tk, a.scale, a.drop);
   SER_LAUNCH_CHECK();
   dim3 gk(ceil_div(a.Tk, ROWS), a.H, a.B);
-  attn_tc_bwd_dkv_kernel<<<gk, NT, 0, s>>>(
+  auto* kdkv = a.drop.on() ? attn_tc_bwd_dkv_kernel<true> : attn_tc_bwd_dkv_kernel<false>;
+  kdkv<<<gk, NT, 0, s>>>(
       reinterpret_cast<const bf16*>(a.Q), a.ldq, reinterpret_cast<const bf16*>(a.K), a.ldk,
       reinterpret_cast<const bf16*>(a.V), a.ldv, a.kmask, reinterpret_cast<const bf16*>(a.dO), a.lddo, a.lse, a.delta,
-      reinterpret_cast<bf16*>(a.dK), a.lddk, reinterpret_cast<bf16*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale);
+      reinterpret_cast<bf16*>(a.dK), a.lddk, reinterpret_cast<bf16*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale, a.drop);
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

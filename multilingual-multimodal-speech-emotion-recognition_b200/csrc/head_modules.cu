@@ -48,8 +48,9 @@ int linear_fwd(int dt, int M, int Nout, int Kin, const void* A, long long lda, c
 // dX[M,Kin] = gate'(dY[M,Nout] W[Nout,Kin]) (+ R)
 int linear_dgrad(int dt, int M, int Nout, int Kin, const void* dY, long long lddy, const void* W, long long ldw,
                  void* dX, long long lddx, int dx_f32, const void* G, long long ldg, int g_f32, int gate_mode,
-                 const void* R, long long ldr, int r_f32, cudaStream_t s) {
+                 const void* R, long long ldr, int r_f32, cudaStream_t s, float alpha = 1.f) {
   GemmArgs g;
+  g.alpha = alpha;
   g.dtype = dt; g.M = M; g.N = Kin; g.K = Nout;
   g.A = dY; g.lda = lddy; g.a_trans = 0;
   g.B = W; g.ldb = ldw; g.b_trans = 1;
@@ -179,6 +180,7 @@ static int xattn_fwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
   // token-level part
   SER_TRY(linear_fwd(dt, Ma, S3, D, d.a, D, fb.wc_a, D, fb.bc_a, d.p_a, S3, f, ACT_NONE, nullptr, 0, f, s));
   SER_TRY(linear_fwd(dt, Mt, S3, D, d.t, D, fb.wc_t, D, fb.bc_t, d.p_t, S3, f, ACT_NONE, nullptr, 0, f, s));
+  const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);
   AttnArgs at{};
   at.dtype = dt; at.B = d.B; at.H = d.H; at.dh = S / d.H;
   at.scale = 1.0f / sqrtf(static_cast<float>(at.dh));
@@ -187,16 +189,21 @@ static int xattn_fwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
   at.K = off(d.p_t, S, dt); at.ldk = S3;
   at.V = off(d.p_t, 2 * S, dt); at.ldv = S3;
   at.kmask = d.t_mask; at.O = d.ctx_a; at.ldo = S; at.lse = d.lse_a;
+  at.drop = with_site(drop, DS_XA_PROB_A);
   SER_TRY(attention_fwd(at, s));
   at.Tq = d.Tt; at.Tk = d.Ta;
   at.Q = d.p_t;
   at.K = off(d.p_a, S, dt);
   at.V = off(d.p_a, 2 * S, dt);
   at.kmask = d.a_mask; at.O = d.ctx_t; at.lse = d.lse_t;
+  at.drop = with_site(drop, DS_XA_PROB_T);
   SER_TRY(attention_fwd(at, s));
-  SER_TRY(linear_fwd(dt, Ma, D, S, d.ctx_a, S, fb.wz_a, S, fb.bz_a, d.z_a, D, f, ACT_NONE, d.a, D, f, s));
+  // z = x + dropout(ctx Wz^T + bz): with dropout on, the residual moves from the GEMM epilogue into the mask pass
+  SER_TRY(linear_fwd(dt, Ma, D, S, d.ctx_a, S, fb.wz_a, S, fb.bz_a, d.z_a, D, f, ACT_NONE, drop.on() ? nullptr : d.a, D, f, s));
+  if (drop.on()) SER_TRY(dropout_apply(d.z_a, d.z_a, d.a, f, Ma, D, with_site(drop, DS_XA_RES_A), s));
   SER_TRY(layernorm_fwd(d.z_a, f, d.enh_a, f, nullptr, f, d.ln_a_g, d.ln_a_b, d.stats_a, Ma, D, 0, s));
-  SER_TRY(linear_fwd(dt, Mt, D, S, d.ctx_t, S, fb.wz_t, S, fb.bz_t, d.z_t, D, f, ACT_NONE, d.t, D, f, s));
+  SER_TRY(linear_fwd(dt, Mt, D, S, d.ctx_t, S, fb.wz_t, S, fb.bz_t, d.z_t, D, f, ACT_NONE, drop.on() ? nullptr : d.t, D, f, s));
+  if (drop.on()) SER_TRY(dropout_apply(d.z_t, d.z_t, d.t, f, Mt, D, with_site(drop, DS_XA_RES_T), s));
   SER_TRY(layernorm_fwd(d.z_t, f, d.enh_t, f, nullptr, f, d.ln_t_g, d.ln_t_b, d.stats_t, Mt, D, 0, s));
   return SER_OK;
 }
@@ -223,6 +230,10 @@ static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
   void* dp_t = ws.take(static_cast<size_t>(Mt) * S3 * e);
   float* delta_a = reinterpret_cast<float*>(ws.take(static_cast<size_t>(d.B) * d.H * d.Ta * sizeof(float)));
   float* delta_t = reinterpret_cast<float*>(ws.take(static_cast<size_t>(d.B) * d.H * d.Tt * sizeof(float)));
+  const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);
+  // with dropout on, the branch gradient is mask * dz (its own buffer: the skip path keeps the unmasked dz)
+  void* dzm_a = drop.on() ? ws.take(static_cast<size_t>(Ma) * D * e) : dz_a;
+  void* dzm_t = drop.on() ? ws.take(static_cast<size_t>(Mt) * D * e) : dz_t;
   // weight-sized scratch, [audio | text] contiguous per kind so one cast / one batched GEMM serves both modalities
   float* dbz[2]; float* dbc[2]; float* dwz32[2]; void* dwz16[2]; float* dwc32[2]; void* dwc16[2];
   {
@@ -252,9 +263,13 @@ static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
   // z = ctx Wz^T + bz + residual
   struct SideZ { int M; void* dz; const void* ctx; void* dctx; const void* wz; const void* wout; const void* wo;
                  float* dwout; float* dwo; int m; };
+  if (drop.on()) {
+    SER_TRY(dropout_apply(dz_a, dzm_a, nullptr, f, Ma, D, with_site(drop, DS_XA_RES_A), s));
+    SER_TRY(dropout_apply(dz_t, dzm_t, nullptr, f, Mt, D, with_site(drop, DS_XA_RES_T), s));
+  }
   const SideZ sz[2] = {
-      {Ma, dz_a, d.ctx_a, dctx_a, fb.wz_a, d.wout_a, d.wo_a, d.dwout_a, d.dwo_a, 0},
-      {Mt, dz_t, d.ctx_t, dctx_t, fb.wz_t, d.wout_t, d.wo_t, d.dwout_t, d.dwo_t, 1},
+      {Ma, dzm_a, d.ctx_a, dctx_a, fb.wz_a, d.wout_a, d.wo_a, d.dwout_a, d.dwo_a, 0},
+      {Mt, dzm_t, d.ctx_t, dctx_t, fb.wz_t, d.wout_t, d.wo_t, d.dwout_t, d.dwo_t, 1},
   };
   for (const SideZ& z : sz) {
     SER_TRY(colsum(z.dz, f, D, z.M, D, dbz[z.m], s));
@@ -274,11 +289,13 @@ static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
   at.Q = d.p_a; at.K = off(d.p_t, S, dt); at.V = off(d.p_t, 2 * S, dt);
   at.kmask = d.t_mask; at.O = d.ctx_a; at.lse = d.lse_a; at.dO = dctx_a; at.delta = delta_a;
   at.dQ = dp_a; at.dK = off(dp_t, S, dt); at.dV = off(dp_t, 2 * S, dt);
+  at.drop = with_site(drop, DS_XA_PROB_A);
   SER_TRY(attention_bwd(at, s));
   at.Tq = d.Tt; at.Tk = d.Ta;
   at.Q = d.p_t; at.K = off(d.p_a, S, dt); at.V = off(d.p_a, 2 * S, dt);
   at.kmask = d.a_mask; at.O = d.ctx_t; at.lse = d.lse_t; at.dO = dctx_t; at.delta = delta_t;
   at.dQ = dp_t; at.dK = off(dp_a, S, dt); at.dV = off(dp_a, 2 * S, dt);
+  at.drop = with_site(drop, DS_XA_PROB_T);
   SER_TRY(attention_bwd(at, s));
   // p = x Wc^T + bc
   struct SideP { int M; void* dp; const void* x; void* dx; const void* dz; const void* wc; const void* wbd; const void* wqkv;
@@ -330,6 +347,7 @@ int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s) {
     SER_TRY(linear_fwd(dt, p.M, S, S, off(p.src, p.scol, dt), S3, off(p.w, static_cast<long long>(p.wrow) * S, dt), S,
                        p.b + p.wrow, off(p.dst, p.dcol, dt), S3, f, ACT_NONE, nullptr, 0, f, s));
   }
+  const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);
   AttnArgs at{};
   at.dtype = dt; at.B = d.B; at.H = d.H; at.dh = S / d.H;
   at.scale = 1.0f / sqrtf(static_cast<float>(at.dh));
@@ -339,6 +357,7 @@ int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s) {
   at.K = off(d.p_t, S, dt); at.ldk = S3;
   at.V = off(d.p_t, 2 * S, dt); at.ldv = S3;
   at.kmask = d.t_mask; at.O = d.ctx_a; at.ldo = S; at.lse = d.lse_a;
+  at.drop = with_site(drop, DS_XA_PROB_A);
   SER_TRY(attention_fwd(at, s));
   // T <- A
   at.Tq = d.Tt; at.Tk = d.Ta;
@@ -346,13 +365,16 @@ int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s) {
   at.K = off(d.p_a, S, dt);
   at.V = off(d.p_a, 2 * S, dt);
   at.kmask = d.a_mask; at.O = d.ctx_t; at.lse = d.lse_t;
+  at.drop = with_site(drop, DS_XA_PROB_T);
   SER_TRY(attention_fwd(at, s));
-  // out_proj, out_a / out_t + residual, LayerNorm (cross_attention.py:42-43,50-51)
+  // out_proj, out_a / out_t, dropout, + residual, LayerNorm (cross_attention.py:42-43,50-51)
   SER_TRY(linear_fwd(dt, Ma, S, S, d.ctx_a, S, d.wo_a, S, d.bo_a, d.o_a, S, f, ACT_NONE, nullptr, 0, f, s));
-  SER_TRY(linear_fwd(dt, Ma, D, S, d.o_a, S, d.wout_a, S, d.bout_a, d.z_a, D, f, ACT_NONE, d.a, D, f, s));
+  SER_TRY(linear_fwd(dt, Ma, D, S, d.o_a, S, d.wout_a, S, d.bout_a, d.z_a, D, f, ACT_NONE, drop.on() ? nullptr : d.a, D, f, s));
+  if (drop.on()) SER_TRY(dropout_apply(d.z_a, d.z_a, d.a, f, Ma, D, with_site(drop, DS_XA_RES_A), s));
   SER_TRY(layernorm_fwd(d.z_a, f, d.enh_a, f, nullptr, f, d.ln_a_g, d.ln_a_b, d.stats_a, Ma, D, 0, s));
   SER_TRY(linear_fwd(dt, Mt, S, S, d.ctx_t, S, d.wo_t, S, d.bo_t, d.o_t, S, f, ACT_NONE, nullptr, 0, f, s));
-  SER_TRY(linear_fwd(dt, Mt, D, S, d.o_t, S, d.wout_t, S, d.bout_t, d.z_t, D, f, ACT_NONE, d.t, D, f, s));
+  SER_TRY(linear_fwd(dt, Mt, D, S, d.o_t, S, d.wout_t, S, d.bout_t, d.z_t, D, f, ACT_NONE, drop.on() ? nullptr : d.t, D, f, s));
+  if (drop.on()) SER_TRY(dropout_apply(d.z_t, d.z_t, d.t, f, Mt, D, with_site(drop, DS_XA_RES_T), s));
   SER_TRY(layernorm_fwd(d.z_t, f, d.enh_t, f, nullptr, f, d.ln_t_g, d.ln_t_b, d.stats_t, Mt, D, 0, s));
   return SER_OK;
 }
@@ -362,7 +384,7 @@ size_t xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H)
   size_t tot = 0;
   for (int T : {Ta, Tt}) {
     const size_t M = static_cast<size_t>(B) * T;
-    tot += pad256(M * D * e);            // dz
+    tot += 2 * pad256(M * D * e);        // dz, mask * dz (dropout)
     tot += 2 * pad256(M * S * e);        // do, dctx
     tot += 2 * pad256(M * 3 * S * e);    // dp, dqkv
     tot += pad256(static_cast<size_t>(B) * H * T * sizeof(float));   // delta
@@ -389,6 +411,9 @@ int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
   void* dqkv_t = ws.take(static_cast<size_t>(Mt) * S3 * e);
   float* delta_a = reinterpret_cast<float*>(ws.take(static_cast<size_t>(d.B) * d.H * d.Ta * sizeof(float)));
   float* delta_t = reinterpret_cast<float*>(ws.take(static_cast<size_t>(d.B) * d.H * d.Tt * sizeof(float)));
+  const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);
+  void* dzm_a = drop.on() ? ws.take(static_cast<size_t>(Ma) * D * e) : dz_a;
+  void* dzm_t = drop.on() ? ws.take(static_cast<size_t>(Mt) * D * e) : dz_t;
   if (!ws.ok) { set_last_error(__FILE__, __LINE__, "xattn_bwd: workspace too small"); return SER_ERR_WORKSPACE; }
 
   // LayerNorm backward (parameter gradients accumulate with atomics -> zero first)
@@ -403,9 +428,13 @@ int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
   // out_a / out_t and out_proj
   struct Side { int M; void* dz; const void* o; const void* ctx; void* dob; void* dctx; const void* wout; const void* wo;
                 float* dwout; float* dbout; float* dwo; float* dbo; };
+  if (drop.on()) {     // branch gradient = mask * dz; the skip path (last two GEMMs below) keeps the unmasked dz
+    SER_TRY(dropout_apply(dz_a, dzm_a, nullptr, f, Ma, D, with_site(drop, DS_XA_RES_A), s));
+    SER_TRY(dropout_apply(dz_t, dzm_t, nullptr, f, Mt, D, with_site(drop, DS_XA_RES_T), s));
+  }
   const Side sides[2] = {
-      {Ma, dz_a, d.o_a, d.ctx_a, do_a, dctx_a, d.wout_a, d.wo_a, d.dwout_a, d.dbout_a, d.dwo_a, d.dbo_a},
-      {Mt, dz_t, d.o_t, d.ctx_t, do_t, dctx_t, d.wout_t, d.wo_t, d.dwout_t, d.dbout_t, d.dwo_t, d.dbo_t},
+      {Ma, dzm_a, d.o_a, d.ctx_a, do_a, dctx_a, d.wout_a, d.wo_a, d.dwout_a, d.dbout_a, d.dwo_a, d.dbo_a},
+      {Mt, dzm_t, d.o_t, d.ctx_t, do_t, dctx_t, d.wout_t, d.wo_t, d.dwout_t, d.dbout_t, d.dwo_t, d.dbo_t},
   };
   for (const Side& sd : sides) {
     SER_TRY(colsum(sd.dz, f, D, sd.M, D, sd.dbout, s));
@@ -425,12 +454,14 @@ int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
   at.Q = d.p_a; at.K = off(d.p_t, S, dt); at.V = off(d.p_t, 2 * S, dt);
   at.kmask = d.t_mask; at.O = d.ctx_a; at.lse = d.lse_a; at.dO = dctx_a; at.delta = delta_a;
   at.dQ = dp_a; at.dK = off(dp_t, S, dt); at.dV = off(dp_t, 2 * S, dt);
+  at.drop = with_site(drop, DS_XA_PROB_A);
   SER_TRY(attention_bwd(at, s));
   // T <- A
   at.Tq = d.Tt; at.Tk = d.Ta;
   at.Q = d.p_t; at.K = off(d.p_a, S, dt); at.V = off(d.p_a, 2 * S, dt);
   at.kmask = d.a_mask; at.O = d.ctx_t; at.lse = d.lse_t; at.dO = dctx_t; at.delta = delta_t;
   at.dQ = dp_t; at.dK = off(dp_a, S, dt); at.dV = off(dp_a, 2 * S, dt);
+  at.drop = with_site(drop, DS_XA_PROB_T);
   SER_TRY(attention_bwd(at, s));
   // MHA in-projection backward
   struct InProjB { const void* dp; const void* src; int M; int col; const void* w; float* dw; float* db; int wrow; void* dsrc; };
@@ -509,10 +540,13 @@ int fusion_fwd(const ser_fusion_desc& d, cudaStream_t s) {
   const int dt = d.dtype, f = is_f32(dt);
   const int B = d.B, P = d.P, G = d.G, Din = d.Din;
   SER_REQUIRE(B > 0 && d.av && d.tv && d.fused, "fusion_fwd: null tensor");
+  const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);       // proj_a[2] / proj_t[2] (fusion.py:9,12)
   SER_TRY(linear_fwd(dt, B, P, Din, d.av, Din, d.w1a, Din, d.b1a, d.ha, P, f, ACT_RELU, nullptr, 0, f, s));
+  if (drop.on()) SER_TRY(dropout_apply(d.ha, d.ha, nullptr, f, B, P, with_site(drop, DS_FUS_A), s));
   SER_TRY(linear_fwd(dt, B, P, P, d.ha, P, d.w2a, P, d.b2a, d.pa, P, f, ACT_NONE, nullptr, 0, f, s));
   SER_TRY(linear_fwd(dt, B, G, P, d.pa, P, d.wg1a, P, d.bg1a, d.ga, G, f, ACT_RELU, nullptr, 0, f, s));
   SER_TRY(linear_fwd(dt, B, P, Din, d.tv, Din, d.w1t, Din, d.b1t, d.ht, P, f, ACT_RELU, nullptr, 0, f, s));
+  if (drop.on()) SER_TRY(dropout_apply(d.ht, d.ht, nullptr, f, B, P, with_site(drop, DS_FUS_T), s));
   SER_TRY(linear_fwd(dt, B, P, P, d.ht, P, d.w2t, P, d.b2t, d.pt, P, f, ACT_NONE, nullptr, 0, f, s));
   SER_TRY(linear_fwd(dt, B, G, P, d.pt, P, d.wg1t, P, d.bg1t, d.gt, G, f, ACT_RELU, nullptr, 0, f, s));
   return fusion_mix_fwd(to_mix(d), s);
@@ -540,6 +574,8 @@ int fusion_bwd(const ser_fusion_desc& d, cudaStream_t s) {
   SER_CUDA_CHECK(cudaMemsetAsync(d.dwg2t, 0, sizeof(float) * G, s));
   SER_CUDA_CHECK(cudaMemsetAsync(d.dbg2a, 0, sizeof(float), s));
   SER_CUDA_CHECK(cudaMemsetAsync(d.dbg2t, 0, sizeof(float), s));
+  const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);
+  const float hscale = drop.on() ? drop.scale : 1.f;
   MixArgs m = to_mix(d);
   m.dpa = dpa; m.dpt = dpt; m.dga = dga; m.dgt = dgt;
   SER_TRY(fusion_mix_bwd(m, s));
@@ -555,7 +591,8 @@ int fusion_bwd(const ser_fusion_desc& d, cudaStream_t s) {
     SER_TRY(linear_dgrad(dt, B, G, P, sd.dg, G, sd.wg1, P, sd.dp, P, f, nullptr, 0, f, GATE_NONE, sd.dp, P, f, s));
     SER_TRY(colsum(sd.dp, f, P, B, P, sd.db2, s));
     SER_TRY(linear_wgrad(dt, B, P, P, sd.dp, P, sd.h, P, sd.dw2, P, s));
-    SER_TRY(linear_dgrad(dt, B, P, P, sd.dp, P, sd.w2, P, sd.dh, P, f, sd.h, P, f, GATE_RELU, nullptr, 0, f, s));
+    // h is saved post-dropout: h > 0 exactly where the unit was kept and the ReLU open; the kept units carry 1/(1-p)
+    SER_TRY(linear_dgrad(dt, B, P, P, sd.dp, P, sd.w2, P, sd.dh, P, f, sd.h, P, f, GATE_RELU, nullptr, 0, f, s, hscale));
     SER_TRY(colsum(sd.dh, f, P, B, P, sd.db1, s));
     SER_TRY(linear_wgrad(dt, B, P, Din, sd.dh, P, sd.v, Din, sd.dw1, Din, s));
     SER_TRY(linear_dgrad(dt, B, P, Din, sd.dh, P, sd.w1, Din, sd.dv, Din, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
@@ -613,8 +650,10 @@ int clf_fwd(const ser_clf_desc& d, cudaStream_t s) {
   // input_projection: Linear -> LayerNorm -> ReLU (classifier.py:105-110)
   SER_TRY(linear_fwd(dt, B, P, P, d.x, P, d.w_in, P, d.b_in, d.p0, P, 1, ACT_NONE, nullptr, 0, 1, s));
   SER_TRY(layernorm_fwd(d.p0, 1, d.h, 1, nullptr, 1, d.ln_in_g, d.ln_in_b, d.stats0, B, P, 1, s));
+  const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);
+  if (drop.on()) SER_TRY(dropout_apply(d.h, d.h, nullptr, 1, B, P, with_site(drop, DS_CLF_IN), s));   // input_projection[3]
   ClfStackArgs sa;
-  const bool fused = stack_args(d, sa);
+  const bool fused = stack_args(d, sa) && !drop.on();
   if (fused) SER_TRY(clf_stack_fwd(sa, s));          // all L blocks in one cluster kernel (clf_stack.cu)
   for (int i = 0; i < L && !fused; ++i) {
     float* hi = d.h + i * BP;
@@ -626,8 +665,10 @@ int clf_fwd(const ser_clf_desc& d, cudaStream_t s) {
     SER_TRY(layernorm2_fwd(hi, yi, ni, f, d.lno_g[i], d.lno_b[i], d.lni_g[i], d.lni_b[i],
                            d.stats_o + static_cast<size_t>(i) * B * 2, d.stats_i + static_cast<size_t>(i) * B * 2, B, P, s));
     SER_TRY(linear_fwd(dt, B, P, P, ni, P, d.w1[i], P, d.b1[i], ri, P, f, ACT_RELU, nullptr, 0, 1, s));
-    // residual from the OUTER-LN output y
-    SER_TRY(linear_fwd(dt, B, P, P, ri, P, d.w2[i], P, d.b2[i], hn, P, 1, ACT_NONE, yi, P, 1, s));
+    if (drop.on()) SER_TRY(dropout_apply(ri, ri, nullptr, f, B, P, with_site(drop, DS_CLF_BLOCK0 + 2 * i), s));   // block[3]
+    // residual from the OUTER-LN output y; with dropout on (block[5]) it is added by the mask pass instead
+    SER_TRY(linear_fwd(dt, B, P, P, ri, P, d.w2[i], P, d.b2[i], hn, P, 1, ACT_NONE, drop.on() ? nullptr : yi, P, 1, s));
+    if (drop.on()) SER_TRY(dropout_apply(hn, hn, yi, 1, B, P, with_site(drop, DS_CLF_BLOCK0 + 2 * i + 1), s));
   }
   const float* hL = d.h + static_cast<size_t>(L) * BP;
   SER_TRY(cast_any(hL, 1, d.h_last, f, static_cast<long long>(BP), s));
@@ -639,8 +680,10 @@ int clf_fwd(const ser_clf_desc& d, cudaStream_t s) {
     return SER_ERR_UNSUPPORTED;
   }
   SER_TRY(layernorm_fwd(d.q, 1, d.f, 1, nullptr, 1, d.ln_out_g, d.ln_out_b, d.stats_q, B, F, 1, s));
+  if (drop.on()) SER_TRY(dropout_apply(d.f, d.f, nullptr, 1, B, F, with_site(drop, DS_CLF_OUT), s));   // output_projection[3]
   // heads run in fp32 on the master weights (tiny: C x 256, 64 x 256), one fused launch (heads.cu)
-  SER_TRY(heads_fwd(d.f, d.w_c, d.b_c, d.w_u1, d.b_u1, d.w_u2, d.b_u2, d.logits, d.u1, d.unc, B, F, d.C, d.U, s));
+  SER_TRY(heads_fwd(d.f, d.w_c, d.b_c, d.w_u1, d.b_u1, d.w_u2, d.b_u2, d.logits, d.u1, d.unc, B, F, d.C, d.U,
+                    with_site(drop, DS_CLF_UNC), s));
   return SER_OK;
 }
 
@@ -675,8 +718,11 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
   if (!ws.ok) { set_last_error(__FILE__, __LINE__, "clf_bwd: workspace too small"); return SER_ERR_WORKSPACE; }
 
   // ---- heads (fp32): row-wise gradients + every head parameter gradient in two launches (heads.cu) ----
+  const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);
+  const float hscale = drop.on() ? drop.scale : 1.f;
   SER_TRY(heads_bwd(d.dlogits, d.dunc, d.unc, d.u1, d.f, d.w_c, d.w_u1, d.w_u2, df, du1, dsg, d.dw_c, d.db_c, d.dw_u1,
-                    d.db_u1, d.dw_u2, d.db_u2, B, F, C, U, s));
+                    d.db_u1, d.dw_u2, d.db_u2, B, F, C, U, with_site(drop, DS_CLF_UNC), s));
+  if (drop.on()) SER_TRY(dropout_apply(df, df, nullptr, 1, B, F, with_site(drop, DS_CLF_OUT), s));
   // ---- output projection: relu(LN(q)) ----
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_out_g, 0, sizeof(float) * F, s));
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_out_b, 0, sizeof(float) * F, s));
@@ -686,7 +732,7 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
   SER_TRY(linear_wgrad(dt, B, F, P, dq, F, d.h_last, P, d.dw_out, P, s));
   SER_TRY(linear_dgrad(dt, B, F, P, dq, F, d.w_out, P, dh32, P, 1, nullptr, 0, 1, GATE_NONE, nullptr, 0, 1, s));
   ClfStackArgs sa;
-  bool fused = stack_args(d, sa) && stack_grad_args(d, sa);
+  bool fused = stack_args(d, sa) && stack_grad_args(d, sa) && !drop.on();
   if (fused) {
     // the whole dX chain + LayerNorm parameter gradients in one cluster kernel; it leaves dL/dh_0 in dh32b and the
     // per-block GEMM operands (dh_{i+1}, da_i as bf16) in dhn_all / dr_all for the batched weight gradients below
@@ -705,7 +751,10 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
     const void* ri = off(static_cast<const void*>(d.r), static_cast<long long>(i) * BP, dt);
     void* dhn_i = off(dhn_all, static_cast<long long>(i) * BP, dt);
     void* dr_i = off(dr_all, static_cast<long long>(i) * BP, dt);
-    SER_TRY(linear_dgrad(dt, B, P, P, dhn_i, P, d.w2[i], P, dr_i, P, f, ri, P, f, GATE_RELU, nullptr, 0, 1, s));
+    // block[5]: the branch sees mask * dh_{i+1} (this act-dtype copy; the fp32 skip path `cur` stays unmasked);
+    // block[3]: r is saved post-dropout, so the ReLU gate is also the keep mask and the kept units carry 1/(1-p)
+    if (drop.on()) SER_TRY(dropout_apply(dhn_i, dhn_i, nullptr, f, B, P, with_site(drop, DS_CLF_BLOCK0 + 2 * i + 1), s));
+    SER_TRY(linear_dgrad(dt, B, P, P, dhn_i, P, d.w2[i], P, dr_i, P, f, ri, P, f, GATE_RELU, nullptr, 0, 1, s, hscale));
     SER_TRY(linear_dgrad(dt, B, P, P, dr_i, P, d.w1[i], P, dn32, P, 1, nullptr, 0, 1, GATE_NONE, nullptr, 0, 1, s));
     // dy = dh_next (skip) + LN_inner'(dn);  dh_i = LN_outer'(dy): fp32 stream + act-dtype copy for block i-1
     void* dh_prev = (i > 0) ? off(dhn_all, static_cast<long long>(i - 1) * BP, dt) : nullptr;
@@ -745,6 +794,7 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
     }
   }
   // ---- input projection: h0 = relu(LN(p0)) ----
+  if (drop.on()) SER_TRY(dropout_apply(cur, cur, nullptr, 1, B, P, with_site(drop, DS_CLF_IN), s));
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_in_g, 0, sizeof(float) * P, s));
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_in_b, 0, sizeof(float) * P, s));
   SER_TRY(layernorm_bwd(cur, 1, d.p0, 1, d.stats0, d.ln_in_g, d.ln_in_b, nullptr, 1, dp0, f, nullptr, 1, d.dln_in_g,

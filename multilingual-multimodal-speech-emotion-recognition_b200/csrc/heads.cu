@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(128)
 heads_fwd_kernel(const float* __restrict__ f, const float* __restrict__ w_c, const float* __restrict__ b_c,
                  const float* __restrict__ w_u1, const float* __restrict__ b_u1, const float* __restrict__ w_u2,
                  const float* __restrict__ b_u2, float* __restrict__ logits, float* __restrict__ u1,
-                 float* __restrict__ unc, int F, int C, int U) {
+                 float* __restrict__ unc, int F, int C, int U, DropSpec drop) {
   extern __shared__ __align__(16) float sm[];
   float* sf = sm;            // [F]
   float* su = sm + F;        // [U]
@@ -35,7 +35,11 @@ heads_fwd_kernel(const float* __restrict__ f, const float* __restrict__ w_c, con
     if (o < C) {
       logits[static_cast<size_t>(row) * C + o] = acc + b_c[o];
     } else {
-      const float v = fmaxf(acc + b_u1[o - C], 0.f);
+      float v = fmaxf(acc + b_u1[o - C], 0.f);
+      if (drop.on()) {                                   // uncertainty_head[2] (classifier.py:195); u1 is saved post-dropout
+        const unsigned j = static_cast<unsigned>(o - C);
+        v *= drop_one(drop_key(drop), static_cast<unsigned>(row) * ((U + 1) / 2) + (j >> 1), j & 1u, drop.thr, drop.scale);
+      }
       su[o - C] = v;
       u1[static_cast<size_t>(row) * U + (o - C)] = v;
     }
@@ -55,7 +59,7 @@ __global__ void __launch_bounds__(256)
 heads_bwd_rows_kernel(const float* __restrict__ dlogits, const float* __restrict__ dunc, const float* __restrict__ unc,
                       const float* __restrict__ u1, const float* __restrict__ w_c, const float* __restrict__ w_u1,
                       const float* __restrict__ w_u2, float* __restrict__ df, float* __restrict__ du1,
-                      float* __restrict__ dsg, int F, int C, int U) {
+                      float* __restrict__ dsg, int F, int C, int U, float uscale) {
   extern __shared__ float sg[];       // [C + U]
   const int row = blockIdx.x;
   const bool have_u = (dunc != nullptr) && (unc != nullptr);
@@ -69,7 +73,8 @@ heads_bwd_rows_kernel(const float* __restrict__ dlogits, const float* __restrict
     if (o < C) g = (dlogits != nullptr) ? dlogits[static_cast<size_t>(row) * C + o] : 0.f;
     else {
       const int j = o - C;
-      g = (have_u && u1[static_cast<size_t>(row) * U + j] > 0.f) ? ds * w_u2[j] : 0.f;
+      // u1 is the post-dropout activation: > 0 exactly where the unit was kept AND the ReLU was open
+      g = (have_u && u1[static_cast<size_t>(row) * U + j] > 0.f) ? ds * w_u2[j] * uscale : 0.f;
       du1[static_cast<size_t>(row) * U + j] = g;
     }
     sg[o] = g;
@@ -141,10 +146,10 @@ heads_bwd_w_kernel(const float* __restrict__ dlogits, const float* __restrict__ 
 
 int heads_fwd(const float* f, const float* w_c, const float* b_c, const float* w_u1, const float* b_u1,
               const float* w_u2, const float* b_u2, float* logits, float* u1, float* unc, int B, int F, int C, int U,
-              cudaStream_t s) {
+              const DropSpec& drop, cudaStream_t s) {
   SER_REQUIRE(B > 0 && F % 4 == 0 && F <= 4096 && C > 0 && U > 0 && U <= 1024, "heads_fwd: unsupported shape");
   ProfScope prof("heads_fwd", 2.0 * B * F * (C + U), 4.0 * (static_cast<double>(B) * F + (C + U) * F), s);
-  heads_fwd_kernel<<<B, 128, sizeof(float) * (F + U), s>>>(f, w_c, b_c, w_u1, b_u1, w_u2, b_u2, logits, u1, unc, F, C, U);
+  heads_fwd_kernel<<<B, 128, sizeof(float) * (F + U), s>>>(f, w_c, b_c, w_u1, b_u1, w_u2, b_u2, logits, u1, unc, F, C, U, drop);
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -152,11 +157,11 @@ int heads_fwd(const float* f, const float* w_c, const float* b_c, const float* w
 int heads_bwd(const float* dlogits, const float* dunc, const float* unc, const float* u1, const float* f,
               const float* w_c, const float* w_u1, const float* w_u2, float* df, float* du1, float* dsg, float* dw_c,
               float* db_c, float* dw_u1, float* db_u1, float* dw_u2, float* db_u2, int B, int F, int C, int U,
-              cudaStream_t s) {
+              const DropSpec& drop, cudaStream_t s) {
   SER_REQUIRE(B > 0 && F <= 1024 && U <= 1024 && C > 0, "heads_bwd: unsupported shape");
   ProfScope prof("heads_bwd", 4.0 * B * F * (C + U), 4.0 * (2.0 * B * F + 2.0 * (C + U) * F), s);
   heads_bwd_rows_kernel<<<B, 256, sizeof(float) * (C + U), s>>>(dlogits, dunc, unc, u1, w_c, w_u1, w_u2, df, du1, dsg,
-                                                              F, C, U);
+                                                              F, C, U, drop.on() ? drop.scale : 1.f);
   SER_LAUNCH_CHECK();
   heads_bwd_w_kernel<<<C + U + 1, 256, 0, s>>>(dlogits, du1, dsg, f, u1, dw_c, db_c, dw_u1, db_u1, dw_u2, db_u2, B, F, C, U);
   SER_LAUNCH_CHECK();

@@ -2,6 +2,7 @@
 // Every function enqueues on `stream`, returns an SER_* code and never synchronises.
 #pragma once
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace ser {
 
@@ -49,6 +50,8 @@ struct AttnArgs {
   void* dK; long long lddk;
   void* dV; long long lddv;
   float* delta;             // [B, H, Tq] scratch: rowsum(dO * O)
+  // dropout on the attention weights (nn.MultiheadAttention(dropout=p)): site [B*H*Tq, Tk]; off by default
+  DropSpec drop;
 };
 int attention_fwd(const AttnArgs& a, cudaStream_t s);
 int attention_bwd(const AttnArgs& a, cudaStream_t s);
@@ -97,12 +100,12 @@ int fold_bwd_glue(const FoldBwdArgs& a, cudaStream_t s);
 // logits + uncertainty head on the fp32 penultimate features (classifier.py:192-198,224,229); u1 / unc may be NULL
 int heads_fwd(const float* f, const float* w_c, const float* b_c, const float* w_u1, const float* b_u1,
               const float* w_u2, const float* b_u2, float* logits, float* u1, float* unc, int B, int F, int C, int U,
-              cudaStream_t s);
+              const DropSpec& drop, cudaStream_t s);
 // dlogits / dunc may be NULL (treated as zero); every parameter gradient is written (not accumulated)
 int heads_bwd(const float* dlogits, const float* dunc, const float* unc, const float* u1, const float* f,
               const float* w_c, const float* w_u1, const float* w_u2, float* df, float* du1, float* dsg, float* dw_c,
               float* db_c, float* dw_u1, float* db_u1, float* dw_u2, float* db_u2, int B, int F, int C, int U,
-              cudaStream_t s);
+              const DropSpec& drop, cudaStream_t s);
 
 // ---- pooling.cu ----------------------------------------------------------------------------------
 // Attentive statistics pooling, everything after the 768->128 tanh GEMM (src/models/pooling.py:21-28).

@@ -24,6 +24,27 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), device=device, dtype=torch.uint8)
 
 
+def _drop_fields(p_drop: float, seed: Optional[torch.Tensor]) -> dict:
+    """Descriptor fields switching in-kernel dropout on: `seed` is a 1-element int64 CUDA tensor read by the kernels
+    (include/ser_head.h, "dropout"); forward and backward of one call get the same tensor."""
+    if seed is None or not p_drop > 0.0:
+        return {}
+    if not (seed.is_cuda and seed.dtype == torch.int64 and seed.numel() == 1):
+        raise L.SerError("dropout seed must be a 1-element int64 CUDA tensor")
+    return dict(p_drop=float(p_drop), drop_seed=seed)
+
+
+def dropout_mask(seed: torch.Tensor, site: int, p: float, rows: int, cols: int) -> torch.Tensor:
+    """The [rows, cols] fp32 multipliers (0 or 1/(1-p)) the kernels apply at dropout site `site` (SER_DS_* of
+    include/ser_head.h) under `seed` -- used by the parity tests to drive the CPU oracle with the same masks."""
+    L.require_cuda(seed)
+    out = torch.empty(rows, cols, device=seed.device, dtype=torch.float32)
+    lib = L.load()
+    L.check(lib.ser_dropout_mask(seed.data_ptr(), int(site), float(p), int(rows), int(cols), out.data_ptr(),
+                                 L.stream_ptr(seed.device)), "ser_dropout_mask")
+    return out
+
+
 # --------------------------------------------------------------------------------------------------
 # a1 adapter
 # --------------------------------------------------------------------------------------------------
@@ -73,10 +94,11 @@ class AdapterFn(torch.autograd.Function):
 # a2 cross-modal attention
 # --------------------------------------------------------------------------------------------------
 class CrossAttentionFn(torch.autograd.Function):
-    """CrossModalAttention.forward (src/models/cross_attention.py:32-53), dropout off."""
+    """CrossModalAttention.forward (src/models/cross_attention.py:32-53); p_drop / seed: attention-weight and
+    residual dropout (0 / None = off)."""
 
     @staticmethod
-    def forward(ctx, a, t, a_mask, t_mask, fp: FlatParams, num_heads: int, *params):
+    def forward(ctx, a, t, a_mask, t_mask, fp: FlatParams, num_heads: int, p_drop: float, seed, *params):
         L.require_cuda(a, t, a_mask, t_mask)
         if a.dtype != t.dtype:
             raise L.SerError("audio and text sequences must share a dtype")
@@ -106,8 +128,9 @@ class CrossAttentionFn(torch.autograd.Function):
         w = CrossAttentionFn._weights(fp, wc)
         keep = []
         d = L.fill(L.XattnDesc(), keep, dtype=dt, B=B, Ta=Ta, Tt=Tt, D=D, S=S, H=num_heads, a=a2, t=t2, a_mask=am,
-                   t_mask=tm, enh_a=enh_a, enh_t=enh_t, **w, **sv)
+                   t_mask=tm, enh_a=enh_a, enh_t=enh_t, **w, **sv, **_drop_fields(p_drop, seed))
         L.call("ser_xattn_fwd", d, dev)
+        ctx.drop = (p_drop, seed)
         ctx.save_for_backward(a2, t2, am, tm, wc, *sv.values())
         ctx.sv_keys = list(sv.keys())
         ctx.fp, ctx.dims = fp, (B, Ta, Tt, D, S, num_heads)
@@ -161,11 +184,11 @@ class CrossAttentionFn(torch.autograd.Function):
         keep = []
         d = L.fill(L.XattnDesc(), keep, dtype=dt, B=B, Ta=Ta, Tt=Tt, D=D, S=S, H=H, a=a2, t=t2, a_mask=am, t_mask=tm,
                    d_enh_a=ga, d_enh_t=gt, da=da, dt=dtt, ws=ws, ws_bytes=ws.numel(),
-                   **CrossAttentionFn._weights(fp, wc), **sv, **grads)
+                   **CrossAttentionFn._weights(fp, wc), **sv, **grads, **_drop_fields(*ctx.drop))
         L.call("ser_xattn_bwd", d, dev)
         return (da.view(B, Ta, D) if ctx.needs_input_grad[0] else None,
                 dtt.view(B, Tt, D) if ctx.needs_input_grad[1] else None,
-                None, None, None, None, *fp.grads_from(g))
+                None, None, None, None, None, None, *fp.grads_from(g))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -225,7 +248,7 @@ class AttentiveStatsPoolingFn(torch.autograd.Function):
 # a4 gated fusion
 # --------------------------------------------------------------------------------------------------
 class FusionFn(torch.autograd.Function):
-    """FusionLayer.forward (src/models/fusion.py:18-25), dropout off."""
+    """FusionLayer.forward (src/models/fusion.py:18-25); p_drop / seed: proj_a[2] / proj_t[2] dropout (0 / None = off)."""
 
     @staticmethod
     def _weights(fp, wc):
@@ -239,7 +262,7 @@ class FusionFn(torch.autograd.Function):
         return out
 
     @staticmethod
-    def forward(ctx, av, tv, fp: FlatParams, *params):
+    def forward(ctx, av, tv, fp: FlatParams, p_drop: float, seed, *params):
         L.require_cuda(av, tv)
         dt = L.dtype_code(av.dtype)
         wc = fp.compute_copy(av.dtype)
@@ -254,8 +277,9 @@ class FusionFn(torch.autograd.Function):
         fused = E(B, P)
         keep = []
         d = L.fill(L.FusionDesc(), keep, dtype=dt, B=B, Din=Din, P=P, G=G, av=av2, tv=tv2, fused=fused,
-                   **FusionFn._weights(fp, wc), **sv)
+                   **FusionFn._weights(fp, wc), **sv, **_drop_fields(p_drop, seed))
         L.call("ser_fusion_fwd", d, dev)
+        ctx.drop = (p_drop, seed)
         ctx.save_for_backward(av2, tv2, wc, *sv.values())
         ctx.sv_keys = list(sv.keys())
         ctx.fp, ctx.dims = fp, (B, Din, P, G)
@@ -282,9 +306,9 @@ class FusionFn(torch.autograd.Function):
         keep = []
         d = L.fill(L.FusionDesc(), keep, dtype=dt, B=B, Din=Din, P=P, G=G, av=av2, tv=tv2,
                    dfused=dfused.to(ty).contiguous(), dav=dav, dtv=dtv, ws=ws, ws_bytes=ws.numel(),
-                   **FusionFn._weights(fp, wc), **sv, **grads)
+                   **FusionFn._weights(fp, wc), **sv, **grads, **_drop_fields(*ctx.drop))
         L.call("ser_fusion_bwd", d, dev)
-        return (dav if ctx.needs_input_grad[0] else None, dtv if ctx.needs_input_grad[1] else None, None,
+        return (dav if ctx.needs_input_grad[0] else None, dtv if ctx.needs_input_grad[1] else None, None, None, None,
                 *fp.grads_from(g))
 
 
@@ -292,8 +316,8 @@ class FusionFn(torch.autograd.Function):
 # a5 classifier stack + heads
 # --------------------------------------------------------------------------------------------------
 class ClassifierFn(torch.autograd.Function):
-    """AdvancedOpenMaxClassifier.forward up to (logits, uncertainty, features) -- classifier.py:200-229, dropout off.
-    Returns (logits [B,C] fp32, unc [B,1] fp32, features [B,256] fp32 (non-differentiable))."""
+    """AdvancedOpenMaxClassifier.forward up to (logits, uncertainty, features) -- classifier.py:200-229;
+    p_drop / seed: every nn.Dropout of the classifier (0 / None = off).  Returns (logits [B,C] fp32, unc [B,1] fp32, features [B,256] fp32 (non-differentiable))."""
 
     @staticmethod
     def _weights(fp, wc, L_):
@@ -335,7 +359,7 @@ class ClassifierFn(torch.autograd.Function):
         )
 
     @staticmethod
-    def forward(ctx, x, fp: FlatParams, num_layers: int, want_unc: bool, *params):
+    def forward(ctx, x, fp: FlatParams, num_layers: int, want_unc: bool, p_drop: float, seed, *params):
         L.require_cuda(x)
         dt = L.dtype_code(x.dtype)
         wc = fp.compute_copy(x.dtype)
@@ -355,8 +379,9 @@ class ClassifierFn(torch.autograd.Function):
         logits = F(B, C_)
         keep = []
         d = L.fill(L.ClfDesc(), keep, dtype=dt, B=B, P=P, F=F_, C=C_, L=Ln, U=U, x=x2, logits=logits,
-                   **ClassifierFn._weights(fp, wc, Ln), **sv)
+                   **ClassifierFn._weights(fp, wc, Ln), **sv, **_drop_fields(p_drop, seed))
         L.call("ser_clf_fwd", d, dev)
+        ctx.drop = (p_drop, seed)
         ctx.save_for_backward(x2, wc, *sv.values())
         ctx.sv_keys = list(sv.keys())
         ctx.fp, ctx.dims = fp, (B, P, F_, C_, Ln, U)
@@ -380,14 +405,15 @@ class ClassifierFn(torch.autograd.Function):
         keep = []
         d = L.fill(L.ClfDesc(), keep, dtype=dt, B=B, P=P, F=F_, C=C_, L=Ln, U=U, x=x2,
                    dlogits=_f32c(dlogits), dunc=_f32c(dunc), dx=dx, ws=ws, ws_bytes=ws.numel(),
-                   **ClassifierFn._weights(fp, wc, Ln), **sv, **ClassifierFn._grads(fp, g, Ln))
+                   **ClassifierFn._weights(fp, wc, Ln), **sv, **ClassifierFn._grads(fp, g, Ln),
+                   **_drop_fields(*ctx.drop))
         L.call("ser_clf_bwd", d, dev)
         grads = fp.grads_from(g)
         # the anchor temperature never receives a gradient in the reference (.grad stays None)
         ti = fp.index.get("anchor_clustering.temperature")
         if ti is not None:
             grads[ti] = None
-        return (dx if ctx.needs_input_grad[0] else None, None, None, None, *grads)
+        return (dx if ctx.needs_input_grad[0] else None, None, None, None, None, None, *grads)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -15,7 +15,7 @@ import torch.nn as nn
 
 from .._params import FlatParams
 from .. import functional as SF
-from ._common import LayerNorm, Linear, check_dropout
+from ._common import DropoutSeed, LayerNorm, Linear, active_dropout
 
 
 class ClassAnchorClustering(nn.Module):
@@ -88,10 +88,13 @@ class AdvancedOpenMaxClassifier(nn.Module):
                                               nn.Sigmoid())
         self._flat = FlatParams([(n, p) for n, p in self.named_parameters()])
         self.last_features: Optional[torch.Tensor] = None     # penultimate 256-d features of the last forward
+        self._drop_seed = DropoutSeed()
 
     def forward(self, x: torch.Tensor, use_openmax: bool = True, return_uncertainty: bool = False):
-        check_dropout(self, self.p_drop, "AdvancedOpenMaxClassifier")
-        logits, unc, feats = SF.ClassifierFn.apply(x, self._flat, self.num_layers, return_uncertainty,
+        # every nn.Dropout of the stack and of the uncertainty head (classifier.py:83,85,109,127,195) runs in-kernel
+        p = active_dropout(self, self.p_drop)
+        seed = self._drop_seed.next(x.device) if p > 0.0 else None
+        logits, unc, feats = SF.ClassifierFn.apply(x, self._flat, self.num_layers, return_uncertainty, p, seed,
                                                    *self._flat.params)
         self.last_features = feats
         anchor_loss = torch.zeros((), device=x.device, dtype=torch.float32)   # identically 0 in the reference

@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from .._params import FlatParams
 from ..functional import CrossAttentionFn
-from ._common import LayerNorm, Linear, check_dropout
+from ._common import DropoutSeed, LayerNorm, Linear, active_dropout
 
 
 class CrossModalAttention(nn.Module):
@@ -41,9 +41,13 @@ class CrossModalAttention(nn.Module):
             order += [f"q_{m}.weight", f"k_{m}.weight", f"v_{m}.weight", f"q_{m}.bias", f"k_{m}.bias", f"v_{m}.bias"]
         order += [n for n in named if n not in order]
         self._flat = FlatParams([(n, named[n]) for n in order])
+        self._drop_seed = DropoutSeed()
 
     def forward(self, audio_seq: torch.Tensor, text_seq: torch.Tensor, audio_mask: Optional[torch.Tensor] = None,
                 text_mask: Optional[torch.Tensor] = None):
-        check_dropout(self, self.p_drop, "CrossModalAttention")
-        return CrossAttentionFn.apply(audio_seq, text_seq, audio_mask, text_mask, self._flat, self.num_heads,
+        # attention-weight dropout of both nn.MultiheadAttention modules and self.dropout on the branch outputs
+        # (cross_attention.py:18,25,43,51) run inside the kernels; `self.dropout.p` is the single rate, as in the reference
+        p = active_dropout(self, self.dropout.p)
+        seed = self._drop_seed.next(audio_seq.device) if p > 0.0 else None
+        return CrossAttentionFn.apply(audio_seq, text_seq, audio_mask, text_mask, self._flat, self.num_heads, p, seed,
                                       *self._flat.params)

@@ -7,7 +7,8 @@ import torch.nn as nn
 
 from .._params import FlatParams
 from ..functional import FusionFn
-from ._common import Linear, check_dropout
+from .. import _lib
+from ._common import DropoutSeed, Linear, active_dropout
 
 
 def _mlp(din: int, dout: int) -> nn.Sequential:
@@ -30,9 +31,13 @@ class FusionLayer(nn.Module):
         self.gate_a = _gate(proj_dim, hidden)
         self.gate_t = _gate(proj_dim, hidden)
         self._flat = FlatParams([(n, p) for n, p in self.named_parameters()])
+        self._drop_seed = DropoutSeed()
 
     def forward(self, audio_vec: torch.Tensor, text_vec: torch.Tensor) -> torch.Tensor:
-        # the reference hard-codes Dropout(0.1) (fusion.py:9,12); set `fusion.proj_a[2].p = fusion.proj_t[2].p = 0`
-        # (FusionHead(dropout=0) does) or call .eval() to run the fused path
-        check_dropout(self, max(self.proj_a[2].p, self.proj_t[2].p), "FusionLayer")
-        return FusionFn.apply(audio_vec, text_vec, self._flat, *self._flat.params)
+        # the reference hard-codes Dropout(0.1) in both projections (fusion.py:9,12); the rate is read from the
+        # nn.Dropout children so it can be changed the usual way (both branches share one rate in the fused kernel)
+        if self.proj_a[2].p != self.proj_t[2].p:
+            raise _lib.SerError("FusionLayer: proj_a[2].p and proj_t[2].p must be equal in the fused path")
+        p = active_dropout(self, self.proj_a[2].p)
+        seed = self._drop_seed.next(audio_vec.device) if p > 0.0 else None
+        return FusionFn.apply(audio_vec, text_vec, self._flat, p, seed, *self._flat.params)

@@ -51,6 +51,37 @@ class operand_rounding:
         _OPERAND_DTYPE = self.prev
 
 
+# Optional dropout: the reference's nn.Dropout / MultiheadAttention(dropout=p) layers draw from torch's Philox stream,
+# which no other implementation can reproduce; what CAN be pinned is the arithmetic given the masks.  Inside
+# `with dropout_masks({site: multiplier tensor})` every dropout site multiplies its input by the given tensor
+# (0 or 1/(1-p) per element -- torch.nn.functional.dropout's output is exactly x * such a tensor); sites without an
+# entry, and all sites outside the context, are the identity (eval mode).  Site names:
+#   cross.prob_a / cross.prob_t [B,H,Tq,Tk]   attention weights of attn_a / attn_t (functional.py multi_head_attention_forward)
+#   cross.res_a / cross.res_t   [B,T,D]       self.dropout(a_out) / self.dropout(t_out)   (cross_attention.py:43,51)
+#   fusion.a / fusion.t         [B,P]         proj_a[2] / proj_t[2]                        (fusion.py:9,12)
+#   clf.in [B,P]; clf.block{i}.hidden, clf.block{i}.out [B,P]; clf.out [B,F]; clf.unc [B,64]   (classifier.py:83,85,109,127,195)
+_DROPOUT_MASKS = None
+
+
+class dropout_masks:
+    def __init__(self, masks):
+        self.masks = masks
+
+    def __enter__(self):
+        global _DROPOUT_MASKS
+        self.prev, _DROPOUT_MASKS = _DROPOUT_MASKS, self.masks
+
+    def __exit__(self, *exc):
+        global _DROPOUT_MASKS
+        _DROPOUT_MASKS = self.prev
+
+
+def _drop(x: Tensor, site: str) -> Tensor:
+    if _DROPOUT_MASKS is None or site not in _DROPOUT_MASKS:
+        return x
+    return x * _DROPOUT_MASKS[site].to(x.dtype).reshape(x.shape)
+
+
 def _ste_round(x: Tensor) -> Tensor:
     return x + (x.to(_OPERAND_DTYPE).to(x.dtype) - x).detach()
 
@@ -82,8 +113,8 @@ def adapter(x: Tensor, w: W) -> Tensor:
 # a2  CrossModalAttention  (src/models/cross_attention.py:32-53; MHA maths torch/nn/functional.py:6609-6645)
 # --------------------------------------------------------------------------------------------------
 def _mha(q_in: Tensor, k_in: Tensor, v_in: Tensor, kpm: Optional[Tensor], in_w: Tensor, in_b: Tensor,
-         out_w: Tensor, out_b: Tensor, num_heads: int) -> Tensor:
-    """nn.MultiheadAttention(batch_first=True) forward, explicit math path, dropout off.
+         out_w: Tensor, out_b: Tensor, num_heads: int, drop_site: str = "") -> Tensor:
+    """nn.MultiheadAttention(batch_first=True) forward, explicit math path; dropout acts on the softmax output.
 
     in_w [3E,E] is chunked q/k/v; q is scaled by 1/sqrt(dh) *after* its bias; key padding becomes an
     additive -inf on the scores; softmax over keys; out_proj.  A sample whose keys are all padded yields
@@ -100,7 +131,7 @@ def _mha(q_in: Tensor, k_in: Tensor, v_in: Tensor, kpm: Optional[Tensor], in_w: 
     s = (q * (1.0 / math.sqrt(dh))) @ k.transpose(-1, -2)                # [B,H,Tq,Tk]
     if kpm is not None:
         s = s.masked_fill(kpm[:, None, None, :], float("-inf"))
-    p = torch.softmax(s, dim=-1)
+    p = _drop(torch.softmax(s, dim=-1), drop_site)
     ctx = (p @ v).transpose(1, 2).reshape(B, Tq, E)
     return linear(ctx, out_w, out_b)
 
@@ -115,17 +146,17 @@ def cross_attention(a: Tensor, t: Tensor, a_mask: Optional[Tensor], t_mask: Opti
     kt = linear(t, w["k_t.weight"], w["k_t.bias"])
     vt = linear(t, w["v_t.weight"], w["v_t.bias"])
     a_ctx = _mha(qa, kt, vt, t_kpm, w["attn_a.in_proj_weight"], w["attn_a.in_proj_bias"],
-                 w["attn_a.out_proj.weight"], w["attn_a.out_proj.bias"], num_heads)
+                 w["attn_a.out_proj.weight"], w["attn_a.out_proj.bias"], num_heads, "cross.prob_a")
     a_out = linear(a_ctx, w["out_a.weight"], w["out_a.bias"])
-    audio_enh = layer_norm(a + a_out, w["norm_a.weight"], w["norm_a.bias"])
+    audio_enh = layer_norm(a + _drop(a_out, "cross.res_a"), w["norm_a.weight"], w["norm_a.bias"])
     # T <- A  (cross_attention.py:46-51)
     qt = linear(t, w["q_t.weight"], w["q_t.bias"])
     ka = linear(a, w["k_a.weight"], w["k_a.bias"])
     va = linear(a, w["v_a.weight"], w["v_a.bias"])
     t_ctx = _mha(qt, ka, va, a_kpm, w["attn_t.in_proj_weight"], w["attn_t.in_proj_bias"],
-                 w["attn_t.out_proj.weight"], w["attn_t.out_proj.bias"], num_heads)
+                 w["attn_t.out_proj.weight"], w["attn_t.out_proj.bias"], num_heads, "cross.prob_t")
     t_out = linear(t_ctx, w["out_t.weight"], w["out_t.bias"])
-    text_enh = layer_norm(t + t_out, w["norm_t.weight"], w["norm_t.bias"])
+    text_enh = layer_norm(t + _drop(t_out, "cross.res_t"), w["norm_t.weight"], w["norm_t.bias"])
     return audio_enh, text_enh
 
 
@@ -145,11 +176,13 @@ def attentive_stats_pooling(x: Tensor, mask: Optional[Tensor], w: W) -> Tensor:
 
 
 # --------------------------------------------------------------------------------------------------
-# a4  FusionLayer  (src/models/fusion.py:18-25), dropout off
+# a4  FusionLayer  (src/models/fusion.py:18-25)
 # --------------------------------------------------------------------------------------------------
 def fusion(av: Tensor, tv: Tensor, w: W) -> Tensor:
-    pa = linear(torch.relu(linear(av, w["proj_a.0.weight"], w["proj_a.0.bias"])), w["proj_a.3.weight"], w["proj_a.3.bias"])
-    pt = linear(torch.relu(linear(tv, w["proj_t.0.weight"], w["proj_t.0.bias"])), w["proj_t.3.weight"], w["proj_t.3.bias"])
+    pa = linear(_drop(torch.relu(linear(av, w["proj_a.0.weight"], w["proj_a.0.bias"])), "fusion.a"),
+                w["proj_a.3.weight"], w["proj_a.3.bias"])
+    pt = linear(_drop(torch.relu(linear(tv, w["proj_t.0.weight"], w["proj_t.0.bias"])), "fusion.t"),
+                w["proj_t.3.weight"], w["proj_t.3.bias"])
     wa = torch.sigmoid(linear(torch.relu(linear(pa, w["gate_a.0.weight"], w["gate_a.0.bias"])),
                               w["gate_a.2.weight"], w["gate_a.2.bias"]))             # [B,1]
     wt = torch.sigmoid(linear(torch.relu(linear(pt, w["gate_t.0.weight"], w["gate_t.0.bias"])),
@@ -162,19 +195,21 @@ def fusion(av: Tensor, tv: Tensor, w: W) -> Tensor:
 # a5 / a6 / a7  AdvancedOpenMaxClassifier  (src/models/classifier.py:200-305)
 # --------------------------------------------------------------------------------------------------
 def classifier_features(x: Tensor, w: W, num_layers: int = 35) -> Tensor:
-    """[B,512] -> penultimate 256-d features (classifier.py:203-218), dropout off."""
+    """[B,512] -> penultimate 256-d features (classifier.py:203-218)."""
     p = "deep_classifier."
     h = torch.relu(layer_norm(linear(x, w[p + "input_projection.0.weight"], w[p + "input_projection.0.bias"]),
                               w[p + "input_projection.1.weight"], w[p + "input_projection.1.bias"]))
+    h = _drop(h, "clf.in")
     for i in range(num_layers):
         # outer LayerNorm first; the residual branch starts from the OUTER-LN output (classifier.py:207-212)
         y = layer_norm(h, w[f"{p}layer_norms.{i}.weight"], w[f"{p}layer_norms.{i}.bias"])
         b = f"{p}residual_layers.{i}.block."
         n = layer_norm(y, w[b + "0.weight"], w[b + "0.bias"])
-        r = torch.relu(linear(n, w[b + "1.weight"], w[b + "1.bias"]))
-        h = y + linear(r, w[b + "4.weight"], w[b + "4.bias"])
+        r = _drop(torch.relu(linear(n, w[b + "1.weight"], w[b + "1.bias"])), f"clf.block{i}.hidden")
+        h = y + _drop(linear(r, w[b + "4.weight"], w[b + "4.bias"]), f"clf.block{i}.out")
     f = linear(h, w[p + "output_projection.0.weight"], w[p + "output_projection.0.bias"])
-    return torch.relu(layer_norm(f, w[p + "output_projection.1.weight"], w[p + "output_projection.1.bias"]))
+    f = torch.relu(layer_norm(f, w[p + "output_projection.1.weight"], w[p + "output_projection.1.bias"]))
+    return _drop(f, "clf.out")
 
 
 def anchor_clustering(f: Tensor, w: W) -> Tuple[Tensor, Tensor]:
@@ -228,7 +263,7 @@ def classifier(x: Tensor, w: W, num_layers: int = 35, use_openmax: bool = True, 
     logits = linear(f, w[p + "output_projection.4.weight"], w[p + "output_projection.4.bias"])
     unc = None
     if return_uncertainty:
-        u = torch.relu(linear(f, w["uncertainty_head.0.weight"], w["uncertainty_head.0.bias"]))
+        u = _drop(torch.relu(linear(f, w["uncertainty_head.0.weight"], w["uncertainty_head.0.bias"])), "clf.unc")
         unc = torch.sigmoid(linear(u, w["uncertainty_head.3.weight"], w["uncertainty_head.3.bias"]))
     if use_openmax and not training:
         logits = openmax(f, logits, w)

@@ -114,6 +114,97 @@ def run_train_case(name, B, Ta, Tt, C, seed, with_masks=True, num_layers=35):
           f"unc={unc_loss.item():.6f} anchor={anchor_loss.item()}")
 
 
+class RecordedDropout:
+    """Replaces torch.nn.functional.dropout while the reference runs in train() mode: every call draws its keep mask
+    from a seeded generator, applies x * keep / (1 - p) (the definition of dropout) and records (shape, p, keep) in
+    call order.  nn.Dropout.forward and nn.MultiheadAttention's math path both resolve `dropout` in
+    torch.nn.functional at call time, so this reaches every dropout of the path."""
+
+    def __init__(self, seed):
+        self.gen = torch.Generator().manual_seed(seed)
+        self.calls = []
+
+    def __call__(self, input, p=0.5, training=True, inplace=False):
+        if not training or p == 0.0:
+            return input
+        keep = torch.rand(input.shape, generator=self.gen) >= p
+        self.calls.append((tuple(input.shape), float(p), keep))
+        return input * keep.to(input.dtype) / (1.0 - p)
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self.F, self.orig = F, F.dropout
+        F.dropout = self
+        return self
+
+    def __exit__(self, *exc):
+        self.F.dropout = self.orig
+
+
+def dropout_site_names(num_layers):
+    """Call order of the dropouts in one reference training forward (src/train.py:145-168): cross attention
+    (attn_a weights, dropout(a_out), attn_t weights, dropout(t_out)), fusion (proj_a[2], proj_t[2]), classifier
+    (input_projection[3], per block block[3] / block[5], output_projection[3], then -- classifier.py:221-229 --
+    the anchor projection's dropout, whose output is discarded, and the uncertainty head's)."""
+    names = ["cross.prob_a", "cross.res_a", "cross.prob_t", "cross.res_t", "fusion.a", "fusion.t", "clf.in"]
+    for i in range(num_layers):
+        names += [f"clf.block{i}.hidden", f"clf.block{i}.out"]
+    names += ["clf.out"]
+    return names
+
+
+def run_train_dropout_case(name, B, Ta, Tt, C, seed, num_layers=35):
+    """Training-mode forward/backward of the reference with every dropout ACTIVE and its masks recorded: pins where
+    the oracle applies which mask (tests/test_oracle_golden.py::test_oracle_matches_reference_train_dropout)."""
+    weights = synth.head_weights(C, num_layers, seed=0)
+    m, L = build_reference_head(C, num_layers, weights)
+    for mod in m.values():
+        mod.train()
+    a_hid, t_hid, a_mask, t_mask, labels = synth.make_inputs(B, Ta, Tt, C, seed, True)
+    with RecordedDropout(seed) as rec:
+        a_seq = a_hid + m["adapter_a"](a_hid)
+        t_seq = t_hid + m["adapter_t"](t_hid)
+        a_enh, t_enh = m["cross"](a_seq, t_seq, a_mask, t_mask)
+        a_vec = m["pool_a"](a_enh, a_mask)
+        t_vec = m["pool_t"](t_enh, t_mask)
+        fused = m["fusion"](a_vec, t_vec)
+        logits, unc, anchor_loss = m["classifier"](fused, use_openmax=False, return_uncertainty=True)
+        ce = L["ce"](logits, labels)
+        focal = L["focal"](logits, labels)
+        unc_loss = torch.mean(unc * (labels == logits.argmax(dim=1)).float())
+        proto = m["prototypes"].prototype_loss(fused, labels)
+        loss = ce + 0.3 * focal + 0.1 * anchor_loss + 0.05 * unc_loss + 0.01 * proto
+        loss.backward()
+    names = dropout_site_names(num_layers)
+    tail = rec.calls[len(names):]
+    # what follows output_projection[3] is identified by shape: [B,128] anchor projection (discarded), [B,64] uncertainty head
+    tail_names = {128: "anchor (unused)", 64: "clf.unc"}
+    assert len(tail) == 2 and sorted(c[0][1] for c in tail) == [64, 128], [c[0] for c in tail]
+    names += [tail_names[c[0][1]] for c in tail]
+    assert len(names) == len(rec.calls)
+    masks = {}
+    for n, (shape, p, keep) in zip(names, rec.calls):
+        if n.startswith("cross.prob"):
+            keep = keep.view(B, 8, shape[1], shape[2])          # MHA flattens (batch, head) -> b * H + h
+        masks[n] = {"p": p, "keep": keep.to(torch.uint8)}
+        print(f"  dropout site {n:24s} shape {tuple(keep.shape)} p={p}")
+    grads = {}
+    for k, mod in m.items():
+        for pn, p in mod.named_parameters():
+            grads[f"{k}/{pn}"] = None if p.grad is None else summarize(p.grad, f"{k}/{pn}")
+    gold = {
+        "config": dict(B=B, Ta=Ta, Tt=Tt, C=C, seed=seed, with_masks=True, num_layers=num_layers),
+        "masks": masks,
+        "logits": logits.detach(), "unc": unc.detach(), "fused": fused.detach(),
+        "a_vec": a_vec.detach(), "t_vec": t_vec.detach(),
+        "a_enh_norm": a_enh.detach().double().norm().item(), "t_enh_norm": t_enh.detach().double().norm().item(),
+        "ce": ce.item(), "focal": focal.item(), "unc_loss": unc_loss.item(), "proto": proto.item(), "loss": loss.item(),
+        "grads": grads, "torch": torch.__version__,
+    }
+    torch.save(gold, os.path.join(OUT, f"{name}.pt"))
+    print(f"{name}: loss={loss.item():.6f} ({len(rec.calls)} dropout calls)")
+
+
 def run_eval_case(name, B, C, seed, views=5):
     """cfg5 semantics at small B: classifier eval path with fitted OpenMax + TTA mean + temperature + energy."""
     weights = synth.head_weights(C, 35, seed=0)
@@ -174,3 +265,4 @@ if __name__ == "__main__":
     run_train_case("train_nomask", B=4, Ta=33, Tt=9, C=4, seed=1238, with_masks=False)
     run_train_case("train_cfg4_long", B=2, Ta=300, Tt=96, C=4, seed=1239)
     run_eval_case("eval_cfg5_small", B=32, C=6, seed=1240)
+    run_train_dropout_case("dropout_train_small", B=4, Ta=40, Tt=17, C=4, seed=1241)

@@ -63,14 +63,16 @@ class Case:
     `cuda(inputs, dtype, device)` -> (dict of outputs, dict 'group/param' -> grad, dict input-name -> grad)."""
 
     def __init__(self, name: str, inputs: Dict[str, torch.Tensor], weights: Dict[str, Dict[str, torch.Tensor]],
-                 oracle: Callable, cuda: Callable, grad_inputs=()):
+                 oracle: Callable, cuda: Callable, grad_inputs=(), prepare: Optional[Callable] = None):
         self.name, self.inputs, self.weights, self.oracle, self.cuda, self.grad_inputs = \
             name, inputs, weights, oracle, cuda, tuple(grad_inputs)
+        # prepare(device) -> extra inputs that need the GPU library (the dropout masks the kernels will apply)
+        self.prepare = prepare
 
     def run_oracle(self, dtype, rounding=None):
         ins = {}
         for k, v in self.inputs.items():
-            if v is not None and v.is_floating_point():
+            if torch.is_tensor(v) and v.is_floating_point():
                 v = v.detach().clone().to(dtype)
                 if k in self.grad_inputs:
                     v.requires_grad_(True)
@@ -91,9 +93,11 @@ class Case:
         tol = TOL[dtype]
         # the bf16 tier feeds bf16-rounded activations; hand the oracle the same rounded inputs
         saved = self.inputs
+        if self.prepare is not None:
+            self.inputs = dict(saved, **self.prepare(device))
         if dtype != torch.float32:
-            self.inputs = {k: (v.to(dtype).float() if (v is not None and v.is_floating_point() and k not in ("a_mask", "t_mask", "mask"))
-                               else v) for k, v in saved.items()}
+            self.inputs = {k: (v.to(dtype).float() if (torch.is_tensor(v) and v.is_floating_point() and k not in ("a_mask", "t_mask", "mask"))
+                               else v) for k, v in self.inputs.items()}
         try:
             e_out, e_g, e_ig = self.run_oracle(torch.float64)
             r_out, r_g, r_ig = self.run_oracle(torch.float32, None if dtype == torch.float32 else dtype)
@@ -164,6 +168,45 @@ def _rand(shape, seed, scale=1.0):
     return torch.randn(*shape, generator=g) * scale
 
 
+# ---------------------------------------------------------------------------------------------------
+# dropout: the kernels' masks are a pure function of (seed, site, row, col) (csrc/dropout.cuh).  The tests pin the seed
+# of each module, export the masks through the C-ABI (ser_dropout_mask) and run the oracle with exactly those masks.
+DROP_SEEDS = {"cross": 0x1234567887654321, "fusion": 0x0BADC0FFEE123457, "classifier": 0x7EDCBA9876543210}
+
+
+def _seed_tensor(name, dev):
+    return torch.tensor([DROP_SEEDS[name]], dtype=torch.int64, device=dev)
+
+
+def _pin_seed(module, name, dev):
+    module._drop_seed.counter = _seed_tensor(name, dev)      # the next forward uses exactly this value
+
+
+def cross_masks(dev, p, B, H, Ta, Tt, D):
+    from mmser_b200.functional import dropout_mask as dm
+    s = _seed_tensor("cross", dev)
+    return {"cross.prob_a": dm(s, 1, p, B * H * Ta, Tt).view(B, H, Ta, Tt).cpu(),
+            "cross.prob_t": dm(s, 2, p, B * H * Tt, Ta).view(B, H, Tt, Ta).cpu(),
+            "cross.res_a": dm(s, 3, p, B * Ta, D).view(B, Ta, D).cpu(),
+            "cross.res_t": dm(s, 4, p, B * Tt, D).view(B, Tt, D).cpu()}
+
+
+def fusion_masks(dev, p, B, P=512):
+    from mmser_b200.functional import dropout_mask as dm
+    s = _seed_tensor("fusion", dev)
+    return {"fusion.a": dm(s, 5, p, B, P).cpu(), "fusion.t": dm(s, 6, p, B, P).cpu()}
+
+
+def classifier_masks(dev, p, B, L, P=512, F=256, U=64):
+    from mmser_b200.functional import dropout_mask as dm
+    s = _seed_tensor("classifier", dev)
+    out = {"clf.in": dm(s, 7, p, B, P).cpu(), "clf.out": dm(s, 8, p, B, F).cpu(), "clf.unc": dm(s, 9, p, B, U).cpu()}
+    for i in range(L):
+        out[f"clf.block{i}.hidden"] = dm(s, 16 + 2 * i, p, B, P).cpu()
+        out[f"clf.block{i}.out"] = dm(s, 16 + 2 * i + 1, p, B, P).cpu()
+    return out
+
+
 def adapter_case(B=3, T=37):
     import mmser_b200
     from mmser_b200 import models as M
@@ -184,7 +227,7 @@ def adapter_case(B=3, T=37):
     return Case("adapter", ins, w, oracle, cuda, grad_inputs=("x",))
 
 
-def cross_case(B=3, Ta=70, Tt=19, masks=True, seed=7):
+def cross_case(B=3, Ta=70, Tt=19, masks=True, seed=7, p_drop=0.0):
     from mmser_b200 import models as M
     w = {"cross": synth.cross_weights()}
     a, t, am, tm, _ = synth.make_inputs(B, Ta, Tt, 4, seed=seed, with_masks=masks)
@@ -193,11 +236,14 @@ def cross_case(B=3, Ta=70, Tt=19, masks=True, seed=7):
     def oracle(i, ws):
         am_ = None if i["a_mask"] is None else i["a_mask"].to(i["a"].dtype)
         tm_ = None if i["t_mask"] is None else i["t_mask"].to(i["a"].dtype)
-        ea, et = O.cross_attention(i["a"], i["t"], am_, tm_, ws["cross"])
+        with O.dropout_masks(i.get("_masks")):
+            ea, et = O.cross_attention(i["a"], i["t"], am_, tm_, ws["cross"])
         return {"audio_enh": ea, "text_enh": et}, (ea * i["ua"]).sum() + (et * i["ut"]).sum()
 
     def cuda(i, dtype, dev):
-        m = M.CrossModalAttention(768, 768, dropout=0.0).to(dev); m.load_state_dict(w["cross"])
+        m = M.CrossModalAttention(768, 768, dropout=p_drop).to(dev); m.load_state_dict(w["cross"])
+        m.train()
+        _pin_seed(m, "cross", dev)
         ag = i["a"].to(dev).to(dtype).requires_grad_(True)
         tg = i["t"].to(dev).to(dtype).requires_grad_(True)
         ea, et = m(ag, tg, None if i["a_mask"] is None else i["a_mask"].to(dev),
@@ -205,7 +251,9 @@ def cross_case(B=3, Ta=70, Tt=19, masks=True, seed=7):
         ((ea.float() * i["ua"].to(dev)).sum() + (et.float() * i["ut"].to(dev)).sum()).backward()
         return {"audio_enh": ea, "text_enh": et}, _param_grads("cross", m), {"a": ag.grad, "t": tg.grad}
 
-    return Case(f"cross{'_masked' if masks else '_nomask'}", ins, w, oracle, cuda, grad_inputs=("a", "t"))
+    prep = (lambda dev: {"_masks": cross_masks(dev, p_drop, B, 8, Ta, Tt, 768)}) if p_drop > 0 else None
+    return Case(f"cross{'_masked' if masks else '_nomask'}{'_dropout' if p_drop > 0 else ''}", ins, w, oracle, cuda,
+                grad_inputs=("a", "t"), prepare=prep)
 
 
 def pool_case(B=4, T=53, masks=True):
@@ -229,46 +277,55 @@ def pool_case(B=4, T=53, masks=True):
     return Case("pool", ins, w, oracle, cuda, grad_inputs=("x",))
 
 
-def fusion_case(B=9):
+def fusion_case(B=9, p_drop=0.0):
     from mmser_b200 import models as M
     w = {"fusion": synth.fusion_weights()}
     ins = {"av": _rand((B, 1536), 6), "tv": _rand((B, 1536), 7), "up": _rand((B, 512), 8)}
 
     def oracle(i, ws):
-        y = O.fusion(i["av"], i["tv"], ws["fusion"])
+        with O.dropout_masks(i.get("_masks")):
+            y = O.fusion(i["av"], i["tv"], ws["fusion"])
         return {"fused": y}, (y * i["up"]).sum()
 
     def cuda(i, dtype, dev):
-        m = M.FusionLayer(1536, 1536, 512).to(dev).eval(); m.load_state_dict(w["fusion"])
+        m = M.FusionLayer(1536, 1536, 512).to(dev); m.load_state_dict(w["fusion"])
+        m.proj_a[2].p = m.proj_t[2].p = p_drop
+        m.train()
+        _pin_seed(m, "fusion", dev)
         av = i["av"].to(dev).to(dtype).requires_grad_(True)
         tv = i["tv"].to(dev).to(dtype).requires_grad_(True)
         y = m(av, tv)
         (y.float() * i["up"].to(dev)).sum().backward()
         return {"fused": y}, _param_grads("fusion", m), {"av": av.grad, "tv": tv.grad}
 
-    return Case("fusion", ins, w, oracle, cuda, grad_inputs=("av", "tv"))
+    prep = (lambda dev: {"_masks": fusion_masks(dev, p_drop, B)}) if p_drop > 0 else None
+    return Case("fusion_dropout" if p_drop > 0 else "fusion", ins, w, oracle, cuda, grad_inputs=("av", "tv"), prepare=prep)
 
 
-def classifier_case(B=64, C=4, L=35):
+def classifier_case(B=64, C=4, L=35, p_drop=0.0):
     from mmser_b200 import models as M
     w = {"classifier": synth.classifier_weights(C, L)}
     ins = {"x": _rand((B, 512), 10), "ul": _rand((B, C), 11), "uu": _rand((B, 1), 12)}
 
     def oracle(i, ws):
-        lg, un, _ = O.classifier(i["x"], ws["classifier"], L, use_openmax=False, training=True, return_uncertainty=True)
-        f = O.classifier_features(i["x"], ws["classifier"], L)
+        with O.dropout_masks(i.get("_masks")):
+            lg, un, _ = O.classifier(i["x"], ws["classifier"], L, use_openmax=False, training=True, return_uncertainty=True)
+            f = O.classifier_features(i["x"], ws["classifier"], L)
         return {"logits": lg, "unc": un, "features": f}, (lg * i["ul"]).sum() + (un * i["uu"]).sum()
 
     def cuda(i, dtype, dev):
-        m = M.AdvancedOpenMaxClassifier(512, C, num_layers=L, dropout=0.0).to(dev); m.load_state_dict(w["classifier"])
+        m = M.AdvancedOpenMaxClassifier(512, C, num_layers=L, dropout=p_drop).to(dev); m.load_state_dict(w["classifier"])
         m.train()
+        _pin_seed(m, "classifier", dev)
         x = i["x"].to(dev).to(dtype).requires_grad_(True)
         lg, un, al = m(x, use_openmax=False, return_uncertainty=True)
         assert float(al) == 0.0
         ((lg * i["ul"].to(dev)).sum() + (un * i["uu"].to(dev)).sum()).backward()
         return {"logits": lg, "unc": un, "features": m.last_features}, _param_grads("classifier", m), {"x": x.grad}
 
-    return Case("classifier" if B == 64 else f"classifier_B{B}", ins, w, oracle, cuda, grad_inputs=("x",))
+    prep = (lambda dev: {"_masks": classifier_masks(dev, p_drop, B, L)}) if p_drop > 0 else None
+    return Case(("classifier" if B == 64 else f"classifier_B{B}") + ("_dropout" if p_drop > 0 else ""), ins, w, oracle,
+                cuda, grad_inputs=("x",), prepare=prep)
 
 
 def loss_case(B=37, C=6):
@@ -299,7 +356,7 @@ def loss_case(B=37, C=6):
     return Case("loss", ins, w, oracle, cuda, grad_inputs=("logits", "unc", "emb"))
 
 
-def head_case(B=4, Ta=50, Tt=16, C=4, masks=True, seed=1234, L=35):
+def head_case(B=4, Ta=50, Tt=16, C=4, masks=True, seed=1234, L=35, p_drop=0.0):
     import mmser_b200
     w = synth.head_weights(C, L)
     a, t, am, tm, labels = synth.make_inputs(B, Ta, Tt, C, seed=seed, with_masks=masks)
@@ -309,11 +366,15 @@ def head_case(B=4, Ta=50, Tt=16, C=4, masks=True, seed=1234, L=35):
     def oracle(i, ws):
         am_ = None if i["a_mask"] is None else i["a_mask"].to(i["a"].dtype)
         tm_ = None if i["t_mask"] is None else i["t_mask"].to(i["a"].dtype)
-        out = O.head_forward(i["a"], i["t"], am_, tm_, i["labels"], ws, C, L)
+        with O.dropout_masks(i.get("_masks")):
+            out = O.head_forward(i["a"], i["t"], am_, tm_, i["labels"], ws, C, L)
         return {k: out[k] for k in keys}, out["loss"]
 
     def cuda(i, dtype, dev):
-        head = mmser_b200.FusionHead(C, num_layers=L).to(dev); head.load_group_state(w)
+        head = mmser_b200.FusionHead(C, num_layers=L, dropout=p_drop).to(dev); head.load_group_state(w)
+        head.train()
+        for grp in ("cross", "fusion", "classifier"):
+            _pin_seed(getattr(head, grp), grp, dev)
         out = head(i["a"].to(dev).to(dtype), i["t"].to(dev).to(dtype),
                    None if i["a_mask"] is None else i["a_mask"].to(dev),
                    None if i["t_mask"] is None else i["t_mask"].to(dev), i["labels"].to(dev))
@@ -323,7 +384,14 @@ def head_case(B=4, Ta=50, Tt=16, C=4, masks=True, seed=1234, L=35):
             grads.update(_param_grads(grp, getattr(head, grp)))
         return {k: out[k] for k in keys}, grads, {}
 
-    return Case(f"head_B{B}_Ta{Ta}_Tt{Tt}_C{C}{'' if masks else '_nomask'}", ins, w, oracle, cuda)
+    def prep(dev):
+        m = cross_masks(dev, p_drop, B, 8, Ta, Tt, 768)
+        m.update(fusion_masks(dev, p_drop, B))
+        m.update(classifier_masks(dev, p_drop, B, L))
+        return {"_masks": m}
+
+    return Case(f"head_B{B}_Ta{Ta}_Tt{Tt}_C{C}{'' if masks else '_nomask'}{'_dropout' if p_drop > 0 else ''}", ins, w, oracle,
+                cuda, prepare=prep if p_drop > 0 else None)
 
 
 ALL_CASES = {
@@ -343,4 +411,10 @@ ALL_CASES = {
     #  ReLU / argmax flips are O(1/B) -- and the comparison degenerates into noise against noise)
     "head_c6_nomask": lambda: head_case(24, 33, 9, 6, False),
     "head_b48": lambda: head_case(48, 60, 20, 4, True),
+    # training mode with dropout active: the oracle is driven by the masks the kernels export (odd Tt: ragged mask pairs)
+    "cross_dropout": lambda: cross_case(masks=True, p_drop=0.1),
+    "cross_long_dropout": lambda: cross_case(B=2, Ta=300, Tt=130, masks=True, seed=11, p_drop=0.25),
+    "fusion_dropout": lambda: fusion_case(p_drop=0.1),
+    "classifier_dropout": lambda: classifier_case(p_drop=0.15),
+    "head_dropout": lambda: head_case(24, 50, 16, 4, True, p_drop=0.1),
 }

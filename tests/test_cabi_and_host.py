@@ -105,11 +105,20 @@ def test_no_cpu_fallback(lib):
         lib.gemm(torch.randn(4, 8), torch.randn(4, 8))
 
 
-def test_dropout_in_training_mode_is_rejected_not_ignored(lib):
+def test_dropout_is_active_only_in_training_mode(lib):
+    """nn.Dropout semantics of the drop-in modules: p > 0 takes effect in train() only, and never silently on CPU."""
     import mmser_b200
-    m = mmser_b200.models.CrossModalAttention(768, 768, dropout=0.1).train()
-    with pytest.raises(NotImplementedError):
-        m(torch.randn(1, 2, 768), torch.randn(1, 2, 768))
+    from mmser_b200.models._common import DropoutSeed, active_dropout
+    m = mmser_b200.models.CrossModalAttention(768, 768, dropout=0.1)
+    assert active_dropout(m.train(), m.dropout.p) == pytest.approx(0.1)
+    assert active_dropout(m.eval(), m.dropout.p) == 0.0
+    with pytest.raises(lib.SerError):            # CPU tensors: no fallback, dropout or not
+        m.train()(torch.randn(1, 2, 768), torch.randn(1, 2, 768))
+    assert DropoutSeed().counter is None         # the seed is drawn lazily, on the first training forward
+    f = mmser_b200.models.FusionLayer(1536, 1536, 512).train()
+    f.proj_a[2].p = 0.3                          # the fused kernel has one rate for both branches
+    with pytest.raises(lib.SerError):
+        f(torch.randn(2, 1536), torch.randn(2, 1536))
 
 
 def test_global_batch_loss_algebra():

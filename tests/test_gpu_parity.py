@@ -25,6 +25,62 @@ def test_parity(case, dtype):
     assert not fails, f"{case}/{dtype}: {len(fails)} tensors out of tolerance, e.g. {fails[:5]}"
 
 
+def test_dropout_mask_statistics_and_determinism():
+    """The counter-based masks: keep rate = 1 - p, multiplier 1/(1-p), neighbouring draws uncorrelated, different
+    sites / seeds give unrelated masks, the same (seed, site) always gives the same mask."""
+    from mmser_b200.functional import dropout_mask as dm
+    dev = _dev()
+    s1 = torch.tensor([0x1234567887654321], dtype=torch.int64, device=dev)
+    s2 = s1 + 1
+    for p in (0.1, 0.15, 0.5):
+        m = dm(s1, 3, p, 4096, 768)
+        keep = (m > 0).float()
+        n = keep.numel()
+        assert abs(keep.mean().item() - (1 - p)) < 4 * (p * (1 - p) / n) ** 0.5 + 2e-5      # 4 sigma + 16-bit rounding of p
+        assert torch.allclose(m[m > 0], torch.tensor(1 / (1 - p), device=dev))
+        # the two halves of a 32-bit draw, neighbouring pairs, neighbouring rows: correlations within 5 sigma of 0
+        k = keep - keep.mean()
+        var = (k * k).mean()
+        for a, b in ((k[:, 0::2], k[:, 1::2]), (k[:, :-2], k[:, 2:]), (k[:-1], k[1:])):
+            assert abs(((a * b).mean() / var).item()) < 5 / (a.numel() ** 0.5)
+        assert torch.equal(m, dm(s1, 3, p, 4096, 768))
+        for other in (dm(s1, 4, p, 4096, 768), dm(s2, 3, p, 4096, 768)):
+            k2 = (other > 0).float() - keep.mean()
+            assert abs(((k * k2).mean() / var).item()) < 5 / (n ** 0.5)
+    # odd column count (attention weights with odd Tk): rows do not share pairs
+    m = dm(s1, 1, 0.25, 1000, 33)
+    assert abs((m > 0).float().mean().item() - 0.75) < 0.02
+    assert dm(s1, 1, 0.0, 4, 6).eq(1).all()
+
+
+def test_dropout_train_eval_and_reseeding():
+    """eval() switches dropout off (bit-identical to p = 0); in train() two consecutive steps draw different masks,
+    torch.manual_seed makes a run reproducible, and forward / backward of one step agree on the mask (checked by the
+    parity cases) -- here: gradient flows only through kept units of fusion.proj_*[0]."""
+    import mmser_b200
+    from oracle import synth
+    dev = _dev()
+    C = 4
+    w = synth.head_weights(C)
+    a, t, am, tm, labels = synth.make_inputs(8, 40, 12, C, seed=5)
+    args = (a.to(dev), t.to(dev), am.to(dev), tm.to(dev), labels.to(dev))
+
+    def build(p):
+        torch.manual_seed(1234)
+        h = mmser_b200.FusionHead(C, dropout=p).to(dev); h.load_group_state(w)
+        return h
+
+    ref = build(0.0)(*args)["logits"]
+    hd = build(0.2)
+    assert torch.equal(hd.eval()(*args)["logits"], ref)           # eval: dropout off, bit-identical
+    hd.train()
+    l1 = hd(*args)["logits"]; l2 = hd(*args)["logits"]
+    assert not torch.equal(l1, ref) and not torch.equal(l1, l2)   # active, and re-drawn every step
+    hd2 = build(0.2).train()
+    assert torch.equal(hd2(*args)["logits"], l1)                  # same torch seed + same module order -> same masks
+    assert torch.equal(hd2(*args)["logits"], l2)
+
+
 def test_argmax_bit_exact_and_anchor_zero():
     """Predictions (argmax of logits) are bit-identical to the oracle; anchor loss is exactly 0 with zero grads."""
     import mmser_b200

@@ -22,6 +22,31 @@ def _train_cases(golden_dir=None):
     return sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(root, "train_*.pt")))
 
 
+def _check_grads(gold, weights):
+    checked = 0
+    for key, summ in gold["grads"].items():
+        grp, name = key.split("/", 1)
+        g = weights[grp][name].grad
+        if summ is None:                      # anchor temperature: reference leaves .grad = None
+            assert g is None or float(g.abs().max()) == 0.0, key
+            continue
+        assert g is not None, key
+        scale = summ["norm"] / max(1.0, g.numel() ** 0.5) + 1e-12
+        if summ["norm"] == 0.0:               # anchor parameters: exactly-zero gradients
+            assert float(g.abs().max()) == 0.0, key
+            continue
+        if summ["norm"] < 1e-6:               # mathematically zero (e.g. MHA key bias): rounding noise only
+            assert g.double().norm().item() < 1e-5, key
+            continue
+        assert abs(g.double().norm().item() - summ["norm"]) <= 5 * TOL * summ["norm"], key
+        probe = g.reshape(-1)[summ["idx"]]
+        assert (probe.double() - summ["vals"].double()).abs().max().item() <= 50 * TOL * max(scale, summ["vals"].abs().max().item()), key
+        if "full" in summ:
+            assert rel(g, summ["full"]) < 10 * TOL, key
+        checked += 1
+    return checked
+
+
 @pytest.mark.parametrize("case", _train_cases())
 def test_oracle_matches_reference_train(case, golden_dir):
     gold = torch.load(os.path.join(golden_dir, f"{case}.pt"), weights_only=False)
@@ -46,28 +71,39 @@ def test_oracle_matches_reference_train(case, golden_dir):
     # bit-exact argmax
     assert torch.equal(out["logits"].argmax(1), gold["logits"].argmax(1))
 
-    checked = 0
-    for key, summ in gold["grads"].items():
-        grp, name = key.split("/", 1)
-        g = weights[grp][name].grad
-        if summ is None:                      # anchor temperature: reference leaves .grad = None
-            assert g is None or float(g.abs().max()) == 0.0, key
-            continue
-        assert g is not None, key
-        scale = summ["norm"] / max(1.0, g.numel() ** 0.5) + 1e-12
-        if summ["norm"] == 0.0:               # anchor parameters: exactly-zero gradients
-            assert float(g.abs().max()) == 0.0, key
-            continue
-        if summ["norm"] < 1e-6:               # mathematically zero (e.g. MHA key bias): rounding noise only
-            assert g.double().norm().item() < 1e-5, key
-            continue
-        assert abs(g.double().norm().item() - summ["norm"]) <= 5 * TOL * summ["norm"], key
-        probe = g.reshape(-1)[summ["idx"]]
-        assert (probe.double() - summ["vals"].double()).abs().max().item() <= 50 * TOL * max(scale, summ["vals"].abs().max().item()), key
-        if "full" in summ:
-            assert rel(g, summ["full"]) < 10 * TOL, key
-        checked += 1
-    assert checked > 300
+    assert _check_grads(gold, weights) > 300
+
+
+def test_oracle_matches_reference_train_dropout(golden_dir):
+    """Training mode with every dropout ACTIVE: the fixture holds the keep masks the reference drew (recorded through a
+    patched torch.nn.functional.dropout, oracle/make_golden.py); the oracle, given the same masks at its named sites,
+    must reproduce outputs and gradients -- this pins WHERE each dropout acts (attention weights after the softmax,
+    branch output before the residual add, post-ReLU hidden units, post-dropout features feeding both heads)."""
+    gold = torch.load(os.path.join(golden_dir, "dropout_train_small.pt"), weights_only=False)
+    cfg = gold["config"]
+    weights = synth.head_weights(cfg["C"], cfg["num_layers"], seed=0)
+    for grp in weights.values():
+        for k, v in grp.items():
+            if v.is_floating_point() and k not in synth.CLASSIFIER_BUFFERS:
+                v.requires_grad_(True)
+    a, t, am, tm, labels = synth.make_inputs(cfg["B"], cfg["Ta"], cfg["Tt"], cfg["C"], cfg["seed"], cfg["with_masks"])
+    masks = {k: v["keep"].float() / (1.0 - v["p"]) for k, v in gold["masks"].items()}
+    assert len(masks) == 4 + 2 + 1 + 2 * cfg["num_layers"] + 1 + 2
+    with O.dropout_masks(masks):
+        out = O.head_forward(a, t, am, tm, labels, weights, cfg["C"], cfg["num_layers"])
+        out["loss"].backward()
+    for k in ("logits", "unc", "fused", "a_vec", "t_vec"):
+        assert rel(out[k], gold[k]) < TOL, k
+    assert abs(out["a_enh"].double().norm().item() - gold["a_enh_norm"]) / gold["a_enh_norm"] < TOL
+    assert abs(out["t_enh"].double().norm().item() - gold["t_enh_norm"]) / gold["t_enh_norm"] < TOL
+    for k in ("ce", "focal", "unc_loss", "proto", "loss"):
+        assert abs(out[k].item() - gold[k]) <= TOL * max(1.0, abs(gold[k])), k
+    assert torch.equal(out["logits"].argmax(1), gold["logits"].argmax(1))
+    assert _check_grads(gold, weights) > 300
+    # and the masks matter: without them the same inputs give a different loss
+    with torch.no_grad():
+        plain = O.head_forward(a, t, am, tm, labels, weights, cfg["C"], cfg["num_layers"])
+    assert abs(plain["loss"].item() - gold["loss"]) > 1e-3
 
 
 def test_oracle_matches_reference_eval(golden_dir):
