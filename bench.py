@@ -112,7 +112,13 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU path
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_run(wl, steps, warmup, sample_B):
+def parse_dropout(text):
+    """--dropout: 'reference' (the rates of the reference's training script) or one rate for every nn.Dropout."""
+    from mmser_b200.head import dropout_rates
+    return dropout_rates("reference" if text == "reference" else float(text))
+
+
+def cpu_reference_run(wl, steps, warmup, sample_B, rates=None):
     from oracle import fusion_head_oracle as O
     from oracle import synth
     torch.set_num_threads(os.cpu_count() or 1)
@@ -128,9 +134,13 @@ def cpu_reference_run(wl, steps, warmup, sample_B):
         for grp in w.values():
             for v in grp.values():
                 v.grad = None
-        out = O.head_forward(a, t, am, tm, labels, w, C)
+        # training-mode dropout like the reference's nn.Dropout layers: fresh Bernoulli masks every step
+        src = O.random_dropout({"cross": rates["cross"], "fusion": rates["fusion"], "clf": rates["classifier"]}) \
+            if rates and any(v > 0 for v in rates.values()) else None
+        with O.dropout_masks(src):
+            out = O.head_forward(a, t, am, tm, labels, w, C)
         out["loss"].backward()
-        return float(out["loss"])
+        return float(out["loss"].detach())
 
     for _ in range(warmup):
         step()
@@ -149,12 +159,13 @@ def run_reference(args, wl):
         return
     sample_B = min(wl["B"], 32)
     steps = max(1, min(args.steps, 8))
-    r = cpu_reference_run(wl, steps, max(1, min(args.warmup, 2)), sample_B)
+    rates = parse_dropout(args.dropout)
+    r = cpu_reference_run(wl, steps, max(1, min(args.warmup, 2)), sample_B, rates)
     line = {
         "impl": "reference", "metric": "fusion_head_train_samples_per_sec", "value": r["value"], "unit": "samples/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "shape": wl["desc"], "sample_batch": sample_B},
+        "config": {"workload": args.workload, "shape": wl["desc"], "sample_batch": sample_B, "dropout": rates},
         "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -192,7 +203,8 @@ def run_ours(args, wl):
     B, Ta, Tt, C = wl["B"], wl["Ta"], wl["Tt"], wl["C"]
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
 
-    head = mmser_b200.FusionHead(C, dropout=0.0).to(dev)
+    rates = parse_dropout(args.dropout)
+    head = mmser_b200.FusionHead(C, dropout=rates).to(dev)
     head.load_group_state(synth.head_weights(C))
     head.train()
     dp = DataParallelHead(head)
@@ -294,6 +306,23 @@ def run_ours(args, wl):
     ms_e2e = timed(e2e_step, max(3, args.steps // 2))
 
     stage(f"e2e timing done: {ms_e2e:.3f} ms/step")
+    # ---------------- the same step with every dropout rate set to 0 (reported beside the headline) ----------------
+    ms_nodrop = None
+    if any(v > 0 for v in rates.values()):
+        head.set_dropout(0.0)
+        g0 = None
+        if graphed is not None:
+            try:
+                g0 = GraphedTrainStep(dp, devin["a"], devin["t"], devin["am"], devin["tm"], devin["labels"])
+            except Exception:  # noqa: BLE001
+                g0 = None
+        step0 = (lambda: g0.replay()) if g0 is not None else (lambda: eager_step(devin))
+        for _ in range(3):
+            step0()
+        ms_nodrop = timed(step0, args.steps)
+        head.set_dropout(rates)
+        del g0
+        stage(f"no-dropout timing done: {ms_nodrop:.3f} ms/step")
     # ---------------- per-kernel-family profile (CUDA events around every launch; separate pass) ----------------
     prof = {}
     nprof = 3
@@ -323,7 +352,7 @@ def run_ours(args, wl):
     # ---------------- cpu baseline (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(WORKLOADS["cfg1"] | {"C": C}, steps=6, warmup=1, sample_B=8)
+        r = cpu_reference_run(WORKLOADS["cfg1"] | {"C": C}, steps=6, warmup=1, sample_B=8, rates=rates)
         cpu = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     def finish():
@@ -377,11 +406,13 @@ def run_ours(args, wl):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": args.workload, "shape": wl["desc"], "global_batch": total_B, "per_gpu_batch": B,
-                   "parallelism": f"dp{world}", "dropout": 0.0, "cuda_graph": graphed is not None,
+                   "parallelism": f"dp{world}", "dropout": rates, "cuda_graph": graphed is not None,
                    "l2": "no explicit flush: one step touches > 2 GB of activations per GPU, far above the 126 MB L2"},
         "step_model_flops_per_gpu": step_flops,
         "model_tflops_per_gpu": step_flops / (ms * 1e-3) / 1e12,
         "model_frac_of_sustained_bf16_peak": step_flops / (ms * 1e-3) / 1e12 / peaks["tf_sus"],
+        "no_dropout": None if ms_nodrop is None else {"value": total_B / (ms_nodrop * 1e-3), "unit": "samples/s",
+                                                      "ms_per_step": ms_nodrop},
         "roofline": roof, "kernel_families": families,
         "cpu_baseline": cpu,
         "e2e": {"value": total_B / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e,
@@ -399,6 +430,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--dropout", default="reference",
+                    help="'reference' = the rates of the reference's training script (cross 0.1, fusion 0.1, classifier 0.15; "
+                         "SURVEY.md 8(d)); or one rate for every nn.Dropout of the head, e.g. 0")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])

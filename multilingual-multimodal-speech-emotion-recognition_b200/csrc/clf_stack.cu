@@ -380,7 +380,21 @@ struct StackParams {
   const float* dh_in; float* dh_out;       // [B, 512] fp32: dL/dh_L in, dL/dh_0 out
   __nv_bfloat16* dhn; __nv_bfloat16* dr;   // [L, B, 512] exchange + weight-gradient operands
   float* dlni_g; float* dlni_b; float* dlno_g; float* dlno_b;    // layer 0 pointers (strides as the parameters)
+  DropSpec drop;                           // block[3] / block[5] dropout (site = DS_CLF_BLOCK0 + 2 layer + {0, 1}); off by default
 };
+
+// multiply the thread's 64-column slice of row `row` by the dropout mask of `site` ([B, 512] site: 256 pairs per row)
+__device__ __forceinline__ void drop_slice(const DropSpec& base, unsigned site, int row, int col0, float (&v)[NS]) {
+  DropSpec d = base;
+  d.site = site;
+  const DropKey key = drop_key(d);
+  const unsigned pair0 = static_cast<unsigned>(row) * (PD / 2) + static_cast<unsigned>(col0 >> 1);
+#pragma unroll
+  for (int k = 0; k < NS / 2; ++k) {
+    const float2 m = drop_pair(key, pair0 + k, d.thr, d.scale);
+    v[2 * k] *= m.x; v[2 * k + 1] *= m.y;
+  }
+}
 
 __device__ __forceinline__ void par_prefetch(const Ctx& c, const StackParams& p, int layer, int buf, int et, int col0, bool on) {
   if (on && et < p.npv * 16) {
@@ -441,6 +455,7 @@ __device__ __forceinline__ void teardown(const Ctx& c, int warp) {
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
+template <bool DROP>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kThreads, 1)
 clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                      const __grid_constant__ CUtensorMap tmN, const __grid_constant__ CUtensorMap tmR,
@@ -539,6 +554,7 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       lds_vec(par_addr(c, pb, 4), par, NS);
 #pragma unroll
       for (int k = 0; k < NS; ++k) nv[k] = fmaxf(nv[k] + par[k], 0.f);
+      if (DROP) drop_slice(p.drop, DS_CLF_BLOCK0 + 2 * i, row, col0, nv);       // block[3]; r is saved post-dropout
       publish_slice(c, nv, rl, active, et, xchg_block(c, p.xchg, 2 * i + 1), &tmR, col0, i);
       tc_fence_before();
       SER_TL(6);
@@ -551,8 +567,16 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       tmem_ld32(taddr, nv);
       tmem_ld32(taddr + 32, nv + 32);
       lds_vec(par_addr(c, pb, 5), par, NS);
+      if (DROP) {                                                              // block[5]: y + dropout(W2 u + b2)
 #pragma unroll
-      for (int k = 0; k < NS; ++k) hv[k] += nv[k] + par[k];
+        for (int k = 0; k < NS; ++k) nv[k] += par[k];
+        drop_slice(p.drop, DS_CLF_BLOCK0 + 2 * i + 1, row, col0, nv);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) hv[k] += nv[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) hv[k] += nv[k] + par[k];
+      }
       store_slice_f32(c, hv, rl, active, et, &tmH, col0, i + 1);
       tc_fence_before();
       SER_TL(9);
@@ -584,6 +608,7 @@ __device__ __forceinline__ void colacc_add(const Ctx& c, int which, int col, flo
   asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(c.sColacc + static_cast<uint32_t>((which * NS + col) * 4)), "f"(v) : "memory");
 }
 
+template <bool DROP>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kThreads, 1)
 clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                      const __grid_constant__ CUtensorMap tmDhn, const __grid_constant__ CUtensorMap tmDr,
@@ -649,7 +674,16 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       par_advance(c, p, i - 1, i > 0, pb ^ 1, et, col0);
       SER_TL(16);
       // ---- publish dh_{i+1} (bf16): A operand of du = dh W2 and of the batched dW2 GEMM
-      publish_slice(c, gv, rl, active, et, xchg_block(c, p.xchg, 2 * (L - 1 - i)), &tmDhn, col0, i);
+      if (DROP) {
+        // block[5]: the branch (GEMM operand and the saved dW2 / db2 operand) sees mask * dh; gv keeps the skip path
+        float gm[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) gm[k] = gv[k];
+        drop_slice(p.drop, DS_CLF_BLOCK0 + 2 * i + 1, row, col0, gm);
+        publish_slice(c, gm, rl, active, et, xchg_block(c, p.xchg, 2 * (L - 1 - i)), &tmDhn, col0, i);
+      } else {
+        publish_slice(c, gv, rl, active, et, xchg_block(c, p.xchg, 2 * (L - 1 - i)), &tmDhn, col0, i);
+      }
       tc_fence_before();
       SER_TL(17);
       cluster_sync_all();
@@ -689,6 +723,10 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
             if ((wds[t] & 0x00007fffu) == 0u) du[8 * k + 2 * t] = 0.f;
             if ((wds[t] & 0x7fff0000u) == 0u) du[8 * k + 2 * t + 1] = 0.f;
           }
+        }
+        if (DROP) {          // block[3]: r is saved post-dropout, so the test above is also the keep mask; kept units carry 1/(1-p)
+#pragma unroll
+          for (int k = 0; k < NS; ++k) du[k] *= p.drop.scale;
         }
         publish_slice(c, du, rl, active, et, xchg_block(c, p.xchg, 2 * (L - 1 - i) + 1), &tmDr, col0, i);
       }
@@ -897,6 +935,7 @@ static StackParams to_params(const ClfStackArgs& a, bool backward) {
   p.npv = backward ? 3 : 6;
   p.dbg = timeline_buffer();
   p.xchg = reinterpret_cast<char*>(a.xchg);
+  p.drop = a.drop;
   return p;
 }
 
@@ -920,7 +959,11 @@ static void timeline_report(const char* what, cudaStream_t s) {
 
 int clf_stack_fwd(const ClfStackArgs& a, cudaStream_t s) {
   static bool configured = false;
-  if (!configured) { SER_TRY(configure(clf_stack_fwd_kernel)); configured = true; }
+  if (!configured) {
+    SER_TRY(configure(clf_stack_fwd_kernel<false>));
+    SER_TRY(configure(clf_stack_fwd_kernel<true>));
+    configured = true;
+  }
   CUtensorMap tmW1, tmW2, tmN, tmR, tmH;
   SER_TRY(make_map(&tmW1, a.w1, PD, a.s_w1, a.L, NS));
   SER_TRY(make_map(&tmW2, a.w2, PD, a.s_w2, a.L, NS));
@@ -932,7 +975,8 @@ int clf_stack_fwd(const ClfStackArgs& a, cudaStream_t s) {
   // algorithmic work: 2 GEMMs per block; bytes: weights once per cluster + the fp32 stream and bf16 operands
   ProfScope prof("clf_stack_fwd", 4.0 * a.B * PD * PD * a.L,
                  static_cast<double>(a.L) * (2.0 * PD * PD * 2 * clusters + a.B * PD * (4.0 + 2.0 + 2.0)), s);
-  clf_stack_fwd_kernel<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmN, tmR, tmH, to_params(a, false));
+  auto* kern = a.drop.on() ? clf_stack_fwd_kernel<true> : clf_stack_fwd_kernel<false>;
+  kern<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmN, tmR, tmH, to_params(a, false));
   SER_LAUNCH_CHECK();
   timeline_report("fwd", s);
   return SER_OK;
@@ -940,7 +984,11 @@ int clf_stack_fwd(const ClfStackArgs& a, cudaStream_t s) {
 
 int clf_stack_bwd(const ClfStackArgs& a, cudaStream_t s) {
   static bool configured = false;
-  if (!configured) { SER_TRY(configure(clf_stack_bwd_kernel)); configured = true; }
+  if (!configured) {
+    SER_TRY(configure(clf_stack_bwd_kernel<false>));
+    SER_TRY(configure(clf_stack_bwd_kernel<true>));
+    configured = true;
+  }
   CUtensorMap tmW1, tmW2, tmDhn, tmDr;
   SER_TRY(make_map(&tmW1, a.w1, PD, a.s_w1, a.L, 64));
   SER_TRY(make_map(&tmW2, a.w2, PD, a.s_w2, a.L, 64));
@@ -950,7 +998,8 @@ int clf_stack_bwd(const ClfStackArgs& a, cudaStream_t s) {
   const int clusters = ceil_div(a.B, rm);
   ProfScope prof("clf_stack_bwd", 4.0 * a.B * PD * PD * a.L,
                  static_cast<double>(a.L) * (2.0 * PD * PD * 2 * clusters + a.B * PD * (4.0 + 2.0 + 2.0 + 2.0)), s);
-  clf_stack_bwd_kernel<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmDhn, tmDr, to_params(a, true));
+  auto* kern = a.drop.on() ? clf_stack_bwd_kernel<true> : clf_stack_bwd_kernel<false>;
+  kern<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmDhn, tmDr, to_params(a, true));
   SER_LAUNCH_CHECK();
   timeline_report("bwd", s);
   return SER_OK;

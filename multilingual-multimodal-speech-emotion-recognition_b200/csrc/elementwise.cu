@@ -106,14 +106,20 @@ colsum_vec_kernel(const void* __restrict__ X0, int x_f32, long long ld, int M, i
   }
 }
 
+template <bool RES>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const void* __restrict__ x, int x_f32, void* __restrict__ y, int y_f32, void* __restrict__ y2,
               int y2_f32, const float* __restrict__ gamma, const float* __restrict__ beta,
-              float* __restrict__ stats, int M, int N, int relu) {
+              float* __restrict__ stats, int M, int N, int relu, const void* __restrict__ res, void* xout,
+              DropSpec drop) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int nch = (N + 255) >> 8;
   const float invN = 1.f / static_cast<float>(N);
+  // optional prologue (res != NULL): the row that is normalised is res + dropout(x), also written to xout
+  // (norm_a(audio_seq + self.dropout(a_out)), cross_attention.py:43) -- x, res and xout share x's dtype
+  DropKey dkey{0u, 1u};
+  if (RES && drop.on()) dkey = drop_key(drop);
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < M; row += gridDim.x * warps_per_block) {
     float v[kMaxChunks][8];
     float s = 0.f;
@@ -122,6 +128,25 @@ ln_fwd_kernel(const void* __restrict__ x, int x_f32, void* __restrict__ y, int y
       const int col = c * 256 + lane * 8;
       if (c < nch && col < N) {
         load8_dyn(x, static_cast<size_t>(row) * N + col, x_f32, v[c]);
+        if (RES) {
+          float r[8];
+          load8_dyn(res, static_cast<size_t>(row) * N + col, x_f32, r);
+          if (drop.on()) {
+            const unsigned pair0 = static_cast<unsigned>(row) * static_cast<unsigned>(N >> 1) + static_cast<unsigned>(col >> 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 m = drop_pair(dkey, pair0 + k, drop.thr, drop.scale);
+              v[c][2 * k] *= m.x; v[c][2 * k + 1] *= m.y;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[c][i] += r[i];
+          store8_dyn(xout, static_cast<size_t>(row) * N + col, x_f32, v[c]);
+          if (!x_f32) {                    // the saved row is bf16: normalise exactly what the backward will read
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[c][i] = __bfloat162float(__float2bfloat16_rn(v[c][i]));
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += v[c][i];
       } else {
@@ -569,21 +594,39 @@ static int ln_grid(int M) {
 }
 
 int layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, void* y2, int y2_f32, const float* gamma,
-                  const float* beta, float* stats, int M, int N, int relu, cudaStream_t s) {
+                  const float* beta, float* stats, int M, int N, int relu, cudaStream_t s, const void* res, void* xout,
+                  const DropSpec* drop) {
   SER_REQUIRE(N % 8 == 0 && N <= kMaxChunks * 256, "layernorm: N must be a multiple of 8 and <= 1024");
+  SER_REQUIRE((res == nullptr) == (xout == nullptr), "layernorm_fwd: res and xout go together");
+  SER_REQUIRE(res == nullptr || static_cast<long long>(M) * (N / 2) < (1LL << 32), "layernorm_fwd: dropout site too large");
   char pname[64];
   if (prof_enabled()) snprintf(pname, sizeof(pname), "layernorm_fwd:%dx%d", M, N);
   ProfScope prof(pname, 0.0, static_cast<double>(M) * N * ((x_f32 ? 4 : 2) + (y_f32 ? 4 : 2) + (y2 ? (y2_f32 ? 4 : 2) : 0)), s);
-  ln_fwd_kernel<<<ln_grid(M), 256, 0, s>>>(x, x_f32, y, y_f32, y2, y2_f32, gamma, beta, stats, M, N, relu);
+  if (res != nullptr)
+    ln_fwd_kernel<true><<<ln_grid(M), 256, 0, s>>>(x, x_f32, y, y_f32, y2, y2_f32, gamma, beta, stats, M, N, relu, res, xout,
+                                                   drop != nullptr ? *drop : DropSpec{});
+  else
+    ln_fwd_kernel<false><<<ln_grid(M), 256, 0, s>>>(x, x_f32, y, y_f32, y2, y2_f32, gamma, beta, stats, M, N, relu, nullptr,
+                                                    nullptr, DropSpec{});
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
 
 int layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const float* stats, const float* gamma,
                   const float* beta, const void* add, int add_f32, void* dx, int dx_f32, void* dx2, int dx2_f32,
-                  float* dgamma, float* dbeta, int M, int N, int relu, cudaStream_t s) {
+                  float* dgamma, float* dbeta, int M, int N, int relu, cudaStream_t s, void* dxm, const DropSpec* drop) {
   SER_REQUIRE(N % 8 == 0 && N <= kMaxChunks * 256, "layernorm: N must be a multiple of 8 and <= 1024");
   SER_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma and dbeta go together");
+  const bool masked = dxm != nullptr && drop != nullptr && drop->on();
+  // token-level bf16 LayerNorms: single-pass kernel (layernorm_fused.cu)
+  if (layernorm_bwd_fused_ok(dy_f32, x_f32, dx_f32, add, dx2, dgamma, M, N, relu))
+    return layernorm_bwd_fused(dy, x, stats, gamma, dx, masked ? dxm : nullptr, masked ? *drop : DropSpec{}, dgamma, dbeta,
+                               M, N, s);
+  if (masked) {       // generic path: dx first, the masked copy as a separate pass
+    SER_TRY(layernorm_bwd(dy, dy_f32, x, x_f32, stats, gamma, beta, add, add_f32, dx, dx_f32, dx2, dx2_f32, dgamma, dbeta,
+                          M, N, relu, s, nullptr, nullptr));
+    return dropout_apply(dx, dxm, nullptr, dx_f32, M, N, *drop, s);
+  }
   char pname[64];
   if (prof_enabled()) snprintf(pname, sizeof(pname), "layernorm_bwd:%dx%d", M, N);
   // algorithmic bytes: dy, x read once, dx (and its copy / the added tensor) moved once

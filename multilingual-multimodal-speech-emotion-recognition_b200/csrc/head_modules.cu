@@ -198,13 +198,15 @@ static int xattn_fwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
   at.kmask = d.a_mask; at.O = d.ctx_t; at.lse = d.lse_t;
   at.drop = with_site(drop, DS_XA_PROB_T);
   SER_TRY(attention_fwd(at, s));
-  // z = x + dropout(ctx Wz^T + bz): with dropout on, the residual moves from the GEMM epilogue into the mask pass
+  // z = x + dropout(ctx Wz^T + bz): with dropout on, mask and residual move from the GEMM epilogue into the
+  // LayerNorm kernel's prologue (which also saves z for the backward)
+  const DropSpec drop_ra = with_site(drop, DS_XA_RES_A), drop_rt = with_site(drop, DS_XA_RES_T);
   SER_TRY(linear_fwd(dt, Ma, D, S, d.ctx_a, S, fb.wz_a, S, fb.bz_a, d.z_a, D, f, ACT_NONE, drop.on() ? nullptr : d.a, D, f, s));
-  if (drop.on()) SER_TRY(dropout_apply(d.z_a, d.z_a, d.a, f, Ma, D, with_site(drop, DS_XA_RES_A), s));
-  SER_TRY(layernorm_fwd(d.z_a, f, d.enh_a, f, nullptr, f, d.ln_a_g, d.ln_a_b, d.stats_a, Ma, D, 0, s));
+  SER_TRY(layernorm_fwd(d.z_a, f, d.enh_a, f, nullptr, f, d.ln_a_g, d.ln_a_b, d.stats_a, Ma, D, 0, s,
+                        drop.on() ? d.a : nullptr, drop.on() ? d.z_a : nullptr, &drop_ra));
   SER_TRY(linear_fwd(dt, Mt, D, S, d.ctx_t, S, fb.wz_t, S, fb.bz_t, d.z_t, D, f, ACT_NONE, drop.on() ? nullptr : d.t, D, f, s));
-  if (drop.on()) SER_TRY(dropout_apply(d.z_t, d.z_t, d.t, f, Mt, D, with_site(drop, DS_XA_RES_T), s));
-  SER_TRY(layernorm_fwd(d.z_t, f, d.enh_t, f, nullptr, f, d.ln_t_g, d.ln_t_b, d.stats_t, Mt, D, 0, s));
+  SER_TRY(layernorm_fwd(d.z_t, f, d.enh_t, f, nullptr, f, d.ln_t_g, d.ln_t_b, d.stats_t, Mt, D, 0, s,
+                        drop.on() ? d.t : nullptr, drop.on() ? d.z_t : nullptr, &drop_rt));
   return SER_OK;
 }
 
@@ -256,17 +258,15 @@ static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_a_b, 0, sizeof(float) * D, s));
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_t_g, 0, sizeof(float) * D, s));
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_t_b, 0, sizeof(float) * D, s));
+  // with dropout on, the LayerNorm backward also writes the branch gradient mask * dz (the skip path keeps dz)
+  const DropSpec drop_ra = with_site(drop, DS_XA_RES_A), drop_rt = with_site(drop, DS_XA_RES_T);
   SER_TRY(layernorm_bwd(d.d_enh_a, f, d.z_a, f, d.stats_a, d.ln_a_g, d.ln_a_b, nullptr, f, dz_a, f, nullptr, f,
-                        d.dln_a_g, d.dln_a_b, Ma, D, 0, s));
+                        d.dln_a_g, d.dln_a_b, Ma, D, 0, s, drop.on() ? dzm_a : nullptr, &drop_ra));
   SER_TRY(layernorm_bwd(d.d_enh_t, f, d.z_t, f, d.stats_t, d.ln_t_g, d.ln_t_b, nullptr, f, dz_t, f, nullptr, f,
-                        d.dln_t_g, d.dln_t_b, Mt, D, 0, s));
+                        d.dln_t_g, d.dln_t_b, Mt, D, 0, s, drop.on() ? dzm_t : nullptr, &drop_rt));
   // z = ctx Wz^T + bz + residual
   struct SideZ { int M; void* dz; const void* ctx; void* dctx; const void* wz; const void* wout; const void* wo;
                  float* dwout; float* dwo; int m; };
-  if (drop.on()) {
-    SER_TRY(dropout_apply(dz_a, dzm_a, nullptr, f, Ma, D, with_site(drop, DS_XA_RES_A), s));
-    SER_TRY(dropout_apply(dz_t, dzm_t, nullptr, f, Mt, D, with_site(drop, DS_XA_RES_T), s));
-  }
   const SideZ sz[2] = {
       {Ma, dzm_a, d.ctx_a, dctx_a, fb.wz_a, d.wout_a, d.wo_a, d.dwout_a, d.dwo_a, 0},
       {Mt, dzm_t, d.ctx_t, dctx_t, fb.wz_t, d.wout_t, d.wo_t, d.dwout_t, d.dwo_t, 1},
@@ -369,13 +369,14 @@ int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s) {
   SER_TRY(attention_fwd(at, s));
   // out_proj, out_a / out_t, dropout, + residual, LayerNorm (cross_attention.py:42-43,50-51)
   SER_TRY(linear_fwd(dt, Ma, S, S, d.ctx_a, S, d.wo_a, S, d.bo_a, d.o_a, S, f, ACT_NONE, nullptr, 0, f, s));
+  const DropSpec drop_ra = with_site(drop, DS_XA_RES_A), drop_rt = with_site(drop, DS_XA_RES_T);
   SER_TRY(linear_fwd(dt, Ma, D, S, d.o_a, S, d.wout_a, S, d.bout_a, d.z_a, D, f, ACT_NONE, drop.on() ? nullptr : d.a, D, f, s));
-  if (drop.on()) SER_TRY(dropout_apply(d.z_a, d.z_a, d.a, f, Ma, D, with_site(drop, DS_XA_RES_A), s));
-  SER_TRY(layernorm_fwd(d.z_a, f, d.enh_a, f, nullptr, f, d.ln_a_g, d.ln_a_b, d.stats_a, Ma, D, 0, s));
+  SER_TRY(layernorm_fwd(d.z_a, f, d.enh_a, f, nullptr, f, d.ln_a_g, d.ln_a_b, d.stats_a, Ma, D, 0, s,
+                        drop.on() ? d.a : nullptr, drop.on() ? d.z_a : nullptr, &drop_ra));
   SER_TRY(linear_fwd(dt, Mt, S, S, d.ctx_t, S, d.wo_t, S, d.bo_t, d.o_t, S, f, ACT_NONE, nullptr, 0, f, s));
   SER_TRY(linear_fwd(dt, Mt, D, S, d.o_t, S, d.wout_t, S, d.bout_t, d.z_t, D, f, ACT_NONE, drop.on() ? nullptr : d.t, D, f, s));
-  if (drop.on()) SER_TRY(dropout_apply(d.z_t, d.z_t, d.t, f, Mt, D, with_site(drop, DS_XA_RES_T), s));
-  SER_TRY(layernorm_fwd(d.z_t, f, d.enh_t, f, nullptr, f, d.ln_t_g, d.ln_t_b, d.stats_t, Mt, D, 0, s));
+  SER_TRY(layernorm_fwd(d.z_t, f, d.enh_t, f, nullptr, f, d.ln_t_g, d.ln_t_b, d.stats_t, Mt, D, 0, s,
+                        drop.on() ? d.t : nullptr, drop.on() ? d.z_t : nullptr, &drop_rt));
   return SER_OK;
 }
 
@@ -421,17 +422,15 @@ int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_a_b, 0, sizeof(float) * D, s));
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_t_g, 0, sizeof(float) * D, s));
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_t_b, 0, sizeof(float) * D, s));
+  const DropSpec drop_ra = with_site(drop, DS_XA_RES_A), drop_rt = with_site(drop, DS_XA_RES_T);
   SER_TRY(layernorm_bwd(d.d_enh_a, f, d.z_a, f, d.stats_a, d.ln_a_g, d.ln_a_b, nullptr, f, dz_a, f, nullptr, f,
-                        d.dln_a_g, d.dln_a_b, Ma, D, 0, s));
+                        d.dln_a_g, d.dln_a_b, Ma, D, 0, s, drop.on() ? dzm_a : nullptr, &drop_ra));
   SER_TRY(layernorm_bwd(d.d_enh_t, f, d.z_t, f, d.stats_t, d.ln_t_g, d.ln_t_b, nullptr, f, dz_t, f, nullptr, f,
-                        d.dln_t_g, d.dln_t_b, Mt, D, 0, s));
+                        d.dln_t_g, d.dln_t_b, Mt, D, 0, s, drop.on() ? dzm_t : nullptr, &drop_rt));
   // out_a / out_t and out_proj
   struct Side { int M; void* dz; const void* o; const void* ctx; void* dob; void* dctx; const void* wout; const void* wo;
                 float* dwout; float* dbout; float* dwo; float* dbo; };
-  if (drop.on()) {     // branch gradient = mask * dz; the skip path (last two GEMMs below) keeps the unmasked dz
-    SER_TRY(dropout_apply(dz_a, dzm_a, nullptr, f, Ma, D, with_site(drop, DS_XA_RES_A), s));
-    SER_TRY(dropout_apply(dz_t, dzm_t, nullptr, f, Mt, D, with_site(drop, DS_XA_RES_T), s));
-  }
+  // (branch gradient = mask * dz from the LayerNorm backward; the skip path -- last two GEMMs below -- keeps dz)
   const Side sides[2] = {
       {Ma, dzm_a, d.o_a, d.ctx_a, do_a, dctx_a, d.wout_a, d.wo_a, d.dwout_a, d.dbout_a, d.dwo_a, d.dbo_a},
       {Mt, dzm_t, d.o_t, d.ctx_t, do_t, dctx_t, d.wout_t, d.wo_t, d.dwout_t, d.dbout_t, d.dwo_t, d.dbo_t},
@@ -653,7 +652,8 @@ int clf_fwd(const ser_clf_desc& d, cudaStream_t s) {
   const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);
   if (drop.on()) SER_TRY(dropout_apply(d.h, d.h, nullptr, 1, B, P, with_site(drop, DS_CLF_IN), s));   // input_projection[3]
   ClfStackArgs sa;
-  const bool fused = stack_args(d, sa) && !drop.on();
+  const bool fused = stack_args(d, sa);
+  sa.drop = drop;
   if (fused) SER_TRY(clf_stack_fwd(sa, s));          // all L blocks in one cluster kernel (clf_stack.cu)
   for (int i = 0; i < L && !fused; ++i) {
     float* hi = d.h + i * BP;
@@ -732,7 +732,8 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
   SER_TRY(linear_wgrad(dt, B, F, P, dq, F, d.h_last, P, d.dw_out, P, s));
   SER_TRY(linear_dgrad(dt, B, F, P, dq, F, d.w_out, P, dh32, P, 1, nullptr, 0, 1, GATE_NONE, nullptr, 0, 1, s));
   ClfStackArgs sa;
-  bool fused = stack_args(d, sa) && stack_grad_args(d, sa) && !drop.on();
+  bool fused = stack_args(d, sa) && stack_grad_args(d, sa);
+  sa.drop = drop;
   if (fused) {
     // the whole dX chain + LayerNorm parameter gradients in one cluster kernel; it leaves dL/dh_0 in dh32b and the
     // per-block GEMM operands (dh_{i+1}, da_i as bf16) in dhn_all / dr_all for the batched weight gradients below

@@ -13,12 +13,21 @@ int cast_any(const void* src, int src_f32, void* dst, int dst_f32, long long n, 
 int colsum(const void* X, int x_f32, long long ld, int M, int N, float* out, cudaStream_t s);
 // y = [relu](LayerNorm(x)); stats[m] = {mean, rstd}.  N % 8 == 0, N <= 1024.  eps = 1e-5.
 int layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, void* y2, int y2_f32, const float* gamma,
-                  const float* beta, float* stats, int M, int N, int relu, cudaStream_t s);
+                  const float* beta, float* stats, int M, int N, int relu, cudaStream_t s, const void* res = nullptr,
+                  void* xout = nullptr, const DropSpec* drop = nullptr);
+// res / xout / drop (optional): normalise res + dropout(x) instead of x and save that row to xout (x's dtype)
 // dx = LN'(dy) [+ add];  dgamma/dbeta accumulate (+=) into fp32 [N] buffers (caller zeroes them).
 // With relu != 0 the op was y = relu(LN(x)) and dy is masked by (LN(x) > 0) first.
 int layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const float* stats, const float* gamma,
                   const float* beta, const void* add, int add_f32, void* dx, int dx_f32, void* dx2, int dx2_f32,
-                  float* dgamma, float* dbeta, int M, int N, int relu, cudaStream_t s);
+                  float* dgamma, float* dbeta, int M, int N, int relu, cudaStream_t s, void* dxm = nullptr,
+                  const DropSpec* drop = nullptr);
+// dxm / drop (optional): also write mask * dx, the gradient entering a dropout-ed branch (dropout.cuh)
+// single-pass variant for bf16 rows of 256 / 512 / 768 columns (layernorm_fused.cu); layernorm_bwd dispatches to it
+bool layernorm_bwd_fused_ok(int dy_f32, int x_f32, int dx_f32, const void* add, const void* dx2, const float* dgamma,
+                            int M, int N, int relu);
+int layernorm_bwd_fused(const void* dy, const void* x, const float* stats, const float* gamma, void* dx, void* dxm,
+                        const DropSpec& drop, float* dgamma, float* dbeta, int M, int N, cudaStream_t s);
 int colsum_batched(const void* X, int x_f32, long long ld, int M, int N, float* out, int batch, long long strideX,
                    long long strideOut, cudaStream_t s);
 // classifier block prologue / its backward: y = LN_outer(h), n = LN_inner(y) in one pass (fp32 stream)
@@ -71,6 +80,7 @@ struct ClfStackArgs {
   void* xchg;                                                           // scratch >= ceil(B/128) * 256 KB (the saved-y buffer)
   const float* dh_in; float* dh_out; void* dhn; void* dr;               // backward
   float* dlni_g; float* dlni_b; float* dlno_g; float* dlno_b;
+  DropSpec drop;                                                        // block[3] / block[5] dropout, off by default
 };
 bool clf_stack_supported(int dtype, int P, int L, const ClfStackArgs& a);
 int clf_stack_fwd(const ClfStackArgs& a, cudaStream_t s);

@@ -13,22 +13,54 @@ from .models import (AdvancedOpenMaxClassifier, AttentiveStatsPooling, Bottlenec
                      FusionLayer, PrototypeMemory)
 
 
+# dropout rates of the reference's training script: CrossModalAttention default (cross_attention.py:7), the
+# hard-coded nn.Dropout(0.1) of FusionLayer (fusion.py:9,12), AdvancedOpenMaxClassifier(dropout=0.15) (train.py:67)
+REFERENCE_DROPOUT = {"cross": 0.1, "fusion": 0.1, "classifier": 0.15}
+
+
+def dropout_rates(dropout) -> Dict[str, float]:
+    """float -> the same rate everywhere; 'reference' -> REFERENCE_DROPOUT; dict -> per-module rates."""
+    if isinstance(dropout, str):
+        if dropout != "reference":
+            raise ValueError("dropout must be a float, a dict or 'reference'")
+        return dict(REFERENCE_DROPOUT)
+    if isinstance(dropout, dict):
+        return {k: float(dropout.get(k, 0.0)) for k in REFERENCE_DROPOUT}
+    return {k: float(dropout) for k in REFERENCE_DROPOUT}
+
+
 class FusionHead(nn.Module):
     def __init__(self, num_labels: int = 4, hidden: int = 768, shared_dim: int = 256, num_heads: int = 8,
-                 proj_dim: int = 512, num_layers: int = 35, dropout: float = 0.0):
+                 proj_dim: int = 512, num_layers: int = 35, dropout=0.0):
         super().__init__()
         self.num_labels = num_labels
+        rates = dropout_rates(dropout)
         self.adapter_a = BottleneckAdapter(hidden, 256)
         self.adapter_t = BottleneckAdapter(hidden, 256)
-        self.cross = CrossModalAttention(hidden, hidden, shared_dim=shared_dim, num_heads=num_heads, dropout=dropout)
+        self.cross = CrossModalAttention(hidden, hidden, shared_dim=shared_dim, num_heads=num_heads,
+                                         dropout=rates["cross"])
         self.pool_a = AttentiveStatsPooling(hidden)
         self.pool_t = AttentiveStatsPooling(hidden)
         self.fusion = FusionLayer(hidden * 2, hidden * 2, proj_dim)
-        self.fusion.proj_a[2].p = self.fusion.proj_t[2].p = float(dropout)   # reference hard-codes 0.1
         self.classifier = AdvancedOpenMaxClassifier(input_dim=proj_dim, num_labels=num_labels, num_layers=num_layers,
-                                                    base_dim=proj_dim, dropout=dropout)
+                                                    base_dim=proj_dim, dropout=rates["classifier"])
+        self.set_dropout(rates)
         self.prototypes = PrototypeMemory(num_labels, proj_dim)
         self.loss_weights = dict(w_ce=1.0, w_focal=0.3, w_unc=0.05, w_proto=0.01)   # train.py:156-168
+
+    def set_dropout(self, dropout) -> Dict[str, float]:
+        """Change the dropout rates of the built head (float, dict or 'reference'); returns the rates in effect."""
+        rates = dropout_rates(dropout)
+        self.cross.dropout.p = self.cross.attn_a.dropout = self.cross.attn_t.dropout = rates["cross"]
+        self.cross.p_drop = rates["cross"]
+        self.fusion.proj_a[2].p = self.fusion.proj_t[2].p = rates["fusion"]
+        self.classifier.p_drop = rates["classifier"]
+        for part in (self.classifier.deep_classifier, self.classifier.uncertainty_head):
+            for m in part.modules():
+                if isinstance(m, nn.Dropout):
+                    m.p = rates["classifier"]
+        self.dropout_rates = rates
+        return rates
 
     GROUPS = ("adapter_a", "adapter_t", "cross", "pool_a", "pool_t", "fusion", "classifier", "prototypes")
 

@@ -77,9 +77,25 @@ class dropout_masks:
 
 
 def _drop(x: Tensor, site: str) -> Tensor:
-    if _DROPOUT_MASKS is None or site not in _DROPOUT_MASKS:
+    if _DROPOUT_MASKS is None:
+        return x
+    if callable(_DROPOUT_MASKS):             # mask source: f(site, x) -> multiplier tensor or None
+        m = _DROPOUT_MASKS(site, x)
+        return x if m is None else x * m.to(x.dtype).reshape(x.shape)
+    if site not in _DROPOUT_MASKS:
         return x
     return x * _DROPOUT_MASKS[site].to(x.dtype).reshape(x.shape)
+
+
+def random_dropout(rates: Dict[str, float], generator=None):
+    """Mask source for `dropout_masks`: fresh Bernoulli keep masks per call, like nn.Dropout in train() mode.
+    `rates` maps the site prefix ('cross', 'fusion', 'clf') to p."""
+    def f(site: str, x: Tensor):
+        p = float(rates.get(site.split(".")[0], 0.0))
+        if p <= 0.0:
+            return None
+        return (torch.rand(x.shape, generator=generator) >= p).to(x.dtype) / (1.0 - p)
+    return f
 
 
 def _ste_round(x: Tensor) -> Tensor:

@@ -56,7 +56,7 @@ def test_blackwell_instructions_present(lib):
     body = {k: "\n".join(v) for k, v in funcs.items()}
     gemm = [k for k in body if "gemm_tc_kernel" in k]
     stack = [k for k in body if "clf_stack_fwd_kernel" in k or "clf_stack_bwd_kernel" in k]
-    assert gemm and len(stack) == 2
+    assert gemm and len(stack) == 4          # forward / backward x dropout off / on
     for k in gemm:
         assert "UTCHMMA" in body[k] and "UTMALDG" in body[k] and "LDTM" in body[k] and "UTMASTG" in body[k], k
     for k in stack:
