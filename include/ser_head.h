@@ -68,6 +68,8 @@ typedef struct ser_gemm_desc {
   int accumulate;                              /* C += result (fp32 C only)                      */
   float alpha;
   int splits;                                  /* split-K factor, 0 = auto                       */
+  float* rowsum;                               /* optional, a_trans = 1 only: rowsum[m] = sum_k op(A)[m,k] -- the bias
+                                                  gradient when A = dY stored [tokens, features]; overwritten; NULL = off */
 } ser_gemm_desc;
 int ser_gemm(const ser_gemm_desc* d, void* stream);
 

@@ -193,7 +193,7 @@ def call(name: str, desc, device) -> None:
 
 
 def gemm(a, b, *, a_trans=False, b_trans=False, bias=None, act=ACT_NONE, residual=None, gate=None,
-         gate_mode=GATE_NONE, out=None, out_dtype=None, accumulate=False, alpha=1.0, splits=0):
+         gate_mode=GATE_NONE, out=None, out_dtype=None, accumulate=False, alpha=1.0, splits=0, rowsum=None):
     """out[M,N] = epilogue(alpha * op(a) @ op(b)^T).  a: [M,K] (or [K,M] if a_trans); b: [N,K] (or [K,N])."""
     lib = load()
     require_cuda(a, b, bias, residual, gate, out)
@@ -217,6 +217,10 @@ def gemm(a, b, *, a_trans=False, b_trans=False, bias=None, act=ACT_NONE, residua
         d.G, d.ldg, d.g_f32 = ptr(gate), gate.stride(0), int(gate.dtype == torch.float32)
     d.gate_mode = gate_mode
     d.act, d.accumulate, d.alpha, d.splits = act, int(accumulate), float(alpha), splits
+    if rowsum is not None:                       # [M] fp32: row sums of op(a) (bias gradient of a dW GEMM)
+        require_cuda(rowsum)
+        assert rowsum.dtype == torch.float32 and rowsum.numel() == M and rowsum.is_contiguous()
+        d.rowsum = ptr(rowsum)
     check(lib.ser_gemm(C.byref(d), stream_ptr(a.device)), "ser_gemm")
     return out
 

@@ -54,6 +54,7 @@ int ser_gemm(const ser_gemm_desc* d, void* stream) {
   a.R = d->R; a.ldr = d->ldr; a.r_f32 = d->r_f32;
   a.G = d->G; a.ldg = d->ldg; a.g_f32 = d->g_f32; a.gate_mode = d->gate_mode;
   a.act = d->act; a.accumulate = d->accumulate; a.alpha = d->alpha; a.splits = d->splits;
+  a.rowsum = d->rowsum;
   return ser::gemm(a, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -184,11 +184,15 @@ struct GemmArgs {
   // batched GEMM: `batch` independent problems, operand / output b at base + b * stride (elements)
   int batch = 1;
   long long strideA = 0, strideB = 0, strideC = 0, strideR = 0, strideG = 0;
+  // optional by-product of dW-type GEMMs (a_trans): rowsum[m] = sum_k op(A)[m, k], i.e. the bias gradient when
+  // A = dY stored [tokens, features].  Overwritten.  Batched: rowsum + b * strideRS.
+  float* rowsum = nullptr; long long strideRS = 0;
 };
 
 int gemm(const GemmArgs& a, cudaStream_t stream);
 int gemm_simt_f32(const GemmArgs& a, cudaStream_t stream);
 int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream);
+bool gemm_tc_rowsum_ok(const GemmArgs& a);
 int device_sm_count();
 
 }  // namespace ser

@@ -2,7 +2,7 @@
 // (the next K tile is in flight while the current one is multiplied), optional split-K.
 // This is the "within 1e-4 of the fp32 reference" path (TF32 tensor cores are not accurate enough,
 // see SURVEY.md section 7 "Hard parts"); it shares the epilogue contract of the tcgen05 kernel.
-#include "common.cuh"
+#include "kernels.cuh"
 #include "prof.cuh"
 #include <mutex>
 
@@ -185,6 +185,16 @@ int gemm_simt_f32(const GemmArgs& a0, cudaStream_t stream) {
 }
 
 int gemm(const GemmArgs& a, cudaStream_t stream) {
+  if (a.rowsum != nullptr && !gemm_tc_rowsum_ok(a)) {
+    // no fused row sum on this path: rowsum of op(A) = column sums of the stored [K, M] operand, as its own launch
+    SER_REQUIRE(a.a_trans, "gemm: rowsum needs an MN-major (a_trans) A operand");
+    const int f32 = a.dtype == DT_F32 ? 1 : 0;
+    if (a.batch > 1) SER_TRY(colsum_batched(a.A, f32, a.lda, a.K, a.M, a.rowsum, a.batch, a.strideA, a.strideRS, stream));
+    else SER_TRY(colsum(a.A, f32, a.lda, a.K, a.M, a.rowsum, stream));
+    GemmArgs b = a;
+    b.rowsum = nullptr;
+    return gemm(b, stream);
+  }
   if (a.dtype == DT_F32) return gemm_simt_f32(a, stream);
   if (a.dtype == DT_BF16) return gemm_tc_bf16(a, stream);
   set_last_error(__FILE__, __LINE__, "gemm: unknown dtype");

@@ -13,12 +13,19 @@
 // the main loop of tile i+1.  Both operands may be K-major or MN-major (nn.Linear weights are
 // consumed in place for forward, dX and dW GEMMs: no transposed copies are ever materialised).
 //
+// Bias gradients ride along (RS variants, dW GEMMs): db = column sums of dY = row sums of the MN-major A operand.
+// CTAs of output column tile 0 issue, per k-block, four extra N = 16 MMAs of the A tile against a constant tile of
+// ones into 16 spare TMEM columns; the epilogue adds column 0 of that accumulator to rowsum[] with one atomic per
+// row.  dY is not read a second time and the 18 colsum launches of a training step disappear.  (RS kernels use a
+// single accumulator buffer: split-K sizes these problems to one work item per CTA anyway.)
+//
 // Serves: adapters, q/k/v + MHA in/out projections, out_a/out_t, pooling scorer, fusion projections,
 // the classifier heads (reference: src/models/audio_encoder.py:19-21, cross_attention.py:38-51,
 // pooling.py:9-13, fusion.py:8-16, classifier.py:73-129) in the bf16 tier.
 #include "common.cuh"
 #include "prof.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 
 namespace ser {
@@ -55,6 +62,8 @@ struct TcEpilogue {
   int act;
   int atomic;        // accumulate with TMA reduce-add (split-K or C +=); fp32 output only
   float alpha;
+  float* rowsum;     // RS kernels: rowsum[m] += sum_k op(A)[m, k]  (pre-zeroed by the host side)
+  long long rs_stride;   // batch stride of rowsum (elements)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -151,6 +160,11 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+  return r;
+}
 
 // Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.
 //   K-major : rows of 128 B; 8-row groups are SBO = 1024 B apart; LBO unused.
@@ -314,7 +328,13 @@ __device__ __forceinline__ void epilogue_tile(const TcEpilogue& ep, const CUtens
 // ------------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------------
-template <int BN, int AMAJ, int BMAJ>
+constexpr int kOnesN = 16;                       // N of the row-sum MMA (the smallest N an M = 128 UMMA takes)
+__device__ __forceinline__ constexpr uint32_t make_idesc_ones(int amaj) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(amaj) << 15) | (0u << 16)   // B (ones): K-major
+         | (static_cast<uint32_t>(kOnesN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+}
+
+template <int BN, int AMAJ, int BMAJ, bool RS>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS,
@@ -356,6 +376,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(Cfg::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // RS: a 16-row x 128-byte K-major tile of bf16 ones lives in the last epilogue warp's (unused) source staging tile
+  uint8_t* ones_tile = smem_stg + (2 * (kEpiWarps - 1) + 1) * kStgTile;
+  if (RS && warp >= 2) {
+    for (int i = threadIdx.x - 64; i < kOnesN * 128 / 16; i += kThreads - 64)
+      sts128(smem_u32(ones_tile) + 16u * i, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -406,9 +433,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t b_lbo = (BMAJ == 0) ? 0u : BK * 128u;
       constexpr uint32_t a_kstep = (AMAJ == 0) ? UMMA_K * 2u : UMMA_K * 128u;   // bytes per K=16 step
       constexpr uint32_t b_kstep = (BMAJ == 0) ? UMMA_K * 2u : UMMA_K * 128u;
+      constexpr uint32_t idesc_ones = make_idesc_ones(AMAJ);
+      const uint64_t ones_desc = make_smem_desc(smem_u32(ones_tile), 0u, 1024);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const bool rs_tile = RS && (tile % n_tiles == 0);     // one column tile per (row tile, split) sums the rows
         const int rest = tile / n_tiles;
         const int sp = (rest / m_tiles) % splits;
         const int kb0 = static_cast<int>((static_cast<long long>(sp) * kblocks) / splits);
@@ -427,11 +457,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
             tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
+          if (rs_tile) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+              tc_mma_bf16(tmem_base + BN, adesc, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+          }
           tc_commit(&empty_bar[stage]);      // frees the smem stage once these MMAs retire
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         tc_commit(&tfull_bar[acc]);          // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (RS) acc_phase ^= 1;              // single accumulator buffer (columns [BN, BN+16) hold the row sums)
+        else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -465,10 +503,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else if (ep.src == SRC_RESIDUAL) epilogue_tile<BN, false, SRC_RESIDUAL>(ep, &tmC, &tmS, w, taddr0, lane, n0, mw, bz, lead, tf, acc_phase);
         else epilogue_tile<BN, false, SRC_GATE>(ep, &tmC, &tmS, w, taddr0, lane, n0, mw, bz, lead, tf, acc_phase);
       }
+      if (RS && nt == 0 && w.half == 0) {
+        // column 0 of the ones-product: this lane's row sum over the k-range of this split
+        const float rsum = __uint_as_float(tmem_ld1(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + BN));
+        tmem_ld_wait();
+        const int row = mw + lane;
+        if (row < M) atomicAdd(ep.rowsum + bz * ep.rs_stride + row, rsum);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (RS) acc_phase ^= 1;
+      else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     // staged tiles must outlive the TMA stores that read them
     if (lane == 0) tma_wait_group_read<0>();
@@ -530,12 +576,12 @@ int make_tmap(CUtensorMap* tm, const void* base, int f32, long long rows, long l
   return SER_OK;
 }
 
-template <int BN, int AMAJ, int BMAJ>
+template <int BN, int AMAJ, int BMAJ, bool RS = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmS,
            const TcEpilogue& ep, int M, int N, int K, int splits, int batch, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ>;
+  auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ, RS>;
   if (!configured) {
     SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
@@ -554,11 +600,19 @@ int dispatch_major(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap&
   const int nb = a.batch > 1 ? a.batch : 1;
   if (!a.a_trans && !a.b_trans) return launch<BN, 0, 0>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
   if (!a.a_trans && a.b_trans) return launch<BN, 0, 1>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
+  if (a.a_trans && a.b_trans && ep.rowsum != nullptr)
+    return launch<BN, 1, 1, true>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
   if (a.a_trans && a.b_trans) return launch<BN, 1, 1>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
   return launch<BN, 1, 0>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
 }
 
 }  // namespace
+
+bool gemm_tc_rowsum_ok(const GemmArgs& a) {
+  static const bool disabled = (getenv("SER_NO_GEMM_ROWSUM") != nullptr);      // A/B switch: separate colsum launches
+  return !disabled && a.dtype == DT_BF16 && a.a_trans && a.b_trans && a.R == nullptr && a.gate_mode == GATE_NONE &&
+         !a.accumulate;
+}
 
 int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   SER_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm_tc: empty problem");
@@ -615,6 +669,14 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   ep.act = a.act;
   ep.alpha = a.alpha;
   ep.src = SRC_NONE;
+  ep.rowsum = a.rowsum;
+  ep.rs_stride = a.strideRS;
+  if (a.rowsum != nullptr) {
+    SER_REQUIRE(gemm_tc_rowsum_ok(a), "gemm_tc: rowsum rides on plain dW-type GEMMs only (both operands MN-major)");
+    const int nb = a.batch > 1 ? a.batch : 1;
+    if (nb == 1 || a.strideRS == a.M) SER_CUDA_CHECK(cudaMemsetAsync(a.rowsum, 0, sizeof(float) * a.M * nb, stream));
+    else SER_CUDA_CHECK(cudaMemset2DAsync(a.rowsum, a.strideRS * sizeof(float), 0, a.M * sizeof(float), nb, stream));
+  }
   const void* R = a.R;
   int accumulate = a.accumulate;
   if (splits > 1 && R != nullptr && R == a.C) {

@@ -60,10 +60,12 @@ int linear_dgrad(int dt, int M, int Nout, int Kin, const void* dY, long long ldd
   return gemm(g, s);
 }
 
-// dW[Nout,Kin] (fp32) = dY[M,Nout]^T X[M,Kin]
+// dW[Nout,Kin] (fp32) = dY[M,Nout]^T X[M,Kin];  db[Nout] (optional) = column sums of dY, produced by the same GEMM in
+// the bf16 tier (gemm_tc.cu row-sum MMAs) and by a colsum launch otherwise
 int linear_wgrad(int dt, int M, int Nout, int Kin, const void* dY, long long lddy, const void* X, long long ldx,
-                 float* dW, long long lddw, cudaStream_t s) {
+                 float* dW, long long lddw, cudaStream_t s, float* db = nullptr) {
   GemmArgs g;
+  g.rowsum = db;
   g.dtype = dt; g.M = Nout; g.N = Kin; g.K = M;
   g.A = dY; g.lda = lddy; g.a_trans = 1;
   g.B = X; g.ldb = ldx; g.b_trans = 1;
@@ -88,11 +90,9 @@ int adapter_fwd(const ser_adapter_desc& d, cudaStream_t s) {
 int adapter_bwd(const ser_adapter_desc& d, cudaStream_t s) {
   const int dt = d.dtype, f = is_f32(dt);
   SER_REQUIRE(d.M > 0 && d.dy && d.dh && d.h && d.x, "adapter_bwd: null tensor");
-  SER_TRY(colsum(d.dy, f, d.D, d.M, d.D, d.db2, s));
-  SER_TRY(linear_wgrad(dt, d.M, d.D, d.S, d.dy, d.D, d.h, d.S, d.dw2, d.S, s));
+  SER_TRY(linear_wgrad(dt, d.M, d.D, d.S, d.dy, d.D, d.h, d.S, d.dw2, d.S, s, d.db2));
   SER_TRY(linear_dgrad(dt, d.M, d.D, d.S, d.dy, d.D, d.w2, d.S, d.dh, d.S, f, d.h, d.S, f, GATE_RELU, nullptr, 0, f, s));
-  SER_TRY(colsum(d.dh, f, d.S, d.M, d.S, d.db1, s));
-  SER_TRY(linear_wgrad(dt, d.M, d.S, d.D, d.dh, d.S, d.x, d.D, d.dw1, d.D, s));
+  SER_TRY(linear_wgrad(dt, d.M, d.S, d.D, d.dh, d.S, d.x, d.D, d.dw1, d.D, s, d.db1));
   if (d.dx != nullptr)
     SER_TRY(linear_dgrad(dt, d.M, d.S, d.D, d.dh, d.S, d.w1, d.D, d.dx, d.D, f, nullptr, 0, f, GATE_NONE,
                          d.add_residual ? d.dy : nullptr, d.D, f, s));
@@ -272,8 +272,7 @@ static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
       {Mt, dzm_t, d.ctx_t, dctx_t, fb.wz_t, d.wout_t, d.wo_t, d.dwout_t, d.dwo_t, 1},
   };
   for (const SideZ& z : sz) {
-    SER_TRY(colsum(z.dz, f, D, z.M, D, dbz[z.m], s));
-    SER_TRY(linear_wgrad(dt, z.M, D, S, z.dz, D, z.ctx, S, dwz32[z.m], S, s));
+    SER_TRY(linear_wgrad(dt, z.M, D, S, z.dz, D, z.ctx, S, dwz32[z.m], S, s, dbz[z.m]));
     SER_TRY(linear_dgrad(dt, z.M, D, S, z.dz, D, z.wz, S, z.dctx, S, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
   }
   SER_TRY(cast_any(dwz32[0], 1, dwz16[0], 0, 2LL * D * S, s));
@@ -305,8 +304,7 @@ static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
       {Mt, dp_t, d.t, d.dt, dz_t, fb.wc_t, fb.wbd_t, d.wqkv_t, d.dwqkv_t, 1},
   };
   for (const SideP& p : sp) {
-    SER_TRY(colsum(p.dp, f, S3, p.M, S3, dbc[p.m], s));
-    SER_TRY(linear_wgrad(dt, p.M, S3, D, p.dp, S3, p.x, D, dwc32[p.m], D, s));
+    SER_TRY(linear_wgrad(dt, p.M, S3, D, p.dp, S3, p.x, D, dwc32[p.m], D, s, dbc[p.m]));
     SER_TRY(linear_dgrad(dt, p.M, S3, D, p.dp, S3, p.wc, D, p.dx, D, f, nullptr, 0, f, GATE_NONE, p.dz, D, f, s));
   }
   SER_TRY(cast_any(dwc32[0], 1, dwc16[0], 0, 2LL * S3 * D, s));
@@ -436,11 +434,9 @@ int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
       {Mt, dzm_t, d.o_t, d.ctx_t, do_t, dctx_t, d.wout_t, d.wo_t, d.dwout_t, d.dbout_t, d.dwo_t, d.dbo_t},
   };
   for (const Side& sd : sides) {
-    SER_TRY(colsum(sd.dz, f, D, sd.M, D, sd.dbout, s));
-    SER_TRY(linear_wgrad(dt, sd.M, D, S, sd.dz, D, sd.o, S, sd.dwout, S, s));
+    SER_TRY(linear_wgrad(dt, sd.M, D, S, sd.dz, D, sd.o, S, sd.dwout, S, s, sd.dbout));
     SER_TRY(linear_dgrad(dt, sd.M, D, S, sd.dz, D, sd.wout, S, sd.dob, S, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
-    SER_TRY(colsum(sd.dob, f, S, sd.M, S, sd.dbo, s));
-    SER_TRY(linear_wgrad(dt, sd.M, S, S, sd.dob, S, sd.ctx, S, sd.dwo, S, s));
+    SER_TRY(linear_wgrad(dt, sd.M, S, S, sd.dob, S, sd.ctx, S, sd.dwo, S, s, sd.dbo));
     SER_TRY(linear_dgrad(dt, sd.M, S, S, sd.dob, S, sd.wo, S, sd.dctx, S, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
   }
   // attention core backward
@@ -474,17 +470,14 @@ int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
   };
   for (const InProjB& p : ip) {
     const void* g = off(p.dp, p.col, dt);
-    SER_TRY(colsum(g, f, S3, p.M, S, p.db + p.wrow, s));
-    SER_TRY(linear_wgrad(dt, p.M, S, S, g, S3, off(p.src, p.col, dt), S3, p.dw + static_cast<long long>(p.wrow) * S, S, s));
+    SER_TRY(linear_wgrad(dt, p.M, S, S, g, S3, off(p.src, p.col, dt), S3, p.dw + static_cast<long long>(p.wrow) * S, S, s, p.db + p.wrow));
     SER_TRY(linear_dgrad(dt, p.M, S, S, g, S3, off(p.w, static_cast<long long>(p.wrow) * S, dt), S,
                          off(p.dsrc, p.col, dt), S3, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
   }
   // outer projections + residual path
-  SER_TRY(colsum(dqkv_a, f, S3, Ma, S3, d.dbqkv_a, s));
-  SER_TRY(linear_wgrad(dt, Ma, S3, D, dqkv_a, S3, d.a, D, d.dwqkv_a, D, s));
+  SER_TRY(linear_wgrad(dt, Ma, S3, D, dqkv_a, S3, d.a, D, d.dwqkv_a, D, s, d.dbqkv_a));
   SER_TRY(linear_dgrad(dt, Ma, S3, D, dqkv_a, S3, d.wqkv_a, D, d.da, D, f, nullptr, 0, f, GATE_NONE, dz_a, D, f, s));
-  SER_TRY(colsum(dqkv_t, f, S3, Mt, S3, d.dbqkv_t, s));
-  SER_TRY(linear_wgrad(dt, Mt, S3, D, dqkv_t, S3, d.t, D, d.dwqkv_t, D, s));
+  SER_TRY(linear_wgrad(dt, Mt, S3, D, dqkv_t, S3, d.t, D, d.dwqkv_t, D, s, d.dbqkv_t));
   SER_TRY(linear_dgrad(dt, Mt, S3, D, dqkv_t, S3, d.wqkv_t, D, d.dt, D, f, nullptr, 0, f, GATE_NONE, dz_t, D, f, s));
   return SER_OK;
 }
@@ -516,8 +509,7 @@ int asp_module_bwd(const ser_asp_desc& d, cudaStream_t s) {
   SER_CUDA_CHECK(cudaMemsetAsync(d.dw2, 0, sizeof(float) * d.Hd, s));
   SER_CUDA_CHECK(cudaMemsetAsync(d.db2, 0, sizeof(float), s));
   SER_TRY(asp_bwd(to_asp(d), s));
-  SER_TRY(colsum(d.dpre, f, d.Hd, M, d.Hd, d.db1, s));
-  SER_TRY(linear_wgrad(dt, M, d.Hd, d.D, d.dpre, d.Hd, d.x, d.D, d.dw1, d.D, s));
+  SER_TRY(linear_wgrad(dt, M, d.Hd, d.D, d.dpre, d.Hd, d.x, d.D, d.dw1, d.D, s, d.db1));
   SER_TRY(linear_dgrad(dt, M, d.Hd, d.D, d.dpre, d.Hd, d.w1, d.D, d.dx, d.D, f, nullptr, 0, f, GATE_NONE, d.dx, d.D, f, s));
   return SER_OK;
 }
@@ -585,15 +577,12 @@ int fusion_bwd(const ser_fusion_desc& d, cudaStream_t s) {
       {dpt, dgt, dht, d.pt, d.ht, d.tv, d.wg1t, d.w2t, d.w1t, d.dwg1t, d.dbg1t, d.dw2t, d.db2t, d.dw1t, d.db1t, d.dtv},
   };
   for (const Side& sd : sides) {
-    SER_TRY(colsum(sd.dg, f, G, B, G, sd.dbg1, s));
-    SER_TRY(linear_wgrad(dt, B, G, P, sd.dg, G, sd.p, P, sd.dwg1, P, s));
+    SER_TRY(linear_wgrad(dt, B, G, P, sd.dg, G, sd.p, P, sd.dwg1, P, s, sd.dbg1));
     SER_TRY(linear_dgrad(dt, B, G, P, sd.dg, G, sd.wg1, P, sd.dp, P, f, nullptr, 0, f, GATE_NONE, sd.dp, P, f, s));
-    SER_TRY(colsum(sd.dp, f, P, B, P, sd.db2, s));
-    SER_TRY(linear_wgrad(dt, B, P, P, sd.dp, P, sd.h, P, sd.dw2, P, s));
+    SER_TRY(linear_wgrad(dt, B, P, P, sd.dp, P, sd.h, P, sd.dw2, P, s, sd.db2));
     // h is saved post-dropout: h > 0 exactly where the unit was kept and the ReLU open; the kept units carry 1/(1-p)
     SER_TRY(linear_dgrad(dt, B, P, P, sd.dp, P, sd.w2, P, sd.dh, P, f, sd.h, P, f, GATE_RELU, nullptr, 0, f, s, hscale));
-    SER_TRY(colsum(sd.dh, f, P, B, P, sd.db1, s));
-    SER_TRY(linear_wgrad(dt, B, P, Din, sd.dh, P, sd.v, Din, sd.dw1, Din, s));
+    SER_TRY(linear_wgrad(dt, B, P, Din, sd.dh, P, sd.v, Din, sd.dw1, Din, s, sd.db1));
     SER_TRY(linear_dgrad(dt, B, P, Din, sd.dh, P, sd.w1, Din, sd.dv, Din, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
   }
   return SER_OK;
@@ -728,8 +717,7 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_out_b, 0, sizeof(float) * F, s));
   SER_TRY(layernorm_bwd(df, 1, d.q, 1, d.stats_q, d.ln_out_g, d.ln_out_b, nullptr, 1, dq, f, nullptr, 1, d.dln_out_g,
                         d.dln_out_b, B, F, 1, s));
-  SER_TRY(colsum(dq, f, F, B, F, d.db_out, s));
-  SER_TRY(linear_wgrad(dt, B, F, P, dq, F, d.h_last, P, d.dw_out, P, s));
+  SER_TRY(linear_wgrad(dt, B, F, P, dq, F, d.h_last, P, d.dw_out, P, s, d.db_out));
   SER_TRY(linear_dgrad(dt, B, F, P, dq, F, d.w_out, P, dh32, P, 1, nullptr, 0, 1, GATE_NONE, nullptr, 0, 1, s));
   ClfStackArgs sa;
   bool fused = stack_args(d, sa) && stack_grad_args(d, sa);
@@ -778,20 +766,17 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
     GemmArgs g;
     g.dtype = dt; g.M = P; g.N = P; g.K = B; g.a_trans = 1; g.b_trans = 1; g.lda = P; g.ldb = P; g.ldc = P; g.c_f32 = 1;
     g.batch = L; g.strideA = static_cast<long long>(BP); g.strideB = static_cast<long long>(BP);
-    g.A = dhn_all; g.B = d.r; g.C = d.dw2[0]; g.strideC = sw2;
+    // bias gradients ride on the weight-gradient GEMMs (row sums of the MN-major dY operand)
+    g.A = dhn_all; g.B = d.r; g.C = d.dw2[0]; g.strideC = sw2; g.rowsum = d.db2[0]; g.strideRS = sb2;
     SER_TRY(gemm(g, s));
-    g.A = dr_all; g.B = d.n; g.C = d.dw1[0]; g.strideC = sw1;
+    g.A = dr_all; g.B = d.n; g.C = d.dw1[0]; g.strideC = sw1; g.rowsum = d.db1[0]; g.strideRS = sb1;
     SER_TRY(gemm(g, s));
-    SER_TRY(colsum_batched(dhn_all, f, P, B, P, d.db2[0], L, static_cast<long long>(BP), sb2, s));
-    SER_TRY(colsum_batched(dr_all, f, P, B, P, d.db1[0], L, static_cast<long long>(BP), sb1, s));
   } else {
     for (int i = 0; i < L; ++i) {
       const void* dhn_i = off(static_cast<const void*>(dhn_all), static_cast<long long>(i) * BP, dt);
       const void* dr_i = off(static_cast<const void*>(dr_all), static_cast<long long>(i) * BP, dt);
-      SER_TRY(colsum(dhn_i, f, P, B, P, d.db2[i], s));
-      SER_TRY(linear_wgrad(dt, B, P, P, dhn_i, P, off(static_cast<const void*>(d.r), static_cast<long long>(i) * BP, dt), P, d.dw2[i], P, s));
-      SER_TRY(colsum(dr_i, f, P, B, P, d.db1[i], s));
-      SER_TRY(linear_wgrad(dt, B, P, P, dr_i, P, off(static_cast<const void*>(d.n), static_cast<long long>(i) * BP, dt), P, d.dw1[i], P, s));
+      SER_TRY(linear_wgrad(dt, B, P, P, dhn_i, P, off(static_cast<const void*>(d.r), static_cast<long long>(i) * BP, dt), P, d.dw2[i], P, s, d.db2[i]));
+      SER_TRY(linear_wgrad(dt, B, P, P, dr_i, P, off(static_cast<const void*>(d.n), static_cast<long long>(i) * BP, dt), P, d.dw1[i], P, s, d.db1[i]));
     }
   }
   // ---- input projection: h0 = relu(LN(p0)) ----
@@ -800,8 +785,7 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
   SER_CUDA_CHECK(cudaMemsetAsync(d.dln_in_b, 0, sizeof(float) * P, s));
   SER_TRY(layernorm_bwd(cur, 1, d.p0, 1, d.stats0, d.ln_in_g, d.ln_in_b, nullptr, 1, dp0, f, nullptr, 1, d.dln_in_g,
                         d.dln_in_b, B, P, 1, s));
-  SER_TRY(colsum(dp0, f, P, B, P, d.db_in, s));
-  SER_TRY(linear_wgrad(dt, B, P, P, dp0, P, d.x, P, d.dw_in, P, s));
+  SER_TRY(linear_wgrad(dt, B, P, P, dp0, P, d.x, P, d.dw_in, P, s, d.db_in));
   if (d.dx != nullptr)
     SER_TRY(linear_dgrad(dt, B, P, P, dp0, P, d.w_in, P, d.dx, P, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
   return SER_OK;

@@ -104,6 +104,36 @@ run_case("tc dW nosplit", bf, 256, 768, 5000, True, True, out_dtype=f32, splits=
 run_case("tc dW bn128", bf, 768, 128, 4096, True, True, out_dtype=f32)
 run_case("tc A MN-major only", bf, 256, 256, 1024, True, False, out_dtype=f32)
 
+
+def rowsum_case(name, dtype, M, N, K, splits=0, b_trans=True):
+    """dW-type GEMM with the bias gradient (row sums of op(A)) as a by-product."""
+    global fails
+    a = torch.randn(K, M, device=dev).to(dtype)
+    b = (torch.randn(K, N, device=dev) if b_trans else torch.randn(N, K, device=dev)).to(dtype)
+    rs = torch.full((M,), 7.0, device=dev)          # must be overwritten, not accumulated
+    out = L.gemm(a, b, a_trans=True, b_trans=b_trans, out_dtype=f32, splits=splits, rowsum=rs)
+    torch.cuda.synchronize()
+    ref = a.double().t() @ (b.double() if b_trans else b.double().t())
+    ref_rs = a.double().sum(0)
+    e1 = ((out.double() - ref).abs().max() / (ref.abs().max() + 1e-9)).item()
+    e2 = ((rs.double() - ref_rs).abs().max() / (ref_rs.abs().max() + 1e-9)).item()
+    ok = e1 < 2e-3 and e2 < 1e-4
+    print(f"[{'ok' if ok else 'FAIL'}] {name}: M={M} N={N} K={K} splits={splits} dW err={e1:.2e} rowsum err={e2:.2e}")
+    if not ok:
+        fails += 1
+        bad = ((rs.double() - ref_rs).abs() / (ref_rs.abs().max() + 1e-9) > 1e-4).nonzero().flatten()[:8].tolist()
+        print("   bad rows:", bad, "got", rs[bad].tolist(), "ref", ref_rs[bad].tolist())
+
+
+print("== dW GEMM + fused bias gradient ==")
+rowsum_case("tc rowsum bn256 split", bf, 768, 768, 20000)
+rowsum_case("tc rowsum bn256 nosplit", bf, 256, 768, 5000, splits=1)
+rowsum_case("tc rowsum bn128", bf, 768, 128, 4096)
+rowsum_case("tc rowsum M tail", bf, 200, 256, 3000)
+rowsum_case("tc rowsum tiny", bf, 512, 512, 256)
+rowsum_case("tc rowsum B K-major (fallback colsum)", bf, 256, 256, 1024, b_trans=False)
+rowsum_case("simt rowsum (fallback colsum)", f32, 192, 128, 700)
+
 print("== timing ==")
 
 
