@@ -77,6 +77,9 @@ int ser_gemm(const ser_gemm_desc* d, void* stream);
 /* ---- utilities ------------------------------------------------------------------------------ */
 /* fp32 -> bf16 parameter copy (the Python modules keep fp32 masters; bf16 tier consumes copies)    */
 int ser_cast(const void* src, int src_f32, void* dst, int dst_f32, long long n, void* stream);
+/* the same for up to 16 buffers in ONE launch, fp32 -> bf16 (all modules of a head before its forward);
+ * src / dst / counts are HOST arrays of length n, counts multiples of 8 elements                      */
+int ser_cast_multi(int n, const void* const* src, void* const* dst, const long long* counts, void* stream);
 
 /* row/column primitives behind the individually callable children of the classifier
  * (nn.LayerNorm / bias-gradient column sums; src/train.py:221-236 calls those children one by one)  */

@@ -103,6 +103,7 @@ def load():
     P, I, LL, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
     lib.ser_gemm.argtypes = [C.POINTER(GemmDesc), P]
     lib.ser_cast.argtypes = [P, I, P, I, LL, P]
+    lib.ser_cast_multi.argtypes = [I, P, P, P, P]
     lib.ser_layernorm_fwd.argtypes = [P, I, P, I, P, P, P, I, I, I, P]
     lib.ser_layernorm_bwd.argtypes = [P, I, P, I, P, P, P, P, I, P, P, I, I, I, P]
     lib.ser_colsum.argtypes = [P, I, LL, I, I, P, P]

@@ -33,6 +33,7 @@ class FlatParams:
         self.total = off
         self.flat: torch.Tensor | None = None
         self._lowp: Dict[torch.dtype, torch.Tensor] = {}
+        self._fresh: Dict[torch.dtype, tuple] = {}     # set by precast(): parameter versions the low-precision copy holds
         self.index = {n: i for i, n in enumerate(self.names)}
         # data-parallel hook: called as hook(flat_params, flat_grad_buffer) at the end of the module's backward,
         # i.e. as soon as this module's gradients are final (see parallel.py)
@@ -77,14 +78,47 @@ class FlatParams:
         self.ensure()
         if dtype == torch.float32:
             return self.flat
-        buf = self._lowp.get(dtype)
-        if buf is None or buf.device != self.flat.device:
-            buf = torch.empty(self.total, device=self.flat.device, dtype=dtype)
-            self._lowp[dtype] = buf
+        buf = self._lowp_buffer(dtype)
+        # already cast for this forward by precast() (one launch for all modules) -- unless a parameter was
+        # modified in between (optimizer step, load_state_dict), which bumps its version counter
+        stamp = self._fresh.pop(dtype, None)
+        if stamp is not None and stamp == self._versions():
+            return buf
         lib = _lib.load()
         _lib.check(lib.ser_cast(self.flat.data_ptr(), 1, buf.data_ptr(), 0, self.total,
                                 _lib.stream_ptr(self.flat.device)), "ser_cast")
         return buf
+
+    def _versions(self):
+        return tuple(p._version for p in self.params)
+
+    def _lowp_buffer(self, dtype: torch.dtype) -> torch.Tensor:
+        buf = self._lowp.get(dtype)
+        if buf is None or buf.device != self.flat.device:
+            buf = torch.empty(self.total, device=self.flat.device, dtype=dtype)
+            self._lowp[dtype] = buf
+        return buf
+
+    @staticmethod
+    def precast(flats: Sequence["FlatParams"], dtype: torch.dtype) -> None:
+        """Produce the bf16 operand copies of several modules with ONE launch (ser_cast_multi); each module's next
+        compute_copy(dtype) then returns its buffer without casting again.  No-op for float32."""
+        if dtype == torch.float32 or not flats:
+            return
+        for fp in flats:
+            fp.ensure()
+        lib = _lib.load()
+        dev = flats[0].flat.device
+        for i in range(0, len(flats), 16):
+            chunk = flats[i:i + 16]
+            bufs = [fp._lowp_buffer(dtype) for fp in chunk]
+            n = len(chunk)
+            src = (C.c_void_p * n)(*[fp.flat.data_ptr() for fp in chunk])
+            dst = (C.c_void_p * n)(*[b.data_ptr() for b in bufs])
+            cnt = (C.c_longlong * n)(*[fp.total for fp in chunk])
+            _lib.check(lib.ser_cast_multi(n, src, dst, cnt, _lib.stream_ptr(dev)), "ser_cast_multi")
+            for fp in chunk:
+                fp._fresh[dtype] = fp._versions()
 
     def new_grad_buffer(self) -> torch.Tensor:
         return torch.zeros(self.total, device=self.flat.device, dtype=torch.float32)

@@ -67,6 +67,10 @@ int ser_cast(const void* src, int src_f32, void* dst, int dst_f32, long long n, 
   return ser::cast_any(src, src_f32, dst, dst_f32, n, SER_STREAM(stream));
 }
 
+int ser_cast_multi(int n, const void* const* src, void* const* dst, const long long* counts, void* stream) {
+  return ser::cast_multi(n, src, dst, counts, SER_STREAM(stream));
+}
+
 int ser_layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, const float* gamma, const float* beta,
                       float* stats, int M, int N, int relu, void* stream) {
   return ser::layernorm_fwd(x, x_f32, y, y_f32, nullptr, 1, gamma, beta, stats, M, N, relu, SER_STREAM(stream));

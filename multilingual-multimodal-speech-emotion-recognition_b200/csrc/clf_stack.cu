@@ -128,6 +128,8 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t cta) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
@@ -383,16 +385,43 @@ struct StackParams {
   DropSpec drop;                           // block[3] / block[5] dropout (site = DS_CLF_BLOCK0 + 2 layer + {0, 1}); off by default
 };
 
-// multiply the thread's 64-column slice of row `row` by the dropout mask of `site` ([B, 512] site: 256 pairs per row)
-__device__ __forceinline__ void drop_slice(const DropSpec& base, unsigned site, int row, int col0, float (&v)[NS]) {
-  DropSpec d = base;
-  d.site = site;
-  const DropKey key = drop_key(d);
-  const unsigned pair0 = static_cast<unsigned>(row) * (PD / 2) + static_cast<unsigned>(col0 >> 1);
+// keep decisions of the thread's 64-column slice of row `row` at dropout site `site` ([B, 512] site: 256 pairs per
+// row), bit k = keep column col0 + k.  Data independent: computed while the thread waits for the tensor cores.
+__device__ __forceinline__ unsigned keep_bits16(const DropKey& key, unsigned pair0, unsigned thr) {
+  unsigned m = 0u;
 #pragma unroll
-  for (int k = 0; k < NS / 2; ++k) {
-    const float2 m = drop_pair(key, pair0 + k, d.thr, d.scale);
-    v[2 * k] *= m.x; v[2 * k + 1] *= m.y;
+  for (int k = 0; k < 16; ++k) {
+    const unsigned b = drop_bits(key, pair0 + k);
+    m |= (((b & 0xffffu) >= thr) ? 1u : 0u) << (2 * k);
+    m |= (((b >> 16) >= thr) ? 1u : 0u) << (2 * k + 1);
+  }
+  return m;
+}
+// `split`: M = 64 clusters leave lanes 16..31 of every row-owner warp without a row; they hash the upper 32 columns of
+// their partner lane's row (same `row` value by construction) and the halves are swapped with one shuffle.
+__device__ __forceinline__ unsigned long long drop_slice_bits(const DropSpec& d, unsigned long long seed, unsigned site,
+                                                             int row, int col0, bool split, int lane) {
+  const DropKey key = drop_key_of(seed, site);      // (the seed is read from global memory once per kernel)
+  const unsigned pair0 = static_cast<unsigned>(row) * (PD / 2) + static_cast<unsigned>(col0 >> 1);
+  unsigned lo, hi;
+  if (split) {
+    const unsigned half = static_cast<unsigned>(lane) >> 4;
+    const unsigned mine = keep_bits16(key, pair0 + half * (NS / 4), d.thr);
+    const unsigned other = __shfl_xor_sync(0xffffffffu, mine, 16);
+    lo = half ? other : mine;
+    hi = half ? mine : other;
+  } else {
+    lo = keep_bits16(key, pair0, d.thr);
+    hi = keep_bits16(key, pair0 + NS / 4, d.thr);
+  }
+  return (static_cast<unsigned long long>(hi) << 32) | lo;
+}
+__device__ __forceinline__ void drop_slice_apply(unsigned long long bits, float scale, float (&v)[NS]) {
+  const unsigned lo = static_cast<unsigned>(bits), hi = static_cast<unsigned>(bits >> 32);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    v[k] = ((lo >> k) & 1u) ? v[k] * scale : 0.f;
+    v[32 + k] = ((hi >> k) & 1u) ? v[32 + k] * scale : 0.f;
   }
 }
 
@@ -503,6 +532,7 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
     const bool valid = active && row < p.B;
     const int col0 = static_cast<int>(c.rank) * NS;
     const uint32_t taddr = c.tmem + (static_cast<uint32_t>(q * 32) << 16);
+    const unsigned long long dseed = DROP ? __ldg(p.drop.seed) : 0ull;
     float hv[NS];
     if (valid) load_vec64(p.h + static_cast<size_t>(row) * PD + col0, hv);
     else {
@@ -543,7 +573,12 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       publish_slice(c, nv, rl, active, et, xchg_block(c, p.xchg, 2 * i), &tmN, col0, i);
       tc_fence_before();
       SER_TL(3);
-      cluster_sync_all();
+      // the dropout decisions are data independent: hashed inside the cluster barrier, while this SM's MMA warp is
+      // idle too (hashing during the GEMM would compete with the single MMA-issuing thread for issue slots)
+      unsigned long long keep = 0ull;
+      cluster_arrive();
+      if (DROP) keep = drop_slice_bits(p.drop, dseed, DS_CLF_BLOCK0 + 2 * i, row, col0, c.rm != RM, lane);
+      cluster_wait();
       SER_TL(4);
       // ---- u = relu(W1 n + b1)
       mbar_wait(c.acc_full, 0u);
@@ -554,11 +589,13 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       lds_vec(par_addr(c, pb, 4), par, NS);
 #pragma unroll
       for (int k = 0; k < NS; ++k) nv[k] = fmaxf(nv[k] + par[k], 0.f);
-      if (DROP) drop_slice(p.drop, DS_CLF_BLOCK0 + 2 * i, row, col0, nv);       // block[3]; r is saved post-dropout
+      if (DROP) drop_slice_apply(keep, p.drop.scale, nv);                      // block[3]; r is saved post-dropout
       publish_slice(c, nv, rl, active, et, xchg_block(c, p.xchg, 2 * i + 1), &tmR, col0, i);
       tc_fence_before();
       SER_TL(6);
-      cluster_sync_all();
+      cluster_arrive();
+      if (DROP) keep = drop_slice_bits(p.drop, dseed, DS_CLF_BLOCK0 + 2 * i + 1, row, col0, c.rm != RM, lane);
+      cluster_wait();
       SER_TL(7);
       // ---- h_next = y + W2 u + b2
       mbar_wait(c.acc_full, 1u);
@@ -570,7 +607,7 @@ clf_stack_fwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
       if (DROP) {                                                              // block[5]: y + dropout(W2 u + b2)
 #pragma unroll
         for (int k = 0; k < NS; ++k) nv[k] += par[k];
-        drop_slice(p.drop, DS_CLF_BLOCK0 + 2 * i + 1, row, col0, nv);
+        drop_slice_apply(keep, p.drop.scale, nv);
 #pragma unroll
         for (int k = 0; k < NS; ++k) hv[k] += nv[k];
       } else {
@@ -660,6 +697,7 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.sColacc + et * 4), "f"(0.f) : "memory");
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(c.sColacc + (et + 128) * 4), "f"(0.f) : "memory");
     named_bar_sync(1, 128);
+    const unsigned long long dseed = DROP ? __ldg(p.drop.seed) : 0ull;
     float gv[NS];
     if (valid) load_vec64(p.dh_in + static_cast<size_t>(row) * PD + col0, gv);
     else {
@@ -668,6 +706,8 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
     }
     // parameter vectors in shared memory: 0 gamma_o, 1 beta_o, 2 gamma_i
     par_prefetch(c, p, L - 1, (L - 1) & 1, et, col0, true);
+    unsigned long long keep = 0ull;             // block[5] keep bits of the block about to be processed
+    if (DROP) keep = drop_slice_bits(p.drop, dseed, DS_CLF_BLOCK0 + 2 * (L - 1) + 1, row, col0, c.rm != RM, lane);
     for (int i = L - 1; i >= 0; --i) {
       const bool tl = (p.dbg != nullptr) && (blockIdx.x == 0) && (et == 0) && (i == L / 2);
       const int pb = i & 1;
@@ -679,14 +719,16 @@ clf_stack_bwd_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_cons
         float gm[NS];
 #pragma unroll
         for (int k = 0; k < NS; ++k) gm[k] = gv[k];
-        drop_slice(p.drop, DS_CLF_BLOCK0 + 2 * i + 1, row, col0, gm);
+        drop_slice_apply(keep, p.drop.scale, gm);
         publish_slice(c, gm, rl, active, et, xchg_block(c, p.xchg, 2 * (L - 1 - i)), &tmDhn, col0, i);
       } else {
         publish_slice(c, gv, rl, active, et, xchg_block(c, p.xchg, 2 * (L - 1 - i)), &tmDhn, col0, i);
       }
       tc_fence_before();
       SER_TL(17);
-      cluster_sync_all();
+      cluster_arrive();
+      if (DROP && i > 0) keep = drop_slice_bits(p.drop, dseed, DS_CLF_BLOCK0 + 2 * (i - 1) + 1, row, col0, c.rm != RM, lane);   // next block's mask
+      cluster_wait();
       SER_TL(18);
       // operands of the epilogues below, requested while the GEMM runs (row-per-thread loads: 32 L1 wavefronts per
       // instruction -- they must not sit in front of the publish in the load/store pipe, measured +4500 cycles)

@@ -51,13 +51,14 @@ __device__ __forceinline__ unsigned drop_mix(unsigned x) {
   x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
   return x;
 }
-__device__ __forceinline__ DropKey drop_key(const DropSpec& d) {
-  const unsigned long long s = __ldg(d.seed);
+// key of (seed value, site); kernels that visit many sites load the seed once and derive the keys from the register
+__device__ __forceinline__ DropKey drop_key_of(unsigned long long s, unsigned site) {
   DropKey k;
-  k.add = drop_mix(static_cast<unsigned>(s) + 0x9E3779B9u * (d.site + 1u));
+  k.add = drop_mix(static_cast<unsigned>(s) + 0x9E3779B9u * (site + 1u));
   k.mul = drop_mix(static_cast<unsigned>(s >> 32) ^ k.add ^ 0x7F4A7C15u) | 1u;
   return k;
 }
+__device__ __forceinline__ DropKey drop_key(const DropSpec& d) { return drop_key_of(__ldg(d.seed), d.site); }
 // the two 16-bit draws of column pair `pair` (= row * ceil(cols/2) + col/2)
 __device__ __forceinline__ unsigned drop_bits(const DropKey& k, unsigned pair) { return drop_mix((pair + k.add) * k.mul); }
 // multipliers (0 or scale) of the even / odd column of a pair

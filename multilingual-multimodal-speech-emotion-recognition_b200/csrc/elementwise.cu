@@ -12,6 +12,7 @@ namespace {
 
 constexpr float kLnEps = 1e-5f;
 constexpr int kMaxChunks = 4;     // N <= 1024
+constexpr int kCastSegs = 16;
 
 __device__ __forceinline__ void load8_dyn(const void* p, size_t idx, int f32, float (&v)[8]) {
   if (f32) load8(reinterpret_cast<const float*>(p) + idx, v);
@@ -33,6 +34,28 @@ __global__ void cast_kernel(const void* __restrict__ src, int src_f32, void* __r
     } else {
       for (long long j = i; j < n; ++j) st_dyn(dst, j, dst_f32, ld_dyn(src, j, src_f32));
     }
+  }
+}
+
+// fp32 -> bf16 copies of up to kCastSegs parameter buffers in ONE launch (every module's flat buffer is a multiple of
+// 64 elements, so an 8-element vector never straddles two segments)
+struct CastSegs {
+  const float* src[kCastSegs];
+  __nv_bfloat16* dst[kCastSegs];
+  long long end[kCastSegs];        // exclusive prefix sums of the segment lengths, in 8-element vectors
+  int n;
+};
+__global__ void __launch_bounds__(256)
+cast_multi_kernel(const CastSegs segs) {
+  const long long total = segs.end[segs.n - 1];
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int k = 0;
+    while (i >= segs.end[k]) ++k;
+    const long long local = i - (k == 0 ? 0 : segs.end[k - 1]);
+    float v[8];
+    load8(segs.src[k] + local * 8, v);
+    store8(segs.dst[k] + local * 8, v);
   }
 }
 
@@ -532,6 +555,28 @@ int cast_any(const void* src, int src_f32, void* dst, int dst_f32, long long n, 
   if (blocks < 1) blocks = 1;
   ProfScope prof("cast", 0.0, static_cast<double>(n) * ((src_f32 ? 4 : 2) + (dst_f32 ? 4 : 2)), s);
   cast_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(src, src_f32, dst, dst_f32, n);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+int cast_multi(int n, const void* const* src, void* const* dst, const long long* counts, cudaStream_t s) {
+  SER_REQUIRE(n >= 1 && n <= kCastSegs, "cast_multi: 1..16 segments");
+  CastSegs segs{};
+  long long acc = 0, bytes = 0;
+  for (int i = 0; i < n; ++i) {
+    SER_REQUIRE(counts[i] > 0 && counts[i] % 8 == 0, "cast_multi: segment lengths must be positive multiples of 8");
+    SER_REQUIRE((reinterpret_cast<uintptr_t>(src[i]) & 31) == 0 && (reinterpret_cast<uintptr_t>(dst[i]) & 15) == 0,
+                "cast_multi: segments must be 32-byte (fp32) / 16-byte (bf16) aligned");
+    segs.src[i] = reinterpret_cast<const float*>(src[i]);
+    segs.dst[i] = reinterpret_cast<__nv_bfloat16*>(dst[i]);
+    acc += counts[i] / 8;
+    segs.end[i] = acc;
+    bytes += counts[i] * 6;
+  }
+  segs.n = n;
+  ProfScope prof("cast", 0.0, static_cast<double>(bytes), s);
+  const int blocks = static_cast<int>(min(static_cast<long long>(device_sm_count()) * 8, (acc + 255) / 256));
+  cast_multi_kernel<<<blocks, 256, 0, s>>>(segs);
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

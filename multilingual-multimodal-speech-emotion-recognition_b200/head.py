@@ -8,6 +8,7 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
+from ._params import FlatParams
 from .functional import HeadLossFn
 from .models import (AdvancedOpenMaxClassifier, AttentiveStatsPooling, BottleneckAdapter, CrossModalAttention,
                      FusionLayer, PrototypeMemory)
@@ -69,6 +70,9 @@ class FusionHead(nn.Module):
             getattr(self, k).load_state_dict(weights[k], strict=True)
 
     def features(self, a_hid, t_hid, a_mask=None, t_mask=None):
+        # bf16 tier: the operand copies of all modules' weights in one launch instead of one per module
+        FlatParams.precast([getattr(self, g)._flat for g in self.GROUPS if hasattr(getattr(self, g), "_flat")],
+                           a_hid.dtype)
         a_seq = self.adapter_a.residual_forward(a_hid)
         t_seq = self.adapter_t.residual_forward(t_hid)
         a_enh, t_enh = self.cross(a_seq, t_seq, a_mask, t_mask)
