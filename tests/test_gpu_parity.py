@@ -81,6 +81,36 @@ def test_dropout_train_eval_and_reseeding():
     assert torch.equal(hd2(*args)["logits"], l2)
 
 
+def test_precast_tracks_parameter_updates():
+    """FusionHead casts the bf16 operand copies of all modules in one launch per forward (FlatParams.precast); an
+    in-place parameter update between two forwards (what an optimizer step is) must be picked up."""
+    import mmser_b200
+    from oracle import synth
+    dev = _dev()
+    C = 4
+    w = synth.head_weights(C)
+    a, t, am, tm, labels = synth.make_inputs(8, 40, 12, C, seed=9)
+    args = (a.to(dev).bfloat16(), t.to(dev).bfloat16(), am.to(dev), tm.to(dev))
+    head = mmser_b200.FusionHead(C).to(dev).eval(); head.load_group_state(w)
+    with torch.no_grad():
+        l1 = head(*args)["logits"].clone()
+        head.fusion.proj_a[0].weight.mul_(1.5)                      # in-place, like optimizer.step()
+        head.adapter_t[0].bias.add_(0.25)
+        l2 = head(*args)["logits"].clone()
+        w2 = {g: {k: v.clone() for k, v in head_state.items()} for g, head_state in
+              ((g, getattr(head, g).state_dict()) for g in head.GROUPS)}
+        fresh = mmser_b200.FusionHead(C).to(dev).eval(); fresh.load_group_state(w2)
+        l3 = fresh(*args)["logits"]
+    assert not torch.equal(l1, l2)
+    assert torch.equal(l2, l3)
+    # calling a module on its own (no head-level precast) after another update also sees the new weights
+    with torch.no_grad():
+        f1 = head.fusion(torch.ones(2, 1536, device=dev).bfloat16(), torch.ones(2, 1536, device=dev).bfloat16()).clone()
+        head.fusion.proj_t[3].weight.mul_(0.5)
+        f2 = head.fusion(torch.ones(2, 1536, device=dev).bfloat16(), torch.ones(2, 1536, device=dev).bfloat16())
+    assert not torch.equal(f1, f2)
+
+
 def test_argmax_bit_exact_and_anchor_zero():
     """Predictions (argmax of logits) are bit-identical to the oracle; anchor loss is exactly 0 with zero grads."""
     import mmser_b200
