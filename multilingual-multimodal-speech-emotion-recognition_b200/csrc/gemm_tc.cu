@@ -39,17 +39,26 @@ constexpr int kEpiWarps = 8;          // two per TMEM lane quarter: they interle
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemTotal = 232448;                    // 227 KB opt-in maximum per CTA
 constexpr int kStgTile = 32 * 128;                    // one staged chunk: 32 rows x 128 B (SWIZZLE_128B)
-constexpr int kStgBytes = kEpiWarps * 2 * kStgTile;   // per epilogue warp: one output tile + one source tile
-constexpr int kBarBytes = 256;
-constexpr int kSmemBudget = kSmemTotal - 1024 /*align*/ - kStgBytes - kBarBytes;
+constexpr int kBarBytes = 1024;                       // mbarriers, TMEM slot, and (offset 512) the 512-byte tile of ones
+constexpr int kMaxStages = 8;
 
+// Shared memory is carved at run time: an epilogue warp needs a 4 KB output staging tile and, only when a residual /
+// gate operand is streamed in, a 4 KB source tile.  GEMMs without a source operand (all dW GEMMs, most forward ones)
+// turn the 32 KB saved into one more pipeline stage: the main loop is bound by the LATENCY of a stage refill (tensor
+// pipe 50 % active with 3 stages of 48 KB in flight -- a 2-CTA multicast that halves the bytes per CTA changes
+// nothing), so depth is what buys throughput.
 template <int BN> struct TileCfg {
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = kSmemBudget / kStageBytes;      // 3 (BN = 256) / 5 (BN = 128)
   static constexpr int kTmemCols = 2 * BN;      // double-buffered accumulator
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kStgBytes + kBarBytes;
+  static constexpr int stg_bytes(bool with_src) { return kEpiWarps * (with_src ? 2 : 1) * kStgTile; }
+  // 3 / 4 stages (BN = 256, with / without source), 5 / 6 (BN = 128)
+  static constexpr int stages(bool with_src) {
+    return (kSmemTotal - 1024 /*align*/ - stg_bytes(with_src) - kBarBytes) / kStageBytes < kMaxStages
+               ? (kSmemTotal - 1024 - stg_bytes(with_src) - kBarBytes) / kStageBytes : kMaxStages;
+  }
+  static constexpr int smem_bytes(bool with_src) { return stages(with_src) * kStageBytes + 1024 + stg_bytes(with_src) + kBarBytes; }
 };
 
 enum : int { SRC_NONE = 0, SRC_RESIDUAL = 1, SRC_GATE = 2 };
@@ -107,6 +116,28 @@ __device__ __forceinline__ void tma_load_3d_raw(const CUtensorMap* tm, uint64_t*
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+// multicast variants (2-CTA clusters): the box lands at the same shared-memory offset of every CTA in `mask` and
+// signals the same-offset mbarrier in each of them
+__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -195,7 +226,7 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 // otherwise 64 bf16 columns.  SRC: residual / gate operand of the same dtype, streamed by TMA.
 // ------------------------------------------------------------------------------------------------
 struct EpiWarp {
-  uint32_t base;              // shared address of this warp's two staging tiles: output, source
+  uint32_t base;              // shared address of this warp's staging tiles: output, then (if streamed) source
   __device__ __forceinline__ uint32_t cst() const { return base; }
   __device__ __forceinline__ uint32_t sst() const { return base + kStgTile; }
   uint64_t* src_full;         // mbarrier of the source tile
@@ -334,22 +365,28 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_ones(int amaj) {
          | (static_cast<uint32_t>(kOnesN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
 }
 
-template <int BN, int AMAJ, int BMAJ, bool RS>
+// MC: launched as 2-CTA clusters.  The two CTAs of a cluster own vertically adjacent 128-row tiles of the same column
+// tile and k-range, so they need the same B tile: each loads half of it and multicasts it to both (per-CTA fill per
+// k-block drops from 16 + BN/8 KB to 16 + BN/16 KB); a stage is free once BOTH CTAs' MMAs have retired it
+// (tcgen05.commit multicast onto both empty barriers, arrival count 2).
+template <int BN, int AMAJ, int BMAJ, bool RS, bool MC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS,
-               const TcEpilogue ep, const int M, const int N, const int K, const int splits, const int batch) {
+               const TcEpilogue ep, const int M, const int N, const int K, const int splits, const int batch,
+               const int nstages) {
   using Cfg = TileCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // (offset arithmetic on the __shared__ array keeps the shared address space visible to the compiler)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int stg_stride = (ep.src != SRC_NONE ? 2 : 1) * kStgTile;     // bytes of staging per epilogue warp
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint8_t* smem_stg = smem + Cfg::kStages * Cfg::kStageBytes;        // 1024-byte aligned: 16 staging tiles of 4 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + kStgBytes);
-  uint64_t* full_bar = bars;                         // [kStages]
-  uint64_t* empty_bar = bars + Cfg::kStages;         // [kStages]
-  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;     // [2]
+  uint8_t* smem_b = smem + nstages * Cfg::kABytes;
+  uint8_t* smem_stg = smem + nstages * Cfg::kStageBytes;             // 1024-byte aligned: 8 or 16 staging tiles of 4 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + kEpiWarps * stg_stride);
+  uint64_t* full_bar = bars;                         // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;           // [kMaxStages]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;       // [2]
   uint64_t* tempty_bar = tfull_bar + 2;              // [2]
   uint64_t* src_bar = tempty_bar + 2;                // [kEpiWarps]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(src_bar + kEpiWarps);
@@ -360,12 +397,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m_tiles = (M + BM - 1) / BM;
   const int n_tiles = N / BN;
   const int kblocks = (K + BK - 1) / BK;
-  const int total_tiles = m_tiles * n_tiles * splits * batch;
+  // work units: MC -> one unit = the pair of row tiles (2u, 2u+1) handled by the two CTAs of a cluster in lockstep
+  const int crank = MC ? static_cast<int>(cluster_ctarank()) : 0;
+  const int m_units = MC ? m_tiles / 2 : m_tiles;
+  const int total_tiles = m_units * n_tiles * splits * batch;
+  const int unit0 = MC ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int unit_step = MC ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MC ? 2 : 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps); }
     for (int s = 0; s < kEpiWarps; ++s) mbar_init(&src_bar[s], 1);
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
@@ -377,27 +419,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                  "r"(Cfg::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // RS: a 16-row x 128-byte K-major tile of bf16 ones lives in the last epilogue warp's (unused) source staging tile
-  uint8_t* ones_tile = smem_stg + (2 * (kEpiWarps - 1) + 1) * kStgTile;
+  // RS: the B operand of the row-sum MMA is a 16 x 16 block of bf16 ones in the un-swizzled core-matrix layout
+  // (four 128-byte core matrices = 512 bytes; all ones, so the LBO / SBO order is immaterial)
+  uint8_t* ones_tile = reinterpret_cast<uint8_t*>(bars) + 512;
   if (RS && warp >= 2) {
-    for (int i = threadIdx.x - 64; i < kOnesN * 128 / 16; i += kThreads - 64)
-      sts128(smem_u32(ones_tile) + 16u * i, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    const int i = threadIdx.x - 64;
+    if (i < 512 / 16) sts128(smem_u32(ones_tile) + 16u * i, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     fence_async_smem();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (MC) cluster_sync();       // the peer's barriers exist before anything is multicast to them
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         const int nt = tile % n_tiles;
         const int rest = tile / n_tiles;
-        const int mt = rest % m_tiles;
-        const int rest2 = rest / m_tiles;
+        const int mt = MC ? 2 * (rest % m_units) + crank : rest % m_units;
+        const int rest2 = rest / m_units;
         const int sp = rest2 % splits;
         const int bz = rest2 / splits;
         const int kb0 = static_cast<int>((static_cast<long long>(sp) * kblocks) / splits);
@@ -415,13 +459,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_3d(&tmA, &full_bar[stage], sa + j * (BK * 128), m0 + 64 * j, k0, bz);
           }
-          if (BMAJ == 0) {
+          if (MC) {
+            // this CTA's half of the B tile, delivered to both CTAs of the cluster
+            if (BMAJ == 0) {
+              tma_load_3d_mc(&tmB, &full_bar[stage], sb + crank * (BN / 2) * 128, k0, n0 + crank * (BN / 2), bz, 0x3);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j) {
+                const int jj = crank * (BN / 128) + j;
+                tma_load_3d_mc(&tmB, &full_bar[stage], sb + jj * (BK * 128), n0 + 64 * jj, k0, bz, 0x3);
+              }
+            }
+          } else if (BMAJ == 0) {
             tma_load_3d(&tmB, &full_bar[stage], sb, k0, n0, bz);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) tma_load_3d(&tmB, &full_bar[stage], sb + j * (BK * 128), n0 + 64 * j, k0, bz);
           }
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -434,13 +489,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t a_kstep = (AMAJ == 0) ? UMMA_K * 2u : UMMA_K * 128u;   // bytes per K=16 step
       constexpr uint32_t b_kstep = (BMAJ == 0) ? UMMA_K * 2u : UMMA_K * 128u;
       constexpr uint32_t idesc_ones = make_idesc_ones(AMAJ);
-      const uint64_t ones_desc = make_smem_desc(smem_u32(ones_tile), 0u, 1024);
+      // SWIZZLE_NONE descriptor: core matrices 128 B apart along K (LBO) and 256 B apart along N (SBO)
+      const uint64_t ones_desc = (make_smem_desc(smem_u32(ones_tile), 128u, 256u) & ~(7ull << 61));
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         const bool rs_tile = RS && (tile % n_tiles == 0);     // one column tile per (row tile, split) sums the rows
         const int rest = tile / n_tiles;
-        const int sp = (rest / m_tiles) % splits;
+        const int sp = (rest / m_units) % splits;
         const int kb0 = static_cast<int>((static_cast<long long>(sp) * kblocks) / splits);
         const int kb1 = static_cast<int>((static_cast<long long>(sp + 1) * kblocks) / splits);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -464,8 +520,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tc_mma_bf16(tmem_base + BN, adesc, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
-          tc_commit(&empty_bar[stage]);      // frees the smem stage once these MMAs retire
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          // frees the smem stage once these MMAs retire (MC: in both CTAs -- the peer's next multicast lands here too)
+          if (MC) tc_commit_mc(&empty_bar[stage], 0x3);
+          else tc_commit(&empty_bar[stage]);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         tc_commit(&tfull_bar[acc]);          // accumulator complete -> epilogue
         if (RS) acc_phase ^= 1;              // single accumulator buffer (columns [BN, BN+16) hold the row sums)
@@ -477,16 +535,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;                  // TMEM lane quarter this warp may access (warp id mod 4)
     const int ew = warp - 2;                 // 0..7
     EpiWarp w;
-    w.base = smem_u32(smem_stg) + static_cast<uint32_t>(ew) * (2u * kStgTile);
+    w.base = smem_u32(smem_stg) + static_cast<uint32_t>(ew * stg_stride);
     w.src_full = src_bar + ew;
     w.sphase = 0;
     w.half = ew >> 2;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = unit0; tile < total_tiles; tile += unit_step) {
       const int nt = tile % n_tiles;
       const int rest = tile / n_tiles;
-      const int mt = rest % m_tiles;
-      const int rest2 = rest / m_tiles;
+      const int mt = MC ? 2 * (rest % m_units) + crank : rest % m_units;
+      const int rest2 = rest / m_units;
       const int sp = rest2 % splits;
       const int bz = rest2 / splits;
       const int mw = mt * BM + q * 32;       // first row of this warp
@@ -528,6 +586,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols)
                  : "memory");
   }
+  if (MC) cluster_sync();       // neither CTA leaves while the other may still signal its barriers
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -576,28 +635,56 @@ int make_tmap(CUtensorMap* tm, const void* base, int f32, long long rows, long l
   return SER_OK;
 }
 
-template <int BN, int AMAJ, int BMAJ, bool RS = false>
+template <int BN, int AMAJ, int BMAJ, bool RS = false, bool MC = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmS,
            const TcEpilogue& ep, int M, int N, int K, int splits, int batch, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ, RS>;
+  auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ, RS, MC>;
   if (!configured) {
-    SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     configured = true;
   }
+  const bool with_src = ep.src != SRC_NONE;
+  static const int stage_cap = getenv("SER_GEMM_STAGES") ? atoi(getenv("SER_GEMM_STAGES")) : kMaxStages;   // A/B switch
+  int nstages = Cfg::stages(with_src);
+  if (stage_cap >= 2 && nstages > stage_cap) nstages = stage_cap;
+  const int smem_bytes = nstages * Cfg::kStageBytes + 1024 + Cfg::stg_bytes(with_src) + kBarBytes;
   const int m_tiles = ceil_div(M, BM), n_tiles = N / BN;
-  const long long total = static_cast<long long>(m_tiles) * n_tiles * splits * batch;
-  const int grid = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
-  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, tmC, tmS, ep, M, N, K, splits, batch);
+  if (!MC) {
+    const long long total = static_cast<long long>(m_tiles) * n_tiles * splits * batch;
+    const int grid = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
+    kern<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmS, ep, M, N, K, splits, batch, nstages);
+  } else {
+    const long long units = static_cast<long long>(m_tiles / 2) * n_tiles * splits * batch;
+    const long long max_clusters = device_sm_count() / 2;
+    const int clusters = static_cast<int>(units < max_clusters ? units : max_clusters);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmS, ep, M, N, K, splits, batch, nstages));
+  }
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
 
 template <int BN>
 int dispatch_major(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
-                   const CUtensorMap& tmS, const TcEpilogue& ep, int splits, cudaStream_t stream) {
+                   const CUtensorMap& tmS, const TcEpilogue& ep, int splits, bool mc, cudaStream_t stream) {
   const int nb = a.batch > 1 ? a.batch : 1;
+  if (mc) {
+    if (!a.a_trans && !a.b_trans) return launch<BN, 0, 0, false, true>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
+    if (!a.a_trans && a.b_trans) return launch<BN, 0, 1, false, true>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
+    if (a.a_trans && a.b_trans && ep.rowsum != nullptr)
+      return launch<BN, 1, 1, true, true>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
+    if (a.a_trans && a.b_trans) return launch<BN, 1, 1, false, true>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
+  }
   if (!a.a_trans && !a.b_trans) return launch<BN, 0, 0>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
   if (!a.a_trans && a.b_trans) return launch<BN, 0, 1>(tmA, tmB, tmC, tmS, ep, a.M, a.N, a.K, splits, nb, stream);
   if (a.a_trans && a.b_trans && ep.rowsum != nullptr)
@@ -653,10 +740,17 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   SER_REQUIRE(a.batch <= 1 || (a.strideA % 8 == 0 && a.strideB % 8 == 0 && a.strideC % 8 == 0),
               "gemm_tc: batch strides must be multiples of 8");
   SER_REQUIRE((reinterpret_cast<uintptr_t>(a.C) & 15) == 0, "gemm_tc: output must be 16-byte aligned");
+  // 2-CTA clusters with a multicast B tile (SER_GEMM_MC=1).  Off by default: measured on B200 it changes nothing
+  // (8192^3: 1.25 -> 1.28 PFLOP/s, the step's shapes +-0) -- each CTA still RECEIVES the whole 48 KB per k-block, and
+  // the bound is the shared-memory fill rate of an SM (~50 B/clk), not the number of bytes it requests.  An L2
+  // prefetch ahead of the pipeline made things worse (-15 %: more TMA operations per k-block).  What helps is fewer
+  // inbound bytes per MMA cycle, i.e. cta_group::2 tiles.
+  static const int mc_env = getenv("SER_GEMM_MC") ? atoi(getenv("SER_GEMM_MC")) : 0;
+  const bool mc = (mc_env == 1) && (m_tiles % 2 == 0) && !(a.a_trans && !a.b_trans);
   CUtensorMap tmA, tmB, tmC, tmS;
   if (!a.a_trans) SER_TRY(make_tmap(&tmA, a.A, 0, a.M, a.K, a.lda, BM, BK, a.batch, a.strideA));
   else            SER_TRY(make_tmap(&tmA, a.A, 0, a.K, a.M, a.lda, BK, 64, a.batch, a.strideA));
-  if (!a.b_trans) SER_TRY(make_tmap(&tmB, a.B, 0, a.N, a.K, a.ldb, BN, BK, a.batch, a.strideB));
+  if (!a.b_trans) SER_TRY(make_tmap(&tmB, a.B, 0, a.N, a.K, a.ldb, mc ? BN / 2 : BN, BK, a.batch, a.strideB));
   else            SER_TRY(make_tmap(&tmB, a.B, 0, a.K, a.N, a.ldb, BK, 64, a.batch, a.strideB));
 
   // epilogue operands travel as 32-row x 128-byte TMA boxes: 64 bf16 or 32 fp32 columns
@@ -722,8 +816,8 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
     snprintf(pname, sizeof(pname), "%s:%dx%dx%d:s%d", a.a_trans ? "gemm_tc_wgrad" : (a.b_trans ? "gemm_tc_dgrad" : "gemm_tc_fwd"),
              a.M, a.N, a.K, splits);
   ProfScope prof(pname, gflops, gbytes, stream);
-  if (BN == 256) return dispatch_major<256>(a, tmA, tmB, tmC, tmS, ep, splits, stream);
-  return dispatch_major<128>(a, tmA, tmB, tmC, tmS, ep, splits, stream);
+  if (BN == 256) return dispatch_major<256>(a, tmA, tmB, tmC, tmS, ep, splits, mc, stream);
+  return dispatch_major<128>(a, tmA, tmB, tmC, tmS, ep, splits, mc, stream);
 }
 
 }  // namespace ser
