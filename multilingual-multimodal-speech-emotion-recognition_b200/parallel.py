@@ -122,9 +122,12 @@ class GraphedTrainStep:
     are static as well, so an optimizer step between replays works as usual.
     """
 
-    def __init__(self, dp: DataParallelHead, a, t, a_mask, t_mask, labels, warmup: int = 3):
+    def __init__(self, dp: DataParallelHead, a, t, a_mask, t_mask, labels, warmup: int = 3,
+                 static_inputs: bool = False):
+        """static_inputs=True adopts the given tensors as the graph's input buffers (no private copies): the caller
+        refills them in place -- e.g. with host-to-device copies -- and calls replay()."""
         self.dp = dp
-        self.static = [None if x is None else x.clone() for x in (a, t, a_mask, t_mask, labels)]
+        self.static = [x if (static_inputs or x is None) else x.clone() for x in (a, t, a_mask, t_mask, labels)]
         side = torch.cuda.Stream(device=a.device)
         side.wait_stream(torch.cuda.current_stream(a.device))
         with torch.cuda.stream(side):                       # warm-up on a side stream, as torch.cuda.graphs requires
