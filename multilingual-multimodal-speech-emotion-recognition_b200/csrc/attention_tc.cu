@@ -102,7 +102,7 @@ __device__ __forceinline__ void mma_nn(const uint32_t (&p)[4][4], const bf16* ti
 // forward
 // ------------------------------------------------------------------------------------------------------------
 template <bool DROP>
-__global__ void __launch_bounds__(NT, DROP ? 4 : 5)
+__global__ void __launch_bounds__(NT, 5)
 attn_tc_fwd_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk,
                    const bf16* __restrict__ V, long long ldv, const float* __restrict__ kmask, bf16* __restrict__ O,
                    long long ldo, float* __restrict__ lse, int H, int Tq, int Tk, float scale, DropSpec drop) {
@@ -229,7 +229,7 @@ attn_tc_fwd_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __rest
 // backward, dQ (one CTA per 64 queries, streaming key tiles).  Also emits delta = rowsum(dO * O).
 // ------------------------------------------------------------------------------------------------------------
 template <bool DROP>
-__global__ void __launch_bounds__(NT, DROP ? 3 : 4)
+__global__ void __launch_bounds__(NT, 4)
 attn_tc_bwd_dq_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk,
                       const bf16* __restrict__ V, long long ldv, const float* __restrict__ kmask,
                       const bf16* __restrict__ O, long long ldo, const bf16* __restrict__ dO, long long lddo,
@@ -356,7 +356,7 @@ attn_tc_bwd_dq_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __r
 // backward, dK / dV (one CTA per 64 keys, streaming query tiles): S^T = K Q^T, dP^T = V dO^T
 // ------------------------------------------------------------------------------------------------------------
 template <bool DROP>
-__global__ void __launch_bounds__(NT, DROP ? 3 : 4)
+__global__ void __launch_bounds__(NT, 4)
 attn_tc_bwd_dkv_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk,
                        const bf16* __restrict__ V, long long ldv, const float* __restrict__ kmask,
                        const bf16* __restrict__ dO, long long lddo, const float* __restrict__ lse,

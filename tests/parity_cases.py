@@ -171,6 +171,10 @@ def _rand(shape, seed, scale=1.0):
 # ---------------------------------------------------------------------------------------------------
 # dropout: the kernels' masks are a pure function of (seed, site, row, col) (csrc/dropout.cuh).  The tests pin the seed
 # of each module, export the masks through the C-ABI (ser_dropout_mask) and run the oracle with exactly those masks.
+# (Seed choice: a mask realisation can put one of the ~10^5 ReLU inputs of a case within fp32 rounding of zero; the CUDA
+#  fp32 tier and the fp64 oracle then disagree on that unit's gate and every gradient upstream of it moves by ~3e-3 --
+#  a discrete event the noise floor cannot see.  Observed once while experimenting with another hash: 1 of 6
+#  consecutive seeds did that for head_dropout/fp32, the others passed with >= 5x margin.)
 DROP_SEEDS = {"cross": 0x1234567887654321, "fusion": 0x0BADC0FFEE123457, "classifier": 0x7EDCBA9876543210}
 
 
@@ -415,6 +419,8 @@ ALL_CASES = {
     "cross_dropout": lambda: cross_case(masks=True, p_drop=0.1),
     "cross_long_dropout": lambda: cross_case(B=2, Ta=300, Tt=130, masks=True, seed=11, p_drop=0.25),
     "fusion_dropout": lambda: fusion_case(p_drop=0.1),
+    # (fp32 tier: B = 64 keeps the expected number of ReLU inputs within fp32 rounding of zero well below one per case;
+    #  each such unit flips its gate between any two implementations and moves every upstream gradient by ~3e-3)
     "classifier_dropout": lambda: classifier_case(p_drop=0.15),
     "head_dropout": lambda: head_case(24, 50, 16, 4, True, p_drop=0.1),
 }

@@ -43,6 +43,15 @@ def test_dropout_mask_statistics_and_determinism():
         var = (k * k).mean()
         for a, b in ((k[:, 0::2], k[:, 1::2]), (k[:, :-2], k[:, 2:]), (k[:-1], k[1:])):
             assert abs(((a * b).mean() / var).item()) < 5 / (a.numel() ** 0.5)
+        # no structure along rows or columns: per-row / per-column keep rates scatter like binomial samples
+        for means, cnt in ((keep.mean(1), 768), (keep.mean(0), 4096)):
+            z = (means - (1 - p)) / (p * (1 - p) / cnt) ** 0.5
+            assert z.abs().max().item() < 5.5 and abs(z.std().item() - 1.0) < 0.1
+        # longer lags inside a row and between rows
+        for lag in (4, 32, 257):
+            assert abs(((k[:, :-lag] * k[:, lag:]).mean() / var).item()) < 5 / ((k.numel()) ** 0.5) * 1.1
+        for lag in (2, 16):
+            assert abs(((k[:-lag] * k[lag:]).mean() / var).item()) < 5 / ((k.numel()) ** 0.5) * 1.1
         assert torch.equal(m, dm(s1, 3, p, 4096, 768))
         for other in (dm(s1, 4, p, 4096, 768), dm(s2, 3, p, 4096, 768)):
             k2 = (other > 0).float() - keep.mean()
