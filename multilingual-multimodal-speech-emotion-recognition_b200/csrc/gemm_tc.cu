@@ -53,12 +53,13 @@ template <int BN> struct TileCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;      // double-buffered accumulator
   static constexpr int stg_bytes(bool with_src) { return kEpiWarps * (with_src ? 2 : 1) * kStgTile; }
-  // 3 / 4 stages (BN = 256, with / without source), 5 / 6 (BN = 128)
-  static constexpr int stages(bool with_src) {
-    return (kSmemTotal - 1024 /*align*/ - stg_bytes(with_src) - kBarBytes) / kStageBytes < kMaxStages
-               ? (kSmemTotal - 1024 - stg_bytes(with_src) - kBarBytes) / kStageBytes : kMaxStages;
+  // bytes of one pipeline stage in ONE CTA: a CTA of a cta_group::2 pair holds its own A rows and HALF of the B tile
+  static constexpr int stage_bytes(bool pair) { return kABytes + (pair ? kBBytes / 2 : kBBytes); }
+  // 3 / 4 stages (BN = 256, with / without source), 5 / 6 (BN = 128); pairs: 5 / 6 (BN = 256), 6 / 8 (BN = 128)
+  static constexpr int stages(bool with_src, bool pair) {
+    return (kSmemTotal - 1024 /*align*/ - stg_bytes(with_src) - kBarBytes) / stage_bytes(pair) < kMaxStages
+               ? (kSmemTotal - 1024 - stg_bytes(with_src) - kBarBytes) / stage_bytes(pair) : kMaxStages;
   }
-  static constexpr int smem_bytes(bool with_src) { return stages(with_src) * kStageBytes + 1024 + stg_bytes(with_src) + kBarBytes; }
 };
 
 enum : int { SRC_NONE = 0, SRC_RESIDUAL = 1, SRC_GATE = 2 };
@@ -117,18 +118,38 @@ __device__ __forceinline__ void tma_load_3d_raw(const CUtensorMap* tm, uint64_t*
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// multicast variants (2-CTA clusters): the box lands at the same shared-memory offset of every CTA in `mask` and
-// signals the same-offset mbarrier in each of them
-__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2,
-                                               uint16_t mask) {
+// ---- cta_group::2 (CTA pair) variants ---------------------------------------------------------------------------
+// shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on an mbarrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* tm, uint32_t leader_bar, void* dst, int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+// one thread of the leader CTA: D[256 x N] (128 rows in each CTA's tensor memory) += A[256 x 16] B[N x 16]^T, A rows and
+// B columns split between the two CTAs' shared memories (same offsets in both)
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the pair's outstanding MMAs retire) on the same-offset mbarrier of both CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(0x3)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -211,14 +232,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
-template <int BN, int AMAJ, int BMAJ>
+template <int BN, int AMAJ, int BMAJ, int MM = BM>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return (1u << 4)                               // D format F32
          | (1u << 7) | (1u << 10)                // A, B format BF16
          | (static_cast<uint32_t>(AMAJ) << 15)   // A major: 0 K, 1 MN
          | (static_cast<uint32_t>(BMAJ) << 16)   // B major
          | (static_cast<uint32_t>(BN >> 3) << 17)
-         | (static_cast<uint32_t>(BM >> 4) << 24);
+         | (static_cast<uint32_t>(MM >> 4) << 24);     // M = 128, or 256 for a cta_group::2 pair
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -360,15 +381,17 @@ __device__ __forceinline__ void epilogue_tile(const TcEpilogue& ep, const CUtens
 // kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int kOnesN = 16;                       // N of the row-sum MMA (the smallest N an M = 128 UMMA takes)
-__device__ __forceinline__ constexpr uint32_t make_idesc_ones(int amaj) {
+__device__ __forceinline__ constexpr uint32_t make_idesc_ones(int amaj, int mm) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(amaj) << 15) | (0u << 16)   // B (ones): K-major
-         | (static_cast<uint32_t>(kOnesN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+         | (static_cast<uint32_t>(kOnesN >> 3) << 17) | (static_cast<uint32_t>(mm >> 4) << 24);
 }
 
-// MC: launched as 2-CTA clusters.  The two CTAs of a cluster own vertically adjacent 128-row tiles of the same column
-// tile and k-range, so they need the same B tile: each loads half of it and multicasts it to both (per-CTA fill per
-// k-block drops from 16 + BN/8 KB to 16 + BN/16 KB); a stage is free once BOTH CTAs' MMAs have retired it
-// (tcgen05.commit multicast onto both empty barriers, arrival count 2).
+// MC ("pair"): launched as 2-CTA clusters driving ONE cta_group::2 MMA per k-step: the pair owns a 256 x BN output tile,
+// each CTA stores its own 128 A rows and HALF of the B tile (so a stage is 16 + BN/16 KB instead of 16 + BN/8 KB:
+// less shared-memory traffic per MMA cycle and a deeper pipeline), the leader CTA's elected thread issues the MMAs, and
+// each CTA's tensor memory receives its 128 accumulator rows.  All TMA bytes of a stage are counted on the LEADER's
+// full barrier; tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs; the follower's
+// epilogue warps release the accumulator on the leader's barrier.
 template <int BN, int AMAJ, int BMAJ, bool RS, bool MC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -380,9 +403,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // (offset arithmetic on the __shared__ array keeps the shared address space visible to the compiler)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stg_stride = (ep.src != SRC_NONE ? 2 : 1) * kStgTile;     // bytes of staging per epilogue warp
+  constexpr int kBStage = MC ? Cfg::kBBytes / 2 : Cfg::kBBytes;       // bytes of B per stage held by this CTA
+  constexpr int kStage = Cfg::kABytes + kBStage;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + nstages * Cfg::kABytes;
-  uint8_t* smem_stg = smem + nstages * Cfg::kStageBytes;             // 1024-byte aligned: 8 or 16 staging tiles of 4 KB
+  uint8_t* smem_stg = smem + nstages * kStage;                       // 1024-byte aligned: 8 or 16 staging tiles of 4 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + kEpiWarps * stg_stride);
   uint64_t* full_bar = bars;                         // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;           // [kMaxStages]
@@ -407,17 +432,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MC ? 2 : 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps); }
+    for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], MC ? 2 * kEpiWarps : kEpiWarps); }
     for (int s = 0; s < kEpiWarps; ++s) mbar_init(&src_bar[s], 1);
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
     if (ep.src != SRC_NONE) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmS)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(Cfg::kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (MC) {       // both CTAs of the pair, same warp id
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(Cfg::kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(Cfg::kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   // RS: the B operand of the row-sum MMA is a 16 x 16 block of bf16 ones in the un-swizzled core-matrix layout
   // (four 128-byte core matrices = 512 bytes; all ones, so the LBO / SBO order is immaterial)
@@ -449,28 +480,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m0 = mt * BM, n0 = nt * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           uint8_t* sa = smem_a + stage * Cfg::kABytes;
-          uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+          uint8_t* sb = smem_b + stage * kBStage;
           const int k0 = kb * BK;
+          if (MC) {
+            // the leader's full barrier counts the bytes of both CTAs of the pair
+            const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStage);
+            if (AMAJ == 0) {
+              tma_load_3d_pair(&tmA, lbar, sa, k0, m0, bz);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_load_3d_pair(&tmA, lbar, sa + j * (BK * 128), m0 + 64 * j, k0, bz);
+            }
+            if (BMAJ == 0) {
+              tma_load_3d_pair(&tmB, lbar, sb, k0, n0 + crank * (BN / 2), bz);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j)
+                tma_load_3d_pair(&tmB, lbar, sb + j * (BK * 128), n0 + 64 * (crank * (BN / 128) + j), k0, bz);
+            }
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           if (AMAJ == 0) {
             tma_load_3d(&tmA, &full_bar[stage], sa, k0, m0, bz);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_3d(&tmA, &full_bar[stage], sa + j * (BK * 128), m0 + 64 * j, k0, bz);
           }
-          if (MC) {
-            // this CTA's half of the B tile, delivered to both CTAs of the cluster
-            if (BMAJ == 0) {
-              tma_load_3d_mc(&tmB, &full_bar[stage], sb + crank * (BN / 2) * 128, k0, n0 + crank * (BN / 2), bz, 0x3);
-            } else {
-#pragma unroll
-              for (int j = 0; j < BN / 128; ++j) {
-                const int jj = crank * (BN / 128) + j;
-                tma_load_3d_mc(&tmB, &full_bar[stage], sb + jj * (BK * 128), n0 + 64 * jj, k0, bz, 0x3);
-              }
-            }
-          } else if (BMAJ == 0) {
+          if (BMAJ == 0) {
             tma_load_3d(&tmB, &full_bar[stage], sb, k0, n0, bz);
           } else {
 #pragma unroll
@@ -482,13 +522,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<BN, AMAJ, BMAJ>();
+    if (lane == 0 && crank == 0) {            // (pair: only the leader CTA issues MMAs)
+      constexpr uint32_t idesc = make_idesc<BN, AMAJ, BMAJ, MC ? 2 * BM : BM>();
       constexpr uint32_t a_lbo = (AMAJ == 0) ? 0u : BK * 128u;
       constexpr uint32_t b_lbo = (BMAJ == 0) ? 0u : BK * 128u;
       constexpr uint32_t a_kstep = (AMAJ == 0) ? UMMA_K * 2u : UMMA_K * 128u;   // bytes per K=16 step
       constexpr uint32_t b_kstep = (BMAJ == 0) ? UMMA_K * 2u : UMMA_K * 128u;
-      constexpr uint32_t idesc_ones = make_idesc_ones(AMAJ);
+      constexpr uint32_t idesc_ones = make_idesc_ones(AMAJ, MC ? 2 * BM : BM);
       // SWIZZLE_NONE descriptor: core matrices 128 B apart along K (LBO) and 256 B apart along N (SBO)
       const uint64_t ones_desc = (make_smem_desc(smem_u32(ones_tile), 128u, 256u) & ~(7ull << 61));
       int stage = 0; uint32_t phase = 0;
@@ -506,26 +546,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem_a + stage * Cfg::kABytes);
-          const uint32_t sb = smem_u32(smem_b + stage * Cfg::kBBytes);
+          const uint32_t sb = smem_u32(smem_b + stage * kBStage);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (MC) tc_mma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           if (rs_tile) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
-              tc_mma_bf16(tmem_base + BN, adesc, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (MC) tc_mma_bf16_pair(tmem_base + BN, adesc, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
+              else tc_mma_bf16(tmem_base + BN, adesc, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
-          // frees the smem stage once these MMAs retire (MC: in both CTAs -- the peer's next multicast lands here too)
-          if (MC) tc_commit_mc(&empty_bar[stage], 0x3);
+          // frees the smem stage once these MMAs retire (pair: in both CTAs)
+          if (MC) tc_commit_pair(&empty_bar[stage]);
           else tc_commit(&empty_bar[stage]);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull_bar[acc]);          // accumulator complete -> epilogue
+        if (MC) tc_commit_pair(&tfull_bar[acc]);     // accumulator complete -> both CTAs' epilogues
+        else tc_commit(&tfull_bar[acc]);             // accumulator complete -> epilogue
         if (RS) acc_phase ^= 1;              // single accumulator buffer (columns [BN, BN+16) hold the row sums)
         else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -570,7 +613,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (MC) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));     // the leader's MMA thread waits for both CTAs
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (RS) acc_phase ^= 1;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -581,12 +627,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync();       // neither CTA frees tensor memory or leaves while the pair's MMAs / arrivals may be in flight
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols)
-                 : "memory");
+    if (MC) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
   }
-  if (MC) cluster_sync();       // neither CTA leaves while the other may still signal its barriers
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -647,9 +693,9 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   }
   const bool with_src = ep.src != SRC_NONE;
   static const int stage_cap = getenv("SER_GEMM_STAGES") ? atoi(getenv("SER_GEMM_STAGES")) : kMaxStages;   // A/B switch
-  int nstages = Cfg::stages(with_src);
+  int nstages = Cfg::stages(with_src, MC);
   if (stage_cap >= 2 && nstages > stage_cap) nstages = stage_cap;
-  const int smem_bytes = nstages * Cfg::kStageBytes + 1024 + Cfg::stg_bytes(with_src) + kBarBytes;
+  const int smem_bytes = nstages * Cfg::stage_bytes(MC) + 1024 + Cfg::stg_bytes(with_src) + kBarBytes;
   const int m_tiles = ceil_div(M, BM), n_tiles = N / BN;
   if (!MC) {
     const long long total = static_cast<long long>(m_tiles) * n_tiles * splits * batch;
@@ -740,13 +786,13 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   SER_REQUIRE(a.batch <= 1 || (a.strideA % 8 == 0 && a.strideB % 8 == 0 && a.strideC % 8 == 0),
               "gemm_tc: batch strides must be multiples of 8");
   SER_REQUIRE((reinterpret_cast<uintptr_t>(a.C) & 15) == 0, "gemm_tc: output must be 16-byte aligned");
-  // 2-CTA clusters with a multicast B tile (SER_GEMM_MC=1).  Off by default: measured on B200 it changes nothing
-  // (8192^3: 1.25 -> 1.28 PFLOP/s, the step's shapes +-0) -- each CTA still RECEIVES the whole 48 KB per k-block, and
-  // the bound is the shared-memory fill rate of an SM (~50 B/clk), not the number of bytes it requests.  An L2
-  // prefetch ahead of the pipeline made things worse (-15 %: more TMA operations per k-block).  What helps is fewer
-  // inbound bytes per MMA cycle, i.e. cta_group::2 tiles.
-  static const int mc_env = getenv("SER_GEMM_MC") ? atoi(getenv("SER_GEMM_MC")) : 0;
-  const bool mc = (mc_env == 1) && (m_tiles % 2 == 0) && !(a.a_trans && !a.b_trans);
+  // cta_group::2 pairs (256 x BN tiles): row-tile pairs of problems large enough to be bound by the main loop
+  static const int mc_env = getenv("SER_GEMM_PAIR") ? atoi(getenv("SER_GEMM_PAIR")) : -1;     // A/B switch: 0 off, 1 force
+  bool mc = (m_tiles % 2 == 0) && !(a.a_trans && !a.b_trans);
+  if (mc_env == 0) mc = false;
+  else if (mc_env != 1)
+    mc = mc && static_cast<long long>(m_tiles) * n_tiles * splits * (a.batch > 1 ? a.batch : 1) >= device_sm_count() - 20 &&
+         kblocks / splits >= 8;      // short contractions (K = 256) are epilogue / HBM bound: 42.7 vs 33.6 us paired
   CUtensorMap tmA, tmB, tmC, tmS;
   if (!a.a_trans) SER_TRY(make_tmap(&tmA, a.A, 0, a.M, a.K, a.lda, BM, BK, a.batch, a.strideA));
   else            SER_TRY(make_tmap(&tmA, a.A, 0, a.K, a.M, a.lda, BK, 64, a.batch, a.strideA));
