@@ -427,6 +427,9 @@ class HeadLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, unc, emb, protos, labels, cfg: dict):
         L.require_cuda(logits, unc, emb, protos, labels)
+        before = cfg.get("before_loss")
+        if before is not None:             # data-parallel: the global class counts' all-reduce, launched before the forward
+            before()
         dev = logits.device
         lg = _f32c(logits)
         B, C_ = lg.shape

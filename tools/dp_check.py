@@ -1,0 +1,51 @@
+"""Data-parallel correctness on real GPUs: gradients of DataParallelHead.train_step on W ranks (different shards) must
+equal the gradients of one process on the concatenated batch.  torchrun --nproc-per-node W tools/dp_check.py"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, ".")
+import mmser_b200  # noqa: E402
+from mmser_b200.parallel import DataParallelHead  # noqa: E402
+from oracle import synth  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+C, Bs, Ta, Tt = 4, 6, 40, 12
+w = synth.head_weights(C)
+shards = [synth.make_inputs(Bs, Ta, Tt, C, seed=100 + r) for r in range(world)]
+worst = 0.0
+for dtype, tol in ((torch.float32, 2e-4), (torch.bfloat16, 6e-2)):
+    head = mmser_b200.FusionHead(C).to(dev); head.load_group_state(w); head.train()
+    dp = DataParallelHead(head)
+    a, t, am, tm, lab = shards[rank]
+    out = dp.train_step(a.to(dev).to(dtype), t.to(dev).to(dtype), am.to(dev), tm.to(dev), lab.to(dev))
+    torch.cuda.synchronize()
+    grads = {n: p.grad.detach().clone() for n, p in head.named_parameters() if p.grad is not None}
+    # every rank holds the same reduced gradients
+    for n, g in grads.items():
+        ref = g.clone(); dist.broadcast(ref, src=0)
+        assert torch.equal(ref, g), f"{n}: ranks disagree"
+    if rank == 0:
+        full = mmser_b200.FusionHead(C).to(dev); full.load_group_state(w); full.train()
+        cat = [torch.cat([s[i] for s in shards]) for i in range(5)]
+        o = full(cat[0].to(dev).to(dtype), cat[1].to(dev).to(dtype), cat[2].to(dev), cat[3].to(dev), cat[4].to(dev))
+        o["loss"].backward()
+        assert abs(float(o["loss"]) - float(out["loss"])) <= tol * abs(float(o["loss"])), (float(o["loss"]), float(out["loss"]))
+        gmax = max(p.grad.double().norm().item() for p in full.parameters() if p.grad is not None)
+        for n, p in full.named_parameters():
+            if p.grad is None:
+                continue
+            # gradients that are mathematically zero (attention key biases: softmax shift invariance) hold rounding
+            # noise only -- measure every tensor against at least 1e-4 of the largest gradient norm of the head
+            e = (grads[n].double() - p.grad.double()).norm().item() / max(p.grad.double().norm().item(), 1e-4 * gmax)
+            worst = max(worst, e)
+            assert e <= tol, f"{dtype} {n}: rel err {e:.3e}"
+        print(f"dp_check {dtype}: world {world}, loss {float(out['loss']):.6f}, worst gradient rel err {worst:.2e} (tol {tol})", flush=True)
+    dist.barrier()
+torch.cuda.synchronize()
+os._exit(0)
