@@ -373,6 +373,7 @@ def run_ours(args, wl):
                 for k, v in sorted(detail.items(), key=lambda kv: -kv[1]["ms"]):
                     f.write(f"{k:44s} n/step={v['launches']/nprof:6.1f} ms/step={v['ms']/nprof:8.4f} us/launch={1e3*v['ms']/v['launches']:8.1f} "
                             f"TFLOP/s={v['flops']/max(v['ms'],1e-9)/1e9:8.1f} GB/s={v['bytes']/max(v['ms'],1e-9)/1e6:8.1f}\n")
+        gemm_detail = {k: v for k, v in detail.items() if k.startswith("gemm_tc")}
         prof = {}
         for k, v in detail.items():            # aggregate shape-tagged records per kernel family
             fam = prof.setdefault(k.split(":")[0], dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
@@ -429,6 +430,22 @@ def run_ours(args, wl):
                 "avg_launch_us": gms * 1e3 / nl, "peak_source": peaks["src"] + " sustained bf16 (kernel timed inside a long step)",
                 "launches_per_step": sum(v["launches_per_step"] for v in fam.values()),
                 "ms_per_step": sum(v["ms_per_step"] for v in fam.values())}
+        # context for `frac`: the family mixes tensor-bound (K = 768), HBM-bound (K = 256) and launch-latency-bound
+        # (M = 256) shapes.  (1) time-weighted fraction of each launch's OWN roofline max(flops / tensor peak,
+        # algorithmic bytes / HBM peak); (2) the same two numbers over the launches of >= 20 us only.
+        def _roof(sel):
+            t = sum(v["ms"] for v in sel)
+            if t <= 0:
+                return None
+            t_roof = sum(max(v["flops"] / (peaks["tf_sus"] * 1e12), v["bytes"] / (peaks["hbm"] * 1e9)) * 1e3 for v in sel)
+            fl = sum(v["flops"] for v in sel)
+            return {"launches_per_step": sum(v["launches"] for v in sel) / nprof, "ms_per_step": t / nprof,
+                    "achieved_tflops": fl / (t * 1e-3) / 1e12, "frac_of_tensor_peak": fl / (t * 1e-3) / 1e12 / peaks["tf_sus"],
+                    "frac_of_own_roofline": t_roof / t}
+        allg = list(gemm_detail.values())
+        big = [v for v in allg if v["ms"] / max(v["launches"], 1) >= 0.020]
+        roof["all_launches"] = _roof(allg)
+        roof["launches_over_20us"] = _roof(big)
     tot_prof_ms = sum(v["ms_per_step"] for v in prof.values()) or 1.0
     families = {k: {"ms_per_step": round(v["ms_per_step"], 4), "launches_per_step": v["launches_per_step"],
                     "share": round(v["ms_per_step"] / tot_prof_ms, 4),

@@ -646,7 +646,8 @@ int layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, void* y2, int y2
   SER_REQUIRE(res == nullptr || static_cast<long long>(M) * (N / 2) < (1LL << 32), "layernorm_fwd: dropout site too large");
   char pname[64];
   if (prof_enabled()) snprintf(pname, sizeof(pname), "layernorm_fwd:%dx%d", M, N);
-  ProfScope prof(pname, 0.0, static_cast<double>(M) * N * ((x_f32 ? 4 : 2) + (y_f32 ? 4 : 2) + (y2 ? (y2_f32 ? 4 : 2) : 0)), s);
+  // algorithmic bytes: x read, y (and its copy) written; with the residual-dropout prologue also res read and xout written
+  ProfScope prof(pname, 0.0, static_cast<double>(M) * N * ((x_f32 ? 4 : 2) * (res ? 3 : 1) + (y_f32 ? 4 : 2) + (y2 ? (y2_f32 ? 4 : 2) : 0)), s);
   if (res != nullptr)
     ln_fwd_kernel<true><<<ln_grid(M), 256, 0, s>>>(x, x_f32, y, y_f32, y2, y2_f32, gamma, beta, stats, M, N, relu, res, xout,
                                                    drop != nullptr ? *drop : DropSpec{});

@@ -4,7 +4,8 @@
 //
 // Pooling layout: x is [B, T, D] row-major.  The statistics kernels run one CTA per (sample, 256-column
 // slab): a warp covers the slab width (512 contiguous bytes of bf16 per row), the 8 warps walk T with 4 rows in flight.
-// The weighted variance is the reference's two-pass form  sum_t a_t (x_t - mu)^2  (pooling.py:26).
+// The weighted variance sum_t a_t (x_t - mu)^2 (pooling.py:26) is computed in one pass over x with the shifted-data
+// identity (pivot = first frame of the column), see asp_stats_kernel.
 // A sample whose frames are all padded yields NaN (softmax over all -inf), as in the reference.
 #include "kernels.cuh"
 #include "prof.cuh"
@@ -76,7 +77,7 @@ asp_stats_kernel(const T* __restrict__ x, const float* __restrict__ e, const flo
   float* sa = smem;                      // [T]
   float* red = sa + Tlen;                // [32]
   float* part = red + 32;                // [RG][SLAB]
-  float* smean = part + RG * SLAB;       // [SLAB]
+  float* smean = part + RG * SLAB;       // [RG][SLAB] (second partial array)
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * SLAB;
   const int cl = (threadIdx.x % KL) * 8; // column offset inside the slab
@@ -86,9 +87,14 @@ asp_stats_kernel(const T* __restrict__ x, const float* __restrict__ e, const flo
     for (int t = threadIdx.x; t < Tlen; t += blockDim.x) alpha[static_cast<size_t>(b) * Tlen + t] = sa[t];
 
   const T* xb = x + static_cast<size_t>(b) * Tlen * D + c0 + cl;
-  float acc[8];
+  // ONE pass over the slab: with weights that sum to 1, sum_t a_t (x_t - mu)^2 = sum_t a_t (x_t - p)^2 - (mu - p)^2 for
+  // any pivot p; p = the column's first frame keeps both terms of the order of the variance itself (the textbook
+  // shifted-data form: no cancellation beyond a factor of a few), and x is read exactly once -- the reference's
+  // two-pass form (pooling.py:24-26) read it twice, the second time from L2.
+  float piv[8], acc[8], acq[8];
+  load8(xb, piv);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int i = 0; i < 8; ++i) { acc[i] = 0.f; acq[i] = 0.f; }
   constexpr int U = 4;                    // independent row loads in flight per thread
   int t = rg;
   for (; t + (U - 1) * RG < Tlen; t += U * RG) {
@@ -99,7 +105,12 @@ asp_stats_kernel(const T* __restrict__ x, const float* __restrict__ e, const flo
     for (int u = 0; u < U; ++u) {
       const float a = sa[t + u * RG];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, v[u][i], acc[i]);
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[u][i] - piv[i];
+        const float ad = a * d;
+        acc[i] += ad;
+        acq[i] = fmaf(ad, d, acq[i]);
+      }
     }
   }
   for (; t < Tlen; t += RG) {
@@ -107,48 +118,26 @@ asp_stats_kernel(const T* __restrict__ x, const float* __restrict__ e, const flo
     load8(xb + static_cast<size_t>(t) * D, v);
     const float a = sa[t];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, v[i], acc[i]);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) part[rg * SLAB + cl + i] = acc[i];
-  __syncthreads();
-  for (int c = threadIdx.x; c < SLAB; c += NTH) {
-    float s = 0.f;
-    for (int r = 0; r < RG; ++r) s += part[r * SLAB + c];
-    smean[c] = s;
-  }
-  __syncthreads();
-  float mu[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { mu[i] = smean[cl + i]; acc[i] = 0.f; }
-  t = rg;
-  for (; t + (U - 1) * RG < Tlen; t += U * RG) {      // second pass: the slab is L2 resident
-    float v[U][8];
-#pragma unroll
-    for (int u = 0; u < U; ++u) load8(xb + static_cast<size_t>(t + u * RG) * D, v[u]);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const float a = sa[t + u * RG];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = v[u][i] - mu[i]; acc[i] = fmaf(a * d, d, acc[i]); }
+    for (int i = 0; i < 8; ++i) {
+      const float d = v[i] - piv[i];
+      const float ad = a * d;
+      acc[i] += ad;
+      acq[i] = fmaf(ad, d, acq[i]);
     }
   }
-  for (; t < Tlen; t += RG) {
-    float v[8];
-    load8(xb + static_cast<size_t>(t) * D, v);
-    const float a = sa[t];
+  float* part2 = smean;                  // second partial array follows the first: [RG][SLAB] each (see asp_fwd's smem size)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { const float d = v[i] - mu[i]; acc[i] = fmaf(a * d, d, acc[i]); }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) part[rg * SLAB + cl + i] = acc[i];
+  for (int i = 0; i < 8; ++i) { part[rg * SLAB + cl + i] = acc[i]; part2[rg * SLAB + cl + i] = acq[i]; }
   __syncthreads();
   for (int c = threadIdx.x; c < SLAB; c += NTH) {
-    float s = 0.f;
-    for (int r = 0; r < RG; ++r) s += part[r * SLAB + c];
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < RG; ++r) { s1 += part[r * SLAB + c]; s2 += part2[r * SLAB + c]; }
+    const float p0 = to_f32(x[static_cast<size_t>(b) * Tlen * D + c0 + c]);
     const size_t o = static_cast<size_t>(b) * 2 * D + c0 + c;
-    st_dyn(out, o, out_f32, smean[c]);
-    st_dyn(out, o + D, out_f32, sqrtf(s + 1e-6f));
+    st_dyn(out, o, out_f32, p0 + s1);
+    float var = s2 - s1 * s1;
+    var = var < 0.f ? 0.f : var;          // (a NaN -- all frames padded -- stays NaN, as in the reference)
+    st_dyn(out, o + D, out_f32, sqrtf(var + 1e-6f));
   }
 }
 
@@ -339,7 +328,7 @@ mix_bwd_kernel(const T* __restrict__ pa, const T* __restrict__ pt, const T* __re
 template <typename T, int SLAB>
 int asp_stats_launch(const AspArgs& a, cudaStream_t s) {
   constexpr int RG = SlabCfg<SLAB>::kRG;
-  const size_t smem = sizeof(float) * (a.T + 32 + RG * SLAB + SLAB);
+  const size_t smem = sizeof(float) * (a.T + 32 + 2 * RG * SLAB);
   auto kern = asp_stats_kernel<T, SLAB>;
   if (smem > 48 * 1024) SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<dim3(a.D / SLAB, a.B), NTH, smem, s>>>(reinterpret_cast<const T*>(a.x), a.e, a.mask, a.alpha, a.out,
