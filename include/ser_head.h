@@ -276,6 +276,17 @@ int ser_loss_fwd(const ser_loss_desc* d, void* stream);
 int ser_loss_finalize(const ser_loss_desc* d, void* stream);
 int ser_loss_bwd(const ser_loss_desc* d, void* stream);
 
+/* ---- SupConLoss  (src/models/losses.py:67-88) ------------------------------------------------------
+ * Supervised contrastive loss over one batch: normalised embeddings, B x B similarities / temperature, row-max shift,
+ * positives = same label off the diagonal, loss = -mean_i(sum_pos log_prob / (n_pos + 1e-12)).  Imported and
+ * constructed by the reference's scripts (train.py:8,86).  f: [B,D] (f_f32: fp32 else bf16), labels int64 [B],
+ * loss: one fp32; backward: df = gscale[0] * dloss/df (gscale NULL = 1).  ws: ser_supcon_ws_bytes(B, D) bytes.       */
+size_t ser_supcon_ws_bytes(int B, int D);
+int ser_supcon_fwd(const void* f, int f_f32, const long long* labels, int B, int D, float temperature, float* loss,
+                   void* ws, size_t ws_bytes, void* stream);
+int ser_supcon_bwd(const void* f, int f_f32, const long long* labels, int B, int D, float temperature,
+                   const float* gscale, void* df, int df_f32, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- a7 / a12: inference post-processing --------------------------------------------------------
  * ser_openmax_fwd : classifier.py:240-275 (Weibull CDF of distances to activation vectors, re-scale logits)
  * ser_eval_post   : eval.py:186-190 (mean over V views), :201-206 (/T, softmax, argmax), utils.py:12-14 (energy)

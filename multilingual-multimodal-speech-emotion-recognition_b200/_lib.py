@@ -98,7 +98,7 @@ def load():
     for n in EXPORTS:
         getattr(lib, n).restype = C.c_int
     lib.ser_last_error.restype = C.c_char_p
-    for n in ("ser_xattn_bwd_ws_bytes", "ser_fusion_bwd_ws_bytes", "ser_clf_bwd_ws_bytes"):
+    for n in ("ser_xattn_bwd_ws_bytes", "ser_fusion_bwd_ws_bytes", "ser_clf_bwd_ws_bytes", "ser_supcon_ws_bytes"):
         getattr(lib, n).restype = C.c_size_t
     P, I, LL, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
     lib.ser_gemm.argtypes = [C.POINTER(GemmDesc), P]
@@ -119,6 +119,9 @@ def load():
     lib.ser_openmax_fwd.argtypes = [P, P, P, P, P, P, P, I, I, I, P]
     lib.ser_eval_post.argtypes = [P, I, I, I, F, P, P, P, P, P]
     lib.ser_temperature_sweep.argtypes = [P, P, I, I, P, I, P, P]
+    lib.ser_supcon_ws_bytes.argtypes = [I, I]
+    lib.ser_supcon_fwd.argtypes = [P, I, P, I, I, F, P, P, C.c_size_t, P]
+    lib.ser_supcon_bwd.argtypes = [P, I, P, I, I, F, P, P, I, P, C.c_size_t, P]
     lib.ser_desc_size.argtypes = [I]
     lib.ser_dropout_mask.argtypes = [P, I, F, LL, I, P, P]
     lib.ser_launch_count.restype = C.c_longlong

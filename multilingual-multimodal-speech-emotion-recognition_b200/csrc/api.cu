@@ -136,6 +136,16 @@ int ser_loss_bwd(const ser_loss_desc* d, void* stream) {
   return ser::loss_bwd_scaled(to_loss_args(*d), d->gscale, SER_STREAM(stream));
 }
 
+size_t ser_supcon_ws_bytes(int B, int D) { return ser::supcon_ws_bytes(B, D); }
+int ser_supcon_fwd(const void* f, int f_f32, const long long* labels, int B, int D, float temperature, float* loss,
+                   void* ws, size_t ws_bytes, void* stream) {
+  return ser::supcon_fwd(f, f_f32, labels, B, D, temperature, loss, ws, ws_bytes, SER_STREAM(stream));
+}
+int ser_supcon_bwd(const void* f, int f_f32, const long long* labels, int B, int D, float temperature,
+                   const float* gscale, void* df, int df_f32, void* ws, size_t ws_bytes, void* stream) {
+  return ser::supcon_bwd(f, f_f32, labels, B, D, temperature, gscale, df, df_f32, ws, ws_bytes, SER_STREAM(stream));
+}
+
 int ser_openmax_fwd(const float* feats, const float* logits, const float* act_vecs, const float* w_alpha,
                     const float* w_beta, const float* w_tau, float* out, int B, int C, int F, void* stream) {
   return ser::openmax_fwd(feats, logits, act_vecs, w_alpha, w_beta, w_tau, out, B, C, F, SER_STREAM(stream));

@@ -194,6 +194,14 @@ int loss_bwd_scaled(const LossArgs& a, const float* gscale, cudaStream_t s);
 int loss_finalize(const float* sums, long long B_global, float margin, float w_ce, float w_focal, float w_unc,
                   float w_proto, int have_proto, float* terms, cudaStream_t s);
 
+// ---- supcon.cu -----------------------------------------------------------------------------------
+// SupConLoss (losses.py:67-88): loss[0] = scalar; backward recomputes the similarities; gscale = device scalar or NULL
+size_t supcon_ws_bytes(int B, int D);
+int supcon_fwd(const void* f, int f_f32, const long long* labels, int B, int D, float temperature, float* loss, void* ws,
+               size_t ws_bytes, cudaStream_t s);
+int supcon_bwd(const void* f, int f_f32, const long long* labels, int B, int D, float temperature, const float* gscale,
+               void* df, int df_f32, void* ws, size_t ws_bytes, cudaStream_t s);
+
 // ---- eval.cu -------------------------------------------------------------------------------------
 // OpenMax re-scaling (classifier.py:240-275): logits_out = logits * (u > 0.3 ? 1 - 0.8u : 1)
 int openmax_fwd(const float* feats, const float* logits, const float* act_vecs, const float* w_alpha,

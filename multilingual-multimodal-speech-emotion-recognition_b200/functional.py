@@ -495,6 +495,44 @@ class HeadLossFn(torch.autograd.Function):
                 demb if ctx.needs_input_grad[2] else None, dprotos, None, None)
 
 
+class SupConFn(torch.autograd.Function):
+    """SupConLoss.forward (src/models/losses.py:75-88): scalar fp32 loss; gradient w.r.t. the features only."""
+
+    @staticmethod
+    def forward(ctx, features, labels, temperature: float):
+        L.require_cuda(features, labels)
+        if features.dim() != 2:
+            raise L.SerError("SupConLoss expects features of shape [B, D]")
+        if features.dtype not in (torch.float32, torch.bfloat16):
+            raise L.SerError(f"unsupported dtype {features.dtype}: float32 or bfloat16")
+        f = features.contiguous()
+        lab = labels.to(torch.int64).contiguous()
+        B, D = f.shape
+        dev = f.device
+        lib = L.load()
+        ws = _ws(lib.ser_supcon_ws_bytes(B, D), dev)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        L.check(lib.ser_supcon_fwd(f.data_ptr(), int(f.dtype == torch.float32), lab.data_ptr(), B, D, float(temperature),
+                                   loss.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev)), "ser_supcon_fwd")
+        ctx.save_for_backward(f, lab)
+        ctx.temperature = float(temperature)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        f, lab = ctx.saved_tensors
+        B, D = f.shape
+        dev = f.device
+        lib = L.load()
+        ws = _ws(lib.ser_supcon_ws_bytes(B, D), dev)
+        df = torch.empty_like(f)
+        g = dloss.reshape(1).to(torch.float32).contiguous()
+        L.check(lib.ser_supcon_bwd(f.data_ptr(), int(f.dtype == torch.float32), lab.data_ptr(), B, D, ctx.temperature,
+                                   g.data_ptr(), df.data_ptr(), int(f.dtype == torch.float32), ws.data_ptr(), ws.numel(),
+                                   L.stream_ptr(dev)), "ser_supcon_bwd")
+        return df, None, None
+
+
 # --------------------------------------------------------------------------------------------------
 # individually callable children (nn.Linear / nn.LayerNorm replacements used by src/train.py:221-236)
 # --------------------------------------------------------------------------------------------------

@@ -3,12 +3,12 @@ from .adapter import BottleneckAdapter
 from .classifier import AdvancedOpenMaxClassifier, ClassAnchorClustering, DeepClassifier, DeepResidualBlock
 from .cross_attention import CrossModalAttention
 from .fusion import FusionLayer
-from .losses import ClassBalancedFocalLoss, LabelSmoothingCrossEntropy
+from .losses import ClassBalancedFocalLoss, LabelSmoothingCrossEntropy, SupConLoss
 from .pooling import AttentiveStatsPooling
 from .prototypes import PrototypeMemory
 
 __all__ = [
     "BottleneckAdapter", "AdvancedOpenMaxClassifier", "ClassAnchorClustering", "DeepClassifier", "DeepResidualBlock",
-    "CrossModalAttention", "FusionLayer", "ClassBalancedFocalLoss", "LabelSmoothingCrossEntropy",
+    "CrossModalAttention", "FusionLayer", "ClassBalancedFocalLoss", "LabelSmoothingCrossEntropy", "SupConLoss",
     "AttentiveStatsPooling", "PrototypeMemory",
 ]

@@ -1,4 +1,4 @@
-"""Drop-in LabelSmoothingCrossEntropy and ClassBalancedFocalLoss (reference: src/models/losses.py:7-64)."""
+"""Drop-in LabelSmoothingCrossEntropy, ClassBalancedFocalLoss and SupConLoss (reference: src/models/losses.py:7-88)."""
 from __future__ import annotations
 
 from typing import Optional
@@ -6,7 +6,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from ..functional import HeadLossFn
+from ..functional import HeadLossFn, SupConFn
 
 
 class LabelSmoothingCrossEntropy(nn.Module):
@@ -33,3 +33,15 @@ class ClassBalancedFocalLoss(nn.Module):
             cfg["counts"] = class_counts
         terms = HeadLossFn.apply(logits, None, None, None, targets, cfg)
         return terms[4]
+
+
+class SupConLoss(nn.Module):
+    """Supervised contrastive loss (losses.py:67-88).  The reference's scripts import and construct it
+    (train.py:8,86; train_crema.py:31,231) without adding it to the training loss; same constructor and call."""
+
+    def __init__(self, temperature: float = 0.07):
+        super().__init__()
+        self.temperature = temperature
+
+    def forward(self, features: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        return SupConFn.apply(features, labels, self.temperature)

@@ -349,6 +349,19 @@ def class_balanced_focal(logits: Tensor, targets: Tensor, beta: float = 0.9999, 
     return loss
 
 
+def supcon_loss(features: Tensor, labels: Tensor, temperature: float = 0.07) -> Tensor:
+    """SupConLoss.forward (src/models/losses.py:75-88): the row max INCLUDES the diagonal; positives and the
+    denominator exclude it; rows without positives contribute 0 / 1e-12 = 0."""
+    f = features / features.norm(dim=-1, keepdim=True).clamp_min(1e-12)            # F.normalize
+    logits = f @ f.t() / temperature
+    logits = logits - logits.max(dim=1, keepdim=True)[0]
+    B = f.shape[0]
+    off = 1.0 - torch.eye(B, dtype=f.dtype)
+    pos = (labels.unsqueeze(1) == labels.unsqueeze(0)).to(f.dtype) * off
+    log_prob = logits - torch.log((torch.exp(logits) * off).sum(dim=1, keepdim=True) + 1e-12)
+    return -((pos * log_prob).sum(dim=1) / (pos.sum(dim=1) + 1e-12)).mean()
+
+
 # --------------------------------------------------------------------------------------------------
 # a11  loss composition  (src/train.py:151-168)  and  a12 eval post-processing (src/eval.py, src/utils.py)
 # --------------------------------------------------------------------------------------------------

@@ -205,6 +205,20 @@ def run_train_dropout_case(name, B, Ta, Tt, C, seed, num_layers=35):
     print(f"{name}: loss={loss.item():.6f} ({len(rec.calls)} dropout calls)")
 
 
+def run_supcon_case(name, B, D, C, seed, temperature):
+    """SupConLoss of the reference (src/models/losses.py:67-88) on random embeddings: loss and d loss / d features."""
+    lo = load_ref("losses")
+    g = torch.Generator().manual_seed(seed)
+    f = (torch.randn(B, D, generator=g) * 2.0).requires_grad_(True)
+    labels = torch.randint(0, C, (B,), generator=g)
+    labels[-1] = C            # one sample without any positive partner
+    loss = lo.SupConLoss(temperature)(f, labels)
+    loss.backward()
+    torch.save({"config": dict(B=B, D=D, C=C, seed=seed, temperature=temperature), "labels": labels,
+                "loss": loss.item(), "grad": f.grad.clone()}, os.path.join(OUT, f"{name}.pt"))
+    print(f"{name}: loss={loss.item():.6f}")
+
+
 def run_eval_case(name, B, C, seed, views=5):
     """cfg5 semantics at small B: classifier eval path with fitted OpenMax + TTA mean + temperature + energy."""
     weights = synth.head_weights(C, 35, seed=0)
@@ -266,3 +280,4 @@ if __name__ == "__main__":
     run_train_case("train_cfg4_long", B=2, Ta=300, Tt=96, C=4, seed=1239)
     run_eval_case("eval_cfg5_small", B=32, C=6, seed=1240)
     run_train_dropout_case("dropout_train_small", B=4, Ta=40, Tt=17, C=4, seed=1241)
+    run_supcon_case("supcon_small", B=48, D=512, C=4, seed=1242, temperature=0.07)

@@ -360,6 +360,26 @@ def loss_case(B=37, C=6):
     return Case("loss", ins, w, oracle, cuda, grad_inputs=("logits", "unc", "emb"))
 
 
+def supcon_case(B=96, D=512, C=4, temperature=0.07):
+    from mmser_b200 import models as M
+    g = torch.Generator().manual_seed(21)
+    labels = torch.randint(0, C, (B,), generator=g)
+    labels[-1] = C                                   # a sample without positives
+    ins = {"f": torch.randn(B, D, generator=g) * 2.0, "labels": labels}
+
+    def oracle(i, ws):
+        loss = O.supcon_loss(i["f"], i["labels"], temperature)
+        return {"supcon": loss}, loss
+
+    def cuda(i, dtype, dev):
+        f = i["f"].to(dev).to(dtype).requires_grad_(True)
+        loss = M.SupConLoss(temperature)(f, i["labels"].to(dev))
+        loss.backward()
+        return {"supcon": loss}, {}, {"f": f.grad}
+
+    return Case("supcon", ins, {}, oracle, cuda, grad_inputs=("f",))
+
+
 def head_case(B=4, Ta=50, Tt=16, C=4, masks=True, seed=1234, L=35, p_drop=0.0):
     import mmser_b200
     w = synth.head_weights(C, L)
@@ -410,6 +430,7 @@ ALL_CASES = {
     # two 128-row clusters of the fused stack kernel, the second one partially filled (rows >= B must stay inert)
     "classifier_b200": lambda: classifier_case(B=200, C=6),
     "loss": loss_case,
+    "supcon": supcon_case,
     "head_cfg1": lambda: head_case(4, 50, 16, 4, True),
     # (B = 24: with a handful of samples the reference arithmetic itself is 20-25 % away from the exact gradients --
     #  ReLU / argmax flips are O(1/B) -- and the comparison degenerates into noise against noise)

@@ -136,6 +136,20 @@ def test_oracle_matches_reference_eval(golden_dir):
         assert rel(O.energy_score(scaled), gold["energy"]) < 1e-4
 
 
+def test_oracle_matches_reference_supcon(golden_dir):
+    gold = torch.load(os.path.join(golden_dir, "supcon_small.pt"), weights_only=False)
+    cfg = gold["config"]
+    g = torch.Generator().manual_seed(cfg["seed"])
+    f = (torch.randn(cfg["B"], cfg["D"], generator=g) * 2.0).requires_grad_(True)
+    labels = torch.randint(0, cfg["C"], (cfg["B"],), generator=g)
+    labels[-1] = cfg["C"]
+    assert torch.equal(labels, gold["labels"])
+    loss = O.supcon_loss(f, labels, cfg["temperature"])
+    loss.backward()
+    assert abs(loss.item() - gold["loss"]) <= TOL * abs(gold["loss"])
+    assert rel(f.grad, gold["grad"]) < 10 * TOL
+
+
 def test_quirks():
     """SURVEY.md 8(a) quirks the CUDA path must reproduce."""
     torch.manual_seed(0)
