@@ -90,6 +90,41 @@ def test_dropout_train_eval_and_reseeding():
     assert torch.equal(hd2(*args)["logits"], l2)
 
 
+@pytest.mark.parametrize("shape", [
+    # (M, N, K, a_trans, b_trans, rowsum)   -- the first three are large enough for the cta_group::2 pair path
+    (8192, 768, 1024, False, False, False),      # forward, K-major operands
+    (8192, 768, 1024, False, True, False),       # dgrad, B MN-major
+    (768, 768, 24000, True, True, True),         # dW with split-K and the fused bias gradient
+    (1000, 256, 200, False, False, False),       # ragged M and K tails, single-CTA path
+    (200, 256, 3000, True, True, True),          # row tail inside the fused row sum
+    (512, 512, 256, True, True, True),           # tiny dW, no split
+])
+def test_tcgen05_gemm_variants_through_the_cabi(shape):
+    """The dominant kernel directly: ser_gemm (bf16 operands, fp32 accumulate) against an fp64 matmul, including the
+    CTA-pair path, MN-major operands, split-K and the row-sum by-product that replaces the bias-gradient launches."""
+    from mmser_b200 import _lib as L
+    dev = _dev()
+    M, N, K, ta, tb, rs = shape
+    g = torch.Generator(device="cpu").manual_seed(M * 31 + N * 7 + K)
+    a = torch.randn((K, M) if ta else (M, K), generator=g).to(dev).bfloat16()
+    b = torch.randn((K, N) if tb else (N, K), generator=g).to(dev).bfloat16()
+    rowsum = torch.full((M,), 3.0, device=dev) if rs else None
+    out = L.gemm(a, b, a_trans=ta, b_trans=tb, out_dtype=torch.float32, rowsum=rowsum)
+    A = a.double().t() if ta else a.double()
+    Bm = b.double() if tb else b.double().t()
+    ref = A @ Bm
+    assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 2e-3
+    if rs:
+        ref_rs = A.sum(1)
+        assert ((rowsum.double() - ref_rs).abs().max() / ref_rs.abs().max()).item() < 1e-4
+    # bf16 output with bias + ReLU epilogue (forward shapes only)
+    if not ta:
+        bias = torch.randn(N, generator=g).to(dev)
+        o2 = L.gemm(a, b, b_trans=tb, bias=bias, act=L.ACT_RELU)
+        ref2 = torch.relu(ref + bias.double())
+        assert ((o2.double() - ref2).abs().max() / ref2.abs().max()).item() < 1e-2
+
+
 def test_precast_tracks_parameter_updates():
     """FusionHead casts the bf16 operand copies of all modules in one launch per forward (FlatParams.precast); an
     in-place parameter update between two forwards (what an optimizer step is) must be picked up."""
