@@ -386,13 +386,13 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_ones(int amaj, int mm) 
          | (static_cast<uint32_t>(kOnesN >> 3) << 17) | (static_cast<uint32_t>(mm >> 4) << 24);
 }
 
-// MC ("pair"): launched as 2-CTA clusters driving ONE cta_group::2 MMA per k-step: the pair owns a 256 x BN output tile,
+// PAIR: launched as 2-CTA clusters driving ONE cta_group::2 MMA per k-step: the pair owns a 256 x BN output tile,
 // each CTA stores its own 128 A rows and HALF of the B tile (so a stage is 16 + BN/16 KB instead of 16 + BN/8 KB:
 // less shared-memory traffic per MMA cycle and a deeper pipeline), the leader CTA's elected thread issues the MMAs, and
 // each CTA's tensor memory receives its 128 accumulator rows.  All TMA bytes of a stage are counted on the LEADER's
 // full barrier; tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs; the follower's
 // epilogue warps release the accumulator on the leader's barrier.
-template <int BN, int AMAJ, int BMAJ, bool RS, bool MC>
+template <int BN, int AMAJ, int BMAJ, bool RS, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS,
@@ -403,7 +403,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // (offset arithmetic on the __shared__ array keeps the shared address space visible to the compiler)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stg_stride = (ep.src != SRC_NONE ? 2 : 1) * kStgTile;     // bytes of staging per epilogue warp
-  constexpr int kBStage = MC ? Cfg::kBBytes / 2 : Cfg::kBBytes;       // bytes of B per stage held by this CTA
+  constexpr int kBStage = PAIR ? Cfg::kBBytes / 2 : Cfg::kBBytes;       // bytes of B per stage held by this CTA
   constexpr int kStage = Cfg::kABytes + kBStage;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + nstages * Cfg::kABytes;
@@ -422,25 +422,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m_tiles = (M + BM - 1) / BM;
   const int n_tiles = N / BN;
   const int kblocks = (K + BK - 1) / BK;
-  // work units: MC -> one unit = the pair of row tiles (2u, 2u+1) handled by the two CTAs of a cluster in lockstep
-  const int crank = MC ? static_cast<int>(cluster_ctarank()) : 0;
-  const int m_units = MC ? m_tiles / 2 : m_tiles;
+  // work units: PAIR -> one unit = the pair of row tiles (2u, 2u+1) handled by the two CTAs of a cluster in lockstep
+  const int crank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int m_units = PAIR ? m_tiles / 2 : m_tiles;
   const int total_tiles = m_units * n_tiles * splits * batch;
-  const int unit0 = MC ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int unit_step = MC ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int unit0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int unit_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], MC ? 2 * kEpiWarps : kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], PAIR ? 2 * kEpiWarps : kEpiWarps); }
     for (int s = 0; s < kEpiWarps; ++s) mbar_init(&src_bar[s], 1);
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmC)) : "memory");
     if (ep.src != SRC_NONE) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmS)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    if (MC) {       // both CTAs of the pair, same warp id
+    if (PAIR) {       // both CTAs of the pair, same warp id
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                    "r"(Cfg::kTmemCols) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -461,7 +461,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (MC) cluster_sync();       // the peer's barriers exist before anything is multicast to them
+  if (PAIR) cluster_sync();       // the peer's barriers exist before anything is multicast to them
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -471,7 +471,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = unit0; tile < total_tiles; tile += unit_step) {
         const int nt = tile % n_tiles;
         const int rest = tile / n_tiles;
-        const int mt = MC ? 2 * (rest % m_units) + crank : rest % m_units;
+        const int mt = PAIR ? 2 * (rest % m_units) + crank : rest % m_units;
         const int rest2 = rest / m_units;
         const int sp = rest2 % splits;
         const int bz = rest2 / splits;
@@ -483,7 +483,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sa = smem_a + stage * Cfg::kABytes;
           uint8_t* sb = smem_b + stage * kBStage;
           const int k0 = kb * BK;
-          if (MC) {
+          if (PAIR) {
             // the leader's full barrier counts the bytes of both CTAs of the pair
             const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
             if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStage);
@@ -523,12 +523,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0 && crank == 0) {            // (pair: only the leader CTA issues MMAs)
-      constexpr uint32_t idesc = make_idesc<BN, AMAJ, BMAJ, MC ? 2 * BM : BM>();
+      constexpr uint32_t idesc = make_idesc<BN, AMAJ, BMAJ, PAIR ? 2 * BM : BM>();
       constexpr uint32_t a_lbo = (AMAJ == 0) ? 0u : BK * 128u;
       constexpr uint32_t b_lbo = (BMAJ == 0) ? 0u : BK * 128u;
       constexpr uint32_t a_kstep = (AMAJ == 0) ? UMMA_K * 2u : UMMA_K * 128u;   // bytes per K=16 step
       constexpr uint32_t b_kstep = (BMAJ == 0) ? UMMA_K * 2u : UMMA_K * 128u;
-      constexpr uint32_t idesc_ones = make_idesc_ones(AMAJ, MC ? 2 * BM : BM);
+      constexpr uint32_t idesc_ones = make_idesc_ones(AMAJ, PAIR ? 2 * BM : BM);
       // SWIZZLE_NONE descriptor: core matrices 128 B apart along K (LBO) and 256 B apart along N (SBO)
       const uint64_t ones_desc = (make_smem_desc(smem_u32(ones_tile), 128u, 256u) & ~(7ull << 61));
       int stage = 0; uint32_t phase = 0;
@@ -551,23 +551,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            if (MC) tc_mma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) tc_mma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           if (rs_tile) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
-              if (MC) tc_mma_bf16_pair(tmem_base + BN, adesc, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (PAIR) tc_mma_bf16_pair(tmem_base + BN, adesc, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
               else tc_mma_bf16(tmem_base + BN, adesc, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
           // frees the smem stage once these MMAs retire (pair: in both CTAs)
-          if (MC) tc_commit_pair(&empty_bar[stage]);
+          if (PAIR) tc_commit_pair(&empty_bar[stage]);
           else tc_commit(&empty_bar[stage]);
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
-        if (MC) tc_commit_pair(&tfull_bar[acc]);     // accumulator complete -> both CTAs' epilogues
+        if (PAIR) tc_commit_pair(&tfull_bar[acc]);     // accumulator complete -> both CTAs' epilogues
         else tc_commit(&tfull_bar[acc]);             // accumulator complete -> epilogue
         if (RS) acc_phase ^= 1;              // single accumulator buffer (columns [BN, BN+16) hold the row sums)
         else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -586,7 +586,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = unit0; tile < total_tiles; tile += unit_step) {
       const int nt = tile % n_tiles;
       const int rest = tile / n_tiles;
-      const int mt = MC ? 2 * (rest % m_units) + crank : rest % m_units;
+      const int mt = PAIR ? 2 * (rest % m_units) + crank : rest % m_units;
       const int rest2 = rest / m_units;
       const int sp = rest2 % splits;
       const int bz = rest2 / splits;
@@ -614,7 +614,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (MC) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));     // the leader's MMA thread waits for both CTAs
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));     // the leader's MMA thread waits for both CTAs
         else mbar_arrive(&tempty_bar[acc]);
       }
       if (RS) acc_phase ^= 1;
@@ -627,10 +627,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync();       // neither CTA frees tensor memory or leaves while the pair's MMAs / arrivals may be in flight
+  if (PAIR) cluster_sync();       // neither CTA frees tensor memory or leaves while the pair's MMAs / arrivals may be in flight
   if (warp == 1) {
     tc_fence_after();
-    if (MC) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
   }
 }
@@ -681,23 +681,23 @@ int make_tmap(CUtensorMap* tm, const void* base, int f32, long long rows, long l
   return SER_OK;
 }
 
-template <int BN, int AMAJ, int BMAJ, bool RS = false, bool MC = false>
+template <int BN, int AMAJ, int BMAJ, bool RS = false, bool PAIR = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmS,
            const TcEpilogue& ep, int M, int N, int K, int splits, int batch, cudaStream_t stream) {
   using Cfg = TileCfg<BN>;
   static bool configured = false;
-  auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ, RS, MC>;
+  auto kern = gemm_tc_kernel<BN, AMAJ, BMAJ, RS, PAIR>;
   if (!configured) {
     SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     configured = true;
   }
   const bool with_src = ep.src != SRC_NONE;
   static const int stage_cap = getenv("SER_GEMM_STAGES") ? atoi(getenv("SER_GEMM_STAGES")) : kMaxStages;   // A/B switch
-  int nstages = Cfg::stages(with_src, MC);
+  int nstages = Cfg::stages(with_src, PAIR);
   if (stage_cap >= 2 && nstages > stage_cap) nstages = stage_cap;
-  const int smem_bytes = nstages * Cfg::stage_bytes(MC) + 1024 + Cfg::stg_bytes(with_src) + kBarBytes;
+  const int smem_bytes = nstages * Cfg::stage_bytes(PAIR) + 1024 + Cfg::stg_bytes(with_src) + kBarBytes;
   const int m_tiles = ceil_div(M, BM), n_tiles = N / BN;
-  if (!MC) {
+  if (!PAIR) {
     const long long total = static_cast<long long>(m_tiles) * n_tiles * splits * batch;
     const int grid = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
     kern<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmS, ep, M, N, K, splits, batch, nstages);
