@@ -287,6 +287,17 @@ int ser_supcon_fwd(const void* f, int f_f32, const long long* labels, int B, int
 int ser_supcon_bwd(const void* f, int f_f32, const long long* labels, int B, int D, float temperature,
                    const float* gscale, void* df, int df_f32, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- optimizer step (the consumer of the head's gradients) ---------------------
+ * ser_adamw_multi: one torch.optim.AdamW step (decoupled weight decay, bias correction with `step` >= 1) over n fp32
+ * tensors of one parameter group (src/train.py:72-83,169-177).  p / g / m / v / counts are HOST arrays of length n
+ * (device pointers, element counts).  gscale: optional device scalar multiplied into every gradient first -- the
+ * coefficient ser_grad_clip_coef leaves in `coef` (torch.nn.utils.clip_grad_norm_, train_crema.py).                    */
+int ser_adamw_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                    const long long* counts, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                    const float* gscale, void* stream);
+int ser_grad_clip_coef(int n, const float* const* g, const long long* counts, float max_norm, float* scratch,
+                       float* coef, float* norm_out, void* stream);
+
 /* ---- a7 / a12: inference post-processing --------------------------------------------------------
  * ser_openmax_fwd : classifier.py:240-275 (Weibull CDF of distances to activation vectors, re-scale logits)
  * ser_eval_post   : eval.py:186-190 (mean over V views), :201-206 (/T, softmax, argmax), utils.py:12-14 (energy)

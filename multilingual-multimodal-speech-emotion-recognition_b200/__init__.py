@@ -6,6 +6,7 @@ hyphens, so the alias module gives it an importable name).
 from . import _lib  # noqa: F401
 from . import functional  # noqa: F401
 from . import models  # noqa: F401
+from . import optim  # noqa: F401
 from .head import FusionHead  # noqa: F401
 
-__all__ = ["_lib", "functional", "models", "FusionHead"]
+__all__ = ["_lib", "functional", "models", "optim", "FusionHead"]

@@ -122,6 +122,8 @@ def load():
     lib.ser_supcon_ws_bytes.argtypes = [I, I]
     lib.ser_supcon_fwd.argtypes = [P, I, P, I, I, F, P, P, C.c_size_t, P]
     lib.ser_supcon_bwd.argtypes = [P, I, P, I, I, F, P, P, I, P, C.c_size_t, P]
+    lib.ser_adamw_multi.argtypes = [I, P, P, P, P, P, F, F, F, F, F, I, P, P]
+    lib.ser_grad_clip_coef.argtypes = [I, P, P, F, P, P, P, P]
     lib.ser_desc_size.argtypes = [I]
     lib.ser_dropout_mask.argtypes = [P, I, F, LL, I, P, P]
     lib.ser_launch_count.restype = C.c_longlong

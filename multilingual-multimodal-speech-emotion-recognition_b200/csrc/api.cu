@@ -146,6 +146,16 @@ int ser_supcon_bwd(const void* f, int f_f32, const long long* labels, int B, int
   return ser::supcon_bwd(f, f_f32, labels, B, D, temperature, gscale, df, df_f32, ws, ws_bytes, SER_STREAM(stream));
 }
 
+int ser_adamw_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                    const long long* counts, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                    const float* gscale, void* stream) {
+  return ser::adamw_multi(n, p, g, m, v, counts, lr, beta1, beta2, eps, weight_decay, step, gscale, SER_STREAM(stream));
+}
+int ser_grad_clip_coef(int n, const float* const* g, const long long* counts, float max_norm, float* scratch,
+                       float* coef, float* norm_out, void* stream) {
+  return ser::grad_clip_coef(n, g, counts, max_norm, scratch, coef, norm_out, SER_STREAM(stream));
+}
+
 int ser_openmax_fwd(const float* feats, const float* logits, const float* act_vecs, const float* w_alpha,
                     const float* w_beta, const float* w_tau, float* out, int B, int C, int F, void* stream) {
   return ser::openmax_fwd(feats, logits, act_vecs, w_alpha, w_beta, w_tau, out, B, C, F, SER_STREAM(stream));

@@ -202,6 +202,15 @@ int supcon_fwd(const void* f, int f_f32, const long long* labels, int B, int D, 
 int supcon_bwd(const void* f, int f_f32, const long long* labels, int B, int D, float temperature, const float* gscale,
                void* df, int df_f32, void* ws, size_t ws_bytes, cudaStream_t s);
 
+// ---- optim.cu ------------------------------------------------------------------------------------
+// torch.optim.AdamW step over n fp32 tensors (host pointer tables); gscale: optional device scalar multiplied into g
+int adamw_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v, const long long* counts,
+                float lr, float beta1, float beta2, float eps, float weight_decay, int step, const float* gscale,
+                cudaStream_t s);
+// coef[0] = min(1, max_norm / (||g||_2 + 1e-6)) over all tensors (clip_grad_norm_), norm_out[0] = ||g||_2 (optional)
+int grad_clip_coef(int n, const float* const* g, const long long* counts, float max_norm, float* scratch, float* coef,
+                   float* norm_out, cudaStream_t s);
+
 // ---- eval.cu -------------------------------------------------------------------------------------
 // OpenMax re-scaling (classifier.py:240-275): logits_out = logits * (u > 0.3 ? 1 - 0.8u : 1)
 int openmax_fwd(const float* feats, const float* logits, const float* act_vecs, const float* w_alpha,

@@ -125,6 +125,49 @@ def test_tcgen05_gemm_variants_through_the_cabi(shape):
         assert ((o2.double() - ref2).abs().max() / ref2.abs().max()).item() < 1e-2
 
 
+def test_fused_adamw_matches_torch_adamw():
+    """FusedAdamW + fused clip_grad_norm_ against the reference's optimizer (torch.optim.AdamW and
+    torch.nn.utils.clip_grad_norm_, run on CPU in float64) over several steps with a LambdaLR schedule, two parameter
+    groups with their own lr / weight decay (src/train.py:72-83), odd tensor sizes and unaligned views."""
+    import mmser_b200
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    shapes = [(768, 256), (256,), (3, 5, 7), (1,), (1027,), (35, 512)]
+    flat = torch.randn(sum(int(torch.tensor(s).prod()) for s in shapes) + 3, generator=g)
+    ref_params, cu_params, off = [], [], 1                      # offset 1: 4-byte aligned only -> scalar path
+    flat_cu = flat.to(dev)
+    for s_ in shapes:
+        n = int(torch.tensor(s_).prod())
+        ref_params.append(flat[off:off + n].view(s_).double().clone().requires_grad_(True))
+        cu_params.append(torch.nn.Parameter(flat_cu[off:off + n].view(s_)))
+        off += n
+    def groups(ps):
+        return [dict(params=ps[:3], lr=2e-3, weight_decay=0.05), dict(params=ps[3:], lr=3e-3, weight_decay=0.0)]
+    ref_opt = torch.optim.AdamW(groups(ref_params), betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    cu_opt = mmser_b200.optim.FusedAdamW(groups(cu_params), betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    lam = lambda step: 0.5 + 0.1 * step                                          # noqa: E731
+    ref_sched = torch.optim.lr_scheduler.LambdaLR(ref_opt, lam)
+    cu_sched = torch.optim.lr_scheduler.LambdaLR(cu_opt, lam)
+    for it in range(4):
+        for rp, cp in zip(ref_params, cu_params):
+            gr = torch.randn(rp.shape, generator=g) * (10.0 if it == 2 else 1.0)
+            rp.grad = gr.double()
+            cp.grad = gr.to(dev)
+        if it >= 1:                                                              # clipping active from the second step on
+            n_ref = torch.nn.utils.clip_grad_norm_(ref_params, 5.0)
+            n_cu = cu_opt.clip_grad_norm_(5.0)
+            assert abs(float(n_cu) - float(n_ref)) <= 1e-5 * float(n_ref)
+        ref_opt.step(); cu_opt.step()
+        ref_sched.step(); cu_sched.step()
+        for rp, cp in zip(ref_params, cu_params):
+            err = (cp.detach().cpu().double() - rp.detach()).abs().max().item() / (rp.detach().abs().max().item() + 1e-12)
+            assert err < 2e-6, (it, tuple(rp.shape), err)
+    st = cu_opt.state_dict()
+    assert len(st["state"]) == len(shapes) and st["param_groups"][1]["weight_decay"] == 0.0
+    # gradients are NOT modified by the fused clipping (the coefficient is applied inside the update)
+    assert torch.equal(cu_params[0].grad, cu_params[0].grad.clone())
+
+
 def test_precast_tracks_parameter_updates():
     """FusionHead casts the bf16 operand copies of all modules in one launch per forward (FlatParams.precast); an
     in-place parameter update between two forwards (what an optimizer step is) must be picked up."""
