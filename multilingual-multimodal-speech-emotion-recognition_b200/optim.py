@@ -75,6 +75,9 @@ class FusedAdamW(torch.optim.Optimizer):
                                         float(group["weight_decay"]), cache["step"],
                                         None if coef is None else coef.data_ptr(), L.stream_ptr(params[0].device)),
                     "ser_adamw_multi")
+            # the kernel wrote the parameters behind autograd's back: bump their version counters like an in-place
+            # torch op would (consumers such as FlatParams' cached bf16 operand copies key on them)
+            torch.autograd.graph.increment_version(params)
         return loss
 
     def _group_cache(self, gi, group, params):

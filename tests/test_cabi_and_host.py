@@ -121,6 +121,21 @@ def test_dropout_is_active_only_in_training_mode(lib):
         f(torch.randn(2, 1536), torch.randn(2, 1536))
 
 
+def test_fused_adamw_host_side(lib):
+    """Constructor contract of the torch.optim.AdamW replacement; CPU tensors fail loudly (no fallback)."""
+    import mmser_b200
+    w = torch.nn.Parameter(torch.zeros(4, 4))
+    with pytest.raises(ValueError):
+        mmser_b200.optim.FusedAdamW([w], lr=-1.0)
+    opt = mmser_b200.optim.FusedAdamW([dict(params=[w], lr=1e-3, weight_decay=0.1)], weight_decay=0.05)
+    assert opt.param_groups[0]["weight_decay"] == 0.1 and opt.param_groups[0]["betas"] == (0.9, 0.999)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 0.5)
+    assert opt.param_groups[0]["lr"] == pytest.approx(5e-4) and sched is not None
+    w.grad = torch.ones(4, 4)
+    with pytest.raises(lib.SerError):
+        opt.step()
+
+
 def test_global_batch_loss_algebra():
     """per-shard raw sums + global class counts + B_global reproduce the single-process loss."""
     from oracle import fusion_head_oracle as O
