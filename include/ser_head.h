@@ -127,6 +127,10 @@ typedef struct ser_adapter_desc {
   void* dh;                                /* [M,S] act scratch                                   */
   void* dx;                                /* [M,D] act or NULL (frozen-encoder input)            */
   float* dw1; float* db1; float* dw2; float* db2;   /* overwritten                                */
+  int grads_zeroed;                        /* 1: the caller hands in zero-filled parameter-gradient buffers (one
+                                              allocation per module in the Python binding), so the library skips its own
+                                              zeroing of split-K / atomically accumulated outputs; same field in the
+                                              descriptors below                                                       */
 } ser_adapter_desc;
 int ser_adapter_fwd(const ser_adapter_desc* d, void* stream);
 int ser_adapter_bwd(const ser_adapter_desc* d, void* stream);
@@ -165,6 +169,7 @@ typedef struct ser_xattn_desc {
   float* dwout_a; float* dbout_a; float* dwout_t; float* dbout_t;
   float* dln_a_g; float* dln_a_b; float* dln_t_g; float* dln_t_b;
   void* ws; size_t ws_bytes;               /* backward scratch, ser_xattn_bwd_ws_bytes()          */
+  int grads_zeroed;
 } ser_xattn_desc;
 size_t ser_xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H);
 int ser_xattn_fwd(const ser_xattn_desc* d, void* stream);
@@ -184,6 +189,7 @@ typedef struct ser_asp_desc {
   void* dx;                                /* [B*T,D] act                                         */
   void* dpre; float* dalpha;               /* [B*T,Hd] act scratch; [B,T] fp32 scratch            */
   float* dw1; float* db1; float* dw2; float* db2;   /* overwritten                                */
+  int grads_zeroed;
 } ser_asp_desc;
 int ser_asp_fwd(const ser_asp_desc* d, void* stream);
 int ser_asp_bwd(const ser_asp_desc* d, void* stream);
@@ -206,6 +212,7 @@ typedef struct ser_fusion_desc {
   float* dw1a; float* db1a; float* dw2a; float* db2a; float* dw1t; float* db1t; float* dw2t; float* db2t;
   float* dwg1a; float* dbg1a; float* dwg2a; float* dbg2a; float* dwg1t; float* dbg1t; float* dwg2t; float* dbg2t;
   void* ws; size_t ws_bytes;               /* ser_fusion_bwd_ws_bytes()                           */
+  int grads_zeroed;
 } ser_fusion_desc;
 size_t ser_fusion_bwd_ws_bytes(int dtype, int B, int Din, int P, int G);
 int ser_fusion_fwd(const ser_fusion_desc* d, void* stream);
@@ -246,6 +253,7 @@ typedef struct ser_clf_desc {
   float* dw_out; float* db_out; float* dln_out_g; float* dln_out_b;
   float* dw_c; float* db_c; float* dw_u1; float* db_u1; float* dw_u2; float* db_u2;
   void* ws; size_t ws_bytes;               /* ser_clf_bwd_ws_bytes()                              */
+  int grads_zeroed;
 } ser_clf_desc;
 size_t ser_clf_bwd_ws_bytes(int dtype, int B, int P, int F, int C, int U);
 int ser_clf_fwd(const ser_clf_desc* d, void* stream);

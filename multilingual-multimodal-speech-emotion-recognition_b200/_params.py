@@ -121,6 +121,8 @@ class FlatParams:
                 fp._fresh[dtype] = fp._versions()
 
     def new_grad_buffer(self) -> torch.Tensor:
+        """Zero-filled: the backward descriptors are filled with grads_zeroed = 1, so the library neither zeroes its
+        split-K / atomically accumulated outputs itself nor touches the alignment padding between parameters."""
         return torch.zeros(self.total, device=self.flat.device, dtype=torch.float32)
 
     def grads_from(self, gflat: torch.Tensor) -> List[torch.Tensor]:

@@ -187,6 +187,8 @@ struct GemmArgs {
   // optional by-product of dW-type GEMMs (a_trans): rowsum[m] = sum_k op(A)[m, k], i.e. the bias gradient when
   // A = dY stored [tokens, features].  Overwritten.  Batched: rowsum + b * strideRS.
   float* rowsum = nullptr; long long strideRS = 0;
+  // the caller guarantees that C (when split-K accumulates into it) and rowsum already hold zeros: skip the memsets
+  int out_zeroed = 0;
 };
 
 int gemm(const GemmArgs& a, cudaStream_t stream);

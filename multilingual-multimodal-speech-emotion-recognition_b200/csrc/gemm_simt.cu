@@ -158,7 +158,7 @@ int gemm_simt_f32(const GemmArgs& a0, cudaStream_t stream) {
     accumulate = 1;
   }
   ep.atomic = (splits > 1 || accumulate) ? 1 : 0;
-  if (ep.atomic && !accumulate) {
+  if (ep.atomic && !accumulate && !a.out_zeroed) {
     SER_CUDA_CHECK(cudaMemset2DAsync(a.C, a.ldc * sizeof(float), 0, a.N * sizeof(float), a.M, stream));
   }
   const float* A = reinterpret_cast<const float*>(a.A);

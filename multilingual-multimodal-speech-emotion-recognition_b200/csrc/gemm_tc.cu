@@ -814,7 +814,8 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   if (a.rowsum != nullptr) {
     SER_REQUIRE(gemm_tc_rowsum_ok(a), "gemm_tc: rowsum rides on plain dW-type GEMMs only (both operands MN-major)");
     const int nb = a.batch > 1 ? a.batch : 1;
-    if (nb == 1 || a.strideRS == a.M) SER_CUDA_CHECK(cudaMemsetAsync(a.rowsum, 0, sizeof(float) * a.M * nb, stream));
+    if (a.out_zeroed) { /* caller's buffer is zero-filled */ }
+    else if (nb == 1 || a.strideRS == a.M) SER_CUDA_CHECK(cudaMemsetAsync(a.rowsum, 0, sizeof(float) * a.M * nb, stream));
     else SER_CUDA_CHECK(cudaMemset2DAsync(a.rowsum, a.strideRS * sizeof(float), 0, a.M * sizeof(float), nb, stream));
   }
   const void* R = a.R;
@@ -846,7 +847,7 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   ep.atomic = (splits > 1 || accumulate) ? 1 : 0;
   if (ep.atomic) {
     SER_REQUIRE(a.c_f32, "gemm_tc: accumulate / split-K needs an fp32 output");
-    if (!accumulate) {
+    if (!accumulate && !a.out_zeroed) {
       for (int b = 0; b < (a.batch > 1 ? a.batch : 1); ++b)
         SER_CUDA_CHECK(cudaMemset2DAsync(reinterpret_cast<float*>(a.C) + b * a.strideC, a.ldc * sizeof(float), 0,
                                          a.N * sizeof(float), a.M, stream));

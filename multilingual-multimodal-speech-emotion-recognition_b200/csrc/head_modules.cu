@@ -63,15 +63,22 @@ int linear_dgrad(int dt, int M, int Nout, int Kin, const void* dY, long long ldd
 // dW[Nout,Kin] (fp32) = dY[M,Nout]^T X[M,Kin];  db[Nout] (optional) = column sums of dY, produced by the same GEMM in
 // the bf16 tier (gemm_tc.cu row-sum MMAs) and by a colsum launch otherwise
 int linear_wgrad(int dt, int M, int Nout, int Kin, const void* dY, long long lddy, const void* X, long long ldx,
-                 float* dW, long long lddw, cudaStream_t s, float* db = nullptr) {
+                 float* dW, long long lddw, cudaStream_t s, float* db = nullptr, int zeroed = 0) {
   GemmArgs g;
   g.rowsum = db;
+  g.out_zeroed = zeroed;          // dW / db already hold zeros (descriptor field grads_zeroed): no memsets
   g.dtype = dt; g.M = Nout; g.N = Kin; g.K = M;
   g.A = dY; g.lda = lddy; g.a_trans = 1;
   g.B = X; g.ldb = ldx; g.b_trans = 1;
   g.C = dW; g.ldc = lddw; g.c_f32 = 1;
   return gemm(g, s);
 }
+
+// zero a parameter-gradient region unless the caller handed in zero-filled buffers
+#define SER_ZERO_UNLESS(zeroed, ptr, bytes)                                   \
+  do {                                                                        \
+    if (!(zeroed)) SER_CUDA_CHECK(cudaMemsetAsync((ptr), 0, (bytes), s));     \
+  } while (0)
 
 }  // namespace
 
@@ -90,9 +97,9 @@ int adapter_fwd(const ser_adapter_desc& d, cudaStream_t s) {
 int adapter_bwd(const ser_adapter_desc& d, cudaStream_t s) {
   const int dt = d.dtype, f = is_f32(dt);
   SER_REQUIRE(d.M > 0 && d.dy && d.dh && d.h && d.x, "adapter_bwd: null tensor");
-  SER_TRY(linear_wgrad(dt, d.M, d.D, d.S, d.dy, d.D, d.h, d.S, d.dw2, d.S, s, d.db2));
+  SER_TRY(linear_wgrad(dt, d.M, d.D, d.S, d.dy, d.D, d.h, d.S, d.dw2, d.S, s, d.db2, d.grads_zeroed));
   SER_TRY(linear_dgrad(dt, d.M, d.D, d.S, d.dy, d.D, d.w2, d.S, d.dh, d.S, f, d.h, d.S, f, GATE_RELU, nullptr, 0, f, s));
-  SER_TRY(linear_wgrad(dt, d.M, d.S, d.D, d.dh, d.S, d.x, d.D, d.dw1, d.D, s, d.db1));
+  SER_TRY(linear_wgrad(dt, d.M, d.S, d.D, d.dh, d.S, d.x, d.D, d.dw1, d.D, s, d.db1, d.grads_zeroed));
   if (d.dx != nullptr)
     SER_TRY(linear_dgrad(dt, d.M, d.S, d.D, d.dh, d.S, d.w1, d.D, d.dx, d.D, f, nullptr, 0, f, GATE_NONE,
                          d.add_residual ? d.dy : nullptr, d.D, f, s));
@@ -253,11 +260,13 @@ static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
     }
   }
   if (!ws.ok) { set_last_error(__FILE__, __LINE__, "xattn_bwd: workspace too small"); return SER_ERR_WORKSPACE; }
+  // the weight-sized scratch (split-K / row-sum targets dbz, dbc, dWz, dWc) is zeroed with ONE memset
+  SER_CUDA_CHECK(cudaMemsetAsync(dbz[0], 0, reinterpret_cast<char*>(dwc16[0]) - reinterpret_cast<char*>(dbz[0]), s));
 
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_a_g, 0, sizeof(float) * D, s));
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_a_b, 0, sizeof(float) * D, s));
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_t_g, 0, sizeof(float) * D, s));
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_t_b, 0, sizeof(float) * D, s));
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_a_g, sizeof(float) * D);
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_a_b, sizeof(float) * D);
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_t_g, sizeof(float) * D);
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_t_b, sizeof(float) * D);
   // with dropout on, the LayerNorm backward also writes the branch gradient mask * dz (the skip path keeps dz)
   const DropSpec drop_ra = with_site(drop, DS_XA_RES_A), drop_rt = with_site(drop, DS_XA_RES_T);
   SER_TRY(layernorm_bwd(d.d_enh_a, f, d.z_a, f, d.stats_a, d.ln_a_g, d.ln_a_b, nullptr, f, dz_a, f, nullptr, f,
@@ -272,7 +281,7 @@ static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
       {Mt, dzm_t, d.ctx_t, dctx_t, fb.wz_t, d.wout_t, d.wo_t, d.dwout_t, d.dwo_t, 1},
   };
   for (const SideZ& z : sz) {
-    SER_TRY(linear_wgrad(dt, z.M, D, S, z.dz, D, z.ctx, S, dwz32[z.m], S, s, dbz[z.m]));
+    SER_TRY(linear_wgrad(dt, z.M, D, S, z.dz, D, z.ctx, S, dwz32[z.m], S, s, dbz[z.m], 1));
     SER_TRY(linear_dgrad(dt, z.M, D, S, z.dz, D, z.wz, S, z.dctx, S, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
   }
   SER_TRY(cast_any(dwz32[0], 1, dwz16[0], 0, 2LL * D * S, s));
@@ -304,7 +313,7 @@ static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
       {Mt, dp_t, d.t, d.dt, dz_t, fb.wc_t, fb.wbd_t, d.wqkv_t, d.dwqkv_t, 1},
   };
   for (const SideP& p : sp) {
-    SER_TRY(linear_wgrad(dt, p.M, S3, D, p.dp, S3, p.x, D, dwc32[p.m], D, s, dbc[p.m]));
+    SER_TRY(linear_wgrad(dt, p.M, S3, D, p.dp, S3, p.x, D, dwc32[p.m], D, s, dbc[p.m], 1));
     SER_TRY(linear_dgrad(dt, p.M, S3, D, p.dp, S3, p.wc, D, p.dx, D, f, nullptr, 0, f, GATE_NONE, p.dz, D, f, s));
   }
   SER_TRY(cast_any(dwc32[0], 1, dwc16[0], 0, 2LL * S3 * D, s));
@@ -416,10 +425,10 @@ int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
   if (!ws.ok) { set_last_error(__FILE__, __LINE__, "xattn_bwd: workspace too small"); return SER_ERR_WORKSPACE; }
 
   // LayerNorm backward (parameter gradients accumulate with atomics -> zero first)
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_a_g, 0, sizeof(float) * D, s));
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_a_b, 0, sizeof(float) * D, s));
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_t_g, 0, sizeof(float) * D, s));
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_t_b, 0, sizeof(float) * D, s));
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_a_g, sizeof(float) * D);
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_a_b, sizeof(float) * D);
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_t_g, sizeof(float) * D);
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_t_b, sizeof(float) * D);
   const DropSpec drop_ra = with_site(drop, DS_XA_RES_A), drop_rt = with_site(drop, DS_XA_RES_T);
   SER_TRY(layernorm_bwd(d.d_enh_a, f, d.z_a, f, d.stats_a, d.ln_a_g, d.ln_a_b, nullptr, f, dz_a, f, nullptr, f,
                         d.dln_a_g, d.dln_a_b, Ma, D, 0, s, drop.on() ? dzm_a : nullptr, &drop_ra));
@@ -434,9 +443,9 @@ int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
       {Mt, dzm_t, d.o_t, d.ctx_t, do_t, dctx_t, d.wout_t, d.wo_t, d.dwout_t, d.dbout_t, d.dwo_t, d.dbo_t},
   };
   for (const Side& sd : sides) {
-    SER_TRY(linear_wgrad(dt, sd.M, D, S, sd.dz, D, sd.o, S, sd.dwout, S, s, sd.dbout));
+    SER_TRY(linear_wgrad(dt, sd.M, D, S, sd.dz, D, sd.o, S, sd.dwout, S, s, sd.dbout, d.grads_zeroed));
     SER_TRY(linear_dgrad(dt, sd.M, D, S, sd.dz, D, sd.wout, S, sd.dob, S, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
-    SER_TRY(linear_wgrad(dt, sd.M, S, S, sd.dob, S, sd.ctx, S, sd.dwo, S, s, sd.dbo));
+    SER_TRY(linear_wgrad(dt, sd.M, S, S, sd.dob, S, sd.ctx, S, sd.dwo, S, s, sd.dbo, d.grads_zeroed));
     SER_TRY(linear_dgrad(dt, sd.M, S, S, sd.dob, S, sd.wo, S, sd.dctx, S, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
   }
   // attention core backward
@@ -470,14 +479,14 @@ int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
   };
   for (const InProjB& p : ip) {
     const void* g = off(p.dp, p.col, dt);
-    SER_TRY(linear_wgrad(dt, p.M, S, S, g, S3, off(p.src, p.col, dt), S3, p.dw + static_cast<long long>(p.wrow) * S, S, s, p.db + p.wrow));
+    SER_TRY(linear_wgrad(dt, p.M, S, S, g, S3, off(p.src, p.col, dt), S3, p.dw + static_cast<long long>(p.wrow) * S, S, s, p.db + p.wrow, d.grads_zeroed));
     SER_TRY(linear_dgrad(dt, p.M, S, S, g, S3, off(p.w, static_cast<long long>(p.wrow) * S, dt), S,
                          off(p.dsrc, p.col, dt), S3, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
   }
   // outer projections + residual path
-  SER_TRY(linear_wgrad(dt, Ma, S3, D, dqkv_a, S3, d.a, D, d.dwqkv_a, D, s, d.dbqkv_a));
+  SER_TRY(linear_wgrad(dt, Ma, S3, D, dqkv_a, S3, d.a, D, d.dwqkv_a, D, s, d.dbqkv_a, d.grads_zeroed));
   SER_TRY(linear_dgrad(dt, Ma, S3, D, dqkv_a, S3, d.wqkv_a, D, d.da, D, f, nullptr, 0, f, GATE_NONE, dz_a, D, f, s));
-  SER_TRY(linear_wgrad(dt, Mt, S3, D, dqkv_t, S3, d.t, D, d.dwqkv_t, D, s, d.dbqkv_t));
+  SER_TRY(linear_wgrad(dt, Mt, S3, D, dqkv_t, S3, d.t, D, d.dwqkv_t, D, s, d.dbqkv_t, d.grads_zeroed));
   SER_TRY(linear_dgrad(dt, Mt, S3, D, dqkv_t, S3, d.wqkv_t, D, d.dt, D, f, nullptr, 0, f, GATE_NONE, dz_t, D, f, s));
   return SER_OK;
 }
@@ -506,10 +515,10 @@ int asp_module_bwd(const ser_asp_desc& d, cudaStream_t s) {
   const int dt = d.dtype, f = is_f32(dt);
   const int M = d.B * d.T;
   SER_REQUIRE(d.dout && d.dx && d.dpre && d.dalpha, "asp_bwd: null tensor");
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dw2, 0, sizeof(float) * d.Hd, s));
-  SER_CUDA_CHECK(cudaMemsetAsync(d.db2, 0, sizeof(float), s));
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dw2, sizeof(float) * d.Hd);
+  SER_ZERO_UNLESS(d.grads_zeroed, d.db2, sizeof(float));
   SER_TRY(asp_bwd(to_asp(d), s));
-  SER_TRY(linear_wgrad(dt, M, d.Hd, d.D, d.dpre, d.Hd, d.x, d.D, d.dw1, d.D, s, d.db1));
+  SER_TRY(linear_wgrad(dt, M, d.Hd, d.D, d.dpre, d.Hd, d.x, d.D, d.dw1, d.D, s, d.db1, d.grads_zeroed));
   SER_TRY(linear_dgrad(dt, M, d.Hd, d.D, d.dpre, d.Hd, d.w1, d.D, d.dx, d.D, f, nullptr, 0, f, GATE_NONE, d.dx, d.D, f, s));
   return SER_OK;
 }
@@ -561,10 +570,10 @@ int fusion_bwd(const ser_fusion_desc& d, cudaStream_t s) {
   void* dga = ws.take(static_cast<size_t>(B) * G * e);
   void* dgt = ws.take(static_cast<size_t>(B) * G * e);
   if (!ws.ok) { set_last_error(__FILE__, __LINE__, "fusion_bwd: workspace too small"); return SER_ERR_WORKSPACE; }
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dwg2a, 0, sizeof(float) * G, s));
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dwg2t, 0, sizeof(float) * G, s));
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dbg2a, 0, sizeof(float), s));
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dbg2t, 0, sizeof(float), s));
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dwg2a, sizeof(float) * G);
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dwg2t, sizeof(float) * G);
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dbg2a, sizeof(float));
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dbg2t, sizeof(float));
   const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);
   const float hscale = drop.on() ? drop.scale : 1.f;
   MixArgs m = to_mix(d);
@@ -577,12 +586,12 @@ int fusion_bwd(const ser_fusion_desc& d, cudaStream_t s) {
       {dpt, dgt, dht, d.pt, d.ht, d.tv, d.wg1t, d.w2t, d.w1t, d.dwg1t, d.dbg1t, d.dw2t, d.db2t, d.dw1t, d.db1t, d.dtv},
   };
   for (const Side& sd : sides) {
-    SER_TRY(linear_wgrad(dt, B, G, P, sd.dg, G, sd.p, P, sd.dwg1, P, s, sd.dbg1));
+    SER_TRY(linear_wgrad(dt, B, G, P, sd.dg, G, sd.p, P, sd.dwg1, P, s, sd.dbg1, d.grads_zeroed));
     SER_TRY(linear_dgrad(dt, B, G, P, sd.dg, G, sd.wg1, P, sd.dp, P, f, nullptr, 0, f, GATE_NONE, sd.dp, P, f, s));
-    SER_TRY(linear_wgrad(dt, B, P, P, sd.dp, P, sd.h, P, sd.dw2, P, s, sd.db2));
+    SER_TRY(linear_wgrad(dt, B, P, P, sd.dp, P, sd.h, P, sd.dw2, P, s, sd.db2, d.grads_zeroed));
     // h is saved post-dropout: h > 0 exactly where the unit was kept and the ReLU open; the kept units carry 1/(1-p)
     SER_TRY(linear_dgrad(dt, B, P, P, sd.dp, P, sd.w2, P, sd.dh, P, f, sd.h, P, f, GATE_RELU, nullptr, 0, f, s, hscale));
-    SER_TRY(linear_wgrad(dt, B, P, Din, sd.dh, P, sd.v, Din, sd.dw1, Din, s, sd.db1));
+    SER_TRY(linear_wgrad(dt, B, P, Din, sd.dh, P, sd.v, Din, sd.dw1, Din, s, sd.db1, d.grads_zeroed));
     SER_TRY(linear_dgrad(dt, B, P, Din, sd.dh, P, sd.w1, Din, sd.dv, Din, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
   }
   return SER_OK;
@@ -713,11 +722,11 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
                     d.db_u1, d.dw_u2, d.db_u2, B, F, C, U, with_site(drop, DS_CLF_UNC), s));
   if (drop.on()) SER_TRY(dropout_apply(df, df, nullptr, 1, B, F, with_site(drop, DS_CLF_OUT), s));
   // ---- output projection: relu(LN(q)) ----
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_out_g, 0, sizeof(float) * F, s));
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_out_b, 0, sizeof(float) * F, s));
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_out_g, sizeof(float) * F);
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_out_b, sizeof(float) * F);
   SER_TRY(layernorm_bwd(df, 1, d.q, 1, d.stats_q, d.ln_out_g, d.ln_out_b, nullptr, 1, dq, f, nullptr, 1, d.dln_out_g,
                         d.dln_out_b, B, F, 1, s));
-  SER_TRY(linear_wgrad(dt, B, F, P, dq, F, d.h_last, P, d.dw_out, P, s, d.db_out));
+  SER_TRY(linear_wgrad(dt, B, F, P, dq, F, d.h_last, P, d.dw_out, P, s, d.db_out, d.grads_zeroed));
   SER_TRY(linear_dgrad(dt, B, F, P, dq, F, d.w_out, P, dh32, P, 1, nullptr, 0, 1, GATE_NONE, nullptr, 0, 1, s));
   ClfStackArgs sa;
   bool fused = stack_args(d, sa) && stack_grad_args(d, sa);
@@ -766,6 +775,7 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
     GemmArgs g;
     g.dtype = dt; g.M = P; g.N = P; g.K = B; g.a_trans = 1; g.b_trans = 1; g.lda = P; g.ldb = P; g.ldc = P; g.c_f32 = 1;
     g.batch = L; g.strideA = static_cast<long long>(BP); g.strideB = static_cast<long long>(BP);
+    g.out_zeroed = d.grads_zeroed;
     // bias gradients ride on the weight-gradient GEMMs (row sums of the MN-major dY operand)
     g.A = dhn_all; g.B = d.r; g.C = d.dw2[0]; g.strideC = sw2; g.rowsum = d.db2[0]; g.strideRS = sb2;
     SER_TRY(gemm(g, s));
@@ -775,17 +785,17 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
     for (int i = 0; i < L; ++i) {
       const void* dhn_i = off(static_cast<const void*>(dhn_all), static_cast<long long>(i) * BP, dt);
       const void* dr_i = off(static_cast<const void*>(dr_all), static_cast<long long>(i) * BP, dt);
-      SER_TRY(linear_wgrad(dt, B, P, P, dhn_i, P, off(static_cast<const void*>(d.r), static_cast<long long>(i) * BP, dt), P, d.dw2[i], P, s, d.db2[i]));
-      SER_TRY(linear_wgrad(dt, B, P, P, dr_i, P, off(static_cast<const void*>(d.n), static_cast<long long>(i) * BP, dt), P, d.dw1[i], P, s, d.db1[i]));
+      SER_TRY(linear_wgrad(dt, B, P, P, dhn_i, P, off(static_cast<const void*>(d.r), static_cast<long long>(i) * BP, dt), P, d.dw2[i], P, s, d.db2[i], d.grads_zeroed));
+      SER_TRY(linear_wgrad(dt, B, P, P, dr_i, P, off(static_cast<const void*>(d.n), static_cast<long long>(i) * BP, dt), P, d.dw1[i], P, s, d.db1[i], d.grads_zeroed));
     }
   }
   // ---- input projection: h0 = relu(LN(p0)) ----
   if (drop.on()) SER_TRY(dropout_apply(cur, cur, nullptr, 1, B, P, with_site(drop, DS_CLF_IN), s));
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_in_g, 0, sizeof(float) * P, s));
-  SER_CUDA_CHECK(cudaMemsetAsync(d.dln_in_b, 0, sizeof(float) * P, s));
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_in_g, sizeof(float) * P);
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_in_b, sizeof(float) * P);
   SER_TRY(layernorm_bwd(cur, 1, d.p0, 1, d.stats0, d.ln_in_g, d.ln_in_b, nullptr, 1, dp0, f, nullptr, 1, d.dln_in_g,
                         d.dln_in_b, B, P, 1, s));
-  SER_TRY(linear_wgrad(dt, B, P, P, dp0, P, d.x, P, d.dw_in, P, s, d.db_in));
+  SER_TRY(linear_wgrad(dt, B, P, P, dp0, P, d.x, P, d.dw_in, P, s, d.db_in, d.grads_zeroed));
   if (d.dx != nullptr)
     SER_TRY(linear_dgrad(dt, B, P, P, dp0, P, d.w_in, P, d.dx, P, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
   return SER_OK;
