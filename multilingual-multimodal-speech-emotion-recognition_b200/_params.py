@@ -34,6 +34,7 @@ class FlatParams:
         self.flat: torch.Tensor | None = None
         self._lowp: Dict[torch.dtype, torch.Tensor] = {}
         self._fresh: Dict[torch.dtype, tuple] = {}     # set by precast(): parameter versions the low-precision copy holds
+        self._next_grad: torch.Tensor | None = None    # set by shared_grad_arena(): this module's slice of one zero-filled arena
         self.index = {n: i for i, n in enumerate(self.names)}
         # data-parallel hook: called as hook(flat_params, flat_grad_buffer) at the end of the module's backward,
         # i.e. as soon as this module's gradients are final (see parallel.py)
@@ -123,7 +124,26 @@ class FlatParams:
     def new_grad_buffer(self) -> torch.Tensor:
         """Zero-filled: the backward descriptors are filled with grads_zeroed = 1, so the library neither zeroes its
         split-K / atomically accumulated outputs itself nor touches the alignment padding between parameters."""
+        g, self._next_grad = self._next_grad, None
+        if g is not None and g.device == self.flat.device:
+            return g
         return torch.zeros(self.total, device=self.flat.device, dtype=torch.float32)
+
+    @staticmethod
+    def shared_grad_arena(flats: Sequence["FlatParams"]) -> None:
+        """One zero-filled allocation (one fill kernel) for the gradient buffers of several modules' next backward:
+        every module's new_grad_buffer() then returns its slice.  Inside a captured CUDA graph every node costs a few
+        microseconds of serialisation, so seven fills become one."""
+        if not flats:
+            return
+        for fp in flats:
+            fp.ensure()
+        dev = flats[0].flat.device
+        arena = torch.zeros(sum(fp.total for fp in flats), device=dev, dtype=torch.float32)
+        off = 0
+        for fp in flats:
+            fp._next_grad = arena[off:off + fp.total]
+            off += fp.total
 
     def grads_from(self, gflat: torch.Tensor) -> List[torch.Tensor]:
         if self.grad_hook is not None:

@@ -71,8 +71,10 @@ class FusionHead(nn.Module):
 
     def features(self, a_hid, t_hid, a_mask=None, t_mask=None):
         # bf16 tier: the operand copies of all modules' weights in one launch instead of one per module
-        FlatParams.precast([getattr(self, g)._flat for g in self.GROUPS if hasattr(getattr(self, g), "_flat")],
-                           a_hid.dtype)
+        flats = [getattr(self, g)._flat for g in self.GROUPS if hasattr(getattr(self, g), "_flat")]
+        FlatParams.precast(flats, a_hid.dtype)
+        if torch.is_grad_enabled():
+            FlatParams.shared_grad_arena(flats)       # one zero fill for all modules' gradient buffers of this step
         a_seq = self.adapter_a.residual_forward(a_hid)
         t_seq = self.adapter_t.residual_forward(t_hid)
         a_enh, t_enh = self.cross(a_seq, t_seq, a_mask, t_mask)
@@ -94,5 +96,5 @@ class FusionHead(nn.Module):
             cfg.update(loss_cfg)
         terms = HeadLossFn.apply(logits, unc, out["fused"], self.prototypes.prototypes, labels, cfg)
         out.update(logits=logits, unc=unc, anchor=anchor_loss, ce=terms[0], focal=terms[1], unc_loss=terms[2],
-                   proto=terms[3], loss=terms[4] + 0.1 * anchor_loss, accuracy=terms[5])
+                   proto=terms[3], loss=terms[4], accuracy=terms[5])      # (+ 0.1 * anchor_loss, train.py:158: identically 0, see classifier)
         return out

@@ -97,7 +97,12 @@ class AdvancedOpenMaxClassifier(nn.Module):
         logits, unc, feats = SF.ClassifierFn.apply(x, self._flat, self.num_layers, return_uncertainty, p, seed,
                                                    *self._flat.params)
         self.last_features = feats
-        anchor_loss = torch.zeros((), device=x.device, dtype=torch.float32)   # identically 0 in the reference
+        # identically 0 in the reference (classifier.py:64-68); one cached device scalar instead of a fill per call
+        z = self.__dict__.get("_zero_scalar")
+        if z is None or z.device != x.device:
+            z = torch.zeros((), device=x.device, dtype=torch.float32)
+            self.__dict__["_zero_scalar"] = z
+        anchor_loss = z
         if use_openmax and not self.training:
             logits = self.openmax_forward(feats, logits)
         if return_uncertainty:
