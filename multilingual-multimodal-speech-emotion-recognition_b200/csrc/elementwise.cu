@@ -59,6 +59,15 @@ cast_multi_kernel(const CastSegs segs) {
   }
 }
 
+// zero a 16-byte aligned region: a kernel node instead of a memset node (inside a captured graph a memset between two
+// kernels costs ~4 us of serialisation, a small kernel well under 2)
+__global__ void __launch_bounds__(256)
+zero_kernel(uint4* __restrict__ p, long long n16) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // blockDim = (32, 8): x walks columns, y walks rows; grid = (ceil(N/32), row_splits)
 __global__ void colsum_kernel(const void* __restrict__ X, int x_f32, long long ld, int M, int N,
                               float* __restrict__ out) {
@@ -555,6 +564,19 @@ int cast_any(const void* src, int src_f32, void* dst, int dst_f32, long long n, 
   if (blocks < 1) blocks = 1;
   ProfScope prof("cast", 0.0, static_cast<double>(n) * ((src_f32 ? 4 : 2) + (dst_f32 ? 4 : 2)), s);
   cast_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(src, src_f32, dst, dst_f32, n);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
+int zero_async(void* p, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return SER_OK;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) != 0 || (bytes & 15) != 0) {
+    SER_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, s));
+    return SER_OK;
+  }
+  const long long n16 = static_cast<long long>(bytes / 16);
+  const int blocks = static_cast<int>(min(static_cast<long long>(device_sm_count()) * 4, (n16 + 255) / 256));
+  zero_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(p), n16);
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

@@ -77,7 +77,7 @@ int linear_wgrad(int dt, int M, int Nout, int Kin, const void* dY, long long ldd
 // zero a parameter-gradient region unless the caller handed in zero-filled buffers
 #define SER_ZERO_UNLESS(zeroed, ptr, bytes)                                   \
   do {                                                                        \
-    if (!(zeroed)) SER_CUDA_CHECK(cudaMemsetAsync((ptr), 0, (bytes), s));     \
+    if (!(zeroed)) SER_TRY(zero_async((ptr), (bytes), s));                    \
   } while (0)
 
 }  // namespace
@@ -261,7 +261,7 @@ static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
   }
   if (!ws.ok) { set_last_error(__FILE__, __LINE__, "xattn_bwd: workspace too small"); return SER_ERR_WORKSPACE; }
   // the weight-sized scratch (split-K / row-sum targets dbz, dbc, dWz, dWc) is zeroed with ONE memset
-  SER_CUDA_CHECK(cudaMemsetAsync(dbz[0], 0, reinterpret_cast<char*>(dwc16[0]) - reinterpret_cast<char*>(dbz[0]), s));
+  SER_TRY(zero_async(dbz[0], reinterpret_cast<char*>(dwc16[0]) - reinterpret_cast<char*>(dbz[0]), s));
 
   SER_ZERO_UNLESS(d.grads_zeroed, d.dln_a_g, sizeof(float) * D);
   SER_ZERO_UNLESS(d.grads_zeroed, d.dln_a_b, sizeof(float) * D);

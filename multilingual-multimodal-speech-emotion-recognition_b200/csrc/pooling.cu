@@ -351,7 +351,7 @@ int asp_fwd_impl(const AspArgs& a, cudaStream_t s) {
 template <typename T>
 int asp_bwd_impl(const AspArgs& a, cudaStream_t s) {
   ProfScope prof("asp_bwd", 0.0, sizeof(T) * static_cast<double>(a.B) * a.T * (2.0 * a.D + 2.0 * a.Hd), s);
-  SER_CUDA_CHECK(cudaMemsetAsync(a.dalpha, 0, sizeof(float) * a.B * a.T, s));
+  SER_TRY(zero_async(a.dalpha, sizeof(float) * a.B * a.T, s));
   if (a.D % 256 == 0)
     asp_bwd_stats_kernel<T, 256><<<dim3(a.D / 256, a.B), NTH, 0, s>>>(reinterpret_cast<const T*>(a.x), a.alpha, a.out,
                                                                       a.out_f32, a.dout, a.dout_f32,
