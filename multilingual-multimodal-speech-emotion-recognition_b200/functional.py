@@ -14,6 +14,12 @@ from . import _lib as L
 from ._params import FlatParams
 
 
+# The gradient buffers this binding hands to the library are zero-filled (FlatParams.new_grad_buffer), so the backward
+# descriptors say so and the library skips its own zeroing passes (memset nodes are the most expensive nodes of the
+# captured step graph).  Set to 0 to make the library zero its split-K / accumulated outputs itself (tests do).
+GRADS_ZEROED = 1
+
+
 def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     if t is None:
         return None
@@ -83,7 +89,7 @@ class AdapterFn(torch.autograd.Function):
         dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
         keep = []
         d = L.fill(L.AdapterDesc(), keep, dtype=L.dtype_code(x2.dtype), M=M, D=D, S=S,
-                   add_residual=int(ctx.add_residual), x=x2, w1=w1, w2=w2, h=h, dy=dy2, dh=dh, dx=dx, grads_zeroed=1,
+                   add_residual=int(ctx.add_residual), x=x2, w1=w1, w2=w2, h=h, dy=dy2, dh=dh, dx=dx, grads_zeroed=GRADS_ZEROED,
                    dw1=fp.view(g, "0.weight"), db1=fp.view(g, "0.bias"), dw2=fp.view(g, "2.weight"),
                    db2=fp.view(g, "2.bias"))
         L.call("ser_adapter_bwd", d, x2.device)
@@ -183,7 +189,7 @@ class CrossAttentionFn(torch.autograd.Function):
         )
         keep = []
         d = L.fill(L.XattnDesc(), keep, dtype=dt, B=B, Ta=Ta, Tt=Tt, D=D, S=S, H=H, a=a2, t=t2, a_mask=am, t_mask=tm,
-                   d_enh_a=ga, d_enh_t=gt, da=da, dt=dtt, ws=ws, ws_bytes=ws.numel(), grads_zeroed=1,
+                   d_enh_a=ga, d_enh_t=gt, da=da, dt=dtt, ws=ws, ws_bytes=ws.numel(), grads_zeroed=GRADS_ZEROED,
                    **CrossAttentionFn._weights(fp, wc), **sv, **grads, **_drop_fields(*ctx.drop))
         L.call("ser_xattn_bwd", d, dev)
         return (da.view(B, Ta, D) if ctx.needs_input_grad[0] else None,
@@ -237,7 +243,7 @@ class AttentiveStatsPoolingFn(torch.autograd.Function):
         keep = []
         d = L.fill(L.AspDesc(), keep, dtype=L.dtype_code(ty), B=B, T=T, D=D, Hd=Hd, x=x2, mask=m, w1=w1,
                    w2=fp.view(fp.flat, "attention.2.weight"), b2=fp.view(fp.flat, "attention.2.bias"), u=u,
-                   alpha=alpha, out=out, out_f32=f32, dout=dout, dout_f32=f32, dx=dx, dpre=dpre, dalpha=dalpha, grads_zeroed=1,
+                   alpha=alpha, out=out, out_f32=f32, dout=dout, dout_f32=f32, dx=dx, dpre=dpre, dalpha=dalpha, grads_zeroed=GRADS_ZEROED,
                    dw1=fp.view(g, "attention.0.weight"), db1=fp.view(g, "attention.0.bias"),
                    dw2=fp.view(g, "attention.2.weight"), db2=fp.view(g, "attention.2.bias"))
         L.call("ser_asp_bwd", d, dev)
@@ -305,7 +311,7 @@ class FusionFn(torch.autograd.Function):
             grads[f"dwg2{m}"] = fp.view(g, f"gate_{m}.2.weight"); grads[f"dbg2{m}"] = fp.view(g, f"gate_{m}.2.bias")
         keep = []
         d = L.fill(L.FusionDesc(), keep, dtype=dt, B=B, Din=Din, P=P, G=G, av=av2, tv=tv2,
-                   dfused=dfused.to(ty).contiguous(), dav=dav, dtv=dtv, ws=ws, ws_bytes=ws.numel(), grads_zeroed=1,
+                   dfused=dfused.to(ty).contiguous(), dav=dav, dtv=dtv, ws=ws, ws_bytes=ws.numel(), grads_zeroed=GRADS_ZEROED,
                    **FusionFn._weights(fp, wc), **sv, **grads, **_drop_fields(*ctx.drop))
         L.call("ser_fusion_bwd", d, dev)
         return (dav if ctx.needs_input_grad[0] else None, dtv if ctx.needs_input_grad[1] else None, None, None, None,
@@ -404,7 +410,7 @@ class ClassifierFn(torch.autograd.Function):
             dlogits = torch.zeros(B, C_, device=dev, dtype=torch.float32)
         keep = []
         d = L.fill(L.ClfDesc(), keep, dtype=dt, B=B, P=P, F=F_, C=C_, L=Ln, U=U, x=x2,
-                   dlogits=_f32c(dlogits), dunc=_f32c(dunc), dx=dx, ws=ws, ws_bytes=ws.numel(), grads_zeroed=1,
+                   dlogits=_f32c(dlogits), dunc=_f32c(dunc), dx=dx, ws=ws, ws_bytes=ws.numel(), grads_zeroed=GRADS_ZEROED,
                    **ClassifierFn._weights(fp, wc, Ln), **sv, **ClassifierFn._grads(fp, g, Ln),
                    **_drop_fields(*ctx.drop))
         L.call("ser_clf_bwd", d, dev)

@@ -221,6 +221,31 @@ def test_training_steps_fused_adamw_vs_torch_adamw():
     assert checked > 500_000
 
 
+def test_library_side_zeroing_path_matches():
+    """grads_zeroed = 0 (what a C-ABI caller without zero-filled gradient buffers passes): the library zeroes its
+    split-K / accumulated outputs itself and must produce the same gradients."""
+    import mmser_b200
+    from mmser_b200 import functional as SF
+    from oracle import synth
+    dev = _dev()
+    C = 4
+    w = synth.head_weights(C)
+    a, t, am, tm, labels = synth.make_inputs(6, 40, 12, C, seed=41)
+    args = (a.to(dev).bfloat16(), t.to(dev).bfloat16(), am.to(dev), tm.to(dev), labels.to(dev))
+    grads = []
+    try:
+        for flag in (1, 0):
+            SF.GRADS_ZEROED = flag
+            h = mmser_b200.FusionHead(C).to(dev); h.load_group_state(w); h.train()
+            h(*args)["loss"].backward()
+            grads.append({n: p.grad.detach().clone() for n, p in h.named_parameters() if p.grad is not None})
+    finally:
+        SF.GRADS_ZEROED = 1
+    gmax = max(g.abs().max().item() for g in grads[0].values())
+    for n, g1 in grads[0].items():
+        assert (g1 - grads[1][n]).abs().max().item() <= 1e-5 * gmax + 1e-4 * g1.abs().max().item(), n
+
+
 def test_precast_tracks_parameter_updates():
     """FusionHead casts the bf16 operand copies of all modules in one launch per forward (FlatParams.precast); an
     in-place parameter update between two forwards (what an optimizer step is) must be picked up."""
