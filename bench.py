@@ -225,7 +225,9 @@ def run_ours(args, wl):
     graphed = None
     if args.graph:
         try:
-            graphed = GraphedTrainStep(dp, devin["a"], devin["t"], devin["am"], devin["tm"], devin["labels"])
+            # the resident device tensors ARE the graph's static inputs: a replay is the step, no staging copy
+            graphed = GraphedTrainStep(dp, devin["a"], devin["t"], devin["am"], devin["tm"], devin["labels"],
+                                       static_inputs=True)
         except Exception as e:  # noqa: BLE001
             if world == 1:
                 raise
@@ -236,6 +238,8 @@ def run_ours(args, wl):
 
     def step(inp):
         if graphed is not None:
+            if inp is devin:
+                return graphed.replay()
             return graphed(inp["a"], inp["t"], inp["am"], inp["tm"], inp["labels"])
         return eager_step(inp)
 
