@@ -50,6 +50,11 @@ def _compile(src, verbose):
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     hdr = _headers_mtime()
+    # a shipped library that is newer than every source and header is current even when the object files did not
+    # travel with it (the build/ directory is not part of a snapshot)
+    newest = max([hdr] + [os.path.getmtime(os.path.join(CSRC, s)) for s in _sources()])
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
+        return LIB
     todo = []
     for src in _sources():
         obj = os.path.join(OBJ, src[:-3] + ".o")
