@@ -184,6 +184,7 @@ struct GemmArgs {
   // batched GEMM: `batch` independent problems, operand / output b at base + b * stride (elements)
   int batch = 1;
   long long strideA = 0, strideB = 0, strideC = 0, strideR = 0, strideG = 0;
+  long long strideBias = 0;      // batch stride of the bias vector (0: all problems share one bias)
   // optional by-product of dW-type GEMMs (a_trans): rowsum[m] = sum_k op(A)[m, k], i.e. the bias gradient when
   // A = dY stored [tokens, features].  Overwritten.  Batched: rowsum + b * strideRS.
   float* rowsum = nullptr; long long strideRS = 0;

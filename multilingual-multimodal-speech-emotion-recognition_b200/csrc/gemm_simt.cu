@@ -119,6 +119,8 @@ int gemm_simt_f32(const GemmArgs& a0, cudaStream_t stream) {
       a.A = reinterpret_cast<const float*>(a0.A) + b * a0.strideA;
       a.B = reinterpret_cast<const float*>(a0.B) + b * a0.strideB;
       a.C = reinterpret_cast<float*>(a0.C) + b * a0.strideC;
+      if (a0.bias) a.bias = a0.bias + b * a0.strideBias;
+      if (a0.rowsum) a.rowsum = a0.rowsum + b * a0.strideRS;
       if (a0.R) a.R = reinterpret_cast<const float*>(a0.R) + b * a0.strideR;
       if (a0.G) a.G = reinterpret_cast<const float*>(a0.G) + b * a0.strideG;
       SER_TRY(gemm_simt_f32(a, stream));

@@ -72,6 +72,7 @@ struct TcEpilogue {
   int act;
   int atomic;        // accumulate with TMA reduce-add (split-K or C +=); fp32 output only
   float alpha;
+  long long bias_stride;   // batch stride of bias (elements)
   float* rowsum;     // RS kernels: rowsum[m] += sum_k op(A)[m, k]  (pre-zeroed by the host side)
   long long rs_stride;   // batch stride of rowsum (elements)
 };
@@ -286,7 +287,7 @@ __device__ __forceinline__ void epilogue_tile(const TcEpilogue& ep, const CUtens
     float v[CW];
     const float alpha = ep.alpha;
     if (ep.bias != nullptr && lead_split) {
-      const float4* bp = reinterpret_cast<const float4*>(ep.bias + n0 + c * CW);
+      const float4* bp = reinterpret_cast<const float4*>(ep.bias + bz * ep.bias_stride + n0 + c * CW);
 #pragma unroll
       for (int j = 0; j < CW / 4; ++j) {
         const float4 b = __ldg(bp + j);
@@ -811,6 +812,8 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   ep.src = SRC_NONE;
   ep.rowsum = a.rowsum;
   ep.rs_stride = a.strideRS;
+  ep.bias_stride = a.strideBias;
+  SER_REQUIRE(a.strideBias % 4 == 0, "gemm_tc: the bias batch stride must be a multiple of 4 elements");
   if (a.rowsum != nullptr) {
     SER_REQUIRE(gemm_tc_rowsum_ok(a), "gemm_tc: rowsum rides on plain dW-type GEMMs only (both operands MN-major)");
     const int nb = a.batch > 1 ? a.batch : 1;

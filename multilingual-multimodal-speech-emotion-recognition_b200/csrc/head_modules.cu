@@ -32,9 +32,8 @@ struct Arena {
 inline size_t pad256(size_t b) { return (b + 255) & ~size_t(255); }
 
 // C[M,Nout] = act(A[M,Kin] W[Nout,Kin]^T + bias) (+ R)
-int linear_fwd(int dt, int M, int Nout, int Kin, const void* A, long long lda, const void* W, long long ldw,
-               const float* bias, void* C, long long ldc, int c_f32, int act, const void* R, long long ldr, int r_f32,
-               cudaStream_t s) {
+GemmArgs fwd_args(int dt, int M, int Nout, int Kin, const void* A, long long lda, const void* W, long long ldw,
+                  const float* bias, void* C, long long ldc, int c_f32, int act, const void* R, long long ldr, int r_f32) {
   GemmArgs g;
   g.dtype = dt; g.M = M; g.N = Nout; g.K = Kin;
   g.A = A; g.lda = lda; g.a_trans = 0;
@@ -42,13 +41,18 @@ int linear_fwd(int dt, int M, int Nout, int Kin, const void* A, long long lda, c
   g.C = C; g.ldc = ldc; g.c_f32 = c_f32;
   g.bias = bias; g.act = act;
   g.R = R; g.ldr = ldr; g.r_f32 = r_f32;
-  return gemm(g, s);
+  return g;
+}
+int linear_fwd(int dt, int M, int Nout, int Kin, const void* A, long long lda, const void* W, long long ldw,
+               const float* bias, void* C, long long ldc, int c_f32, int act, const void* R, long long ldr, int r_f32,
+               cudaStream_t s) {
+  return gemm(fwd_args(dt, M, Nout, Kin, A, lda, W, ldw, bias, C, ldc, c_f32, act, R, ldr, r_f32), s);
 }
 
 // dX[M,Kin] = gate'(dY[M,Nout] W[Nout,Kin]) (+ R)
-int linear_dgrad(int dt, int M, int Nout, int Kin, const void* dY, long long lddy, const void* W, long long ldw,
-                 void* dX, long long lddx, int dx_f32, const void* G, long long ldg, int g_f32, int gate_mode,
-                 const void* R, long long ldr, int r_f32, cudaStream_t s, float alpha = 1.f) {
+GemmArgs dgrad_args(int dt, int M, int Nout, int Kin, const void* dY, long long lddy, const void* W, long long ldw,
+                    void* dX, long long lddx, int dx_f32, const void* G, long long ldg, int g_f32, int gate_mode,
+                    const void* R, long long ldr, int r_f32, float alpha = 1.f) {
   GemmArgs g;
   g.alpha = alpha;
   g.dtype = dt; g.M = M; g.N = Kin; g.K = Nout;
@@ -57,13 +61,18 @@ int linear_dgrad(int dt, int M, int Nout, int Kin, const void* dY, long long ldd
   g.C = dX; g.ldc = lddx; g.c_f32 = dx_f32;
   g.G = G; g.ldg = ldg; g.g_f32 = g_f32; g.gate_mode = gate_mode;
   g.R = R; g.ldr = ldr; g.r_f32 = r_f32;
-  return gemm(g, s);
+  return g;
+}
+int linear_dgrad(int dt, int M, int Nout, int Kin, const void* dY, long long lddy, const void* W, long long ldw,
+                 void* dX, long long lddx, int dx_f32, const void* G, long long ldg, int g_f32, int gate_mode,
+                 const void* R, long long ldr, int r_f32, cudaStream_t s, float alpha = 1.f) {
+  return gemm(dgrad_args(dt, M, Nout, Kin, dY, lddy, W, ldw, dX, lddx, dx_f32, G, ldg, g_f32, gate_mode, R, ldr, r_f32, alpha), s);
 }
 
 // dW[Nout,Kin] (fp32) = dY[M,Nout]^T X[M,Kin];  db[Nout] (optional) = column sums of dY, produced by the same GEMM in
 // the bf16 tier (gemm_tc.cu row-sum MMAs) and by a colsum launch otherwise
-int linear_wgrad(int dt, int M, int Nout, int Kin, const void* dY, long long lddy, const void* X, long long ldx,
-                 float* dW, long long lddw, cudaStream_t s, float* db = nullptr, int zeroed = 0) {
+GemmArgs wgrad_args(int dt, int M, int Nout, int Kin, const void* dY, long long lddy, const void* X, long long ldx,
+                    float* dW, long long lddw, float* db = nullptr, int zeroed = 0) {
   GemmArgs g;
   g.rowsum = db;
   g.out_zeroed = zeroed;          // dW / db already hold zeros (descriptor field grads_zeroed): no memsets
@@ -71,7 +80,41 @@ int linear_wgrad(int dt, int M, int Nout, int Kin, const void* dY, long long ldd
   g.A = dY; g.lda = lddy; g.a_trans = 1;
   g.B = X; g.ldb = ldx; g.b_trans = 1;
   g.C = dW; g.ldc = lddw; g.c_f32 = 1;
-  return gemm(g, s);
+  return g;
+}
+int linear_wgrad(int dt, int M, int Nout, int Kin, const void* dY, long long lddy, const void* X, long long ldx,
+                 float* dW, long long lddw, cudaStream_t s, float* db = nullptr, int zeroed = 0) {
+  return gemm(wgrad_args(dt, M, Nout, Kin, dY, lddy, X, ldx, dW, lddw, db, zeroed), s);
+}
+
+// The same GEMM for the audio-side and the text-side operands of a module: ONE batched launch (batch = 2) when every
+// operand's text-side pointer sits at a positive, 8-element aligned distance from its audio-side twin (the Python
+// binding allocates the twin activations as halves of one tensor, and a module's parameters / gradients are laid out
+// symmetrically in its flat buffer); two launches otherwise.
+int gemm_pair(const GemmArgs& g0, const GemmArgs& g1, cudaStream_t s) {
+  auto dist = [](const void* p1, const void* p0, long long es, long long* out) -> bool {
+    if ((p0 == nullptr) != (p1 == nullptr)) return false;
+    if (p0 == nullptr) { *out = 0; return true; }
+    const long long bytes = reinterpret_cast<const char*>(p1) - reinterpret_cast<const char*>(p0);
+    if (bytes <= 0 || bytes % (8 * es) != 0) return false;
+    *out = bytes / es;
+    return true;
+  };
+  static const bool disabled = (getenv("SER_NO_PAIR_BATCH") != nullptr);      // A/B switch
+  const long long ea = g0.dtype == DT_F32 ? 4 : 2;
+  GemmArgs g = g0;
+  bool ok = !disabled && g0.M == g1.M && g0.N == g1.N && g0.K == g1.K && g0.lda == g1.lda && g0.ldb == g1.ldb &&
+            g0.ldc == g1.ldc && g0.ldr == g1.ldr && g0.ldg == g1.ldg && g0.batch <= 1 && g1.batch <= 1;
+  ok = ok && dist(g1.A, g0.A, ea, &g.strideA) && dist(g1.B, g0.B, ea, &g.strideB) &&
+       dist(g1.C, g0.C, g0.c_f32 ? 4 : 2, &g.strideC) && dist(g1.R, g0.R, g0.r_f32 ? 4 : 2, &g.strideR) &&
+       dist(g1.G, g0.G, g0.g_f32 ? 4 : 2, &g.strideG) && dist(g1.bias, g0.bias, 4, &g.strideBias) &&
+       dist(g1.rowsum, g0.rowsum, 4, &g.strideRS);
+  if (ok) {
+    g.batch = 2;
+    return gemm(g, s);
+  }
+  SER_TRY(gemm(g0, s));
+  return gemm(g1, s);
 }
 
 // zero a parameter-gradient region unless the caller handed in zero-filled buffers
@@ -541,14 +584,17 @@ int fusion_fwd(const ser_fusion_desc& d, cudaStream_t s) {
   const int B = d.B, P = d.P, G = d.G, Din = d.Din;
   SER_REQUIRE(B > 0 && d.av && d.tv && d.fused, "fusion_fwd: null tensor");
   const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);       // proj_a[2] / proj_t[2] (fusion.py:9,12)
-  SER_TRY(linear_fwd(dt, B, P, Din, d.av, Din, d.w1a, Din, d.b1a, d.ha, P, f, ACT_RELU, nullptr, 0, f, s));
-  if (drop.on()) SER_TRY(dropout_apply(d.ha, d.ha, nullptr, f, B, P, with_site(drop, DS_FUS_A), s));
-  SER_TRY(linear_fwd(dt, B, P, P, d.ha, P, d.w2a, P, d.b2a, d.pa, P, f, ACT_NONE, nullptr, 0, f, s));
-  SER_TRY(linear_fwd(dt, B, G, P, d.pa, P, d.wg1a, P, d.bg1a, d.ga, G, f, ACT_RELU, nullptr, 0, f, s));
-  SER_TRY(linear_fwd(dt, B, P, Din, d.tv, Din, d.w1t, Din, d.b1t, d.ht, P, f, ACT_RELU, nullptr, 0, f, s));
-  if (drop.on()) SER_TRY(dropout_apply(d.ht, d.ht, nullptr, f, B, P, with_site(drop, DS_FUS_T), s));
-  SER_TRY(linear_fwd(dt, B, P, P, d.ht, P, d.w2t, P, d.b2t, d.pt, P, f, ACT_NONE, nullptr, 0, f, s));
-  SER_TRY(linear_fwd(dt, B, G, P, d.pt, P, d.wg1t, P, d.bg1t, d.gt, G, f, ACT_RELU, nullptr, 0, f, s));
+  // the two modality branches run the same three GEMMs: each pair is one batched launch when the operands are twins
+  SER_TRY(gemm_pair(fwd_args(dt, B, P, Din, d.av, Din, d.w1a, Din, d.b1a, d.ha, P, f, ACT_RELU, nullptr, 0, f),
+                    fwd_args(dt, B, P, Din, d.tv, Din, d.w1t, Din, d.b1t, d.ht, P, f, ACT_RELU, nullptr, 0, f), s));
+  if (drop.on()) {
+    SER_TRY(dropout_apply(d.ha, d.ha, nullptr, f, B, P, with_site(drop, DS_FUS_A), s));
+    SER_TRY(dropout_apply(d.ht, d.ht, nullptr, f, B, P, with_site(drop, DS_FUS_T), s));
+  }
+  SER_TRY(gemm_pair(fwd_args(dt, B, P, P, d.ha, P, d.w2a, P, d.b2a, d.pa, P, f, ACT_NONE, nullptr, 0, f),
+                    fwd_args(dt, B, P, P, d.ht, P, d.w2t, P, d.b2t, d.pt, P, f, ACT_NONE, nullptr, 0, f), s));
+  SER_TRY(gemm_pair(fwd_args(dt, B, G, P, d.pa, P, d.wg1a, P, d.bg1a, d.ga, G, f, ACT_RELU, nullptr, 0, f),
+                    fwd_args(dt, B, G, P, d.pt, P, d.wg1t, P, d.bg1t, d.gt, G, f, ACT_RELU, nullptr, 0, f), s));
   return fusion_mix_fwd(to_mix(d), s);
 }
 
@@ -585,14 +631,23 @@ int fusion_bwd(const ser_fusion_desc& d, cudaStream_t s) {
       {dpa, dga, dha, d.pa, d.ha, d.av, d.wg1a, d.w2a, d.w1a, d.dwg1a, d.dbg1a, d.dw2a, d.db2a, d.dw1a, d.db1a, d.dav},
       {dpt, dgt, dht, d.pt, d.ht, d.tv, d.wg1t, d.w2t, d.w1t, d.dwg1t, d.dbg1t, d.dw2t, d.db2t, d.dw1t, d.db1t, d.dtv},
   };
-  for (const Side& sd : sides) {
-    SER_TRY(linear_wgrad(dt, B, G, P, sd.dg, G, sd.p, P, sd.dwg1, P, s, sd.dbg1, d.grads_zeroed));
-    SER_TRY(linear_dgrad(dt, B, G, P, sd.dg, G, sd.wg1, P, sd.dp, P, f, nullptr, 0, f, GATE_NONE, sd.dp, P, f, s));
-    SER_TRY(linear_wgrad(dt, B, P, P, sd.dp, P, sd.h, P, sd.dw2, P, s, sd.db2, d.grads_zeroed));
+  {
+    const Side& A_ = sides[0];
+    const Side& T_ = sides[1];
+    const int z = d.grads_zeroed;
+    SER_TRY(gemm_pair(wgrad_args(dt, B, G, P, A_.dg, G, A_.p, P, A_.dwg1, P, A_.dbg1, z),
+                      wgrad_args(dt, B, G, P, T_.dg, G, T_.p, P, T_.dwg1, P, T_.dbg1, z), s));
+    SER_TRY(gemm_pair(dgrad_args(dt, B, G, P, A_.dg, G, A_.wg1, P, A_.dp, P, f, nullptr, 0, f, GATE_NONE, A_.dp, P, f),
+                      dgrad_args(dt, B, G, P, T_.dg, G, T_.wg1, P, T_.dp, P, f, nullptr, 0, f, GATE_NONE, T_.dp, P, f), s));
+    SER_TRY(gemm_pair(wgrad_args(dt, B, P, P, A_.dp, P, A_.h, P, A_.dw2, P, A_.db2, z),
+                      wgrad_args(dt, B, P, P, T_.dp, P, T_.h, P, T_.dw2, P, T_.db2, z), s));
     // h is saved post-dropout: h > 0 exactly where the unit was kept and the ReLU open; the kept units carry 1/(1-p)
-    SER_TRY(linear_dgrad(dt, B, P, P, sd.dp, P, sd.w2, P, sd.dh, P, f, sd.h, P, f, GATE_RELU, nullptr, 0, f, s, hscale));
-    SER_TRY(linear_wgrad(dt, B, P, Din, sd.dh, P, sd.v, Din, sd.dw1, Din, s, sd.db1, d.grads_zeroed));
-    SER_TRY(linear_dgrad(dt, B, P, Din, sd.dh, P, sd.w1, Din, sd.dv, Din, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
+    SER_TRY(gemm_pair(dgrad_args(dt, B, P, P, A_.dp, P, A_.w2, P, A_.dh, P, f, A_.h, P, f, GATE_RELU, nullptr, 0, f, hscale),
+                      dgrad_args(dt, B, P, P, T_.dp, P, T_.w2, P, T_.dh, P, f, T_.h, P, f, GATE_RELU, nullptr, 0, f, hscale), s));
+    SER_TRY(gemm_pair(wgrad_args(dt, B, P, Din, A_.dh, P, A_.v, Din, A_.dw1, Din, A_.db1, z),
+                      wgrad_args(dt, B, P, Din, T_.dh, P, T_.v, Din, T_.dw1, Din, T_.db1, z), s));
+    SER_TRY(gemm_pair(dgrad_args(dt, B, P, Din, A_.dh, P, A_.w1, Din, A_.dv, Din, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f),
+                      dgrad_args(dt, B, P, Din, T_.dh, P, T_.w1, Din, T_.dv, Din, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f), s));
   }
   return SER_OK;
 }

@@ -217,7 +217,15 @@ class AttentiveStatsPoolingFn(torch.autograd.Function):
         u = torch.empty(B * T, Hd, device=dev, dtype=ty)
         e = torch.empty(B, T, device=dev, dtype=torch.float32)
         alpha = torch.empty(B, T, device=dev, dtype=torch.float32)
-        out = torch.empty(B, 2 * D, device=dev, dtype=ty)
+        # optional caller-provided [B, 2D] output storage (FusionHead hands the two pooling modules the halves of one
+        # tensor, so the fusion module sees its two inputs as twins and batches its GEMM pairs).  It travels outside
+        # autograd's view (a module attribute, not a Function input); detach() gives a tensor that merely shares it.
+        out_buf, fp._out_buffer = getattr(fp, "_out_buffer", None), None
+        if out_buf is not None and tuple(out_buf.shape) == (B, 2 * D) and out_buf.dtype == ty and out_buf.is_contiguous() \
+                and out_buf.device == dev:
+            out = out_buf.detach()
+        else:
+            out = torch.empty(B, 2 * D, device=dev, dtype=ty)
         keep = []
         d = L.fill(L.AspDesc(), keep, dtype=dt, B=B, T=T, D=D, Hd=Hd, x=x2, mask=m, w1=w1,
                    b1=fp.view(fp.flat, "attention.0.bias"), w2=fp.view(fp.flat, "attention.2.weight"),
@@ -278,7 +286,9 @@ class FusionFn(torch.autograd.Function):
         G = fp.params[fp.index["gate_a.0.weight"]].shape[0]
         dev, ty = av.device, av.dtype
         E = lambda *s: torch.empty(*s, device=dev, dtype=ty)   # noqa: E731
-        sv = dict(ha=E(B, P), ht=E(B, P), pa=E(B, P), pt=E(B, P), ga=E(B, G), gt=E(B, G),
+        # audio / text twins are the halves of one allocation: the library then runs each GEMM pair as one batched launch
+        hh, pp, gg = E(2, B, P), E(2, B, P), E(2, B, G)
+        sv = dict(ha=hh[0], ht=hh[1], pa=pp[0], pt=pp[1], ga=gg[0], gt=gg[1],
                   gates=torch.empty(B, 2, device=dev, dtype=torch.float32))
         fused = E(B, P)
         keep = []
@@ -300,7 +310,8 @@ class FusionFn(torch.autograd.Function):
         dev, ty = av2.device, av2.dtype
         dt = L.dtype_code(ty)
         g = fp.new_grad_buffer()
-        dav, dtv = torch.empty_like(av2), torch.empty_like(tv2)
+        dvv = torch.empty(2, B, Din, device=dev, dtype=ty)
+        dav, dtv = dvv[0], dvv[1]
         lib = L.load()
         ws = _ws(lib.ser_fusion_bwd_ws_bytes(dt, B, Din, P, G), dev)
         grads = {}

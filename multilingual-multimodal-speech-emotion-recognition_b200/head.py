@@ -78,6 +78,9 @@ class FusionHead(nn.Module):
         a_seq = self.adapter_a.residual_forward(a_hid)
         t_seq = self.adapter_t.residual_forward(t_hid)
         a_enh, t_enh = self.cross(a_seq, t_seq, a_mask, t_mask)
+        # the pooled vectors land in the two halves of one tensor (see AttentiveStatsPoolingFn / FusionFn)
+        pooled = torch.empty(2, a_enh.shape[0], 2 * a_enh.shape[2], device=a_enh.device, dtype=a_enh.dtype)
+        self.pool_a._out_buffer, self.pool_t._out_buffer = pooled[0], pooled[1]
         a_vec = self.pool_a(a_enh, a_mask)
         t_vec = self.pool_t(t_enh, t_mask)
         fused = self.fusion(a_vec, t_vec)

@@ -23,4 +23,5 @@ class AttentiveStatsPooling(nn.Module):
         self._flat = FlatParams([(n, p) for n, p in self.named_parameters()])
 
     def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        self._flat._out_buffer = self.__dict__.pop("_out_buffer", None)      # see AttentiveStatsPoolingFn.forward
         return AttentiveStatsPoolingFn.apply(x, mask, self._flat, *self._flat.params)
