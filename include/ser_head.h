@@ -107,6 +107,7 @@ int ser_colsum(const void* X, int x_f32, long long ld, int M, int N, float* out,
 #define SER_DS_CLF_IN 7      /* input_projection[3] [B, P] */
 #define SER_DS_CLF_OUT 8     /* output_projection[3] [B, F] */
 #define SER_DS_CLF_UNC 9     /* uncertainty_head[2] [B, U] */
+#define SER_DS_FEAT 10       /* utterance-feature fusion output [B*T, D] (ser_featfuse_*) */
 #define SER_DS_CLF_BLOCK0 16 /* residual block l: 16 + 2l = block[3] (after ReLU), 16 + 2l + 1 = block[5] */
 int ser_dropout_mask(const unsigned long long* seed, int site, float p, long long rows, int cols, float* out,
                      void* stream);
@@ -174,6 +175,35 @@ typedef struct ser_xattn_desc {
 size_t ser_xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H);
 int ser_xattn_fwd(const ser_xattn_desc* d, void* stream);
 int ser_xattn_bwd(const ser_xattn_desc* d, void* stream);
+
+/* ---- f1: per-utterance feature fusion between the adapter and cross attention ------------------
+ * (AudioEncoder.quality_fusion / conditioning_fusion / combined_fusion,
+ *  src/models/audio_encoder.py:29-52 applied :114-138, and TextEncoder.asr_fusion, text_encoder.py:26-30,60-73)
+ *   y[u,t,:] = dropout(relu(W [x[u,t,:] ; f[u,:]] + b)),   W [D, D+F] = nn.Linear(hid + F, hid).weight (fp32 master)
+ * The F features are constant over the frames of utterance u, so the concatenation is never built:
+ *   c[u,:] = W[:, D:] f[u] + b   (B x D, fp32),     y = dropout(relu(x W[:, :D]^T + c[u]))
+ * wx is the packed copy of W[:, :D] in the tier's dtype (nn.Linear's row pitch D+F is not TMA-addressable); forward
+ * writes it, backward reads it.  y is stored post-dropout, so y > 0 is both the ReLU gate and the keep mask.       */
+typedef struct ser_featfuse_desc {
+  int dtype; int B; int T; int D; int F;   /* utterances, frames per utterance, 768, 8 / 12 / 20   */
+  const void* x;                           /* [B*T, D] act                                         */
+  const float* feats;                      /* [B, F] fp32                                          */
+  const float* w; const float* b;          /* [D, D+F], [D] fp32 masters                           */
+  void* wx;                                /* [D, D] act: packed W[:, :D]                          */
+  float* c;                                /* [B, D] fp32 scratch (forward)                        */
+  void* y;                                 /* [B*T, D] act: output, saved for backward             */
+  float p_drop; const unsigned long long* drop_seed;   /* site SER_DS_FEAT, rows = B*T, cols = D   */
+  /* backward */
+  const void* dy;                          /* [B*T, D] act                                         */
+  void* dz;                                /* [B*T, D] act scratch                                 */
+  void* dx;                                /* [B*T, D] act or NULL (frozen-encoder input)          */
+  float* dc;                               /* [B, D] fp32 scratch                                  */
+  float* dwx;                              /* [D, D] fp32 scratch (zero-filled if grads_zeroed)    */
+  float* dw; float* db;                    /* [D, D+F], [D]: overwritten                           */
+  int grads_zeroed;
+} ser_featfuse_desc;
+int ser_featfuse_fwd(const ser_featfuse_desc* d, void* stream);
+int ser_featfuse_bwd(const ser_featfuse_desc* d, void* stream);
 
 /* ---- a3: AttentiveStatsPooling.forward  (src/models/pooling.py:15-28) -------------------------- */
 typedef struct ser_asp_desc {

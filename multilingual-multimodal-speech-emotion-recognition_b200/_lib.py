@@ -77,6 +77,7 @@ AspDesc = STRUCTS["ser_asp_desc"]
 FusionDesc = STRUCTS["ser_fusion_desc"]
 ClfDesc = STRUCTS["ser_clf_desc"]
 LossDesc = STRUCTS["ser_loss_desc"]
+FeatFuseDesc = STRUCTS["ser_featfuse_desc"]
 
 _lib = None
 
@@ -108,7 +109,7 @@ def load():
     lib.ser_layernorm_bwd.argtypes = [P, I, P, I, P, P, P, P, I, P, P, I, I, I, P]
     lib.ser_colsum.argtypes = [P, I, LL, I, I, P, P]
     for n, S in (("adapter", AdapterDesc), ("xattn", XattnDesc), ("asp", AspDesc), ("fusion", FusionDesc),
-                 ("clf", ClfDesc)):
+                 ("clf", ClfDesc), ("featfuse", FeatFuseDesc)):
         getattr(lib, f"ser_{n}_fwd").argtypes = [C.POINTER(S), P]
         getattr(lib, f"ser_{n}_bwd").argtypes = [C.POINTER(S), P]
     for n in ("ser_loss_fwd", "ser_loss_finalize", "ser_loss_bwd"):
@@ -129,7 +130,7 @@ def load():
     lib.ser_launch_count.restype = C.c_longlong
     lib.ser_prof_enable.argtypes = [I]
     lib.ser_prof_report.argtypes = [C.c_char_p, I]
-    for i, S in enumerate((GemmDesc, AdapterDesc, XattnDesc, AspDesc, FusionDesc, ClfDesc, LossDesc)):
+    for i, S in enumerate((GemmDesc, AdapterDesc, XattnDesc, AspDesc, FusionDesc, ClfDesc, LossDesc, FeatFuseDesc)):
         if lib.ser_desc_size(i) != C.sizeof(S):
             raise SerError(f"layout mismatch for {S.__name__}: C {lib.ser_desc_size(i)} vs ctypes {C.sizeof(S)}")
     _lib = lib

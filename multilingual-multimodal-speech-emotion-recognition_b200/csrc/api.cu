@@ -39,6 +39,7 @@ int ser_desc_size(int id) {
     case 4: return static_cast<int>(sizeof(ser_fusion_desc));
     case 5: return static_cast<int>(sizeof(ser_clf_desc));
     case 6: return static_cast<int>(sizeof(ser_loss_desc));
+    case 7: return static_cast<int>(sizeof(ser_featfuse_desc));
     default: return -1;
   }
 }
@@ -95,6 +96,9 @@ int ser_dropout_mask(const unsigned long long* seed, int site, float p, long lon
 
 int ser_adapter_fwd(const ser_adapter_desc* d, void* stream) { SER_NOT_NULL(d); return ser::adapter_fwd(*d, SER_STREAM(stream)); }
 int ser_adapter_bwd(const ser_adapter_desc* d, void* stream) { SER_NOT_NULL(d); return ser::adapter_bwd(*d, SER_STREAM(stream)); }
+
+int ser_featfuse_fwd(const ser_featfuse_desc* d, void* stream) { SER_NOT_NULL(d); return ser::featfuse_fwd(*d, SER_STREAM(stream)); }
+int ser_featfuse_bwd(const ser_featfuse_desc* d, void* stream) { SER_NOT_NULL(d); return ser::featfuse_bwd(*d, SER_STREAM(stream)); }
 
 size_t ser_xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H) {
   return ser::xattn_bwd_ws_bytes(dtype, B, Ta, Tt, D, S, H);

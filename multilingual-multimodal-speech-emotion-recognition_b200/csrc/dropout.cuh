@@ -20,7 +20,7 @@ namespace ser {
 enum : unsigned {
   DS_XA_PROB_A = SER_DS_XA_PROB_A, DS_XA_PROB_T = SER_DS_XA_PROB_T, DS_XA_RES_A = SER_DS_XA_RES_A, DS_XA_RES_T = SER_DS_XA_RES_T,
   DS_FUS_A = SER_DS_FUS_A, DS_FUS_T = SER_DS_FUS_T,
-  DS_CLF_IN = SER_DS_CLF_IN, DS_CLF_OUT = SER_DS_CLF_OUT, DS_CLF_UNC = SER_DS_CLF_UNC,
+  DS_FEAT = SER_DS_FEAT, DS_CLF_IN = SER_DS_CLF_IN, DS_CLF_OUT = SER_DS_CLF_OUT, DS_CLF_UNC = SER_DS_CLF_UNC,
   DS_CLF_BLOCK0 = SER_DS_CLF_BLOCK0,
 };
 

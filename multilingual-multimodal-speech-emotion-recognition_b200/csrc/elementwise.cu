@@ -645,8 +645,10 @@ int colsum_batched(const void* X, int x_f32, long long ld, int M, int N, float* 
   const int gx = ceil_div(N, 256);
   int gy = ceil_div(M, 64);
   if (gy > 8) gy = 8;
-  if (gy > 1)
-    for (int b = 0; b < batch; ++b) SER_CUDA_CHECK(cudaMemsetAsync(out + b * strideOut, 0, sizeof(float) * N, s));
+  if (gy > 1) {
+    if (strideOut == N) SER_TRY(zero_async(out, sizeof(float) * N * static_cast<size_t>(batch), s));   // contiguous: one launch
+    else for (int b = 0; b < batch; ++b) SER_CUDA_CHECK(cudaMemsetAsync(out + b * strideOut, 0, sizeof(float) * N, s));
+  }
   ProfScope prof("colsum_batched", 0.0, static_cast<double>(batch) * M * N * (x_f32 ? 4 : 2), s);
   colsum_vec_kernel<<<dim3(gx, gy, batch), 256, 0, s>>>(X, x_f32, ld, M, N, out, strideX, strideOut);
   SER_LAUNCH_CHECK();

@@ -6,6 +6,8 @@
 namespace ser {
 int adapter_fwd(const ser_adapter_desc& d, cudaStream_t s);
 int adapter_bwd(const ser_adapter_desc& d, cudaStream_t s);
+int featfuse_fwd(const ser_featfuse_desc& d, cudaStream_t s);
+int featfuse_bwd(const ser_featfuse_desc& d, cudaStream_t s);
 int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s);
 int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s);
 size_t xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H);

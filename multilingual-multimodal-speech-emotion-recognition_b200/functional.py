@@ -97,6 +97,59 @@ class AdapterFn(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------------
+# f1 per-utterance feature fusion
+# --------------------------------------------------------------------------------------------------
+class FeatureFusionFn(torch.autograd.Function):
+    """y[u,t] = dropout(relu(W [x[u,t] ; f[u]] + b)): the quality / conditioning / ASR feature fusion the encoders
+    apply between the adapter and cross attention (src/models/audio_encoder.py:29-52,114-138;
+    src/models/text_encoder.py:26-30,60-73).  x [B,T,D], feats [B,F] (constant over the frames of an utterance)."""
+
+    SITE = 10      # SER_DS_FEAT
+
+    @staticmethod
+    def forward(ctx, x, feats, fp: FlatParams, p_drop: float, seed, *params):
+        L.require_cuda(x, feats)
+        fp.ensure()
+        B, T, D = x.shape
+        F = feats.shape[-1]
+        w = fp.view(fp.flat, "0.weight")
+        if tuple(w.shape) != (D, D + F) or feats.shape[0] != B:
+            raise L.SerError(f"feature fusion: weight {tuple(w.shape)} does not fit x {tuple(x.shape)} / feats {tuple(feats.shape)}")
+        dev, ty = x.device, x.dtype
+        x2 = x.reshape(B * T, D).contiguous()
+        f2 = _f32c(feats.detach())
+        wx = torch.empty(D, D, device=dev, dtype=ty)
+        c = torch.empty(B, D, device=dev, dtype=torch.float32)
+        y = torch.empty(B * T, D, device=dev, dtype=ty)
+        keep = []
+        d = L.fill(L.FeatFuseDesc(), keep, dtype=L.dtype_code(ty), B=B, T=T, D=D, F=F, x=x2, feats=f2, w=w,
+                   b=fp.view(fp.flat, "0.bias"), wx=wx, c=c, y=y, **_drop_fields(p_drop, seed))
+        L.call("ser_featfuse_fwd", d, dev)
+        ctx.save_for_backward(x2, f2, wx, y)
+        ctx.fp, ctx.drop, ctx.shape = fp, (p_drop, seed), (B, T, D, F)
+        return y.view(B, T, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, f2, wx, y = ctx.saved_tensors
+        fp = ctx.fp
+        B, T, D, F = ctx.shape
+        dev, ty = x2.device, x2.dtype
+        dy2 = dy.reshape(B * T, D).to(ty).contiguous()
+        g = fp.new_grad_buffer()
+        dz = torch.empty_like(y)
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        dc = torch.empty(B, D, device=dev, dtype=torch.float32)
+        dwx = torch.zeros(D, D, device=dev, dtype=torch.float32)
+        keep = []
+        d = L.fill(L.FeatFuseDesc(), keep, dtype=L.dtype_code(ty), B=B, T=T, D=D, F=F, x=x2, feats=f2, wx=wx, y=y,
+                   dy=dy2, dz=dz, dx=dx, dc=dc, dwx=dwx, dw=fp.view(g, "0.weight"), db=fp.view(g, "0.bias"),
+                   grads_zeroed=GRADS_ZEROED, **_drop_fields(*ctx.drop))
+        L.call("ser_featfuse_bwd", d, dev)
+        return (dx.view(B, T, D) if dx is not None else None, None, None, None, None, *fp.grads_from(g))
+
+
+# --------------------------------------------------------------------------------------------------
 # a2 cross-modal attention
 # --------------------------------------------------------------------------------------------------
 class CrossAttentionFn(torch.autograd.Function):

@@ -2,6 +2,7 @@
 from .adapter import BottleneckAdapter
 from .classifier import AdvancedOpenMaxClassifier, ClassAnchorClustering, DeepClassifier, DeepResidualBlock
 from .cross_attention import CrossModalAttention
+from .feature_fusion import UtteranceFeatureFusion
 from .fusion import FusionLayer
 from .losses import ClassBalancedFocalLoss, LabelSmoothingCrossEntropy, SupConLoss
 from .pooling import AttentiveStatsPooling
@@ -10,5 +11,5 @@ from .prototypes import PrototypeMemory
 __all__ = [
     "BottleneckAdapter", "AdvancedOpenMaxClassifier", "ClassAnchorClustering", "DeepClassifier", "DeepResidualBlock",
     "CrossModalAttention", "FusionLayer", "ClassBalancedFocalLoss", "LabelSmoothingCrossEntropy", "SupConLoss",
-    "AttentiveStatsPooling", "PrototypeMemory",
+    "AttentiveStatsPooling", "PrototypeMemory", "UtteranceFeatureFusion",
 ]

@@ -59,6 +59,7 @@ class operand_rounding:
 #   cross.prob_a / cross.prob_t [B,H,Tq,Tk]   attention weights of attn_a / attn_t (functional.py multi_head_attention_forward)
 #   cross.res_a / cross.res_t   [B,T,D]       self.dropout(a_out) / self.dropout(t_out)   (cross_attention.py:43,51)
 #   fusion.a / fusion.t         [B,P]         proj_a[2] / proj_t[2]                        (fusion.py:9,12)
+#   feat.out                    [B,T,D]       combined_fusion[2] etc.                      (audio_encoder.py:33,42,51)
 #   clf.in [B,P]; clf.block{i}.hidden, clf.block{i}.out [B,P]; clf.out [B,F]; clf.unc [B,64]   (classifier.py:83,85,109,127,195)
 _DROPOUT_MASKS = None
 
@@ -123,6 +124,19 @@ def adapter(x: Tensor, w: W) -> Tensor:
     """seq = seq + Linear(768->256) . ReLU . Linear(256->768)(seq); keys '0.weight','0.bias','2.weight','2.bias'."""
     h = torch.relu(linear(x, w["0.weight"], w["0.bias"]))
     return x + linear(h, w["2.weight"], w["2.bias"])
+
+
+# --------------------------------------------------------------------------------------------------
+# f1  per-utterance feature fusion  (SURVEY.md 8(f) rank 1; src/models/audio_encoder.py:29-52 applied :114-138,
+#     src/models/text_encoder.py:26-30 applied :60-73)
+# --------------------------------------------------------------------------------------------------
+def utterance_feature_fusion(seq: Tensor, feats: Tensor, w: W) -> Tensor:
+    """seq [B,T,hid], feats [B,F]: per utterance the reference expands the feature vector over the frames, concatenates
+    it to the hidden states and applies Sequential(Linear(hid+F, hid), ReLU, Dropout): keys '0.weight', '0.bias';
+    dropout site 'feat.out' [B,T,hid]."""
+    B, T, _ = seq.shape
+    fused_input = torch.cat([seq, feats.unsqueeze(1).expand(B, T, feats.shape[-1])], dim=-1)
+    return _drop(torch.relu(linear(fused_input, w["0.weight"], w["0.bias"])), "feat.out")
 
 
 # --------------------------------------------------------------------------------------------------

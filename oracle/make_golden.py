@@ -219,6 +219,56 @@ def run_supcon_case(name, B, D, C, seed, temperature):
     print(f"{name}: loss={loss.item():.6f}")
 
 
+def reference_feature_fusion(attr: str, hid: int):
+    """Build `self.<attr>` exactly as the reference's source does: the nn.Sequential(...) constructor expression is cut
+    out of src/models/audio_encoder.py / text_encoder.py and evaluated with the given `hid` (the encoder classes
+    themselves cannot be imported: quality_gates needs librosa)."""
+    fname = "text_encoder.py" if attr == "asr_fusion" else "audio_encoder.py"
+    src = open(os.path.join(REF, "src", "models", fname)).read()
+    start = src.index(f"self.{attr} = nn.Sequential(") + len(f"self.{attr} = ")
+    depth, i = 0, start
+    while True:
+        depth += {"(": 1, ")": -1}.get(src[i], 0)
+        i += 1
+        if depth == 0 and src[i - 1] == ")":
+            break
+    return eval(src[start:i], {"nn": nn, "hid": hid})
+
+
+def run_feature_fusion_case(name, attr, F, B, T, hid, seed):
+    """The per-utterance fusion loop of AudioEncoder.forward (audio_encoder.py:114-138; text side text_encoder.py:68-73):
+    features expanded over the frames, concatenated, pushed through the Sequential -- eval mode and train mode (recorded
+    dropout masks), with gradients of sum(y * up)."""
+    mod = reference_feature_fusion(attr, hid)
+    w = synth.feature_fusion_weights(attr, F, seed=0, hidden=hid)
+    mod.load_state_dict(w)
+    g = torch.Generator().manual_seed(seed)
+    seq = torch.randn(B, T, hid, generator=g)
+    feats = torch.rand(B, F, generator=g) * 2.0 - 0.5
+    up = torch.randn(B, T, hid, generator=g)
+    out = {"config": dict(attr=attr, F=F, B=B, T=T, hid=hid, seed=seed)}
+    for mode in ("eval", "train"):
+        mod.train(mode == "train")
+        mod.zero_grad()
+        x = seq.clone().requires_grad_(True)
+        with RecordedDropout(seed + 1) as rec:
+            ys = []
+            for i in range(B):                      # one utterance at a time, as the reference does
+                base_seq = x[i]
+                all_features = feats[i].unsqueeze(0).expand(base_seq.size(0), -1)
+                fused_input = torch.cat([base_seq, all_features], dim=-1)
+                ys.append(mod(fused_input))
+            y = torch.stack(ys)
+        (y * up).sum().backward()
+        out[mode] = {"y": y.detach().clone(), "dx": x.grad.clone(), "dw": mod[0].weight.grad.clone(),
+                     "db": mod[0].bias.grad.clone()}
+        if mode == "train":
+            assert len(rec.calls) == B
+            out["train"]["mask"] = torch.stack([keep.to(torch.float32) / (1.0 - p) for _, p, keep in rec.calls])
+    torch.save(out, os.path.join(OUT, f"{name}.pt"))
+    print(f"{name}: |y_eval|={out['eval']['y'].abs().mean():.4f} kept={float((out['train']['mask'] > 0).float().mean()):.3f}")
+
+
 def run_eval_case(name, B, C, seed, views=5):
     """cfg5 semantics at small B: classifier eval path with fitted OpenMax + TTA mean + temperature + energy."""
     weights = synth.head_weights(C, 35, seed=0)
@@ -281,3 +331,5 @@ if __name__ == "__main__":
     run_eval_case("eval_cfg5_small", B=32, C=6, seed=1240)
     run_train_dropout_case("dropout_train_small", B=4, Ta=40, Tt=17, C=4, seed=1241)
     run_supcon_case("supcon_small", B=48, D=512, C=4, seed=1242, temperature=0.07)
+    run_feature_fusion_case("feature_fusion_combined", "combined_fusion", F=20, B=3, T=13, hid=128, seed=1243)
+    run_feature_fusion_case("feature_fusion_asr", "asr_fusion", F=8, B=2, T=7, hid=128, seed=1244)

@@ -56,6 +56,14 @@ def adapter_weights(tag: str, seed: int = 0) -> Dict[str, torch.Tensor]:
     }
 
 
+def feature_fusion_weights(tag: str, num_features: int, seed: int = 0, hidden: int = D) -> Dict[str, torch.Tensor]:
+    """nn.Sequential(nn.Linear(hid + F, hid), nn.ReLU(), nn.Dropout(0.1)): audio_encoder.py:29-52, text_encoder.py:26-30."""
+    return {
+        "0.weight": _fill(f"{tag}.0.weight", (hidden, hidden + num_features), "linear_w", seed),
+        "0.bias": _fill(f"{tag}.0.bias", (hidden,), "bias", seed),
+    }
+
+
 def cross_weights(seed: int = 0) -> Dict[str, torch.Tensor]:
     w = {}
     for n in ("q_a", "k_t", "v_t", "q_t", "k_a", "v_a"):

@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_layouts_match_the_compiled_library(lib):
     l = lib.load()
     for i, S in enumerate((lib.GemmDesc, lib.AdapterDesc, lib.XattnDesc, lib.AspDesc, lib.FusionDesc, lib.ClfDesc,
-                           lib.LossDesc)):
+                           lib.LossDesc, lib.FeatFuseDesc)):
         assert l.ser_desc_size(i) == ctypes.sizeof(S), S.__name__
 
 
@@ -103,6 +103,12 @@ def test_no_cpu_fallback(lib):
         mmser_b200.models.FusionLayer(1536, 1536, 512).eval()(torch.randn(2, 1536), torch.randn(2, 1536))
     with pytest.raises(lib.SerError):
         lib.gemm(torch.randn(4, 8), torch.randn(4, 8))
+    fuse = mmser_b200.models.UtteranceFeatureFusion(768, 20)
+    assert list(fuse.state_dict()) == ["0.weight", "0.bias"] and fuse[0].weight.shape == (768, 788)   # audio_encoder.py:47-52
+    with pytest.raises(lib.SerError):
+        fuse.eval()(torch.randn(2, 5, 768), torch.randn(2, 20))
+    with pytest.raises(lib.SerError):            # shape errors are reported before anything reaches the device
+        fuse(torch.randn(2, 5, 768), torch.randn(3, 20))
 
 
 def test_dropout_is_active_only_in_training_mode(lib):

@@ -360,6 +360,56 @@ def test_against_reference_golden(name, golden_dir):
     assert checked > 300
 
 
+@pytest.mark.parametrize("name", ["feature_fusion_combined", "feature_fusion_asr"])
+def test_feature_fusion_against_reference_golden(name, golden_dir):
+    """SURVEY 8(f) rank 1 against the fixture produced by the reference's own nn.Sequential, called the way the
+    reference calls it (one utterance at a time on the pre-concatenated [frames, hid + F] input, audio_encoder.py:131)
+    and batched; eval mode pins the values, train mode the dropout semantics (output is 0 or eval / (1 - p))."""
+    from mmser_b200 import models as M
+    from oracle import synth
+    dev = _dev()
+    gold = torch.load(os.path.join(golden_dir, f"{name}.pt"), weights_only=False)
+    cfg = gold["config"]
+    B, T, hid, F = cfg["B"], cfg["T"], cfg["hid"], cfg["F"]
+    g = torch.Generator().manual_seed(cfg["seed"])
+    seq = torch.randn(B, T, hid, generator=g)
+    feats = torch.rand(B, F, generator=g) * 2.0 - 0.5
+    up = torch.randn(B, T, hid, generator=g)
+    m = M.UtteranceFeatureFusion(hid, F).to(dev)
+    m.load_state_dict(synth.feature_fusion_weights(cfg["attr"], F, seed=0, hidden=hid))
+    rel = lambda x, y: (x.detach().double().cpu() - y.double()).abs().max().item() / (y.double().abs().max().item() + 1e-12)  # noqa: E731
+    m.eval()
+    x = seq.to(dev).requires_grad_(True)
+    ys = []
+    for i in range(B):
+        fused_input = torch.cat([x[i], feats[i].to(dev).unsqueeze(0).expand(T, -1)], dim=-1)
+        ys.append(m(fused_input))
+    y = torch.stack(ys)
+    (y * up.to(dev)).sum().backward()
+    ref = gold["eval"]
+    assert rel(y, ref["y"]) < 1e-4 and rel(x.grad, ref["dx"]) < 1e-4
+    assert rel(m[0].weight.grad, ref["dw"]) < 1e-4 and rel(m[0].bias.grad, ref["db"]) < 1e-4
+    # batched call = the per-utterance calls
+    m.zero_grad()
+    xb = seq.to(dev).requires_grad_(True)
+    yb = m(xb, feats.to(dev))
+    (yb * up.to(dev)).sum().backward()
+    assert rel(yb, ref["y"]) < 1e-4 and rel(xb.grad, ref["dx"]) < 1e-4 and rel(m[0].weight.grad, ref["dw"]) < 1e-4
+    # train mode: every element is dropped or the eval value / (1 - p); about p of them dropped
+    m.train()
+    yt = m(seq.to(dev), feats.to(dev)).cpu()
+    ye = ref["y"]
+    kept = yt != 0
+    assert (yt[kept] - ye[kept] / 0.9).abs().max() <= 1e-4 * ye.abs().max()
+    frac = 1.0 - kept[ye > 0].float().mean().item()
+    assert 0.05 < frac < 0.15, frac
+    # bf16 tier
+    m.eval()
+    y16 = m(seq.to(dev).bfloat16(), feats.to(dev))
+    assert y16.dtype == torch.bfloat16
+    assert (y16.float().cpu() - ye).norm() <= 2e-2 * ye.norm()
+
+
 def test_eval_path_against_reference_golden(golden_dir):
     """cfg5 semantics: fitted OpenMax, 5-view TTA mean, temperature sweep, softmax/argmax/energy."""
     import mmser_b200

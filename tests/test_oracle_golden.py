@@ -150,6 +150,30 @@ def test_oracle_matches_reference_supcon(golden_dir):
     assert rel(f.grad, gold["grad"]) < 10 * TOL
 
 
+@pytest.mark.parametrize("name", ["feature_fusion_combined", "feature_fusion_asr"])
+def test_oracle_matches_reference_feature_fusion(golden_dir, name):
+    """the per-utterance feature fusion of the encoders, eval and train (recorded masks)."""
+    gold = torch.load(os.path.join(golden_dir, f"{name}.pt"), weights_only=False)
+    cfg = gold["config"]
+    w = synth.feature_fusion_weights(cfg["attr"], cfg["F"], seed=0, hidden=cfg["hid"])
+    g = torch.Generator().manual_seed(cfg["seed"])
+    seq = torch.randn(cfg["B"], cfg["T"], cfg["hid"], generator=g)
+    feats = torch.rand(cfg["B"], cfg["F"], generator=g) * 2.0 - 0.5
+    up = torch.randn(cfg["B"], cfg["T"], cfg["hid"], generator=g)
+    for mode in ("eval", "train"):
+        ws = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+        x = seq.clone().requires_grad_(True)
+        masks = {"feat.out": gold["train"]["mask"]} if mode == "train" else {}
+        with O.dropout_masks(masks):
+            y = O.utterance_feature_fusion(x, feats, ws)
+        (y * up).sum().backward()
+        ref = gold[mode]
+        assert rel(y, ref["y"]) < TOL
+        assert rel(x.grad, ref["dx"]) < 10 * TOL
+        assert rel(ws["0.weight"].grad, ref["dw"]) < 10 * TOL
+        assert rel(ws["0.bias"].grad, ref["db"]) < 10 * TOL
+
+
 def test_quirks():
     """SURVEY.md 8(a) quirks the CUDA path must reproduce."""
     torch.manual_seed(0)
