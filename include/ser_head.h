@@ -346,6 +346,15 @@ int ser_eval_post(const float* logits_views, int V, int B, int C, float temperat
                   float* probs, long long* preds, float* energy, void* stream);
 int ser_temperature_sweep(const float* logits, const long long* labels, int B, int C, const float* temps, int nT,
                           float* err, void* stream);
+/* ser_late_ood : late-stage OOD scoring (src/models/dual_gate_ood.py:203-220 energy,
+ *   :280-312 diagonal-Mahalanobis prototype distances, :360-383 score mix), one launch, one warp per sample:
+ *   energy = -logsumexp(logits / *temperature);  dist[b,c] = sqrt(sum_d (f[b,d] - P[c,d])^2 / (cov[c,d] + 1e-8));
+ *   e_norm = sigmoid(-energy), d_norm = exp(-min_c dist), combined = softmax(mix)[0] e_norm + softmax(mix)[1] d_norm.
+ *   temperature [1], mix [2], prototypes / covariances [C,D] are DEVICE pointers (nn.Parameters: no host sync);
+ *   feats [B,D] fp32 or bf16; distances [B,C]; scores [B,5] = energy, min distance, e_norm, d_norm, combined.        */
+int ser_late_ood(const float* logits, const void* feats, int feats_f32, const float* prototypes,
+                 const float* covariances, const float* temperature, const float* mix, float* distances,
+                 float* scores, int B, int C, int D, void* stream);
 
 #ifdef __cplusplus
 }

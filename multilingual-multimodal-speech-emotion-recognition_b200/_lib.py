@@ -118,6 +118,7 @@ def load():
     lib.ser_fusion_bwd_ws_bytes.argtypes = [I] * 5
     lib.ser_clf_bwd_ws_bytes.argtypes = [I] * 6
     lib.ser_openmax_fwd.argtypes = [P, P, P, P, P, P, P, I, I, I, P]
+    lib.ser_late_ood.argtypes = [P, P, I, P, P, P, P, P, P, I, I, I, P]
     lib.ser_eval_post.argtypes = [P, I, I, I, F, P, P, P, P, P]
     lib.ser_temperature_sweep.argtypes = [P, P, I, I, P, I, P, P]
     lib.ser_supcon_ws_bytes.argtypes = [I, I]

@@ -160,6 +160,12 @@ int ser_grad_clip_coef(int n, const float* const* g, const long long* counts, fl
   return ser::grad_clip_coef(n, g, counts, max_norm, scratch, coef, norm_out, SER_STREAM(stream));
 }
 
+int ser_late_ood(const float* logits, const void* feats, int feats_f32, const float* prototypes,
+                 const float* covariances, const float* temperature, const float* mix, float* distances,
+                 float* scores, int B, int C, int D, void* stream) {
+  return ser::late_ood(logits, feats, feats_f32, prototypes, covariances, temperature, mix, distances, scores, B, C, D,
+                       SER_STREAM(stream));
+}
 int ser_openmax_fwd(const float* feats, const float* logits, const float* act_vecs, const float* w_alpha,
                     const float* w_beta, const float* w_tau, float* out, int B, int C, int F, void* stream) {
   return ser::openmax_fwd(feats, logits, act_vecs, w_alpha, w_beta, w_tau, out, B, C, F, SER_STREAM(stream));

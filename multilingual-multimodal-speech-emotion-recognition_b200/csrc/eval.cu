@@ -97,7 +97,56 @@ temp_sweep_kernel(const float* __restrict__ logits, const long long* __restrict_
   if (threadIdx.x == 0) atomicAdd(err + blockIdx.y, acc / static_cast<float>(B));
 }
 
+// late-stage OOD scores (src/models/dual_gate_ood.py:203-220, :280-312, :360-383): one warp per sample
+__global__ void __launch_bounds__(256)
+late_ood_kernel(const float* __restrict__ logits, const void* __restrict__ feats, int feats_f32,
+                const float* __restrict__ protos, const float* __restrict__ cov, const float* __restrict__ temperature,
+                const float* __restrict__ mix, float* __restrict__ distances, float* __restrict__ scores, int B, int C,
+                int D) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  // energy of the temperature-scaled logits: -logsumexp(logits / T)
+  const float z = (lane < C) ? logits[static_cast<size_t>(row) * C + lane] / temperature[0] : -INFINITY;
+  const float mx = warp_max(z);
+  const float se = warp_sum((lane < C) ? expf(z - mx) : 0.f);
+  const float energy = -(mx + logf(se));
+  // diagonal Mahalanobis distance to every class prototype
+  float min_d = INFINITY;
+  for (int c = 0; c < C; ++c) {
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float df = ld_dyn(feats, static_cast<size_t>(row) * D + d, feats_f32) - protos[static_cast<size_t>(c) * D + d];
+      s += df * df * (1.f / (cov[static_cast<size_t>(c) * D + d] + 1e-8f));
+    }
+    const float dist = sqrtf(warp_sum(s));
+    if (lane == 0) distances[static_cast<size_t>(row) * C + c] = dist;
+    min_d = fminf(min_d, dist);
+  }
+  if (lane == 0) {
+    const float e_norm = 1.f / (1.f + expf(energy));          // sigmoid(-energy)
+    const float d_norm = expf(-min_d);
+    const float m = fmaxf(mix[0], mix[1]);
+    const float w0 = expf(mix[0] - m), w1 = expf(mix[1] - m);
+    float* o = scores + static_cast<size_t>(row) * 5;
+    o[0] = energy; o[1] = min_d; o[2] = e_norm; o[3] = d_norm;
+    o[4] = (w0 * e_norm + w1 * d_norm) / (w0 + w1);
+  }
+}
+
 }  // namespace
+
+int late_ood(const float* logits, const void* feats, int feats_f32, const float* prototypes, const float* covariances,
+             const float* temperature, const float* mix, float* distances, float* scores, int B, int C, int D,
+             cudaStream_t s) {
+  SER_REQUIRE(B > 0 && C > 0 && C <= kMaxC && D > 0, "late_ood: bad shape (num_classes <= 32)");
+  SER_REQUIRE(logits && feats && prototypes && covariances && temperature && mix && distances && scores,
+              "late_ood: null tensor");
+  late_ood_kernel<<<ceil_div(B, 8), 256, 0, s>>>(logits, feats, feats_f32, prototypes, covariances, temperature, mix,
+                                                  distances, scores, B, C, D);
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
 
 int openmax_fwd(const float* feats, const float* logits, const float* act_vecs, const float* w_alpha,
                 const float* w_beta, const float* w_tau, float* out, int B, int C, int F, cudaStream_t s) {

@@ -215,6 +215,9 @@ int grad_clip_coef(int n, const float* const* g, const long long* counts, float 
 
 // ---- eval.cu -------------------------------------------------------------------------------------
 // OpenMax re-scaling (classifier.py:240-275): logits_out = logits * (u > 0.3 ? 1 - 0.8u : 1)
+int late_ood(const float* logits, const void* feats, int feats_f32, const float* prototypes, const float* covariances,
+             const float* temperature, const float* mix, float* distances, float* scores, int B, int C, int D,
+             cudaStream_t s);
 int openmax_fwd(const float* feats, const float* logits, const float* act_vecs, const float* w_alpha,
                 const float* w_beta, const float* w_tau, float* out, int B, int C, int F, cudaStream_t s);
 // TTA view mean + temperature + softmax / argmax / energy (eval.py:186-206, utils.py:12-14)

@@ -687,6 +687,30 @@ def openmax(features, logits, activation_vectors, weibull_alpha, weibull_beta, w
     return out
 
 
+def late_ood(logits, features, prototypes, covariances, temperature, mix):
+    """Late-stage OOD scores in one launch (src/models/dual_gate_ood.py:203-220, :280-312, :360-383).  logits [B,C],
+    features [B,D] (fp32 or bf16); prototypes / covariances [C,D], temperature [] and mix [2] are device tensors (the
+    reference's nn.Parameters, read by the kernel: no host sync).  Returns dict(energy [B], distances [B,C],
+    min_distance [B], energy_norm [B], distance_norm [B], combined [B])."""
+    L.require_cuda(logits, features)
+    lg = _f32c(logits)
+    f = features.contiguous() if features.dtype in (torch.float32, torch.bfloat16) else _f32c(features)
+    B, C_ = lg.shape
+    D = f.shape[1]
+    if tuple(prototypes.shape) != (C_, D) or tuple(covariances.shape) != (C_, D) or f.shape[0] != B:
+        raise L.SerError(f"late_ood: logits {tuple(lg.shape)}, features {tuple(f.shape)}, prototypes {tuple(prototypes.shape)}")
+    dev = lg.device
+    dist = torch.empty(B, C_, device=dev, dtype=torch.float32)
+    scores = torch.empty(B, 5, device=dev, dtype=torch.float32)
+    lib = L.load()
+    L.check(lib.ser_late_ood(lg.data_ptr(), f.data_ptr(), int(f.dtype == torch.float32), _f32c(prototypes.detach()).data_ptr(),
+                             _f32c(covariances.detach()).data_ptr(), _f32c(temperature.detach()).reshape(1).data_ptr(),
+                             _f32c(mix.detach()).data_ptr(), dist.data_ptr(), scores.data_ptr(), B, C_, D,
+                             L.stream_ptr(dev)), "ser_late_ood")
+    return dict(energy=scores[:, 0], distances=dist, min_distance=scores[:, 1], energy_norm=scores[:, 2],
+                distance_norm=scores[:, 3], combined=scores[:, 4])
+
+
 def eval_post(logits_views, temperature: float = 1.0):
     """[V,B,C] (or [B,C]) logits -> dict(mean_logits, probs, preds, energy): TTA mean, /T, softmax, argmax, energy."""
     L.require_cuda(logits_views)

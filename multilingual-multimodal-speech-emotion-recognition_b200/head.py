@@ -69,6 +69,62 @@ class FusionHead(nn.Module):
         for k in self.GROUPS:
             getattr(self, k).load_state_dict(weights[k], strict=True)
 
+    # ------------------------------------------------------------------------------------------------------------
+    # checkpoint wire format of the reference (src/train.py:247-262 writes, src/eval.py:109-123 reads): one dict of
+    # state_dicts keyed 'audio_encoder', 'text_encoder', 'cross', 'pool_a', 'pool_t', 'fusion', 'classifier',
+    # 'prototypes' (+ 'optimizer', 'scheduler', 'epoch', 'f1').  The head owns everything but the encoders; of those it
+    # owns the adapters, which live in the encoders' state_dicts under 'adapter.*' (audio_encoder.py:19, text_encoder.py:17).
+    # ------------------------------------------------------------------------------------------------------------
+    CKPT_GROUPS = ("cross", "pool_a", "pool_t", "fusion", "classifier", "prototypes")
+    CKPT_ADAPTERS = {"audio_encoder": "adapter_a", "text_encoder": "adapter_t"}
+
+    def checkpoint_state(self, encoders: Optional[Dict[str, Dict[str, torch.Tensor]]] = None, **extra) -> dict:
+        """The reference's checkpoint dict for this head.  `encoders` = {'audio_encoder': state_dict, 'text_encoder':
+        state_dict} of the (unchanged) encoder modules, whose 'adapter.*' entries are replaced by this head's adapters;
+        without it the two encoder entries hold the adapter keys only.  `extra`: optimizer / scheduler state_dicts,
+        epoch, f1 (train.py:258-261)."""
+        ckpt = {}
+        for enc, grp in self.CKPT_ADAPTERS.items():
+            sd = dict(encoders[enc]) if encoders and enc in encoders else {}
+            sd.update({f"adapter.{k}": v for k, v in getattr(self, grp).state_dict().items()})
+            ckpt[enc] = sd
+        for grp in self.CKPT_GROUPS:
+            ckpt[grp] = getattr(self, grp).state_dict()
+        ckpt.update(extra)
+        return ckpt
+
+    def load_checkpoint_state(self, ckpt: dict) -> None:
+        """Load a checkpoint written by the reference's train.py (or by checkpoint_state): strict on every group the head
+        owns; encoder keys other than 'adapter.*' are the encoders' business and are ignored here."""
+        for enc, grp in self.CKPT_ADAPTERS.items():
+            sd = {k[len("adapter."):]: v for k, v in ckpt[enc].items() if k.startswith("adapter.")}
+            getattr(self, grp).load_state_dict(sd, strict=True)
+        for grp in self.CKPT_GROUPS:
+            getattr(self, grp).load_state_dict(ckpt[grp], strict=True)
+
+    @torch.no_grad()
+    def fit_weibull_on(self, batches) -> int:
+        """The Weibull-fitting pass after the last epoch (src/train.py:204-245): run the validation batches
+        (a_hid, t_hid, a_mask, t_mask, labels) through the head in eval mode, collect the classifier's 256-d penultimate
+        features -- the fused stack hands them out (`classifier.last_features`), so the reference's hand-unrolled walk
+        over the classifier's children is not needed -- and call classifier.fit_weibull.  Returns the sample count."""
+        was_training = self.training
+        self.eval()
+        feats, labels = [], []
+        try:
+            for a_hid, t_hid, a_mask, t_mask, y in batches:
+                out = self.features(a_hid, t_hid, a_mask, t_mask)
+                self.classifier(out["fused"], use_openmax=False)
+                feats.append(self.classifier.last_features.float())
+                labels.append(y.to(feats[-1].device))
+        finally:
+            self.train(was_training)
+        if not feats:
+            return 0
+        f, y = torch.cat(feats), torch.cat(labels)
+        self.classifier.fit_weibull(f, y)
+        return int(y.numel())
+
     def features(self, a_hid, t_hid, a_mask=None, t_mask=None):
         # bf16 tier: the operand copies of all modules' weights in one launch instead of one per module
         flats = [getattr(self, g)._flat for g in self.GROUPS if hasattr(getattr(self, g), "_flat")]

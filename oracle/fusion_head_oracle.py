@@ -401,6 +401,21 @@ def energy_score(logits: Tensor) -> Tensor:
     return -torch.logsumexp(logits, dim=-1)
 
 
+def late_ood_scores(logits: Tensor, features: Tensor, w: W) -> Dict[str, Tensor]:
+    """Late-stage OOD scoring: src/models/dual_gate_ood.py:203-220 (energy of logits / T),
+    :280-312 (diagonal Mahalanobis distance to each class prototype, eps 1e-8 on the variances), :374-383 (sigmoid(-E),
+    exp(-min distance), softmax-weighted mix).  Keys as in LateStageOODDetector.state_dict()."""
+    energy = -torch.logsumexp(logits / w["energy_detector.temperature"], dim=-1)
+    P, cov = w["prototype_detector.prototypes"], w["prototype_detector.covariances"]
+    diff = features.unsqueeze(1) - P.unsqueeze(0)                              # [B,C,D]
+    dist = torch.sqrt((diff * diff * (1.0 / (cov + 1e-8)).unsqueeze(0)).sum(-1))
+    min_d = dist.min(dim=-1).values
+    e_norm, d_norm = torch.sigmoid(-energy), torch.exp(-min_d)
+    mix = torch.softmax(w["combination_weights"], dim=0)
+    return dict(energy=energy, distances=dist, min_distance=min_d, energy_norm=e_norm, distance_norm=d_norm,
+                combined=mix[0] * e_norm + mix[1] * d_norm)
+
+
 def tta_mean(logits_views: Tensor) -> Tensor:
     """mean of logits over augmentation views [V,B,C] -> [B,C]  (src/eval.py:186-190, README.md:152)."""
     return logits_views.mean(dim=0)

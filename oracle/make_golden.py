@@ -269,6 +269,39 @@ def run_feature_fusion_case(name, attr, F, B, T, hid, seed):
     print(f"{name}: |y_eval|={out['eval']['y'].abs().mean():.4f} kept={float((out['train']['mask'] > 0).float().mean()):.3f}")
 
 
+def run_late_ood_case(name, B, C, D, seed):
+    """LateStageOODDetector of the reference (src/models/dual_gate_ood.py:331-413) with fitted prototypes
+    (update_prototypes on a synthetic labelled set), a non-default temperature and mix: the detector's own components'
+    outputs plus the scalars of the LateOODResult."""
+    path = os.path.join(REF, "src", "models", "dual_gate_ood.py")
+    spec = importlib.util.spec_from_file_location("ref_dual_gate_ood", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = torch.Generator().manual_seed(seed)
+    det = mod.LateStageOODDetector(C, D)
+    centers = torch.randn(C, D, generator=g)
+    fit_labels = torch.randint(0, C, (40 * C,), generator=g)
+    fit_feats = centers[fit_labels] + 0.5 * torch.randn(40 * C, D, generator=g)
+    det.prototype_detector.update_prototypes(fit_feats, fit_labels)
+    with torch.no_grad():
+        det.energy_detector.temperature.fill_(1.7)
+        det.combination_weights.copy_(torch.tensor([0.9, 0.2]))
+    labels = torch.randint(0, C, (B,), generator=g)
+    feats = centers[labels] + 0.5 * torch.randn(B, D, generator=g)
+    feats[::5] += 0.3                           # a few samples off their class
+    logits = torch.randn(B, C, generator=g) * 3.0
+    with torch.no_grad():
+        energy, _ = det.energy_detector(logits)
+        dist, min_d = det.prototype_detector(feats)
+        res = det(logits, feats)
+    torch.save({"config": dict(B=B, C=C, D=D, seed=seed), "state": {k: v.clone() for k, v in det.state_dict().items()},
+                "logits": logits, "features": feats, "energy": energy, "distances": dist, "min_distance": min_d,
+                "result": dict(is_ood=res.is_ood, energy_score=res.energy_score, prototype_distance=res.prototype_distance,
+                               combined_score=res.combined_score, confidence_score=res.confidence_score,
+                               reason=res.reason.value)}, os.path.join(OUT, f"{name}.pt"))
+    print(f"{name}: combined={res.combined_score:.5f} min_dist={res.prototype_distance:.4f} reason={res.reason.value}")
+
+
 def run_eval_case(name, B, C, seed, views=5):
     """cfg5 semantics at small B: classifier eval path with fitted OpenMax + TTA mean + temperature + energy."""
     weights = synth.head_weights(C, 35, seed=0)
@@ -332,4 +365,5 @@ if __name__ == "__main__":
     run_train_dropout_case("dropout_train_small", B=4, Ta=40, Tt=17, C=4, seed=1241)
     run_supcon_case("supcon_small", B=48, D=512, C=4, seed=1242, temperature=0.07)
     run_feature_fusion_case("feature_fusion_combined", "combined_fusion", F=20, B=3, T=13, hid=128, seed=1243)
+    run_late_ood_case("late_ood_small", B=37, C=6, D=64, seed=1245)
     run_feature_fusion_case("feature_fusion_asr", "asr_fusion", F=8, B=2, T=7, hid=128, seed=1244)

@@ -81,6 +81,34 @@ def test_state_dict_keys_match_reference_goldens(lib, golden_dir):
     assert {"weibull_alpha", "weibull_beta", "weibull_tau", "activation_vectors"} <= clf_keys and len(clf_keys) == 304
 
 
+def test_reference_checkpoint_wire_format(lib):
+    """src/train.py:247-262 / src/eval.py:109-123: dict of state_dicts; the adapters travel inside the encoders' entries."""
+    import mmser_b200
+    from oracle import synth
+    C = 4
+    w = synth.head_weights(C, 2)
+    enc_a = {"encoder.layers.0.weight": torch.randn(3, 3), "pool.attention.0.weight": torch.randn(128, 768)}
+    enc_a.update({f"adapter.{k}": v for k, v in w["adapter_a"].items()})
+    enc_t = {f"adapter.{k}": v for k, v in w["adapter_t"].items()}
+    ckpt = {"audio_encoder": enc_a, "text_encoder": enc_t, "epoch": 3, "f1": 0.5}
+    ckpt.update({g: w[g] for g in ("cross", "pool_a", "pool_t", "fusion", "classifier", "prototypes")})
+    head = mmser_b200.FusionHead(C, num_layers=2)
+    head.load_checkpoint_state(ckpt)
+    out = head.checkpoint_state(encoders={"audio_encoder": enc_a}, epoch=4, f1=0.75)
+    assert set(out) == {"audio_encoder", "text_encoder", "cross", "pool_a", "pool_t", "fusion", "classifier",
+                        "prototypes", "epoch", "f1"}
+    assert out["epoch"] == 4 and set(out["audio_encoder"]) == set(enc_a) and set(out["text_encoder"]) == set(enc_t)
+    for grp in ("cross", "pool_a", "pool_t", "fusion", "classifier", "prototypes"):
+        assert set(out[grp]) == set(w[grp]), grp
+        for k in w[grp]:
+            assert torch.equal(out[grp][k].cpu(), w[grp][k]), (grp, k)
+    for k, v in w["adapter_a"].items():
+        assert torch.equal(out["audio_encoder"][f"adapter.{k}"], v)
+    bad = dict(ckpt, fusion={k: v for k, v in w["fusion"].items() if k != "gate_a.0.bias"})
+    with pytest.raises(RuntimeError):
+        head.load_checkpoint_state(bad)
+
+
 def test_flat_param_packing(lib):
     from mmser_b200._params import ALIGN, FlatParams
     import mmser_b200

@@ -448,6 +448,73 @@ def test_eval_path_against_reference_golden(golden_dir):
         assert rel(post["energy"], gold["energy"]) < 1e-3
 
 
+def test_weibull_fitting_pass_matches_hand_unrolled_walk():
+    """FusionHead.fit_weibull_on = the reference's after-last-epoch pass (src/train.py:204-245): same buffers as walking
+    the classifier's children one by one over the same validation batches."""
+    import mmser_b200
+    from oracle import synth
+    dev = _dev()
+    C = 4
+    head = mmser_b200.FusionHead(C, num_layers=35, dropout="reference").to(dev)
+    head.load_group_state(synth.head_weights(C, 35))
+    batches = []
+    for i in range(3):
+        a, t, am, tm, y = synth.make_inputs(6, 40, 12, C, 2000 + i, True)
+        batches.append((a.to(dev), t.to(dev), am.to(dev), tm.to(dev), y.to(dev)))
+    head.train()
+    n = head.fit_weibull_on(batches)
+    assert n == 18 and head.training
+    got = {k: getattr(head.classifier, k).clone() for k in synth.CLASSIFIER_BUFFERS}
+    head.eval()
+    feats = []
+    with torch.no_grad():
+        for a, t, am, tm, y in batches:
+            f = head.features(a, t, am, tm)["fused"]
+            dc = head.classifier.deep_classifier
+            for layer in dc.input_projection:
+                f = layer(f)
+            for blk, ln in zip(dc.residual_layers, dc.layer_norms):
+                f = blk(ln(f))
+            for i in range(4):
+                f = dc.output_projection[i](f)
+            feats.append(f)
+        head.classifier.fit_weibull(torch.cat(feats), torch.cat([b[4] for b in batches]))
+    for k in synth.CLASSIFIER_BUFFERS:
+        ref = getattr(head.classifier, k)
+        assert (got[k] - ref).abs().max() <= 1e-3 * ref.abs().max().clamp_min(1e-6), k
+    assert float(got["weibull_beta"].min()) > 0 and float(got["activation_vectors"].abs().max()) > 0
+
+
+def test_late_ood_against_reference_golden(golden_dir):
+    """LateStageOODDetector (one launch) against the fixture produced by the reference's detector."""
+    from mmser_b200 import models as M
+    from oracle import fusion_head_oracle as O
+    dev = _dev()
+    gold = torch.load(os.path.join(golden_dir, "late_ood_small.pt"), weights_only=False)
+    cfg = gold["config"]
+    det = M.LateStageOODDetector(cfg["C"], cfg["D"]).to(dev)
+    det.load_state_dict(gold["state"])
+    logits, feats = gold["logits"].to(dev), gold["features"].to(dev)
+    rel = lambda x, y: (x.detach().double().cpu() - y.double()).abs().max().item() / (y.double().abs().max().item() + 1e-12)  # noqa: E731
+    s = det.scores(logits, feats)
+    ref = O.late_ood_scores(gold["logits"].double(), gold["features"].double(), {k: v.double() for k, v in gold["state"].items()})
+    assert rel(s["energy"], gold["energy"]) < 1e-4 and rel(s["distances"], gold["distances"]) < 1e-4
+    assert rel(s["min_distance"], gold["min_distance"]) < 1e-4
+    for k in ("energy_norm", "distance_norm", "combined"):
+        assert rel(s[k], ref[k]) < 1e-4, k
+    assert torch.equal(s["is_ood"].cpu(), ref["combined"] < 0.5)
+    e, _ = det.energy_detector(logits)
+    d, md = det.prototype_detector(feats)
+    assert rel(e, gold["energy"]) < 1e-4 and rel(d, gold["distances"]) < 1e-4 and rel(md, gold["min_distance"]) < 1e-4
+    res, r = det(logits, feats), gold["result"]
+    assert res.is_ood == r["is_ood"] and res.reason.value == r["reason"]
+    for k in ("energy_score", "prototype_distance", "combined_score", "confidence_score"):
+        assert abs(getattr(res, k) - r[k]) <= 1e-4 * max(1e-3, abs(r[k])), k
+    # bf16 features (what the bf16 tier's classifier hands out): distances within the tier's tolerance
+    s16 = det.scores(logits, feats.bfloat16())
+    assert rel(s16["distances"], gold["distances"]) < 2e-2
+
+
 def test_children_callable_like_reference():
     """src/train.py:221-236 walks the classifier's children one by one; they must stay callable and agree with the
     fused forward."""

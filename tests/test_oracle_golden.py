@@ -174,6 +174,19 @@ def test_oracle_matches_reference_feature_fusion(golden_dir, name):
         assert rel(ws["0.bias"].grad, ref["db"]) < 10 * TOL
 
 
+def test_oracle_matches_reference_late_ood(golden_dir):
+    """energy + prototype-distance OOD scoring against the reference's LateStageOODDetector."""
+    gold = torch.load(os.path.join(golden_dir, "late_ood_small.pt"), weights_only=False)
+    s = O.late_ood_scores(gold["logits"], gold["features"], gold["state"])
+    assert rel(s["energy"], gold["energy"]) < TOL
+    assert rel(s["distances"], gold["distances"]) < TOL and rel(s["min_distance"], gold["min_distance"]) < TOL
+    r = gold["result"]
+    assert abs(s["energy"].mean().item() - r["energy_score"]) <= TOL * abs(r["energy_score"])
+    assert abs(s["min_distance"].mean().item() - r["prototype_distance"]) <= TOL * abs(r["prototype_distance"])
+    assert abs(s["combined"].mean().item() - r["combined_score"]) <= TOL * abs(r["combined_score"])
+    assert bool((s["combined"] < 0.5).any()) == r["is_ood"]
+
+
 def test_quirks():
     """SURVEY.md 8(a) quirks the CUDA path must reproduce."""
     torch.manual_seed(0)
