@@ -122,8 +122,16 @@ heads_bwd_w_kernel(const float* __restrict__ dlogits, const float* __restrict__ 
     for (int c = 0; c < 4; ++c) {
       const int k = threadIdx.x + c * 256;
       if (k < width) {
+        // the loads are independent of the FMA chain: a deep unroll keeps 16 of them in flight per thread (the kernel
+        // runs ~70 CTAs, so memory-level parallelism per thread is what hides the L2 latency)
         float a = acc[c];
-        for (int i = 0; i < nr; ++i) a = fmaf(sgr[i], x[static_cast<size_t>(r0 + i) * width + k], a);
+        const float* xp = x + static_cast<size_t>(r0) * width + k;
+        if (nr == 256) {
+#pragma unroll 16
+          for (int i = 0; i < 256; ++i) a = fmaf(sgr[i], xp[static_cast<size_t>(i) * width], a);
+        } else {
+          for (int i = 0; i < nr; ++i) a = fmaf(sgr[i], xp[static_cast<size_t>(i) * width], a);
+        }
         acc[c] = a;
       }
     }

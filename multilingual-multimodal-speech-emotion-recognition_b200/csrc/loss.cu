@@ -147,89 +147,108 @@ loss_rows_kernel(LossArgs a) {
 }
 
 __global__ void __launch_bounds__(256)
-loss_bwd_kernel(LossArgs a, const float* __restrict__ gscale) {
+loss_bwd_kernel(LossArgs a, const float* __restrict__ gscale, int stage_dprotos) {
+  // prototype gradients of the CTA's 8 samples are summed in shared memory first ([C, D] floats, when that fits): one
+  // global atomic per (class, column) and CTA instead of one per sample -- B-way contention on C*D addresses otherwise
+  extern __shared__ float sdp[];
+  const bool staged = stage_dprotos != 0 && a.dprotos != nullptr && a.emb != nullptr && a.demb != nullptr;
+  if (staged) {
+    for (int i = threadIdx.x; i < a.C * a.D; i += blockDim.x) sdp[i] = 0.f;
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= a.B) return;
-  const float gs = gscale ? gscale[0] : 1.f;
-  const float invB = 1.f / static_cast<float>(a.B_global);
-  const bool ok_ce = isfinite(a.sums[LS_CE] * invB);
-  const bool ok_focal = isfinite(a.sums[LS_FOCAL] * invB);
-  const bool ok_proto = isfinite(a.sums[LS_POS] * invB + a.margin - a.sums[LS_NEG] * invB);
-  long long yl = a.labels[row];
-  const int y = static_cast<int>(yl < 0 ? 0 : (yl > a.C - 1 ? a.C - 1 : yl));
-  const float* lg = a.logits + static_cast<size_t>(row) * a.C;
-  const RowSoftmax r = row_softmax(lg, a.C, lane);
-  if (a.dlogits != nullptr) {
-    float g = 0.f;
-    if (lane < a.C) {
-      const float delta = (lane == y) ? 1.f : 0.f;
-      if (ok_ce && a.w_ce != 0.f) {
-        const float q = (lane == y) ? 1.f - a.smoothing : a.smoothing / static_cast<float>(a.C - 1);
-        g += a.w_ce * (r.p - q);
+  if (row < a.B) {
+    const float gs = gscale ? gscale[0] : 1.f;
+    const float invB = 1.f / static_cast<float>(a.B_global);
+    const bool ok_ce = isfinite(a.sums[LS_CE] * invB);
+    const bool ok_focal = isfinite(a.sums[LS_FOCAL] * invB);
+    const bool ok_proto = isfinite(a.sums[LS_POS] * invB + a.margin - a.sums[LS_NEG] * invB);
+    long long yl = a.labels[row];
+    const int y = static_cast<int>(yl < 0 ? 0 : (yl > a.C - 1 ? a.C - 1 : yl));
+    const float* lg = a.logits + static_cast<size_t>(row) * a.C;
+    const RowSoftmax r = row_softmax(lg, a.C, lane);
+    if (a.dlogits != nullptr) {
+      float g = 0.f;
+      if (lane < a.C) {
+        const float delta = (lane == y) ? 1.f : 0.f;
+        if (ok_ce && a.w_ce != 0.f) {
+          const float q = (lane == y) ? 1.f - a.smoothing : a.smoothing / static_cast<float>(a.C - 1);
+          g += a.w_ce * (r.p - q);
+        }
       }
-    }
-    const float logp_y = __shfl_sync(0xffffffffu, r.logp, y);
-    const float p_y = __shfl_sync(0xffffffffu, r.p, y);
-    if (lane < a.C && ok_focal && a.w_focal != 0.f) {
-      const float delta = (lane == y) ? 1.f : 0.f;
-      const bool in_range = (p_y >= 1e-6f && p_y <= 1.f);
-      const float pt = fminf(fmaxf(p_y, 1e-6f), 1.f);
-      const float wy = a.class_w[y];
-      const float fw = powf(1.f - pt, a.gamma);
-      const float dfw_dpt = in_range ? -a.gamma * powf(1.f - pt, a.gamma - 1.f) : 0.f;
-      const float dpt_dz = p_y * (delta - r.p);
-      const float ce_w = -wy * logp_y;
-      const float dce_dz = wy * (r.p - delta);
-      g += a.w_focal * (dfw_dpt * dpt_dz * ce_w + fw * dce_dz);
-    }
-    if (lane < a.C) a.dlogits[static_cast<size_t>(row) * a.C + lane] = r.inside ? g * invB * gs : 0.f;
-  }
-  if (a.dunc != nullptr && lane == 0) {
-    const float mean_correct = a.sums[LS_CORRECT] * invB;
-    a.dunc[row] = a.w_unc * mean_correct * invB * gs;
-  }
-  if (a.emb != nullptr && a.demb != nullptr) {
-    const bool on = ok_proto && a.w_proto != 0.f;
-    // recompute distances
-    float mysq = 0.f;
-    for (int c = 0; c < a.C; ++c) {
-      float s = 0.f;
-      for (int d = lane; d < a.D; d += 32) {
-        float e = ld_dyn(a.emb, static_cast<size_t>(row) * a.D + d, a.emb_f32);
-        e = fminf(fmaxf(e, -10.f), 10.f);
-        const float df = e - a.protos[static_cast<size_t>(c) * a.D + d];
-        s = fmaf(df, df, s);
+      const float logp_y = __shfl_sync(0xffffffffu, r.logp, y);
+      const float p_y = __shfl_sync(0xffffffffu, r.p, y);
+      if (lane < a.C && ok_focal && a.w_focal != 0.f) {
+        const float delta = (lane == y) ? 1.f : 0.f;
+        const bool in_range = (p_y >= 1e-6f && p_y <= 1.f);
+        const float pt = fminf(fmaxf(p_y, 1e-6f), 1.f);
+        const float wy = a.class_w[y];
+        const float fw = powf(1.f - pt, a.gamma);
+        const float dfw_dpt = in_range ? -a.gamma * powf(1.f - pt, a.gamma - 1.f) : 0.f;
+        const float dpt_dz = p_y * (delta - r.p);
+        const float ce_w = -wy * logp_y;
+        const float dce_dz = wy * (r.p - delta);
+        g += a.w_focal * (dfw_dpt * dpt_dz * ce_w + fw * dce_dz);
       }
-      s = warp_sum(s);
-      if (lane == c) mysq = s;
+      if (lane < a.C) a.dlogits[static_cast<size_t>(row) * a.C + lane] = r.inside ? g * invB * gs : 0.f;
     }
-    const float pos = sqrtf(__shfl_sync(0xffffffffu, mysq, y));
-    const float dist = sqrtf(mysq + 1e-6f);
-    const float nd = (lane < a.C) ? ((lane == y) ? 10.f : fminf(dist, 10.f)) : INFINITY;
-    const float mn = -warp_max(-nd);
-    const float ex = (lane < a.C) ? expf(-(nd - mn)) : 0.f;
-    const float sm = ex / warp_sum(ex);                          // softmax(-nd)
-    // coefficient of (e - P_c) for each class: own class +1/pos ; others -s_c/d_c when d_c <= 10
-    float coef = 0.f;
-    if (lane < a.C) {
-      if (lane == y) coef = pos > 0.f ? 1.f / pos : 0.f;
-      else if (dist <= 10.f) coef = -sm / dist;
+    if (a.dunc != nullptr && lane == 0) {
+      const float mean_correct = a.sums[LS_CORRECT] * invB;
+      a.dunc[row] = a.w_unc * mean_correct * invB * gs;
     }
-    const float k = on ? a.w_proto * invB * gs : 0.f;
-    for (int d = lane; d < a.D; d += 32) {
-      const float raw = ld_dyn(a.emb, static_cast<size_t>(row) * a.D + d, a.emb_f32);
-      const float e = fminf(fmaxf(raw, -10.f), 10.f);
-      const bool inside = (raw >= -10.f && raw <= 10.f);
-      float ge = 0.f;
+    if (a.emb != nullptr && a.demb != nullptr) {
+      const bool on = ok_proto && a.w_proto != 0.f;
+      // recompute distances
+      float mysq = 0.f;
       for (int c = 0; c < a.C; ++c) {
-        const float cc = __shfl_sync(0xffffffffu, coef, c);
-        const float df = e - a.protos[static_cast<size_t>(c) * a.D + d];
-        const float t = cc * df * k;
-        ge += t;
-        if (a.dprotos != nullptr && t != 0.f) atomicAdd(a.dprotos + static_cast<size_t>(c) * a.D + d, -t);
+        float s = 0.f;
+        for (int d = lane; d < a.D; d += 32) {
+          float e = ld_dyn(a.emb, static_cast<size_t>(row) * a.D + d, a.emb_f32);
+          e = fminf(fmaxf(e, -10.f), 10.f);
+          const float df = e - a.protos[static_cast<size_t>(c) * a.D + d];
+          s = fmaf(df, df, s);
+        }
+        s = warp_sum(s);
+        if (lane == c) mysq = s;
       }
-      st_dyn(a.demb, static_cast<size_t>(row) * a.D + d, a.demb_f32, inside ? ge : 0.f);
+      const float pos = sqrtf(__shfl_sync(0xffffffffu, mysq, y));
+      const float dist = sqrtf(mysq + 1e-6f);
+      const float nd = (lane < a.C) ? ((lane == y) ? 10.f : fminf(dist, 10.f)) : INFINITY;
+      const float mn = -warp_max(-nd);
+      const float ex = (lane < a.C) ? expf(-(nd - mn)) : 0.f;
+      const float sm = ex / warp_sum(ex);                          // softmax(-nd)
+      // coefficient of (e - P_c) for each class: own class +1/pos ; others -s_c/d_c when d_c <= 10
+      float coef = 0.f;
+      if (lane < a.C) {
+        if (lane == y) coef = pos > 0.f ? 1.f / pos : 0.f;
+        else if (dist <= 10.f) coef = -sm / dist;
+      }
+      const float k = on ? a.w_proto * invB * gs : 0.f;
+      for (int d = lane; d < a.D; d += 32) {
+        const float raw = ld_dyn(a.emb, static_cast<size_t>(row) * a.D + d, a.emb_f32);
+        const float e = fminf(fmaxf(raw, -10.f), 10.f);
+        const bool inside = (raw >= -10.f && raw <= 10.f);
+        float ge = 0.f;
+        for (int c = 0; c < a.C; ++c) {
+          const float cc = __shfl_sync(0xffffffffu, coef, c);
+          const float df = e - a.protos[static_cast<size_t>(c) * a.D + d];
+          const float t = cc * df * k;
+          ge += t;
+          if (a.dprotos != nullptr && t != 0.f) {
+            if (staged) atomicAdd(&sdp[c * a.D + d], -t);
+            else atomicAdd(a.dprotos + static_cast<size_t>(c) * a.D + d, -t);
+          }
+        }
+        st_dyn(a.demb, static_cast<size_t>(row) * a.D + d, a.demb_f32, inside ? ge : 0.f);
+      }
+    }
+  }  // row < B
+  if (staged) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.C * a.D; i += blockDim.x) {
+      const float v = sdp[i];
+      if (v != 0.f) atomicAdd(a.dprotos + i, v);
     }
   }
 }
@@ -250,7 +269,9 @@ int loss_fwd(const LossArgs& a, cudaStream_t s) {
 int loss_bwd_scaled(const LossArgs& a, const float* gscale, cudaStream_t s) {
   SER_REQUIRE(a.C >= 2 && a.C <= kMaxC, "loss: 2 <= num_classes <= 32");
   ProfScope prof("loss_bwd", 0.0, 4.0 * a.B * (2.0 * a.C + (a.emb ? 2.0 * a.D : 0)), s);
-  loss_bwd_kernel<<<ceil_div(a.B, 8), 256, 0, s>>>(a, gscale);
+  const size_t stage_bytes = sizeof(float) * static_cast<size_t>(a.C) * (a.emb ? a.D : 0);
+  const int stage = (a.dprotos != nullptr && stage_bytes > 0 && stage_bytes <= 40 * 1024) ? 1 : 0;
+  loss_bwd_kernel<<<ceil_div(a.B, 8), 256, stage ? stage_bytes : 0, s>>>(a, gscale, stage);
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

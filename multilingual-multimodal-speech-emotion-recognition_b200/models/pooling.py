@@ -24,4 +24,7 @@ class AttentiveStatsPooling(nn.Module):
 
     def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         self._flat._out_buffer = self.__dict__.pop("_out_buffer", None)      # see AttentiveStatsPoolingFn.forward
-        return AttentiveStatsPoolingFn.apply(x, mask, self._flat, *self._flat.params)
+        try:
+            return AttentiveStatsPoolingFn.apply(x, mask, self._flat, *self._flat.params)
+        finally:
+            self._flat._out_buffer = None                                    # never outlives the call it was meant for
