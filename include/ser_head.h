@@ -43,7 +43,7 @@ const char* ser_last_error(void);
 int ser_sm_count(void);
 /* number of CUDA kernels this library has launched so far in this process                       */
 long long ser_launch_count(void);
-/* sizeof() of descriptor `id` as compiled (0 gemm, 1 adapter, 2 xattn, 3 asp, 4 fusion, 5 clf, 6 loss):
+/* sizeof() of descriptor `id` as compiled (0 gemm, 1 adapter, 2 xattn, 3 asp, 4 fusion, 5 clf, 6 loss, 7 featfuse):
  * lets a foreign-language binding verify its struct layout at load time                           */
 int ser_desc_size(int id);
 
