@@ -11,7 +11,7 @@ the gradients inside the update kernel -- no pass over the gradients just to sca
 from __future__ import annotations
 
 import ctypes as C
-from typing import Iterable, Optional
+from typing import Optional
 
 import torch
 
