@@ -174,6 +174,34 @@ def test_oracle_matches_reference_feature_fusion(golden_dir, name):
         assert rel(ws["0.bias"].grad, ref["db"]) < 10 * TOL
 
 
+def test_feature_fusion_decomposition_identity():
+    """The algebra csrc/featfuse.cu relies on: with features constant over the frames of an utterance, the concatenated
+    Linear equals a 768-wide GEMM plus a per-utterance bias c[u] = W[:, D:] f[u] + b, and the weight gradient splits into
+    dW[:, :D] = dz^T x, dW[:, D:] = (sum_t dz[u, t])^T f, db = sum dz.  Checked in fp64 against the oracle's
+    concatenation form."""
+    torch.manual_seed(3)
+    B, T, D, F = 3, 5, 16, 4
+    x = torch.randn(B, T, D, dtype=torch.float64)
+    f = torch.randn(B, F, dtype=torch.float64)
+    up = torch.randn(B, T, D, dtype=torch.float64)
+    w = {"0.weight": torch.randn(D, D + F, dtype=torch.float64).requires_grad_(True),
+         "0.bias": torch.randn(D, dtype=torch.float64).requires_grad_(True)}
+    xr = x.clone().requires_grad_(True)
+    y = O.utterance_feature_fusion(xr, f, w)
+    (y * up).sum().backward()
+    W, b = w["0.weight"].detach(), w["0.bias"].detach()
+    c = f @ W[:, D:].T + b                                     # [B, D]
+    z = x @ W[:, :D].T + c[:, None, :]
+    y2 = torch.relu(z)
+    dz = up * (y2 > 0)
+    assert torch.allclose(y2, y.detach(), atol=1e-12)
+    assert torch.allclose(dz @ W[:, :D], xr.grad, atol=1e-12)
+    dW = w["0.weight"].grad
+    assert torch.allclose(dz.reshape(-1, D).T @ x.reshape(-1, D), dW[:, :D], atol=1e-12)
+    assert torch.allclose(dz.sum(1).T @ f, dW[:, D:], atol=1e-12)
+    assert torch.allclose(dz.sum((0, 1)), w["0.bias"].grad, atol=1e-12)
+
+
 def test_oracle_matches_reference_late_ood(golden_dir):
     """energy + prototype-distance OOD scoring against the reference's LateStageOODDetector."""
     gold = torch.load(os.path.join(golden_dir, "late_ood_small.pt"), weights_only=False)
