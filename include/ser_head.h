@@ -173,6 +173,10 @@ typedef struct ser_xattn_desc {
   int grads_zeroed;
 } ser_xattn_desc;
 size_t ser_xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H);
+/* 1 when ser_xattn_fwd / _bwd take the folded path for this (dtype, D, S) PROVIDED fold_w / fold_b are given; the
+ * caller sizes its buffers from this answer: folded -> fold_w / fold_b required, qkv_* / o_* may be NULL;
+ * not folded -> qkv_* / o_* must be full size ([M,3S] / [M,S]), fold_* are ignored                       */
+int ser_xattn_folded(int dtype, int D, int S);
 int ser_xattn_fwd(const ser_xattn_desc* d, void* stream);
 int ser_xattn_bwd(const ser_xattn_desc* d, void* stream);
 
@@ -333,6 +337,15 @@ int ser_supcon_bwd(const void* f, int f_f32, const long long* labels, int B, int
 int ser_adamw_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
                     const long long* counts, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                     const float* gscale, void* stream);
+/* The same step behind torch.amp.GradScaler.step(optimizer) (src/train.py:88,169-177, the fp16 AMP branch): nothing
+ * is read back to the host.  found_inf [1] (device, may be NULL): non-zero -> the whole update is skipped;
+ * grad_scale [1] (device, may be NULL): gradients are divided by it (the scaler's loss scale when the caller did not
+ * unscale_ first); step_dev [1] (device, required): the bias-correction step count t >= 1 of THIS step as a float --
+ * the caller advances it with `step_dev += 1 - found_inf` before the call, so skipped steps do not count.            */
+int ser_adamw_multi_amp(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                        const long long* counts, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        const float* step_dev, const float* gscale, const float* grad_scale, const float* found_inf,
+                        void* stream);
 int ser_grad_clip_coef(int n, const float* const* g, const long long* counts, float max_norm, float* scratch,
                        float* coef, float* norm_out, void* stream);
 

@@ -115,6 +115,7 @@ def load():
     for n in ("ser_loss_fwd", "ser_loss_finalize", "ser_loss_bwd"):
         getattr(lib, n).argtypes = [C.POINTER(LossDesc), P]
     lib.ser_xattn_bwd_ws_bytes.argtypes = [I] * 7
+    lib.ser_xattn_folded.argtypes = [I] * 3
     lib.ser_fusion_bwd_ws_bytes.argtypes = [I] * 5
     lib.ser_clf_bwd_ws_bytes.argtypes = [I] * 6
     lib.ser_openmax_fwd.argtypes = [P, P, P, P, P, P, P, I, I, I, P]
@@ -125,6 +126,7 @@ def load():
     lib.ser_supcon_fwd.argtypes = [P, I, P, I, I, F, P, P, C.c_size_t, P]
     lib.ser_supcon_bwd.argtypes = [P, I, P, I, I, F, P, P, I, P, C.c_size_t, P]
     lib.ser_adamw_multi.argtypes = [I, P, P, P, P, P, F, F, F, F, F, I, P, P]
+    lib.ser_adamw_multi_amp.argtypes = [I, P, P, P, P, P, F, F, F, F, F, P, P, P, P, P]
     lib.ser_grad_clip_coef.argtypes = [I, P, P, F, P, P, P, P]
     lib.ser_desc_size.argtypes = [I]
     lib.ser_dropout_mask.argtypes = [P, I, F, LL, I, P, P]

@@ -130,16 +130,27 @@ class FlatParams:
         return torch.zeros(self.total, device=self.flat.device, dtype=torch.float32)
 
     @staticmethod
-    def shared_grad_arena(flats: Sequence["FlatParams"]) -> None:
+    def shared_grad_arena(flats: Sequence["FlatParams"], holder=None) -> None:
         """One zero-filled allocation (one fill kernel) for the gradient buffers of several modules' next backward:
         every module's new_grad_buffer() then returns its slice.  Inside a captured CUDA graph every node costs a few
-        microseconds of serialisation, so seven fills become one."""
+        microseconds of serialisation, so seven fills become one.
+        `holder` (any object): keep ONE arena on it and re-zero it every step instead of allocating -- `.grad` storage is
+        then the same for every step and every captured graph.  Only for callers that never accumulate gradients over
+        several backward passes (the previous step's `.grad` views alias the new ones)."""
         if not flats:
             return
         for fp in flats:
             fp.ensure()
         dev = flats[0].flat.device
-        arena = torch.zeros(sum(fp.total for fp in flats), device=dev, dtype=torch.float32)
+        n = sum(fp.total for fp in flats)
+        if holder is not None:
+            arena = holder.__dict__.get("_grad_arena")
+            if arena is None or arena.numel() != n or arena.device != dev:
+                arena = torch.empty(n, device=dev, dtype=torch.float32)
+                holder.__dict__["_grad_arena"] = arena
+            arena.zero_()
+        else:
+            arena = torch.zeros(n, device=dev, dtype=torch.float32)
         off = 0
         for fp in flats:
             fp._next_grad = arena[off:off + fp.total]

@@ -103,6 +103,7 @@ int ser_featfuse_bwd(const ser_featfuse_desc* d, void* stream) { SER_NOT_NULL(d)
 size_t ser_xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H) {
   return ser::xattn_bwd_ws_bytes(dtype, B, Ta, Tt, D, S, H);
 }
+int ser_xattn_folded(int dtype, int D, int S) { return ser::xattn_fold_enabled(dtype, D, S) ? 1 : 0; }
 int ser_xattn_fwd(const ser_xattn_desc* d, void* stream) { SER_NOT_NULL(d); return ser::xattn_fwd(*d, SER_STREAM(stream)); }
 int ser_xattn_bwd(const ser_xattn_desc* d, void* stream) { SER_NOT_NULL(d); return ser::xattn_bwd(*d, SER_STREAM(stream)); }
 
@@ -154,6 +155,14 @@ int ser_adamw_multi(int n, float* const* p, const float* const* g, float* const*
                     const long long* counts, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                     const float* gscale, void* stream) {
   return ser::adamw_multi(n, p, g, m, v, counts, lr, beta1, beta2, eps, weight_decay, step, gscale, SER_STREAM(stream));
+}
+int ser_adamw_multi_amp(int n, float* const* p, const float* const* g, float* const* m, float* const* v,
+                        const long long* counts, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        const float* step_dev, const float* gscale, const float* grad_scale, const float* found_inf,
+                        void* stream) {
+  if (step_dev == nullptr) { ser::set_last_error(__FILE__, __LINE__, "adamw_amp: step_dev is required"); return SER_ERR_ARG; }
+  return ser::adamw_multi(n, p, g, m, v, counts, lr, beta1, beta2, eps, weight_decay, 1, gscale, SER_STREAM(stream),
+                          grad_scale, found_inf, step_dev);
 }
 int ser_grad_clip_coef(int n, const float* const* g, const long long* counts, float max_norm, float* scratch,
                        float* coef, float* norm_out, void* stream) {

@@ -792,8 +792,12 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
   bool mc = (m_tiles % 2 == 0) && !(a.a_trans && !a.b_trans);
   if (mc_env == 0) mc = false;
   else if (mc_env != 1)
-    mc = mc && BN == 256 &&        // (N = 128 tiles, e.g. the pooling scorer 64000x128x768: 29.5 us paired vs 27.5 us single) static_cast<long long>(m_tiles) * n_tiles * splits * (a.batch > 1 ? a.batch : 1) >= device_sm_count() - 20 &&
-         kblocks / splits >= 8;      // short contractions (K = 256) are epilogue / HBM bound: 42.7 vs 33.6 us paired
+    // BN = 128 tiles stay single (the pooling scorer 64000x128x768: 29.5 us paired vs 27.5 us single); grids that
+    // cannot fill the SMs stay single (pairing halves the number of independent CTAs); short contractions (K = 256)
+    // are epilogue / HBM bound (42.7 vs 33.6 us paired)
+    mc = mc && BN == 256 &&
+         static_cast<long long>(m_tiles) * n_tiles * splits * (a.batch > 1 ? a.batch : 1) >= device_sm_count() - 20 &&
+         kblocks / splits >= 8;
   CUtensorMap tmA, tmB, tmC, tmS;
   if (!a.a_trans) SER_TRY(make_tmap(&tmA, a.A, 0, a.M, a.K, a.lda, BM, BK, a.batch, a.strideA));
   else            SER_TRY(make_tmap(&tmA, a.A, 0, a.K, a.M, a.lda, BK, 64, a.batch, a.strideA));

@@ -2,6 +2,7 @@
 // reference module (forward or backward) on the caller's stream.  The same code drives both tiers:
 // `dtype` picks the CUDA-core fp32 GEMM or the tcgen05 bf16 GEMM and the storage type of activations.
 #include "kernels.cuh"
+#include "modules.cuh"
 #include <stdlib.h>
 #include "../../include/ser_head.h"
 
@@ -208,10 +209,17 @@ int small_gemm2(int M, int N, int K, const void* A0, const void* A1, long long l
   return small_gemm(M, N, K, A1, lda, a_trans, B1, ldb, b_trans, C1, ldc, c_f32, s);
 }
 bool xattn_folded(const ser_xattn_desc& d) {
-  static const bool disabled = (getenv("SER_NO_FOLD") != nullptr);     // A/B switch
-  return !disabled && d.dtype == DT_BF16 && d.fold_w != nullptr && d.fold_b != nullptr && d.D == 3 * d.S;
+  return xattn_fold_enabled(d.dtype, d.D, d.S) && d.fold_w != nullptr && d.fold_b != nullptr;
 }
 }  // namespace
+
+// The ONE place that decides whether the Linear chains of cross attention are folded (exported as ser_xattn_folded):
+// the binding sizes qkv_* / o_* / fold_* from this answer, so the SER_NO_FOLD switch can never make the library write
+// full-size activations into placeholder buffers.
+bool xattn_fold_enabled(int dtype, int D, int S) {
+  static const bool disabled = (getenv("SER_NO_FOLD") != nullptr);     // A/B switch
+  return !disabled && dtype == DT_BF16 && D == 3 * S;
+}
 
 static int xattn_fwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
   const int dt = d.dtype, f = 0;
@@ -380,6 +388,7 @@ int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s) {
   const int Ma = d.B * d.Ta, Mt = d.B * d.Tt;
   SER_REQUIRE(S % d.H == 0, "xattn: shared_dim must be divisible by num_heads");   // cross_attention.py:12
   SER_REQUIRE(Ma > 0 && Mt > 0, "xattn: empty input");
+  SER_REQUIRE(d.qkv_a && d.qkv_t && d.o_a && d.o_t, "xattn: the unfolded path needs full-size qkv_* / o_* buffers");
   // outer projections, one packed GEMM per modality (cross_attention.py:38-40,46-48)
   SER_TRY(linear_fwd(dt, Ma, S3, D, d.a, D, d.wqkv_a, D, d.bqkv_a, d.qkv_a, S3, f, ACT_NONE, nullptr, 0, f, s));
   SER_TRY(linear_fwd(dt, Mt, S3, D, d.t, D, d.wqkv_t, D, d.bqkv_t, d.qkv_t, S3, f, ACT_NONE, nullptr, 0, f, s));
@@ -445,6 +454,7 @@ size_t xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H)
 
 int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
   if (xattn_folded(d)) return xattn_bwd_folded(d, s);
+  SER_REQUIRE(d.qkv_a && d.qkv_t && d.o_a && d.o_t, "xattn: the unfolded path needs full-size qkv_* / o_* buffers");
   const int dt = d.dtype, f = is_f32(dt);
   const int S = d.S, D = d.D, S3 = 3 * d.S;
   const int Ma = d.B * d.Ta, Mt = d.B * d.Tt;

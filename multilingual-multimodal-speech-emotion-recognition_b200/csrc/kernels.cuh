@@ -206,9 +206,11 @@ int supcon_bwd(const void* f, int f_f32, const long long* labels, int B, int D, 
 
 // ---- optim.cu ------------------------------------------------------------------------------------
 // torch.optim.AdamW step over n fp32 tensors (host pointer tables); gscale: optional device scalar multiplied into g
+// AMP (optional): grad_scale divides the gradients, found_inf != 0 skips the update, step_dev = device step count
 int adamw_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v, const long long* counts,
                 float lr, float beta1, float beta2, float eps, float weight_decay, int step, const float* gscale,
-                cudaStream_t s);
+                cudaStream_t s, const float* grad_scale = nullptr, const float* found_inf = nullptr,
+                const float* step_dev = nullptr);
 // coef[0] = min(1, max_norm / (||g||_2 + 1e-6)) over all tensors (clip_grad_norm_), norm_out[0] = ||g||_2 (optional)
 int grad_clip_coef(int n, const float* const* g, const long long* counts, float max_norm, float* scratch, float* coef,
                    float* norm_out, cudaStream_t s);

@@ -11,6 +11,7 @@ int featfuse_bwd(const ser_featfuse_desc& d, cudaStream_t s);
 int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s);
 int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s);
 size_t xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H);
+bool xattn_fold_enabled(int dtype, int D, int S);
 int asp_module_fwd(const ser_asp_desc& d, cudaStream_t s);
 int asp_module_bwd(const ser_asp_desc& d, cudaStream_t s);
 int fusion_fwd(const ser_fusion_desc& d, cudaStream_t s);

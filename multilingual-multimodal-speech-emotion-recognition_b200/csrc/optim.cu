@@ -22,11 +22,28 @@ struct AdamSegs {
   int n;
 };
 
+// AMP hand-off (torch.amp.GradScaler.step(optimizer), src/train.py:88,169-177): `found_inf` != 0 skips the whole update
+// (every thread returns before touching memory), `grad_scale` divides the gradients (the scaler's loss scale, when the
+// caller did not unscale_ first), and the bias-correction step count is then read from DEVICE memory (`step_dev`, kept
+// by the caller: incremented only on steps that were not skipped -- the host cannot know without a sync).
 __global__ void __launch_bounds__(256)
 adamw_multi_kernel(const AdamSegs s, float lr, float b1, float b2, float eps, float wd, float bc1, float rsqrt_bc2,
-                   const float* __restrict__ gscale) {
+                   const float* __restrict__ gscale, const float* __restrict__ grad_scale,
+                   const float* __restrict__ found_inf, const float* __restrict__ step_dev) {
+  if (found_inf != nullptr && found_inf[0] != 0.f) return;
   const long long total = s.end[s.n - 1];
-  const float gs = gscale != nullptr ? gscale[0] : 1.f;      // e.g. the clip coefficient of clip_grad_norm
+  float gs = gscale != nullptr ? gscale[0] : 1.f;      // e.g. the clip coefficient of clip_grad_norm
+  if (grad_scale != nullptr) gs /= grad_scale[0];
+  if (step_dev != nullptr) {                           // block-uniform: bias corrections from the device step count
+    __shared__ float sh_bc[2];
+    if (threadIdx.x == 0) {
+      const double t = static_cast<double>(step_dev[0]);
+      sh_bc[0] = static_cast<float>(1.0 - pow(static_cast<double>(b1), t));
+      sh_bc[1] = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(b2), t)));
+    }
+    __syncthreads();
+    bc1 = sh_bc[0]; rsqrt_bc2 = sh_bc[1];
+  }
   const float decay = 1.f - lr * wd, step = lr / bc1;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -106,7 +123,8 @@ __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm
 
 int adamw_multi(int n, float* const* p, const float* const* g, float* const* m, float* const* v, const long long* counts,
                 float lr, float beta1, float beta2, float eps, float weight_decay, int step, const float* gscale,
-                cudaStream_t s) {
+                cudaStream_t s, const float* grad_scale, const float* found_inf, const float* step_dev) {
+  if (step_dev != nullptr && step < 1) step = 1;       // the host value is a placeholder when the device count is used
   SER_REQUIRE(n >= 1 && step >= 1, "adamw: need at least one tensor and step >= 1");
   const float bc1 = 1.f - static_cast<float>(pow(static_cast<double>(beta1), step));
   const float bc2 = 1.f - static_cast<float>(pow(static_cast<double>(beta2), step));
@@ -126,7 +144,8 @@ int adamw_multi(int n, float* const* p, const float* const* g, float* const* m, 
     segs.n = cnt;
     ProfScope prof("adamw", 12.0 * elems, 28.0 * elems, s);
     const int blocks = static_cast<int>(min(static_cast<long long>(device_sm_count()) * 8, (acc + 255) / 256));
-    adamw_multi_kernel<<<blocks, 256, 0, s>>>(segs, lr, beta1, beta2, eps, weight_decay, bc1, rsqrt_bc2, gscale);
+    adamw_multi_kernel<<<blocks, 256, 0, s>>>(segs, lr, beta1, beta2, eps, weight_decay, bc1, rsqrt_bc2, gscale, grad_scale,
+                                              found_inf, step_dev);
     SER_LAUNCH_CHECK();
   }
   return SER_OK;

@@ -174,9 +174,10 @@ class CrossAttentionFn(torch.autograd.Function):
         E = lambda *s: torch.empty(*s, device=dev, dtype=ty)           # noqa: E731
         F = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)  # noqa: E731
         # bf16 tier: consecutive Linear layers are folded (csrc/fold.cu) -- the library then never touches the
-        # outer-projection outputs qkv_* nor the out_proj outputs o_*, and keeps the folded weights in fold_w / fold_b
-        folded = (ty == torch.bfloat16) and (D == 3 * S)
-        tok = (lambda M, n: E(1, 8)) if folded else (lambda M, n: E(M, n))
+        # outer-projection outputs qkv_* nor the out_proj outputs o_*, and keeps the folded weights in fold_w / fold_b.
+        # The LIBRARY decides (it also honours the SER_NO_FOLD A/B switch); the buffers are sized from its answer.
+        folded = bool(L.load().ser_xattn_folded(dt, D, S))
+        tok = (lambda M, n: None) if folded else (lambda M, n: E(M, n))
         sv = dict(qkv_a=tok(Ma, 3 * S), qkv_t=tok(Mt, 3 * S), p_a=E(Ma, 3 * S), p_t=E(Mt, 3 * S), ctx_a=E(Ma, S),
                   ctx_t=E(Mt, S), lse_a=F(B, num_heads, Ta), lse_t=F(B, num_heads, Tt), o_a=tok(Ma, S), o_t=tok(Mt, S),
                   z_a=E(Ma, D), z_t=E(Mt, D), stats_a=F(Ma, 2), stats_t=F(Mt, 2))
@@ -190,6 +191,7 @@ class CrossAttentionFn(torch.autograd.Function):
                    t_mask=tm, enh_a=enh_a, enh_t=enh_t, **w, **sv, **_drop_fields(p_drop, seed))
         L.call("ser_xattn_fwd", d, dev)
         ctx.drop = (p_drop, seed)
+        sv = {k: v for k, v in sv.items() if v is not None}
         ctx.save_for_backward(a2, t2, am, tm, wc, *sv.values())
         ctx.sv_keys = list(sv.keys())
         ctx.fp, ctx.dims = fp, (B, Ta, Tt, D, S, num_heads)

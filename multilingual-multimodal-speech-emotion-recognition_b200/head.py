@@ -48,6 +48,7 @@ class FusionHead(nn.Module):
         self.set_dropout(rates)
         self.prototypes = PrototypeMemory(num_labels, proj_dim)
         self.loss_weights = dict(w_ce=1.0, w_focal=0.3, w_unc=0.05, w_proto=0.01)   # train.py:156-168
+        self.persistent_grad_arena = False
 
     def set_dropout(self, dropout) -> Dict[str, float]:
         """Change the dropout rates of the built head (float, dict or 'reference'); returns the rates in effect."""
@@ -130,7 +131,9 @@ class FusionHead(nn.Module):
         flats = [getattr(self, g)._flat for g in self.GROUPS if hasattr(getattr(self, g), "_flat")]
         FlatParams.precast(flats, a_hid.dtype)
         if torch.is_grad_enabled():
-            FlatParams.shared_grad_arena(flats)       # one zero fill for all modules' gradient buffers of this step
+            # one zero fill for all modules' gradient buffers of this step (a fresh allocation per step, or -- when the
+            # caller guarantees zero_grad() before every step, as DataParallelHead.train_step does -- one persistent arena)
+            FlatParams.shared_grad_arena(flats, holder=self if self.persistent_grad_arena else None)
         a_seq = self.adapter_a.residual_forward(a_hid)
         t_seq = self.adapter_t.residual_forward(t_hid)
         a_enh, t_enh = self.cross(a_seq, t_seq, a_mask, t_mask)

@@ -71,13 +71,17 @@ class GradBucketReducer:
 
 
 def global_loss_cfg(labels: torch.Tensor, num_classes: int, group=None) -> Dict:
-    """loss_cfg entries that turn the per-shard loss kernels into the exact global-batch loss."""
+    """loss_cfg entries that turn the per-shard loss kernels into the exact global-batch loss.  Every rank must hold
+    the SAME number of samples: B_global = B * world is a host-side divisor baked into the loss descriptor (a
+    DistributedSampler with drop_last gives exactly that)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return dict(B_global=int(labels.shape[0]))        # the loss kernel counts the labels itself
     # scatter_add instead of torch.bincount: no device->host sync, CUDA-graph capturable
+    # (out-of-range labels -- an error in the reference, losses.py:45 -- are not counted, like the single-process kernel)
     counts = torch.zeros(num_classes, device=labels.device, dtype=torch.float32)
-    counts.scatter_add_(0, labels.clamp(0, num_classes - 1), torch.ones_like(labels, dtype=torch.float32))
+    inside = ((labels >= 0) & (labels < num_classes)).to(torch.float32)
+    counts.scatter_add_(0, labels.clamp(0, num_classes - 1), inside)
     # the label counts depend on the labels only: their all-reduce travels during the forward pass and is awaited by
     # the loss (HeadLossFn calls cfg["before_loss"] first)
     work = dist.all_reduce(counts, group=group, async_op=True)
@@ -105,6 +109,9 @@ class DataParallelHead:
             fp.grad_hook = self._make_hook(name)
             self._flats.append((name, fp))
         self._last: Dict[str, torch.Tensor] = {}
+        # train_step() always starts from zero_grad(set_to_none=True), so the gradient buffers of consecutive steps may
+        # share one persistent allocation (never true for callers that accumulate gradients over several backwards)
+        head.persistent_grad_arena = True
         if broadcast and dist.is_initialized() and dist.get_world_size(group) > 1:
             for _, fp in self._flats:
                 dist.broadcast(fp.flat, src=0, group=group)
@@ -148,8 +155,10 @@ class GraphedTrainStep:
 
         g = GraphedTrainStep(dp, a, t, a_mask, t_mask, labels)      # warm-up + capture
         out = g(a, t, a_mask, t_mask, labels)                        # copy into static inputs, replay
-    Outputs (loss terms, logits, ...) are static tensors overwritten by every replay; parameter .grad tensors
-    are static as well, so an optimizer step between replays works as usual.
+    Outputs (loss terms, logits, ...) are static tensors overwritten by every replay.  Parameter gradients are written
+    into the head's PERSISTENT gradient arena (allocated once, outside capture: DataParallelHead switches it on, see
+    FlatParams.shared_grad_arena), so every graph captured over one head (bench.py keeps one per input buffer) writes the
+    same `.grad` storage and an optimizer step between replays of any of them works as usual.
     """
 
     def __init__(self, dp: DataParallelHead, a, t, a_mask, t_mask, labels, warmup: int = 3,

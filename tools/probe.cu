@@ -1,7 +1,7 @@
 // Hardware probe (debug aid, not part of the C-ABI in include/ser_head.h): where does tcgen05.mma cta_group::1 with
 // M = 64 put accumulator row r in tensor memory?  D[r][n] = (r + 1) * (n + 1) is computed with one K = 16 MMA and
 // all 128 TMEM lanes x 64 columns are dumped, so the lane that holds row r can be read off the values.
-#include "common.cuh"
+#include "common.cuh"   // -I <package>/csrc (tools/probe_tmem_layout.py builds this file)
 #include <cuda.h>
 
 namespace ser {
