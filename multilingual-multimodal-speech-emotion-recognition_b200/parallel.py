@@ -29,6 +29,9 @@ class GradBucketReducer:
 
     def __init__(self, group=None):
         self.group = group
+        # False: every bucket is held back and all-reduced after the backward pass (one coalesced call) -- the
+        # "without overlap" arm of the benchmark
+        self.overlap = True
         self.pending: List = []
         self.deferred: List[torch.Tensor] = []
         self.order: List[str] = []          # bucket names in launch order (for tests / logging)
@@ -40,7 +43,7 @@ class GradBucketReducer:
         self.order.append(name)
         if not self._active():
             return
-        if flat.numel() * flat.element_size() < self.SMALL_BYTES:
+        if not self.overlap or flat.numel() * flat.element_size() < self.SMALL_BYTES:
             self.deferred.append(flat)
             return
         self.pending.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))

@@ -105,6 +105,9 @@ class Case:
         finally:
             self.inputs = saved
         fails, worst = [], 0.0
+        # every tensor's raw numbers, no noise term and no outlier set-aside: (kind, name, err(G,E), err(R,E), err(G,R),
+        # elements) in the tier's metric -- what tools/gpu_parity_report.py prints against the PLAIN tolerance
+        self.records = []
 
         def one(kind, name, got, ref_exact, ref_noise, floor=0.0, companion=None):
             nonlocal worst
@@ -112,6 +115,8 @@ class Case:
                 fails.append(f"{kind} {name}: missing")
                 return
             is_grad = kind != "out"
+            self.records.append((kind, name, _err(got, ref_exact, frob, floor), _err(ref_noise, ref_exact, frob, floor),
+                                 _err(got, ref_noise, frob, floor), int(ref_exact.numel())))
             e = _err(got, ref_exact, frob, floor, outliers=is_grad)
             n = _err(ref_noise, ref_exact, frob, floor, outliers=is_grad)
             if companion is not None:
@@ -151,6 +156,47 @@ class Case:
                         comp = (e_g[kw], r_g[kw])
                 one("grad", k, g_g.get(k), e_g[k], r_g[k], floor=1e-2 * scale, companion=comp)
         return fails, worst
+
+    def group_errors(self, dtype, device):
+        """Raw parity numbers per parameter group at any size, NO noise term, NO outlier set-aside, NO floors:
+        {group: dict(ge, re, gr, n)} with  ge = ||G - E|| / ||E||  over all gradient tensors of the group concatenated
+        (E = fp64 oracle, R = the oracle in the tier's reference arithmetic, G = CUDA), plus 'out/<name>' entries for the
+        forward quantities.  Used by the BASELINE-size parity tests."""
+        saved = self.inputs
+        if self.prepare is not None:
+            self.inputs = dict(saved, **self.prepare(device))
+        if dtype != torch.float32:
+            self.inputs = {k: (v.to(dtype).float() if (torch.is_tensor(v) and v.is_floating_point() and k not in ("a_mask", "t_mask", "mask"))
+                               else v) for k, v in self.inputs.items()}
+        try:
+            e_out, e_g, e_ig = self.run_oracle(torch.float64)
+            r_out, r_g, r_ig = self.run_oracle(torch.float32, None if dtype == torch.float32 else dtype)
+            g_out, g_g, g_ig = self.cuda(self.inputs, dtype, device)
+        finally:
+            self.inputs = saved
+
+        def rel(x, y):
+            return (x - y).norm().item() / max(y.norm().item(), 1e-30)
+
+        def cat(d, keys):
+            return torch.cat([d[k].detach().double().cpu().reshape(-1) for k in keys])
+
+        res = {}
+        for k in e_out:
+            if k in g_out:
+                E, R, G = (t[k].detach().double().cpu().reshape(-1) for t in (e_out, r_out, g_out))
+                res[f"out/{k}"] = dict(ge=rel(G, E), re=rel(R, E), gr=rel(G, R), n=int(E.numel()))
+        for k in e_ig:
+            E, R, G = (t[k].detach().double().cpu().reshape(-1) for t in (e_ig, r_ig, g_ig))
+            res[f"din/{k}"] = dict(ge=rel(G, E), re=rel(R, E), gr=rel(G, R), n=int(E.numel()))
+        for grp in sorted({k.split("/")[0] for k in e_g}):
+            keys = [k for k in e_g if k.startswith(grp + "/") and not k.endswith("anchor_clustering.temperature")
+                    and g_g.get(k) is not None]
+            if not keys:
+                continue
+            E, R, G = cat(e_g, keys), cat(r_g, keys), cat(g_g, keys)
+            res[f"grad/{grp}"] = dict(ge=rel(G, E), re=rel(R, E), gr=rel(G, R), n=int(E.numel()))
+        return res
 
 
 class _Null:
@@ -357,7 +403,7 @@ def classifier_case(B=64, C=4, L=35, p_drop=0.0):
         return {"logits": lg, "unc": un, "features": m.last_features}, _param_grads("classifier", m), {"x": x.grad}
 
     prep = (lambda dev: {"_masks": classifier_masks(dev, p_drop, B, L)}) if p_drop > 0 else None
-    return Case(("classifier" if B == 64 else f"classifier_B{B}") + ("_dropout" if p_drop > 0 else ""), ins, w, oracle,
+    return Case(("classifier" if B == 64 else f"classifier_b{B}") + ("_dropout" if p_drop > 0 else ""), ins, w, oracle,
                 cuda, grad_inputs=("x",), prepare=prep)
 
 
@@ -461,6 +507,9 @@ ALL_CASES = {
     "classifier": classifier_case,
     # two 128-row clusters of the fused stack kernel, the second one partially filled (rows >= B must stay inert)
     "classifier_b200": lambda: classifier_case(B=200, C=6),
+    # the M = 128 row-group path of the fused stack kernel (B > 1152; BASELINE cfg5 runs the classifier at B = 4096)
+    "classifier_b1280": lambda: classifier_case(B=1280),
+    "classifier_b4096": lambda: classifier_case(B=4096, C=6),
     "loss": loss_case,
     "supcon": supcon_case,
     "head_cfg1": lambda: head_case(4, 50, 16, 4, True),

@@ -206,6 +206,15 @@ def _dp_worker(rank, world, port, q):
     for n, b in bufs.items():                 # backward order: classifier first
         red.reduce_async(n, b)
     red.finish()
+    # the "without overlap" arm: nothing is launched before finish(), the result is the same
+    red2 = GradBucketReducer()
+    red2.overlap = False
+    late = {n: torch.full((2_000_000,), float(rank + 1)) for n in ("big",)}
+    for n, b in late.items():
+        red2.reduce_async(n, b)
+    assert not red2.pending and len(red2.deferred) == 1
+    red2.finish()
+    assert float(late["big"][0]) == 3.0 and float(late["big"][-1]) == 3.0
     labels = torch.tensor([0, 1, 1, 3]) if rank == 0 else torch.tensor([2, 2, 1, 0])
     cfg = global_loss_cfg(labels, 4)
     sums = torch.tensor([1.0, 2.0]) * (rank + 1)

@@ -9,7 +9,7 @@ import torch.distributed as dist
 sys.path.insert(0, ".")
 import mmser_b200  # noqa: E402
 from mmser_b200.parallel import DataParallelHead  # noqa: E402
-from oracle import synth  # noqa: E402
+from mmser_b200 import synth  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -19,9 +19,10 @@ C, Bs, Ta, Tt = 4, 6, 40, 12
 w = synth.head_weights(C)
 shards = [synth.make_inputs(Bs, Ta, Tt, C, seed=100 + r) for r in range(world)]
 worst = 0.0
-for dtype, tol in ((torch.float32, 2e-4), (torch.bfloat16, 6e-2)):
+for dtype, tol, overlap in ((torch.float32, 2e-4, True), (torch.bfloat16, 6e-2, True), (torch.float32, 2e-4, False)):
     head = mmser_b200.FusionHead(C).to(dev); head.load_group_state(w); head.train()
     dp = DataParallelHead(head)
+    dp.reducer.overlap = overlap            # False: every bucket all-reduced after the backward pass
     a, t, am, tm, lab = shards[rank]
     out = dp.train_step(a.to(dev).to(dtype), t.to(dev).to(dtype), am.to(dev), tm.to(dev), lab.to(dev))
     torch.cuda.synchronize()
@@ -45,7 +46,7 @@ for dtype, tol in ((torch.float32, 2e-4), (torch.bfloat16, 6e-2)):
             e = (grads[n].double() - p.grad.double()).norm().item() / max(p.grad.double().norm().item(), 1e-4 * gmax)
             worst = max(worst, e)
             assert e <= tol, f"{dtype} {n}: rel err {e:.3e}"
-        print(f"dp_check {dtype}: world {world}, loss {float(out['loss']):.6f}, worst gradient rel err {worst:.2e} (tol {tol})", flush=True)
+        print(f"dp_check {dtype} overlap={overlap}: world {world}, loss {float(out['loss']):.6f}, worst gradient rel err {worst:.2e} (tol {tol})", flush=True)
     dist.barrier()
 torch.cuda.synchronize()
 os._exit(0)
