@@ -194,8 +194,7 @@ class EagerHead(nn.Module):
         e = emb.clamp(-10.0, 10.0)
         pos = (e - protos[y]).norm(dim=1).mean()
         d = torch.sqrt(((e.unsqueeze(1) - protos.unsqueeze(0)) ** 2).sum(dim=2) + 1e-6)
-        own = torch.zeros_like(d, dtype=torch.bool)
-        own[torch.arange(e.shape[0], device=e.device), y] = True
+        own = torch.zeros_like(d, dtype=torch.bool).scatter_(1, y.unsqueeze(1), True)
         d = d.masked_fill(own, float("inf")).clamp(max=10.0)      # the own-class entry stays in the soft-min as 10.0
         neg = (-torch.logsumexp(-d, dim=1)).mean()
         return self._finite_or_zero(pos + margin - neg)
