@@ -43,7 +43,7 @@ const char* ser_last_error(void);
 int ser_sm_count(void);
 /* number of CUDA kernels this library has launched so far in this process                       */
 long long ser_launch_count(void);
-/* sizeof() of descriptor `id` as compiled (0 gemm, 1 adapter, 2 xattn, 3 asp, 4 fusion, 5 clf, 6 loss, 7 featfuse):
+/* sizeof() of descriptor `id` as compiled (0 gemm, 1 adapter, 2 xattn, 3 asp, 4 fusion, 5 clf, 6 loss, 7 featfuse, 8 attn):
  * lets a foreign-language binding verify its struct layout at load time                           */
 int ser_desc_size(int id);
 
@@ -179,6 +179,30 @@ size_t ser_xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, in
 int ser_xattn_folded(int dtype, int D, int S);
 int ser_xattn_fwd(const ser_xattn_desc* d, void* stream);
 int ser_xattn_bwd(const ser_xattn_desc* d, void* stream);
+
+/* ---- attention core of a2 (building block, like ser_gemm; also what the unit tests and micro-benchmarks call) ------
+ * Masked multi-head attention of nn.MultiheadAttention's math path (src/models/cross_attention.py:18,25,41,49;
+ * torch/nn/functional.py:6609-6645) on already projected, head-packed operands: head h = columns [h*dh, (h+1)*dh).
+ *   Q [B*Tq, H*dh] (row pitch ldq), K / V [B*Tk, H*dh]; kmask [B,Tk] float, 0 = padded key, or NULL;
+ *   O [B*Tq, H*dh]; lse [B,H,Tq] fp32 = log-sum-exp of the scaled masked scores (saved for the backward);
+ *   dropout on the attention weights: site rows = (b*H + h)*Tq + i, cols = Tk.
+ * Backward: dQ / dK / dV from dO (delta [B,H,Tq] fp32 scratch).  impl: 0 = choose, 1 = mma.sync kernels,
+ * 2 = tcgen05 / TMEM / TMA kernels (bf16 tier, dh = 32, even H; SER_ERR_UNSUPPORTED otherwise).                  */
+typedef struct ser_attn_desc {
+  int dtype; int B, H, Tq, Tk, dh;
+  const void* Q; long long ldq; const void* K; long long ldk; const void* V; long long ldv;
+  const float* kmask;
+  void* O; long long ldo; float* lse;
+  float scale;                             /* 1 / sqrt(dh) in the reference                        */
+  float p_drop; const unsigned long long* drop_seed; int drop_site;
+  int impl;
+  /* backward */
+  const void* dO; long long lddo;
+  void* dQ; long long lddq; void* dK; long long lddk; void* dV; long long lddv;
+  float* delta;
+} ser_attn_desc;
+int ser_attention_fwd(const ser_attn_desc* d, void* stream);
+int ser_attention_bwd(const ser_attn_desc* d, void* stream);
 
 /* ---- f1: per-utterance feature fusion between the adapter and cross attention ------------------
  * (AudioEncoder.quality_fusion / conditioning_fusion / combined_fusion,

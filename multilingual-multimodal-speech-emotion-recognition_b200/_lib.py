@@ -78,6 +78,7 @@ FusionDesc = STRUCTS["ser_fusion_desc"]
 ClfDesc = STRUCTS["ser_clf_desc"]
 LossDesc = STRUCTS["ser_loss_desc"]
 FeatFuseDesc = STRUCTS["ser_featfuse_desc"]
+AttnDesc = STRUCTS["ser_attn_desc"]
 
 _lib = None
 
@@ -112,6 +113,8 @@ def load():
                  ("clf", ClfDesc), ("featfuse", FeatFuseDesc)):
         getattr(lib, f"ser_{n}_fwd").argtypes = [C.POINTER(S), P]
         getattr(lib, f"ser_{n}_bwd").argtypes = [C.POINTER(S), P]
+    for n in ("ser_attention_fwd", "ser_attention_bwd"):
+        getattr(lib, n).argtypes = [C.POINTER(AttnDesc), P]
     for n in ("ser_loss_fwd", "ser_loss_finalize", "ser_loss_bwd"):
         getattr(lib, n).argtypes = [C.POINTER(LossDesc), P]
     lib.ser_xattn_bwd_ws_bytes.argtypes = [I] * 7
@@ -133,7 +136,7 @@ def load():
     lib.ser_launch_count.restype = C.c_longlong
     lib.ser_prof_enable.argtypes = [I]
     lib.ser_prof_report.argtypes = [C.c_char_p, I]
-    for i, S in enumerate((GemmDesc, AdapterDesc, XattnDesc, AspDesc, FusionDesc, ClfDesc, LossDesc, FeatFuseDesc)):
+    for i, S in enumerate((GemmDesc, AdapterDesc, XattnDesc, AspDesc, FusionDesc, ClfDesc, LossDesc, FeatFuseDesc, AttnDesc)):
         if lib.ser_desc_size(i) != C.sizeof(S):
             raise SerError(f"layout mismatch for {S.__name__}: C {lib.ser_desc_size(i)} vs ctypes {C.sizeof(S)}")
     _lib = lib

@@ -40,6 +40,7 @@ int ser_desc_size(int id) {
     case 5: return static_cast<int>(sizeof(ser_clf_desc));
     case 6: return static_cast<int>(sizeof(ser_loss_desc));
     case 7: return static_cast<int>(sizeof(ser_featfuse_desc));
+    case 8: return static_cast<int>(sizeof(ser_attn_desc));
     default: return -1;
   }
 }
@@ -103,6 +104,20 @@ int ser_featfuse_bwd(const ser_featfuse_desc* d, void* stream) { SER_NOT_NULL(d)
 size_t ser_xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H) {
   return ser::xattn_bwd_ws_bytes(dtype, B, Ta, Tt, D, S, H);
 }
+static ser::AttnArgs to_attn_args(const ser_attn_desc& d) {
+  ser::AttnArgs a{};
+  a.dtype = d.dtype; a.B = d.B; a.H = d.H; a.Tq = d.Tq; a.Tk = d.Tk; a.dh = d.dh;
+  a.Q = d.Q; a.ldq = d.ldq; a.K = d.K; a.ldk = d.ldk; a.V = d.V; a.ldv = d.ldv; a.kmask = d.kmask;
+  a.O = d.O; a.ldo = d.ldo; a.lse = d.lse; a.scale = d.scale;
+  a.dO = d.dO; a.lddo = d.lddo; a.dQ = d.dQ; a.lddq = d.lddq; a.dK = d.dK; a.lddk = d.lddk; a.dV = d.dV; a.lddv = d.lddv;
+  a.delta = d.delta;
+  a.drop = ser::make_drop(d.drop_seed, d.p_drop, static_cast<unsigned>(d.drop_site));
+  a.impl = d.impl;
+  return a;
+}
+int ser_attention_fwd(const ser_attn_desc* d, void* stream) { SER_NOT_NULL(d); return ser::attention_fwd(to_attn_args(*d), SER_STREAM(stream)); }
+int ser_attention_bwd(const ser_attn_desc* d, void* stream) { SER_NOT_NULL(d); return ser::attention_bwd(to_attn_args(*d), SER_STREAM(stream)); }
+
 int ser_xattn_folded(int dtype, int D, int S) { return ser::xattn_fold_enabled(dtype, D, S) ? 1 : 0; }
 int ser_xattn_fwd(const ser_xattn_desc* d, void* stream) { SER_NOT_NULL(d); return ser::xattn_fwd(*d, SER_STREAM(stream)); }
 int ser_xattn_bwd(const ser_xattn_desc* d, void* stream) { SER_NOT_NULL(d); return ser::xattn_bwd(*d, SER_STREAM(stream)); }

@@ -328,13 +328,23 @@ int check(const AttnArgs& a) {
 int attention_fwd(const AttnArgs& a, cudaStream_t s) {
   SER_TRY(check(a));
   // bf16 tier: tensor-core kernels (attention_tc.cu); fp32 tier: the CUDA-core kernels of this file
-  return a.dtype == DT_F32 ? fwd_impl<float>(a, s) : attention_fwd_tc(a, s);
+  if (a.dtype == DT_F32) return fwd_impl<float>(a, s);
+  if (a.impl == 2 && !attention_tc5_supported(a)) {
+    set_last_error(__FILE__, __LINE__, "attention: the tcgen05 kernels need head dim 32, an even head count and 16-byte aligned operands");
+    return SER_ERR_UNSUPPORTED;
+  }
+  return (a.impl != 1 && attention_tc5_supported(a)) ? attention_fwd_tc5(a, s) : attention_fwd_tc(a, s);
 }
 
 int attention_bwd(const AttnArgs& a, cudaStream_t s) {
   SER_TRY(check(a));
   SER_REQUIRE(a.delta != nullptr && a.lse != nullptr, "attention_bwd: lse / delta buffers required");
-  return a.dtype == DT_F32 ? bwd_impl<float>(a, s) : attention_bwd_tc(a, s);
+  if (a.dtype == DT_F32) return bwd_impl<float>(a, s);
+  if (a.impl == 2 && !attention_tc5_supported(a)) {
+    set_last_error(__FILE__, __LINE__, "attention: the tcgen05 kernels need head dim 32, an even head count and 16-byte aligned operands");
+    return SER_ERR_UNSUPPORTED;
+  }
+  return (a.impl != 1 && attention_tc5_supported(a)) ? attention_bwd_tc5(a, s) : attention_bwd_tc(a, s);
 }
 
 }  // namespace ser

@@ -65,12 +65,17 @@ struct AttnArgs {
   float* delta;             // [B, H, Tq] scratch: rowsum(dO * O)
   // dropout on the attention weights (nn.MultiheadAttention(dropout=p)): site [B*H*Tq, Tk]; off by default
   DropSpec drop;
+  int impl = 0;             // bf16 tier: 0 = choose (tcgen05 kernels when the shape qualifies), 1 = mma.sync, 2 = tcgen05
 };
 int attention_fwd(const AttnArgs& a, cudaStream_t s);
 int attention_bwd(const AttnArgs& a, cudaStream_t s);
 // bf16 tensor-core variants (attention_tc.cu); attention_fwd / attention_bwd dispatch to them for dtype == bf16
 int attention_fwd_tc(const AttnArgs& a, cudaStream_t s);
 int attention_bwd_tc(const AttnArgs& a, cudaStream_t s);
+// tcgen05 / TMEM / TMA variants (attention_tc5.cu): head dim 32, even head count, TMA-addressable operands
+bool attention_tc5_supported(const AttnArgs& a);
+int attention_fwd_tc5(const AttnArgs& a, cudaStream_t s);
+int attention_bwd_tc5(const AttnArgs& a, cudaStream_t s);
 
 // ---- clf_stack.cu --------------------------------------------------------------------------------
 // The whole residual stack (classifier.py:207-212) as one cluster kernel per direction, bf16 tier, base_dim 512.

@@ -1,0 +1,159 @@
+"""Attention core on its own (ser_attention_fwd / ser_attention_bwd): the tcgen05 kernels (impl 2) against an fp64
+torch reference and against the mma.sync kernels (impl 1), plus CUDA-event timings of both at the BASELINE shapes.
+Run on the GPU box:  python tools/attn_check.py [fwd|all] [--time]"""
+import ctypes as C
+import math
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from mmser_b200 import _lib as L  # noqa: E402
+from mmser_b200.functional import dropout_mask  # noqa: E402
+
+dev = torch.device("cuda:0")
+lib = L.load()
+DH, S3 = 32, 768
+
+
+def run(impl, B, H, Tq, Tk, q, k, v, kmask, p_drop=0.0, seed=None, site=1, dO=None):
+    """q/k/v: [B*T, 768] bf16 projection buffers (heads in the first / second / third 256 columns as in p_a / p_t)."""
+    d = L.AttnDesc()
+    keep = []
+    O = torch.zeros(B * Tq, H * DH, device=dev, dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, Tq, device=dev)
+    f = dict(dtype=L.SER_BF16, B=B, H=H, Tq=Tq, Tk=Tk, dh=DH, Q=q, ldq=S3, K=k, ldk=S3, V=v, ldv=S3, kmask=kmask, O=O,
+             ldo=H * DH, lse=lse, scale=1.0 / math.sqrt(DH), impl=impl, drop_site=site)
+    if p_drop > 0:
+        f.update(p_drop=p_drop, drop_seed=seed)
+    out = {"O": O, "lse": lse}
+    if dO is not None:
+        dq = torch.zeros(B * Tq, S3, device=dev, dtype=torch.bfloat16)
+        dkv = torch.zeros(B * Tk, S3, device=dev, dtype=torch.bfloat16)
+        delta = torch.zeros(B, H, Tq, device=dev)
+        f.update(dO=dO, lddo=H * DH, dQ=dq, lddq=S3, dK=dkv[:, 256:], lddk=S3, dV=dkv[:, 512:], lddv=S3, delta=delta)
+        out.update(dQ=dq[:, :256], dK=dkv[:, 256:512], dV=dkv[:, 512:])
+    for kk, vv in f.items():
+        if isinstance(vv, torch.Tensor):
+            keep.append(vv)
+            setattr(d, kk, vv.data_ptr())
+        elif vv is not None:
+            setattr(d, kk, vv)
+    L.check(lib.ser_attention_fwd(C.byref(d), L.stream_ptr(dev)), "ser_attention_fwd")
+    if dO is not None:
+        L.check(lib.ser_attention_bwd(C.byref(d), L.stream_ptr(dev)), "ser_attention_bwd")
+    torch.cuda.synchronize()
+    return out
+
+
+def reference(B, H, Tq, Tk, q, k, v, kmask, mask_mult=None, dO=None):
+    qh = q[:, :256].double().view(B, Tq, H, DH).transpose(1, 2).requires_grad_(dO is not None)
+    kh = k.double().view(B, Tk, H, DH).transpose(1, 2).requires_grad_(dO is not None)
+    vh = v.double().view(B, Tk, H, DH).transpose(1, 2).requires_grad_(dO is not None)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(DH)
+    if kmask is not None:
+        s = s.masked_fill((kmask == 0)[:, None, None, :], float("-inf"))
+    lse = torch.logsumexp(s, dim=-1)
+    p = torch.softmax(s, dim=-1)
+    if mask_mult is not None:
+        p = p * mask_mult.double()
+    o = (p @ vh).transpose(1, 2).reshape(B * Tq, H * DH)
+    out = {"O": o, "lse": lse}
+    if dO is not None:
+        (o * dO.double()).sum().backward()
+        out.update(dQ=qh.grad.transpose(1, 2).reshape(B * Tq, H * DH), dK=kh.grad.transpose(1, 2).reshape(B * Tk, H * DH),
+                   dV=vh.grad.transpose(1, 2).reshape(B * Tk, H * DH))
+    return out
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    ok = ~(torch.isnan(a) | torch.isnan(b))
+    if not torch.equal(torch.isnan(a), torch.isnan(b)):
+        return float("inf")
+    return ((a[ok] - b[ok]).norm() / b[ok].norm().clamp_min(1e-30)).item()
+
+
+def case(B, H, Tq, Tk, masked, p_drop, bwd, seed):
+    g = torch.Generator().manual_seed(seed)
+    qb = (torch.randn(B * Tq, S3, generator=g) * 1.5).to(dev).bfloat16()      # Q in columns 0..255
+    kvb = (torch.randn(B * Tk, S3, generator=g) * 1.5).to(dev).bfloat16()     # K in 256..511, V in 512..767
+    kmask = None
+    if masked:
+        lens = torch.randint(max(1, Tk // 4), Tk + 1, (B,), generator=g)
+        kmask = (torch.arange(Tk)[None] < lens[:, None]).float().to(dev)
+        if B > 2:
+            kmask[1, ::3] = 0.0                      # a non-contiguous mask as well
+    dO = (torch.randn(B * Tq, H * DH, generator=g)).to(dev).bfloat16() if bwd else None
+    sd = torch.tensor([0x1234567887654321 + seed], dtype=torch.int64, device=dev)
+    mm = dropout_mask(sd, 1, p_drop, B * H * Tq, Tk).view(B, H, Tq, Tk) if p_drop > 0 else None
+    k, v = kvb[:, 256:], kvb[:, 512:]
+    ref = reference(B, H, Tq, Tk, qb, kvb[:, 256:512], kvb[:, 512:], kmask, mm, dO)
+    res = {}
+    for impl in (1, 2):
+        out = run(impl, B, H, Tq, Tk, qb, k, v, kmask, p_drop, sd, 1, dO)
+        res[impl] = {kk: rel(out[kk], ref[kk]) for kk in ref}
+    tag = f"B{B} H{H} Tq{Tq} Tk{Tk} {'mask' if masked else 'nomask'} p={p_drop}"
+    bad = any(not (vv < 3e-2) for vv in res[2].values())
+    print(f"{'FAIL' if bad else 'ok  '} {tag:38s} tcgen05: " + " ".join(f"{kk}={vv:.2e}" for kk, vv in res[2].items()) +
+          "   | mma.sync: " + " ".join(f"{kk}={vv:.2e}" for kk, vv in res[1].items()), flush=True)
+    return not bad
+
+
+def timing(B, H, Tq, Tk, bwd, p_drop=0.1):
+    g = torch.Generator().manual_seed(1)
+    qb = torch.randn(B * Tq, S3, generator=g).to(dev).bfloat16()
+    kvb = torch.randn(B * Tk, S3, generator=g).to(dev).bfloat16()
+    lens = torch.randint(max(1, Tk // 4), Tk + 1, (B,), generator=g)
+    kmask = (torch.arange(Tk)[None] < lens[:, None]).float().to(dev)
+    dO = torch.randn(B * Tq, H * DH, generator=g).to(dev).bfloat16() if bwd else None
+    sd = torch.tensor([77], dtype=torch.int64, device=dev)
+    line = f"time B{B} Tq{Tq} Tk{Tk} {'fwd+bwd' if bwd else 'fwd'} p={p_drop}: "
+    for impl in (1, 2):
+        for _ in range(3):
+            run(impl, B, H, Tq, Tk, qb, kvb[:, 256:], kvb[:, 512:], kmask, p_drop, sd, 1, dO)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 10
+        d = L.AttnDesc()
+        O = torch.zeros(B * Tq, H * DH, device=dev, dtype=torch.bfloat16); lse = torch.zeros(B, H, Tq, device=dev)
+        dq = torch.zeros(B * Tq, S3, device=dev, dtype=torch.bfloat16); dkv = torch.zeros(B * Tk, S3, device=dev, dtype=torch.bfloat16)
+        delta = torch.zeros(B, H, Tq, device=dev)
+        f = dict(dtype=L.SER_BF16, B=B, H=H, Tq=Tq, Tk=Tk, dh=DH, Q=qb.data_ptr(), ldq=S3, K=kvb[:, 256:].data_ptr(), ldk=S3,
+                 V=kvb[:, 512:].data_ptr(), ldv=S3, kmask=kmask.data_ptr(), O=O.data_ptr(), ldo=H * DH, lse=lse.data_ptr(),
+                 scale=1.0 / math.sqrt(DH), impl=impl, drop_site=1)
+        if p_drop > 0:
+            f.update(p_drop=p_drop, drop_seed=sd.data_ptr())
+        if bwd:
+            f.update(dO=dO.data_ptr(), lddo=H * DH, dQ=dq.data_ptr(), lddq=S3, dK=dkv[:, 256:].data_ptr(), lddk=S3,
+                     dV=dkv[:, 512:].data_ptr(), lddv=S3, delta=delta.data_ptr())
+        for kk, vv in f.items():
+            setattr(d, kk, vv)
+        st = L.stream_ptr(dev)
+        e0.record()
+        for _ in range(n):
+            lib.ser_attention_fwd(C.byref(d), st)
+            if bwd:
+                lib.ser_attention_bwd(C.byref(d), st)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / n * 1e3
+        fl = (14.0 if bwd else 4.0) * B * H * Tq * Tk * DH
+        line += f"{'mma.sync' if impl == 1 else 'tcgen05'} {us:8.1f} us ({fl / us / 1e6:6.1f} TFLOP/s)   "
+    print(line, flush=True)
+
+
+if __name__ == "__main__":
+    bwd = "all" in sys.argv
+    ok = True
+    for i, (B, Tq, Tk, masked, p) in enumerate([(3, 70, 19, True, 0.0), (3, 70, 19, False, 0.0), (2, 300, 130, True, 0.0),
+                                                (4, 250, 64, True, 0.0), (4, 64, 250, True, 0.0), (2, 1500, 256, True, 0.0),
+                                                (2, 256, 1500, True, 0.0), (3, 70, 19, True, 0.1), (2, 300, 130, True, 0.25),
+                                                (1, 1, 1, False, 0.0), (2, 129, 65, True, 0.1)]):
+        ok = case(B, 8, Tq, Tk, masked, p, bwd, 10 + i) and ok
+    print("ALL OK" if ok else "SOME FAILED", flush=True)
+    if "--time" in sys.argv:
+        for (B, Tq, Tk) in ((256, 250, 64), (256, 64, 250), (128, 1500, 256), (128, 256, 1500)):
+            timing(B, 8, Tq, Tk, False, 0.0)
+            timing(B, 8, Tq, Tk, False, 0.1)
+            if bwd:
+                timing(B, 8, Tq, Tk, True, 0.1)

@@ -138,8 +138,77 @@ __global__ void __launch_bounds__(128) mma_time_kernel(long long* __restrict__ o
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
+// Tensor-memory load / store throughput probe: `nw` warps of one CTA (block of 512 threads) each issue `reps`
+// back-to-back tcgen05.ld (or st) of 32 lanes x 32 columns (4 KB per instruction) and one wait; clock64 per warp.
+// mode 0: ld 32x32b.x32, 1: st 32x32b.x32, 2: ld 32x32b.x64, 3: ld 16x256b.x8 (also 4 KB)
+__global__ void __launch_bounds__(512) ldtm_time_kernel(long long* __restrict__ out, int nw, int reps, int mode) {
+  __shared__ uint32_t slot;
+  const int t = threadIdx.x, warp = t >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s32(&slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = slot;
+  uint32_t acc = 0;
+  if (warp < nw) {
+    const uint32_t base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    uint32_t r[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) r[i] = i;
+    const long long t0 = clock64();
+    for (int k = 0; k < reps; ++k) {
+      const uint32_t a = base + static_cast<uint32_t>((k * 64) & 255);
+      if (mode == 0) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                       "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(a));
+      } else if (mode == 1) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                     "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                     "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                     ::"r"(a), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                       "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                       "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+                       "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+      } else if (mode == 3) {
+        asm volatile("tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                       "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(a));
+      }
+    }
+    if (mode == 1) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    else asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const long long t1 = clock64();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc ^= r[i];
+    if ((t & 31) == 0) out[warp] = t1 - t0;
+  }
+  if (acc == 0x12345678u) out[63] = acc;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 }  // namespace
 }  // namespace ser
+
+extern "C" int ser_debug_ldtm_time(long long* out, int nw, int reps, int mode, int ctas, void* stream) {
+  ser::ldtm_time_kernel<<<ctas, 512, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out, nw, reps, mode);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
 
 // out: [128 lanes][64 columns] fp32 (device).  m = 64 or 128.
 extern "C" int ser_debug_probe_tmem_layout(float* out, int m, void* stream) {
