@@ -87,7 +87,7 @@ template <bool DROP>
 __global__ void __launch_bounds__(A5_THREADS, 2)
 attn5_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const float* __restrict__ kmask, bf16* __restrict__ O,
-                 long long ldo, float* __restrict__ lse, int H, int Tq, int Tk, float scale, DropSpec drop) {
+                 long long ldo, float* __restrict__ lse, int H, int Tq, int Tk, float scale, DropSpec drop, int narrow) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                                  // [128 x 128 B]   Q rows, both heads of the pair
@@ -142,7 +142,10 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const bool leader = (quarter == 0 && lane == 0);        // issues this head's MMAs
   const int col0 = hp * 2 * A5_DH;
   constexpr uint32_t idesc_s = make_idesc<A5_KT, 0, 0, A5_ROWS>();        // S: A = Q K-major, B = K K-major, N = 64 keys
-  constexpr uint32_t idesc_pv = make_idesc<2 * A5_DH, 0, 1, A5_ROWS>();   // P V: A = P K-major, B = V MN-major, N = 64
+  // P V: A = P K-major, B = V MN-major.  narrow = 0: N = 64 (both heads' V columns, each head keeps its 32);
+  // narrow = 1: N = 32, the B descriptor starts 64 h bytes into the 128-byte atom (this head's V columns only)
+  const uint32_t idesc_pv = narrow ? make_idesc<A5_DH, 0, 1, A5_ROWS>() : make_idesc<2 * A5_DH, 0, 1, A5_ROWS>();
+  const uint32_t v_off = narrow ? static_cast<uint32_t>(h * 64) : 0u;
   const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP + h * A5_TILE_OWN);
   auto load_kv = [&](int t) {                               // head 0's leader only
     const int st = t & 1;
@@ -178,7 +181,8 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const bool active = (q0 + quarter * 32) < Tq;             // warp-uniform: warps past the end of the sample only keep the barriers moving
   const int head = hp * 2 + h;
   const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(h * A5_KT);
-  const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(128 + h * 64 + h * A5_DH);
+  const uint32_t t_o = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                       static_cast<uint32_t>(128 + h * 64 + (narrow ? 0 : h * A5_DH));
   const float c = scale * kLog2e;
   const uint32_t p_row = aP + static_cast<uint32_t>(row) * 128u;
   const uint32_t swz = static_cast<uint32_t>(row & 7);
@@ -273,7 +277,7 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t aV = smem_u32(sV + (t & 1) * A5_TILE_STR);
 #pragma unroll
       for (int k = 0; k < A5_KT / UMMA_K; ++k)
-        tc_mma_bf16(tmem_base + 128 + h * 64, desc_kmajor(aP, k * 32), desc_mnmajor(aV, k), idesc_pv, k > 0 ? 1u : 0u);
+        tc_mma_bf16(tmem_base + 128 + h * 64, desc_kmajor(aP, k * 32), desc_mnmajor(aV + v_off, k), idesc_pv, k > 0 ? 1u : 0u);
       tc_commit(&bars->o_full[h]);
       tc_commit(&bars->kv_empty[t & 1]);                    // (one of the two arrivals that release this K / V stage)
       if (t + 1 < ntiles) issue_s(t + 1);
@@ -303,6 +307,430 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         *reinterpret_cast<uint4*>(dst + 8 * j) = v;
       }
       if (lse != nullptr) lse[(static_cast<size_t>(b) * H + head) * Tq + qi] = (l > 0.f) ? m * kLn2 + logf(l) : nan;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward.  Two kernels, as in attention_tc.cu: dQ (CTA = 128 query rows x head pair, streams 32-key tiles) and
+// dK / dV (CTA = 128 key rows x head pair, streams 32-query tiles).  Per streamed tile and head, two products land in
+// tensor memory -- the scores and dP = dO V^T (or their transposes) -- the softmax warps turn them into P and
+// dS = P (mask dP - delta) with the saved log-sum-exp, write those as bf16 into ONE swizzled shared tile (P in bytes
+// 0..63 of a row, dS in bytes 64..127: two K = 32 operands addressed by descriptor offsets), and the gradient
+// products accumulate in tensor memory over all tiles (N = 32: the MN-major B descriptor starts 64 h bytes into the
+// 128-byte atom, i.e. at this head's columns).  Tensor memory per head: 32 + 32 + 32 (+ 32) columns -> 256 per CTA,
+// two CTAs per SM.  The thread that issues a head's MMAs rotates over its four warps from tile to tile.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int B5_KT = 32;                          // streamed rows per tile
+constexpr int B5_TILE_STR = B5_KT * 128;           // bytes of a 32-row x 128-byte tile
+constexpr int B5_NST = 4;                          // stages of the streamed operand pair (dQ kernel)
+constexpr int B5_NST_KV = 2;                       // ... (dK / dV kernel)
+
+template <int NST>
+struct BwdBars {
+  uint64_t own_full;                      // the CTA's own two 128-row tiles landed
+  uint64_t str_full[NST], str_empty[NST]; // streamed tile pair landed / released (both heads' accumulate MMAs retired)
+  uint64_t s_full[2];                     // per head: score + dP products of the current tile written
+  uint64_t acc_full[2];                   // per head: the accumulators are final
+  uint32_t tmem_slot;
+};
+
+template <bool DROP>
+__global__ void __launch_bounds__(A5_THREADS, 2)
+attn5_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG,
+                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                    const float* __restrict__ kmask, const bf16* __restrict__ O, long long ldo,
+                    const bf16* __restrict__ dO, long long lddo, const float* __restrict__ lse,
+                    float* __restrict__ delta, bf16* __restrict__ dQ, long long lddq, int H, int Tq, int Tk, float scale,
+                    DropSpec drop) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                                  // [128 x 128 B] Q rows (both heads)
+  uint8_t* sG = sQ + A5_TILE_OWN;                      // [128 x 128 B] dO rows
+  uint8_t* sK = sG + A5_TILE_OWN;                      // NST x [32 x 128 B]
+  uint8_t* sV = sK + B5_NST * B5_TILE_STR;             // NST x [32 x 128 B]
+  uint8_t* sD = sV + B5_NST * B5_TILE_STR;             // 2 heads x [128 x 128 B]: dS in bytes 0..63 of a row
+  BwdBars<B5_NST>* bars = reinterpret_cast<BwdBars<B5_NST>*>(sD + 2 * A5_TILE_OWN);
+  float* kbias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [ntiles * 32]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, hp = blockIdx.y, q0 = blockIdx.x * A5_ROWS;
+  const int ntiles = (Tk + B5_KT - 1) / B5_KT;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmG)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
+      mbar_init(&bars->own_full, 1);
+      for (int i = 0; i < B5_NST; ++i) { mbar_init(&bars->str_full[i], 1); mbar_init(&bars->str_empty[i], 2); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->acc_full[i], 1); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)), "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int j = threadIdx.x; j < ntiles * B5_KT; j += A5_THREADS) {
+    const bool ok = j < Tk && (kmask == nullptr || kmask[static_cast<size_t>(b) * Tk + j] != 0.f);
+    kbias[j] = ok ? 0.f : -INFINITY;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_slot;
+  // tensor-memory columns: S_h at [32 h, +32), dP_h at [64 + 32 h, +32), dQ_h at [128 + 32 h, +32)
+
+  const int h = warp >> 2, quarter = warp & 3;
+  const int col0 = hp * 2 * A5_DH;
+  constexpr uint32_t idesc_s = make_idesc<B5_KT, 0, 0, A5_ROWS>();       // [128 x 32] = A(K-major) B(K-major)^T, K = d
+  constexpr uint32_t idesc_acc = make_idesc<A5_DH, 0, 1, A5_ROWS>();     // [128 x 32] += A(K-major) B(MN-major), K = tile rows
+  const uint32_t aQ = smem_u32(sQ), aG = smem_u32(sG), aD = smem_u32(sD + h * A5_TILE_OWN);
+  auto load_tile = [&](int t) {
+    const int st = t % B5_NST;
+    mbar_expect_tx(&bars->str_full[st], 2 * B5_TILE_STR);
+    tma_load_3d(&tmK, &bars->str_full[st], sK + st * B5_TILE_STR, col0, b * Tk + t * B5_KT, 0);
+    tma_load_3d(&tmV, &bars->str_full[st], sV + st * B5_TILE_STR, col0, b * Tk + t * B5_KT, 0);
+  };
+  auto issue_products = [&](int t) {                        // S_h(t) = Q_h K_h^T, dP_h(t) = dO_h V_h^T
+    const int st = t % B5_NST;
+    mbar_wait(&bars->str_full[st], (t / B5_NST) & 1);
+    tc_fence_after();
+    const uint32_t aK = smem_u32(sK + st * B5_TILE_STR), aV = smem_u32(sV + st * B5_TILE_STR);
+#pragma unroll
+    for (int k = 0; k < A5_DH / UMMA_K; ++k)
+      tc_mma_bf16(tmem_base + h * 32, desc_kmajor(aQ, h * 64 + k * 32), desc_kmajor(aK, h * 64 + k * 32), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < A5_DH / UMMA_K; ++k)
+      tc_mma_bf16(tmem_base + 64 + h * 32, desc_kmajor(aG, h * 64 + k * 32), desc_kmajor(aV, h * 64 + k * 32), idesc_s, k > 0 ? 1u : 0u);
+    tc_commit(&bars->s_full[h]);
+  };
+  if (quarter == 3 && lane == 0) {                          // the leader "before tile 0"
+    if (h == 0) {
+      mbar_expect_tx(&bars->own_full, 2 * A5_TILE_OWN);
+      tma_load_3d(&tmQ, &bars->own_full, sQ, col0, b * Tq + q0, 0);
+      tma_load_3d(&tmG, &bars->own_full, sG, col0, b * Tq + q0, 0);
+      for (int t = 0; t < B5_NST && t < ntiles; ++t) load_tile(t);
+    }
+    mbar_wait(&bars->own_full, 0);
+    issue_products(0);
+  }
+  __syncwarp();
+
+  const int row = quarter * 32 + lane;
+  const int qi = q0 + row;
+  const bool active = (q0 + quarter * 32) < Tq;
+  const int head = hp * 2 + h;
+  const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+  const float c = scale * kLog2e;
+  const uint32_t d_row = aD + static_cast<uint32_t>(row) * 128u;
+  const uint32_t swz = static_cast<uint32_t>(row & 7);
+  DropKey dkey{0u, 1u};
+  unsigned drow = 0u;
+  if (DROP) {
+    dkey = drop_key(drop);
+    drow = ((static_cast<unsigned>(b) * H + head) * Tq + qi) * static_cast<unsigned>((Tk + 1) / 2);
+  }
+  // per-row constants: -lse in log2 units (+inf log-sum-exp for rows past the sample -> P = 0) and delta = sum(dO * O)
+  float nl = -INFINITY, dl = 0.f;
+  if (qi < Tq) {
+    const size_t r = static_cast<size_t>(b) * Tq + qi;
+    nl = -lse[(static_cast<size_t>(b) * H + head) * Tq + qi] * kLog2e;
+    float g[8], ov[8];
+#pragma unroll
+    for (int i = 0; i < A5_DH / 8; ++i) {
+      load8(dO + r * lddo + head * A5_DH + 8 * i, g);
+      load8(O + r * ldo + head * A5_DH + 8 * i, ov);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dl = fmaf(g[k], ov[k], dl);
+    }
+    delta[(static_cast<size_t>(b) * H + head) * Tq + qi] = dl;
+  }
+
+  for (int t = 0; t < ntiles; ++t) {
+    mbar_wait(&bars->s_full[h], t & 1);                    // (also: the previous tile's dQ MMAs have retired)
+    tc_fence_after();
+    if (h == 0 && quarter == (t & 3) && lane == 0 && t >= 1 && t - 1 + B5_NST < ntiles) {
+      mbar_wait(&bars->str_empty[(t - 1) % B5_NST], ((t - 1) / B5_NST) & 1);
+      load_tile(t - 1 + B5_NST);
+    }
+    __syncwarp();
+    if (active) {
+      uint32_t sv[B5_KT], dv[B5_KT];
+      tmem_ld32_issue(lane_base + h * 32, sv);
+      tmem_ld32_issue(lane_base + 64 + h * 32, dv);
+      tmem_ld_wait();
+      const float4* kb = reinterpret_cast<const float4*>(kbias + t * B5_KT);
+#pragma unroll
+      for (int j8 = 0; j8 < B5_KT / 8; ++j8) {
+        uint32_t w[4];
+        const float4 b0 = kb[2 * j8], b1 = kb[2 * j8 + 1];
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = 8 * j8 + 2 * u;
+          const float p0 = ex2(fmaf(__uint_as_float(sv[j]), c, bb[2 * u] + nl));
+          const float p1 = ex2(fmaf(__uint_as_float(sv[j + 1]), c, bb[2 * u + 1] + nl));
+          float g0 = __uint_as_float(dv[j]), g1 = __uint_as_float(dv[j + 1]);
+          if (DROP) {                                       // dP = mask * (dO V^T)
+            const float2 mk = drop_pair(dkey, drow + static_cast<unsigned>(t * (B5_KT / 2) + (j >> 1)), drop.thr, drop.scale);
+            g0 *= mk.x; g1 *= mk.y;
+          }
+          w[u] = pack_bf16x2(p0 * (g0 - dl), p1 * (g1 - dl));
+        }
+        sts128(d_row + ((static_cast<uint32_t>(j8) ^ swz) << 4), w[0], w[1], w[2], w[3]);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    group_sync(h);
+    if (quarter == (t & 3) && lane == 0) {
+      tc_fence_after();
+      const uint32_t aK = smem_u32(sK + (t % B5_NST) * B5_TILE_STR) + static_cast<uint32_t>(h * 64);
+#pragma unroll
+      for (int k = 0; k < B5_KT / UMMA_K; ++k)             // dQ_h += dS_h K_h   (K tile as the MN-major operand)
+        tc_mma_bf16(tmem_base + 128 + h * 32, desc_kmajor(aD, k * 32), desc_mnmajor(aK, k), idesc_acc, (t > 0 || k > 0) ? 1u : 0u);
+      tc_commit(&bars->str_empty[t % B5_NST]);
+      if (t + 1 < ntiles) issue_products(t + 1);
+      else tc_commit(&bars->acc_full[h]);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bars->acc_full[h], 0);
+  tc_fence_after();
+  if (active) {
+    uint32_t acc[A5_DH];
+    tmem_ld32_issue(lane_base + 128 + h * 32, acc);
+    tmem_ld_wait();
+    if (qi < Tq) {
+      bf16* dst = dQ + (static_cast<size_t>(b) * Tq + qi) * lddq + head * A5_DH;
+#pragma unroll
+      for (int j = 0; j < A5_DH / 8; ++j) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(acc[8 * j]) * scale, __uint_as_float(acc[8 * j + 1]) * scale);
+        v.y = pack_bf16x2(__uint_as_float(acc[8 * j + 2]) * scale, __uint_as_float(acc[8 * j + 3]) * scale);
+        v.z = pack_bf16x2(__uint_as_float(acc[8 * j + 4]) * scale, __uint_as_float(acc[8 * j + 5]) * scale);
+        v.w = pack_bf16x2(__uint_as_float(acc[8 * j + 6]) * scale, __uint_as_float(acc[8 * j + 7]) * scale);
+        *reinterpret_cast<uint4*>(dst + 8 * j) = v;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+  }
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(A5_THREADS, 2)
+attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG,
+                     const float* __restrict__ kmask, const float* __restrict__ lse, const float* __restrict__ delta,
+                     bf16* __restrict__ dK, long long lddk, bf16* __restrict__ dV, long long lddv, int H, int Tq, int Tk,
+                     float scale, DropSpec drop) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sK = smem;                                  // [128 x 128 B] K rows (both heads)
+  uint8_t* sV = sK + A5_TILE_OWN;                      // [128 x 128 B] V rows
+  uint8_t* sQ = sV + A5_TILE_OWN;                      // NST x [32 x 128 B]
+  uint8_t* sG = sQ + B5_NST_KV * B5_TILE_STR;          // NST x [32 x 128 B] dO rows
+  uint8_t* sD = sG + B5_NST_KV * B5_TILE_STR;          // 2 heads x [128 x 128 B]: P^T in bytes 0..63 of a row, dS^T in 64..127
+  BwdBars<B5_NST_KV>* bars = reinterpret_cast<BwdBars<B5_NST_KV>*>(sD + 2 * A5_TILE_OWN);
+  // per streamed tile and head: -lse in log2 units (-inf past the sample: P = 0) and delta of its 32 queries, double
+  // buffered: [buffer][head][0: -lse, 1: delta][32]
+  float* sLD = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, hp = blockIdx.y, k0 = blockIdx.x * A5_ROWS;
+  const int ntiles = (Tq + B5_KT - 1) / B5_KT;
+  // (warp 1 of each head fetches them for the NEXT tile before the head's barrier of the current one)
+  auto fetch_ld = [&](int t, int hh) {
+    const int q = t * B5_KT + lane;
+    const size_t idx = (static_cast<size_t>(b) * H + hp * 2 + hh) * Tq + q;
+    float* dst = sLD + ((t & 1) * 2 + hh) * 64;
+    dst[lane] = (q < Tq) ? -lse[idx] * kLog2e : -INFINITY;
+    dst[32 + lane] = (q < Tq) ? delta[idx] : 0.f;
+  };
+  if ((warp & 3) == 1) fetch_ld(0, warp >> 2);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmK)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmV)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmG)) : "memory");
+      mbar_init(&bars->own_full, 1);
+      for (int i = 0; i < B5_NST_KV; ++i) { mbar_init(&bars->str_full[i], 1); mbar_init(&bars->str_empty[i], 2); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&bars->s_full[i], 1); mbar_init(&bars->acc_full[i], 1); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)), "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_slot;
+  // tensor-memory columns: S^T_h at [32 h, +32), dP^T_h at [64 + 32 h, +32), dV_h at [128 + 32 h, +32), dK_h at [192 + 32 h, +32)
+
+  const int h = warp >> 2, quarter = warp & 3;
+  const int col0 = hp * 2 * A5_DH;
+  constexpr uint32_t idesc_s = make_idesc<B5_KT, 0, 0, A5_ROWS>();
+  constexpr uint32_t idesc_acc = make_idesc<A5_DH, 0, 1, A5_ROWS>();
+  const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aD = smem_u32(sD + h * A5_TILE_OWN);
+  auto load_tile = [&](int t) {
+    const int st = t % B5_NST_KV;
+    mbar_expect_tx(&bars->str_full[st], 2 * B5_TILE_STR);
+    tma_load_3d(&tmQ, &bars->str_full[st], sQ + st * B5_TILE_STR, col0, b * Tq + t * B5_KT, 0);
+    tma_load_3d(&tmG, &bars->str_full[st], sG + st * B5_TILE_STR, col0, b * Tq + t * B5_KT, 0);
+  };
+  auto issue_products = [&](int t) {                        // S^T_h(t) = K_h Q_h^T, dP^T_h(t) = V_h dO_h^T
+    const int st = t % B5_NST_KV;
+    mbar_wait(&bars->str_full[st], (t / B5_NST_KV) & 1);
+    tc_fence_after();
+    const uint32_t aQ = smem_u32(sQ + st * B5_TILE_STR), aG = smem_u32(sG + st * B5_TILE_STR);
+#pragma unroll
+    for (int k = 0; k < A5_DH / UMMA_K; ++k)
+      tc_mma_bf16(tmem_base + h * 32, desc_kmajor(aK, h * 64 + k * 32), desc_kmajor(aQ, h * 64 + k * 32), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < A5_DH / UMMA_K; ++k)
+      tc_mma_bf16(tmem_base + 64 + h * 32, desc_kmajor(aV, h * 64 + k * 32), desc_kmajor(aG, h * 64 + k * 32), idesc_s, k > 0 ? 1u : 0u);
+    tc_commit(&bars->s_full[h]);
+  };
+  if (quarter == 3 && lane == 0) {
+    if (h == 0) {
+      mbar_expect_tx(&bars->own_full, 2 * A5_TILE_OWN);
+      tma_load_3d(&tmK, &bars->own_full, sK, col0, b * Tk + k0, 0);
+      tma_load_3d(&tmV, &bars->own_full, sV, col0, b * Tk + k0, 0);
+      for (int t = 0; t < B5_NST_KV && t < ntiles; ++t) load_tile(t);
+    }
+    mbar_wait(&bars->own_full, 0);
+    issue_products(0);
+  }
+  __syncwarp();
+
+  const int row = quarter * 32 + lane;
+  const int kj = k0 + row;
+  const bool active = (k0 + quarter * 32) < Tk;
+  const int head = hp * 2 + h;
+  const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+  const float c = scale * kLog2e;
+  const uint32_t d_row = aD + static_cast<uint32_t>(row) * 128u;
+  const uint32_t swz = static_cast<uint32_t>(row & 7);
+  const float kb = (kj < Tk && (kmask == nullptr || kmask[static_cast<size_t>(b) * Tk + kj] != 0.f)) ? 0.f : -INFINITY;
+  DropKey dkey{0u, 1u};
+  unsigned half_tk = 0u, dcol = 0u, dhalf = 0u, drow0 = 0u;
+  if (DROP) {
+    dkey = drop_key(drop);
+    half_tk = static_cast<unsigned>((Tk + 1) / 2);
+    dcol = static_cast<unsigned>(kj) >> 1; dhalf = static_cast<unsigned>(kj) & 1u;
+    drow0 = (static_cast<unsigned>(b) * H + head) * Tq;
+  }
+
+  for (int t = 0; t < ntiles; ++t) {
+    mbar_wait(&bars->s_full[h], t & 1);
+    tc_fence_after();
+    if (h == 0 && quarter == (t & 3) && lane == 0 && t >= 1 && t - 1 + B5_NST_KV < ntiles) {
+      mbar_wait(&bars->str_empty[(t - 1) % B5_NST_KV], ((t - 1) / B5_NST_KV) & 1);
+      load_tile(t - 1 + B5_NST_KV);
+    }
+    __syncwarp();
+    if (active) {
+      const int qt = t * B5_KT;
+      const bool partial = qt + B5_KT > Tq;                 // the last tile: columns past the sample carry other rows' data
+      uint32_t sv[B5_KT], dv[B5_KT];
+      tmem_ld32_issue(lane_base + h * 32, sv);
+      tmem_ld32_issue(lane_base + 64 + h * 32, dv);
+      tmem_ld_wait();
+      const float4* ld4 = reinterpret_cast<const float4*>(sLD + ((t & 1) * 2 + h) * 64);
+#pragma unroll
+      for (int j8 = 0; j8 < B5_KT / 8; ++j8) {
+        const float4 l0 = ld4[2 * j8], l1 = ld4[2 * j8 + 1], e0 = ld4[8 + 2 * j8], e1 = ld4[8 + 2 * j8 + 1];
+        const float lq[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        const float dq_[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+        uint32_t wp[4], wd[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float pv[2], dsv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = 8 * j8 + 2 * u + e;
+            float p = ex2(fmaf(__uint_as_float(sv[j]), c, kb) + lq[2 * u + e]);
+            float g = __uint_as_float(dv[j]);
+            if (partial && !(qt + j < Tq)) { p = 0.f; g = 0.f; }      // never let a foreign row's NaN through 0 * NaN
+            float w = p;
+            if (DROP) {
+              const float mk = drop_one(dkey, (drow0 + static_cast<unsigned>(qt + j)) * half_tk + dcol, dhalf, drop.thr, drop.scale);
+              w *= mk; g *= mk;
+            }
+            pv[e] = w;
+            dsv[e] = p * (g - dq_[2 * u + e]);
+          }
+          wp[u] = pack_bf16x2(pv[0], pv[1]);
+          wd[u] = pack_bf16x2(dsv[0], dsv[1]);
+        }
+        sts128(d_row + ((static_cast<uint32_t>(j8) ^ swz) << 4), wp[0], wp[1], wp[2], wp[3]);
+        sts128(d_row + ((static_cast<uint32_t>(4 + j8) ^ swz) << 4), wd[0], wd[1], wd[2], wd[3]);
+      }
+    }
+    if (quarter == 1 && t + 1 < ntiles) fetch_ld(t + 1, h);
+    fence_async_smem();
+    tc_fence_before();
+    group_sync(h);
+    if (quarter == (t & 3) && lane == 0) {
+      tc_fence_after();
+      const int st = t % B5_NST_KV;
+      const uint32_t aG = smem_u32(sG + st * B5_TILE_STR) + static_cast<uint32_t>(h * 64);
+      const uint32_t aQ = smem_u32(sQ + st * B5_TILE_STR) + static_cast<uint32_t>(h * 64);
+#pragma unroll
+      for (int k = 0; k < B5_KT / UMMA_K; ++k)             // dV_h += P^T_h dO_h
+        tc_mma_bf16(tmem_base + 128 + h * 32, desc_kmajor(aD, k * 32), desc_mnmajor(aG, k), idesc_acc, (t > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < B5_KT / UMMA_K; ++k)             // dK_h += dS^T_h Q_h
+        tc_mma_bf16(tmem_base + 192 + h * 32, desc_kmajor(aD, 64 + k * 32), desc_mnmajor(aQ, k), idesc_acc, (t > 0 || k > 0) ? 1u : 0u);
+      tc_commit(&bars->str_empty[st]);
+      if (t + 1 < ntiles) issue_products(t + 1);
+      else tc_commit(&bars->acc_full[h]);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bars->acc_full[h], 0);
+  tc_fence_after();
+  if (active) {
+    uint32_t av[A5_DH], ak[A5_DH];
+    tmem_ld32_issue(lane_base + 128 + h * 32, av);
+    tmem_ld32_issue(lane_base + 192 + h * 32, ak);
+    tmem_ld_wait();
+    if (kj < Tk) {
+      const size_t r = static_cast<size_t>(b) * Tk + kj;
+      bf16* pk = dK + r * lddk + head * A5_DH;
+      bf16* pv = dV + r * lddv + head * A5_DH;
+#pragma unroll
+      for (int j = 0; j < A5_DH / 8; ++j) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(ak[8 * j]) * scale, __uint_as_float(ak[8 * j + 1]) * scale);
+        v.y = pack_bf16x2(__uint_as_float(ak[8 * j + 2]) * scale, __uint_as_float(ak[8 * j + 3]) * scale);
+        v.z = pack_bf16x2(__uint_as_float(ak[8 * j + 4]) * scale, __uint_as_float(ak[8 * j + 5]) * scale);
+        v.w = pack_bf16x2(__uint_as_float(ak[8 * j + 6]) * scale, __uint_as_float(ak[8 * j + 7]) * scale);
+        *reinterpret_cast<uint4*>(pk + 8 * j) = v;
+        v.x = pack_bf16x2(__uint_as_float(av[8 * j]), __uint_as_float(av[8 * j + 1]));
+        v.y = pack_bf16x2(__uint_as_float(av[8 * j + 2]), __uint_as_float(av[8 * j + 3]));
+        v.z = pack_bf16x2(__uint_as_float(av[8 * j + 4]), __uint_as_float(av[8 * j + 5]));
+        v.w = pack_bf16x2(__uint_as_float(av[8 * j + 6]), __uint_as_float(av[8 * j + 7]));
+        *reinterpret_cast<uint4*>(pv + 8 * j) = v;
+      }
     }
   }
   tc_fence_before();
@@ -345,12 +773,66 @@ int attention_fwd_tc5(const AttnArgs& a, cudaStream_t s) {
     configured[a.drop.on() ? 1 : 0] = true;
   }
   dim3 grid(ceil_div(a.Tq, A5_ROWS), a.H / 2, a.B);
+  static const int narrow = getenv("SER_ATTN_NARROW") ? atoi(getenv("SER_ATTN_NARROW")) : 0;     // A/B switch
   kern<<<grid, A5_THREADS, smem, s>>>(tmQ, tmK, tmV, a.kmask, reinterpret_cast<bf16*>(a.O), a.ldo, a.lse, a.H, a.Tq, a.Tk,
-                                      a.scale, a.drop);
+                                      a.scale, a.drop, narrow);
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
 
-int attention_bwd_tc5(const AttnArgs& a, cudaStream_t s) { return attention_bwd_tc(a, s); }   // (tcgen05 backward: below, WIP)
+int attention_bwd_tc5(const AttnArgs& a, cudaStream_t s) {
+  const double fl = 10.0 * a.B * a.H * static_cast<double>(a.Tq) * a.Tk * a.dh;
+  const double by = 2.0 * static_cast<double>(a.B) * a.H * a.dh * (4.0 * a.Tq + 4.0 * a.Tk);
+  ProfScope prof("attention_bwd", fl, by, s);
+  auto ok_ptr = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  SER_REQUIRE(ok_ptr(a.dO) && ok_ptr(a.dQ) && ok_ptr(a.dK) && ok_ptr(a.dV) && a.lddo % 8 == 0 && a.lddq % 8 == 0 &&
+                  a.lddk % 8 == 0 && a.lddv % 8 == 0,
+              "attention_bwd_tc5: gradient buffers must be 16-byte aligned with 8-element aligned leading dimensions");
+  const int HD = a.H * a.dh;
+  const long long Mq = static_cast<long long>(a.B) * a.Tq, Mk = static_cast<long long>(a.B) * a.Tk;
+  const bool drop = a.drop.on();
+  {
+    CUtensorMap tmQ, tmG, tmK, tmV;
+    SER_TRY(make_tmap(&tmQ, a.Q, 0, Mq, HD, a.ldq, A5_ROWS, 64, 1, 0));
+    SER_TRY(make_tmap(&tmG, a.dO, 0, Mq, HD, a.lddo, A5_ROWS, 64, 1, 0));
+    SER_TRY(make_tmap(&tmK, a.K, 0, Mk, HD, a.ldk, B5_KT, 64, 1, 0));
+    SER_TRY(make_tmap(&tmV, a.V, 0, Mk, HD, a.ldv, B5_KT, 64, 1, 0));
+    const int ntiles = ceil_div(a.Tk, B5_KT);
+    const int smem = 1024 + 4 * A5_TILE_OWN + 2 * B5_NST * B5_TILE_STR + 256 + ntiles * B5_KT * static_cast<int>(sizeof(float));
+    auto* kern = drop ? attn5_bwd_dq_kernel<true> : attn5_bwd_dq_kernel<false>;
+    static bool configured[2] = {false, false};
+    if (!configured[drop ? 1 : 0]) {
+      SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          1024 + 4 * A5_TILE_OWN + 2 * B5_NST * B5_TILE_STR + 256 + (8192 + 32) * 4));
+      SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      configured[drop ? 1 : 0] = true;
+    }
+    dim3 grid(ceil_div(a.Tq, A5_ROWS), a.H / 2, a.B);
+    kern<<<grid, A5_THREADS, smem, s>>>(tmQ, tmG, tmK, tmV, a.kmask, reinterpret_cast<const bf16*>(a.O), a.ldo,
+                                        reinterpret_cast<const bf16*>(a.dO), a.lddo, a.lse, a.delta,
+                                        reinterpret_cast<bf16*>(a.dQ), a.lddq, a.H, a.Tq, a.Tk, a.scale, a.drop);
+    SER_LAUNCH_CHECK();
+  }
+  {
+    CUtensorMap tmK, tmV, tmQ, tmG;
+    SER_TRY(make_tmap(&tmK, a.K, 0, Mk, HD, a.ldk, A5_ROWS, 64, 1, 0));
+    SER_TRY(make_tmap(&tmV, a.V, 0, Mk, HD, a.ldv, A5_ROWS, 64, 1, 0));
+    SER_TRY(make_tmap(&tmQ, a.Q, 0, Mq, HD, a.ldq, B5_KT, 64, 1, 0));
+    SER_TRY(make_tmap(&tmG, a.dO, 0, Mq, HD, a.lddo, B5_KT, 64, 1, 0));
+    const int smem = 1024 + 4 * A5_TILE_OWN + 2 * B5_NST_KV * B5_TILE_STR + 256 + 1024;
+    auto* kern = drop ? attn5_bwd_dkv_kernel<true> : attn5_bwd_dkv_kernel<false>;
+    static bool configured[2] = {false, false};
+    if (!configured[drop ? 1 : 0]) {
+      SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      configured[drop ? 1 : 0] = true;
+    }
+    dim3 grid(ceil_div(a.Tk, A5_ROWS), a.H / 2, a.B);
+    kern<<<grid, A5_THREADS, smem, s>>>(tmK, tmV, tmQ, tmG, a.kmask, a.lse, a.delta, reinterpret_cast<bf16*>(a.dK), a.lddk,
+                                        reinterpret_cast<bf16*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale, a.drop);
+    SER_LAUNCH_CHECK();
+  }
+  return SER_OK;
+}
 
 }  // namespace ser
