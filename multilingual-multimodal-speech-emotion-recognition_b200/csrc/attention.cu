@@ -8,6 +8,7 @@
 // one thread owns one query row (dh = 32 values in registers), K/V tiles are staged in shared memory.
 // The score matrix never touches HBM; only the per-row log-sum-exp is saved for the backward pass.
 #include "kernels.cuh"
+#include <stdlib.h>
 #include "prof.cuh"
 
 namespace ser {
@@ -325,6 +326,24 @@ int check(const AttnArgs& a) {
 
 }  // namespace
 
+// bf16 tier: which tensor-core path.  The tcgen05 kernels (attention_tc5.cu) win where a CTA has several streamed tiles
+// to amortise its set-up (tensor-memory allocation, barrier initialisation, the first TMA round trip): measured on a
+// B200 with dropout 0.1 (tools/attn_check.py --time), forward 332 / 287 us vs 486 / 470 us for the mma.sync kernels at
+// (Tq, Tk) = (1500, 256) / (256, 1500) and 52 vs 60 us at (250, 64); they lose where half of a 128-row tile is empty and
+// the loop is short: forward 56 vs 50 us at (64, 250), backward 186 / 157 us vs 140 / 130 us at the two cfg2 shapes
+// (backward at the long shapes: 969 / 933 us vs 1070 / 1070 us).  impl = 2 / 1 (or SER_ATTN_FWD / SER_ATTN_BWD = 2 / 1)
+// forces one path.
+static bool use_tc5(const AttnArgs& a, bool backward) {
+  static const int env_f = getenv("SER_ATTN_FWD") ? atoi(getenv("SER_ATTN_FWD")) : 0;
+  static const int env_b = getenv("SER_ATTN_BWD") ? atoi(getenv("SER_ATTN_BWD")) : 0;
+  const int forced = a.impl != 0 ? a.impl : (backward ? env_b : env_f);
+  if (forced == 1 || !attention_tc5_supported(a)) return false;
+  if (forced == 2) return true;
+  const long long cells = static_cast<long long>(a.Tq) * a.Tk;
+  if (backward) return cells >= 131072;
+  return a.Tq > 64 || cells >= 131072;
+}
+
 int attention_fwd(const AttnArgs& a, cudaStream_t s) {
   SER_TRY(check(a));
   // bf16 tier: tensor-core kernels (attention_tc.cu); fp32 tier: the CUDA-core kernels of this file
@@ -333,7 +352,7 @@ int attention_fwd(const AttnArgs& a, cudaStream_t s) {
     set_last_error(__FILE__, __LINE__, "attention: the tcgen05 kernels need head dim 32, an even head count and 16-byte aligned operands");
     return SER_ERR_UNSUPPORTED;
   }
-  return (a.impl != 1 && attention_tc5_supported(a)) ? attention_fwd_tc5(a, s) : attention_fwd_tc(a, s);
+  return use_tc5(a, false) ? attention_fwd_tc5(a, s) : attention_fwd_tc(a, s);
 }
 
 int attention_bwd(const AttnArgs& a, cudaStream_t s) {
@@ -344,7 +363,7 @@ int attention_bwd(const AttnArgs& a, cudaStream_t s) {
     set_last_error(__FILE__, __LINE__, "attention: the tcgen05 kernels need head dim 32, an even head count and 16-byte aligned operands");
     return SER_ERR_UNSUPPORTED;
   }
-  return (a.impl != 1 && attention_tc5_supported(a)) ? attention_bwd_tc5(a, s) : attention_bwd_tc(a, s);
+  return use_tc5(a, true) ? attention_bwd_tc5(a, s) : attention_bwd_tc(a, s);
 }
 
 }  // namespace ser

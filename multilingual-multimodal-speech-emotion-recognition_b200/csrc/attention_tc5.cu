@@ -228,22 +228,24 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld_wait();
         if (full) {
 #pragma unroll
-          for (int j = 0; j < A5_KT; ++j) x[j] = __uint_as_float(sv[j]) * c;
-        } else {
+          for (int j = 0; j < A5_KT; ++j) x[j] = __uint_as_float(sv[j]);
+        } else {                                            // padded keys: -inf in raw score units
           const float4* kb = reinterpret_cast<const float4*>(kbias + t * A5_KT);
 #pragma unroll
           for (int j = 0; j < A5_KT / 4; ++j) {
             const float4 bb = kb[j];
-            x[4 * j] = fmaf(__uint_as_float(sv[4 * j]), c, bb.x);
-            x[4 * j + 1] = fmaf(__uint_as_float(sv[4 * j + 1]), c, bb.y);
-            x[4 * j + 2] = fmaf(__uint_as_float(sv[4 * j + 2]), c, bb.z);
-            x[4 * j + 3] = fmaf(__uint_as_float(sv[4 * j + 3]), c, bb.w);
+            x[4 * j] = __uint_as_float(sv[4 * j]) + bb.x;
+            x[4 * j + 1] = __uint_as_float(sv[4 * j + 1]) + bb.y;
+            x[4 * j + 2] = __uint_as_float(sv[4 * j + 2]) + bb.z;
+            x[4 * j + 3] = __uint_as_float(sv[4 * j + 3]) + bb.w;
           }
         }
       }
+      // x holds RAW masked scores; the softmax scale rides in the exponent's FFMA: p = 2^(x c - max)
       float tmax = -INFINITY;
 #pragma unroll
       for (int j = 0; j < A5_KT; j += 4) tmax = fmaxf(tmax, fmaxf(fmaxf(x[j], x[j + 1]), fmaxf(x[j + 2], x[j + 3])));
+      tmax *= c;                                            // c > 0
       const float mn = fmaxf(m, tmax);
       const float mu = (mn == -INFINITY) ? 0.f : mn;        // nothing but padded keys so far: keep exp2 finite
       const float corr = ex2(m - mu);                       // m = -inf -> 0
@@ -257,7 +259,7 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = 8 * j8 + 2 * u;
-          float p0 = ex2(x[j] - mu), p1 = ex2(x[j + 1] - mu);
+          float p0 = ex2(fmaf(x[j], c, -mu)), p1 = ex2(fmaf(x[j + 1], c, -mu));
           ls += p0 + p1;                                    // the normaliser sees every key; dropout acts on the weights
           if (DROP) {
             const float2 mk = drop_pair(dkey, drow + static_cast<unsigned>(t * (A5_KT / 2) + (j >> 1)), drop.thr, drop.scale);
@@ -684,6 +686,16 @@ attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
         sts128(d_row + ((static_cast<uint32_t>(j8) ^ swz) << 4), wp[0], wp[1], wp[2], wp[3]);
         sts128(d_row + ((static_cast<uint32_t>(4 + j8) ^ swz) << 4), wd[0], wd[1], wd[2], wd[3]);
       }
+      // The last tile's rows past the sample are another sample's dO rows (TMA boxes do not know about samples): their
+      // P^T / dS^T columns are zero, but 0 x NaN inside the tensor core is NaN, and a fully padded neighbour hands back
+      // NaN gradients.  This head's 64 bytes of those rows are cleared before they become the B operand of dV (the
+      // products that read them as dP^T have retired: s_full).
+      if (partial && quarter == 0 && qt + lane >= Tq) {
+        const uint32_t g_row = smem_u32(sG + (t % B5_NST_KV) * B5_TILE_STR) + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+        for (int cix = 0; cix < 4; ++cix)
+          sts128(g_row + ((static_cast<uint32_t>(4 * h + cix) ^ static_cast<uint32_t>(lane & 7)) << 4), 0u, 0u, 0u, 0u);
+      }
     }
     if (quarter == 1 && t + 1 < ntiles) fetch_ld(t + 1, h);
     fence_async_smem();
@@ -773,7 +785,7 @@ int attention_fwd_tc5(const AttnArgs& a, cudaStream_t s) {
     configured[a.drop.on() ? 1 : 0] = true;
   }
   dim3 grid(ceil_div(a.Tq, A5_ROWS), a.H / 2, a.B);
-  static const int narrow = getenv("SER_ATTN_NARROW") ? atoi(getenv("SER_ATTN_NARROW")) : 0;     // A/B switch
+  static const int narrow = getenv("SER_ATTN_NARROW") ? atoi(getenv("SER_ATTN_NARROW")) : 1;     // A/B switch
   kern<<<grid, A5_THREADS, smem, s>>>(tmQ, tmK, tmV, a.kmask, reinterpret_cast<bf16*>(a.O), a.ldo, a.lse, a.H, a.Tq, a.Tk,
                                       a.scale, a.drop, narrow);
   SER_LAUNCH_CHECK();

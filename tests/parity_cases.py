@@ -501,6 +501,10 @@ ALL_CASES = {
     "cross_masked": lambda: cross_case(masks=True),
     "cross_nomask": lambda: cross_case(masks=False),
     "cross_long": lambda: cross_case(B=2, Ta=300, Tt=130, masks=True, seed=11),
+    # long enough for the tcgen05 attention kernels in BOTH directions, forward and backward (csrc/attention.cu use_tc5:
+    # Tq * Tk >= 131072), ragged tails on both sides, masks, dropout on the attention weights
+    "cross_xlong": lambda: cross_case(B=1, Ta=610, Tt=250, masks=True, seed=13),
+    "cross_xlong_dropout": lambda: cross_case(B=2, Ta=530, Tt=260, masks=True, seed=17, p_drop=0.1),
     "pool": pool_case,
     "pool_nomask": lambda: pool_case(masks=False),
     "fusion": fusion_case,

@@ -35,14 +35,14 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_layouts_match_the_compiled_library(lib):
     l = lib.load()
     for i, S in enumerate((lib.GemmDesc, lib.AdapterDesc, lib.XattnDesc, lib.AspDesc, lib.FusionDesc, lib.ClfDesc,
-                           lib.LossDesc, lib.FeatFuseDesc)):
+                           lib.LossDesc, lib.FeatFuseDesc, lib.AttnDesc)):
         assert l.ser_desc_size(i) == ctypes.sizeof(S), S.__name__
 
 
 def test_blackwell_instructions_present(lib):
-    """The GEMM path and the fused classifier stack must be tcgen05 + TMA + TMEM (SASS: UTCHMMA / UTMALDG / UTMASTG /
-    LDTM).  The legacy mma.sync path (SASS HMMA) is allowed in exactly one place: the dh = 32 attention core
-    (attention_tc.cu), and nowhere else."""
+    """The GEMM path, the fused classifier stack and the attention core (attention_tc5.cu: forward, dQ, dK/dV) must be
+    tcgen05 + TMA + TMEM (SASS: UTCHMMA / UTMALDG / LDTM ...).  The legacy mma.sync path (SASS HMMA) is allowed in
+    exactly one place: the small-shape attention kernels of attention_tc.cu, and nowhere else."""
     sass = subprocess.run(["cuobjdump", "-sass", lib.LIB_PATH], capture_output=True, text=True).stdout
     if not sass:
         pytest.skip("cuobjdump unavailable")
@@ -61,6 +61,11 @@ def test_blackwell_instructions_present(lib):
         assert "UTCHMMA" in body[k] and "UTMALDG" in body[k] and "LDTM" in body[k] and "UTMASTG" in body[k], k
     for k in stack:
         assert "UTCHMMA" in body[k] and "LDTM" in body[k] and "UTMASTG" in body[k] and "UBLKCP" in body[k], k
+    attn5 = [k for k in body if "attn5_fwd_kernel" in k or "attn5_bwd_dq_kernel" in k or "attn5_bwd_dkv_kernel" in k]
+    assert len(attn5) == 6                   # three kernels x dropout off / on
+    for k in attn5:
+        assert "UTCHMMA" in body[k] and "UTMALDG" in body[k] and "LDTM" in body[k], k
+        assert "HMMA." not in body[k].replace("UTCHMMA", ""), k
     legacy = [k for k, b in body.items() if "HMMA." in b.replace("UTCHMMA", "")]
     assert legacy and all("attn_tc_" in k for k in legacy), legacy
 
