@@ -222,6 +222,7 @@ def _dp_worker(rank, world, port, q):
     assert float(late["big"][0]) == 3.0 and float(late["big"][-1]) == 3.0
     labels = torch.tensor([0, 1, 1, 3]) if rank == 0 else torch.tensor([2, 2, 1, 0])
     cfg = global_loss_cfg(labels, 4)
+    cfg["before_loss"]()                      # the count all-reduce is asynchronous: the loss awaits it, so do we
     sums = torch.tensor([1.0, 2.0]) * (rank + 1)
     cfg["all_reduce"](sums)
     q.put((rank, red.order, {n: float(b[0]) for n, b in bufs.items()}, cfg["counts"].tolist(), cfg["B_global"], sums.tolist()))
