@@ -401,13 +401,30 @@ class Ctx:
             os._exit(0)
 
 
+_EVENT_FLOOR = {"us": None}      # CUDA-event interval of an empty kernel, measured in the profiling pass
+
+
 def profile_pass(L, ctx, run_once, nprof=3, detail_path=""):
     """Per-kernel-family CUDA-event profile of `nprof` eager passes (rank 0 records): (families, gemm_detail)."""
     ctx.barrier()
+    # events cannot be timed inside a graph replay, so the eager launches are profiled -- but issued one by one the
+    # device outruns the host and every event interval would contain the host's launch latency (6-8 us on top of the
+    # small kernels).  Each profiled pass is therefore enqueued behind a stall kernel that lasts longer than the host
+    # needs to enqueue the whole step: the device then runs the step's kernels back to back, as in the replayed graph.
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run_once()
+    host_us = (time.perf_counter() - t0) * 1e6          # host time to enqueue one eager step
+    torch.cuda.synchronize()
     if ctx.rank == 0:
         L.prof_enable(True)
     for _ in range(nprof):             # every rank runs the pass (the steps contain collectives); rank 0 records
-        run_once()                     # events cannot be timed inside a graph replay: profile the eager launches
+        L.prof_stall(1.5 * host_us + 2000.0, torch.cuda.current_device())
+        run_once()
+        torch.cuda.synchronize()
+    if ctx.rank == 0:                  # floor of one event interval: an empty kernel, measured the same way
+        L.prof_stall(3000.0, torch.cuda.current_device())
+        L.prof_null(32, torch.cuda.current_device())
     ctx.barrier()
     if ctx.rank != 0:
         return {}, {}
@@ -418,6 +435,8 @@ def profile_pass(L, ctx, run_once, nprof=3, detail_path=""):
             for k, v in sorted(detail.items(), key=lambda kv: -kv[1]["ms"]):
                 f.write(f"{k:44s} n/step={v['launches']/nprof:6.1f} ms/step={v['ms']/nprof:8.4f} us/launch={1e3*v['ms']/v['launches']:8.1f} "
                         f"TFLOP/s={v['flops']/max(v['ms'],1e-9)/1e9:8.1f} GB/s={v['bytes']/max(v['ms'],1e-9)/1e6:8.1f}\n")
+    null = detail.pop("prof_null", None)
+    _EVENT_FLOOR["us"] = (1e3 * null["ms"] / null["launches"]) if null and null["launches"] else None
     gemm_detail = {k: v for k, v in detail.items() if k.startswith("gemm_tc")}
     prof = {}
     for k, v in detail.items():            # aggregate shape-tagged records per kernel family
@@ -478,6 +497,14 @@ def roofline_block(prof, gemm_detail, peaks, nprof):
         big = [v for v in allg if v["ms"] / max(v["launches"], 1) >= 0.020]
         roof["all_launches"] = _roof(allg)
         roof["launches_over_20us"] = _roof(big)
+        # every record is one event interval around one launch: it contains the launch + drain latency of an isolated
+        # kernel and the two event records, which a CUDA-graph replay does not pay per kernel.  The interval of an
+        # EMPTY kernel measured the same way is that floor; `frac` above is the raw figure, this one is net of it.
+        floor_us = _EVENT_FLOOR["us"]
+        if floor_us is not None and gms * 1e3 > nl * floor_us:
+            net_ms = gms - nl * floor_us * 1e-3
+            roof["event_interval_floor_us"] = floor_us
+            roof["frac_net_of_event_floor"] = gflops / (net_ms * 1e-3) / 1e12 / peaks["tf_burst"]
     tot_prof_ms = sum(v["ms_per_step"] for v in prof.values()) or 1.0
     families = {k: {"ms_per_step": round(v["ms_per_step"], 4), "launches_per_step": v["launches_per_step"],
                     "share": round(v["ms_per_step"] / tot_prof_ms, 4),

@@ -51,6 +51,12 @@ int ser_desc_size(int id);
 int ser_prof_enable(int on);
 /* device-synchronises; writes "<family> <launches> <total_ms> <alg_flops> <alg_bytes>\n" per family       */
 int ser_prof_report(char* buf, int cap);
+/* keeps `stream` busy for `microseconds` (one spinning thread).  The profiling pass enqueues it in front of a step of
+ * eager launches so that the host runs ahead of the device and the per-kernel event intervals measure kernels that run
+ * back to back, as they do inside the replayed CUDA graph, instead of the host's launch latency between them.  */
+int ser_prof_stall(double microseconds, void* stream);
+/* n profiled launches of an empty kernel, recorded as family "prof_null": the floor of one event interval          */
+int ser_prof_null(int n, void* stream);
 
 /* ---- generic fused GEMM (building block; also exported for tests and micro-benchmarks) -------
  * C[M,N] = epilogue(alpha * op(A) op(B)^T), see csrc/common.cuh GemmArgs.  Replaces every nn.Linear

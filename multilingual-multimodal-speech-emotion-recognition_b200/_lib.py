@@ -136,6 +136,8 @@ def load():
     lib.ser_launch_count.restype = C.c_longlong
     lib.ser_prof_enable.argtypes = [I]
     lib.ser_prof_report.argtypes = [C.c_char_p, I]
+    lib.ser_prof_stall.argtypes = [C.c_double, P]
+    lib.ser_prof_null.argtypes = [I, P]
     for i, S in enumerate((GemmDesc, AdapterDesc, XattnDesc, AspDesc, FusionDesc, ClfDesc, LossDesc, FeatFuseDesc, AttnDesc)):
         if lib.ser_desc_size(i) != C.sizeof(S):
             raise SerError(f"layout mismatch for {S.__name__}: C {lib.ser_desc_size(i)} vs ctypes {C.sizeof(S)}")
@@ -244,6 +246,16 @@ def launch_count() -> int:
 
 def prof_enable(on: bool) -> None:
     load().ser_prof_enable(int(on))
+
+
+def prof_stall(microseconds: float, device) -> None:
+    """Keep the current stream of `device` busy for that long, so that the launches enqueued next run back to back."""
+    check(load().ser_prof_stall(float(microseconds), stream_ptr(device)), "ser_prof_stall")
+
+
+def prof_null(n: int, device) -> None:
+    """n profiled launches of an empty kernel (family 'prof_null'): the floor of one event interval."""
+    check(load().ser_prof_null(int(n), stream_ptr(device)), "ser_prof_null")
 
 
 def prof_report():

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "modules.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace ser {
@@ -17,6 +18,12 @@ const char* last_error() { return g_err; }
 static long long g_launches = 0;
 void count_launch() { ++g_launches; }
 long long launch_count() { return g_launches; }
+
+// A/B switch: SER_PDL=0 launches every kernel with plain stream serialization
+bool pdl_enabled() {
+  static const bool on = !(getenv("SER_PDL") != nullptr && atoi(getenv("SER_PDL")) == 0);
+  return on;
+}
 
 }  // namespace ser
 

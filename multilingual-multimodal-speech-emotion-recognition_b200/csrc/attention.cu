@@ -61,6 +61,7 @@ __global__ void __launch_bounds__(NT)
 attn_fwd_kernel(const T* __restrict__ Q, long long ldq, const T* __restrict__ K, long long ldk,
                 const T* __restrict__ V, long long ldv, const float* __restrict__ kmask, T* __restrict__ O,
                 long long ldo, float* __restrict__ lse, int H, int Tq, int Tk, float scale, DropSpec drop) {
+  pdl_sync();
   __shared__ float sK[KT][DH];
   __shared__ float sV[KT][DH];
   __shared__ float sMask[KT];
@@ -144,6 +145,7 @@ attn_bwd_dq_kernel(const T* __restrict__ Q, long long ldq, const T* __restrict__
                    const T* __restrict__ O, long long ldo, const T* __restrict__ dO, long long lddo,
                    const float* __restrict__ lse, float* __restrict__ delta, T* __restrict__ dQ, long long lddq,
                    int H, int Tq, int Tk, float scale, DropSpec drop) {
+  pdl_sync();
   __shared__ float sK[KT][DH];
   __shared__ float sV[KT][DH];
   __shared__ float sMask[KT];
@@ -213,6 +215,7 @@ attn_bwd_dkv_kernel(const T* __restrict__ Q, long long ldq, const T* __restrict_
                     const T* __restrict__ dO, long long lddo, const float* __restrict__ lse,
                     const float* __restrict__ delta, T* __restrict__ dK, long long lddk, T* __restrict__ dV,
                     long long lddv, int H, int Tq, int Tk, float scale, DropSpec drop) {
+  pdl_sync();
   __shared__ float sQ[KT][DH];
   __shared__ float sG[KT][DH];
   __shared__ float sLse[KT];
@@ -286,9 +289,9 @@ int fwd_impl(const AttnArgs& a, cudaStream_t s) {
   const double by = sizeof(T) * static_cast<double>(a.B) * a.H * a.dh * (2.0 * a.Tq + 2.0 * a.Tk);
   ProfScope prof("attention_fwd", fl, by, s);
   dim3 grid(ceil_div(a.Tq, NT), a.H, a.B);
-  attn_fwd_kernel<T><<<grid, NT, 0, s>>>(reinterpret_cast<const T*>(a.Q), a.ldq, reinterpret_cast<const T*>(a.K),
+  SER_CUDA_CHECK(launch_pdl(attn_fwd_kernel<T>, dim3(grid), dim3(NT), 0, s, reinterpret_cast<const T*>(a.Q), a.ldq, reinterpret_cast<const T*>(a.K),
                                          a.ldk, reinterpret_cast<const T*>(a.V), a.ldv, a.kmask,
-                                         reinterpret_cast<T*>(a.O), a.ldo, a.lse, a.H, a.Tq, a.Tk, a.scale, a.drop);
+                                         reinterpret_cast<T*>(a.O), a.ldo, a.lse, a.H, a.Tq, a.Tk, a.scale, a.drop));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -299,17 +302,15 @@ int bwd_impl(const AttnArgs& a, cudaStream_t s) {
   const double by = sizeof(T) * static_cast<double>(a.B) * a.H * a.dh * (4.0 * a.Tq + 4.0 * a.Tk);
   ProfScope prof("attention_bwd", fl, by, s);
   dim3 gq(ceil_div(a.Tq, NT), a.H, a.B);
-  attn_bwd_dq_kernel<T><<<gq, NT, 0, s>>>(
-      reinterpret_cast<const T*>(a.Q), a.ldq, reinterpret_cast<const T*>(a.K), a.ldk,
+  SER_CUDA_CHECK(launch_pdl(attn_bwd_dq_kernel<T>, dim3(gq), dim3(NT), 0, s, reinterpret_cast<const T*>(a.Q), a.ldq, reinterpret_cast<const T*>(a.K), a.ldk,
       reinterpret_cast<const T*>(a.V), a.ldv, a.kmask, reinterpret_cast<const T*>(a.O), a.ldo,
       reinterpret_cast<const T*>(a.dO), a.lddo, a.lse, a.delta, reinterpret_cast<T*>(a.dQ), a.lddq, a.H, a.Tq, a.Tk,
-      a.scale, a.drop);
+      a.scale, a.drop));
   SER_LAUNCH_CHECK();
   dim3 gk(ceil_div(a.Tk, NT), a.H, a.B);
-  attn_bwd_dkv_kernel<T><<<gk, NT, 0, s>>>(
-      reinterpret_cast<const T*>(a.Q), a.ldq, reinterpret_cast<const T*>(a.K), a.ldk,
+  SER_CUDA_CHECK(launch_pdl(attn_bwd_dkv_kernel<T>, dim3(gk), dim3(NT), 0, s, reinterpret_cast<const T*>(a.Q), a.ldq, reinterpret_cast<const T*>(a.K), a.ldk,
       reinterpret_cast<const T*>(a.V), a.ldv, a.kmask, reinterpret_cast<const T*>(a.dO), a.lddo, a.lse, a.delta,
-      reinterpret_cast<T*>(a.dK), a.lddk, reinterpret_cast<T*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale, a.drop);
+      reinterpret_cast<T*>(a.dK), a.lddk, reinterpret_cast<T*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale, a.drop));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

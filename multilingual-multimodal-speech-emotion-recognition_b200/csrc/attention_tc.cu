@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(NT, 5)
 attn_tc_fwd_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk,
                    const bf16* __restrict__ V, long long ldv, const float* __restrict__ kmask, bf16* __restrict__ O,
                    long long ldo, float* __restrict__ lse, int H, int Tq, int Tk, float scale, DropSpec drop) {
+  pdl_sync();
   __shared__ __align__(16) bf16 sQ[ROWS * LDS];
   __shared__ __align__(16) bf16 sK[2][TILE * LDS];
   __shared__ __align__(16) bf16 sV[2][TILE * LDS];
@@ -235,6 +236,7 @@ attn_tc_bwd_dq_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __r
                       const bf16* __restrict__ O, long long ldo, const bf16* __restrict__ dO, long long lddo,
                       const float* __restrict__ lse, float* __restrict__ delta, bf16* __restrict__ dQ, long long lddq,
                       int H, int Tq, int Tk, float scale, DropSpec drop) {
+  pdl_sync();
   __shared__ __align__(16) bf16 sQ[ROWS * LDS];
   __shared__ __align__(16) bf16 sG[ROWS * LDS];
   __shared__ __align__(16) bf16 sK[2][TILE * LDS];
@@ -362,6 +364,7 @@ attn_tc_bwd_dkv_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __
                        const bf16* __restrict__ dO, long long lddo, const float* __restrict__ lse,
                        const float* __restrict__ delta, bf16* __restrict__ dK, long long lddk, bf16* __restrict__ dV,
                        long long lddv, int H, int Tq, int Tk, float scale, DropSpec drop) {
+  pdl_sync();
   __shared__ __align__(16) bf16 sK[ROWS * LDS];
   __shared__ __align__(16) bf16 sV[ROWS * LDS];
   __shared__ __align__(16) bf16 sQ[2][TILE * LDS];
@@ -480,9 +483,9 @@ int attention_fwd_tc(const AttnArgs& a, cudaStream_t s) {
   ProfScope prof("attention_fwd", fl, by, s);
   dim3 grid(ceil_div(a.Tq, ROWS), a.H, a.B);
   auto* kern = a.drop.on() ? attn_tc_fwd_kernel<true> : attn_tc_fwd_kernel<false>;
-  kern<<<grid, NT, 0, s>>>(reinterpret_cast<const bf16*>(a.Q), a.ldq, reinterpret_cast<const bf16*>(a.K), a.ldk,
+  SER_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(NT), 0, s, reinterpret_cast<const bf16*>(a.Q), a.ldq, reinterpret_cast<const bf16*>(a.K), a.ldk,
                            reinterpret_cast<const bf16*>(a.V), a.ldv, a.kmask, reinterpret_cast<bf16*>(a.O), a.ldo, a.lse,
-                           a.H, a.Tq, a.Tk, a.scale, a.drop);
+                           a.H, a.Tq, a.Tk, a.scale, a.drop));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -493,18 +496,16 @@ int attention_bwd_tc(const AttnArgs& a, cudaStream_t s) {
   ProfScope prof("attention_bwd", fl, by, s);
   dim3 gq(ceil_div(a.Tq, ROWS), a.H, a.B);
   auto* kdq = a.drop.on() ? attn_tc_bwd_dq_kernel<true> : attn_tc_bwd_dq_kernel<false>;
-  kdq<<<gq, NT, 0, s>>>(
-      reinterpret_cast<const bf16*>(a.Q), a.ldq, reinterpret_cast<const bf16*>(a.K), a.ldk,
+  SER_CUDA_CHECK(launch_pdl(kdq, dim3(gq), dim3(NT), 0, s, reinterpret_cast<const bf16*>(a.Q), a.ldq, reinterpret_cast<const bf16*>(a.K), a.ldk,
       reinterpret_cast<const bf16*>(a.V), a.ldv, a.kmask, reinterpret_cast<const bf16*>(a.O), a.ldo,
       reinterpret_cast<const bf16*>(a.dO), a.lddo, a.lse, a.delta, reinterpret_cast<bf16*>(a.dQ), a.lddq, a.H, a.Tq,
-      a.Tk, a.scale, a.drop);
+      a.Tk, a.scale, a.drop));
   SER_LAUNCH_CHECK();
   dim3 gk(ceil_div(a.Tk, ROWS), a.H, a.B);
   auto* kdkv = a.drop.on() ? attn_tc_bwd_dkv_kernel<true> : attn_tc_bwd_dkv_kernel<false>;
-  kdkv<<<gk, NT, 0, s>>>(
-      reinterpret_cast<const bf16*>(a.Q), a.ldq, reinterpret_cast<const bf16*>(a.K), a.ldk,
+  SER_CUDA_CHECK(launch_pdl(kdkv, dim3(gk), dim3(NT), 0, s, reinterpret_cast<const bf16*>(a.Q), a.ldq, reinterpret_cast<const bf16*>(a.K), a.ldk,
       reinterpret_cast<const bf16*>(a.V), a.ldv, a.kmask, reinterpret_cast<const bf16*>(a.dO), a.lddo, a.lse, a.delta,
-      reinterpret_cast<bf16*>(a.dK), a.lddk, reinterpret_cast<bf16*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale, a.drop);
+      reinterpret_cast<bf16*>(a.dK), a.lddk, reinterpret_cast<bf16*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale, a.drop));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

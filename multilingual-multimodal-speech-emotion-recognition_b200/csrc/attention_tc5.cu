@@ -119,6 +119,7 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_sync();
   for (int t = warp; t < ntiles; t += A5_THREADS / 32) {     // one warp per tile: two keys per lane
     bool ok2 = true;
 #pragma unroll
@@ -381,6 +382,7 @@ attn5_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_sync();
   for (int j = threadIdx.x; j < ntiles * B5_KT; j += A5_THREADS) {
     const bool ok = j < Tk && (kmask == nullptr || kmask[static_cast<size_t>(b) * Tk + j] != 0.f);
     kbias[j] = ok ? 0.f : -INFINITY;
@@ -563,6 +565,7 @@ attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     dst[lane] = (q < Tq) ? -lse[idx] * kLog2e : -INFINITY;
     dst[32 + lane] = (q < Tq) ? delta[idx] : 0.f;
   };
+  pdl_sync();
   if ((warp & 3) == 1) fetch_ld(0, warp >> 2);
 
   if (warp == 0) {
@@ -786,8 +789,8 @@ int attention_fwd_tc5(const AttnArgs& a, cudaStream_t s) {
   }
   dim3 grid(ceil_div(a.Tq, A5_ROWS), a.H / 2, a.B);
   static const int narrow = getenv("SER_ATTN_NARROW") ? atoi(getenv("SER_ATTN_NARROW")) : 1;     // A/B switch
-  kern<<<grid, A5_THREADS, smem, s>>>(tmQ, tmK, tmV, a.kmask, reinterpret_cast<bf16*>(a.O), a.ldo, a.lse, a.H, a.Tq, a.Tk,
-                                      a.scale, a.drop, narrow);
+  SER_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(A5_THREADS), smem, s, tmQ, tmK, tmV, a.kmask, reinterpret_cast<bf16*>(a.O), a.ldo, a.lse, a.H, a.Tq, a.Tk,
+                                      a.scale, a.drop, narrow));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -820,9 +823,9 @@ int attention_bwd_tc5(const AttnArgs& a, cudaStream_t s) {
       configured[drop ? 1 : 0] = true;
     }
     dim3 grid(ceil_div(a.Tq, A5_ROWS), a.H / 2, a.B);
-    kern<<<grid, A5_THREADS, smem, s>>>(tmQ, tmG, tmK, tmV, a.kmask, reinterpret_cast<const bf16*>(a.O), a.ldo,
+    SER_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(A5_THREADS), smem, s, tmQ, tmG, tmK, tmV, a.kmask, reinterpret_cast<const bf16*>(a.O), a.ldo,
                                         reinterpret_cast<const bf16*>(a.dO), a.lddo, a.lse, a.delta,
-                                        reinterpret_cast<bf16*>(a.dQ), a.lddq, a.H, a.Tq, a.Tk, a.scale, a.drop);
+                                        reinterpret_cast<bf16*>(a.dQ), a.lddq, a.H, a.Tq, a.Tk, a.scale, a.drop));
     SER_LAUNCH_CHECK();
   }
   {
@@ -840,8 +843,8 @@ int attention_bwd_tc5(const AttnArgs& a, cudaStream_t s) {
       configured[drop ? 1 : 0] = true;
     }
     dim3 grid(ceil_div(a.Tk, A5_ROWS), a.H / 2, a.B);
-    kern<<<grid, A5_THREADS, smem, s>>>(tmK, tmV, tmQ, tmG, a.kmask, a.lse, a.delta, reinterpret_cast<bf16*>(a.dK), a.lddk,
-                                        reinterpret_cast<bf16*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale, a.drop);
+    SER_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(A5_THREADS), smem, s, tmK, tmV, tmQ, tmG, a.kmask, a.lse, a.delta, reinterpret_cast<bf16*>(a.dK), a.lddk,
+                                        reinterpret_cast<bf16*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale, a.drop));
     SER_LAUNCH_CHECK();
   }
   return SER_OK;

@@ -468,6 +468,7 @@ __device__ __forceinline__ void setup(Ctx& c, uint8_t* smem, int warp, int lane,
   __syncthreads();
   tc_fence_after();
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c.tmem) : "r"(tmem_slot) : "memory");
+  pdl_sync();                    // barriers, tensor memory and the cluster are set up while the previous kernel drains
   cluster_sync_all();            // every CTA's barriers / stats buffers exist before any remote traffic
 }
 
@@ -1018,7 +1019,7 @@ int clf_stack_fwd(const ClfStackArgs& a, cudaStream_t s) {
   ProfScope prof("clf_stack_fwd", 4.0 * a.B * PD * PD * a.L,
                  static_cast<double>(a.L) * (2.0 * PD * PD * 2 * clusters + a.B * PD * (4.0 + 2.0 + 2.0)), s);
   auto* kern = a.drop.on() ? clf_stack_fwd_kernel<true> : clf_stack_fwd_kernel<false>;
-  kern<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmN, tmR, tmH, to_params(a, false));
+  SER_CUDA_CHECK(launch_pdl(kern, dim3(clusters * CS), dim3(kThreads), kSmemBytes, s, tmW1, tmW2, tmN, tmR, tmH, to_params(a, false)));
   SER_LAUNCH_CHECK();
   timeline_report("fwd", s);
   return SER_OK;
@@ -1041,7 +1042,7 @@ int clf_stack_bwd(const ClfStackArgs& a, cudaStream_t s) {
   ProfScope prof("clf_stack_bwd", 4.0 * a.B * PD * PD * a.L,
                  static_cast<double>(a.L) * (2.0 * PD * PD * 2 * clusters + a.B * PD * (4.0 + 2.0 + 2.0 + 2.0)), s);
   auto* kern = a.drop.on() ? clf_stack_bwd_kernel<true> : clf_stack_bwd_kernel<false>;
-  kern<<<clusters * CS, kThreads, kSmemBytes, s>>>(tmW1, tmW2, tmDhn, tmDr, to_params(a, true));
+  SER_CUDA_CHECK(launch_pdl(kern, dim3(clusters * CS), dim3(kThreads), kSmemBytes, s, tmW1, tmW2, tmDhn, tmDr, to_params(a, true)));
   SER_LAUNCH_CHECK();
   timeline_report("bwd", s);
   return SER_OK;

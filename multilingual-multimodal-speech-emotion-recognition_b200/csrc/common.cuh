@@ -17,9 +17,9 @@ enum : int { GATE_NONE = 0, GATE_RELU = 1 /* g > 0 */, GATE_TANH = 2 /* 1 - g^2 
 
 // error codes returned through the C-ABI are the SER_OK / SER_ERR_* macros of include/ser_head.h
 
-#define SER_CUDA_CHECK(expr)                                                         \
+#define SER_CUDA_CHECK(...)                                                          \
   do {                                                                               \
-    cudaError_t _e = (expr);                                                         \
+    cudaError_t _e = (__VA_ARGS__);                                                       \
     if (_e != cudaSuccess) {                                                         \
       ser::set_last_error(__FILE__, __LINE__, cudaGetErrorString(_e));               \
       return SER_ERR_CUDA;                                                      \
@@ -158,6 +158,40 @@ __device__ __forceinline__ float apply_gate(float v, float g, int mode) {
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A training step is ~100 dependent launches replayed as one CUDA graph; with a
+// plain kernel -> kernel edge the next grid is only scheduled after the previous one has drained and flushed, which
+// costs 2-4 us per boundary -- more than most of the small kernels of the classifier tail.  Every kernel of the library
+// therefore (1) runs its data-independent prologue (barrier init, tensor-memory allocation, descriptor prefetch, index
+// arithmetic), (2) executes pdl_wait() BEFORE its first global-memory access that can alias another kernel's output --
+// it returns once every prerequisite grid has completed and its writes are visible --, and (3) executes pdl_trigger()
+// right after, which lets the NEXT grid of the stream be scheduled as soon as SM resources allow and run its own
+// prologue up to its own pdl_wait().  Since a grid cannot complete before its wait has returned, completion stays
+// transitive: kernel N+2 never runs ahead of kernel N.  launch_pdl() attaches the launch attribute; kernels launched
+// without it (pdl_enabled() false: SER_PDL=0) see both instructions as no-ops.
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 
 // ---------------------------------------------------------------------------------
 // GEMM front end shared by both tiers.  C[M,N] = epilogue(alpha * op(A) op(B)^T)

@@ -12,6 +12,7 @@ namespace {
 template <typename T>
 __global__ void __launch_bounds__(256)
 dropout_apply_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ res, long long n8, DropSpec d) {
+  pdl_sync();
   const DropKey key = drop_key(d);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -35,6 +36,7 @@ dropout_apply_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __r
 template <typename T>
 __global__ void dropout_apply_tail_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ res,
                                           long long begin, long long n, DropSpec d) {
+  pdl_sync();
   const DropKey key = drop_key(d);
   const long long i = begin + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
@@ -44,6 +46,7 @@ __global__ void dropout_apply_tail_kernel(const T* __restrict__ in, T* __restric
 }
 
 __global__ void dropout_mask_kernel(float* __restrict__ out, long long rows, int cols, DropSpec d) {
+  pdl_sync();
   const DropKey key = d.on() ? drop_key(d) : DropKey{0u, 1u};      // p = 0: no seed to read, all ones
   const long long n = rows * cols;
   const unsigned half_cols = static_cast<unsigned>((cols + 1) / 2);
@@ -63,12 +66,12 @@ int apply_impl(const void* in, void* out, const void* res, long long n, const Dr
   const long long n8 = aligned ? n / 8 : 0;
   if (n8 > 0) {
     const int blocks = static_cast<int>(min(static_cast<long long>(device_sm_count()) * 8, (n8 + 255) / 256));
-    dropout_apply_kernel<T><<<blocks, 256, 0, s>>>(pi, po, pr, n8, d);
+    SER_CUDA_CHECK(launch_pdl(dropout_apply_kernel<T>, dim3(blocks), dim3(256), 0, s, pi, po, pr, n8, d));
     SER_LAUNCH_CHECK();
   }
   if (n8 * 8 < n) {
     const long long rem = n - n8 * 8;
-    dropout_apply_tail_kernel<T><<<ceil_div(rem, 256), 256, 0, s>>>(pi, po, pr, n8 * 8, n, d);
+    SER_CUDA_CHECK(launch_pdl(dropout_apply_tail_kernel<T>, dim3(ceil_div(rem, 256)), dim3(256), 0, s, pi, po, pr, n8 * 8, n, d));
     SER_LAUNCH_CHECK();
   }
   return SER_OK;
@@ -91,7 +94,7 @@ int dropout_mask(const DropSpec& d, long long rows, int cols, float* out, cudaSt
   SER_REQUIRE(rows * ((cols + 1) / 2) < (1LL << 32), "dropout: site too large for the 32-bit pair index");
   const long long n = rows * cols;
   const int blocks = static_cast<int>(min(static_cast<long long>(device_sm_count()) * 8, (n + 255) / 256));
-  dropout_mask_kernel<<<blocks, 256, 0, s>>>(out, rows, cols, d);
+  SER_CUDA_CHECK(launch_pdl(dropout_mask_kernel, dim3(blocks), dim3(256), 0, s, out, rows, cols, d));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

@@ -25,6 +25,7 @@ __device__ __forceinline__ void store8_dyn(void* p, size_t idx, int f32, const f
 
 __global__ void cast_kernel(const void* __restrict__ src, int src_f32, void* __restrict__ dst, int dst_f32,
                             long long n) {
+  pdl_sync();
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 8;
   for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
@@ -47,6 +48,7 @@ struct CastSegs {
 };
 __global__ void __launch_bounds__(256)
 cast_multi_kernel(const CastSegs segs) {
+  pdl_sync();
   const long long total = segs.end[segs.n - 1];
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -63,6 +65,7 @@ cast_multi_kernel(const CastSegs segs) {
 // kernels costs ~4 us of serialisation, a small kernel well under 2)
 __global__ void __launch_bounds__(256)
 zero_kernel(uint4* __restrict__ p, long long n16) {
+  pdl_sync();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     p[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -71,6 +74,7 @@ zero_kernel(uint4* __restrict__ p, long long n16) {
 // blockDim = (32, 8): x walks columns, y walks rows; grid = (ceil(N/32), row_splits)
 __global__ void colsum_kernel(const void* __restrict__ X, int x_f32, long long ld, int M, int N,
                               float* __restrict__ out) {
+  pdl_sync();
   __shared__ float red[8][33];
   const int n = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
@@ -95,6 +99,7 @@ __global__ void colsum_kernel(const void* __restrict__ X, int x_f32, long long l
 __global__ void __launch_bounds__(256)
 colsum_vec_kernel(const void* __restrict__ X0, int x_f32, long long ld, int M, int N, float* __restrict__ out0,
                   long long strideX, long long strideOut) {
+  pdl_sync();
   __shared__ float red[8][256 + 8];
   const void* X = x_f32 ? static_cast<const void*>(reinterpret_cast<const float*>(X0) + blockIdx.z * strideX)
                         : static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(X0) + blockIdx.z * strideX);
@@ -144,6 +149,7 @@ ln_fwd_kernel(const void* __restrict__ x, int x_f32, void* __restrict__ y, int y
               int y2_f32, const float* __restrict__ gamma, const float* __restrict__ beta,
               float* __restrict__ stats, int M, int N, int relu, const void* __restrict__ res, void* xout,
               DropSpec drop) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int nch = (N + 255) >> 8;
@@ -229,6 +235,7 @@ ln_bwd_dx_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict
                  const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                  const void* __restrict__ add, int add_f32, void* __restrict__ dx, int dx_f32, void* __restrict__ dx2,
                  int dx2_f32, int M, int N, int relu) {
+  pdl_sync();
   // gamma / beta live in shared memory (broadcast-free 128-bit reads) so a row costs only its own x and dy in
   // registers: <= 85 registers per thread keeps 24 warps per SM resident, which is what hides the HBM latency here
   __shared__ __align__(16) float sg[NCH * 256];
@@ -305,6 +312,7 @@ __global__ void __launch_bounds__(256)
 ln_bwd_param_kernel(const void* __restrict__ dy, int dy_f32, const void* __restrict__ x, int x_f32,
                     const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int N, int relu) {
+  pdl_sync();
   __shared__ float red[2][8][256 + 8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + lane * 8;
@@ -377,6 +385,7 @@ __global__ void __launch_bounds__(256)
 ln2_fwd_kernel(const float* __restrict__ h, float* __restrict__ y, void* __restrict__ n, int n_f32,
                const float* __restrict__ go, const float* __restrict__ bo, const float* __restrict__ gi,
                const float* __restrict__ bi, float* __restrict__ stats_o, float* __restrict__ stats_i, int M, int N) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nch = (N + 255) >> 8;
@@ -454,6 +463,7 @@ ln2_bwd_kernel(const float* __restrict__ dn, const float* __restrict__ dskip, co
                const float* __restrict__ bo, const float* __restrict__ gi, float* __restrict__ dh,
                void* __restrict__ dh2, int dh2_f32, float* __restrict__ dgi, float* __restrict__ dbi,
                float* __restrict__ dgo, float* __restrict__ dbo, int M, int N) {
+  pdl_sync();
   __shared__ float sacc[4][kMaxChunks * 256];
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -546,6 +556,7 @@ ln2_bwd_kernel(const float* __restrict__ dn, const float* __restrict__ dskip, co
 
 __global__ void sigmoid_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ ds,
                                    long long n) {
+  pdl_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) ds[i] = dy[i] * y[i] * (1.f - y[i]);
 }
@@ -563,7 +574,7 @@ int cast_any(const void* src, int src_f32, void* dst, int dst_f32, long long n, 
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   ProfScope prof("cast", 0.0, static_cast<double>(n) * ((src_f32 ? 4 : 2) + (dst_f32 ? 4 : 2)), s);
-  cast_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(src, src_f32, dst, dst_f32, n);
+  SER_CUDA_CHECK(launch_pdl(cast_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, s, src, src_f32, dst, dst_f32, n));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -576,7 +587,7 @@ int zero_async(void* p, size_t bytes, cudaStream_t s) {
   }
   const long long n16 = static_cast<long long>(bytes / 16);
   const int blocks = static_cast<int>(min(static_cast<long long>(device_sm_count()) * 4, (n16 + 255) / 256));
-  zero_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(p), n16);
+  SER_CUDA_CHECK(launch_pdl(zero_kernel, dim3(blocks), dim3(256), 0, s, reinterpret_cast<uint4*>(p), n16));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -598,7 +609,7 @@ int cast_multi(int n, const void* const* src, void* const* dst, const long long*
   segs.n = n;
   ProfScope prof("cast", 0.0, static_cast<double>(bytes), s);
   const int blocks = static_cast<int>(min(static_cast<long long>(device_sm_count()) * 8, (acc + 255) / 256));
-  cast_multi_kernel<<<blocks, 256, 0, s>>>(segs);
+  SER_CUDA_CHECK(launch_pdl(cast_multi_kernel, dim3(blocks), dim3(256), 0, s, segs));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -621,7 +632,7 @@ int colsum(const void* X, int x_f32, long long ld, int M, int N, float* out, cud
     if (gy > max_gy) gy = max_gy;
     if (gy < 1) gy = 1;
     if (gy > 1) SER_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * N, s));
-    colsum_vec_kernel<<<dim3(gx, gy, 1), 256, 0, s>>>(X, x_f32, ld, M, N, out, 0, 0);
+    SER_CUDA_CHECK(launch_pdl(colsum_vec_kernel, dim3(dim3(gx, gy, 1)), dim3(256), 0, s, X, x_f32, ld, M, N, out, 0, 0));
     SER_LAUNCH_CHECK();
     return SER_OK;
   }
@@ -631,7 +642,7 @@ int colsum(const void* X, int x_f32, long long ld, int M, int N, float* out, cud
   if (gy > max_gy) gy = max_gy;
   if (gy < 1) gy = 1;
   if (gy > 1) SER_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * N, s));
-  colsum_kernel<<<dim3(gx, gy), dim3(32, 8), 0, s>>>(X, x_f32, ld, M, N, out);
+  SER_CUDA_CHECK(launch_pdl(colsum_kernel, dim3(dim3(gx, gy)), dim3(dim3(32, 8)), 0, s, X, x_f32, ld, M, N, out));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -650,7 +661,7 @@ int colsum_batched(const void* X, int x_f32, long long ld, int M, int N, float* 
     else for (int b = 0; b < batch; ++b) SER_CUDA_CHECK(cudaMemsetAsync(out + b * strideOut, 0, sizeof(float) * N, s));
   }
   ProfScope prof("colsum_batched", 0.0, static_cast<double>(batch) * M * N * (x_f32 ? 4 : 2), s);
-  colsum_vec_kernel<<<dim3(gx, gy, batch), 256, 0, s>>>(X, x_f32, ld, M, N, out, strideX, strideOut);
+  SER_CUDA_CHECK(launch_pdl(colsum_vec_kernel, dim3(dim3(gx, gy, batch)), dim3(256), 0, s, X, x_f32, ld, M, N, out, strideX, strideOut));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -673,11 +684,11 @@ int layernorm_fwd(const void* x, int x_f32, void* y, int y_f32, void* y2, int y2
   // algorithmic bytes: x read, y (and its copy) written; with the residual-dropout prologue also res read and xout written
   ProfScope prof(pname, 0.0, static_cast<double>(M) * N * ((x_f32 ? 4 : 2) * (res ? 3 : 1) + (y_f32 ? 4 : 2) + (y2 ? (y2_f32 ? 4 : 2) : 0)), s);
   if (res != nullptr)
-    ln_fwd_kernel<true><<<ln_grid(M), 256, 0, s>>>(x, x_f32, y, y_f32, y2, y2_f32, gamma, beta, stats, M, N, relu, res, xout,
-                                                   drop != nullptr ? *drop : DropSpec{});
+    SER_CUDA_CHECK(launch_pdl(ln_fwd_kernel<true>, dim3(ln_grid(M)), dim3(256), 0, s, x, x_f32, y, y_f32, y2, y2_f32, gamma, beta, stats, M, N, relu, res, xout,
+                                                   drop != nullptr ? *drop : DropSpec{}));
   else
-    ln_fwd_kernel<false><<<ln_grid(M), 256, 0, s>>>(x, x_f32, y, y_f32, y2, y2_f32, gamma, beta, stats, M, N, relu, nullptr,
-                                                    nullptr, DropSpec{});
+    SER_CUDA_CHECK(launch_pdl(ln_fwd_kernel<false>, dim3(ln_grid(M)), dim3(256), 0, s, x, x_f32, y, y_f32, y2, y2_f32, gamma, beta, stats, M, N, relu, nullptr,
+                                                    nullptr, DropSpec{}));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -708,8 +719,8 @@ int layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const fl
   if (blocks < 1) blocks = 1;
   const int nch = ceil_div(N, 256);
 #define SER_LN_DX(NCH)                                                                                              \
-  ln_bwd_dx_kernel<NCH><<<blocks, 256, 0, s>>>(dy, dy_f32, x, x_f32, stats, gamma, beta, add, add_f32, dx, dx_f32,  \
-                                               dx2, dx2_f32, M, N, relu)
+  SER_CUDA_CHECK(launch_pdl(ln_bwd_dx_kernel<NCH>, dim3(blocks), dim3(256), 0, s, dy, dy_f32, x, x_f32, stats, gamma, beta, add, add_f32, dx, dx_f32,  \
+                                               dx2, dx2_f32, M, N, relu))
   if (nch == 1) SER_LN_DX(1); else if (nch == 2) SER_LN_DX(2); else if (nch == 3) SER_LN_DX(3); else SER_LN_DX(4);
 #undef SER_LN_DX
   SER_LAUNCH_CHECK();
@@ -719,7 +730,7 @@ int layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const fl
     const int max_gy = ceil_div(M, 64);
     if (gy > max_gy) gy = max_gy;
     if (gy < 1) gy = 1;
-    ln_bwd_param_kernel<<<dim3(gx, gy), 256, 0, s>>>(dy, dy_f32, x, x_f32, stats, gamma, beta, dgamma, dbeta, M, N, relu);
+    SER_CUDA_CHECK(launch_pdl(ln_bwd_param_kernel, dim3(dim3(gx, gy)), dim3(256), 0, s, dy, dy_f32, x, x_f32, stats, gamma, beta, dgamma, dbeta, M, N, relu));
     SER_LAUNCH_CHECK();
   }
   return SER_OK;
@@ -729,7 +740,7 @@ int layernorm2_fwd(const float* h, float* y, void* n, int n_f32, const float* go
                    const float* bi, float* stats_o, float* stats_i, int M, int N, cudaStream_t s) {
   SER_REQUIRE(N % 8 == 0 && N <= kMaxChunks * 256 && M > 0, "layernorm2: N must be a multiple of 8 and <= 1024");
   ProfScope prof("layernorm2_fwd", 0.0, static_cast<double>(M) * N * (8 + (n_f32 ? 4 : 2)), s);
-  ln2_fwd_kernel<<<ln_grid(M), 256, 0, s>>>(h, y, n, n_f32, go, bo, gi, bi, stats_o, stats_i, M, N);
+  SER_CUDA_CHECK(launch_pdl(ln2_fwd_kernel, dim3(ln_grid(M)), dim3(256), 0, s, h, y, n, n_f32, go, bo, gi, bi, stats_o, stats_i, M, N));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -742,14 +753,14 @@ int layernorm2_bwd(const float* dn, const float* dskip, const float* h, const fl
   const int cap = 2 * device_sm_count();
   if (blocks > cap) blocks = cap;
   ProfScope prof("layernorm2_bwd", 0.0, static_cast<double>(M) * N * (16 + (dh2 ? (dh2_f32 ? 4 : 2) : 0)), s);
-  ln2_bwd_kernel<<<blocks, 256, 0, s>>>(dn, dskip, h, stats_o, stats_i, go, bo, gi, dh, dh2, dh2_f32, dgi, dbi, dgo, dbo, M, N);
+  SER_CUDA_CHECK(launch_pdl(ln2_bwd_kernel, dim3(blocks), dim3(256), 0, s, dn, dskip, h, stats_o, stats_i, go, bo, gi, dh, dh2, dh2_f32, dgi, dbi, dgo, dbo, M, N));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
 
 int sigmoid_bwd(const float* dy, const float* y, float* ds, long long n, cudaStream_t s) {
   if (n <= 0) return SER_OK;
-  sigmoid_bwd_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, s>>>(dy, y, ds, n);
+  SER_CUDA_CHECK(launch_pdl(sigmoid_bwd_kernel, dim3(static_cast<int>((n + 255) / 256)), dim3(256), 0, s, dy, y, ds, n));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

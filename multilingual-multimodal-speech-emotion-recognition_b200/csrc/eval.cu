@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256)
 openmax_kernel(const float* __restrict__ feats, const float* __restrict__ logits, const float* __restrict__ av,
                const float* __restrict__ w_alpha, const float* __restrict__ w_beta, const float* __restrict__ w_tau,
                float* __restrict__ out, int B, int C, int F) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -37,6 +38,7 @@ openmax_kernel(const float* __restrict__ feats, const float* __restrict__ logits
 __global__ void __launch_bounds__(256)
 eval_post_kernel(const float* __restrict__ lv, int V, int B, int C, float temperature, float* __restrict__ mean_logits,
                  float* __restrict__ probs, long long* __restrict__ preds, float* __restrict__ energy) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -71,6 +73,7 @@ eval_post_kernel(const float* __restrict__ lv, int V, int B, int C, float temper
 __global__ void __launch_bounds__(256)
 temp_sweep_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, int B, int C,
                   const float* __restrict__ temps, float* __restrict__ err) {
+  pdl_sync();
   __shared__ float acc;
   if (threadIdx.x == 0) acc = 0.f;
   __syncthreads();
@@ -103,6 +106,7 @@ late_ood_kernel(const float* __restrict__ logits, const void* __restrict__ feats
                 const float* __restrict__ protos, const float* __restrict__ cov, const float* __restrict__ temperature,
                 const float* __restrict__ mix, float* __restrict__ distances, float* __restrict__ scores, int B, int C,
                 int D) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -142,8 +146,8 @@ int late_ood(const float* logits, const void* feats, int feats_f32, const float*
   SER_REQUIRE(B > 0 && C > 0 && C <= kMaxC && D > 0, "late_ood: bad shape (num_classes <= 32)");
   SER_REQUIRE(logits && feats && prototypes && covariances && temperature && mix && distances && scores,
               "late_ood: null tensor");
-  late_ood_kernel<<<ceil_div(B, 8), 256, 0, s>>>(logits, feats, feats_f32, prototypes, covariances, temperature, mix,
-                                                  distances, scores, B, C, D);
+  SER_CUDA_CHECK(launch_pdl(late_ood_kernel, dim3(ceil_div(B, 8)), dim3(256), 0, s, logits, feats, feats_f32, prototypes, covariances, temperature, mix,
+                                                  distances, scores, B, C, D));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -151,7 +155,7 @@ int late_ood(const float* logits, const void* feats, int feats_f32, const float*
 int openmax_fwd(const float* feats, const float* logits, const float* act_vecs, const float* w_alpha,
                 const float* w_beta, const float* w_tau, float* out, int B, int C, int F, cudaStream_t s) {
   SER_REQUIRE(C <= kMaxC && B > 0, "openmax: num_classes <= 32");
-  openmax_kernel<<<ceil_div(B, 8), 256, 0, s>>>(feats, logits, act_vecs, w_alpha, w_beta, w_tau, out, B, C, F);
+  SER_CUDA_CHECK(launch_pdl(openmax_kernel, dim3(ceil_div(B, 8)), dim3(256), 0, s, feats, logits, act_vecs, w_alpha, w_beta, w_tau, out, B, C, F));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -159,7 +163,7 @@ int openmax_fwd(const float* feats, const float* logits, const float* act_vecs, 
 int eval_post(const float* logits_views, int V, int B, int C, float temperature, float* mean_logits, float* probs,
               long long* preds, float* energy, cudaStream_t s) {
   SER_REQUIRE(C <= kMaxC && B > 0 && V > 0, "eval_post: bad shape");
-  eval_post_kernel<<<ceil_div(B, 8), 256, 0, s>>>(logits_views, V, B, C, temperature, mean_logits, probs, preds, energy);
+  SER_CUDA_CHECK(launch_pdl(eval_post_kernel, dim3(ceil_div(B, 8)), dim3(256), 0, s, logits_views, V, B, C, temperature, mean_logits, probs, preds, energy));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -168,7 +172,7 @@ int temperature_sweep(const float* logits, const long long* labels, int B, int C
                       float* err, cudaStream_t s) {
   SER_REQUIRE(C <= kMaxC && B > 0 && nT > 0, "temperature_sweep: bad shape");
   SER_CUDA_CHECK(cudaMemsetAsync(err, 0, sizeof(float) * nT, s));
-  temp_sweep_kernel<<<dim3(ceil_div(B, 8), nT), 256, 0, s>>>(logits, labels, B, C, temps, err);
+  SER_CUDA_CHECK(launch_pdl(temp_sweep_kernel, dim3(dim3(ceil_div(B, 8), nT)), dim3(256), 0, s, logits, labels, B, C, temps, err));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

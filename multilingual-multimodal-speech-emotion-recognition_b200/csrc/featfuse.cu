@@ -22,6 +22,7 @@ namespace {
 template <typename TD>
 __global__ void __launch_bounds__(256)
 copy2d_kernel(const float* __restrict__ src, long long lds, TD* __restrict__ dst, long long ldd, int rows, int cols4) {
+  pdl_sync();
   const long long n = static_cast<long long>(rows) * cols4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -36,7 +37,7 @@ template <typename TD>
 int copy2d(const float* src, long long lds, TD* dst, long long ldd, int rows, int cols, cudaStream_t s) {
   const long long n = static_cast<long long>(rows) * (cols / 4);
   const int blocks = static_cast<int>(min(static_cast<long long>(device_sm_count()) * 4, (n + 255) / 256));
-  copy2d_kernel<TD><<<blocks, 256, 0, s>>>(src, lds, dst, ldd, rows, cols / 4);
+  SER_CUDA_CHECK(launch_pdl(copy2d_kernel<TD>, dim3(blocks), dim3(256), 0, s, src, lds, dst, ldd, rows, cols / 4));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -47,6 +48,7 @@ template <typename T, bool DROP>
 __global__ void __launch_bounds__(256)
 bias_relu_drop_kernel(T* __restrict__ y, const float* __restrict__ c, unsigned n8, unsigned cols8, unsigned frames,
                       DropSpec d) {
+  pdl_sync();
   DropKey key{0u, 1u};
   if (DROP) key = drop_key(d);
   const unsigned stride = gridDim.x * blockDim.x;
@@ -73,6 +75,7 @@ bias_relu_drop_kernel(T* __restrict__ y, const float* __restrict__ c, unsigned n
 template <typename T>
 __global__ void __launch_bounds__(256)
 relu_keep_gate_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dz, long long n8, float scale) {
+  pdl_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float g[8], v[8];
@@ -128,10 +131,10 @@ int featfuse_fwd(const ser_featfuse_desc& d, cudaStream_t s) {
   const unsigned frames = static_cast<unsigned>(d.T), cols8 = static_cast<unsigned>(D / 8);
 #define SER_FF_EPI(TY_)                                                                                             \
   do {                                                                                                              \
-    if (drop.on()) bias_relu_drop_kernel<TY_, true><<<stream_grid(n8), 256, 0, s>>>(reinterpret_cast<TY_*>(d.y),    \
-                                                                                     d.c, n8, cols8, frames, drop);  \
-    else bias_relu_drop_kernel<TY_, false><<<stream_grid(n8), 256, 0, s>>>(reinterpret_cast<TY_*>(d.y), d.c, n8,    \
-                                                                           cols8, frames, drop);                    \
+    if (drop.on()) SER_CUDA_CHECK(launch_pdl(bias_relu_drop_kernel<TY_, true>, dim3(stream_grid(n8)), dim3(256), 0, s, reinterpret_cast<TY_*>(d.y),    \
+                                                                                     d.c, n8, cols8, frames, drop));  \
+    else SER_CUDA_CHECK(launch_pdl(bias_relu_drop_kernel<TY_, false>, dim3(stream_grid(n8)), dim3(256), 0, s, reinterpret_cast<TY_*>(d.y), d.c, n8,    \
+                                                                           cols8, frames, drop));                    \
   } while (0)
   if (f) SER_FF_EPI(float); else SER_FF_EPI(__nv_bfloat16);
 #undef SER_FF_EPI
@@ -151,11 +154,9 @@ int featfuse_bwd(const ser_featfuse_desc& d, cudaStream_t s) {
   {
     const long long n8 = static_cast<long long>(M) * D / 8;
     ProfScope prof("featfuse_gate", 0.0, static_cast<double>(M) * D * (f ? 12.0 : 6.0), s);
-    if (f) relu_keep_gate_kernel<float><<<stream_grid(n8), 256, 0, s>>>(
-        reinterpret_cast<const float*>(d.dy), reinterpret_cast<const float*>(d.y), reinterpret_cast<float*>(d.dz), n8, drop.scale);
-    else relu_keep_gate_kernel<__nv_bfloat16><<<stream_grid(n8), 256, 0, s>>>(
-        reinterpret_cast<const __nv_bfloat16*>(d.dy), reinterpret_cast<const __nv_bfloat16*>(d.y),
-        reinterpret_cast<__nv_bfloat16*>(d.dz), n8, drop.scale);
+    if (f) SER_CUDA_CHECK(launch_pdl(relu_keep_gate_kernel<float>, dim3(stream_grid(n8)), dim3(256), 0, s, reinterpret_cast<const float*>(d.dy), reinterpret_cast<const float*>(d.y), reinterpret_cast<float*>(d.dz), n8, drop.scale));
+    else SER_CUDA_CHECK(launch_pdl(relu_keep_gate_kernel<__nv_bfloat16>, dim3(stream_grid(n8)), dim3(256), 0, s, reinterpret_cast<const __nv_bfloat16*>(d.dy), reinterpret_cast<const __nv_bfloat16*>(d.y),
+        reinterpret_cast<__nv_bfloat16*>(d.dz), n8, drop.scale));
     SER_LAUNCH_CHECK();
   }
 

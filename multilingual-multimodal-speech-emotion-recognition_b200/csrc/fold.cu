@@ -19,6 +19,7 @@ typedef __nv_bfloat16 bf16;
 // audio tokens pass through attn_a's q rows and attn_t's k, v rows; text tokens the other way round.
 __global__ void fold_assemble_kernel(const bf16* __restrict__ win_a, const bf16* __restrict__ win_t,
                                      bf16* __restrict__ wbd_a, bf16* __restrict__ wbd_t, int S) {
+  pdl_sync();
   const int S3 = 3 * S;
   const int mod = blockIdx.y;                    // 0 audio, 1 text
   const int r = blockIdx.x;
@@ -41,6 +42,7 @@ __global__ void fold_bias_fwd_kernel(const bf16* __restrict__ win_a, const bf16*
                                      const float* __restrict__ bout_a, const float* __restrict__ bout_t,
                                      float* __restrict__ bc_a, float* __restrict__ bc_t, float* __restrict__ bz_a,
                                      float* __restrict__ bz_t, int S, int D) {
+  pdl_sync();
   const int S3 = 3 * S;
   const int lane = threadIdx.x & 31;
   const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // [0, 2*3S + 2*D)
@@ -72,6 +74,7 @@ __global__ void fold_in_bwd_rows_kernel(const float* __restrict__ dwbd_a, const 
                                         const float* __restrict__ bqkv_a, const float* __restrict__ bqkv_t,
                                         float* __restrict__ dwin_a, float* __restrict__ dwin_t,
                                         float* __restrict__ dbin_a, float* __restrict__ dbin_t, int S) {
+  pdl_sync();
   const int S3 = 3 * S;
   const int mod = blockIdx.y, r = blockIdx.x, b = r / S;
   const bool use_a = ((b == 0) == (mod == 0));
@@ -93,6 +96,7 @@ fold_bias_bwd_cols_kernel(const bf16* __restrict__ win_a, const bf16* __restrict
                           const float* __restrict__ dbz_a, const float* __restrict__ dbz_t,
                           float* __restrict__ dbqkv_a, float* __restrict__ dbqkv_t,
                           float* __restrict__ dbo_a, float* __restrict__ dbo_t, int S, int D) {
+  pdl_sync();
   __shared__ float red[8][33];
   const int S3 = 3 * S;
   const int mod = blockIdx.y;
@@ -129,6 +133,7 @@ __global__ void fold_out_bwd_rows_kernel(const float* __restrict__ dbz_a, const 
                                          const float* __restrict__ bo_a, const float* __restrict__ bo_t,
                                          float* __restrict__ dwout_a, float* __restrict__ dwout_t,
                                          float* __restrict__ dbout_a, float* __restrict__ dbout_t, int S) {
+  pdl_sync();
   const int mod = blockIdx.y, r = blockIdx.x;
   const float g = (mod == 0 ? dbz_a : dbz_t)[r];
   const float* bo = (mod == 0 ? bo_a : bo_t);
@@ -141,8 +146,8 @@ __global__ void fold_out_bwd_rows_kernel(const float* __restrict__ dbz_a, const 
 
 int fold_assemble(const void* win_a, const void* win_t, void* wbd_a, void* wbd_t, int S, cudaStream_t s) {
   ProfScope prof("fold_glue", 0.0, 2.0 * 9.0 * S * S * 2.0, s);
-  fold_assemble_kernel<<<dim3(3 * S, 2), 256, 0, s>>>(reinterpret_cast<const bf16*>(win_a), reinterpret_cast<const bf16*>(win_t),
-                                                      reinterpret_cast<bf16*>(wbd_a), reinterpret_cast<bf16*>(wbd_t), S);
+  SER_CUDA_CHECK(launch_pdl(fold_assemble_kernel, dim3(dim3(3 * S, 2)), dim3(256), 0, s, reinterpret_cast<const bf16*>(win_a), reinterpret_cast<const bf16*>(win_t),
+                                                      reinterpret_cast<bf16*>(wbd_a), reinterpret_cast<bf16*>(wbd_t), S));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -150,26 +155,24 @@ int fold_assemble(const void* win_a, const void* win_t, void* wbd_a, void* wbd_t
 int fold_bias_fwd(const FoldBiasArgs& a, cudaStream_t s) {
   ProfScope prof("fold_glue", 0.0, 0.0, s);
   const int outs = 2 * 3 * a.S + 2 * a.D;
-  fold_bias_fwd_kernel<<<ceil_div(outs, 8), 256, 0, s>>>(
-      reinterpret_cast<const bf16*>(a.win_a), reinterpret_cast<const bf16*>(a.win_t), a.bin_a, a.bin_t, a.bqkv_a, a.bqkv_t,
+  SER_CUDA_CHECK(launch_pdl(fold_bias_fwd_kernel, dim3(ceil_div(outs, 8)), dim3(256), 0, s, reinterpret_cast<const bf16*>(a.win_a), reinterpret_cast<const bf16*>(a.win_t), a.bin_a, a.bin_t, a.bqkv_a, a.bqkv_t,
       reinterpret_cast<const bf16*>(a.wout_a), reinterpret_cast<const bf16*>(a.wout_t), a.bo_a, a.bo_t, a.bout_a, a.bout_t,
-      a.bc_a, a.bc_t, a.bz_a, a.bz_t, a.S, a.D);
+      a.bc_a, a.bc_t, a.bz_a, a.bz_t, a.S, a.D));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
 
 int fold_bwd_glue(const FoldBwdArgs& a, cudaStream_t s) {
   ProfScope prof("fold_glue", 0.0, 0.0, s);
-  fold_in_bwd_rows_kernel<<<dim3(3 * a.S, 2), 256, 0, s>>>(a.dwbd_a, a.dwbd_t, a.dbc_a, a.dbc_t, a.bqkv_a, a.bqkv_t, a.dwin_a,
-                                                           a.dwin_t, a.dbin_a, a.dbin_t, a.S);
+  SER_CUDA_CHECK(launch_pdl(fold_in_bwd_rows_kernel, dim3(dim3(3 * a.S, 2)), dim3(256), 0, s, a.dwbd_a, a.dwbd_t, a.dbc_a, a.dbc_t, a.bqkv_a, a.bqkv_t, a.dwin_a,
+                                                           a.dwin_t, a.dbin_a, a.dbin_t, a.S));
   SER_LAUNCH_CHECK();
-  fold_bias_bwd_cols_kernel<<<dim3(ceil_div(4 * a.S, 32), 2), 256, 0, s>>>(
-      reinterpret_cast<const bf16*>(a.win_a), reinterpret_cast<const bf16*>(a.win_t), reinterpret_cast<const bf16*>(a.wout_a),
+  SER_CUDA_CHECK(launch_pdl(fold_bias_bwd_cols_kernel, dim3(dim3(ceil_div(4 * a.S, 32), 2)), dim3(256), 0, s, reinterpret_cast<const bf16*>(a.win_a), reinterpret_cast<const bf16*>(a.win_t), reinterpret_cast<const bf16*>(a.wout_a),
       reinterpret_cast<const bf16*>(a.wout_t), a.dbc_a, a.dbc_t, a.dbz_a, a.dbz_t, a.dbqkv_a, a.dbqkv_t, a.dbo_a, a.dbo_t,
-      a.S, a.D);
+      a.S, a.D));
   SER_LAUNCH_CHECK();
-  fold_out_bwd_rows_kernel<<<dim3(a.D, 2), 256, 0, s>>>(a.dbz_a, a.dbz_t, a.bo_a, a.bo_t, a.dwout_a, a.dwout_t, a.dbout_a,
-                                                        a.dbout_t, a.S);
+  SER_CUDA_CHECK(launch_pdl(fold_out_bwd_rows_kernel, dim3(dim3(a.D, 2)), dim3(256), 0, s, a.dbz_a, a.dbz_t, a.bo_a, a.bo_t, a.dwout_a, a.dwout_t, a.dbout_a,
+                                                        a.dbout_t, a.S));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

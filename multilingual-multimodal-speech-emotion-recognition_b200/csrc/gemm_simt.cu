@@ -28,6 +28,7 @@ template <bool A_KCONT, bool B_KCONT>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ B,
                  long long sbn, long long sbk, SimtEpilogue ep, int M, int N, int K, int splits) {
+  pdl_sync();
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -175,13 +176,13 @@ int gemm_simt_f32(const GemmArgs& a0, cudaStream_t stream) {
   ProfScope prof(a.a_trans ? "gemm_simt_wgrad" : (a.b_trans ? "gemm_simt_dgrad" : "gemm_simt_fwd"), gflops, gbytes, stream);
   dim3 grid(nt, mt, splits);
   if (!a.a_trans && !a.b_trans)
-    gemm_simt_kernel<true, true><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, ep, a.M, a.N, a.K, splits);
+    SER_CUDA_CHECK(launch_pdl(gemm_simt_kernel<true, true>, dim3(grid), dim3(256), 0, stream, A, sam, sak, B, sbn, sbk, ep, a.M, a.N, a.K, splits));
   else if (!a.a_trans && a.b_trans)
-    gemm_simt_kernel<true, false><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, ep, a.M, a.N, a.K, splits);
+    SER_CUDA_CHECK(launch_pdl(gemm_simt_kernel<true, false>, dim3(grid), dim3(256), 0, stream, A, sam, sak, B, sbn, sbk, ep, a.M, a.N, a.K, splits));
   else if (a.a_trans && a.b_trans)
-    gemm_simt_kernel<false, false><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, ep, a.M, a.N, a.K, splits);
+    SER_CUDA_CHECK(launch_pdl(gemm_simt_kernel<false, false>, dim3(grid), dim3(256), 0, stream, A, sam, sak, B, sbn, sbk, ep, a.M, a.N, a.K, splits));
   else
-    gemm_simt_kernel<false, true><<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, ep, a.M, a.N, a.K, splits);
+    SER_CUDA_CHECK(launch_pdl(gemm_simt_kernel<false, true>, dim3(grid), dim3(256), 0, stream, A, sam, sak, B, sbn, sbk, ep, a.M, a.N, a.K, splits));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

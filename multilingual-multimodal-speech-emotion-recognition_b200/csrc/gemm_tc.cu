@@ -300,6 +300,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   if (PAIR) cluster_sync();       // the peer's barriers exist before anything is multicast to them
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();                     // everything above is independent of the previous kernel's output
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -541,7 +542,8 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   if (!PAIR) {
     const long long total = static_cast<long long>(m_tiles) * n_tiles * splits * batch;
     const int grid = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
-    kern<<<grid, kThreads, smem_bytes, stream>>>(tmA, tmB, tmC, tmS, ep, M, N, K, splits, batch, nstages);
+    SER_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, tmC, tmS, ep, M, N, K, splits,
+                              batch, nstages));
   } else {
     const long long units = static_cast<long long>(m_tiles / 2) * n_tiles * splits * batch;
     const long long max_clusters = device_sm_count() / 2;
@@ -551,10 +553,12 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     SER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmS, ep, M, N, K, splits, batch, nstages));
   }
   SER_LAUNCH_CHECK();

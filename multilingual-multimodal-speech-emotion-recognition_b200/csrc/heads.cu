@@ -16,6 +16,7 @@ heads_fwd_kernel(const float* __restrict__ f, const float* __restrict__ w_c, con
                  const float* __restrict__ w_u1, const float* __restrict__ b_u1, const float* __restrict__ w_u2,
                  const float* __restrict__ b_u2, float* __restrict__ logits, float* __restrict__ u1,
                  float* __restrict__ unc, int F, int C, int U, DropSpec drop) {
+  pdl_sync();
   extern __shared__ __align__(16) float sm[];
   float* sf = sm;            // [F]
   float* su = sm + F;        // [U]
@@ -60,6 +61,7 @@ heads_bwd_rows_kernel(const float* __restrict__ dlogits, const float* __restrict
                       const float* __restrict__ u1, const float* __restrict__ w_c, const float* __restrict__ w_u1,
                       const float* __restrict__ w_u2, float* __restrict__ df, float* __restrict__ du1,
                       float* __restrict__ dsg, int F, int C, int U, float uscale) {
+  pdl_sync();
   extern __shared__ float sg[];       // [C + U]
   const int row = blockIdx.x;
   const bool have_u = (dunc != nullptr) && (unc != nullptr);
@@ -97,6 +99,7 @@ heads_bwd_w_kernel(const float* __restrict__ dlogits, const float* __restrict__ 
                    const float* __restrict__ f, const float* __restrict__ u1, float* __restrict__ dw_c,
                    float* __restrict__ db_c, float* __restrict__ dw_u1, float* __restrict__ db_u1,
                    float* __restrict__ dw_u2, float* __restrict__ db_u2, int B, int F, int C, int U) {
+  pdl_sync();
   __shared__ float sgr[256];
   __shared__ float red[32];
   const int o = blockIdx.x;
@@ -157,7 +160,7 @@ int heads_fwd(const float* f, const float* w_c, const float* b_c, const float* w
               const DropSpec& drop, cudaStream_t s) {
   SER_REQUIRE(B > 0 && F % 4 == 0 && F <= 4096 && C > 0 && U > 0 && U <= 1024, "heads_fwd: unsupported shape");
   ProfScope prof("heads_fwd", 2.0 * B * F * (C + U), 4.0 * (static_cast<double>(B) * F + (C + U) * F), s);
-  heads_fwd_kernel<<<B, 128, sizeof(float) * (F + U), s>>>(f, w_c, b_c, w_u1, b_u1, w_u2, b_u2, logits, u1, unc, F, C, U, drop);
+  SER_CUDA_CHECK(launch_pdl(heads_fwd_kernel, dim3(B), dim3(128), sizeof(float) * (F + U), s, f, w_c, b_c, w_u1, b_u1, w_u2, b_u2, logits, u1, unc, F, C, U, drop));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -168,10 +171,10 @@ int heads_bwd(const float* dlogits, const float* dunc, const float* unc, const f
               const DropSpec& drop, cudaStream_t s) {
   SER_REQUIRE(B > 0 && F <= 1024 && U <= 1024 && C > 0, "heads_bwd: unsupported shape");
   ProfScope prof("heads_bwd", 4.0 * B * F * (C + U), 4.0 * (2.0 * B * F + 2.0 * (C + U) * F), s);
-  heads_bwd_rows_kernel<<<B, 256, sizeof(float) * (C + U), s>>>(dlogits, dunc, unc, u1, w_c, w_u1, w_u2, df, du1, dsg,
-                                                              F, C, U, drop.on() ? drop.scale : 1.f);
+  SER_CUDA_CHECK(launch_pdl(heads_bwd_rows_kernel, dim3(B), dim3(256), sizeof(float) * (C + U), s, dlogits, dunc, unc, u1, w_c, w_u1, w_u2, df, du1, dsg,
+                                                              F, C, U, drop.on() ? drop.scale : 1.f));
   SER_LAUNCH_CHECK();
-  heads_bwd_w_kernel<<<C + U + 1, 256, 0, s>>>(dlogits, du1, dsg, f, u1, dw_c, db_c, dw_u1, db_u1, dw_u2, db_u2, B, F, C, U);
+  SER_CUDA_CHECK(launch_pdl(heads_bwd_w_kernel, dim3(C + U + 1), dim3(256), 0, s, dlogits, du1, dsg, f, u1, dw_c, db_c, dw_u1, db_u1, dw_u2, db_u2, B, F, C, U));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

@@ -40,6 +40,7 @@ ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     const float* __restrict__ stats, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
                     __nv_bfloat16* __restrict__ dxm, DropSpec drop, float* __restrict__ dgamma,
                     float* __restrict__ dbeta, int M) {
+  pdl_sync();
   constexpr int N = NCH * 256;
   __shared__ __align__(16) float sg[N];
   __shared__ __align__(16) float red[kWarps][N];
@@ -176,10 +177,10 @@ int layernorm_bwd_fused(const void* dy, const void* x, const float* stats, const
   __nv_bfloat16* pdm = reinterpret_cast<__nv_bfloat16*>(dxm);
 #define SER_LN_FUSED(NCH)                                                                                              \
   do {                                                                                                                 \
-    if (masked) ln_bwd_fused_kernel<NCH, true><<<blocks, kWarps * 32, 0, s>>>(pdy, px, stats, gamma, pdx, pdm, drop,   \
-                                                                              dgamma, dbeta, M);                       \
-    else ln_bwd_fused_kernel<NCH, false><<<blocks, kWarps * 32, 0, s>>>(pdy, px, stats, gamma, pdx, pdm, drop, dgamma, \
-                                                                        dbeta, M);                                     \
+    if (masked) SER_CUDA_CHECK(launch_pdl(ln_bwd_fused_kernel<NCH, true>, dim3(blocks), dim3(kWarps * 32), 0, s, pdy, px, stats, gamma, pdx, pdm, drop,   \
+                                                                              dgamma, dbeta, M));                       \
+    else SER_CUDA_CHECK(launch_pdl(ln_bwd_fused_kernel<NCH, false>, dim3(blocks), dim3(kWarps * 32), 0, s, pdy, px, stats, gamma, pdx, pdm, drop, dgamma, \
+                                                                        dbeta, M));                                     \
   } while (0)
   if (N == 256) SER_LN_FUSED(1); else if (N == 512) SER_LN_FUSED(2); else SER_LN_FUSED(3);
 #undef SER_LN_FUSED

@@ -18,6 +18,7 @@ constexpr int kMaxC = 32;
 __global__ void loss_prep_kernel(const long long* __restrict__ labels, const float* __restrict__ counts_in, int B,
                                  int C, float beta, int use_weights, float* __restrict__ class_w,
                                  float* __restrict__ sums) {
+  pdl_sync();
   __shared__ float cnt[kMaxC];
   __shared__ float w[kMaxC];
   if (threadIdx.x < kMaxC) cnt[threadIdx.x] = 0.f;
@@ -90,6 +91,7 @@ __device__ __forceinline__ int row_argmax(const float* __restrict__ logits, int 
 
 __global__ void __launch_bounds__(256)
 loss_rows_kernel(LossArgs a) {
+  pdl_sync();
   __shared__ float acc[LS_COUNT];
   if (threadIdx.x < LS_COUNT) acc[threadIdx.x] = 0.f;
   __syncthreads();
@@ -148,6 +150,7 @@ loss_rows_kernel(LossArgs a) {
 
 __global__ void __launch_bounds__(256)
 loss_bwd_kernel(LossArgs a, const float* __restrict__ gscale, int stage_dprotos) {
+  pdl_sync();
   // prototype gradients of the CTA's 8 samples are summed in shared memory first ([C, D] floats, when that fits): one
   // global atomic per (class, column) and CTA instead of one per sample -- B-way contention on C*D addresses otherwise
   extern __shared__ float sdp[];
@@ -259,9 +262,9 @@ int loss_fwd(const LossArgs& a, cudaStream_t s) {
   SER_REQUIRE(a.C >= 2 && a.C <= kMaxC, "loss: 2 <= num_classes <= 32");
   SER_REQUIRE(a.B > 0, "loss: empty batch");
   ProfScope prof("loss_fwd", 0.0, 4.0 * a.B * (a.C + (a.emb ? a.D : 0)), s);
-  loss_prep_kernel<<<1, 256, 0, s>>>(a.labels, a.counts, a.B, a.C, a.beta, a.focal_use_weights, a.class_w, a.sums);
+  SER_CUDA_CHECK(launch_pdl(loss_prep_kernel, dim3(1), dim3(256), 0, s, a.labels, a.counts, a.B, a.C, a.beta, a.focal_use_weights, a.class_w, a.sums));
   SER_LAUNCH_CHECK();
-  loss_rows_kernel<<<ceil_div(a.B, 8), 256, 0, s>>>(a);
+  SER_CUDA_CHECK(launch_pdl(loss_rows_kernel, dim3(ceil_div(a.B, 8)), dim3(256), 0, s, a));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -271,7 +274,7 @@ int loss_bwd_scaled(const LossArgs& a, const float* gscale, cudaStream_t s) {
   ProfScope prof("loss_bwd", 0.0, 4.0 * a.B * (2.0 * a.C + (a.emb ? 2.0 * a.D : 0)), s);
   const size_t stage_bytes = sizeof(float) * static_cast<size_t>(a.C) * (a.emb ? a.D : 0);
   const int stage = (a.dprotos != nullptr && stage_bytes > 0 && stage_bytes <= 40 * 1024) ? 1 : 0;
-  loss_bwd_kernel<<<ceil_div(a.B, 8), 256, stage ? stage_bytes : 0, s>>>(a, gscale, stage);
+  SER_CUDA_CHECK(launch_pdl(loss_bwd_kernel, dim3(ceil_div(a.B, 8)), dim3(256), stage ? stage_bytes : 0, s, a, gscale, stage));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -284,6 +287,7 @@ namespace {
 __global__ void loss_finalize_kernel(const float* __restrict__ sums, long long B_global, float margin, float w_ce,
                                      float w_focal, float w_unc, float w_proto, int have_proto,
                                      float* __restrict__ terms) {
+  pdl_sync();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float invB = 1.f / static_cast<float>(B_global);
   float ce = sums[LS_CE] * invB;
@@ -302,7 +306,7 @@ __global__ void loss_finalize_kernel(const float* __restrict__ sums, long long B
 
 int loss_finalize(const float* sums, long long B_global, float margin, float w_ce, float w_focal, float w_unc,
                   float w_proto, int have_proto, float* terms, cudaStream_t s) {
-  loss_finalize_kernel<<<1, 32, 0, s>>>(sums, B_global, margin, w_ce, w_focal, w_unc, w_proto, have_proto, terms);
+  SER_CUDA_CHECK(launch_pdl(loss_finalize_kernel, dim3(1), dim3(32), 0, s, sums, B_global, margin, w_ce, w_focal, w_unc, w_proto, have_proto, terms));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

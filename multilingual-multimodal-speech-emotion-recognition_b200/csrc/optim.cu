@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256)
 adamw_multi_kernel(const AdamSegs s, float lr, float b1, float b2, float eps, float wd, float bc1, float rsqrt_bc2,
                    const float* __restrict__ gscale, const float* __restrict__ grad_scale,
                    const float* __restrict__ found_inf, const float* __restrict__ step_dev) {
+  pdl_sync();
   if (found_inf != nullptr && found_inf[0] != 0.f) return;
   const long long total = s.end[s.n - 1];
   float gs = gscale != nullptr ? gscale[0] : 1.f;      // e.g. the clip coefficient of clip_grad_norm
@@ -90,6 +91,7 @@ struct NormSegs { const float* g[kSegs]; long long end[kSegs]; long long len[kSe
 // out[0] += sum of squares of all gradient elements (caller zeroes out)
 __global__ void __launch_bounds__(256)
 sumsq_multi_kernel(const NormSegs s, float* __restrict__ out) {
+  pdl_sync();
   __shared__ float red[32];
   const long long total = s.end[s.n - 1];
   float acc = 0.f;
@@ -113,6 +115,7 @@ sumsq_multi_kernel(const NormSegs s, float* __restrict__ out) {
 
 // coef[0] = min(1, max_norm / (sqrt(sumsq) + 1e-6)) -- torch.nn.utils.clip_grad_norm_; norm_out[0] = sqrt(sumsq)
 __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ coef, float* __restrict__ norm_out) {
+  pdl_sync();
   const float nrm = sqrtf(sumsq[0]);
   const float c = max_norm / (nrm + 1e-6f);
   coef[0] = c < 1.f ? c : 1.f;
@@ -144,8 +147,8 @@ int adamw_multi(int n, float* const* p, const float* const* g, float* const* m, 
     segs.n = cnt;
     ProfScope prof("adamw", 12.0 * elems, 28.0 * elems, s);
     const int blocks = static_cast<int>(min(static_cast<long long>(device_sm_count()) * 8, (acc + 255) / 256));
-    adamw_multi_kernel<<<blocks, 256, 0, s>>>(segs, lr, beta1, beta2, eps, weight_decay, bc1, rsqrt_bc2, gscale, grad_scale,
-                                              found_inf, step_dev);
+    SER_CUDA_CHECK(launch_pdl(adamw_multi_kernel, dim3(blocks), dim3(256), 0, s, segs, lr, beta1, beta2, eps, weight_decay, bc1, rsqrt_bc2, gscale, grad_scale,
+                                              found_inf, step_dev));
     SER_LAUNCH_CHECK();
   }
   return SER_OK;
@@ -169,10 +172,10 @@ int grad_clip_coef(int n, const float* const* g, const long long* counts, float 
     segs.n = cnt;
     ProfScope prof("grad_norm", 2.0 * elems, 4.0 * elems, s);
     const int blocks = static_cast<int>(min(static_cast<long long>(device_sm_count()) * 8, (acc + 255) / 256));
-    sumsq_multi_kernel<<<blocks, 256, 0, s>>>(segs, scratch);
+    SER_CUDA_CHECK(launch_pdl(sumsq_multi_kernel, dim3(blocks), dim3(256), 0, s, segs, scratch));
     SER_LAUNCH_CHECK();
   }
-  clip_coef_kernel<<<1, 1, 0, s>>>(scratch, max_norm, coef, norm_out);
+  SER_CUDA_CHECK(launch_pdl(clip_coef_kernel, dim3(1), dim3(1), 0, s, scratch, max_norm, coef, norm_out));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

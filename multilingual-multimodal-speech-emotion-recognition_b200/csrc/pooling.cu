@@ -28,6 +28,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 asp_score_kernel(const T* __restrict__ u, const float* __restrict__ w2, const float* __restrict__ b2,
                  float* __restrict__ e, int M, int Hd) {
+  pdl_sync();
   const int lpr = Hd >> 3;                         // lanes per row (power of two <= 32)
   const int rpw = 32 / lpr;                        // rows per warp
   const int lane = threadIdx.x & 31;
@@ -72,6 +73,7 @@ template <typename T, int SLAB>
 __global__ void __launch_bounds__(NTH)
 asp_stats_kernel(const T* __restrict__ x, const float* __restrict__ e, const float* __restrict__ mask,
                  float* __restrict__ alpha, void* __restrict__ out, int out_f32, int Tlen, int D) {
+  pdl_sync();
   constexpr int RG = SlabCfg<SLAB>::kRG, KL = SlabCfg<SLAB>::kLanes;
   extern __shared__ float smem[];
   float* sa = smem;                      // [T]
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(NTH)
 asp_bwd_stats_kernel(const T* __restrict__ x, const float* __restrict__ alpha, const void* __restrict__ out,
                      int out_f32, const void* __restrict__ dout, int dout_f32, T* __restrict__ dx,
                      float* __restrict__ dalpha, int Tlen, int D) {
+  pdl_sync();
   constexpr int RG = SlabCfg<SLAB>::kRG, KL = SlabCfg<SLAB>::kLanes;
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * SLAB;
@@ -201,6 +204,7 @@ __global__ void __launch_bounds__(256)
 asp_bwd_score_kernel(const T* __restrict__ u, const float* __restrict__ w2, const float* __restrict__ alpha,
                      const float* __restrict__ dalpha, T* __restrict__ dpre, float* __restrict__ dw2,
                      float* __restrict__ db2, int Tlen, int Hd) {
+  pdl_sync();
   extern __shared__ float smem[];
   float* sde = smem;             // [T]
   float* red = sde + Tlen;       // [32]
@@ -259,6 +263,7 @@ __global__ void __launch_bounds__(256)
 mix_fwd_kernel(const T* __restrict__ pa, const T* __restrict__ pt, const T* __restrict__ ga, const T* __restrict__ gt,
                const float* __restrict__ wga, const float* __restrict__ bga, const float* __restrict__ wgt,
                const float* __restrict__ bgt, float* __restrict__ gates, T* __restrict__ fused, int B, int P, int G) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= B) return;
@@ -286,6 +291,7 @@ mix_bwd_kernel(const T* __restrict__ pa, const T* __restrict__ pt, const T* __re
                const T* __restrict__ dfused, T* __restrict__ dpa, T* __restrict__ dpt, T* __restrict__ dga,
                T* __restrict__ dgt, float* __restrict__ dwga, float* __restrict__ dbga, float* __restrict__ dwgt,
                float* __restrict__ dbgt, int B, int P, int G) {
+  pdl_sync();
   extern __shared__ float smem[];       // [2*G + 2] block-local accumulation of gate-weight grads
   for (int i = threadIdx.x; i < 2 * G + 2; i += blockDim.x) smem[i] = 0.f;
   __syncthreads();
@@ -331,8 +337,8 @@ int asp_stats_launch(const AspArgs& a, cudaStream_t s) {
   const size_t smem = sizeof(float) * (a.T + 32 + 2 * RG * SLAB);
   auto kern = asp_stats_kernel<T, SLAB>;
   if (smem > 48 * 1024) SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<dim3(a.D / SLAB, a.B), NTH, smem, s>>>(reinterpret_cast<const T*>(a.x), a.e, a.mask, a.alpha, a.out,
-                                                a.out_f32, a.T, a.D);
+  SER_CUDA_CHECK(launch_pdl(kern, dim3(dim3(a.D / SLAB, a.B)), dim3(NTH), smem, s, reinterpret_cast<const T*>(a.x), a.e, a.mask, a.alpha, a.out,
+                                                a.out_f32, a.T, a.D));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -343,7 +349,7 @@ int asp_fwd_impl(const AspArgs& a, cudaStream_t s) {
   // algorithmic bytes: x read once + u read once (single-pass minimum)
   ProfScope prof("asp_fwd", 0.0, sizeof(T) * static_cast<double>(M) * (a.D + a.Hd), s);
   const int rows_per_cta = 8 * (32 / (a.Hd >> 3));
-  asp_score_kernel<T><<<ceil_div(M, rows_per_cta), 256, 0, s>>>(reinterpret_cast<const T*>(a.u), a.w2, a.b2, a.e, M, a.Hd);
+  SER_CUDA_CHECK(launch_pdl(asp_score_kernel<T>, dim3(ceil_div(M, rows_per_cta)), dim3(256), 0, s, reinterpret_cast<const T*>(a.u), a.w2, a.b2, a.e, M, a.Hd));
   SER_LAUNCH_CHECK();
   return (a.D % 256 == 0) ? asp_stats_launch<T, 256>(a, s) : asp_stats_launch<T, 64>(a, s);
 }
@@ -353,19 +359,19 @@ int asp_bwd_impl(const AspArgs& a, cudaStream_t s) {
   ProfScope prof("asp_bwd", 0.0, sizeof(T) * static_cast<double>(a.B) * a.T * (2.0 * a.D + 2.0 * a.Hd), s);
   SER_TRY(zero_async(a.dalpha, sizeof(float) * a.B * a.T, s));
   if (a.D % 256 == 0)
-    asp_bwd_stats_kernel<T, 256><<<dim3(a.D / 256, a.B), NTH, 0, s>>>(reinterpret_cast<const T*>(a.x), a.alpha, a.out,
+    SER_CUDA_CHECK(launch_pdl(asp_bwd_stats_kernel<T, 256>, dim3(dim3(a.D / 256, a.B)), dim3(NTH), 0, s, reinterpret_cast<const T*>(a.x), a.alpha, a.out,
                                                                       a.out_f32, a.dout, a.dout_f32,
-                                                                      reinterpret_cast<T*>(a.dx), a.dalpha, a.T, a.D);
+                                                                      reinterpret_cast<T*>(a.dx), a.dalpha, a.T, a.D));
   else
-    asp_bwd_stats_kernel<T, 64><<<dim3(a.D / 64, a.B), NTH, 0, s>>>(reinterpret_cast<const T*>(a.x), a.alpha, a.out,
+    SER_CUDA_CHECK(launch_pdl(asp_bwd_stats_kernel<T, 64>, dim3(dim3(a.D / 64, a.B)), dim3(NTH), 0, s, reinterpret_cast<const T*>(a.x), a.alpha, a.out,
                                                                     a.out_f32, a.dout, a.dout_f32,
-                                                                    reinterpret_cast<T*>(a.dx), a.dalpha, a.T, a.D);
+                                                                    reinterpret_cast<T*>(a.dx), a.dalpha, a.T, a.D));
   SER_LAUNCH_CHECK();
   const size_t smem = sizeof(float) * (a.T + 32 + a.Hd);
   auto kern = asp_bwd_score_kernel<T>;
   if (smem > 48 * 1024) SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<a.B, 256, smem, s>>>(reinterpret_cast<const T*>(a.u), a.w2, a.alpha, a.dalpha, reinterpret_cast<T*>(a.dpre),
-                              a.dw2, a.db2, a.T, a.Hd);
+  SER_CUDA_CHECK(launch_pdl(kern, dim3(a.B), dim3(256), smem, s, reinterpret_cast<const T*>(a.u), a.w2, a.alpha, a.dalpha, reinterpret_cast<T*>(a.dpre),
+                              a.dw2, a.db2, a.T, a.Hd));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -387,10 +393,10 @@ int asp_bwd(const AspArgs& a, cudaStream_t s) {
 int fusion_mix_fwd(const MixArgs& a, cudaStream_t s) {
   ProfScope prof("fusion_mix_fwd", 0.0, (a.dtype == DT_F32 ? 4.0 : 2.0) * a.B * (3.0 * a.P + 2.0 * a.G), s);
 #define SER_MIX_FWD(T)                                                                                             \
-  mix_fwd_kernel<T><<<ceil_div(a.B, 8), 256, 0, s>>>(                                                              \
+  SER_CUDA_CHECK(launch_pdl(mix_fwd_kernel<T>, dim3(ceil_div(a.B, 8)), dim3(256), 0, s, \
       reinterpret_cast<const T*>(a.pa), reinterpret_cast<const T*>(a.pt), reinterpret_cast<const T*>(a.ga),       \
       reinterpret_cast<const T*>(a.gt), a.wga, a.bga, a.wgt, a.bgt, a.gates, reinterpret_cast<T*>(a.fused), a.B,  \
-      a.P, a.G)
+      a.P, a.G))
   if (a.dtype == DT_F32) SER_MIX_FWD(float); else SER_MIX_FWD(__nv_bfloat16);
 #undef SER_MIX_FWD
   SER_LAUNCH_CHECK();
@@ -401,11 +407,11 @@ int fusion_mix_bwd(const MixArgs& a, cudaStream_t s) {
   ProfScope prof("fusion_mix_bwd", 0.0, (a.dtype == DT_F32 ? 4.0 : 2.0) * a.B * (5.0 * a.P + 4.0 * a.G), s);
   const size_t smem = sizeof(float) * (2 * a.G + 2);
 #define SER_MIX_BWD(T)                                                                                             \
-  mix_bwd_kernel<T><<<ceil_div(a.B, 8), 256, smem, s>>>(                                                           \
+  SER_CUDA_CHECK(launch_pdl(mix_bwd_kernel<T>, dim3(ceil_div(a.B, 8)), dim3(256), smem, s, \
       reinterpret_cast<const T*>(a.pa), reinterpret_cast<const T*>(a.pt), reinterpret_cast<const T*>(a.ga),       \
       reinterpret_cast<const T*>(a.gt), a.wga, a.wgt, a.gates, reinterpret_cast<const T*>(a.dfused),              \
       reinterpret_cast<T*>(a.dpa), reinterpret_cast<T*>(a.dpt), reinterpret_cast<T*>(a.dga),                      \
-      reinterpret_cast<T*>(a.dgt), a.dwga, a.dbga, a.dwgt, a.dbgt, a.B, a.P, a.G)
+      reinterpret_cast<T*>(a.dgt), a.dwga, a.dbga, a.dwgt, a.dbgt, a.B, a.P, a.G))
   if (a.dtype == DT_F32) SER_MIX_BWD(float); else SER_MIX_BWD(__nv_bfloat16);
 #undef SER_MIX_BWD
   SER_LAUNCH_CHECK();

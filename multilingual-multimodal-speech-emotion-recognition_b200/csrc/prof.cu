@@ -42,9 +42,40 @@ void prof_end(cudaStream_t s) {
   if (!S.recs.empty()) cudaEventRecord(S.recs.back().e1, s);
 }
 
+namespace {
+__global__ void prof_stall_kernel(unsigned long long ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    __nanosleep(1000);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+}
+__global__ void prof_null_kernel() { pdl_sync(); }
+}  // namespace
+
 }  // namespace ser
 
 extern "C" {
+
+// n profiled launches of an empty kernel (family "prof_null"): the floor of one event interval -- what the events
+// themselves and an isolated launch add to every record of the profile
+int ser_prof_null(int n, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int i = 0; i < n; ++i) {
+    ser::ProfScope prof("prof_null", 0.0, 0.0, s);
+    SER_CUDA_CHECK(ser::launch_pdl(ser::prof_null_kernel, dim3(1), dim3(32), 0, s));
+  }
+  return SER_OK;
+}
+
+int ser_prof_stall(double microseconds, void* stream) {
+  if (microseconds <= 0.0) return SER_OK;
+  if (microseconds > 2.0e5) microseconds = 2.0e5;          // never more than 0.2 s
+  ser::prof_stall_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned long long>(microseconds * 1e3));
+  SER_CUDA_CHECK(cudaGetLastError());
+  return SER_OK;
+}
 
 int ser_prof_enable(int on) {
   ser::st().enabled = (on != 0);

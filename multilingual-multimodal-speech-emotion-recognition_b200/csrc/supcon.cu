@@ -17,6 +17,7 @@ constexpr float kLogEps = 1e-12f;
 // fn[i,:] = f[i,:] / max(||f_i||, eps); inv[i] = 1 / max(||f_i||, eps).  One warp per row.
 __global__ void __launch_bounds__(256)
 supcon_normalize_kernel(const void* __restrict__ f, int f_f32, float* __restrict__ fn, float* __restrict__ inv, int B, int D) {
+  pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
@@ -33,6 +34,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(256)
 supcon_rows_kernel(float* __restrict__ S, const long long* __restrict__ labels, float* __restrict__ stats,
                    float* __restrict__ loss, const float* __restrict__ gscale, int B) {
+  pdl_sync();
   extern __shared__ float srow[];            // [B]
   __shared__ float red[32];
   const int i = blockIdx.x;
@@ -77,6 +79,7 @@ supcon_rows_kernel(float* __restrict__ S, const long long* __restrict__ labels, 
 __global__ void __launch_bounds__(256)
 supcon_normalize_bwd_kernel(const float* __restrict__ fn, const float* __restrict__ inv, const float* __restrict__ dfn,
                             void* __restrict__ df, int df_f32, int B, int D) {
+  pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= B) return;
@@ -112,7 +115,7 @@ static SupconBufs supcon_bufs(void* ws, int B, int D) {
 }
 
 static int supcon_similarities(const SupconBufs& b, const void* f, int f_f32, int B, int D, float temperature, cudaStream_t s) {
-  supcon_normalize_kernel<<<ceil_div(B, 8), 256, 0, s>>>(f, f_f32, b.fn, b.inv, B, D);
+  SER_CUDA_CHECK(launch_pdl(supcon_normalize_kernel, dim3(ceil_div(B, 8)), dim3(256), 0, s, f, f_f32, b.fn, b.inv, B, D));
   SER_LAUNCH_CHECK();
   GemmArgs g;
   g.dtype = DT_F32; g.M = B; g.N = B; g.K = D;
@@ -129,7 +132,7 @@ int supcon_fwd(const void* f, int f_f32, const long long* labels, int B, int D, 
   const SupconBufs b = supcon_bufs(ws, B, D);
   SER_TRY(supcon_similarities(b, f, f_f32, B, D, temperature, s));
   SER_CUDA_CHECK(cudaMemsetAsync(loss, 0, sizeof(float), s));
-  supcon_rows_kernel<false><<<B, 256, sizeof(float) * B, s>>>(b.S, labels, b.stats, loss, nullptr, B);
+  SER_CUDA_CHECK(launch_pdl(supcon_rows_kernel<false>, dim3(B), dim3(256), sizeof(float) * B, s, b.S, labels, b.stats, loss, nullptr, B));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -143,7 +146,7 @@ int supcon_bwd(const void* f, int f_f32, const long long* labels, int B, int D, 
   ProfScope prof("supcon_bwd", 6.0 * B * B * D, 4.0 * (3.0 * B * D + 2.0 * B * B), s);
   const SupconBufs b = supcon_bufs(ws, B, D);
   SER_TRY(supcon_similarities(b, f, f_f32, B, D, temperature, s));
-  supcon_rows_kernel<true><<<B, 256, sizeof(float) * B, s>>>(b.S, labels, b.stats, nullptr, gscale, B);
+  SER_CUDA_CHECK(launch_pdl(supcon_rows_kernel<true>, dim3(B), dim3(256), sizeof(float) * B, s, b.S, labels, b.stats, nullptr, gscale, B));
   SER_LAUNCH_CHECK();
   // S = fn fn^T / T  ->  dfn = (G + G^T) fn / T
   GemmArgs g;
@@ -154,7 +157,7 @@ int supcon_bwd(const void* f, int f_f32, const long long* labels, int B, int D, 
   SER_TRY(gemm(g, s));
   g.a_trans = 1; g.accumulate = 1;
   SER_TRY(gemm(g, s));
-  supcon_normalize_bwd_kernel<<<ceil_div(B, 8), 256, 0, s>>>(b.fn, b.inv, b.dfn, df, df_f32, B, D);
+  SER_CUDA_CHECK(launch_pdl(supcon_normalize_bwd_kernel, dim3(ceil_div(B, 8)), dim3(256), 0, s, b.fn, b.inv, b.dfn, df, df_f32, B, D));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
