@@ -41,6 +41,8 @@ extern "C" {
 int ser_version(void);
 const char* ser_last_error(void);
 int ser_sm_count(void);
+/* leave `n` SMs out of the persistent GEMM grids (for the NCCL kernels of a data-parallel step); 0 = use them all */
+int ser_set_reserved_sms(int n);
 /* number of CUDA kernels this library has launched so far in this process                       */
 long long ser_launch_count(void);
 /* sizeof() of descriptor `id` as compiled (0 gemm, 1 adapter, 2 xattn, 3 asp, 4 fusion, 5 clf, 6 loss, 7 featfuse, 8 attn):
@@ -86,6 +88,13 @@ int ser_cast(const void* src, int src_f32, void* dst, int dst_f32, long long n, 
 /* the same for up to 16 buffers in ONE launch, fp32 -> bf16 (all modules of a head before its forward);
  * src / dst / counts are HOST arrays of length n, counts multiples of 8 elements                      */
 int ser_cast_multi(int n, const void* const* src, void* const* dst, const long long* counts, void* stream);
+
+/* packed valid frames -> zero-padded batch + mask: out[b,t,:] = t < len_b ? packed[offsets[b] + t, :] : 0 and
+ * mask[b,t] = t < len_b (mask may be NULL), len_b = offsets[b+1] - offsets[b]; offsets = B + 1 int64 values in device
+ * memory.  Replaces the zero-padding of the encoders' batch assembly (src/models/audio_encoder.py:140-163,
+ * src/models/text_encoder.py:75-78) when the hidden states arrive from the host: only valid frames cross PCIe.   */
+int ser_unpack_frames(const void* packed, const long long* offsets, void* out, float* mask, int B, int T, int D,
+                      int elem_bytes, void* stream);
 
 /* row/column primitives behind the individually callable children of the classifier
  * (nn.LayerNorm / bias-gradient column sums; src/train.py:221-236 calls those children one by one)  */

@@ -106,6 +106,8 @@ def load():
     lib.ser_gemm.argtypes = [C.POINTER(GemmDesc), P]
     lib.ser_cast.argtypes = [P, I, P, I, LL, P]
     lib.ser_cast_multi.argtypes = [I, P, P, P, P]
+    lib.ser_set_reserved_sms.argtypes = [I]
+    lib.ser_unpack_frames.argtypes = [P, P, P, P, I, I, I, I, P]
     lib.ser_layernorm_fwd.argtypes = [P, I, P, I, P, P, P, I, I, I, P]
     lib.ser_layernorm_bwd.argtypes = [P, I, P, I, P, P, P, P, I, P, P, I, I, I, P]
     lib.ser_colsum.argtypes = [P, I, LL, I, I, P, P]
@@ -238,6 +240,11 @@ def gemm(a, b, *, a_trans=False, b_trans=False, bias=None, act=ACT_NONE, residua
         d.rowsum = ptr(rowsum)
     check(lib.ser_gemm(C.byref(d), stream_ptr(a.device)), "ser_gemm")
     return out
+
+
+def set_reserved_sms(n: int) -> None:
+    """Leave n SMs out of the persistent GEMM grids (NCCL's channel CTAs in data-parallel steps)."""
+    check(load().ser_set_reserved_sms(int(n)), "ser_set_reserved_sms")
 
 
 def launch_count() -> int:

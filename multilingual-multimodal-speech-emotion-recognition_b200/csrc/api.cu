@@ -35,6 +35,8 @@ const char* ser_last_error(void) { return ser::last_error(); }
 
 int ser_sm_count(void) { return ser::device_sm_count(); }
 
+int ser_set_reserved_sms(int n) { ser::set_reserved_sms(n); return SER_OK; }
+
 long long ser_launch_count(void) { return ser::launch_count(); }
 
 int ser_desc_size(int id) {
@@ -74,6 +76,11 @@ int ser_gemm(const ser_gemm_desc* d, void* stream) {
 
 int ser_cast(const void* src, int src_f32, void* dst, int dst_f32, long long n, void* stream) {
   return ser::cast_any(src, src_f32, dst, dst_f32, n, SER_STREAM(stream));
+}
+
+int ser_unpack_frames(const void* packed, const long long* offsets, void* out, float* mask, int B, int T, int D,
+                      int elem_bytes, void* stream) {
+  return ser::unpack_frames(packed, offsets, out, mask, B, T, D, elem_bytes, SER_STREAM(stream));
 }
 
 int ser_cast_multi(int n, const void* const* src, void* const* dst, const long long* counts, void* stream) {

@@ -231,5 +231,7 @@ int gemm_simt_f32(const GemmArgs& a, cudaStream_t stream);
 int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream);
 bool gemm_tc_rowsum_ok(const GemmArgs& a);
 int device_sm_count();
+int gemm_grid_sms();               // device_sm_count() minus the SMs reserved for concurrent collectives
+void set_reserved_sms(int n);
 
 }  // namespace ser

@@ -579,6 +579,56 @@ int cast_any(const void* src, int src_f32, void* dst, int dst_f32, long long n, 
   return SER_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Packed valid frames -> zero-padded batch.  The encoders pad every utterance of a batch to the longest one
+// (src/models/audio_encoder.py:140-163, text_encoder.py:75-78: zero frames + a 1/0 mask); a host that feeds hidden
+// states to the head therefore ships 25-40 % zeros.  Here the host sends only the valid frames, concatenated, plus the
+// B + 1 row offsets, and one pass rebuilds out[b, t, :] = t < len_b ? packed[off_b + t, :] : 0 and mask[b, t].
+// Warp per output row, 16-byte accesses.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+unpack_frames_kernel(const uint4* __restrict__ packed, const long long* __restrict__ offsets, uint4* __restrict__ out,
+                     float* __restrict__ mask, int B, int T, int row16) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31;
+  const long long nrows = static_cast<long long>(B) * T;
+  for (long long r = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows;
+       r += static_cast<long long>(gridDim.x) * (blockDim.x >> 5)) {
+    const int b = static_cast<int>(r / T), t = static_cast<int>(r % T);
+    const long long o0 = __ldg(offsets + b), o1 = __ldg(offsets + b + 1);
+    const bool ok = t < (o1 - o0);
+    uint4* dst = out + r * row16;
+    if (ok) {
+      const uint4* src = packed + (o0 + t) * row16;
+      for (int i = lane; i < row16; i += 32) dst[i] = __ldg(src + i);
+    } else {
+      for (int i = lane; i < row16; i += 32) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (mask != nullptr && lane == 0) mask[r] = ok ? 1.f : 0.f;
+  }
+}
+}  // namespace
+
+int unpack_frames(const void* packed, const long long* offsets, void* out, float* mask, int B, int T, int D, int elem_bytes,
+                  cudaStream_t s) {
+  SER_REQUIRE(B > 0 && T > 0 && D > 0, "unpack_frames: empty problem");
+  SER_REQUIRE((static_cast<long long>(D) * elem_bytes) % 16 == 0, "unpack_frames: rows must be multiples of 16 bytes");
+  SER_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "unpack_frames: buffers must be 16-byte aligned");
+  const int row16 = static_cast<int>(static_cast<long long>(D) * elem_bytes / 16);
+  const long long nrows = static_cast<long long>(B) * T;
+  long long blocks = (nrows + 7) / 8;
+  const long long cap = 8LL * device_sm_count();
+  if (blocks > cap) blocks = cap;
+  // algorithmic bytes: every output row written once, valid rows read once (upper bound: all rows valid)
+  ProfScope prof("unpack_frames", 0.0, 2.0 * nrows * D * elem_bytes, s);
+  SER_CUDA_CHECK(launch_pdl(unpack_frames_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, s,
+                            reinterpret_cast<const uint4*>(packed), offsets, reinterpret_cast<uint4*>(out), mask, B, T, row16));
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
 int zero_async(void* p, size_t bytes, cudaStream_t s) {
   if (bytes == 0) return SER_OK;
   if ((reinterpret_cast<uintptr_t>(p) & 15) != 0 || (bytes & 15) != 0) {

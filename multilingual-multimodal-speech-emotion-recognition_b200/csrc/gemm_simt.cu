@@ -215,4 +215,15 @@ int device_sm_count() {
   return sms;
 }
 
+// SMs the persistent tcgen05 GEMM grids leave free.  In data-parallel runs an NCCL all-reduce kernel is resident for
+// most of the backward pass (one CTA per channel); a persistent GEMM CTA assigned to an SM NCCL occupies cannot start
+// until another CTA of its own grid has finished ALL its tiles, which stretches that GEMM by up to one full tile
+// sequence.  parallel.DataParallelHead reserves as many SMs as NCCL has channels (ser_set_reserved_sms).
+static int g_reserved_sms = 0;
+void set_reserved_sms(int n) { g_reserved_sms = n < 0 ? 0 : n; }
+int gemm_grid_sms() {
+  const int n = device_sm_count() - g_reserved_sms;
+  return n < 16 ? 16 : n;
+}
+
 }  // namespace ser

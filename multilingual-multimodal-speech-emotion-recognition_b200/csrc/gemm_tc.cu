@@ -541,12 +541,12 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   const int m_tiles = ceil_div(M, BM), n_tiles = N / BN;
   if (!PAIR) {
     const long long total = static_cast<long long>(m_tiles) * n_tiles * splits * batch;
-    const int grid = static_cast<int>(total < device_sm_count() ? total : device_sm_count());
+    const int grid = static_cast<int>(total < gemm_grid_sms() ? total : gemm_grid_sms());
     SER_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kThreads), smem_bytes, stream, tmA, tmB, tmC, tmS, ep, M, N, K, splits,
                               batch, nstages));
   } else {
     const long long units = static_cast<long long>(m_tiles / 2) * n_tiles * splits * batch;
-    const long long max_clusters = device_sm_count() / 2;
+    const long long max_clusters = gemm_grid_sms() / 2;
     const int clusters = static_cast<int>(units < max_clusters ? units : max_clusters);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * clusters, 1, 1);

@@ -11,6 +11,8 @@ int cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStre
 int cast_any(const void* src, int src_f32, void* dst, int dst_f32, long long n, cudaStream_t s);
 // zero `bytes` bytes with a kernel launch (falls back to cudaMemsetAsync for unaligned regions)
 int zero_async(void* p, size_t bytes, cudaStream_t s);
+int unpack_frames(const void* packed, const long long* offsets, void* out, float* mask, int B, int T, int D, int elem_bytes,
+                  cudaStream_t s);
 // fp32 -> bf16 of n <= 16 buffers in one launch; src / dst / counts are HOST arrays (counts multiples of 8)
 int cast_multi(int n, const void* const* src, void* const* dst, const long long* counts, cudaStream_t s);
 // out[n] (fp32) = sum_m X[m, n]           X: [M, N] with leading dim ld, fp32 or bf16

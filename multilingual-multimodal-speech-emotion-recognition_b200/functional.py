@@ -52,6 +52,41 @@ def dropout_mask(seed: torch.Tensor, site: int, p: float, rows: int, cols: int) 
 
 
 # --------------------------------------------------------------------------------------------------
+# input side: packed valid frames <-> zero-padded batch (src/models/audio_encoder.py:140-163, text_encoder.py:75-78)
+# --------------------------------------------------------------------------------------------------
+def pack_frames(x: torch.Tensor, mask: torch.Tensor):
+    """HOST side (any device): keep the valid frames only.  x [B, T, D] zero-padded on the right, mask [B, T] 1/0 with
+    the valid frames of every sample first (what the encoders produce).  Returns (packed [sum(len), D], offsets [B + 1]
+    int64); `unpack_frames` rebuilds x and the mask bit-exactly on the device."""
+    lens = mask.to(torch.int64).sum(1)
+    B, T = mask.shape
+    if not bool(((torch.arange(T, device=mask.device)[None, :] < lens[:, None]) == (mask != 0)).all()):
+        raise ValueError("pack_frames: the mask must be right-padded (valid frames first)")
+    offsets = torch.zeros(B + 1, dtype=torch.int64, device=mask.device)
+    offsets[1:] = torch.cumsum(lens, 0)
+    return x[mask != 0].contiguous(), offsets
+
+
+def unpack_frames(packed: torch.Tensor, offsets: torch.Tensor, T: int, out: Optional[torch.Tensor] = None,
+                  mask_out: Optional[torch.Tensor] = None, with_mask: bool = True):
+    """Device side of `pack_frames`: one pass writes out [B, T, D] (valid frames copied, the rest zero) and the float
+    mask [B, T].  packed [n, D] (fp32 or bf16) and offsets [B + 1] int64 are CUDA tensors; `out` / `mask_out` may be
+    preallocated (the CUDA-graph input buffers of a training step).  Returns (out, mask)."""
+    L.require_cuda(packed, offsets, out, mask_out)
+    assert packed.dim() == 2 and packed.is_contiguous() and offsets.dtype == torch.int64 and offsets.is_contiguous()
+    B, D = offsets.numel() - 1, packed.shape[1]
+    if out is None:
+        out = torch.empty(B, T, D, device=packed.device, dtype=packed.dtype)
+    if mask_out is None and with_mask:
+        mask_out = torch.empty(B, T, device=packed.device, dtype=torch.float32)
+    assert out.is_contiguous() and tuple(out.shape) == (B, T, D) and out.dtype == packed.dtype
+    assert mask_out is None or (mask_out.is_contiguous() and mask_out.dtype == torch.float32 and tuple(mask_out.shape) == (B, T))
+    L.check(L.load().ser_unpack_frames(packed.data_ptr(), offsets.data_ptr(), out.data_ptr(), L.ptr(mask_out), B, int(T), D,
+                                       packed.element_size(), L.stream_ptr(packed.device)), "ser_unpack_frames")
+    return out, mask_out
+
+
+# --------------------------------------------------------------------------------------------------
 # a1 adapter
 # --------------------------------------------------------------------------------------------------
 class AdapterFn(torch.autograd.Function):

@@ -115,6 +115,12 @@ class DataParallelHead:
         # train_step() always starts from zero_grad(set_to_none=True), so the gradient buffers of consecutive steps may
         # share one persistent allocation (never true for callers that accumulate gradients over several backwards)
         head.persistent_grad_arena = True
+        if dist.is_initialized() and dist.get_world_size(group) > 1 and next(head.parameters()).is_cuda:
+            # SMs left to the NCCL kernels that run beside the backward GEMMs (see csrc/gemm_simt.cu set_reserved_sms);
+            # SER_SM_RESERVE overrides (0 = none)
+            import os
+            from . import _lib
+            _lib.set_reserved_sms(int(os.environ.get("SER_SM_RESERVE", "0")))
         if broadcast and dist.is_initialized() and dist.get_world_size(group) > 1:
             for _, fp in self._flats:
                 dist.broadcast(fp.flat, src=0, group=group)

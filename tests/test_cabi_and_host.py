@@ -245,3 +245,17 @@ def test_data_parallel_reduction_world2_gloo(lib):
         assert vals == {"classifier": 3.0, "fusion": 6.0, "cross": 9.0}      # SUM over ranks
         assert counts == [2.0, 3.0, 2.0, 1.0] and bg == 8
         assert sums == [3.0, 6.0]
+
+
+def test_pack_frames_host_side():
+    """functional.pack_frames (host half of ser_unpack_frames): valid frames in batch order, B + 1 offsets, and a clear
+    error for masks that are not right-padded."""
+    sys.path.insert(0, ROOT)
+    from mmser_b200.functional import pack_frames
+    x = torch.arange(2 * 4 * 3, dtype=torch.float32).reshape(2, 4, 3)
+    mask = torch.tensor([[1., 1., 0., 0.], [1., 1., 1., 0.]])
+    packed, off = pack_frames(x * mask[:, :, None], mask)
+    assert off.tolist() == [0, 2, 5] and packed.shape == (5, 3)
+    assert torch.equal(packed, torch.cat([x[0, :2], x[1, :3]]))
+    with pytest.raises(ValueError):
+        pack_frames(x, torch.tensor([[1., 0., 1., 0.], [1., 1., 1., 0.]]))

@@ -632,3 +632,26 @@ def test_large_shape_properties():
     out32 = head(a.to(dev)[:32], t.to(dev)[:32], am.to(dev)[:32], tm.to(dev)[:32], labels.to(dev)[:32])
     d = (out["logits"][:32] - out32["logits"]).abs().max() / out32["logits"].abs().max()
     assert float(d) < 2e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_unpack_frames_bit_exact(dtype):
+    """Packed valid frames -> zero-padded batch + mask (ser_unpack_frames) against the padding the encoders do
+    (src/models/audio_encoder.py:140-163): bit-exact, including an empty utterance, a full-length one and T = 1."""
+    from mmser_b200.functional import pack_frames, unpack_frames
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    for B, T, D in ((7, 53, 768), (3, 1, 768), (5, 130, 256)):
+        lens = torch.randint(0, T + 1, (B,), generator=g)
+        lens[0], lens[-1] = T, 0
+        mask = (torch.arange(T)[None, :] < lens[:, None]).float()
+        x = (torch.randn(B, T, D, generator=g) * mask[:, :, None]).to(dtype)
+        packed, offsets = pack_frames(x, mask)                       # host side
+        assert packed.shape[0] == int(lens.sum()) and offsets[-1] == lens.sum()
+        out, m = unpack_frames(packed.to(dev), offsets.to(dev), T)
+        assert torch.equal(out.cpu(), x) and torch.equal(m.cpu(), mask)
+        # into preallocated (dirty) buffers, as the benchmark's copy stream does
+        out2 = torch.full((B, T, D), 7.0, device=dev, dtype=dtype)
+        m2 = torch.full((B, T), 7.0, device=dev)
+        unpack_frames(packed.to(dev), offsets.to(dev), T, out=out2, mask_out=m2)
+        assert torch.equal(out2.cpu(), x) and torch.equal(m2.cpu(), mask)
