@@ -176,6 +176,11 @@ typedef struct ser_xattn_desc {
    * o_* are not touched.                                                                             */
   void* fold_w; float* fold_b;
   float p_drop; const unsigned long long* drop_seed;   /* attention-weight + residual dropout; 0 / NULL = off */
+  /* optional, bf16 tier with dropout on: keep decisions of the attention-weight dropout, one bit per (b, h, query, key),
+   * keep_a [B*H*Ta, ceil(Tt/32)] (audio queries) and keep_t [B*H*Tt, ceil(Ta/32)] uint32 words.  The forward kernel
+   * writes them while it applies the mask, the two backward kernels read them instead of re-hashing every element
+   * (the hash was > 50 % of their instruction stream).  NULL = regenerate from the seed.                              */
+  unsigned int* keep_a; unsigned int* keep_t;
   /* backward */
   const void* d_enh_a; const void* d_enh_t;
   void* da; void* dt;                      /* [M,D] act gradients w.r.t. the inputs               */
@@ -215,6 +220,9 @@ typedef struct ser_attn_desc {
   const void* dO; long long lddo;
   void* dQ; long long lddq; void* dK; long long lddk; void* dV; long long lddv;
   float* delta;
+  /* optional (tcgen05 kernels, dropout on): keep bits [B*H*Tq, ceil(Tk/32)] uint32, bit k%32 of word k/32 of row
+   * (b*H + h)*Tq + i = "weight (i, k) is kept"; written by the forward, read by the backward; NULL = re-hash       */
+  unsigned int* keep_bits;
 } ser_attn_desc;
 int ser_attention_fwd(const ser_attn_desc* d, void* stream);
 int ser_attention_bwd(const ser_attn_desc* d, void* stream);

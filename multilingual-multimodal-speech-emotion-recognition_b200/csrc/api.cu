@@ -126,6 +126,7 @@ static ser::AttnArgs to_attn_args(const ser_attn_desc& d) {
   a.dO = d.dO; a.lddo = d.lddo; a.dQ = d.dQ; a.lddq = d.lddq; a.dK = d.dK; a.lddk = d.lddk; a.dV = d.dV; a.lddv = d.lddv;
   a.delta = d.delta;
   a.drop = ser::make_drop(d.drop_seed, d.p_drop, static_cast<unsigned>(d.drop_site));
+  a.keep_bits = d.keep_bits;
   a.impl = d.impl;
   return a;
 }

@@ -345,6 +345,13 @@ static bool use_tc5(const AttnArgs& a, bool backward) {
   return a.Tq > 64 || cells >= 131072;
 }
 
+// A/B switch: SER_ATTN_KEEPBITS=0 makes the backward kernels re-hash the dropout decisions instead of reading the bits
+// the forward kernel stored
+static bool keep_bits_enabled() {
+  static const bool on = !(getenv("SER_ATTN_KEEPBITS") != nullptr && atoi(getenv("SER_ATTN_KEEPBITS")) == 0);
+  return on;
+}
+
 int attention_fwd(const AttnArgs& a, cudaStream_t s) {
   SER_TRY(check(a));
   // bf16 tier: tensor-core kernels (attention_tc.cu); fp32 tier: the CUDA-core kernels of this file
@@ -353,7 +360,10 @@ int attention_fwd(const AttnArgs& a, cudaStream_t s) {
     set_last_error(__FILE__, __LINE__, "attention: the tcgen05 kernels need head dim 32, an even head count and 16-byte aligned operands");
     return SER_ERR_UNSUPPORTED;
   }
-  return use_tc5(a, false) ? attention_fwd_tc5(a, s) : attention_fwd_tc(a, s);
+  if (!use_tc5(a, false)) return attention_fwd_tc(a, s);
+  AttnArgs b = a;
+  if (!keep_bits_enabled()) b.keep_bits = nullptr;
+  return attention_fwd_tc5(b, s);
 }
 
 int attention_bwd(const AttnArgs& a, cudaStream_t s) {
@@ -364,7 +374,11 @@ int attention_bwd(const AttnArgs& a, cudaStream_t s) {
     set_last_error(__FILE__, __LINE__, "attention: the tcgen05 kernels need head dim 32, an even head count and 16-byte aligned operands");
     return SER_ERR_UNSUPPORTED;
   }
-  return use_tc5(a, true) ? attention_bwd_tc5(a, s) : attention_bwd_tc(a, s);
+  if (!use_tc5(a, true)) return attention_bwd_tc(a, s);
+  AttnArgs b = a;
+  // the keep bits exist only if the FORWARD of this problem ran on the tcgen05 kernel (same shape, same impl / switches)
+  if (!keep_bits_enabled() || !use_tc5(a, false)) b.keep_bits = nullptr;
+  return attention_bwd_tc5(b, s);
 }
 
 }  // namespace ser

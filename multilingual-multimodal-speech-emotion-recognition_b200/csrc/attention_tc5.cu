@@ -87,7 +87,8 @@ template <bool DROP>
 __global__ void __launch_bounds__(A5_THREADS, 2)
 attn5_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const float* __restrict__ kmask, bf16* __restrict__ O,
-                 long long ldo, float* __restrict__ lse, int H, int Tq, int Tk, float scale, DropSpec drop, int narrow) {
+                 long long ldo, float* __restrict__ lse, int H, int Tq, int Tk, float scale, DropSpec drop, int narrow,
+                 unsigned* __restrict__ keep_bits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                                  // [128 x 128 B]   Q rows, both heads of the pair
@@ -254,6 +255,7 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < A5_DH; ++j) o[j] *= corr;
       float ls = 0.f;
+      unsigned kw = 0u;                                     // keep decisions of 32 keys (bit j%32), stored every 32 keys
 #pragma unroll
       for (int j8 = 0; j8 < A5_KT / 8; ++j8) {              // 8 keys = one 16-byte chunk of the P row
         uint32_t w[4];
@@ -263,12 +265,22 @@ attn5_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           float p0 = ex2(fmaf(x[j], c, -mu)), p1 = ex2(fmaf(x[j + 1], c, -mu));
           ls += p0 + p1;                                    // the normaliser sees every key; dropout acts on the weights
           if (DROP) {
-            const float2 mk = drop_pair(dkey, drow + static_cast<unsigned>(t * (A5_KT / 2) + (j >> 1)), drop.thr, drop.scale);
-            p0 *= mk.x; p1 *= mk.y;
+            const unsigned bb = drop_bits(dkey, drow + static_cast<unsigned>(t * (A5_KT / 2) + (j >> 1)));
+            const bool k0 = (bb & 0xffffu) >= drop.thr, k1 = (bb >> 16) >= drop.thr;
+            p0 *= k0 ? drop.scale : 0.f;
+            p1 *= k1 ? drop.scale : 0.f;
+            if (k0) kw |= 1u << (j & 31);                    // (compile-time positions: one predicated OR per decision)
+            if (k1) kw |= 2u << (j & 31);
           }
           w[u] = pack_bf16x2(p0, p1);
         }
         sts128(p_row + ((static_cast<uint32_t>(j8) ^ swz) << 4), w[0], w[1], w[2], w[3]);
+        if (DROP && (j8 & 3) == 3) {                        // 32 decisions complete: the backward kernels read them instead of re-hashing
+          const int wi = 2 * t + (j8 >> 2), W = (Tk + 31) >> 5;
+          if (keep_bits != nullptr && qi < Tq && wi < W)
+            keep_bits[((static_cast<size_t>(b) * H + head) * Tq + qi) * W + wi] = kw;
+          kw = 0u;
+        }
       }
       l = fmaf(l, corr, ls);
     }
@@ -351,7 +363,7 @@ attn5_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const float* __restrict__ kmask, const bf16* __restrict__ O, long long ldo,
                     const bf16* __restrict__ dO, long long lddo, const float* __restrict__ lse,
                     float* __restrict__ delta, bf16* __restrict__ dQ, long long lddq, int H, int Tq, int Tk, float scale,
-                    DropSpec drop) {
+                    DropSpec drop, const unsigned* __restrict__ keep_bits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                                  // [128 x 128 B] Q rows (both heads)
@@ -459,7 +471,16 @@ attn5_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     delta[(static_cast<size_t>(b) * H + head) * Tq + qi] = dl;
   }
 
+  // keep bits written by the forward kernel: one word per (row, 32-key tile), requested one tile ahead
+  const unsigned* krow = nullptr;
+  unsigned kcur = 0u;
+  if (DROP && keep_bits != nullptr && qi < Tq) {
+    krow = keep_bits + ((static_cast<size_t>(b) * H + head) * Tq + qi) * ((Tk + 31) >> 5);
+    kcur = __ldg(krow);
+  }
   for (int t = 0; t < ntiles; ++t) {
+    unsigned knext = 0u;
+    if (DROP && krow != nullptr && t + 1 < ntiles) knext = __ldg(krow + t + 1);
     mbar_wait(&bars->s_full[h], t & 1);                    // (also: the previous tile's dQ MMAs have retired)
     tc_fence_after();
     if (h == 0 && quarter == (t & 3) && lane == 0 && t >= 1 && t - 1 + B5_NST < ntiles) {
@@ -485,8 +506,13 @@ attn5_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float p1 = ex2(fmaf(__uint_as_float(sv[j + 1]), c, bb[2 * u + 1] + nl));
           float g0 = __uint_as_float(dv[j]), g1 = __uint_as_float(dv[j + 1]);
           if (DROP) {                                       // dP = mask * (dO V^T)
-            const float2 mk = drop_pair(dkey, drow + static_cast<unsigned>(t * (B5_KT / 2) + (j >> 1)), drop.thr, drop.scale);
-            g0 *= mk.x; g1 *= mk.y;
+            if (keep_bits != nullptr) {
+              g0 = ((kcur >> j) & 1u) ? g0 * drop.scale : 0.f;
+              g1 = ((kcur >> (j + 1)) & 1u) ? g1 * drop.scale : 0.f;
+            } else {
+              const float2 mk = drop_pair(dkey, drow + static_cast<unsigned>(t * (B5_KT / 2) + (j >> 1)), drop.thr, drop.scale);
+              g0 *= mk.x; g1 *= mk.y;
+            }
           }
           w[u] = pack_bf16x2(p0 * (g0 - dl), p1 * (g1 - dl));
         }
@@ -507,6 +533,7 @@ attn5_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       else tc_commit(&bars->acc_full[h]);
     }
     __syncwarp();
+    kcur = knext;
   }
   mbar_wait(&bars->acc_full[h], 0);
   tc_fence_after();
@@ -541,7 +568,7 @@ attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
                      const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG,
                      const float* __restrict__ kmask, const float* __restrict__ lse, const float* __restrict__ delta,
                      bf16* __restrict__ dK, long long lddk, bf16* __restrict__ dV, long long lddv, int H, int Tq, int Tk,
-                     float scale, DropSpec drop) {
+                     float scale, DropSpec drop, const unsigned* __restrict__ keep_bits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sK = smem;                                  // [128 x 128 B] K rows (both heads)
@@ -644,7 +671,29 @@ attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     drow0 = (static_cast<unsigned>(b) * H + head) * Tq;
   }
 
+  // keep bits written by the forward kernel: word (query, kw) holds the decisions of keys 32 kw .. 32 kw + 31 -- exactly
+  // this warp's 32 key rows.  Lane l fetches the word of query qt + l (one tile ahead); a 32 x 32 bit transpose across the
+  // warp (5 butterfly steps) then leaves lane l with its own key's decisions for the tile's 32 queries.
+  const int kwords = (Tk + 31) >> 5;
+  const unsigned* kbase = nullptr;
+  unsigned kraw = 0u;
+  if (DROP && keep_bits != nullptr && active) {
+    kbase = keep_bits + (static_cast<size_t>(b) * H + head) * Tq * kwords + ((k0 + quarter * 32) >> 5);
+    if (lane < Tq) kraw = __ldg(kbase + static_cast<size_t>(lane) * kwords);
+  }
   for (int t = 0; t < ntiles; ++t) {
+    unsigned knext = 0u, kcol = 0u;
+    if (DROP && kbase != nullptr) {
+      const int qn = (t + 1) * B5_KT + lane;
+      if (qn < Tq) knext = __ldg(kbase + static_cast<size_t>(qn) * kwords);
+      kcol = kraw;
+#pragma unroll
+      for (int sft = 16; sft >= 1; sft >>= 1) {
+        const unsigned m = sft == 16 ? 0x0000FFFFu : sft == 8 ? 0x00FF00FFu : sft == 4 ? 0x0F0F0F0Fu : sft == 2 ? 0x33333333u : 0x55555555u;
+        const unsigned pr = __shfl_xor_sync(0xffffffffu, kcol, sft);
+        kcol = (lane & sft) ? (((pr & ~m) >> sft) | (kcol & ~m)) : ((kcol & m) | ((pr & m) << sft));
+      }
+    }
     mbar_wait(&bars->s_full[h], t & 1);
     tc_fence_after();
     if (h == 0 && quarter == (t & 3) && lane == 0 && t >= 1 && t - 1 + B5_NST_KV < ntiles) {
@@ -677,8 +726,14 @@ attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
             if (partial && !(qt + j < Tq)) { p = 0.f; g = 0.f; }      // never let a foreign row's NaN through 0 * NaN
             float w = p;
             if (DROP) {
-              const float mk = drop_one(dkey, (drow0 + static_cast<unsigned>(qt + j)) * half_tk + dcol, dhalf, drop.thr, drop.scale);
-              w *= mk; g *= mk;
+              if (keep_bits != nullptr) {
+                const bool kp = ((kcol >> j) & 1u) != 0u;
+                w = kp ? w * drop.scale : 0.f;
+                g = kp ? g * drop.scale : 0.f;
+              } else {
+                const float mk = drop_one(dkey, (drow0 + static_cast<unsigned>(qt + j)) * half_tk + dcol, dhalf, drop.thr, drop.scale);
+                w *= mk; g *= mk;
+              }
             }
             pv[e] = w;
             dsv[e] = p * (g - dq_[2 * u + e]);
@@ -720,6 +775,7 @@ attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
       else tc_commit(&bars->acc_full[h]);
     }
     __syncwarp();
+    kraw = knext;
   }
   mbar_wait(&bars->acc_full[h], 0);
   tc_fence_after();
@@ -790,7 +846,7 @@ int attention_fwd_tc5(const AttnArgs& a, cudaStream_t s) {
   dim3 grid(ceil_div(a.Tq, A5_ROWS), a.H / 2, a.B);
   static const int narrow = getenv("SER_ATTN_NARROW") ? atoi(getenv("SER_ATTN_NARROW")) : 1;     // A/B switch
   SER_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(A5_THREADS), smem, s, tmQ, tmK, tmV, a.kmask, reinterpret_cast<bf16*>(a.O), a.ldo, a.lse, a.H, a.Tq, a.Tk,
-                                      a.scale, a.drop, narrow));
+                                      a.scale, a.drop, narrow, a.keep_bits));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -825,7 +881,8 @@ int attention_bwd_tc5(const AttnArgs& a, cudaStream_t s) {
     dim3 grid(ceil_div(a.Tq, A5_ROWS), a.H / 2, a.B);
     SER_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(A5_THREADS), smem, s, tmQ, tmG, tmK, tmV, a.kmask, reinterpret_cast<const bf16*>(a.O), a.ldo,
                                         reinterpret_cast<const bf16*>(a.dO), a.lddo, a.lse, a.delta,
-                                        reinterpret_cast<bf16*>(a.dQ), a.lddq, a.H, a.Tq, a.Tk, a.scale, a.drop));
+                                        reinterpret_cast<bf16*>(a.dQ), a.lddq, a.H, a.Tq, a.Tk, a.scale, a.drop,
+                                        static_cast<const unsigned*>(a.keep_bits)));
     SER_LAUNCH_CHECK();
   }
   {
@@ -844,7 +901,8 @@ int attention_bwd_tc5(const AttnArgs& a, cudaStream_t s) {
     }
     dim3 grid(ceil_div(a.Tk, A5_ROWS), a.H / 2, a.B);
     SER_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(A5_THREADS), smem, s, tmK, tmV, tmQ, tmG, a.kmask, a.lse, a.delta, reinterpret_cast<bf16*>(a.dK), a.lddk,
-                                        reinterpret_cast<bf16*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale, a.drop));
+                                        reinterpret_cast<bf16*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale, a.drop,
+                                        static_cast<const unsigned*>(a.keep_bits)));
     SER_LAUNCH_CHECK();
   }
   return SER_OK;

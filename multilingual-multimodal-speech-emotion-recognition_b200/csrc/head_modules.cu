@@ -247,14 +247,14 @@ static int xattn_fwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
   at.K = off(d.p_t, S, dt); at.ldk = S3;
   at.V = off(d.p_t, 2 * S, dt); at.ldv = S3;
   at.kmask = d.t_mask; at.O = d.ctx_a; at.ldo = S; at.lse = d.lse_a;
-  at.drop = with_site(drop, DS_XA_PROB_A);
+  at.drop = with_site(drop, DS_XA_PROB_A); at.keep_bits = d.keep_a;
   SER_TRY(attention_fwd(at, s));
   at.Tq = d.Tt; at.Tk = d.Ta;
   at.Q = d.p_t;
   at.K = off(d.p_a, S, dt);
   at.V = off(d.p_a, 2 * S, dt);
   at.kmask = d.a_mask; at.O = d.ctx_t; at.lse = d.lse_t;
-  at.drop = with_site(drop, DS_XA_PROB_T);
+  at.drop = with_site(drop, DS_XA_PROB_T); at.keep_bits = d.keep_t;
   SER_TRY(attention_fwd(at, s));
   // z = x + dropout(ctx Wz^T + bz): with dropout on, mask and residual move from the GEMM epilogue into the
   // LayerNorm kernel's prologue (which also saves z for the backward)
@@ -348,13 +348,13 @@ static int xattn_bwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
   at.Q = d.p_a; at.K = off(d.p_t, S, dt); at.V = off(d.p_t, 2 * S, dt);
   at.kmask = d.t_mask; at.O = d.ctx_a; at.lse = d.lse_a; at.dO = dctx_a; at.delta = delta_a;
   at.dQ = dp_a; at.dK = off(dp_t, S, dt); at.dV = off(dp_t, 2 * S, dt);
-  at.drop = with_site(drop, DS_XA_PROB_A);
+  at.drop = with_site(drop, DS_XA_PROB_A); at.keep_bits = d.keep_a;
   SER_TRY(attention_bwd(at, s));
   at.Tq = d.Tt; at.Tk = d.Ta;
   at.Q = d.p_t; at.K = off(d.p_a, S, dt); at.V = off(d.p_a, 2 * S, dt);
   at.kmask = d.a_mask; at.O = d.ctx_t; at.lse = d.lse_t; at.dO = dctx_t; at.delta = delta_t;
   at.dQ = dp_t; at.dK = off(dp_a, S, dt); at.dV = off(dp_a, 2 * S, dt);
-  at.drop = with_site(drop, DS_XA_PROB_T);
+  at.drop = with_site(drop, DS_XA_PROB_T); at.keep_bits = d.keep_t;
   SER_TRY(attention_bwd(at, s));
   // p = x Wc^T + bc
   struct SideP { int M; void* dp; const void* x; void* dx; const void* dz; const void* wc; const void* wbd; const void* wqkv;
@@ -416,7 +416,7 @@ int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s) {
   at.K = off(d.p_t, S, dt); at.ldk = S3;
   at.V = off(d.p_t, 2 * S, dt); at.ldv = S3;
   at.kmask = d.t_mask; at.O = d.ctx_a; at.ldo = S; at.lse = d.lse_a;
-  at.drop = with_site(drop, DS_XA_PROB_A);
+  at.drop = with_site(drop, DS_XA_PROB_A); at.keep_bits = d.keep_a;
   SER_TRY(attention_fwd(at, s));
   // T <- A
   at.Tq = d.Tt; at.Tk = d.Ta;
@@ -424,7 +424,7 @@ int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s) {
   at.K = off(d.p_a, S, dt);
   at.V = off(d.p_a, 2 * S, dt);
   at.kmask = d.a_mask; at.O = d.ctx_t; at.lse = d.lse_t;
-  at.drop = with_site(drop, DS_XA_PROB_T);
+  at.drop = with_site(drop, DS_XA_PROB_T); at.keep_bits = d.keep_t;
   SER_TRY(attention_fwd(at, s));
   // out_proj, out_a / out_t, dropout, + residual, LayerNorm (cross_attention.py:42-43,50-51)
   SER_TRY(linear_fwd(dt, Ma, S, S, d.ctx_a, S, d.wo_a, S, d.bo_a, d.o_a, S, f, ACT_NONE, nullptr, 0, f, s));
@@ -511,14 +511,14 @@ int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
   at.Q = d.p_a; at.K = off(d.p_t, S, dt); at.V = off(d.p_t, 2 * S, dt);
   at.kmask = d.t_mask; at.O = d.ctx_a; at.lse = d.lse_a; at.dO = dctx_a; at.delta = delta_a;
   at.dQ = dp_a; at.dK = off(dp_t, S, dt); at.dV = off(dp_t, 2 * S, dt);
-  at.drop = with_site(drop, DS_XA_PROB_A);
+  at.drop = with_site(drop, DS_XA_PROB_A); at.keep_bits = d.keep_a;
   SER_TRY(attention_bwd(at, s));
   // T <- A
   at.Tq = d.Tt; at.Tk = d.Ta;
   at.Q = d.p_t; at.K = off(d.p_a, S, dt); at.V = off(d.p_a, 2 * S, dt);
   at.kmask = d.a_mask; at.O = d.ctx_t; at.lse = d.lse_t; at.dO = dctx_t; at.delta = delta_t;
   at.dQ = dp_t; at.dK = off(dp_a, S, dt); at.dV = off(dp_a, 2 * S, dt);
-  at.drop = with_site(drop, DS_XA_PROB_T);
+  at.drop = with_site(drop, DS_XA_PROB_T); at.keep_bits = d.keep_t;
   SER_TRY(attention_bwd(at, s));
   // MHA in-projection backward
   struct InProjB { const void* dp; const void* src; int M; int col; const void* w; float* dw; float* db; int wrow; void* dsrc; };

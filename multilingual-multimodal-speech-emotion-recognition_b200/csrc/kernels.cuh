@@ -68,6 +68,9 @@ struct AttnArgs {
   // dropout on the attention weights (nn.MultiheadAttention(dropout=p)): site [B*H*Tq, Tk]; off by default
   DropSpec drop;
   int impl = 0;             // bf16 tier: 0 = choose (tcgen05 kernels when the shape qualifies), 1 = mma.sync, 2 = tcgen05
+  // optional keep bits of the attention-weight dropout, [B*H*Tq, ceil(Tk/32)] words (tcgen05 kernels: the forward writes
+  // them, the backward kernels read them instead of re-hashing); nullptr = regenerate from the seed
+  unsigned* keep_bits = nullptr;
 };
 int attention_fwd(const AttnArgs& a, cudaStream_t s);
 int attention_bwd(const AttnArgs& a, cudaStream_t s);

@@ -9,6 +9,7 @@
 // A sample whose frames are all padded yields NaN (softmax over all -inf), as in the reference.
 #include "kernels.cuh"
 #include "prof.cuh"
+#include <stdlib.h>
 
 namespace ser {
 
@@ -331,6 +332,21 @@ mix_bwd_kernel(const T* __restrict__ pa, const T* __restrict__ pt, const T* __re
   if (threadIdx.x == 0) { atomicAdd(dbga, smem[2 * G]); atomicAdd(dbgt, smem[2 * G + 1]); }
 }
 
+// column slab of the statistics kernels (SER_ASP_SLAB: A/B switch)
+int asp_slab(int D) {
+  static const int env = getenv("SER_ASP_SLAB") ? atoi(getenv("SER_ASP_SLAB")) : 0;
+  if ((env == 256 || env == 128 || env == 64) && D % env == 0) return env;
+  return (D % 256 == 0) ? 256 : (D % 128 == 0) ? 128 : 64;
+}
+
+template <typename T, int SLAB>
+int asp_bwd_stats_launch(const AspArgs& a, cudaStream_t s) {
+  SER_CUDA_CHECK(launch_pdl(asp_bwd_stats_kernel<T, SLAB>, dim3(a.D / SLAB, a.B), dim3(NTH), 0, s, reinterpret_cast<const T*>(a.x),
+                            a.alpha, a.out, a.out_f32, a.dout, a.dout_f32, reinterpret_cast<T*>(a.dx), a.dalpha, a.T, a.D));
+  SER_LAUNCH_CHECK();
+  return SER_OK;
+}
+
 template <typename T, int SLAB>
 int asp_stats_launch(const AspArgs& a, cudaStream_t s) {
   constexpr int RG = SlabCfg<SLAB>::kRG;
@@ -351,22 +367,17 @@ int asp_fwd_impl(const AspArgs& a, cudaStream_t s) {
   const int rows_per_cta = 8 * (32 / (a.Hd >> 3));
   SER_CUDA_CHECK(launch_pdl(asp_score_kernel<T>, dim3(ceil_div(M, rows_per_cta)), dim3(256), 0, s, reinterpret_cast<const T*>(a.u), a.w2, a.b2, a.e, M, a.Hd));
   SER_LAUNCH_CHECK();
-  return (a.D % 256 == 0) ? asp_stats_launch<T, 256>(a, s) : asp_stats_launch<T, 64>(a, s);
+  const int slab = asp_slab(a.D);
+  return slab == 256 ? asp_stats_launch<T, 256>(a, s) : slab == 128 ? asp_stats_launch<T, 128>(a, s) : asp_stats_launch<T, 64>(a, s);
 }
 
 template <typename T>
 int asp_bwd_impl(const AspArgs& a, cudaStream_t s) {
   ProfScope prof("asp_bwd", 0.0, sizeof(T) * static_cast<double>(a.B) * a.T * (2.0 * a.D + 2.0 * a.Hd), s);
   SER_TRY(zero_async(a.dalpha, sizeof(float) * a.B * a.T, s));
-  if (a.D % 256 == 0)
-    SER_CUDA_CHECK(launch_pdl(asp_bwd_stats_kernel<T, 256>, dim3(dim3(a.D / 256, a.B)), dim3(NTH), 0, s, reinterpret_cast<const T*>(a.x), a.alpha, a.out,
-                                                                      a.out_f32, a.dout, a.dout_f32,
-                                                                      reinterpret_cast<T*>(a.dx), a.dalpha, a.T, a.D));
-  else
-    SER_CUDA_CHECK(launch_pdl(asp_bwd_stats_kernel<T, 64>, dim3(dim3(a.D / 64, a.B)), dim3(NTH), 0, s, reinterpret_cast<const T*>(a.x), a.alpha, a.out,
-                                                                    a.out_f32, a.dout, a.dout_f32,
-                                                                    reinterpret_cast<T*>(a.dx), a.dalpha, a.T, a.D));
-  SER_LAUNCH_CHECK();
+  const int slab = asp_slab(a.D);
+  SER_TRY(slab == 256 ? (asp_bwd_stats_launch<T, 256>(a, s)) : slab == 128 ? (asp_bwd_stats_launch<T, 128>(a, s))
+                                                                         : (asp_bwd_stats_launch<T, 64>(a, s)));
   const size_t smem = sizeof(float) * (a.T + 32 + a.Hd);
   auto kern = asp_bwd_score_kernel<T>;
   if (smem > 48 * 1024) SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

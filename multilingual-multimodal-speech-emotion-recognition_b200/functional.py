@@ -219,6 +219,11 @@ class CrossAttentionFn(torch.autograd.Function):
         if folded:
             sv["fold_w"] = E(2 * 9 * S * S + 2 * 3 * S * D + 2 * D * S)
             sv["fold_b"] = F(2 * 3 * S + 2 * D)
+        if ty == torch.bfloat16 and seed is not None and p_drop > 0.0:
+            # one bit per attention weight: the forward kernel records its dropout decisions, the backward kernels read them
+            I32 = lambda n: torch.empty(n, device=dev, dtype=torch.int32)  # noqa: E731
+            sv["keep_a"] = I32(B * num_heads * Ta * ((Tt + 31) // 32))
+            sv["keep_t"] = I32(B * num_heads * Tt * ((Ta + 31) // 32))
         enh_a, enh_t = E(Ma, D), E(Mt, D)
         w = CrossAttentionFn._weights(fp, wc)
         keep = []

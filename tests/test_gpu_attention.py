@@ -51,6 +51,39 @@ def test_attention_core_against_fp64(shape, impl):
         assert err < (1e-2 if small else 2e-2), (k, err)
 
 
+@pytest.mark.parametrize("shape", [(3, 70, 19, True, 0.1), (2, 300, 130, True, 0.25), (2, 129, 65, True, 0.1),
+                                   (1, 610, 250, True, 0.1), (2, 33, 97, False, 0.15)],
+                         ids=lambda s: f"B{s[0]}_Tq{s[1]}_Tk{s[2]}_p{s[4]}")
+def test_stored_keep_bits_reproduce_the_rehashed_masks(shape):
+    """tcgen05 kernels with a keep_bits buffer (the forward records its dropout decisions, dQ and dK/dV read them --
+    dK/dV through a 32 x 32 bit transpose across the warp) against (a) the exported masks, bit for bit, (b) the fp64
+    reference driven by those masks, (c) the same kernels re-hashing every element."""
+    A = _tools()
+    import numpy as np
+    B, Tq, Tk, masked, p = shape
+    g = torch.Generator().manual_seed(7 + Tq)
+    qb = (torch.randn(B * Tq, A.S3, generator=g) * 1.5).to(A.dev).bfloat16()
+    kvb = (torch.randn(B * Tk, A.S3, generator=g) * 1.5).to(A.dev).bfloat16()
+    kmask = None
+    if masked:
+        lens = torch.randint(max(1, Tk // 4), Tk + 1, (B,), generator=g)
+        kmask = (torch.arange(Tk)[None] < lens[:, None]).float().to(A.dev)
+    dO = torch.randn(B * Tq, 256, generator=g).to(A.dev).bfloat16()
+    sd = torch.tensor([0x0123456789ABCDEF + Tk], dtype=torch.int64, device=A.dev)
+    mm = A.dropout_mask(sd, 1, p, B * 8 * Tq, Tk)
+    out_hash = A.run(2, B, 8, Tq, Tk, qb, kvb[:, 256:], kvb[:, 512:], kmask, p, sd, 1, dO)
+    out_bits = A.run(2, B, 8, Tq, Tk, qb, kvb[:, 256:], kvb[:, 512:], kmask, p, sd, 1, dO, keepbits=True)
+    W = (Tk + 31) // 32
+    words = out_bits["keep_bits"].view(B * 8 * Tq, W).cpu().numpy().astype(np.uint32)
+    bits = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).reshape(B * 8 * Tq, W * 32)[:, :Tk]
+    assert np.array_equal(bits.astype(bool), (mm > 0).cpu().numpy())
+    ref = A.reference(B, 8, Tq, Tk, qb, kvb[:, 256:512], kvb[:, 512:], kmask, mm.view(B, 8, Tq, Tk), dO)
+    for k in ("O", "lse", "dQ", "dK", "dV"):
+        assert A.rel(out_bits[k], ref[k]) < 2e-2, k
+        assert A.rel(out_bits[k], out_hash[k]) < 1e-4, k        # same decisions; one FMA contracts differently
+    assert torch.equal(torch.nan_to_num(out_bits["O"].float()), torch.nan_to_num(out_hash["O"].float()))
+
+
 @pytest.mark.parametrize("impl", [2, 1], ids=["tcgen05", "mma_sync"])
 def test_fully_padded_sample_is_nan_and_stays_in_its_sample(impl):
     """A sample whose keys are all padded yields NaN for its own queries (softmax over all -inf, as the reference) and

@@ -16,7 +16,7 @@ lib = L.load()
 DH, S3 = 32, 768
 
 
-def run(impl, B, H, Tq, Tk, q, k, v, kmask, p_drop=0.0, seed=None, site=1, dO=None):
+def run(impl, B, H, Tq, Tk, q, k, v, kmask, p_drop=0.0, seed=None, site=1, dO=None, keepbits=False):
     """q/k/v: [B*T, 768] bf16 projection buffers (heads in the first / second / third 256 columns as in p_a / p_t)."""
     d = L.AttnDesc()
     keep = []
@@ -26,7 +26,11 @@ def run(impl, B, H, Tq, Tk, q, k, v, kmask, p_drop=0.0, seed=None, site=1, dO=No
              ldo=H * DH, lse=lse, scale=1.0 / math.sqrt(DH), impl=impl, drop_site=site)
     if p_drop > 0:
         f.update(p_drop=p_drop, drop_seed=seed)
+        if keepbits:      # dropout decisions stored by the forward kernel, read by the backward kernels (garbage-filled first)
+            f.update(keep_bits=torch.randint(-2**31, 2**31 - 1, (B * H * Tq * ((Tk + 31) // 32),), device=dev, dtype=torch.int32))
     out = {"O": O, "lse": lse}
+    if "keep_bits" in f:
+        out["keep_bits"] = f["keep_bits"]
     if dO is not None:
         dq = torch.zeros(B * Tq, S3, device=dev, dtype=torch.bfloat16)
         dkv = torch.zeros(B * Tk, S3, device=dev, dtype=torch.bfloat16)
@@ -96,6 +100,15 @@ def case(B, H, Tq, Tk, masked, p_drop, bwd, seed):
         res[impl] = {kk: rel(out[kk], ref[kk]) for kk in ref}
     tag = f"B{B} H{H} Tq{Tq} Tk{Tk} {'mask' if masked else 'nomask'} p={p_drop}"
     bad = any(not (vv < 3e-2) for vv in res[2].values())
+    if p_drop > 0:
+        # stored keep bits must reproduce the re-hashed result: same decisions, so identical up to the rounding of one
+        # fused multiply-add (mask * g - delta contracts differently around a select): a handful of bf16 last-place flips
+        o2 = run(2, B, H, Tq, Tk, qb, k, v, kmask, p_drop, sd, 1, dO)
+        o3 = run(2, B, H, Tq, Tk, qb, k, v, kmask, p_drop, sd, 1, dO, keepbits=True)
+        worst = max(rel(o3[kk], o2[kk]) for kk in o2)      # (o2 has no keep_bits entry)
+        same = worst < 1e-4 and torch.equal(torch.nan_to_num(o2["O"].float()), torch.nan_to_num(o3["O"].float()))
+        tag += f" bits:{worst:.0e}"
+        bad = bad or not same
     print(f"{'FAIL' if bad else 'ok  '} {tag:38s} tcgen05: " + " ".join(f"{kk}={vv:.2e}" for kk, vv in res[2].items()) +
           "   | mma.sync: " + " ".join(f"{kk}={vv:.2e}" for kk, vv in res[1].items()), flush=True)
     return not bad
@@ -110,7 +123,12 @@ def timing(B, H, Tq, Tk, bwd, p_drop=0.1):
     dO = torch.randn(B * Tq, H * DH, generator=g).to(dev).bfloat16() if bwd else None
     sd = torch.tensor([77], dtype=torch.int64, device=dev)
     line = f"time B{B} Tq{Tq} Tk{Tk} {'fwd+bwd' if bwd else 'fwd'} p={p_drop}: "
-    for impl in (1, 2):
+    kb = torch.zeros(B * H * Tq * ((Tk + 31) // 32), device=dev, dtype=torch.int32)
+    for impl in (1, 2, 3):
+        keepbits = impl == 3
+        if keepbits and not p_drop > 0:
+            continue
+        impl = min(impl, 2)
         for _ in range(3):
             run(impl, B, H, Tq, Tk, qb, kvb[:, 256:], kvb[:, 512:], kmask, p_drop, sd, 1, dO)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -124,6 +142,8 @@ def timing(B, H, Tq, Tk, bwd, p_drop=0.1):
                  scale=1.0 / math.sqrt(DH), impl=impl, drop_site=1)
         if p_drop > 0:
             f.update(p_drop=p_drop, drop_seed=sd.data_ptr())
+            if keepbits:
+                f.update(keep_bits=kb.data_ptr())
         if bwd:
             f.update(dO=dO.data_ptr(), lddo=H * DH, dQ=dq.data_ptr(), lddq=S3, dK=dkv[:, 256:].data_ptr(), lddk=S3,
                      dV=dkv[:, 512:].data_ptr(), lddv=S3, delta=delta.data_ptr())
@@ -139,7 +159,7 @@ def timing(B, H, Tq, Tk, bwd, p_drop=0.1):
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / n * 1e3
         fl = (14.0 if bwd else 4.0) * B * H * Tq * Tk * DH
-        line += f"{'mma.sync' if impl == 1 else 'tcgen05'} {us:8.1f} us ({fl / us / 1e6:6.1f} TFLOP/s)   "
+        line += f"{'mma.sync' if impl == 1 else ('tcgen05+bits' if keepbits else 'tcgen05')} {us:8.1f} us ({fl / us / 1e6:6.1f} TFLOP/s)   "
     print(line, flush=True)
 
 
@@ -149,7 +169,8 @@ if __name__ == "__main__":
     for i, (B, Tq, Tk, masked, p) in enumerate([(3, 70, 19, True, 0.0), (3, 70, 19, False, 0.0), (2, 300, 130, True, 0.0),
                                                 (4, 250, 64, True, 0.0), (4, 64, 250, True, 0.0), (2, 1500, 256, True, 0.0),
                                                 (2, 256, 1500, True, 0.0), (3, 70, 19, True, 0.1), (2, 300, 130, True, 0.25),
-                                                (1, 1, 1, False, 0.0), (2, 129, 65, True, 0.1)]):
+                                                (1, 1, 1, False, 0.0), (2, 129, 65, True, 0.1), (2, 1500, 256, True, 0.1),
+                                                (2, 256, 1500, True, 0.15), (3, 33, 97, False, 0.1)]):
         ok = case(B, 8, Tq, Tk, masked, p, bwd, 10 + i) and ok
     print("ALL OK" if ok else "SOME FAILED", flush=True)
     if "--time" in sys.argv:
