@@ -181,6 +181,11 @@ typedef struct ser_xattn_desc {
    * writes them while it applies the mask, the two backward kernels read them instead of re-hashing every element
    * (the hash was > 50 % of their instruction stream).  NULL = regenerate from the seed.                              */
   unsigned int* keep_a; unsigned int* keep_t;
+  /* forward only, inference: non-zero = p_t (and qkv_t, or fold_w / fold_b on the folded path) still hold the
+   * projections of THIS text batch under THESE weights from an earlier ser_xattn_fwd call with the same buffers --
+   * the text-side projection GEMMs and the weight folding are skipped.  Test-time augmentation evaluates V audio views
+   * of one utterance against the same text (src/eval.py:186-190): 4 of 5 calls take this path.                  */
+  int reuse_text;
   /* backward */
   const void* d_enh_a; const void* d_enh_t;
   void* da; void* dt;                      /* [M,D] act gradients w.r.t. the inputs               */
@@ -306,7 +311,7 @@ int ser_fusion_bwd(const ser_fusion_desc* d, void* stream);
  * loss is identically zero with exactly-zero gradients (classifier.py:64-68).     */
 typedef struct ser_clf_desc {
   int dtype; int B, P, F, C, L, U;         /* 512, 256, classes, 35, 64                           */
-  const void* x;                           /* [B,P] act                                           */
+  const void* x;                           /* [B,Pin] act (Pin = P unless the last field says otherwise) */
   const void* w_in; const float* b_in; const float* ln_in_g; const float* ln_in_b;
   const void* const* w1; const float* const* b1; const void* const* w2; const float* const* b2;
   const float* const* lno_g; const float* const* lno_b; const float* const* lni_g; const float* const* lni_b;
@@ -327,7 +332,7 @@ typedef struct ser_clf_desc {
   float p_drop; const unsigned long long* drop_seed;   /* all classifier dropouts; 0 / NULL = off; h[0], r, f, u1 are saved post-dropout */
   /* backward */
   const float* dlogits; const float* dunc; /* [B,C]; [B,1] or NULL                                */
-  void* dx;                                /* [B,P] act                                           */
+  void* dx;                                /* [B,Pin] act                                         */
   float* dw_in; float* db_in; float* dln_in_g; float* dln_in_b;
   float* const* dw1; float* const* db1; float* const* dw2; float* const* db2;
   float* const* dlno_g; float* const* dlno_b; float* const* dlni_g; float* const* dlni_b;  /* ACCUMULATED: pass zeroed */
@@ -335,6 +340,8 @@ typedef struct ser_clf_desc {
   float* dw_c; float* db_c; float* dw_u1; float* db_u1; float* dw_u2; float* db_u2;
   void* ws; size_t ws_bytes;               /* ser_clf_bwd_ws_bytes()                              */
   int grads_zeroed;
+  int Pin;                                 /* width of x and dx (DeepClassifier input_dim, classifier.py:96-105); 0 = P.
+                                            * bf16 tier: a multiple of 128 (dx is a tcgen05 GEMM output)          */
 } ser_clf_desc;
 size_t ser_clf_bwd_ws_bytes(int dtype, int B, int P, int F, int C, int U);
 int ser_clf_fwd(const ser_clf_desc* d, void* stream);

@@ -226,18 +226,20 @@ static int xattn_fwd_folded(const ser_xattn_desc& d, cudaStream_t s) {
   const int S = d.S, D = d.D, S3 = 3 * d.S;
   const int Ma = d.B * d.Ta, Mt = d.B * d.Tt;
   const FoldBufs fb = fold_bufs(d);
-  // weight-only part: block-diagonal in-projections, folded weights and biases
-  SER_TRY(fold_assemble(d.win_a, d.win_t, fb.wbd_a, fb.wbd_t, S, s));
-  SER_TRY(small_gemm2(S3, D, S3, fb.wbd_a, fb.wbd_t, S3, 0, d.wqkv_a, d.wqkv_t, D, 1, fb.wc_a, fb.wc_t, D, 0, s));   // Wc = Wbd Wqkv
-  SER_TRY(small_gemm2(D, S, S, d.wout_a, d.wout_t, S, 0, d.wo_a, d.wo_t, S, 1, fb.wz_a, fb.wz_t, S, 0, s));           // Wz = Wout Wo
-  FoldBiasArgs ba{};
-  ba.S = S; ba.D = D; ba.win_a = d.win_a; ba.win_t = d.win_t; ba.bin_a = d.bin_a; ba.bin_t = d.bin_t;
-  ba.bqkv_a = d.bqkv_a; ba.bqkv_t = d.bqkv_t; ba.wout_a = d.wout_a; ba.wout_t = d.wout_t; ba.bo_a = d.bo_a; ba.bo_t = d.bo_t;
-  ba.bout_a = d.bout_a; ba.bout_t = d.bout_t; ba.bc_a = fb.bc_a; ba.bc_t = fb.bc_t; ba.bz_a = fb.bz_a; ba.bz_t = fb.bz_t;
-  SER_TRY(fold_bias_fwd(ba, s));
+  if (!d.reuse_text) {      // (reuse_text: the folded weights of an earlier call with these buffers are still valid)
+    // weight-only part: block-diagonal in-projections, folded weights and biases
+    SER_TRY(fold_assemble(d.win_a, d.win_t, fb.wbd_a, fb.wbd_t, S, s));
+    SER_TRY(small_gemm2(S3, D, S3, fb.wbd_a, fb.wbd_t, S3, 0, d.wqkv_a, d.wqkv_t, D, 1, fb.wc_a, fb.wc_t, D, 0, s));   // Wc = Wbd Wqkv
+    SER_TRY(small_gemm2(D, S, S, d.wout_a, d.wout_t, S, 0, d.wo_a, d.wo_t, S, 1, fb.wz_a, fb.wz_t, S, 0, s));           // Wz = Wout Wo
+    FoldBiasArgs ba{};
+    ba.S = S; ba.D = D; ba.win_a = d.win_a; ba.win_t = d.win_t; ba.bin_a = d.bin_a; ba.bin_t = d.bin_t;
+    ba.bqkv_a = d.bqkv_a; ba.bqkv_t = d.bqkv_t; ba.wout_a = d.wout_a; ba.wout_t = d.wout_t; ba.bo_a = d.bo_a; ba.bo_t = d.bo_t;
+    ba.bout_a = d.bout_a; ba.bout_t = d.bout_t; ba.bc_a = fb.bc_a; ba.bc_t = fb.bc_t; ba.bz_a = fb.bz_a; ba.bz_t = fb.bz_t;
+    SER_TRY(fold_bias_fwd(ba, s));
+  }
   // token-level part
   SER_TRY(linear_fwd(dt, Ma, S3, D, d.a, D, fb.wc_a, D, fb.bc_a, d.p_a, S3, f, ACT_NONE, nullptr, 0, f, s));
-  SER_TRY(linear_fwd(dt, Mt, S3, D, d.t, D, fb.wc_t, D, fb.bc_t, d.p_t, S3, f, ACT_NONE, nullptr, 0, f, s));
+  if (!d.reuse_text) SER_TRY(linear_fwd(dt, Mt, S3, D, d.t, D, fb.wc_t, D, fb.bc_t, d.p_t, S3, f, ACT_NONE, nullptr, 0, f, s));
   const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);
   AttnArgs at{};
   at.dtype = dt; at.B = d.B; at.H = d.H; at.dh = S / d.H;
@@ -391,7 +393,7 @@ int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s) {
   SER_REQUIRE(d.qkv_a && d.qkv_t && d.o_a && d.o_t, "xattn: the unfolded path needs full-size qkv_* / o_* buffers");
   // outer projections, one packed GEMM per modality (cross_attention.py:38-40,46-48)
   SER_TRY(linear_fwd(dt, Ma, S3, D, d.a, D, d.wqkv_a, D, d.bqkv_a, d.qkv_a, S3, f, ACT_NONE, nullptr, 0, f, s));
-  SER_TRY(linear_fwd(dt, Mt, S3, D, d.t, D, d.wqkv_t, D, d.bqkv_t, d.qkv_t, S3, f, ACT_NONE, nullptr, 0, f, s));
+  if (!d.reuse_text) SER_TRY(linear_fwd(dt, Mt, S3, D, d.t, D, d.wqkv_t, D, d.bqkv_t, d.qkv_t, S3, f, ACT_NONE, nullptr, 0, f, s));
   // MHA in-projections (torch/nn/functional.py:5798 chunking): attn_a takes (qa, kt, vt), attn_t takes (qt, ka, va)
   struct InProj { const void* src; int M; int scol; const void* w; const float* b; int wrow; void* dst; int dcol; };
   const InProj ip[6] = {
@@ -403,6 +405,7 @@ int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s) {
       {d.qkv_a, Ma, 2 * S, d.win_t, d.bin_t, 2 * S, d.p_a, 2 * S},
   };
   for (const InProj& p : ip) {
+    if (d.reuse_text && p.dst == d.p_t) continue;          // text-side projections of an earlier view
     SER_TRY(linear_fwd(dt, p.M, S, S, off(p.src, p.scol, dt), S3, off(p.w, static_cast<long long>(p.wrow) * S, dt), S,
                        p.b + p.wrow, off(p.dst, p.dcol, dt), S3, f, ACT_NONE, nullptr, 0, f, s));
   }
@@ -710,7 +713,8 @@ int clf_fwd(const ser_clf_desc& d, cudaStream_t s) {
   const size_t BP = static_cast<size_t>(B) * P;
   SER_REQUIRE(B > 0 && d.x && d.h && d.y && d.n && d.r && d.logits, "clf_fwd: null tensor");
   // input_projection: Linear -> LayerNorm -> ReLU (classifier.py:105-110)
-  SER_TRY(linear_fwd(dt, B, P, P, d.x, P, d.w_in, P, d.b_in, d.p0, P, 1, ACT_NONE, nullptr, 0, 1, s));
+  const int Pin = d.Pin > 0 ? d.Pin : P;             // DeepClassifier(input_dim != base_dim): only this GEMM sees input_dim
+  SER_TRY(linear_fwd(dt, B, P, Pin, d.x, Pin, d.w_in, Pin, d.b_in, d.p0, P, 1, ACT_NONE, nullptr, 0, 1, s));
   SER_TRY(layernorm_fwd(d.p0, 1, d.h, 1, nullptr, 1, d.ln_in_g, d.ln_in_b, d.stats0, B, P, 1, s));
   const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);
   if (drop.on()) SER_TRY(dropout_apply(d.h, d.h, nullptr, 1, B, P, with_site(drop, DS_CLF_IN), s));   // input_projection[3]
@@ -860,9 +864,10 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
   SER_ZERO_UNLESS(d.grads_zeroed, d.dln_in_b, sizeof(float) * P);
   SER_TRY(layernorm_bwd(cur, 1, d.p0, 1, d.stats0, d.ln_in_g, d.ln_in_b, nullptr, 1, dp0, f, nullptr, 1, d.dln_in_g,
                         d.dln_in_b, B, P, 1, s));
-  SER_TRY(linear_wgrad(dt, B, P, P, dp0, P, d.x, P, d.dw_in, P, s, d.db_in, d.grads_zeroed));
+  const int Pin = d.Pin > 0 ? d.Pin : P;
+  SER_TRY(linear_wgrad(dt, B, P, Pin, dp0, P, d.x, Pin, d.dw_in, Pin, s, d.db_in, d.grads_zeroed));
   if (d.dx != nullptr)
-    SER_TRY(linear_dgrad(dt, B, P, P, dp0, P, d.w_in, P, d.dx, P, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
+    SER_TRY(linear_dgrad(dt, B, P, Pin, dp0, P, d.w_in, Pin, d.dx, Pin, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
   return SER_OK;
 }
 

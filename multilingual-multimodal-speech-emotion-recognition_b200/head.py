@@ -145,6 +145,26 @@ class FusionHead(nn.Module):
         fused = self.fusion(a_vec, t_vec)
         return dict(a_enh=a_enh, t_enh=t_enh, a_vec=a_vec, t_vec=t_vec, fused=fused)
 
+    @torch.no_grad()
+    def forward_views(self, audio_views, t_hid, a_mask=None, t_mask=None, use_openmax: bool = True) -> torch.Tensor:
+        """Test-time augmentation (src/eval.py:174-190): V audio views of the same utterances against ONE text batch ->
+        logits [V, B, C] (OpenMax-recalibrated in eval mode, as classifier.forward does).  Equal to calling the head once
+        per view, but everything that depends on the text alone is computed once: the text adapter, the text-side
+        q / k / v projections (and the folded projection weights) of cross attention -- SURVEY.md section 8(d), cfg5."""
+        flats = [getattr(self, g)._flat for g in self.GROUPS if hasattr(getattr(self, g), "_flat")]
+        t_seq = self.adapter_t.residual_forward(t_hid)
+        cache: dict = {}
+        logits = []
+        for a_hid in audio_views:
+            FlatParams.precast(flats, a_hid.dtype)
+            a_seq = self.adapter_a.residual_forward(a_hid)
+            a_enh, t_enh = self.cross(a_seq, t_seq, a_mask, t_mask, _text_cache=cache)
+            pooled = torch.empty(2, a_enh.shape[0], 2 * a_enh.shape[2], device=a_enh.device, dtype=a_enh.dtype)
+            self.pool_a._out_buffer, self.pool_t._out_buffer = pooled[0], pooled[1]
+            fused = self.fusion(self.pool_a(a_enh, a_mask), self.pool_t(t_enh, t_mask))
+            logits.append(self.classifier(fused, use_openmax=use_openmax))
+        return torch.stack(logits)
+
     def forward(self, a_hid: torch.Tensor, t_hid: torch.Tensor, a_mask: Optional[torch.Tensor] = None,
                 t_mask: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
                 loss_cfg: Optional[dict] = None) -> Dict[str, torch.Tensor]:

@@ -75,8 +75,8 @@ class AdvancedOpenMaxClassifier(nn.Module):
     def __init__(self, input_dim: int, num_labels: int, num_layers: int = 35, base_dim: int = 512, dropout: float = 0.1,
                  alpha: float = 20.0):
         super().__init__()
-        if input_dim != base_dim:
-            raise ValueError("the fused stack expects input_dim == base_dim (512 in every reference script)")
+        # (input_dim may differ from base_dim, as in the reference: only input_projection[0] sees it; bf16 inputs need a
+        #  multiple of 128 -- every reference script uses 512 / 512)
         self.num_labels, self.alpha, self.num_layers, self.p_drop = num_labels, alpha, num_layers, float(dropout)
         self.deep_classifier = DeepClassifier(input_dim, num_labels, num_layers, base_dim, dropout)
         self.anchor_clustering = ClassAnchorClustering(base_dim // 2, num_labels, anchor_dim=128)

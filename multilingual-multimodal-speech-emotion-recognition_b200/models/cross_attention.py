@@ -44,10 +44,13 @@ class CrossModalAttention(nn.Module):
         self._drop_seed = DropoutSeed()
 
     def forward(self, audio_seq: torch.Tensor, text_seq: torch.Tensor, audio_mask: Optional[torch.Tensor] = None,
-                text_mask: Optional[torch.Tensor] = None):
+                text_mask: Optional[torch.Tensor] = None, _text_cache: Optional[dict] = None):
+        """Reference signature (cross_attention.py:32).  `_text_cache` (inference only, optional): a dict shared by the
+        calls that evaluate several audio views against ONE text batch -- the text-side projections are computed by the
+        first call and reused by the others (FusionHead.forward_views)."""
         # attention-weight dropout of both nn.MultiheadAttention modules and self.dropout on the branch outputs
         # (cross_attention.py:18,25,43,51) run inside the kernels; `self.dropout.p` is the single rate, as in the reference
         p = active_dropout(self, self.dropout.p)
         seed = self._drop_seed.next(audio_seq.device) if p > 0.0 else None
         return CrossAttentionFn.apply(audio_seq, text_seq, audio_mask, text_mask, self._flat, self.num_heads, p, seed,
-                                      *self._flat.params)
+                                      _text_cache, *self._flat.params)

@@ -106,10 +106,10 @@ def fusion_weights(seed: int = 0) -> Dict[str, torch.Tensor]:
     return w
 
 
-def classifier_weights(num_labels: int, num_layers: int = 35, seed: int = 0) -> Dict[str, torch.Tensor]:
+def classifier_weights(num_labels: int, num_layers: int = 35, seed: int = 0, input_dim: int = P) -> Dict[str, torch.Tensor]:
     w = {}
     p = "deep_classifier."
-    w[p + "input_projection.0.weight"] = _fill("clf.in.0.weight", (P, P), "xavier_w", seed)
+    w[p + "input_projection.0.weight"] = _fill("clf.in.0.weight", (P, input_dim), "xavier_w", seed)
     w[p + "input_projection.0.bias"] = _fill("clf.in.0.bias", (P,), "bias", seed)
     w[p + "input_projection.1.weight"] = _fill("clf.in.1.weight", (P,), "ln_w", seed)
     w[p + "input_projection.1.bias"] = _fill("clf.in.1.bias", (P,), "ln_b", seed)

@@ -381,10 +381,10 @@ def fusion_case(B=9, p_drop=0.0):
     return Case("fusion_dropout" if p_drop > 0 else "fusion", ins, w, oracle, cuda, grad_inputs=("av", "tv"), prepare=prep)
 
 
-def classifier_case(B=64, C=4, L=35, p_drop=0.0):
+def classifier_case(B=64, C=4, L=35, p_drop=0.0, input_dim=512):
     from mmser_b200 import models as M
-    w = {"classifier": synth.classifier_weights(C, L)}
-    ins = {"x": _rand((B, 512), 10), "ul": _rand((B, C), 11), "uu": _rand((B, 1), 12)}
+    w = {"classifier": synth.classifier_weights(C, L, input_dim=input_dim)}
+    ins = {"x": _rand((B, input_dim), 10), "ul": _rand((B, C), 11), "uu": _rand((B, 1), 12)}
 
     def oracle(i, ws):
         with O.dropout_masks(i.get("_masks")):
@@ -393,7 +393,7 @@ def classifier_case(B=64, C=4, L=35, p_drop=0.0):
         return {"logits": lg, "unc": un, "features": f}, (lg * i["ul"]).sum() + (un * i["uu"]).sum()
 
     def cuda(i, dtype, dev):
-        m = M.AdvancedOpenMaxClassifier(512, C, num_layers=L, dropout=p_drop).to(dev); m.load_state_dict(w["classifier"])
+        m = M.AdvancedOpenMaxClassifier(input_dim, C, num_layers=L, dropout=p_drop).to(dev); m.load_state_dict(w["classifier"])
         m.train()
         _pin_seed(m, "classifier", dev)
         x = i["x"].to(dev).to(dtype).requires_grad_(True)
@@ -403,7 +403,8 @@ def classifier_case(B=64, C=4, L=35, p_drop=0.0):
         return {"logits": lg, "unc": un, "features": m.last_features}, _param_grads("classifier", m), {"x": x.grad}
 
     prep = (lambda dev: {"_masks": classifier_masks(dev, p_drop, B, L)}) if p_drop > 0 else None
-    return Case(("classifier" if B == 64 else f"classifier_b{B}") + ("_dropout" if p_drop > 0 else ""), ins, w, oracle,
+    return Case(("classifier" if B == 64 else f"classifier_b{B}") + ("_dropout" if p_drop > 0 else "") +
+                ("" if input_dim == 512 else f"_in{input_dim}"), ins, w, oracle,
                 cuda, grad_inputs=("x",), prepare=prep)
 
 
@@ -512,6 +513,8 @@ ALL_CASES = {
     # two 128-row clusters of the fused stack kernel, the second one partially filled (rows >= B must stay inert)
     "classifier_b200": lambda: classifier_case(B=200, C=6),
     # the M = 128 row-group path of the fused stack kernel (B > 1152; BASELINE cfg5 runs the classifier at B = 4096)
+    # AdvancedOpenMaxClassifier(input_dim != base_dim) (classifier.py:96-105): only input_projection[0] sees input_dim
+    "classifier_in384": lambda: classifier_case(B=48, L=4, input_dim=384),
     "classifier_b1280": lambda: classifier_case(B=1280),
     "classifier_b4096": lambda: classifier_case(B=4096, C=6),
     "loss": loss_case,

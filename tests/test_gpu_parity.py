@@ -655,3 +655,29 @@ def test_unpack_frames_bit_exact(dtype):
         m2 = torch.full((B, T), 7.0, device=dev)
         unpack_frames(packed.to(dev), offsets.to(dev), T, out=out2, mask_out=m2)
         assert torch.equal(out2.cpu(), x) and torch.equal(m2.cpu(), mask)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_forward_views_equals_per_view_forward(dtype):
+    """FusionHead.forward_views (test-time augmentation, src/eval.py:174-190: V audio views, one text batch, the text-side
+    adapter / projections computed once) against one full head call per view: bit-identical logits, with fitted
+    (non-default) OpenMax buffers, and a second text batch through a fresh cache."""
+    import mmser_b200
+    from oracle import synth
+    dev = _dev()
+    C = 6
+    head = mmser_b200.FusionHead(C, num_layers=3, dropout="reference").to(dev)
+    head.load_group_state(synth.head_weights(C, 3))
+    head.eval()
+    a, t, am, tm, labels = synth.make_inputs(6, 70, 19, C, seed=21)
+    a, t, am, tm, labels = a.to(dev).to(dtype), t.to(dev).to(dtype), am.to(dev), tm.to(dev), labels.to(dev)
+    with torch.no_grad():
+        head.fit_weibull_on([(a, t, am, tm, labels)])
+        g = torch.Generator(device="cpu").manual_seed(3)
+        views = [a] + [(a.float() + 0.05 * torch.randn(a.shape, generator=g).to(dev) * am[..., None]).to(dtype) for _ in range(3)]
+        ref = torch.stack([head(v, t, am, tm)["logits"] for v in views])
+        got = head.forward_views(views, t, am, tm)
+        assert torch.equal(got, ref)
+        t2 = torch.flip(t, dims=[0]).contiguous()
+        assert torch.equal(head.forward_views(views[:2], t2, am, torch.flip(tm, dims=[0]).contiguous()),
+                           torch.stack([head(v, t2, am, torch.flip(tm, dims=[0]).contiguous())["logits"] for v in views[:2]]))
