@@ -25,6 +25,58 @@ bool pdl_enabled() {
   return on;
 }
 
+// ---- side branch (common.cuh) ----
+namespace {
+struct SideState {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[32];
+  int next = 0;
+  bool ok = false, tried = false;
+};
+SideState& side_state() {
+  static thread_local SideState st[16];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SideState& s = st[dev & 15];
+  if (!s.tried) {
+    s.tried = true;
+    const char* e = getenv("SER_SIDE_STREAM");
+    if (!(e != nullptr && atoi(e) == 0)) {
+      bool good = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+      for (int i = 0; i < 32 && good; ++i) good = cudaEventCreateWithFlags(&s.ev[i], cudaEventDisableTiming) == cudaSuccess;
+      s.ok = good;
+      if (!good) cudaGetLastError();
+    }
+  }
+  return s;
+}
+cudaEvent_t next_event(SideState& s) { cudaEvent_t e = s.ev[s.next]; s.next = (s.next + 1) & 31; return e; }
+}  // namespace
+
+SideBranch::SideBranch(cudaStream_t main_s) : main_stream(main_s) {
+  SideState& st = side_state();
+  on = st.ok;
+  side_stream = st.stream;
+}
+int SideBranch::fork() {
+  if (!on) return SER_OK;
+  SideState& st = side_state();
+  cudaEvent_t e = next_event(st);
+  SER_CUDA_CHECK(cudaEventRecord(e, main_stream));
+  SER_CUDA_CHECK(cudaStreamWaitEvent(side_stream, e, 0));
+  used = true;
+  return SER_OK;
+}
+int SideBranch::join() {
+  if (!on || !used) return SER_OK;
+  SideState& st = side_state();
+  cudaEvent_t e = next_event(st);
+  SER_CUDA_CHECK(cudaEventRecord(e, side_stream));
+  SER_CUDA_CHECK(cudaStreamWaitEvent(main_stream, e, 0));
+  used = false;
+  return SER_OK;
+}
+
 }  // namespace ser
 
 extern "C" {

@@ -230,6 +230,23 @@ int gemm(const GemmArgs& a, cudaStream_t stream);
 int gemm_simt_f32(const GemmArgs& a, cudaStream_t stream);
 int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream);
 bool gemm_tc_rowsum_ok(const GemmArgs& a);
+// ---------------------------------------------------------------------------------
+// Side branch: weight-gradient kernels are leaves of the backward dependency graph (nothing but the optimizer / the
+// gradient all-reduce consumes them), yet in stream order they sit ON the chain of small dX kernels of the classifier
+// tail and the fusion MLP.  A module's backward forks them onto a library-owned second stream (event record on the
+// caller's stream -> wait on the side stream), keeps the dX chain on the caller's stream, and joins before it
+// returns, so the caller sees ordinary stream semantics; under CUDA-graph capture the fork / join events become
+// parallel branches of the step graph.  SER_SIDE_STREAM=0 keeps everything on the caller's stream.
+// ---------------------------------------------------------------------------------
+struct SideBranch {
+  cudaStream_t main_stream = nullptr, side_stream = nullptr;
+  bool on = false, used = false;
+  explicit SideBranch(cudaStream_t main_s);
+  int fork();                         // work enqueued on side() from now on sees everything enqueued on main so far
+  int join();                         // main waits for everything enqueued on the side stream (no-op if never forked)
+  cudaStream_t side() const { return on ? side_stream : main_stream; }
+};
+
 int device_sm_count();
 int gemm_grid_sms();               // device_sm_count() minus the SMs reserved for concurrent collectives
 void set_reserved_sms(int n);

@@ -603,6 +603,9 @@ int gemm_tc_bf16(const GemmArgs& a, cudaStream_t stream) {
               "gemm_tc: the gate operand must be bf16 with an 8-element aligned leading dimension");
   SER_REQUIRE(a.R == nullptr || a.ldr % 8 == 0, "gemm_tc: ldr must be a multiple of 8");
   int BN = (a.N % 256 == 0) ? 256 : 128;
+  static const int bn_env = getenv("SER_GEMM_BN") ? atoi(getenv("SER_GEMM_BN")) : 0;      // A/B switch: force 128-wide tiles
+  if (bn_env == 128) BN = 128;
+  // (measured with it: 768 <- 256 + residual, 64000 rows, cold operands: 56.7 us with 128-wide tiles vs 51.4 us with 256)
   // small problems: narrower tiles put twice as many SMs to work and halve each CTA's serial epilogue
   // (long contractions are split along K instead and keep the wider, shared-memory-friendlier tile)
   if (BN == 256 && ceil_div(a.K, BK) < 64 &&

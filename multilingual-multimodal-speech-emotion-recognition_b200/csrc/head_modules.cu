@@ -648,19 +648,26 @@ int fusion_bwd(const ser_fusion_desc& d, cudaStream_t s) {
     const Side& A_ = sides[0];
     const Side& T_ = sides[1];
     const int z = d.grads_zeroed;
+    // the three weight-gradient pairs run on the side branch; the dX chain (gate dgrad -> proj[3] dgrad -> proj[0] dgrad)
+    // stays on the caller's stream as three consecutive launches
+    SideBranch sb(s);
+    SER_TRY(sb.fork());
     SER_TRY(gemm_pair(wgrad_args(dt, B, G, P, A_.dg, G, A_.p, P, A_.dwg1, P, A_.dbg1, z),
-                      wgrad_args(dt, B, G, P, T_.dg, G, T_.p, P, T_.dwg1, P, T_.dbg1, z), s));
+                      wgrad_args(dt, B, G, P, T_.dg, G, T_.p, P, T_.dwg1, P, T_.dbg1, z), sb.side()));
     SER_TRY(gemm_pair(dgrad_args(dt, B, G, P, A_.dg, G, A_.wg1, P, A_.dp, P, f, nullptr, 0, f, GATE_NONE, A_.dp, P, f),
                       dgrad_args(dt, B, G, P, T_.dg, G, T_.wg1, P, T_.dp, P, f, nullptr, 0, f, GATE_NONE, T_.dp, P, f), s));
+    SER_TRY(sb.fork());
     SER_TRY(gemm_pair(wgrad_args(dt, B, P, P, A_.dp, P, A_.h, P, A_.dw2, P, A_.db2, z),
-                      wgrad_args(dt, B, P, P, T_.dp, P, T_.h, P, T_.dw2, P, T_.db2, z), s));
+                      wgrad_args(dt, B, P, P, T_.dp, P, T_.h, P, T_.dw2, P, T_.db2, z), sb.side()));
     // h is saved post-dropout: h > 0 exactly where the unit was kept and the ReLU open; the kept units carry 1/(1-p)
     SER_TRY(gemm_pair(dgrad_args(dt, B, P, P, A_.dp, P, A_.w2, P, A_.dh, P, f, A_.h, P, f, GATE_RELU, nullptr, 0, f, hscale),
                       dgrad_args(dt, B, P, P, T_.dp, P, T_.w2, P, T_.dh, P, f, T_.h, P, f, GATE_RELU, nullptr, 0, f, hscale), s));
+    SER_TRY(sb.fork());
     SER_TRY(gemm_pair(wgrad_args(dt, B, P, Din, A_.dh, P, A_.v, Din, A_.dw1, Din, A_.db1, z),
-                      wgrad_args(dt, B, P, Din, T_.dh, P, T_.v, Din, T_.dw1, Din, T_.db1, z), s));
+                      wgrad_args(dt, B, P, Din, T_.dh, P, T_.v, Din, T_.dw1, Din, T_.db1, z), sb.side()));
     SER_TRY(gemm_pair(dgrad_args(dt, B, P, Din, A_.dh, P, A_.w1, Din, A_.dv, Din, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f),
                       dgrad_args(dt, B, P, Din, T_.dh, P, T_.w1, Din, T_.dv, Din, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f), s));
+    SER_TRY(sb.join());
   }
   return SER_OK;
 }
@@ -787,15 +794,20 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
   // ---- heads (fp32): row-wise gradients + every head parameter gradient in two launches (heads.cu) ----
   const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);
   const float hscale = drop.on() ? drop.scale : 1.f;
+  // weight gradients are leaves of the backward graph: they run on the side branch (common.cuh SideBranch) beside the
+  // dX chain -- the heads' and the output projection's beside the 35-block stack kernel (which occupies 32 SMs), the
+  // stack's own batched weight gradients beside the input projection's backward
+  SideBranch sb(s);
   SER_TRY(heads_bwd(d.dlogits, d.dunc, d.unc, d.u1, d.f, d.w_c, d.w_u1, d.w_u2, df, du1, dsg, d.dw_c, d.db_c, d.dw_u1,
-                    d.db_u1, d.dw_u2, d.db_u2, B, F, C, U, with_site(drop, DS_CLF_UNC), s));
+                    d.db_u1, d.dw_u2, d.db_u2, B, F, C, U, with_site(drop, DS_CLF_UNC), s, &sb));
   if (drop.on()) SER_TRY(dropout_apply(df, df, nullptr, 1, B, F, with_site(drop, DS_CLF_OUT), s));
   // ---- output projection: relu(LN(q)) ----
   SER_ZERO_UNLESS(d.grads_zeroed, d.dln_out_g, sizeof(float) * F);
   SER_ZERO_UNLESS(d.grads_zeroed, d.dln_out_b, sizeof(float) * F);
   SER_TRY(layernorm_bwd(df, 1, d.q, 1, d.stats_q, d.ln_out_g, d.ln_out_b, nullptr, 1, dq, f, nullptr, 1, d.dln_out_g,
                         d.dln_out_b, B, F, 1, s));
-  SER_TRY(linear_wgrad(dt, B, F, P, dq, F, d.h_last, P, d.dw_out, P, s, d.db_out, d.grads_zeroed));
+  SER_TRY(sb.fork());
+  SER_TRY(linear_wgrad(dt, B, F, P, dq, F, d.h_last, P, d.dw_out, P, sb.side(), d.db_out, d.grads_zeroed));
   SER_TRY(linear_dgrad(dt, B, F, P, dq, F, d.w_out, P, dh32, P, 1, nullptr, 0, 1, GATE_NONE, nullptr, 0, 1, s));
   ClfStackArgs sa;
   bool fused = stack_args(d, sa) && stack_grad_args(d, sa);
@@ -840,6 +852,8 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
                 (d.db1[i] - d.db1[i - 1] == sb1) && (d.db2[i] - d.db2[i - 1] == sb2);
     uniform = uniform && sw1 > 0 && sw2 > 0 && sb1 > 0 && sb2 > 0 && (P % 8 == 0);
   }
+  SER_TRY(sb.fork());                                   // (dhn_all / dr_all are complete: the stack kernel has been enqueued)
+  cudaStream_t sw = sb.side();
   if (uniform) {
     GemmArgs g;
     g.dtype = dt; g.M = P; g.N = P; g.K = B; g.a_trans = 1; g.b_trans = 1; g.lda = P; g.ldb = P; g.ldc = P; g.c_f32 = 1;
@@ -847,15 +861,15 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
     g.out_zeroed = d.grads_zeroed;
     // bias gradients ride on the weight-gradient GEMMs (row sums of the MN-major dY operand)
     g.A = dhn_all; g.B = d.r; g.C = d.dw2[0]; g.strideC = sw2; g.rowsum = d.db2[0]; g.strideRS = sb2;
-    SER_TRY(gemm(g, s));
+    SER_TRY(gemm(g, sw));
     g.A = dr_all; g.B = d.n; g.C = d.dw1[0]; g.strideC = sw1; g.rowsum = d.db1[0]; g.strideRS = sb1;
-    SER_TRY(gemm(g, s));
+    SER_TRY(gemm(g, sw));
   } else {
     for (int i = 0; i < L; ++i) {
       const void* dhn_i = off(static_cast<const void*>(dhn_all), static_cast<long long>(i) * BP, dt);
       const void* dr_i = off(static_cast<const void*>(dr_all), static_cast<long long>(i) * BP, dt);
-      SER_TRY(linear_wgrad(dt, B, P, P, dhn_i, P, off(static_cast<const void*>(d.r), static_cast<long long>(i) * BP, dt), P, d.dw2[i], P, s, d.db2[i], d.grads_zeroed));
-      SER_TRY(linear_wgrad(dt, B, P, P, dr_i, P, off(static_cast<const void*>(d.n), static_cast<long long>(i) * BP, dt), P, d.dw1[i], P, s, d.db1[i], d.grads_zeroed));
+      SER_TRY(linear_wgrad(dt, B, P, P, dhn_i, P, off(static_cast<const void*>(d.r), static_cast<long long>(i) * BP, dt), P, d.dw2[i], P, sw, d.db2[i], d.grads_zeroed));
+      SER_TRY(linear_wgrad(dt, B, P, P, dr_i, P, off(static_cast<const void*>(d.n), static_cast<long long>(i) * BP, dt), P, d.dw1[i], P, sw, d.db1[i], d.grads_zeroed));
     }
   }
   // ---- input projection: h0 = relu(LN(p0)) ----
@@ -865,9 +879,11 @@ int clf_bwd(const ser_clf_desc& d, cudaStream_t s) {
   SER_TRY(layernorm_bwd(cur, 1, d.p0, 1, d.stats0, d.ln_in_g, d.ln_in_b, nullptr, 1, dp0, f, nullptr, 1, d.dln_in_g,
                         d.dln_in_b, B, P, 1, s));
   const int Pin = d.Pin > 0 ? d.Pin : P;
-  SER_TRY(linear_wgrad(dt, B, P, Pin, dp0, P, d.x, Pin, d.dw_in, Pin, s, d.db_in, d.grads_zeroed));
+  SER_TRY(sb.fork());
+  SER_TRY(linear_wgrad(dt, B, P, Pin, dp0, P, d.x, Pin, d.dw_in, Pin, sb.side(), d.db_in, d.grads_zeroed));
   if (d.dx != nullptr)
     SER_TRY(linear_dgrad(dt, B, P, Pin, dp0, P, d.w_in, Pin, d.dx, Pin, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
+  SER_TRY(sb.join());
   return SER_OK;
 }
 

@@ -168,13 +168,16 @@ int heads_fwd(const float* f, const float* w_c, const float* b_c, const float* w
 int heads_bwd(const float* dlogits, const float* dunc, const float* unc, const float* u1, const float* f,
               const float* w_c, const float* w_u1, const float* w_u2, float* df, float* du1, float* dsg, float* dw_c,
               float* db_c, float* dw_u1, float* db_u1, float* dw_u2, float* db_u2, int B, int F, int C, int U,
-              const DropSpec& drop, cudaStream_t s) {
+              const DropSpec& drop, cudaStream_t s, SideBranch* sb) {
   SER_REQUIRE(B > 0 && F <= 1024 && U <= 1024 && C > 0, "heads_bwd: unsupported shape");
   ProfScope prof("heads_bwd", 4.0 * B * F * (C + U), 4.0 * (2.0 * B * F + 2.0 * (C + U) * F), s);
   SER_CUDA_CHECK(launch_pdl(heads_bwd_rows_kernel, dim3(B), dim3(256), sizeof(float) * (C + U), s, dlogits, dunc, unc, u1, w_c, w_u1, w_u2, df, du1, dsg,
                                                               F, C, U, drop.on() ? drop.scale : 1.f));
   SER_LAUNCH_CHECK();
-  SER_CUDA_CHECK(launch_pdl(heads_bwd_w_kernel, dim3(C + U + 1), dim3(256), 0, s, dlogits, du1, dsg, f, u1, dw_c, db_c, dw_u1, db_u1, dw_u2, db_u2, B, F, C, U));
+  // the weight gradients are leaves: on the side branch they run beside the dX chain that continues on `s`
+  cudaStream_t sw = s;
+  if (sb != nullptr) { SER_TRY(sb->fork()); sw = sb->side(); }
+  SER_CUDA_CHECK(launch_pdl(heads_bwd_w_kernel, dim3(C + U + 1), dim3(256), 0, sw, dlogits, du1, dsg, f, u1, dw_c, db_c, dw_u1, db_u1, dw_u2, db_u2, B, F, C, U));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

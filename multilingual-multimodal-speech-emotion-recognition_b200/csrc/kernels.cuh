@@ -129,7 +129,7 @@ int heads_fwd(const float* f, const float* w_c, const float* b_c, const float* w
 int heads_bwd(const float* dlogits, const float* dunc, const float* unc, const float* u1, const float* f,
               const float* w_c, const float* w_u1, const float* w_u2, float* df, float* du1, float* dsg, float* dw_c,
               float* db_c, float* dw_u1, float* db_u1, float* dw_u2, float* db_u2, int B, int F, int C, int U,
-              const DropSpec& drop, cudaStream_t s);
+              const DropSpec& drop, cudaStream_t s, SideBranch* sb = nullptr);
 
 // ---- pooling.cu ----------------------------------------------------------------------------------
 // Attentive statistics pooling, everything after the 768->128 tanh GEMM (src/models/pooling.py:21-28).
