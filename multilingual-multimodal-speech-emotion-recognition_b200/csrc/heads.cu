@@ -10,29 +10,51 @@ namespace ser {
 
 namespace {
 
-// one CTA per sample; thread o < C + U owns one output (dot product of length F against the staged feature row)
+// one CTA per sample; warp per output (C + U dot products of length F against the staged feature row).
+// The weights do not depend on the preceding kernels of the step, so the CTA copies them into shared memory BEFORE
+// griddepcontrol.wait (programmatic dependent launch: this prologue runs while the predecessor still executes) with all
+// loads in flight at once -- the fp32 master weights are cold by this point of a step (one DRAM round trip instead of a
+// chain of eight per output row); only the feature row is read after the wait.
+template <bool STAGE_W>
 __global__ void __launch_bounds__(128)
 heads_fwd_kernel(const float* __restrict__ f, const float* __restrict__ w_c, const float* __restrict__ b_c,
                  const float* __restrict__ w_u1, const float* __restrict__ b_u1, const float* __restrict__ w_u2,
                  const float* __restrict__ b_u2, float* __restrict__ logits, float* __restrict__ u1,
                  float* __restrict__ unc, int F, int C, int U, DropSpec drop) {
-  pdl_sync();
   extern __shared__ __align__(16) float sm[];
   float* sf = sm;            // [F]
   float* su = sm + F;        // [U]
+  float* sw = su + ((U + 3) & ~3);     // [C + U][F] (STAGE_W)
+  const int nout = C + (unc != nullptr ? U : 0);
+  if (STAGE_W) {
+    const int nc4 = C * F / 4, nu4 = (nout - C) * F / 4;
+    for (int i = threadIdx.x; i < nc4; i += blockDim.x)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(sw + 4 * i))),
+                   "l"(w_c + 4 * i) : "memory");
+    for (int i = threadIdx.x; i < nu4; i += blockDim.x)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(sw + C * F + 4 * i))),
+                   "l"(w_u1 + 4 * i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  pdl_sync();
   const int row = blockIdx.x;
   for (int k = threadIdx.x * 4; k < F; k += blockDim.x * 4)
     *reinterpret_cast<float4*>(sf + k) = __ldg(reinterpret_cast<const float4*>(f + static_cast<size_t>(row) * F + k));
+  if (STAGE_W) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  const int nout = C + (unc != nullptr ? U : 0);
-  for (int o = threadIdx.x; o < nout; o += blockDim.x) {
-    const float* w = (o < C) ? w_c + static_cast<size_t>(o) * F : w_u1 + static_cast<size_t>(o - C) * F;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+#pragma unroll 4
+  for (int o = warp; o < nout; o += nwarps) {
+    const float* w = STAGE_W ? sw + static_cast<size_t>(o) * F
+                             : ((o < C) ? w_c + static_cast<size_t>(o) * F : w_u1 + static_cast<size_t>(o - C) * F);
     float acc = 0.f;
-    for (int k = 0; k < F; k += 4) {
+    for (int k = lane * 4; k < F; k += 128) {
       const float4 a = *reinterpret_cast<const float4*>(sf + k);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(w + k));
+      const float4 b = STAGE_W ? *reinterpret_cast<const float4*>(w + k) : __ldg(reinterpret_cast<const float4*>(w + k));
       acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
     }
+    acc = warp_sum(acc);
+    if (lane != 0) continue;
     if (o < C) {
       logits[static_cast<size_t>(row) * C + o] = acc + b_c[o];
     } else {
@@ -160,7 +182,20 @@ int heads_fwd(const float* f, const float* w_c, const float* b_c, const float* w
               const DropSpec& drop, cudaStream_t s) {
   SER_REQUIRE(B > 0 && F % 4 == 0 && F <= 4096 && C > 0 && U > 0 && U <= 1024, "heads_fwd: unsupported shape");
   ProfScope prof("heads_fwd", 2.0 * B * F * (C + U), 4.0 * (static_cast<double>(B) * F + (C + U) * F), s);
-  SER_CUDA_CHECK(launch_pdl(heads_fwd_kernel, dim3(B), dim3(128), sizeof(float) * (F + U), s, f, w_c, b_c, w_u1, b_u1, w_u2, b_u2, logits, u1, unc, F, C, U, drop));
+  // weights staged in shared memory when they fit beside the feature row (reference sizes: 68 x 256 fp32 = 68 KB)
+  const size_t base = sizeof(float) * (F + ((U + 3) & ~3));
+  const size_t staged = base + sizeof(float) * static_cast<size_t>(C + U) * F;
+  const bool ok16 = (reinterpret_cast<uintptr_t>(w_c) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_u1) & 15) == 0;
+  if (staged <= 96 * 1024 && ok16) {
+    static bool configured = false;
+    if (!configured) {
+      SER_CUDA_CHECK(cudaFuncSetAttribute(heads_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      configured = true;
+    }
+    SER_CUDA_CHECK(launch_pdl(heads_fwd_kernel<true>, dim3(B), dim3(128), staged, s, f, w_c, b_c, w_u1, b_u1, w_u2, b_u2, logits, u1, unc, F, C, U, drop));
+  } else {
+    SER_CUDA_CHECK(launch_pdl(heads_fwd_kernel<false>, dim3(B), dim3(128), base, s, f, w_c, b_c, w_u1, b_u1, w_u2, b_u2, logits, u1, unc, F, C, U, drop));
+  }
   SER_LAUNCH_CHECK();
   return SER_OK;
 }

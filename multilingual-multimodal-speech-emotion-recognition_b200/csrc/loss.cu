@@ -89,8 +89,43 @@ __device__ __forceinline__ int row_argmax(const float* __restrict__ logits, int 
   return idx;
 }
 
+// The lane's share of one embedding row (columns lane, lane + 32, ...), read ONCE and clamped (prototypes.py:18): the
+// class loop below then runs on registers.  kEmbRegs * 32 columns fit (D <= 512, the reference's proj_dim); wider
+// rows take the generic loop.
+constexpr int kEmbRegs = 16;
+__device__ __forceinline__ void load_emb_lane(const LossArgs& a, int row, int lane, float (&raw)[kEmbRegs], float (&e)[kEmbRegs]) {
+#pragma unroll
+  for (int k = 0; k < kEmbRegs; ++k) {
+    const int d = lane + 32 * k;
+    raw[k] = (d < a.D) ? ld_dyn(a.emb, static_cast<size_t>(row) * a.D + d, a.emb_f32) : 0.f;
+    e[k] = fminf(fmaxf(raw[k], -10.f), 10.f);
+  }
+}
+// squared distance of the row to prototype c, same summation order as the generic loop (lane-strided, then warp_sum)
+__device__ __forceinline__ float sqdist_lane(const LossArgs& a, const float* __restrict__ protos, const float (&e)[kEmbRegs],
+                                             int c, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kEmbRegs; ++k) {
+    const int d = lane + 32 * k;
+    if (d < a.D) {
+      const float df = e[k] - protos[static_cast<size_t>(c) * a.D + d];
+      s = fmaf(df, df, s);
+    }
+  }
+  return warp_sum(s);
+}
+
 __global__ void __launch_bounds__(256)
-loss_rows_kernel(LossArgs a) {
+loss_rows_kernel(LossArgs a, int stage_protos) {
+  // the prototypes are parameters (nothing in this step writes them): copied to shared memory BEFORE
+  // griddepcontrol.wait, while the preceding kernel still runs -- by now they are cold in L2
+  extern __shared__ float sproto[];
+  const float* protos = a.protos;
+  if (stage_protos && a.emb != nullptr) {
+    for (int i = threadIdx.x; i < a.C * a.D; i += blockDim.x) sproto[i] = __ldg(a.protos + i);
+    protos = sproto;
+  }
   pdl_sync();
   __shared__ float acc[LS_COUNT];
   if (threadIdx.x < LS_COUNT) acc[threadIdx.x] = 0.f;
@@ -118,16 +153,25 @@ loss_rows_kernel(LossArgs a) {
     if (a.emb != nullptr) {
       // squared distances to every prototype; lane c keeps class c
       float mysq = 0.f;
-      for (int c = 0; c < a.C; ++c) {
-        float s = 0.f;
-        for (int d = lane; d < a.D; d += 32) {
-          float e = ld_dyn(a.emb, static_cast<size_t>(row) * a.D + d, a.emb_f32);
-          e = fminf(fmaxf(e, -10.f), 10.f);
-          const float df = e - a.protos[static_cast<size_t>(c) * a.D + d];
-          s = fmaf(df, df, s);
+      if (a.D <= 32 * kEmbRegs) {
+        float raw[kEmbRegs], ev[kEmbRegs];
+        load_emb_lane(a, row, lane, raw, ev);
+        for (int c = 0; c < a.C; ++c) {
+          const float s = sqdist_lane(a, protos, ev, c, lane);
+          if (lane == c) mysq = s;
         }
-        s = warp_sum(s);
-        if (lane == c) mysq = s;
+      } else {
+        for (int c = 0; c < a.C; ++c) {
+          float s = 0.f;
+          for (int d = lane; d < a.D; d += 32) {
+            float e = ld_dyn(a.emb, static_cast<size_t>(row) * a.D + d, a.emb_f32);
+            e = fminf(fmaxf(e, -10.f), 10.f);
+            const float df = e - protos[static_cast<size_t>(c) * a.D + d];
+            s = fmaf(df, df, s);
+          }
+          s = warp_sum(s);
+          if (lane == c) mysq = s;
+        }
       }
       pos = sqrtf(__shfl_sync(0xffffffffu, mysq, y));
       float nd = (lane < a.C) ? ((lane == y) ? 10.f : fminf(sqrtf(mysq + 1e-6f), 10.f)) : INFINITY;
@@ -150,15 +194,22 @@ loss_rows_kernel(LossArgs a) {
 
 __global__ void __launch_bounds__(256)
 loss_bwd_kernel(LossArgs a, const float* __restrict__ gscale, int stage_dprotos) {
-  pdl_sync();
   // prototype gradients of the CTA's 8 samples are summed in shared memory first ([C, D] floats, when that fits): one
-  // global atomic per (class, column) and CTA instead of one per sample -- B-way contention on C*D addresses otherwise
+  // global atomic per (class, column) and CTA instead of one per sample -- B-way contention on C*D addresses otherwise.
+  // The second [C, D] block holds the prototypes themselves, copied before griddepcontrol.wait (see loss_rows_kernel).
   extern __shared__ float sdp[];
   const bool staged = stage_dprotos != 0 && a.dprotos != nullptr && a.emb != nullptr && a.demb != nullptr;
+  const float* protos = a.protos;
+  if (stage_dprotos != 0 && a.emb != nullptr) {
+    float* sproto = sdp + a.C * a.D;
+    for (int i = threadIdx.x; i < a.C * a.D; i += blockDim.x) sproto[i] = __ldg(a.protos + i);
+    protos = sproto;
+  }
+  pdl_sync();
   if (staged) {
     for (int i = threadIdx.x; i < a.C * a.D; i += blockDim.x) sdp[i] = 0.f;
-    __syncthreads();
   }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row < a.B) {
@@ -202,18 +253,28 @@ loss_bwd_kernel(LossArgs a, const float* __restrict__ gscale, int stage_dprotos)
     }
     if (a.emb != nullptr && a.demb != nullptr) {
       const bool on = ok_proto && a.w_proto != 0.f;
-      // recompute distances
+      // recompute distances (the lane's share of the row stays in registers for the gradient loop below)
+      const bool in_regs = a.D <= 32 * kEmbRegs;
+      float rawv[kEmbRegs], ev[kEmbRegs];
       float mysq = 0.f;
-      for (int c = 0; c < a.C; ++c) {
-        float s = 0.f;
-        for (int d = lane; d < a.D; d += 32) {
-          float e = ld_dyn(a.emb, static_cast<size_t>(row) * a.D + d, a.emb_f32);
-          e = fminf(fmaxf(e, -10.f), 10.f);
-          const float df = e - a.protos[static_cast<size_t>(c) * a.D + d];
-          s = fmaf(df, df, s);
+      if (in_regs) {
+        load_emb_lane(a, row, lane, rawv, ev);
+        for (int c = 0; c < a.C; ++c) {
+          const float s = sqdist_lane(a, protos, ev, c, lane);
+          if (lane == c) mysq = s;
         }
-        s = warp_sum(s);
-        if (lane == c) mysq = s;
+      } else {
+        for (int c = 0; c < a.C; ++c) {
+          float s = 0.f;
+          for (int d = lane; d < a.D; d += 32) {
+            float e = ld_dyn(a.emb, static_cast<size_t>(row) * a.D + d, a.emb_f32);
+            e = fminf(fmaxf(e, -10.f), 10.f);
+            const float df = e - protos[static_cast<size_t>(c) * a.D + d];
+            s = fmaf(df, df, s);
+          }
+          s = warp_sum(s);
+          if (lane == c) mysq = s;
+        }
       }
       const float pos = sqrtf(__shfl_sync(0xffffffffu, mysq, y));
       const float dist = sqrtf(mysq + 1e-6f);
@@ -228,14 +289,13 @@ loss_bwd_kernel(LossArgs a, const float* __restrict__ gscale, int stage_dprotos)
         else if (dist <= 10.f) coef = -sm / dist;
       }
       const float k = on ? a.w_proto * invB * gs : 0.f;
-      for (int d = lane; d < a.D; d += 32) {
-        const float raw = ld_dyn(a.emb, static_cast<size_t>(row) * a.D + d, a.emb_f32);
+      auto grad_col = [&](int d, float raw) {
         const float e = fminf(fmaxf(raw, -10.f), 10.f);
         const bool inside = (raw >= -10.f && raw <= 10.f);
         float ge = 0.f;
         for (int c = 0; c < a.C; ++c) {
           const float cc = __shfl_sync(0xffffffffu, coef, c);
-          const float df = e - a.protos[static_cast<size_t>(c) * a.D + d];
+          const float df = e - protos[static_cast<size_t>(c) * a.D + d];
           const float t = cc * df * k;
           ge += t;
           if (a.dprotos != nullptr && t != 0.f) {
@@ -244,6 +304,19 @@ loss_bwd_kernel(LossArgs a, const float* __restrict__ gscale, int stage_dprotos)
           }
         }
         st_dyn(a.demb, static_cast<size_t>(row) * a.D + d, a.demb_f32, inside ? ge : 0.f);
+      };
+      if (in_regs) {
+        // (the shuffles inside grad_col need the whole warp: D is a multiple of 32 here or the tail lanes idle together)
+#pragma unroll
+        for (int kk = 0; kk < kEmbRegs; ++kk) {
+          if (32 * kk < a.D) {                               // warp-uniform
+            const int d = lane + 32 * kk;
+            if (d < a.D) grad_col(d, rawv[kk]);
+            else for (int c = 0; c < a.C; ++c) (void)__shfl_sync(0xffffffffu, coef, c);
+          }
+        }
+      } else {
+        for (int d = lane; d < a.D; d += 32) grad_col(d, ld_dyn(a.emb, static_cast<size_t>(row) * a.D + d, a.emb_f32));
       }
     }
   }  // row < B
@@ -264,7 +337,9 @@ int loss_fwd(const LossArgs& a, cudaStream_t s) {
   ProfScope prof("loss_fwd", 0.0, 4.0 * a.B * (a.C + (a.emb ? a.D : 0)), s);
   SER_CUDA_CHECK(launch_pdl(loss_prep_kernel, dim3(1), dim3(256), 0, s, a.labels, a.counts, a.B, a.C, a.beta, a.focal_use_weights, a.class_w, a.sums));
   SER_LAUNCH_CHECK();
-  SER_CUDA_CHECK(launch_pdl(loss_rows_kernel, dim3(ceil_div(a.B, 8)), dim3(256), 0, s, a));
+  const size_t pbytes = sizeof(float) * static_cast<size_t>(a.C) * (a.emb ? a.D : 0);
+  const int stage_p = (pbytes > 0 && pbytes <= 20 * 1024) ? 1 : 0;
+  SER_CUDA_CHECK(launch_pdl(loss_rows_kernel, dim3(ceil_div(a.B, 8)), dim3(256), stage_p ? pbytes : 0, s, a, stage_p));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
@@ -273,8 +348,8 @@ int loss_bwd_scaled(const LossArgs& a, const float* gscale, cudaStream_t s) {
   SER_REQUIRE(a.C >= 2 && a.C <= kMaxC, "loss: 2 <= num_classes <= 32");
   ProfScope prof("loss_bwd", 0.0, 4.0 * a.B * (2.0 * a.C + (a.emb ? 2.0 * a.D : 0)), s);
   const size_t stage_bytes = sizeof(float) * static_cast<size_t>(a.C) * (a.emb ? a.D : 0);
-  const int stage = (a.dprotos != nullptr && stage_bytes > 0 && stage_bytes <= 40 * 1024) ? 1 : 0;
-  SER_CUDA_CHECK(launch_pdl(loss_bwd_kernel, dim3(ceil_div(a.B, 8)), dim3(256), stage ? stage_bytes : 0, s, a, gscale, stage));
+  const int stage = (a.dprotos != nullptr && stage_bytes > 0 && stage_bytes <= 20 * 1024) ? 1 : 0;
+  SER_CUDA_CHECK(launch_pdl(loss_bwd_kernel, dim3(ceil_div(a.B, 8)), dim3(256), stage ? 2 * stage_bytes : 0, s, a, gscale, stage));
   SER_LAUNCH_CHECK();
   return SER_OK;
 }
