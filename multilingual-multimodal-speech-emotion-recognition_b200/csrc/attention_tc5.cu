@@ -79,6 +79,11 @@ __device__ __forceinline__ void group_sync(int h) {
   else asm volatile("bar.sync 2, 128;" ::: "memory");
 }
 
+__device__ __forceinline__ void group_sync_n(int h, int n) {
+  if (h == 0) asm volatile("bar.sync 1, %0;" ::"r"(n) : "memory");
+  else asm volatile("bar.sync 2, %0;" ::"r"(n) : "memory");
+}
+
 // 256 threads, no dedicated control warp: a ninth warp would sit on one of the four sub-partitions and its register
 // allocation alone would keep a second CTA off the SM.  The first lane of each head's first warp issues that head's
 // MMAs (and, for head 0, the TMA loads) in program order; the four warps of a head meet at a named barrier once their
@@ -562,8 +567,11 @@ attn5_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
-template <bool DROP>
-__global__ void __launch_bounds__(A5_THREADS, 2)
+// SPLIT = 2 (experiment, off by default -- see the launcher): two threads per key row, each owning 16 of a streamed
+// tile's 32 query columns (the warps w and w + 4 of a head share a tensor-memory lane quarter, like the two epilogue
+// warps of gemm_tc.cu): 32 resident warps per SM instead of 16.
+template <bool DROP, int SPLIT>
+__global__ void __launch_bounds__(A5_THREADS * SPLIT, 2)
 attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmG,
                      const float* __restrict__ kmask, const float* __restrict__ lse, const float* __restrict__ delta,
@@ -593,7 +601,9 @@ attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     dst[32 + lane] = (q < Tq) ? delta[idx] : 0.f;
   };
   pdl_sync();
-  if ((warp & 3) == 1) fetch_ld(0, warp >> 2);
+  constexpr int WPH = 4 * SPLIT;                       // warps per head
+  constexpr int CW = B5_KT / SPLIT;                    // query columns of a tile per thread
+  if ((warp % WPH) == 1) fetch_ld(0, warp / WPH);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -617,7 +627,8 @@ attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
   const uint32_t tmem_base = bars->tmem_slot;
   // tensor-memory columns: S^T_h at [32 h, +32), dP^T_h at [64 + 32 h, +32), dV_h at [128 + 32 h, +32), dK_h at [192 + 32 h, +32)
 
-  const int h = warp >> 2, quarter = warp & 3;
+  const int h = warp / WPH, quarter = warp & 3, half = (warp % WPH) >> 2;   // half: which CW columns of a tile
+  const int c0 = half * CW;
   const int col0 = hp * 2 * A5_DH;
   constexpr uint32_t idesc_s = make_idesc<B5_KT, 0, 0, A5_ROWS>();
   constexpr uint32_t idesc_acc = make_idesc<A5_DH, 0, 1, A5_ROWS>();
@@ -641,7 +652,7 @@ attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
       tc_mma_bf16(tmem_base + 64 + h * 32, desc_kmajor(aV, h * 64 + k * 32), desc_kmajor(aG, h * 64 + k * 32), idesc_s, k > 0 ? 1u : 0u);
     tc_commit(&bars->s_full[h]);
   };
-  if (quarter == 3 && lane == 0) {
+  if (quarter == 3 && half == 0 && lane == 0) {
     if (h == 0) {
       mbar_expect_tx(&bars->own_full, 2 * A5_TILE_OWN);
       tma_load_3d(&tmK, &bars->own_full, sK, col0, b * Tk + k0, 0);
@@ -696,7 +707,7 @@ attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     }
     mbar_wait(&bars->s_full[h], t & 1);
     tc_fence_after();
-    if (h == 0 && quarter == (t & 3) && lane == 0 && t >= 1 && t - 1 + B5_NST_KV < ntiles) {
+    if (h == 0 && half == 0 && quarter == (t & 3) && lane == 0 && t >= 1 && t - 1 + B5_NST_KV < ntiles) {
       mbar_wait(&bars->str_empty[(t - 1) % B5_NST_KV], ((t - 1) / B5_NST_KV) & 1);
       load_tile(t - 1 + B5_NST_KV);
     }
@@ -704,13 +715,18 @@ attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     if (active) {
       const int qt = t * B5_KT;
       const bool partial = qt + B5_KT > Tq;                 // the last tile: columns past the sample carry other rows' data
-      uint32_t sv[B5_KT], dv[B5_KT];
-      tmem_ld32_issue(lane_base + h * 32, sv);
-      tmem_ld32_issue(lane_base + 64 + h * 32, dv);
+      uint32_t sv[CW], dv[CW];
+      if (SPLIT == 1) {
+        tmem_ld32_issue(lane_base + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[0]));
+        tmem_ld32_issue(lane_base + 64 + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&dv[0]));
+      } else {
+        tmem_ld16_issue(lane_base + h * 32 + c0, *reinterpret_cast<uint32_t(*)[16]>(&sv[0]));
+        tmem_ld16_issue(lane_base + 64 + h * 32 + c0, *reinterpret_cast<uint32_t(*)[16]>(&dv[0]));
+      }
       tmem_ld_wait();
-      const float4* ld4 = reinterpret_cast<const float4*>(sLD + ((t & 1) * 2 + h) * 64);
+      const float4* ld4 = reinterpret_cast<const float4*>(sLD + ((t & 1) * 2 + h) * 64) + c0 / 4;
 #pragma unroll
-      for (int j8 = 0; j8 < B5_KT / 8; ++j8) {
+      for (int j8 = 0; j8 < CW / 8; ++j8) {
         const float4 l0 = ld4[2 * j8], l1 = ld4[2 * j8 + 1], e0 = ld4[8 + 2 * j8], e1 = ld4[8 + 2 * j8 + 1];
         const float lq[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
         const float dq_[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
@@ -723,15 +739,15 @@ attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
             const int j = 8 * j8 + 2 * u + e;
             float p = ex2(fmaf(__uint_as_float(sv[j]), c, kb) + lq[2 * u + e]);
             float g = __uint_as_float(dv[j]);
-            if (partial && !(qt + j < Tq)) { p = 0.f; g = 0.f; }      // never let a foreign row's NaN through 0 * NaN
+            if (partial && !(qt + c0 + j < Tq)) { p = 0.f; g = 0.f; }      // never let a foreign row's NaN through 0 * NaN
             float w = p;
             if (DROP) {
               if (keep_bits != nullptr) {
-                const bool kp = ((kcol >> j) & 1u) != 0u;
+                const bool kp = ((kcol >> (c0 + j)) & 1u) != 0u;
                 w = kp ? w * drop.scale : 0.f;
                 g = kp ? g * drop.scale : 0.f;
               } else {
-                const float mk = drop_one(dkey, (drow0 + static_cast<unsigned>(qt + j)) * half_tk + dcol, dhalf, drop.thr, drop.scale);
+                const float mk = drop_one(dkey, (drow0 + static_cast<unsigned>(qt + c0 + j)) * half_tk + dcol, dhalf, drop.thr, drop.scale);
                 w *= mk; g *= mk;
               }
             }
@@ -741,25 +757,25 @@ attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
           wp[u] = pack_bf16x2(pv[0], pv[1]);
           wd[u] = pack_bf16x2(dsv[0], dsv[1]);
         }
-        sts128(d_row + ((static_cast<uint32_t>(j8) ^ swz) << 4), wp[0], wp[1], wp[2], wp[3]);
-        sts128(d_row + ((static_cast<uint32_t>(4 + j8) ^ swz) << 4), wd[0], wd[1], wd[2], wd[3]);
+        sts128(d_row + ((static_cast<uint32_t>(c0 / 8 + j8) ^ swz) << 4), wp[0], wp[1], wp[2], wp[3]);
+        sts128(d_row + ((static_cast<uint32_t>(4 + c0 / 8 + j8) ^ swz) << 4), wd[0], wd[1], wd[2], wd[3]);
       }
       // The last tile's rows past the sample are another sample's dO rows (TMA boxes do not know about samples): their
       // P^T / dS^T columns are zero, but 0 x NaN inside the tensor core is NaN, and a fully padded neighbour hands back
       // NaN gradients.  This head's 64 bytes of those rows are cleared before they become the B operand of dV (the
       // products that read them as dP^T have retired: s_full).
-      if (partial && quarter == 0 && qt + lane >= Tq) {
+      if (partial && quarter == 0 && half == 0 && qt + lane >= Tq) {
         const uint32_t g_row = smem_u32(sG + (t % B5_NST_KV) * B5_TILE_STR) + static_cast<uint32_t>(lane) * 128u;
 #pragma unroll
         for (int cix = 0; cix < 4; ++cix)
           sts128(g_row + ((static_cast<uint32_t>(4 * h + cix) ^ static_cast<uint32_t>(lane & 7)) << 4), 0u, 0u, 0u, 0u);
       }
     }
-    if (quarter == 1 && t + 1 < ntiles) fetch_ld(t + 1, h);
+    if (quarter == 1 && half == 0 && t + 1 < ntiles) fetch_ld(t + 1, h);
     fence_async_smem();
     tc_fence_before();
-    group_sync(h);
-    if (quarter == (t & 3) && lane == 0) {
+    group_sync_n(h, 128 * SPLIT);
+    if (half == 0 && quarter == (t & 3) && lane == 0) {
       tc_fence_after();
       const int st = t % B5_NST_KV;
       const uint32_t aG = smem_u32(sG + st * B5_TILE_STR) + static_cast<uint32_t>(h * 64);
@@ -780,16 +796,22 @@ attn5_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
   mbar_wait(&bars->acc_full[h], 0);
   tc_fence_after();
   if (active) {
-    uint32_t av[A5_DH], ak[A5_DH];
-    tmem_ld32_issue(lane_base + 128 + h * 32, av);
-    tmem_ld32_issue(lane_base + 192 + h * 32, ak);
+    constexpr int EW = A5_DH / SPLIT;                  // accumulator columns per thread
+    uint32_t av[EW], ak[EW];
+    if (SPLIT == 1) {
+      tmem_ld32_issue(lane_base + 128 + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&av[0]));
+      tmem_ld32_issue(lane_base + 192 + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&ak[0]));
+    } else {
+      tmem_ld16_issue(lane_base + 128 + h * 32 + half * EW, *reinterpret_cast<uint32_t(*)[16]>(&av[0]));
+      tmem_ld16_issue(lane_base + 192 + h * 32 + half * EW, *reinterpret_cast<uint32_t(*)[16]>(&ak[0]));
+    }
     tmem_ld_wait();
     if (kj < Tk) {
       const size_t r = static_cast<size_t>(b) * Tk + kj;
-      bf16* pk = dK + r * lddk + head * A5_DH;
-      bf16* pv = dV + r * lddv + head * A5_DH;
+      bf16* pk = dK + r * lddk + head * A5_DH + half * EW;
+      bf16* pv = dV + r * lddv + head * A5_DH + half * EW;
 #pragma unroll
-      for (int j = 0; j < A5_DH / 8; ++j) {
+      for (int j = 0; j < EW / 8; ++j) {
         uint4 v;
         v.x = pack_bf16x2(__uint_as_float(ak[8 * j]) * scale, __uint_as_float(ak[8 * j + 1]) * scale);
         v.y = pack_bf16x2(__uint_as_float(ak[8 * j + 2]) * scale, __uint_as_float(ak[8 * j + 3]) * scale);
@@ -892,7 +914,13 @@ int attention_bwd_tc5(const AttnArgs& a, cudaStream_t s) {
     SER_TRY(make_tmap(&tmQ, a.Q, 0, Mq, HD, a.ldq, B5_KT, 64, 1, 0));
     SER_TRY(make_tmap(&tmG, a.dO, 0, Mq, HD, a.lddo, B5_KT, 64, 1, 0));
     const int smem = 1024 + 4 * A5_TILE_OWN + 2 * B5_NST_KV * B5_TILE_STR + 256 + 1024;
-    auto* kern = drop ? attn5_bwd_dkv_kernel<true> : attn5_bwd_dkv_kernel<false>;
+    // A/B switch.  Measured (fwd + bwd, dropout 0.1, stored keep bits): (1500, 256) 1196 us with one thread per key row,
+    // 1298 us with two; (256, 1500) 1141 vs 1272 us -- the second set of warps pays a second bit transpose, a 256-thread
+    // named barrier per tile and 72 bytes of spills at the 64-register cap, and the MMA / barrier chain per tile, not the
+    // element-wise latency, is what the kernel waits on.  One thread per row stays the default.
+    static const int split = (getenv("SER_ATTN_DKV_SPLIT") && atoi(getenv("SER_ATTN_DKV_SPLIT")) == 2) ? 2 : 1;
+    auto* kern = split == 2 ? (drop ? attn5_bwd_dkv_kernel<true, 2> : attn5_bwd_dkv_kernel<false, 2>)
+                            : (drop ? attn5_bwd_dkv_kernel<true, 1> : attn5_bwd_dkv_kernel<false, 1>);
     static bool configured[2] = {false, false};
     if (!configured[drop ? 1 : 0]) {
       SER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -900,7 +928,7 @@ int attention_bwd_tc5(const AttnArgs& a, cudaStream_t s) {
       configured[drop ? 1 : 0] = true;
     }
     dim3 grid(ceil_div(a.Tk, A5_ROWS), a.H / 2, a.B);
-    SER_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(A5_THREADS), smem, s, tmK, tmV, tmQ, tmG, a.kmask, a.lse, a.delta, reinterpret_cast<bf16*>(a.dK), a.lddk,
+    SER_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(A5_THREADS * split), smem, s, tmK, tmV, tmQ, tmG, a.kmask, a.lse, a.delta, reinterpret_cast<bf16*>(a.dK), a.lddk,
                                         reinterpret_cast<bf16*>(a.dV), a.lddv, a.H, a.Tq, a.Tk, a.scale, a.drop,
                                         static_cast<const unsigned*>(a.keep_bits)));
     SER_LAUNCH_CHECK();
