@@ -62,7 +62,7 @@ def test_blackwell_instructions_present(lib):
     for k in stack:
         assert "UTCHMMA" in body[k] and "LDTM" in body[k] and "UTMASTG" in body[k] and "UBLKCP" in body[k], k
     attn5 = [k for k in body if "attn5_fwd_kernel" in k or "attn5_bwd_dq_kernel" in k or "attn5_bwd_dkv_kernel" in k]
-    assert len(attn5) == 6                   # three kernels x dropout off / on
+    assert len(attn5) == 8                   # forward, dQ, dK/dV (one / two threads per key row) x dropout off / on
     for k in attn5:
         assert "UTCHMMA" in body[k] and "UTMALDG" in body[k] and "LDTM" in body[k], k
         assert "HMMA." not in body[k].replace("UTCHMMA", ""), k
