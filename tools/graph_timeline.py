@@ -33,13 +33,19 @@ def main():
     ap.add_argument("--dropout", type=float, default=-1.0)
     args = ap.parse_args()
     B, Ta, Tt, C = WL[args.workload]
-    dev = torch.device("cuda:0")
+    import os
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:                                   # under torchrun: the data-parallel step, NCCL kernels included
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     rates = {"cross": 0.1, "fusion": 0.1, "classifier": 0.15} if args.dropout < 0 else args.dropout
     head = mmser_b200.FusionHead(C, dropout=rates).to(dev)
     head.load_group_state(synth.head_weights(C))
     head.train()
     dp = DataParallelHead(head)
-    a, t, am, tm, labels = synth.make_inputs(B, Ta, Tt, C, seed=1234)
+    a, t, am, tm, labels = synth.make_inputs(B, Ta, Tt, C, seed=1234 + rank)
     ins = [x.to(dev) for x in (a.bfloat16(), t.bfloat16(), am, tm, labels)]
     g = GraphedTrainStep(dp, *ins, static_inputs=True)
     for _ in range(5):
@@ -50,6 +56,11 @@ def main():
         for _ in range(args.replays):
             g.replay()
         torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+        if rank != 0:
+            torch.distributed.destroy_process_group()
+            return
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
     evs = sorted(evs, key=lambda e: e.time_range.start)
     evs = [e for e in evs if "memcpy" not in e.name.lower() and "memset" not in e.name.lower()]
