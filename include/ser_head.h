@@ -196,6 +196,11 @@ typedef struct ser_xattn_desc {
   float* dln_a_g; float* dln_a_b; float* dln_t_g; float* dln_t_b;
   void* ws; size_t ws_bytes;               /* backward scratch, ser_xattn_bwd_ws_bytes()          */
   int grads_zeroed;
+  /* CrossModalAttention(audio_dim != text_dim) (cross_attention.py:7-30): width of the TEXT sequence and of every
+   * text-side tensor (t, wqkv_t [3S,Dt], wout_t [Dt,S], ln_t_*, z_t, enh_t, dt, ...); 0 = D.  D is then the audio
+   * width.  Unequal widths take the unfolded path (the audio / text GEMM twins are no longer one batched launch);
+   * size the backward scratch with ser_xattn_bwd_ws_bytes(max(D, Dt)).                                        */
+  int Dt;
 } ser_xattn_desc;
 size_t ser_xattn_bwd_ws_bytes(int dtype, int B, int Ta, int Tt, int D, int S, int H);
 /* 1 when ser_xattn_fwd / _bwd take the folded path for this (dtype, D, S) PROVIDED fold_w / fold_b are given; the
@@ -299,6 +304,7 @@ typedef struct ser_fusion_desc {
   float* dwg1a; float* dbg1a; float* dwg2a; float* dbg2a; float* dwg1t; float* dbg1t; float* dwg2t; float* dbg2t;
   void* ws; size_t ws_bytes;               /* ser_fusion_bwd_ws_bytes()                           */
   int grads_zeroed;
+  int Din_t;                               /* FusionLayer(audio_dim != text_dim) (fusion.py:6-16): width of tv / w1t / dtv; 0 = Din */
 } ser_fusion_desc;
 size_t ser_fusion_bwd_ws_bytes(int dtype, int B, int Din, int P, int G);
 int ser_fusion_fwd(const ser_fusion_desc* d, void* stream);

@@ -209,7 +209,7 @@ int small_gemm2(int M, int N, int K, const void* A0, const void* A1, long long l
   return small_gemm(M, N, K, A1, lda, a_trans, B1, ldb, b_trans, C1, ldc, c_f32, s);
 }
 bool xattn_folded(const ser_xattn_desc& d) {
-  return xattn_fold_enabled(d.dtype, d.D, d.S) && d.fold_w != nullptr && d.fold_b != nullptr;
+  return xattn_fold_enabled(d.dtype, d.D, d.S) && (d.Dt == 0 || d.Dt == d.D) && d.fold_w != nullptr && d.fold_b != nullptr;
 }
 }  // namespace
 
@@ -387,13 +387,14 @@ int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s) {
   if (xattn_folded(d)) return xattn_fwd_folded(d, s);
   const int dt = d.dtype, f = is_f32(dt);
   const int S = d.S, D = d.D, S3 = 3 * d.S;
+  const int Dt = d.Dt > 0 ? d.Dt : d.D;              // CrossModalAttention(audio_dim != text_dim): text-side width
   const int Ma = d.B * d.Ta, Mt = d.B * d.Tt;
   SER_REQUIRE(S % d.H == 0, "xattn: shared_dim must be divisible by num_heads");   // cross_attention.py:12
   SER_REQUIRE(Ma > 0 && Mt > 0, "xattn: empty input");
   SER_REQUIRE(d.qkv_a && d.qkv_t && d.o_a && d.o_t, "xattn: the unfolded path needs full-size qkv_* / o_* buffers");
   // outer projections, one packed GEMM per modality (cross_attention.py:38-40,46-48)
   SER_TRY(linear_fwd(dt, Ma, S3, D, d.a, D, d.wqkv_a, D, d.bqkv_a, d.qkv_a, S3, f, ACT_NONE, nullptr, 0, f, s));
-  if (!d.reuse_text) SER_TRY(linear_fwd(dt, Mt, S3, D, d.t, D, d.wqkv_t, D, d.bqkv_t, d.qkv_t, S3, f, ACT_NONE, nullptr, 0, f, s));
+  if (!d.reuse_text) SER_TRY(linear_fwd(dt, Mt, S3, Dt, d.t, Dt, d.wqkv_t, Dt, d.bqkv_t, d.qkv_t, S3, f, ACT_NONE, nullptr, 0, f, s));
   // MHA in-projections (torch/nn/functional.py:5798 chunking): attn_a takes (qa, kt, vt), attn_t takes (qt, ka, va)
   struct InProj { const void* src; int M; int scol; const void* w; const float* b; int wrow; void* dst; int dcol; };
   const InProj ip[6] = {
@@ -436,8 +437,8 @@ int xattn_fwd(const ser_xattn_desc& d, cudaStream_t s) {
   SER_TRY(layernorm_fwd(d.z_a, f, d.enh_a, f, nullptr, f, d.ln_a_g, d.ln_a_b, d.stats_a, Ma, D, 0, s,
                         drop.on() ? d.a : nullptr, drop.on() ? d.z_a : nullptr, &drop_ra));
   SER_TRY(linear_fwd(dt, Mt, S, S, d.ctx_t, S, d.wo_t, S, d.bo_t, d.o_t, S, f, ACT_NONE, nullptr, 0, f, s));
-  SER_TRY(linear_fwd(dt, Mt, D, S, d.o_t, S, d.wout_t, S, d.bout_t, d.z_t, D, f, ACT_NONE, drop.on() ? nullptr : d.t, D, f, s));
-  SER_TRY(layernorm_fwd(d.z_t, f, d.enh_t, f, nullptr, f, d.ln_t_g, d.ln_t_b, d.stats_t, Mt, D, 0, s,
+  SER_TRY(linear_fwd(dt, Mt, Dt, S, d.o_t, S, d.wout_t, S, d.bout_t, d.z_t, Dt, f, ACT_NONE, drop.on() ? nullptr : d.t, Dt, f, s));
+  SER_TRY(layernorm_fwd(d.z_t, f, d.enh_t, f, nullptr, f, d.ln_t_g, d.ln_t_b, d.stats_t, Mt, Dt, 0, s,
                         drop.on() ? d.t : nullptr, drop.on() ? d.z_t : nullptr, &drop_rt));
   return SER_OK;
 }
@@ -460,11 +461,12 @@ int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
   SER_REQUIRE(d.qkv_a && d.qkv_t && d.o_a && d.o_t, "xattn: the unfolded path needs full-size qkv_* / o_* buffers");
   const int dt = d.dtype, f = is_f32(dt);
   const int S = d.S, D = d.D, S3 = 3 * d.S;
+  const int Dt = d.Dt > 0 ? d.Dt : d.D;              // text-side width (ser_head.h: Dt)
   const int Ma = d.B * d.Ta, Mt = d.B * d.Tt;
   const size_t e = esize(dt);
   Arena ws(d.ws, d.ws_bytes);
   void* dz_a = ws.take(static_cast<size_t>(Ma) * D * e);
-  void* dz_t = ws.take(static_cast<size_t>(Mt) * D * e);
+  void* dz_t = ws.take(static_cast<size_t>(Mt) * Dt * e);
   void* do_a = ws.take(static_cast<size_t>(Ma) * S * e);
   void* do_t = ws.take(static_cast<size_t>(Mt) * S * e);
   void* dctx_a = ws.take(static_cast<size_t>(Ma) * S * e);
@@ -477,30 +479,30 @@ int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
   float* delta_t = reinterpret_cast<float*>(ws.take(static_cast<size_t>(d.B) * d.H * d.Tt * sizeof(float)));
   const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);
   void* dzm_a = drop.on() ? ws.take(static_cast<size_t>(Ma) * D * e) : dz_a;
-  void* dzm_t = drop.on() ? ws.take(static_cast<size_t>(Mt) * D * e) : dz_t;
+  void* dzm_t = drop.on() ? ws.take(static_cast<size_t>(Mt) * Dt * e) : dz_t;
   if (!ws.ok) { set_last_error(__FILE__, __LINE__, "xattn_bwd: workspace too small"); return SER_ERR_WORKSPACE; }
 
   // LayerNorm backward (parameter gradients accumulate with atomics -> zero first)
   SER_ZERO_UNLESS(d.grads_zeroed, d.dln_a_g, sizeof(float) * D);
   SER_ZERO_UNLESS(d.grads_zeroed, d.dln_a_b, sizeof(float) * D);
-  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_t_g, sizeof(float) * D);
-  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_t_b, sizeof(float) * D);
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_t_g, sizeof(float) * Dt);
+  SER_ZERO_UNLESS(d.grads_zeroed, d.dln_t_b, sizeof(float) * Dt);
   const DropSpec drop_ra = with_site(drop, DS_XA_RES_A), drop_rt = with_site(drop, DS_XA_RES_T);
   SER_TRY(layernorm_bwd(d.d_enh_a, f, d.z_a, f, d.stats_a, d.ln_a_g, d.ln_a_b, nullptr, f, dz_a, f, nullptr, f,
                         d.dln_a_g, d.dln_a_b, Ma, D, 0, s, drop.on() ? dzm_a : nullptr, &drop_ra));
   SER_TRY(layernorm_bwd(d.d_enh_t, f, d.z_t, f, d.stats_t, d.ln_t_g, d.ln_t_b, nullptr, f, dz_t, f, nullptr, f,
-                        d.dln_t_g, d.dln_t_b, Mt, D, 0, s, drop.on() ? dzm_t : nullptr, &drop_rt));
+                        d.dln_t_g, d.dln_t_b, Mt, Dt, 0, s, drop.on() ? dzm_t : nullptr, &drop_rt));
   // out_a / out_t and out_proj
-  struct Side { int M; void* dz; const void* o; const void* ctx; void* dob; void* dctx; const void* wout; const void* wo;
+  struct Side { int M; int D; void* dz; const void* o; const void* ctx; void* dob; void* dctx; const void* wout; const void* wo;
                 float* dwout; float* dbout; float* dwo; float* dbo; };
   // (branch gradient = mask * dz from the LayerNorm backward; the skip path -- last two GEMMs below -- keeps dz)
   const Side sides[2] = {
-      {Ma, dzm_a, d.o_a, d.ctx_a, do_a, dctx_a, d.wout_a, d.wo_a, d.dwout_a, d.dbout_a, d.dwo_a, d.dbo_a},
-      {Mt, dzm_t, d.o_t, d.ctx_t, do_t, dctx_t, d.wout_t, d.wo_t, d.dwout_t, d.dbout_t, d.dwo_t, d.dbo_t},
+      {Ma, D, dzm_a, d.o_a, d.ctx_a, do_a, dctx_a, d.wout_a, d.wo_a, d.dwout_a, d.dbout_a, d.dwo_a, d.dbo_a},
+      {Mt, Dt, dzm_t, d.o_t, d.ctx_t, do_t, dctx_t, d.wout_t, d.wo_t, d.dwout_t, d.dbout_t, d.dwo_t, d.dbo_t},
   };
   for (const Side& sd : sides) {
-    SER_TRY(linear_wgrad(dt, sd.M, D, S, sd.dz, D, sd.o, S, sd.dwout, S, s, sd.dbout, d.grads_zeroed));
-    SER_TRY(linear_dgrad(dt, sd.M, D, S, sd.dz, D, sd.wout, S, sd.dob, S, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
+    SER_TRY(linear_wgrad(dt, sd.M, sd.D, S, sd.dz, sd.D, sd.o, S, sd.dwout, S, s, sd.dbout, d.grads_zeroed));
+    SER_TRY(linear_dgrad(dt, sd.M, sd.D, S, sd.dz, sd.D, sd.wout, S, sd.dob, S, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
     SER_TRY(linear_wgrad(dt, sd.M, S, S, sd.dob, S, sd.ctx, S, sd.dwo, S, s, sd.dbo, d.grads_zeroed));
     SER_TRY(linear_dgrad(dt, sd.M, S, S, sd.dob, S, sd.wo, S, sd.dctx, S, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f, s));
   }
@@ -542,8 +544,8 @@ int xattn_bwd(const ser_xattn_desc& d, cudaStream_t s) {
   // outer projections + residual path
   SER_TRY(linear_wgrad(dt, Ma, S3, D, dqkv_a, S3, d.a, D, d.dwqkv_a, D, s, d.dbqkv_a, d.grads_zeroed));
   SER_TRY(linear_dgrad(dt, Ma, S3, D, dqkv_a, S3, d.wqkv_a, D, d.da, D, f, nullptr, 0, f, GATE_NONE, dz_a, D, f, s));
-  SER_TRY(linear_wgrad(dt, Mt, S3, D, dqkv_t, S3, d.t, D, d.dwqkv_t, D, s, d.dbqkv_t, d.grads_zeroed));
-  SER_TRY(linear_dgrad(dt, Mt, S3, D, dqkv_t, S3, d.wqkv_t, D, d.dt, D, f, nullptr, 0, f, GATE_NONE, dz_t, D, f, s));
+  SER_TRY(linear_wgrad(dt, Mt, S3, Dt, dqkv_t, S3, d.t, Dt, d.dwqkv_t, Dt, s, d.dbqkv_t, d.grads_zeroed));
+  SER_TRY(linear_dgrad(dt, Mt, S3, Dt, dqkv_t, S3, d.wqkv_t, Dt, d.dt, Dt, f, nullptr, 0, f, GATE_NONE, dz_t, Dt, f, s));
   return SER_OK;
 }
 
@@ -595,11 +597,12 @@ static MixArgs to_mix(const ser_fusion_desc& d) {
 int fusion_fwd(const ser_fusion_desc& d, cudaStream_t s) {
   const int dt = d.dtype, f = is_f32(dt);
   const int B = d.B, P = d.P, G = d.G, Din = d.Din;
+  const int Dint = d.Din_t > 0 ? d.Din_t : d.Din;      // FusionLayer(audio_dim != text_dim): the pair below becomes two launches
   SER_REQUIRE(B > 0 && d.av && d.tv && d.fused, "fusion_fwd: null tensor");
   const DropSpec drop = make_drop(d.drop_seed, d.p_drop, 0);       // proj_a[2] / proj_t[2] (fusion.py:9,12)
   // the two modality branches run the same three GEMMs: each pair is one batched launch when the operands are twins
   SER_TRY(gemm_pair(fwd_args(dt, B, P, Din, d.av, Din, d.w1a, Din, d.b1a, d.ha, P, f, ACT_RELU, nullptr, 0, f),
-                    fwd_args(dt, B, P, Din, d.tv, Din, d.w1t, Din, d.b1t, d.ht, P, f, ACT_RELU, nullptr, 0, f), s));
+                    fwd_args(dt, B, P, Dint, d.tv, Dint, d.w1t, Dint, d.b1t, d.ht, P, f, ACT_RELU, nullptr, 0, f), s));
   if (drop.on()) {
     SER_TRY(dropout_apply(d.ha, d.ha, nullptr, f, B, P, with_site(drop, DS_FUS_A), s));
     SER_TRY(dropout_apply(d.ht, d.ht, nullptr, f, B, P, with_site(drop, DS_FUS_T), s));
@@ -620,6 +623,7 @@ size_t fusion_bwd_ws_bytes(int dtype, int B, int Din, int P, int G) {
 int fusion_bwd(const ser_fusion_desc& d, cudaStream_t s) {
   const int dt = d.dtype, f = is_f32(dt);
   const int B = d.B, P = d.P, G = d.G, Din = d.Din;
+  const int Dint = d.Din_t > 0 ? d.Din_t : d.Din;
   const size_t e = esize(dt);
   Arena ws(d.ws, d.ws_bytes);
   void* dpa = ws.take(static_cast<size_t>(B) * P * e);
@@ -664,9 +668,9 @@ int fusion_bwd(const ser_fusion_desc& d, cudaStream_t s) {
                       dgrad_args(dt, B, P, P, T_.dp, P, T_.w2, P, T_.dh, P, f, T_.h, P, f, GATE_RELU, nullptr, 0, f, hscale), s));
     SER_TRY(sb.fork());
     SER_TRY(gemm_pair(wgrad_args(dt, B, P, Din, A_.dh, P, A_.v, Din, A_.dw1, Din, A_.db1, z),
-                      wgrad_args(dt, B, P, Din, T_.dh, P, T_.v, Din, T_.dw1, Din, T_.db1, z), sb.side()));
+                      wgrad_args(dt, B, P, Dint, T_.dh, P, T_.v, Dint, T_.dw1, Dint, T_.db1, z), sb.side()));
     SER_TRY(gemm_pair(dgrad_args(dt, B, P, Din, A_.dh, P, A_.w1, Din, A_.dv, Din, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f),
-                      dgrad_args(dt, B, P, Din, T_.dh, P, T_.w1, Din, T_.dv, Din, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f), s));
+                      dgrad_args(dt, B, P, Dint, T_.dh, P, T_.w1, Dint, T_.dv, Dint, f, nullptr, 0, f, GATE_NONE, nullptr, 0, f), s));
     SER_TRY(sb.join());
   }
   return SER_OK;

@@ -199,11 +199,11 @@ class CrossAttentionFn(torch.autograd.Function):
         dt = L.dtype_code(a.dtype)
         wc = fp.compute_copy(a.dtype)
         B, Ta, D = a.shape
-        Tt = t.shape[1]
+        Tt, Dt = t.shape[1], t.shape[2]            # Dt != D: CrossModalAttention(audio_dim != text_dim), unfolded path
         S = fp.params[fp.index["q_a.weight"]].shape[0]
         dev, ty = a.device, a.dtype
         a2 = a.reshape(B * Ta, D).contiguous()
-        t2 = t.reshape(B * Tt, D).contiguous()
+        t2 = t.reshape(B * Tt, Dt).contiguous()
         am, tm = _f32c(a_mask), _f32c(t_mask)
         Ma, Mt = B * Ta, B * Tt
         E = lambda *s: torch.empty(*s, device=dev, dtype=ty)           # noqa: E731
@@ -211,11 +211,11 @@ class CrossAttentionFn(torch.autograd.Function):
         # bf16 tier: consecutive Linear layers are folded (csrc/fold.cu) -- the library then never touches the
         # outer-projection outputs qkv_* nor the out_proj outputs o_*, and keeps the folded weights in fold_w / fold_b.
         # The LIBRARY decides (it also honours the SER_NO_FOLD A/B switch); the buffers are sized from its answer.
-        folded = bool(L.load().ser_xattn_folded(dt, D, S))
+        folded = bool(L.load().ser_xattn_folded(dt, D, S)) and Dt == D
         tok = (lambda M, n: None) if folded else (lambda M, n: E(M, n))
         sv = dict(qkv_a=tok(Ma, 3 * S), qkv_t=tok(Mt, 3 * S), p_a=E(Ma, 3 * S), p_t=E(Mt, 3 * S), ctx_a=E(Ma, S),
                   ctx_t=E(Mt, S), lse_a=F(B, num_heads, Ta), lse_t=F(B, num_heads, Tt), o_a=tok(Ma, S), o_t=tok(Mt, S),
-                  z_a=E(Ma, D), z_t=E(Mt, D), stats_a=F(Ma, 2), stats_t=F(Mt, 2))
+                  z_a=E(Ma, D), z_t=E(Mt, Dt), stats_a=F(Ma, 2), stats_t=F(Mt, 2))
         if folded:
             sv["fold_w"] = E(2 * 9 * S * S + 2 * 3 * S * D + 2 * D * S)
             sv["fold_b"] = F(2 * 3 * S + 2 * D)
@@ -237,18 +237,18 @@ class CrossAttentionFn(torch.autograd.Function):
             I32 = lambda n: torch.empty(n, device=dev, dtype=torch.int32)  # noqa: E731
             sv["keep_a"] = I32(B * num_heads * Ta * ((Tt + 31) // 32))
             sv["keep_t"] = I32(B * num_heads * Tt * ((Ta + 31) // 32))
-        enh_a, enh_t = E(Ma, D), E(Mt, D)
+        enh_a, enh_t = E(Ma, D), E(Mt, Dt)
         w = CrossAttentionFn._weights(fp, wc)
         keep = []
-        d = L.fill(L.XattnDesc(), keep, dtype=dt, B=B, Ta=Ta, Tt=Tt, D=D, S=S, H=num_heads, a=a2, t=t2, a_mask=am,
+        d = L.fill(L.XattnDesc(), keep, dtype=dt, B=B, Ta=Ta, Tt=Tt, D=D, Dt=Dt, S=S, H=num_heads, a=a2, t=t2, a_mask=am,
                    t_mask=tm, enh_a=enh_a, enh_t=enh_t, reuse_text=reuse, **w, **sv, **_drop_fields(p_drop, seed))
         L.call("ser_xattn_fwd", d, dev)
         ctx.drop = (p_drop, seed)
         sv = {k: v for k, v in sv.items() if v is not None}
         ctx.save_for_backward(a2, t2, am, tm, wc, *sv.values())
         ctx.sv_keys = list(sv.keys())
-        ctx.fp, ctx.dims = fp, (B, Ta, Tt, D, S, num_heads)
-        return enh_a.view(B, Ta, D), enh_t.view(B, Tt, D)
+        ctx.fp, ctx.dims = fp, (B, Ta, Tt, D, Dt, S, num_heads)
+        return enh_a.view(B, Ta, D), enh_t.view(B, Tt, Dt)
 
     @staticmethod
     def _weights(fp: FlatParams, wc: torch.Tensor):
@@ -271,18 +271,18 @@ class CrossAttentionFn(torch.autograd.Function):
         a2, t2, am, tm, wc, *svt = ctx.saved_tensors
         sv = dict(zip(ctx.sv_keys, svt))
         fp = ctx.fp
-        B, Ta, Tt, D, S, H = ctx.dims
+        B, Ta, Tt, D, Dt, S, H = ctx.dims
         dev, ty = a2.device, a2.dtype
         dt = L.dtype_code(ty)
         Ma, Mt = B * Ta, B * Tt
-        zero = lambda M: torch.zeros(M, D, device=dev, dtype=ty)   # noqa: E731
-        ga = d_enh_a.reshape(Ma, D).to(ty).contiguous() if d_enh_a is not None else zero(Ma)
-        gt = d_enh_t.reshape(Mt, D).to(ty).contiguous() if d_enh_t is not None else zero(Mt)
+        zero = lambda M, n: torch.zeros(M, n, device=dev, dtype=ty)   # noqa: E731
+        ga = d_enh_a.reshape(Ma, D).to(ty).contiguous() if d_enh_a is not None else zero(Ma, D)
+        gt = d_enh_t.reshape(Mt, Dt).to(ty).contiguous() if d_enh_t is not None else zero(Mt, Dt)
         g = fp.new_grad_buffer()
         da = torch.empty_like(a2)
         dtt = torch.empty_like(t2)
         lib = L.load()
-        ws = _ws(lib.ser_xattn_bwd_ws_bytes(dt, B, Ta, Tt, D, S, H), dev)
+        ws = _ws(lib.ser_xattn_bwd_ws_bytes(dt, B, Ta, Tt, max(D, Dt), S, H), dev)
         grads = dict(
             dwqkv_a=fp.view(g, "q_a.weight", 3), dbqkv_a=fp.view(g, "q_a.bias", 3),
             dwqkv_t=fp.view(g, "q_t.weight", 3), dbqkv_t=fp.view(g, "q_t.bias", 3),
@@ -296,12 +296,12 @@ class CrossAttentionFn(torch.autograd.Function):
             dln_t_g=fp.view(g, "norm_t.weight"), dln_t_b=fp.view(g, "norm_t.bias"),
         )
         keep = []
-        d = L.fill(L.XattnDesc(), keep, dtype=dt, B=B, Ta=Ta, Tt=Tt, D=D, S=S, H=H, a=a2, t=t2, a_mask=am, t_mask=tm,
+        d = L.fill(L.XattnDesc(), keep, dtype=dt, B=B, Ta=Ta, Tt=Tt, D=D, Dt=Dt, S=S, H=H, a=a2, t=t2, a_mask=am, t_mask=tm,
                    d_enh_a=ga, d_enh_t=gt, da=da, dt=dtt, ws=ws, ws_bytes=ws.numel(), grads_zeroed=GRADS_ZEROED,
                    **CrossAttentionFn._weights(fp, wc), **sv, **grads, **_drop_fields(*ctx.drop))
         L.call("ser_xattn_bwd", d, dev)
         return (da.view(B, Ta, D) if ctx.needs_input_grad[0] else None,
-                dtt.view(B, Tt, D) if ctx.needs_input_grad[1] else None,
+                dtt.view(B, Tt, Dt) if ctx.needs_input_grad[1] else None,
                 None, None, None, None, None, None, None, *fp.grads_from(g))
 
 
@@ -390,6 +390,7 @@ class FusionFn(torch.autograd.Function):
         wc = fp.compute_copy(av.dtype)
         av2, tv2 = av.contiguous(), tv.to(av.dtype).contiguous()
         B, Din = av2.shape
+        Din_t = tv2.shape[1]                       # != Din: FusionLayer(audio_dim != text_dim), the first GEMM pair splits
         P = fp.params[fp.index["proj_a.0.weight"]].shape[0]
         G = fp.params[fp.index["gate_a.0.weight"]].shape[0]
         dev, ty = av.device, av.dtype
@@ -400,13 +401,13 @@ class FusionFn(torch.autograd.Function):
                   gates=torch.empty(B, 2, device=dev, dtype=torch.float32))
         fused = E(B, P)
         keep = []
-        d = L.fill(L.FusionDesc(), keep, dtype=dt, B=B, Din=Din, P=P, G=G, av=av2, tv=tv2, fused=fused,
+        d = L.fill(L.FusionDesc(), keep, dtype=dt, B=B, Din=Din, Din_t=Din_t, P=P, G=G, av=av2, tv=tv2, fused=fused,
                    **FusionFn._weights(fp, wc), **sv, **_drop_fields(p_drop, seed))
         L.call("ser_fusion_fwd", d, dev)
         ctx.drop = (p_drop, seed)
         ctx.save_for_backward(av2, tv2, wc, *sv.values())
         ctx.sv_keys = list(sv.keys())
-        ctx.fp, ctx.dims = fp, (B, Din, P, G)
+        ctx.fp, ctx.dims = fp, (B, Din, Din_t, P, G)
         return fused
 
     @staticmethod
@@ -414,12 +415,15 @@ class FusionFn(torch.autograd.Function):
         av2, tv2, wc, *svt = ctx.saved_tensors
         sv = dict(zip(ctx.sv_keys, svt))
         fp = ctx.fp
-        B, Din, P, G = ctx.dims
+        B, Din, Din_t, P, G = ctx.dims
         dev, ty = av2.device, av2.dtype
         dt = L.dtype_code(ty)
         g = fp.new_grad_buffer()
-        dvv = torch.empty(2, B, Din, device=dev, dtype=ty)
-        dav, dtv = dvv[0], dvv[1]
+        if Din_t == Din:
+            dvv = torch.empty(2, B, Din, device=dev, dtype=ty)       # twins: one batched launch for the pair
+            dav, dtv = dvv[0], dvv[1]
+        else:
+            dav, dtv = torch.empty(B, Din, device=dev, dtype=ty), torch.empty(B, Din_t, device=dev, dtype=ty)
         lib = L.load()
         ws = _ws(lib.ser_fusion_bwd_ws_bytes(dt, B, Din, P, G), dev)
         grads = {}
@@ -429,7 +433,7 @@ class FusionFn(torch.autograd.Function):
             grads[f"dwg1{m}"] = fp.view(g, f"gate_{m}.0.weight"); grads[f"dbg1{m}"] = fp.view(g, f"gate_{m}.0.bias")
             grads[f"dwg2{m}"] = fp.view(g, f"gate_{m}.2.weight"); grads[f"dbg2{m}"] = fp.view(g, f"gate_{m}.2.bias")
         keep = []
-        d = L.fill(L.FusionDesc(), keep, dtype=dt, B=B, Din=Din, P=P, G=G, av=av2, tv=tv2,
+        d = L.fill(L.FusionDesc(), keep, dtype=dt, B=B, Din=Din, Din_t=Din_t, P=P, G=G, av=av2, tv=tv2,
                    dfused=dfused.to(ty).contiguous(), dav=dav, dtv=dtv, ws=ws, ws_bytes=ws.numel(), grads_zeroed=GRADS_ZEROED,
                    **FusionFn._weights(fp, wc), **sv, **grads, **_drop_fields(*ctx.drop))
         L.call("ser_fusion_bwd", d, dev)

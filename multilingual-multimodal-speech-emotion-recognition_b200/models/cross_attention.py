@@ -21,8 +21,8 @@ class CrossModalAttention(nn.Module):
         super().__init__()
         if shared_dim % num_heads != 0:
             raise AssertionError(f"shared_dim {shared_dim} must be divisible by num_heads {num_heads}")
-        if audio_dim != text_dim:
-            raise ValueError("the fused kernel expects audio_dim == text_dim (768 for wav2vec2-base / xlm-roberta-base)")
+        # audio_dim != text_dim (e.g. wav2vec2-base with xlm-roberta-large) runs the per-layer GEMM path of the library;
+        # equal widths with audio_dim == 3 * shared_dim (every reference script) take the folded, pair-batched one
         self.shared_dim, self.num_heads, self.p_drop = shared_dim, num_heads, float(dropout)
         for direction, (q_src, kv_src) in (("a", ("a", "t")), ("t", ("t", "a"))):
             dim_q = audio_dim if q_src == "a" else text_dim

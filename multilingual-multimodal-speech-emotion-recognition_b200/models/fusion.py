@@ -23,8 +23,6 @@ def _gate(d: int, hidden: int) -> nn.Sequential:
 class FusionLayer(nn.Module):
     def __init__(self, audio_dim: int, text_dim: int, proj_dim: int):
         super().__init__()
-        if audio_dim != text_dim:
-            raise ValueError("the fused kernel expects audio_dim == text_dim (both 2*768 in every reference script)")
         self.proj_a = _mlp(audio_dim, proj_dim)
         self.proj_t = _mlp(text_dim, proj_dim)
         hidden = max(32, proj_dim // 2)

@@ -64,10 +64,11 @@ def feature_fusion_weights(tag: str, num_features: int, seed: int = 0, hidden: i
     }
 
 
-def cross_weights(seed: int = 0) -> Dict[str, torch.Tensor]:
+def cross_weights(seed: int = 0, audio_dim: int = D, text_dim: int = D) -> Dict[str, torch.Tensor]:
     w = {}
+    dim = {"a": audio_dim, "t": text_dim}
     for n in ("q_a", "k_t", "v_t", "q_t", "k_a", "v_a"):
-        w[f"{n}.weight"] = _fill(f"cross.{n}.weight", (S, D), "linear_w", seed)
+        w[f"{n}.weight"] = _fill(f"cross.{n}.weight", (S, dim[n[-1]]), "linear_w", seed)
         w[f"{n}.bias"] = _fill(f"cross.{n}.bias", (S,), "bias", seed)
     for n in ("attn_a", "attn_t"):
         w[f"{n}.in_proj_weight"] = _fill(f"cross.{n}.in_proj_weight", (3 * S, S), "linear_w", seed)
@@ -75,11 +76,11 @@ def cross_weights(seed: int = 0) -> Dict[str, torch.Tensor]:
         w[f"{n}.out_proj.weight"] = _fill(f"cross.{n}.out_proj.weight", (S, S), "linear_w", seed)
         w[f"{n}.out_proj.bias"] = _fill(f"cross.{n}.out_proj.bias", (S,), "bias", seed)
     for n in ("out_a", "out_t"):
-        w[f"{n}.weight"] = _fill(f"cross.{n}.weight", (D, S), "linear_w", seed)
-        w[f"{n}.bias"] = _fill(f"cross.{n}.bias", (D,), "bias", seed)
+        w[f"{n}.weight"] = _fill(f"cross.{n}.weight", (dim[n[-1]], S), "linear_w", seed)
+        w[f"{n}.bias"] = _fill(f"cross.{n}.bias", (dim[n[-1]],), "bias", seed)
     for n in ("norm_a", "norm_t"):
-        w[f"{n}.weight"] = _fill(f"cross.{n}.weight", (D,), "ln_w", seed)
-        w[f"{n}.bias"] = _fill(f"cross.{n}.bias", (D,), "ln_b", seed)
+        w[f"{n}.weight"] = _fill(f"cross.{n}.weight", (dim[n[-1]],), "ln_w", seed)
+        w[f"{n}.bias"] = _fill(f"cross.{n}.bias", (dim[n[-1]],), "ln_b", seed)
     return w
 
 
@@ -92,10 +93,10 @@ def pool_weights(tag: str, seed: int = 0) -> Dict[str, torch.Tensor]:
     }
 
 
-def fusion_weights(seed: int = 0) -> Dict[str, torch.Tensor]:
+def fusion_weights(seed: int = 0, audio_dim: int = 2 * D, text_dim: int = 2 * D) -> Dict[str, torch.Tensor]:
     w = {}
     for m in ("a", "t"):
-        w[f"proj_{m}.0.weight"] = _fill(f"fusion.proj_{m}.0.weight", (P, 2 * D), "linear_w", seed)
+        w[f"proj_{m}.0.weight"] = _fill(f"fusion.proj_{m}.0.weight", (P, audio_dim if m == "a" else text_dim), "linear_w", seed)
         w[f"proj_{m}.0.bias"] = _fill(f"fusion.proj_{m}.0.bias", (P,), "bias", seed)
         w[f"proj_{m}.3.weight"] = _fill(f"fusion.proj_{m}.3.weight", (P, P), "linear_w", seed)
         w[f"proj_{m}.3.bias"] = _fill(f"fusion.proj_{m}.3.bias", (P,), "bias", seed)

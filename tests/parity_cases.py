@@ -232,13 +232,13 @@ def _pin_seed(module, name, dev):
     module._drop_seed.counter = _seed_tensor(name, dev)      # the next forward uses exactly this value
 
 
-def cross_masks(dev, p, B, H, Ta, Tt, D):
+def cross_masks(dev, p, B, H, Ta, Tt, D, Dt=None):
     from mmser_b200.functional import dropout_mask as dm
     s = _seed_tensor("cross", dev)
     return {"cross.prob_a": dm(s, 1, p, B * H * Ta, Tt).view(B, H, Ta, Tt).cpu(),
             "cross.prob_t": dm(s, 2, p, B * H * Tt, Ta).view(B, H, Tt, Ta).cpu(),
             "cross.res_a": dm(s, 3, p, B * Ta, D).view(B, Ta, D).cpu(),
-            "cross.res_t": dm(s, 4, p, B * Tt, D).view(B, Tt, D).cpu()}
+            "cross.res_t": dm(s, 4, p, B * Tt, Dt or D).view(B, Tt, Dt or D).cpu()}
 
 
 def fusion_masks(dev, p, B, P=512):
@@ -306,11 +306,14 @@ def feature_fusion_case(B=3, T=37, F=20, p_drop=0.0):
                 prepare=prep if p_drop > 0 else None)
 
 
-def cross_case(B=3, Ta=70, Tt=19, masks=True, seed=7, p_drop=0.0):
+def cross_case(B=3, Ta=70, Tt=19, masks=True, seed=7, p_drop=0.0, text_dim=768):
+    """text_dim != 768: CrossModalAttention(audio_dim != text_dim) (cross_attention.py:7-30), the library's unfolded path."""
     from mmser_b200 import models as M
-    w = {"cross": synth.cross_weights()}
+    w = {"cross": synth.cross_weights(text_dim=text_dim)}
     a, t, am, tm, _ = synth.make_inputs(B, Ta, Tt, 4, seed=seed, with_masks=masks)
-    ins = {"a": a, "t": t, "a_mask": am, "t_mask": tm, "ua": _rand((B, Ta, 768), 3), "ut": _rand((B, Tt, 768), 4)}
+    if text_dim != 768:
+        t = _rand((B, Tt, text_dim), 5) * (t.abs().sum(-1, keepdim=True) > 0)      # same padding pattern (zero-filled)
+    ins = {"a": a, "t": t, "a_mask": am, "t_mask": tm, "ua": _rand((B, Ta, 768), 3), "ut": _rand((B, Tt, text_dim), 4)}
 
     def oracle(i, ws):
         am_ = None if i["a_mask"] is None else i["a_mask"].to(i["a"].dtype)
@@ -320,7 +323,7 @@ def cross_case(B=3, Ta=70, Tt=19, masks=True, seed=7, p_drop=0.0):
         return {"audio_enh": ea, "text_enh": et}, (ea * i["ua"]).sum() + (et * i["ut"]).sum()
 
     def cuda(i, dtype, dev):
-        m = M.CrossModalAttention(768, 768, dropout=p_drop).to(dev); m.load_state_dict(w["cross"])
+        m = M.CrossModalAttention(768, text_dim, dropout=p_drop).to(dev); m.load_state_dict(w["cross"])
         m.train()
         _pin_seed(m, "cross", dev)
         ag = i["a"].to(dev).to(dtype).requires_grad_(True)
@@ -330,7 +333,7 @@ def cross_case(B=3, Ta=70, Tt=19, masks=True, seed=7, p_drop=0.0):
         ((ea.float() * i["ua"].to(dev)).sum() + (et.float() * i["ut"].to(dev)).sum()).backward()
         return {"audio_enh": ea, "text_enh": et}, _param_grads("cross", m), {"a": ag.grad, "t": tg.grad}
 
-    prep = (lambda dev: {"_masks": cross_masks(dev, p_drop, B, 8, Ta, Tt, 768)}) if p_drop > 0 else None
+    prep = (lambda dev: {"_masks": cross_masks(dev, p_drop, B, 8, Ta, Tt, 768, text_dim)}) if p_drop > 0 else None
     return Case(f"cross{'_masked' if masks else '_nomask'}{'_dropout' if p_drop > 0 else ''}", ins, w, oracle, cuda,
                 grad_inputs=("a", "t"), prepare=prep)
 
@@ -356,10 +359,13 @@ def pool_case(B=4, T=53, masks=True):
     return Case("pool", ins, w, oracle, cuda, grad_inputs=("x",))
 
 
-def fusion_case(B=9, p_drop=0.0):
+def fusion_case(B=9, p_drop=0.0, text_dim=1536):
+    """text_dim != 1536: FusionLayer(audio_dim != text_dim) (fusion.py:6-16)."""
     from mmser_b200 import models as M
-    w = {"fusion": synth.fusion_weights()}
-    ins = {"av": _rand((B, 1536), 6), "tv": _rand((B, 1536), 7), "up": _rand((B, 512), 8)}
+    w = {"fusion": synth.fusion_weights(text_dim=text_dim)}
+    # (bf16 tier: a gate-MLP ReLU input within bf16 rounding of zero is one discrete flip = 1/sqrt(B * 128) ~ 3e-2 on that
+    #  layer's gradient for whichever implementation draws it -- DESIGN.md section 4; the seeds are fixed, not tuned per run)
+    ins = {"av": _rand((B, 1536), 6), "tv": _rand((B, text_dim), 7 if text_dim == 1536 else 27), "up": _rand((B, 512), 8)}
 
     def oracle(i, ws):
         with O.dropout_masks(i.get("_masks")):
@@ -367,7 +373,7 @@ def fusion_case(B=9, p_drop=0.0):
         return {"fused": y}, (y * i["up"]).sum()
 
     def cuda(i, dtype, dev):
-        m = M.FusionLayer(1536, 1536, 512).to(dev); m.load_state_dict(w["fusion"])
+        m = M.FusionLayer(1536, text_dim, 512).to(dev); m.load_state_dict(w["fusion"])
         m.proj_a[2].p = m.proj_t[2].p = p_drop
         m.train()
         _pin_seed(m, "fusion", dev)
@@ -509,6 +515,11 @@ ALL_CASES = {
     "pool": pool_case,
     "pool_nomask": lambda: pool_case(masks=False),
     "fusion": fusion_case,
+    # unequal audio / text widths (wav2vec2-base 768 with a 1024-wide text encoder; pooled 1536 / 2048)
+    "cross_mixed_dims": lambda: cross_case(B=3, Ta=70, Tt=19, masks=True, text_dim=1024),
+    "cross_mixed_dims_dropout": lambda: cross_case(B=2, Ta=66, Tt=35, masks=True, seed=9, p_drop=0.1, text_dim=1024),
+    "fusion_mixed_dims": lambda: fusion_case(B=9, text_dim=2048),
+    "fusion_mixed_dims_dropout": lambda: fusion_case(B=9, p_drop=0.1, text_dim=2048),
     "classifier": classifier_case,
     # two 128-row clusters of the fused stack kernel, the second one partially filled (rows >= B must stay inert)
     "classifier_b200": lambda: classifier_case(B=200, C=6),

@@ -130,6 +130,27 @@ def test_flat_param_packing(lib):
         fp.ensure()                      # CPU parameters: no CPU path, fail loudly
 
 
+def test_unequal_audio_text_widths_keep_the_reference_layout(lib):
+    """CrossModalAttention / FusionLayer with audio_dim != text_dim (reference constructors cross_attention.py:7-30,
+    fusion.py:6-16): reference parameter names and shapes, packed q|k|v views per modality, descriptor fields present."""
+    import mmser_b200
+    from mmser_b200 import synth
+    m = mmser_b200.models.CrossModalAttention(768, 1024)
+    shapes = {n: tuple(p.shape) for n, p in m.named_parameters()}
+    assert shapes["q_a.weight"] == (256, 768) and shapes["k_a.weight"] == (256, 768) and shapes["v_a.weight"] == (256, 768)
+    assert shapes["q_t.weight"] == (256, 1024) and shapes["k_t.weight"] == (256, 1024) and shapes["v_t.weight"] == (256, 1024)
+    assert shapes["out_a.weight"] == (768, 256) and shapes["out_t.weight"] == (1024, 256)
+    assert shapes["norm_a.weight"] == (768,) and shapes["norm_t.weight"] == (1024,)
+    m.load_state_dict(synth.cross_weights(text_dim=1024))
+    fp = m._flat
+    flat = torch.arange(fp.total, dtype=torch.float32)
+    assert fp.view(flat, "q_t.weight", 3).shape == (768, 1024) and fp.view(flat, "q_a.weight", 3).shape == (768, 768)
+    f = mmser_b200.models.FusionLayer(1536, 2048, 512)
+    f.load_state_dict(synth.fusion_weights(text_dim=2048))
+    assert tuple(f.proj_a[0].weight.shape) == (512, 1536) and tuple(f.proj_t[0].weight.shape) == (512, 2048)
+    assert "Dt" in dict(lib.XattnDesc._fields_) and "Din_t" in dict(lib.FusionDesc._fields_)
+
+
 def test_no_cpu_fallback(lib):
     import mmser_b200
     with pytest.raises(lib.SerError):
