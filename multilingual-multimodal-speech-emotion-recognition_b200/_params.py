@@ -130,15 +130,17 @@ class FlatParams:
         return torch.zeros(self.total, device=self.flat.device, dtype=torch.float32)
 
     @staticmethod
-    def shared_grad_arena(flats: Sequence["FlatParams"], holder=None) -> None:
+    def shared_grad_arena(flats: Sequence["FlatParams"], holder=None, zero: bool = True):
         """One zero-filled allocation (one fill kernel) for the gradient buffers of several modules' next backward:
         every module's new_grad_buffer() then returns its slice.  Inside a captured CUDA graph every node costs a few
         microseconds of serialisation, so seven fills become one.
         `holder` (any object): keep ONE arena on it and re-zero it every step instead of allocating -- `.grad` storage is
         then the same for every step and every captured graph.  Only for callers that never accumulate gradients over
-        several backward passes (the previous step's `.grad` views alias the new ones)."""
+        several backward passes (the previous step's `.grad` views alias the new ones).
+        `zero=False` (persistent arena only): the caller fills the returned arena with zeros itself before the backward
+        pass starts (FusionHead does it on a side stream, beside the latency-bound fusion chain)."""
         if not flats:
-            return
+            return None
         for fp in flats:
             fp.ensure()
         dev = flats[0].flat.device
@@ -148,13 +150,15 @@ class FlatParams:
             if arena is None or arena.numel() != n or arena.device != dev:
                 arena = torch.empty(n, device=dev, dtype=torch.float32)
                 holder.__dict__["_grad_arena"] = arena
-            arena.zero_()
+            if zero:
+                arena.zero_()
         else:
             arena = torch.zeros(n, device=dev, dtype=torch.float32)
         off = 0
         for fp in flats:
             fp._next_grad = arena[off:off + fp.total]
             off += fp.total
+        return arena
 
     def grads_from(self, gflat: torch.Tensor) -> List[torch.Tensor]:
         if self.grad_hook is not None:

@@ -3,6 +3,8 @@ one nn.Module over the drop-in modules.  This is the public entry point used by 
 the individual modules remain usable on their own exactly like the reference's."""
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Optional
 
 import torch
@@ -49,6 +51,18 @@ class FusionHead(nn.Module):
         self.prototypes = PrototypeMemory(num_labels, proj_dim)
         self.loss_weights = dict(w_ce=1.0, w_focal=0.3, w_unc=0.05, w_proto=0.01)   # train.py:156-168
         self.persistent_grad_arena = False
+        # step preparation that nothing before the fusion layer depends on -- the bf16 copy of the classifier's weights
+        # (78 % of all parameters) and the zero fill of the persistent gradient arena, both pure HBM traffic -- runs on a
+        # side stream beside the fusion MLP / gate chain (a dozen M = B GEMMs on a handful of SMs); SER_PREP_SIDE=0 or
+        # this flag keep it at the start of the step on the caller's stream
+        self.side_prep = os.environ.get("SER_PREP_SIDE", "1") != "0"
+
+    def _side_stream(self, dev) -> "torch.cuda.Stream":
+        s = self.__dict__.get("_side")
+        if s is None or s.device != dev:
+            s = torch.cuda.Stream(device=dev)
+            self.__dict__["_side"] = s
+        return s
 
     def set_dropout(self, dropout) -> Dict[str, float]:
         """Change the dropout rates of the built head (float, dict or 'reference'); returns the rates in effect."""
@@ -129,11 +143,17 @@ class FusionHead(nn.Module):
     def features(self, a_hid, t_hid, a_mask=None, t_mask=None):
         # bf16 tier: the operand copies of all modules' weights in one launch instead of one per module
         flats = [getattr(self, g)._flat for g in self.GROUPS if hasattr(getattr(self, g), "_flat")]
-        FlatParams.precast(flats, a_hid.dtype)
+        side = self.side_prep and a_hid.is_cuda
+        late = [self.classifier._flat] if side else []            # cast beside the fusion chain (below)
+        FlatParams.precast([f for f in flats if all(f is not l for l in late)], a_hid.dtype)
+        arena = None
         if torch.is_grad_enabled():
             # one zero fill for all modules' gradient buffers of this step (a fresh allocation per step, or -- when the
-            # caller guarantees zero_grad() before every step, as DataParallelHead.train_step does -- one persistent arena)
-            FlatParams.shared_grad_arena(flats, holder=self if self.persistent_grad_arena else None)
+            # caller guarantees zero_grad() before every step, as DataParallelHead.train_step does -- one persistent arena,
+            # which is then filled on the side stream)
+            defer = side and self.persistent_grad_arena
+            arena = FlatParams.shared_grad_arena(flats, holder=self if self.persistent_grad_arena else None, zero=not defer)
+            arena = arena if defer else None
         a_seq = self.adapter_a.residual_forward(a_hid)
         t_seq = self.adapter_t.residual_forward(t_hid)
         a_enh, t_enh = self.cross(a_seq, t_seq, a_mask, t_mask)
@@ -142,7 +162,16 @@ class FusionHead(nn.Module):
         self.pool_a._out_buffer, self.pool_t._out_buffer = pooled[0], pooled[1]
         a_vec = self.pool_a(a_enh, a_mask)
         t_vec = self.pool_t(t_enh, t_mask)
+        if side:
+            main, sd = torch.cuda.current_stream(a_hid.device), self._side_stream(a_hid.device)
+            sd.wait_stream(main)                                  # fork (a parallel branch of a captured step graph)
+            with torch.cuda.stream(sd):
+                FlatParams.precast(late, a_hid.dtype)
+                if arena is not None:
+                    arena.zero_()
         fused = self.fusion(a_vec, t_vec)
+        if side:
+            main.wait_stream(sd)                                  # join: before the classifier and long before any backward kernel
         return dict(a_enh=a_enh, t_enh=t_enh, a_vec=a_vec, t_vec=t_vec, fused=fused)
 
     @torch.no_grad()

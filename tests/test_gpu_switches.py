@@ -1,5 +1,5 @@
 """The library's A/B switches change scheduling (programmatic dependent launch, the side branch for weight gradients,
-stored vs re-hashed dropout decisions, tcgen05 vs mma.sync attention), never results: one training step under each
+the side stream for step preparation, stored vs re-hashed dropout decisions, tcgen05 vs mma.sync attention), never results: one training step under each
 switch, in a fresh process (the switches are read once per process), against the default build."""
 import json
 import os
@@ -40,6 +40,12 @@ def test_switches_do_not_change_results(shape):
         assert set(got) == set(ref)
         for k in ref:
             assert _close(got[k], ref[k], 1e-5), (env, k, got[k], ref[k])
+    # step preparation (classifier weight cast, zero fill of the persistent gradient arena) beside the fusion chain on a
+    # side stream vs at the start of the step: second of two steps on one persistent arena
+    ref_p = _run({}, *args, "persist")
+    got = _run({"SER_PREP_SIDE": "0"}, *args, "persist")
+    for k in ref_p:
+        assert _close(got[k], ref_p[k], 1e-5), ("prep side", k, got[k], ref_p[k])
     # stored vs re-hashed dropout decisions: the same masks, one fused multiply-add contracts differently (bf16 last places)
     got = _run({"SER_ATTN_KEEPBITS": "0"}, *args)
     for k in ref:

@@ -18,7 +18,11 @@ head.load_group_state(synth.head_weights(C, 4))
 head.train()
 torch.manual_seed(3)                                   # dropout seeds are drawn from torch's CPU generator
 a, t, am, tm, labels = synth.make_inputs(B, Ta, Tt, C, seed=5)
-out = head(a.to(dev).bfloat16(), t.to(dev).bfloat16(), am.to(dev), tm.to(dev), labels.to(dev))
+ins = (a.to(dev).bfloat16(), t.to(dev).bfloat16(), am.to(dev), tm.to(dev), labels.to(dev))
+if "persist" in sys.argv:          # one persistent gradient arena, re-zeroed every step (what DataParallelHead.train_step uses)
+    head.persistent_grad_arena = True
+    head(*ins)["loss"].backward()  # the reported step is the SECOND one: its zero fill meets the first step's gradients
+out = head(*ins)
 out["loss"].backward()
 torch.cuda.synchronize()
 res = {"loss": float(out["loss"]), "logits": out["logits"].double().abs().sum().item()}
