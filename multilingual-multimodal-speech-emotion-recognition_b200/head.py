@@ -145,6 +145,12 @@ class FusionHead(nn.Module):
         flats = [getattr(self, g)._flat for g in self.GROUPS if hasattr(getattr(self, g), "_flat")]
         side = self.side_prep and a_hid.is_cuda
         late = [self.classifier._flat] if side else []            # cast beside the fusion chain (below)
+        for f in late:
+            # everything that may ALLOCATE (the flat master buffer after a .to(), the bf16 copy's storage) happens here, on
+            # the caller's stream: the caching allocator ties a block to the stream that was current when it was allocated
+            f.ensure()
+            if a_hid.dtype != torch.float32:
+                f._lowp_buffer(a_hid.dtype)
         FlatParams.precast([f for f in flats if all(f is not l for l in late)], a_hid.dtype)
         arena = None
         if torch.is_grad_enabled():
