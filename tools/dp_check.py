@@ -20,6 +20,7 @@ w = synth.head_weights(C)
 shards = [synth.make_inputs(Bs, Ta, Tt, C, seed=100 + r) for r in range(world)]
 worst = 0.0
 for dtype, tol, overlap in ((torch.float32, 2e-4, True), (torch.bfloat16, 6e-2, True), (torch.float32, 2e-4, False)):
+    worst = 0.0
     head = mmser_b200.FusionHead(C).to(dev); head.load_group_state(w); head.train()
     dp = DataParallelHead(head)
     dp.reducer.overlap = overlap            # False: every bucket all-reduced after the backward pass
