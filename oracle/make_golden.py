@@ -341,6 +341,45 @@ def run_eval_case(name, B, C, seed, views=5):
     print(f"{name}: T={T:.4f} preds={preds[:8].tolist()}")
 
 
+def run_mixed_dims_case(name, B, Ta, Tt, audio_dim, text_dim, seed):
+    """CrossModalAttention(audio_dim != text_dim) and FusionLayer(2 audio_dim != 2 text_dim) of the reference
+    (src/models/cross_attention.py:7-53, fusion.py:6-25), eval mode, with key-padding masks: outputs and the gradients
+    of a fixed linear objective with respect to inputs and every parameter."""
+    ca = load_ref("cross_attention"); fu = load_ref("fusion")
+    wc = synth.cross_weights(audio_dim=audio_dim, text_dim=text_dim)
+    wf = synth.fusion_weights(audio_dim=2 * audio_dim, text_dim=2 * text_dim)
+    cross = ca.CrossModalAttention(audio_dim, text_dim, shared_dim=256, num_heads=8).eval()
+    fusion = fu.FusionLayer(2 * audio_dim, 2 * text_dim, 512).eval()
+    assert not cross.load_state_dict(wc, strict=True).missing_keys
+    assert not fusion.load_state_dict(wf, strict=True).missing_keys
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(B, Ta, audio_dim, generator=g)
+    t = torch.randn(B, Tt, text_dim, generator=g)
+    la = torch.randint((Ta + 1) // 2, Ta + 1, (B,), generator=g)
+    lt = torch.randint(max(1, (Tt + 3) // 4), Tt + 1, (B,), generator=g)
+    am = (torch.arange(Ta)[None] < la[:, None]).float()
+    tm = (torch.arange(Tt)[None] < lt[:, None]).float()
+    a = (a * am[..., None]).requires_grad_(True)
+    t = (t * tm[..., None]).requires_grad_(True)
+    av = torch.randn(B, 2 * audio_dim, generator=g).requires_grad_(True)
+    tv = torch.randn(B, 2 * text_dim, generator=g).requires_grad_(True)
+    ua, ut, up = torch.randn(B, Ta, audio_dim, generator=g), torch.randn(B, Tt, text_dim, generator=g), torch.randn(B, 512, generator=g)
+    ea, et = cross(a, t, am, tm)
+    fused = fusion(av, tv)
+    ((ea * ua).sum() + (et * ut).sum() + (fused * up).sum()).backward()
+    gold = {"config": dict(B=B, Ta=Ta, Tt=Tt, audio_dim=audio_dim, text_dim=text_dim, seed=seed),
+            "inputs": {"a": a.detach().clone(), "t": t.detach().clone(), "a_mask": am, "t_mask": tm, "av": av.detach().clone(),
+                       "tv": tv.detach().clone(), "ua": ua, "ut": ut, "up": up},
+            "audio_enh": ea.detach().clone(), "text_enh": et.detach().clone(), "fused": fused.detach().clone(),
+            "din": {"a": a.grad.clone(), "t": t.grad.clone(), "av": av.grad.clone(), "tv": tv.grad.clone()},
+            "grads": {}}
+    for grp, mod in (("cross", cross), ("fusion", fusion)):
+        for n, p in mod.named_parameters():
+            gold["grads"][f"{grp}/{n}"] = summarize(p.grad, f"{grp}/{n}")
+    torch.save(gold, os.path.join(OUT, f"{name}.pt"))
+    print(f"{name}: |audio_enh|={ea.norm().item():.4f} |text_enh|={et.norm().item():.4f} |fused|={fused.norm().item():.4f}")
+
+
 def load_eval_helpers():
     """temperature_scaling + find_optimal_temperature from src/eval.py:43-67, extracted without importing the
     script's heavy dependencies."""
@@ -367,3 +406,4 @@ if __name__ == "__main__":
     run_feature_fusion_case("feature_fusion_combined", "combined_fusion", F=20, B=3, T=13, hid=128, seed=1243)
     run_late_ood_case("late_ood_small", B=37, C=6, D=64, seed=1245)
     run_feature_fusion_case("feature_fusion_asr", "asr_fusion", F=8, B=2, T=7, hid=128, seed=1244)
+    run_mixed_dims_case("mixed_dims_small", B=3, Ta=21, Tt=9, audio_dim=768, text_dim=1024, seed=1246)

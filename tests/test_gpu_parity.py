@@ -367,6 +367,41 @@ def test_against_reference_golden(name, golden_dir):
     assert checked > 300
 
 
+def test_mixed_dims_against_reference_golden(golden_dir):
+    """CrossModalAttention(768, 1024) and FusionLayer(1536, 2048, 512) -- unequal audio / text widths -- against the
+    fixture produced by the reference's own modules (oracle/make_golden.py run_mixed_dims_case), fp32 tier."""
+    from mmser_b200 import models as M
+    from oracle import synth
+    dev = _dev()
+    gold = torch.load(os.path.join(golden_dir, "mixed_dims_small.pt"), weights_only=False)
+    cfg, ins = gold["config"], gold["inputs"]
+    cross = M.CrossModalAttention(cfg["audio_dim"], cfg["text_dim"], dropout=0.0).to(dev)
+    cross.load_state_dict(synth.cross_weights(audio_dim=cfg["audio_dim"], text_dim=cfg["text_dim"]))
+    fusion = M.FusionLayer(2 * cfg["audio_dim"], 2 * cfg["text_dim"], 512).to(dev)
+    fusion.load_state_dict(synth.fusion_weights(audio_dim=2 * cfg["audio_dim"], text_dim=2 * cfg["text_dim"]))
+    cross.eval(); fusion.eval()
+    x = {k: ins[k].to(dev).requires_grad_(True) for k in ("a", "t", "av", "tv")}
+    ea, et = cross(x["a"], x["t"], ins["a_mask"].to(dev), ins["t_mask"].to(dev))
+    fused = fusion(x["av"], x["tv"])
+    ((ea * ins["ua"].to(dev)).sum() + (et * ins["ut"].to(dev)).sum() + (fused * ins["up"].to(dev)).sum()).backward()
+    rel = lambda g, r: (g.detach().double().cpu() - r.double()).abs().max().item() / (r.double().abs().max().item() + 1e-12)  # noqa: E731
+    assert rel(ea, gold["audio_enh"]) < 1e-4 and rel(et, gold["text_enh"]) < 1e-4 and rel(fused, gold["fused"]) < 1e-4
+    for k in ("a", "t", "av", "tv"):
+        assert rel(x[k].grad, gold["din"][k]) < 1e-4, k
+    checked = 0
+    for grp, mod in (("cross", cross), ("fusion", fusion)):
+        for n, p in mod.named_parameters():
+            summ = gold["grads"][f"{grp}/{n}"]
+            if summ["norm"] < 1e-6:           # mathematically zero (MHA key bias: softmax shift invariance)
+                assert p.grad.double().norm().item() < 1e-4, n
+                continue
+            assert abs(p.grad.double().norm().item() - summ["norm"]) <= 2e-3 * summ["norm"], n
+            if "full" in summ:
+                assert rel(p.grad, summ["full"]) < 1e-3, n
+            checked += 1
+    assert checked >= 40
+
+
 @pytest.mark.parametrize("name", ["feature_fusion_combined", "feature_fusion_asr"])
 def test_feature_fusion_against_reference_golden(name, golden_dir):
     """SURVEY 8(f) rank 1 against the fixture produced by the reference's own nn.Sequential, called the way the

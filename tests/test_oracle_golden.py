@@ -74,6 +74,26 @@ def test_oracle_matches_reference_train(case, golden_dir):
     assert _check_grads(gold, weights) > 300
 
 
+def test_oracle_matches_reference_mixed_dims(golden_dir):
+    """CrossModalAttention(768, 1024) / FusionLayer(1536, 2048, 512) of the reference (unequal audio / text widths:
+    cross_attention.py:7-30, fusion.py:6-16) against the oracle's restatement on the fixture's own inputs."""
+    gold = torch.load(os.path.join(golden_dir, "mixed_dims_small.pt"), weights_only=False)
+    cfg, ins = gold["config"], gold["inputs"]
+    weights = {"cross": synth.cross_weights(audio_dim=cfg["audio_dim"], text_dim=cfg["text_dim"]),
+               "fusion": synth.fusion_weights(audio_dim=2 * cfg["audio_dim"], text_dim=2 * cfg["text_dim"])}
+    for grp in weights.values():
+        for v in grp.values():
+            v.requires_grad_(True)
+    x = {k: ins[k].clone().requires_grad_(True) for k in ("a", "t", "av", "tv")}
+    ea, et = O.cross_attention(x["a"], x["t"], ins["a_mask"], ins["t_mask"], weights["cross"])
+    fused = O.fusion(x["av"], x["tv"], weights["fusion"])
+    ((ea * ins["ua"]).sum() + (et * ins["ut"]).sum() + (fused * ins["up"]).sum()).backward()
+    assert rel(ea, gold["audio_enh"]) < TOL and rel(et, gold["text_enh"]) < TOL and rel(fused, gold["fused"]) < TOL
+    for k in ("a", "t", "av", "tv"):
+        assert rel(x[k].grad, gold["din"][k]) < 10 * TOL, k
+    assert _check_grads(gold, weights) >= 40
+
+
 def test_oracle_matches_reference_train_dropout(golden_dir):
     """Training mode with every dropout ACTIVE: the fixture holds the keep masks the reference drew (recorded through a
     patched torch.nn.functional.dropout, oracle/make_golden.py); the oracle, given the same masks at its named sites,
