@@ -12,6 +12,7 @@
 // q|k|v projection buffers (row stride 768), so there is no head transpose anywhere.
 #include "kernels.cuh"
 #include "prof.cuh"
+#include <stdlib.h>
 
 namespace ser {
 
@@ -475,6 +476,266 @@ attn_tc_bwd_dkv_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// backward, fused (dQ, dK and dV of one (sample, head) in one CTA) for SMALL problems: Tq, Tk <= 256.
+// At the cfg2 shapes (250 x 64 and 64 x 250 per head) the two kernels above each load Q / K / V / dO, recompute the
+// scores, the exponentials and the dropout decisions; here that happens once.  Orientation as in the dK/dV kernel:
+// every warp owns 16 keys of the current 64-key tile and walks the query tiles, S^T = K Q^T, dP^T = V dO^T, dK / dV
+// accumulate in registers.  dQ needs the other orientation: the packed dS^T fragments are transposed 8 x 8 block by
+// block in registers (movmatrix) into the A operand of dQ_part[64 q x 32] = dS[q x own 16 keys] K_own; the four warps'
+// partial products (different keys, same queries) go to one shared-memory slab each and are summed by fixed owner
+// threads (no atomics: fp32 shared-memory atomics are compare-and-swap loops) -- straight to global memory when
+// there is one key tile, into an fp32 dQ buffer [Tq, 32] otherwise.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int FQ = 256;                                  // queries (and keys) per head the fused kernel accepts
+constexpr int SLD = 40;                                  // slab row pitch in floats (conflict-free 8-byte stores)
+// shared memory: K, V tiles | Q, dO tiles (double buffered when there are several query tiles) | lse, delta | slabs | dQ
+static size_t fused_smem_bytes(int Tq, int Tk) {
+  const int nqt = (Tq + TILE - 1) / TILE, nkt = (Tk + ROWS - 1) / ROWS;
+  const size_t tiles = static_cast<size_t>(2 * ROWS * LDS + (nqt > 1 ? 4 : 2) * TILE * LDS) * 2;
+  return tiles + 2 * static_cast<size_t>(nqt) * TILE * 4 + 4 * TILE * SLD * 4 + (nkt > 1 ? static_cast<size_t>(nqt) * TILE * DH * 4 : 0);
+}
+
+__device__ __forceinline__ uint32_t movmatrix_t(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+
+template <bool DROP>
+__global__ void __launch_bounds__(NT, 3)
+attn_tc_bwd_fused_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* __restrict__ K, long long ldk,
+                         const bf16* __restrict__ V, long long ldv, const float* __restrict__ kmask,
+                         const bf16* __restrict__ O, long long ldo, const bf16* __restrict__ dO, long long lddo,
+                         const float* __restrict__ lse, float* __restrict__ delta, bf16* __restrict__ dQ, long long lddq,
+                         bf16* __restrict__ dK, long long lddk, bf16* __restrict__ dV, long long lddv, int H, int Tq,
+                         int Tk, float scale, DropSpec drop) {
+  pdl_sync();
+  extern __shared__ __align__(16) unsigned char fsm[];
+  bf16* sK = reinterpret_cast<bf16*>(fsm);
+  bf16* sV = sK + ROWS * LDS;
+  const int nqt = (Tq + TILE - 1) / TILE, nkt = (Tk + ROWS - 1) / ROWS;
+  const int nbuf = nqt > 1 ? 2 : 1;
+  bf16* sQ = sV + ROWS * LDS;                            // [nbuf][TILE * LDS]
+  bf16* sG = sQ + nbuf * TILE * LDS;                     // [nbuf][TILE * LDS]
+  float* sLse = reinterpret_cast<float*>(sG + nbuf * TILE * LDS);   // [nqt * TILE] log2 units; +inf beyond Tq -> P = 0
+  float* sDel = sLse + nqt * TILE;                       // [nqt * TILE]
+  float* sSlab = sDel + nqt * TILE;                      // [4 warps][TILE][SLD]: one warp's dQ partial of a query tile
+  float* sDQ = sSlab + 4 * TILE * SLD;                   // [nqt * TILE][DH] fp32, only with several key tiles
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float c = scale * kLog2e;
+  const int orow = threadIdx.x >> 1, ocol = (threadIdx.x & 1) * 16;   // owner of 16 dQ columns of one query row per tile
+  const bf16* Qb = Q + static_cast<size_t>(b) * Tq * ldq + h * DH;
+  const bf16* Gb = dO + static_cast<size_t>(b) * Tq * lddo + h * DH;
+  const bf16* Ob = O + static_cast<size_t>(b) * Tq * ldo + h * DH;
+  const size_t bh_q = (static_cast<size_t>(b) * H + h) * Tq;
+
+  // ---- per-query constants and the zeroed dQ accumulator
+  if (nkt > 1)
+    for (int i = threadIdx.x; i < nqt * TILE * DH; i += NT) sDQ[i] = 0.f;
+  for (int q_base = 0; q_base < nqt * TILE; q_base += TILE) {
+    // delta[q] = sum_d dO[q,d] * O[q,d]: two threads per query, 16 columns each
+    const int r = q_base + (threadIdx.x >> 1), half = threadIdx.x & 1;
+    float acc = 0.f;
+    if (r < Tq) {
+      float g[8], ov[8];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        load8(Gb + static_cast<size_t>(r) * lddo + half * 16 + i * 8, g);
+        load8(Ob + static_cast<size_t>(r) * ldo + half * 16 + i * 8, ov);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(g[k], ov[k], acc);
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (half == 0) {
+      sDel[r] = (r < Tq) ? acc : 0.f;
+      sLse[r] = (r < Tq) ? lse[bh_q + r] * kLog2e : INFINITY;
+      if (r < Tq) delta[bh_q + r] = acc;
+    }
+  }
+  auto stage_q = [&](int t, int buf) {
+    const int q0 = t * TILE, rows = min(TILE, Tq - q0);
+    stage_rows_async(Qb + static_cast<size_t>(q0) * ldq, ldq, rows, sQ + buf * TILE * LDS);
+    stage_rows_async(Gb + static_cast<size_t>(q0) * lddo, lddo, rows, sG + buf * TILE * LDS);
+    cp_async_commit();
+  };
+  DropKey dkey{0u, 1u};
+  unsigned half_tk = 0u, dq0 = 0u;
+  if (DROP) {
+    dkey = drop_key(drop);
+    half_tk = static_cast<unsigned>((Tk + 1) / 2);
+    dq0 = (static_cast<unsigned>(b) * H + h) * Tq + 2 * (lane & 3);
+  }
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int k0 = kt * ROWS, krows = min(ROWS, Tk - k0);
+    __syncthreads();                  // the previous key tile (and its last query tile) is no longer read; sDQ / sLse written
+    stage_rows_async(K + (static_cast<size_t>(b) * Tk + k0) * ldk + h * DH, ldk, krows, sK);
+    stage_rows_async(V + (static_cast<size_t>(b) * Tk + k0) * ldv + h * DH, ldv, krows, sV);
+    stage_q(0, 0);
+    float kb[2];                      // 0 / -inf per owned key row
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int kj = k0 + warp * 16 + (lane >> 2) + 8 * r;
+      const bool ok = kj < Tk && (kmask == nullptr || kmask[static_cast<size_t>(b) * Tk + kj] != 0.f);
+      kb[r] = ok ? 0.f : -INFINITY;
+    }
+    // dropout: element (query q, key kj) -> pair (row(q) * ceil(Tk/2) + kj / 2), half kj & 1 (kj, kj + 8: same parity)
+    unsigned dcol[2] = {0u, 0u}, dhalf = 0u;
+    if (DROP) {
+      const unsigned kj0 = static_cast<unsigned>(k0 + warp * 16 + (lane >> 2));
+      dcol[0] = kj0 >> 1; dcol[1] = (kj0 + 8) >> 1; dhalf = kj0 & 1u;
+    }
+    uint32_t ka[2][4], va[2][4], kbf[2][4];
+    float dk[4][4], dv[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { dk[j][i] = 0.f; dv[j][i] = 0.f; }
+
+    for (int t = 0; t < nqt; ++t) {
+      const int buf = t & (nbuf - 1);
+      const bf16* tQ = sQ + buf * TILE * LDS;
+      const bf16* tG = sG + buf * TILE * LDS;
+      cp_async_wait_all();
+      __syncthreads();
+      if (t + 1 < nqt) stage_q(t + 1, buf ^ 1);          // (nqt > 1 => two buffers)
+      if (t == 0) {
+        load_a_frags(sK, warp * 16, lane, ka);
+        load_a_frags(sV, warp * 16, lane, va);
+        // B operand of the dQ product: K_own [k = own 16 keys][n = d], n-tiles (2 jj, 2 jj + 1) per ldmatrix
+        const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj)
+          ldsm_x4_t(smem_addr(sK + r * LDS + 16 * jj + (lane >> 4) * 8), kbf[jj][0], kbf[jj][1], kbf[jj][2], kbf[jj][3]);
+      }
+      float s[8][4], dp[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { s[j][i] = 0.f; dp[j][i] = 0.f; }
+      mma_nt(ka, tQ, lane, s);                    // [keys x queries]
+      mma_nt(va, tG, lane, dp);
+      uint32_t pt[4][4], dst[4][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int qc = t * TILE + 8 * j + 2 * (lane & 3);
+        const float2 ql = *reinterpret_cast<const float2*>(&sLse[qc]);
+        const float2 qd = *reinterpret_cast<const float2*>(&sDel[qc]);
+        const float p0 = exp2f(s[j][0] * c + kb[0] - ql.x), p1 = exp2f(s[j][1] * c + kb[0] - ql.y);
+        const float p2 = exp2f(s[j][2] * c + kb[1] - ql.x), p3 = exp2f(s[j][3] * c + kb[1] - ql.y);
+        float w0 = p0, w1 = p1, w2 = p2, w3 = p3;      // dropped weights feed dV; dP is masked the same way
+        if (DROP) {
+          // one hash decides a PAIR of neighbouring keys; the lane that owns the other key of the pair (lane ^ 4: same
+          // queries, key ^ 1) needs the same four hashes -- each of the two computes two and they swap
+          const unsigned qa = (dq0 + t * TILE + 8 * j) * half_tk, qb = qa + half_tk;   // queries q, q + 1
+          const unsigned sel = dhalf ? dcol[1] : dcol[0];
+          const unsigned ha = drop_bits(dkey, qa + sel), hb = drop_bits(dkey, qb + sel);
+          const unsigned oa = __shfl_xor_sync(0xffffffffu, ha, 4), ob = __shfl_xor_sync(0xffffffffu, hb, 4);
+          const unsigned sh = dhalf ? 16u : 0u;
+          const float m0 = ((((dhalf ? oa : ha) >> sh) & 0xffffu) >= drop.thr) ? drop.scale : 0.f;   // (q,     keys dcol[0])
+          const float m1 = ((((dhalf ? ob : hb) >> sh) & 0xffffu) >= drop.thr) ? drop.scale : 0.f;   // (q + 1, keys dcol[0])
+          const float m2 = ((((dhalf ? ha : oa) >> sh) & 0xffffu) >= drop.thr) ? drop.scale : 0.f;   // (q,     keys dcol[1])
+          const float m3 = ((((dhalf ? hb : ob) >> sh) & 0xffffu) >= drop.thr) ? drop.scale : 0.f;   // (q + 1, keys dcol[1])
+          w0 *= m0; w1 *= m1; w2 *= m2; w3 *= m3;
+          dp[j][0] *= m0; dp[j][1] *= m1; dp[j][2] *= m2; dp[j][3] *= m3;
+        }
+        pt[j >> 1][(j & 1) * 2] = pack_bf16(w0, w1);
+        pt[j >> 1][(j & 1) * 2 + 1] = pack_bf16(w2, w3);
+        dst[j >> 1][(j & 1) * 2] = pack_bf16(p0 * (dp[j][0] - qd.x), p1 * (dp[j][1] - qd.y));
+        dst[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2 * (dp[j][2] - qd.x), p3 * (dp[j][3] - qd.y));
+      }
+      mma_nn(pt, tG, lane, dv);                   // dV += P^T dO
+      mma_nn(dst, tQ, lane, dk);                  // dK += dS^T Q
+      // dQ_part[16 queries of m-tile mt][32] = dS[q x own 16 keys] K_own: register dst[mt][(jh) * 2 + r] is the 8 x 8
+      // block (keys 8 r.., queries 16 mt + 8 jh..); its transpose is the (queries, keys) block of the A operand
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        uint32_t a[4];
+        a[0] = movmatrix_t(dst[mt][0]);           // queries 0-7,  keys 0-7
+        a[1] = movmatrix_t(dst[mt][2]);           // queries 8-15, keys 0-7
+        a[2] = movmatrix_t(dst[mt][1]);           // queries 0-7,  keys 8-15
+        a[3] = movmatrix_t(dst[mt][3]);           // queries 8-15, keys 8-15
+        float acc[4][4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          mma16816(acc[2 * jj], a, kbf[jj][0], kbf[jj][1]);
+          mma16816(acc[2 * jj + 1], a, kbf[jj][2], kbf[jj][3]);
+        }
+        float* row0 = sSlab + (warp * TILE + 16 * mt + (lane >> 2)) * SLD + 2 * (lane & 3);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          *reinterpret_cast<float2*>(row0 + 8 * n) = make_float2(acc[n][0], acc[n][1]);
+          *reinterpret_cast<float2*>(row0 + 8 * SLD + 8 * n) = make_float2(acc[n][2], acc[n][3]);
+        }
+      }
+      __syncthreads();                            // the four slabs of this query tile are complete
+      {
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float4* src = reinterpret_cast<const float4*>(sSlab + (w * TILE + orow) * SLD + ocol);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 x = src[k];
+            v[4 * k] += x.x; v[4 * k + 1] += x.y; v[4 * k + 2] += x.z; v[4 * k + 3] += x.w;
+          }
+        }
+        const int q = t * TILE + orow;
+        if (nkt > 1) {                            // owner threads accumulate over the key tiles (no other thread touches these)
+#pragma unroll
+          for (int k = 0; k < 16; ++k) sDQ[q * DH + ocol + k] += v[k];
+        } else if (q < Tq) {
+          float o8[8];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o8[k] = v[8 * hh + k] * scale;
+            store8(dQ + (static_cast<size_t>(b) * Tq + q) * lddq + h * DH + ocol + 8 * hh, o8);
+          }
+        }
+      }
+      // (the next iteration's barrier -- or the key-tile loop's -- keeps the slabs until every owner has read them)
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int kj = k0 + warp * 16 + (lane >> 2) + 8 * r;
+      if (kj < Tk) {
+        const size_t row = static_cast<size_t>(b) * Tk + kj;
+        bf16* pk = dK + row * lddk + h * DH + 2 * (lane & 3);
+        bf16* pv = dV + row * lddv + h * DH + 2 * (lane & 3);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          *reinterpret_cast<uint32_t*>(pk + 8 * j) = pack_bf16(dk[j][2 * r] * scale, dk[j][2 * r + 1] * scale);
+          *reinterpret_cast<uint32_t*>(pv + 8 * j) = pack_bf16(dv[j][2 * r], dv[j][2 * r + 1]);
+        }
+      }
+    }
+  }
+  if (nkt > 1) {                                  // dQ = scale * sum over the key tiles, written by the owner threads
+    for (int t = 0; t < nqt; ++t) {
+      const int q = t * TILE + orow;
+      if (q >= Tq) break;
+      float o8[8];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o8[k] = sDQ[q * DH + ocol + 8 * hh + k] * scale;
+        store8(dQ + (static_cast<size_t>(b) * Tq + q) * lddq + h * DH + ocol + 8 * hh, o8);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 int attention_fwd_tc(const AttnArgs& a, cudaStream_t s) {
@@ -494,6 +755,27 @@ int attention_bwd_tc(const AttnArgs& a, cudaStream_t s) {
   const double fl = 10.0 * a.B * a.H * static_cast<double>(a.Tq) * a.Tk * a.dh;
   const double by = 2.0 * static_cast<double>(a.B) * a.H * a.dh * (4.0 * a.Tq + 4.0 * a.Tk);
   ProfScope prof("attention_bwd", fl, by, s);
+  // small problems (both sequence lengths of a head fit the fused kernel's shared-memory dQ buffer): one kernel
+  // instead of dQ + dK/dV -- operands, scores, exponentials and dropout decisions are produced once.  SER_ATTN_BWD_FUSED=0
+  // keeps the two-kernel path (A/B switch).
+  static const bool fused_on = !(getenv("SER_ATTN_BWD_FUSED") != nullptr && atoi(getenv("SER_ATTN_BWD_FUSED")) == 0);
+  if (fused_on && a.Tq <= FQ && a.Tk <= FQ && a.B <= 65535) {
+    static bool configured = false;
+    if (!configured) {
+      const int most = static_cast<int>(fused_smem_bytes(FQ, FQ));
+      SER_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+      SER_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+      configured = true;
+    }
+    auto* kf = a.drop.on() ? attn_tc_bwd_fused_kernel<true> : attn_tc_bwd_fused_kernel<false>;
+    SER_CUDA_CHECK(launch_pdl(kf, dim3(a.H, a.B), dim3(NT), fused_smem_bytes(a.Tq, a.Tk), s, reinterpret_cast<const bf16*>(a.Q), a.ldq,
+        reinterpret_cast<const bf16*>(a.K), a.ldk, reinterpret_cast<const bf16*>(a.V), a.ldv, a.kmask,
+        reinterpret_cast<const bf16*>(a.O), a.ldo, reinterpret_cast<const bf16*>(a.dO), a.lddo, a.lse, a.delta,
+        reinterpret_cast<bf16*>(a.dQ), a.lddq, reinterpret_cast<bf16*>(a.dK), a.lddk, reinterpret_cast<bf16*>(a.dV), a.lddv,
+        a.H, a.Tq, a.Tk, a.scale, a.drop));
+    SER_LAUNCH_CHECK();
+    return SER_OK;
+  }
   dim3 gq(ceil_div(a.Tq, ROWS), a.H, a.B);
   auto* kdq = a.drop.on() ? attn_tc_bwd_dq_kernel<true> : attn_tc_bwd_dq_kernel<false>;
   SER_CUDA_CHECK(launch_pdl(kdq, dim3(gq), dim3(NT), 0, s, reinterpret_cast<const bf16*>(a.Q), a.ldq, reinterpret_cast<const bf16*>(a.K), a.ldk,

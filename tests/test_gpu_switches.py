@@ -50,6 +50,11 @@ def test_switches_do_not_change_results(shape):
     got = _run({"SER_ATTN_KEEPBITS": "0"}, *args)
     for k in ref:
         assert _close(got[k], ref[k], 2e-3), ("keepbits", k, got[k], ref[k])
+    # fused attention backward (one kernel per small problem) vs the dQ + dK/dV pair: the same arithmetic per element,
+    # dQ summed over the keys in another order (bf16 last places)
+    got = _run({"SER_ATTN_BWD_FUSED": "0"}, *args)
+    for k in ref:
+        assert _close(got[k], ref[k], 2e-3), ("fused attention backward", k, got[k], ref[k])
     # tcgen05 vs mma.sync attention kernels: two implementations of the same maths in bf16 -- forward quantities agree at
     # the bf16 tolerance; gradients only at the bf16 floor of this head (ReLU-gate flips)
     got = _run({"SER_ATTN_FWD": "1", "SER_ATTN_BWD": "1"}, *args)
