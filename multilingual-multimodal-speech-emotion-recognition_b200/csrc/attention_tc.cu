@@ -573,9 +573,11 @@ attn_tc_bwd_fused_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* 
   for (int kt = 0; kt < nkt; ++kt) {
     const int k0 = kt * ROWS, krows = min(ROWS, Tk - k0);
     __syncthreads();                  // the previous key tile (and its last query tile) is no longer read; sDQ / sLse written
-    stage_rows_async(K + (static_cast<size_t>(b) * Tk + k0) * ldk + h * DH, ldk, krows, sK);
-    stage_rows_async(V + (static_cast<size_t>(b) * Tk + k0) * ldv + h * DH, ldv, krows, sV);
-    stage_q(0, 0);
+    if (kt == 0) {                    // (later key tiles were requested while the previous one was being used, below)
+      stage_rows_async(K + (static_cast<size_t>(b) * Tk + k0) * ldk + h * DH, ldk, krows, sK);
+      stage_rows_async(V + (static_cast<size_t>(b) * Tk + k0) * ldv + h * DH, ldv, krows, sV);
+    }
+    if (kt == 0 || nqt > 1) stage_q(0, 0);      // a single query tile stays in its buffer for all key tiles
     float kb[2];                      // 0 / -inf per owned key row
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -611,6 +613,15 @@ attn_tc_bwd_fused_kernel(const bf16* __restrict__ Q, long long ldq, const bf16* 
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj)
           ldsm_x4_t(smem_addr(sK + r * LDS + 16 * jj + (lane >> 4) * 8), kbf[jj][0], kbf[jj][1], kbf[jj][2], kbf[jj][3]);
+        // K / V now live in registers (ka, va, kbf): once every warp has its fragments, the NEXT key tile travels into
+        // the same buffers while this one is being used
+        if (kt + 1 < nkt) {
+          __syncthreads();
+          const int k1 = k0 + ROWS, rows1 = min(ROWS, Tk - k1);
+          stage_rows_async(K + (static_cast<size_t>(b) * Tk + k1) * ldk + h * DH, ldk, rows1, sK);
+          stage_rows_async(V + (static_cast<size_t>(b) * Tk + k1) * ldv + h * DH, ldv, rows1, sV);
+          cp_async_commit();
+        }
       }
       float s[8][4], dp[8][4];
 #pragma unroll
